@@ -1,0 +1,384 @@
+// api.cu — extern "C" entry points of include/gtars_gpu.h: context, memory, and the host-buffer wrappers
+// (H2D → kernels → D2H) around the device-resident launches in kernels.cu.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace gtgpu {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int32_t fail(int32_t code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+}  // namespace gtgpu
+
+using namespace gtgpu;
+
+// ---- ctx members ---------------------------------------------------------------------------------------------------
+int32_t gtgpu_ctx::scratch_get(int role, size_t bytes, void** out) {
+    if (scratch.size() < (size_t)SC_N_ROLES) scratch.resize(SC_N_ROLES);
+    DevBuffer& b = scratch[role];
+    bytes = std::max<size_t>(bytes, 256);
+    if (b.cap < bytes) {
+        if (b.ptr) cudaFree(b.ptr);
+        b.ptr = nullptr;
+        b.cap = 0;
+        size_t want = bytes + bytes / 16;  // a little slack so slowly growing batches do not realloc every call
+        cudaError_t e = cudaMalloc(&b.ptr, want);
+        if (e != cudaSuccess) {
+            want = bytes;
+            e = cudaMalloc(&b.ptr, want);
+        }
+        if (e != cudaSuccess)
+            return fail(GTGPU_ERR_NOMEM, "cudaMalloc(" + std::to_string(bytes) + " B): " + cudaGetErrorString(e));
+        b.cap = want;
+    }
+    *out = b.ptr;
+    return GTGPU_OK;
+}
+
+int32_t gtgpu_ctx::pinned_get(size_t bytes, PinnedBlock* out) {
+    bytes = std::max<size_t>(bytes, 64);
+    int best = -1;
+    for (size_t i = 0; i < pinned_free.size(); ++i)
+        if (pinned_free[i].cap >= bytes && (best < 0 || pinned_free[i].cap < pinned_free[best].cap)) best = (int)i;
+    if (best >= 0) {
+        *out = pinned_free[best];
+        pinned_free.erase(pinned_free.begin() + best);
+        return GTGPU_OK;
+    }
+    PinnedBlock b;
+    cudaError_t e = cudaHostAlloc(&b.ptr, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        // free the cache and retry once
+        for (auto& f : pinned_free) cudaFreeHost(f.ptr);
+        pinned_free.clear();
+        e = cudaHostAlloc(&b.ptr, bytes, cudaHostAllocDefault);
+    }
+    if (e != cudaSuccess)
+        return fail(GTGPU_ERR_NOMEM, "cudaHostAlloc(" + std::to_string(bytes) + " B): " + cudaGetErrorString(e));
+    b.cap = bytes;
+    *out = b;
+    return GTGPU_OK;
+}
+
+void gtgpu_ctx::pinned_put(PinnedBlock b) {
+    if (!b.ptr) return;
+    pinned_free.push_back(b);
+    // keep at most 8 blocks; drop the smallest first
+    while (pinned_free.size() > 8) {
+        size_t k = 0;
+        for (size_t i = 1; i < pinned_free.size(); ++i)
+            if (pinned_free[i].cap < pinned_free[k].cap) k = i;
+        cudaFreeHost(pinned_free[k].ptr);
+        pinned_free.erase(pinned_free.begin() + k);
+    }
+}
+
+extern "C" {
+
+const char* gtgpu_last_error(void) { return g_last_error.c_str(); }
+const char* gtgpu_version(void) { return "gtars-b200 0.1 (sm_100a)"; }
+
+int32_t gtgpu_device_count(int32_t* out_n) {
+    if (!out_n) return fail(GTGPU_ERR_INVALID, "device_count: null argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *out_n = 0;
+        return fail(GTGPU_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *out_n = n;
+    return GTGPU_OK;
+}
+
+int32_t gtgpu_init(int32_t device, void* stream_or_null, gtgpu_ctx** out_ctx) {
+    if (!out_ctx) return fail(GTGPU_ERR_INVALID, "init: null argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(GTGPU_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") +
+                                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= n) return fail(GTGPU_ERR_INVALID, "init: device index out of range");
+    GT_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(GTGPU_ERR_UNSUPPORTED, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                               "; this library is built for sm_100a only");
+    gtgpu_ctx* ctx = new gtgpu_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream_or_null) {
+        ctx->stream = (cudaStream_t)stream_or_null;
+    } else {
+        GT_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    GT_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    GT_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    GT_CUDA(cudaHostAlloc((void**)&ctx->h_scalars, 64 * sizeof(uint64_t), cudaHostAllocDefault));
+    *out_ctx = ctx;
+    return GTGPU_OK;
+}
+
+int32_t gtgpu_shutdown(gtgpu_ctx* ctx) {
+    if (!ctx) return GTGPU_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->scratch)
+        if (b.ptr) cudaFree(b.ptr);
+    for (auto& b : ctx->pinned_free) cudaFreeHost(b.ptr);
+    if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_in);
+    cudaStreamDestroy(ctx->copy_out);
+    delete ctx;
+    return GTGPU_OK;
+}
+
+int32_t gtgpu_synchronize(gtgpu_ctx* ctx) {
+    if (!ctx) return fail(GTGPU_ERR_INVALID, "synchronize: null ctx");
+    GT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GTGPU_OK;
+}
+
+int32_t gtgpu_launch_count(gtgpu_ctx* ctx, uint64_t* out_n) {
+    if (!ctx || !out_n) return fail(GTGPU_ERR_INVALID, "launch_count: null argument");
+    *out_n = ctx->launches;
+    return GTGPU_OK;
+}
+
+int32_t gtgpu_host_alloc(uint64_t bytes, void** out_ptr) {
+    if (!out_ptr) return fail(GTGPU_ERR_INVALID, "host_alloc: null argument");
+    cudaError_t e = cudaHostAlloc(out_ptr, std::max<uint64_t>(bytes, 64), cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(GTGPU_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    return GTGPU_OK;
+}
+
+int32_t gtgpu_host_free(void* ptr) {
+    if (ptr) GT_CUDA(cudaFreeHost(ptr));
+    return GTGPU_OK;
+}
+
+const void* gtgpu_buf_data(const gtgpu_buf* buf) { return buf ? buf->block.ptr : nullptr; }
+uint64_t gtgpu_buf_len(const gtgpu_buf* buf) { return buf ? buf->len : 0; }
+int32_t gtgpu_buf_free(gtgpu_buf* buf) {
+    if (!buf) return GTGPU_OK;
+    {
+        std::lock_guard<std::mutex> lk(buf->ctx->mu);
+        buf->ctx->pinned_put(buf->block);
+    }
+    delete buf;
+    return GTGPU_OK;
+}
+
+}  // extern "C"
+
+// ---- host-buffer wrappers ------------------------------------------------------------------------------------------
+namespace {
+
+struct DevQueries {
+    uint32_t *chr = nullptr, *start = nullptr, *end = nullptr;
+};
+
+int32_t upload_queries(gtgpu_ctx* ctx, uint64_t n, const uint32_t* chr, const uint32_t* start, const uint32_t* end,
+                       DevQueries* q) {
+    GT_TRY(ctx->scratch_get(SC_CHR, n * 4, (void**)&q->chr));
+    GT_TRY(ctx->scratch_get(SC_START, n * 4, (void**)&q->start));
+    GT_TRY(ctx->scratch_get(SC_END, n * 4, (void**)&q->end));
+    if (n) {
+        GT_CUDA(cudaMemcpyAsync(q->chr, chr, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        GT_CUDA(cudaMemcpyAsync(q->start, start, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        GT_CUDA(cudaMemcpyAsync(q->end, end, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return GTGPU_OK;
+}
+
+int32_t count_host(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start, const uint32_t* end,
+                   int32_t min_overlap, int mode, void* out, size_t elem) {
+    if (!ix || (n && (!chr || !start || !end || !out))) return fail(GTGPU_ERR_INVALID, "count: null argument");
+    if (mode == COUNT_BITS_RAW_U64 && ix->kind != GTGPU_KIND_BITS)
+        return fail(GTGPU_ERR_INVALID, "bits_count: index is not GTGPU_KIND_BITS");
+    gtgpu_ctx* ctx = ix->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    GT_CUDA(cudaSetDevice(ctx->device));
+    if (n == 0) return GTGPU_OK;
+    DevQueries q;
+    GT_TRY(upload_queries(ctx, n, chr, start, end, &q));
+    void* d_out = nullptr;
+    GT_TRY(ctx->scratch_get(SC_COUNTS, n * elem, &d_out));
+    GT_TRY(launch_count(ix, n, q.chr, q.start, q.end, min_overlap, mode, d_out));
+    GT_CUDA(cudaMemcpyAsync(out, d_out, n * elem, cudaMemcpyDeviceToHost, ctx->stream));
+    GT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GTGPU_OK;
+}
+
+// Shared body of gtgpu_find (per-query offsets, no files) and gtgpu_tokenize_files (per-file offsets + [unk]).
+int32_t find_host(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start, const uint32_t* end,
+                  int32_t min_overlap, uint64_t* out_offsets, bool files, uint64_t n_files,
+                  const uint64_t* file_offsets, uint32_t unk_id, uint64_t* out_file_tok, gtgpu_buf** out_ids) {
+    gtgpu_ctx* ctx = ix->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    GT_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+
+    DevQueries q;
+    GT_TRY(upload_queries(ctx, n, chr, start, end, &q));
+    uint64_t *d_file_offsets = nullptr, *d_raw_tok = nullptr, *d_out_tok = nullptr, *d_offsets = nullptr;
+    if (files) {
+        GT_TRY(ctx->scratch_get(SC_FILE_OFFS, (n_files + 1) * 8, (void**)&d_file_offsets));
+        GT_TRY(ctx->scratch_get(SC_FILE_TOK, (n_files + 1) * 8, (void**)&d_raw_tok));
+        GT_TRY(ctx->scratch_get(SC_FILE_TOK2, (n_files + 1) * 8, (void**)&d_out_tok));
+        GT_CUDA(cudaMemcpyAsync(d_file_offsets, file_offsets, (n_files + 1) * 8, cudaMemcpyHostToDevice, st));
+    } else {
+        GT_TRY(ctx->scratch_get(SC_OUT_OFFS, (n + 1) * 8, (void**)&d_offsets));
+    }
+    void* d_ws = nullptr;
+    GT_TRY(ctx->scratch_get(SC_TILE_STATUS, fused_workspace_bytes(n), &d_ws));
+    uint64_t* d_misc = nullptr;  // [0] total, [1] n_empty, [2] err flag (u32)
+    GT_TRY(ctx->scratch_get(SC_MISC, 64, (void**)&d_misc));
+
+    uint64_t cap = n + n / 4 + 1024;
+    uint64_t total = 0, n_empty = 0;
+    uint32_t* d_ids = nullptr;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        GT_TRY(ctx->scratch_get(SC_OUT_IDS, cap * 4, (void**)&d_ids));
+        GT_CUDA(cudaMemsetAsync(d_misc, 0, 64, st));
+        GT_TRY(launch_fused_find(ix, n, n_files, d_file_offsets, q.chr, q.start, q.end, min_overlap, d_ids, cap,
+                                 d_offsets, d_raw_tok, d_ws, nullptr, d_misc, (uint32_t*)(d_misc + 2)));
+        if (files) GT_TRY(launch_unk_offsets(ctx, n_files, d_raw_tok, d_out_tok, d_misc + 1));
+        GT_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_misc, 24, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+        total = ctx->h_scalars[0];
+        n_empty = ctx->h_scalars[1];
+        if ((uint32_t)ctx->h_scalars[2] != 0)
+            return fail(GTGPU_ERR_UNSUPPORTED, "find: more than 2^32 hits inside one 1024-query tile");
+        if (total <= cap) break;
+        if (attempt == 1) return fail(GTGPU_ERR_CAPACITY, "find: output capacity exceeded twice");
+        cap = total;  // exact re-run
+    }
+
+    const uint32_t* d_final = d_ids;
+    uint64_t final_total = total;
+    if (files && n_empty > 0) {
+        uint32_t* d_ids2 = nullptr;
+        final_total = total + n_empty;
+        GT_TRY(ctx->scratch_get(SC_OUT_IDS2, final_total * 4, (void**)&d_ids2));
+        GT_TRY(launch_unk_expand(ctx, n_files, d_raw_tok, d_out_tok, d_ids, unk_id, d_ids2));
+        d_final = d_ids2;
+    }
+
+    gtgpu_buf* buf = new gtgpu_buf();
+    buf->ctx = ctx;
+    buf->len = final_total;
+    int32_t s = ctx->pinned_get(final_total * 4, &buf->block);
+    if (s != GTGPU_OK) {
+        delete buf;
+        return s;
+    }
+    cudaError_t e = cudaSuccess;
+    if (final_total) e = cudaMemcpyAsync(buf->block.ptr, d_final, final_total * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && files)
+        e = cudaMemcpyAsync(out_file_tok, d_out_tok, (n_files + 1) * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && !files)
+        e = cudaMemcpyAsync(out_offsets, d_offsets, (n + 1) * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        ctx->pinned_put(buf->block);
+        delete buf;
+        return fail(GTGPU_ERR_CUDA, std::string("find: D2H: ") + cudaGetErrorString(e));
+    }
+    *out_ids = buf;
+    return GTGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t gtgpu_count(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start, const uint32_t* end,
+                    int32_t min_overlap, uint32_t* out_counts) {
+    return count_host(ix, n, chr, start, end, min_overlap, COUNT_U32, out_counts, 4);
+}
+
+int32_t gtgpu_bits_count(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start,
+                         const uint32_t* end, uint64_t* out_counts) {
+    return count_host(ix, n, chr, start, end, 0, COUNT_BITS_RAW_U64, out_counts, 8);
+}
+
+int32_t gtgpu_any(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start, const uint32_t* end,
+                  int32_t min_overlap, uint8_t* out_any) {
+    return count_host(ix, n, chr, start, end, min_overlap, COUNT_ANY_U8, out_any, 1);
+}
+
+int32_t gtgpu_find(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start, const uint32_t* end,
+                   int32_t min_overlap, uint64_t* out_offsets, gtgpu_buf** out_vals) {
+    if (!ix || !out_offsets || !out_vals || (n && (!chr || !start || !end)))
+        return fail(GTGPU_ERR_INVALID, "find: null argument");
+    return find_host(ix, n, chr, start, end, min_overlap, out_offsets, false, 0, nullptr, 0, nullptr, out_vals);
+}
+
+int32_t gtgpu_tokenize_files(gtgpu_index* ix, uint64_t n_files, const uint64_t* file_offsets, const uint32_t* chr,
+                             const uint32_t* start, const uint32_t* end, uint32_t unk_id,
+                             uint64_t* out_file_token_offsets, gtgpu_buf** out_ids) {
+    if (!ix || !file_offsets || !out_file_token_offsets || !out_ids)
+        return fail(GTGPU_ERR_INVALID, "tokenize_files: null argument");
+    if (file_offsets[0] != 0) return fail(GTGPU_ERR_INVALID, "tokenize_files: file_offsets[0] must be 0");
+    for (uint64_t f = 0; f < n_files; ++f)
+        if (file_offsets[f] > file_offsets[f + 1])
+            return fail(GTGPU_ERR_INVALID, "tokenize_files: file_offsets not monotone");
+    uint64_t n = file_offsets[n_files];
+    if (n && (!chr || !start || !end)) return fail(GTGPU_ERR_INVALID, "tokenize_files: null query arrays");
+    return find_host(ix, n, chr, start, end, 0, nullptr, true, n_files, file_offsets, unk_id, out_file_token_offsets,
+                     out_ids);
+}
+
+int32_t gtgpu_count_dev(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
+                        const uint32_t* d_end, int32_t min_overlap, uint32_t* d_out_counts) {
+    if (!ix || (n && (!d_chr || !d_start || !d_end || !d_out_counts)))
+        return fail(GTGPU_ERR_INVALID, "count_dev: null argument");
+    std::lock_guard<std::mutex> lk(ix->ctx->mu);
+    GT_CUDA(cudaSetDevice(ix->ctx->device));
+    return launch_count(ix, n, d_chr, d_start, d_end, min_overlap, COUNT_U32, d_out_counts);
+}
+
+int32_t gtgpu_find_dev(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
+                       const uint32_t* d_end, int32_t min_overlap, uint64_t n_files, const uint64_t* d_file_offsets,
+                       uint32_t* d_out_ids, uint64_t ids_capacity, uint64_t* d_out_offsets,
+                       uint64_t* d_out_file_token_offsets, uint64_t* d_out_total) {
+    if (!ix || !d_out_total || (n && (!d_chr || !d_start || !d_end)) || (ids_capacity && !d_out_ids))
+        return fail(GTGPU_ERR_INVALID, "find_dev: null argument");
+    if (d_out_file_token_offsets && !d_file_offsets)
+        return fail(GTGPU_ERR_INVALID, "find_dev: per-file offsets requested without d_file_offsets");
+    gtgpu_ctx* ctx = ix->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    GT_CUDA(cudaSetDevice(ctx->device));
+    void* d_ws = nullptr;
+    GT_TRY(ctx->scratch_get(SC_TILE_STATUS, fused_workspace_bytes(n), &d_ws));
+    uint64_t* d_misc = nullptr;
+    GT_TRY(ctx->scratch_get(SC_MISC, 64, (void**)&d_misc));
+    GT_CUDA(cudaMemsetAsync(d_misc, 0, 64, ctx->stream));
+    return launch_fused_find(ix, n, d_out_file_token_offsets ? n_files : 0, d_file_offsets, d_chr, d_start, d_end,
+                             min_overlap, d_out_ids, ids_capacity, d_out_offsets, d_out_file_token_offsets, d_ws, nullptr,
+                             d_out_total, (uint32_t*)(d_misc + 2));
+}
+
+int32_t gtgpu_unk_rule_dev(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* d_raw_file_token_offsets,
+                           const uint32_t* d_raw_ids, uint32_t unk_id, uint64_t* d_out_file_token_offsets,
+                           uint32_t* d_out_ids, uint64_t* d_out_n_empty) {
+    if (!ctx || !d_raw_file_token_offsets || !d_out_file_token_offsets || !d_out_ids || !d_out_n_empty)
+        return fail(GTGPU_ERR_INVALID, "unk_rule_dev: null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    GT_CUDA(cudaSetDevice(ctx->device));
+    GT_TRY(launch_unk_offsets(ctx, n_files, d_raw_file_token_offsets, d_out_file_token_offsets, d_out_n_empty));
+    return launch_unk_expand(ctx, n_files, d_raw_file_token_offsets, d_out_file_token_offsets, d_raw_ids, unk_id,
+                             d_out_ids);
+}
+
+}  // extern "C"

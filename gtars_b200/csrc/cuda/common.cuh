@@ -1,0 +1,150 @@
+// common.cuh — shared declarations for libgtars_gpu.so (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../../include/gtars_gpu.h"
+
+namespace gtgpu {
+
+// ---- error plumbing ---------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int32_t fail(int32_t code, const std::string& msg);
+
+#define GT_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return ::gtgpu::fail(GTGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
+    } while (0)
+
+#define GT_TRY(expr)                   \
+    do {                               \
+        int32_t _s = (expr);           \
+        if (_s != GTGPU_OK) return _s; \
+    } while (0)
+
+// ---- device-side view of an index -----------------------------------------------------------------------------
+// One *segment* = one (chromosome, AIList component) run of intervals, start-sorted, with the running max of
+// its ends (pmax).  Bits has exactly one segment per chromosome.  All arrays are SoA, 32-bit coordinates.
+// Every sorted array that gets searched has a bin LUT in front of it: lut[b] = lower_bound(arr, b << shift),
+// so a search is one LUT read (two adjacent words) plus a bisection inside one bin (0–3 probes for peak-like
+// universes).  The LUTs and the arrays of a 1 M-region universe are ≈ 25 MB and stay L2-resident.
+struct SegMeta {      // 32 bytes, read as two 128-bit loads
+    uint32_t off;     // first interval of this segment in starts/ends/pmax/vals
+    uint32_t len;
+    uint32_t lut_s;   // offset of the LUT over starts (nb_s + 1 entries, segment-local indices)
+    uint32_t nb_s;
+    uint32_t lut_p;   // offset of the LUT over pmax
+    uint32_t nb_p;
+    uint32_t mono;    // 1 when ends are non-decreasing in segment order (pmax == ends: every candidate is a hit)
+    uint32_t pad;
+};
+
+struct ChromMeta {    // 32 bytes
+    uint32_t seg_begin, seg_end;  // segments of this chromosome (component order)
+    uint32_t off, len;            // chromosome range in cs_starts / cs_ends
+    uint32_t lut_cs, nb_cs;       // LUT over the chromosome's independently sorted starts
+    uint32_t lut_ce, nb_ce;       // LUT over the chromosome's independently sorted ends
+};
+
+struct IndexView {
+    const ChromMeta* chroms;
+    const SegMeta* segs;
+    const uint32_t* starts;
+    const uint32_t* ends;
+    const uint32_t* pmax;
+    const uint32_t* vals;
+    const uint32_t* cs_starts;
+    const uint32_t* cs_ends;
+    const uint32_t* lut;
+    uint32_t n_chroms;
+    uint32_t shift;
+    uint32_t descending;  // 1 = AIList emission order (descending position inside a segment)
+    uint32_t proper;      // 1 = every interval has start <= end (Bits identity usable)
+};
+
+// ---- host-side objects ---------------------------------------------------------------------------------------
+struct DevBuffer {
+    void* ptr = nullptr;
+    size_t cap = 0;
+};
+
+struct PinnedBlock {
+    void* ptr = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace gtgpu
+
+struct gtgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    std::mutex mu;
+    std::vector<gtgpu::DevBuffer> scratch;       // grow-only device scratch, indexed by role
+    std::vector<gtgpu::PinnedBlock> pinned_free;  // cache of pinned result blocks
+    uint64_t* h_scalars = nullptr;                // small pinned mailbox
+    int32_t scratch_get(int role, size_t bytes, void** out);
+    int32_t pinned_get(size_t bytes, gtgpu::PinnedBlock* out);
+    void pinned_put(gtgpu::PinnedBlock b);
+};
+
+struct gtgpu_buf {
+    gtgpu_ctx* ctx = nullptr;
+    gtgpu::PinnedBlock block;
+    uint64_t len = 0;  // elements
+    uint32_t elem_size = 4;
+};
+
+struct gtgpu_index {
+    gtgpu_ctx* ctx = nullptr;
+    int32_t kind = 0;
+    gtgpu::IndexView view{};
+    std::vector<void*> allocs;
+    uint64_t n_intervals = 0, n_segments = 0, device_bytes = 0, max_components = 0;
+};
+
+namespace gtgpu {
+
+enum ScratchRole {
+    SC_CHR = 0, SC_START, SC_END, SC_BARCODE, SC_OUT_IDS, SC_OUT_IDS2, SC_OUT_OFFS, SC_FILE_OFFS, SC_FILE_TOK,
+    SC_FILE_TOK2, SC_TILE_STATUS, SC_TILE_FILE, SC_MISC, SC_COUNTS, SC_IN2_CHR, SC_IN2_START, SC_IN2_END,
+    SC_IN3_CHR, SC_IN3_START, SC_IN3_END, SC_SET_ID, SC_MATRIX, SC_N_ROLES
+};
+
+// kernels.cu
+constexpr int FUSED_BLOCK = 256;
+constexpr int FUSED_ITEMS = 4;
+constexpr int FUSED_TILE = FUSED_BLOCK * FUSED_ITEMS;
+
+enum CountMode { COUNT_U32 = 0, COUNT_ANY_U8 = 1, COUNT_BITS_RAW_U64 = 2 };
+
+int32_t launch_count(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
+                     const uint32_t* d_end, int32_t min_overlap, int mode, void* d_out);
+
+// Workspace the fused kernel needs (device): tile status words + per-tile first-file marks + 2 scalars.
+size_t fused_workspace_bytes(uint64_t n);
+// d_base (device u64, may be null = 0) is the id offset this launch starts at; *d_total_out receives
+// base + ids produced.  d_errflag (device u32) is set to 1 when a tile overflows 32-bit local offsets.
+int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const uint64_t* d_file_offsets,
+                          const uint32_t* d_chr, const uint32_t* d_start, const uint32_t* d_end,
+                          int32_t min_overlap, uint32_t* d_out_ids, uint64_t ids_capacity,
+                          uint64_t* d_out_offsets, uint64_t* d_out_file_tok, void* d_workspace,
+                          const uint64_t* d_base, uint64_t* d_total_out, uint32_t* d_errflag);
+// Per-call [unk] rule: expands raw per-file id runs into d_out, inserting unk_id for files with no ids.
+int32_t launch_unk_offsets(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* d_raw_file_tok,
+                           uint64_t* d_out_file_tok, uint64_t* d_n_empty);
+int32_t launch_unk_expand(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* d_raw_file_tok,
+                          const uint64_t* d_out_file_tok, const uint32_t* d_raw_ids, uint32_t unk_id,
+                          uint32_t* d_out_ids);
+
+}  // namespace gtgpu

@@ -1,0 +1,236 @@
+// index.cu — host-side build of the device index (gtgpu_index_build).
+//
+// Order semantics of the reference are fixed here, once:
+//   Bits   (gtars-overlaprs/src/bits.rs:101-128):   stable sort by (start,end); one segment per chromosome.
+//   AIList (gtars-overlaprs/src/ailist.rs:105-151, 198-236): stable sort by start, then repeated peeling of
+//          "long" intervals (>= 10 of the next 19 end earlier) into further components; no cap on components.
+// Both get the same device layout: start-sorted SoA segments + running max of ends + bin LUTs, so the kernels
+// locate candidates identically and only the emission direction differs.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace gtgpu {
+
+namespace {
+
+struct HostSeg {
+    uint32_t chrom;
+    std::vector<uint32_t> order;  // indices into the caller's arrays
+};
+
+// lut[b] = lower_bound(arr, b << shift) for b in [0, nb], nb = (max >> shift) + 1, lut[nb] = n.
+void build_lut(const uint32_t* arr, uint32_t n, uint32_t shift, std::vector<uint32_t>& lut, uint32_t& lut_off,
+               uint32_t& nb) {
+    lut_off = (uint32_t)lut.size();
+    if (n == 0) {
+        nb = 0;
+        lut.push_back(0);
+        return;
+    }
+    nb = (arr[n - 1] >> shift) + 1;
+    lut.resize(lut.size() + (size_t)nb + 1);
+    uint32_t* L = lut.data() + lut_off;
+    uint32_t i = 0;
+    for (uint32_t b = 0; b < nb; ++b) {
+        uint64_t key = (uint64_t)b << shift;
+        while (i < n && arr[i] < key) ++i;
+        L[b] = i;
+    }
+    L[nb] = n;
+}
+
+uint64_t lut_entries(const std::vector<uint32_t>& maxima, uint32_t shift) {
+    uint64_t t = 0;
+    for (uint32_t m : maxima) t += ((uint64_t)m >> shift) + 2;
+    return t;
+}
+
+template <class T>
+int32_t upload(gtgpu_index* ix, const std::vector<T>& v, const T** out) {
+    void* d = nullptr;
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) return fail(GTGPU_ERR_NOMEM, std::string("cudaMalloc(index): ") + cudaGetErrorString(e));
+    ix->allocs.push_back(d);
+    ix->device_bytes += bytes;
+    if (!v.empty()) GT_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)d;
+    return GTGPU_OK;
+}
+
+}  // namespace
+
+}  // namespace gtgpu
+
+using namespace gtgpu;
+
+extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_chroms, const uint64_t* chrom_offsets,
+                                     const uint32_t* starts, const uint32_t* ends, const uint32_t* vals,
+                                     gtgpu_index** out_index) {
+    if (!ctx || !out_index || (n_chroms && !chrom_offsets)) return fail(GTGPU_ERR_INVALID, "index_build: null argument");
+    if (kind != GTGPU_KIND_BITS && kind != GTGPU_KIND_AILIST) return fail(GTGPU_ERR_INVALID, "index_build: bad kind");
+    uint64_t total = n_chroms ? chrom_offsets[n_chroms] : 0;
+    if (total >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "index_build: more than 2^32-2 intervals");
+    if (total && (!starts || !ends)) return fail(GTGPU_ERR_INVALID, "index_build: null coordinate arrays");
+    for (uint32_t c = 0; c < n_chroms; ++c)
+        if (chrom_offsets[c] > chrom_offsets[c + 1]) return fail(GTGPU_ERR_INVALID, "index_build: chrom_offsets not monotone");
+    GT_CUDA(cudaSetDevice(ctx->device));
+
+    // ---- 1. per-chromosome ordering + AIList decomposition ------------------------------------------------
+    std::vector<HostSeg> segs;
+    std::vector<ChromMeta> chroms(n_chroms);
+    uint64_t max_components = 0;
+    bool proper = true;
+    for (uint32_t c = 0; c < n_chroms; ++c) {
+        uint64_t lo = chrom_offsets[c], hi = chrom_offsets[c + 1];
+        chroms[c].seg_begin = (uint32_t)segs.size();
+        if (hi > lo) {
+            std::vector<uint32_t> order(hi - lo);
+            std::iota(order.begin(), order.end(), (uint32_t)lo);
+            if (kind == GTGPU_KIND_BITS) {
+                std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+                    return starts[a] != starts[b] ? starts[a] < starts[b] : ends[a] < ends[b];
+                });
+                segs.push_back(HostSeg{c, std::move(order)});
+            } else {
+                std::stable_sort(order.begin(), order.end(),
+                                 [&](uint32_t a, uint32_t b) { return starts[a] < starts[b]; });
+                const size_t min_cov = 10;
+                std::vector<uint32_t> next;
+                while (!order.empty()) {
+                    HostSeg seg{c, {}};
+                    next.clear();
+                    for (size_t i = 0; i < order.size(); ++i) {
+                        size_t covered = 0;
+                        uint32_t e_i = ends[order[i]];
+                        for (size_t j = 1; j < 2 * min_cov && i + j < order.size(); ++j)
+                            covered += e_i > ends[order[i + j]];
+                        if (covered >= min_cov) next.push_back(order[i]);
+                        else seg.order.push_back(order[i]);
+                    }
+                    // A pass that keeps nothing cannot happen: the last interval of a list always has covered == 0.
+                    segs.push_back(std::move(seg));
+                    order.swap(next);
+                }
+            }
+        }
+        chroms[c].seg_end = (uint32_t)segs.size();
+        max_components = std::max<uint64_t>(max_components, chroms[c].seg_end - chroms[c].seg_begin);
+    }
+
+    // ---- 2. flatten to SoA ---------------------------------------------------------------------------------
+    std::vector<uint32_t> h_starts(total), h_ends(total), h_pmax(total), h_vals(total), h_cs(total), h_ce(total);
+    std::vector<SegMeta> seg_meta(segs.size());
+    {
+        uint64_t pos = 0;
+        for (size_t s = 0; s < segs.size(); ++s) {
+            SegMeta& m = seg_meta[s];
+            m.off = (uint32_t)pos;
+            m.len = (uint32_t)segs[s].order.size();
+            m.mono = 1;
+            m.pad = 0;
+            uint32_t mx = 0;
+            for (uint32_t id : segs[s].order) {
+                h_starts[pos] = starts[id];
+                h_ends[pos] = ends[id];
+                h_vals[pos] = vals ? vals[id] : id;
+                if (ends[id] < mx) m.mono = 0;
+                mx = std::max(mx, ends[id]);
+                h_pmax[pos] = mx;
+                if (starts[id] > ends[id]) proper = false;
+                ++pos;
+            }
+        }
+        for (uint32_t c = 0; c < n_chroms; ++c) {
+            uint64_t lo = chrom_offsets[c], hi = chrom_offsets[c + 1];
+            chroms[c].off = (uint32_t)lo;
+            chroms[c].len = (uint32_t)(hi - lo);
+            std::copy(starts + lo, starts + hi, h_cs.begin() + lo);
+            std::copy(ends + lo, ends + hi, h_ce.begin() + lo);
+            std::sort(h_cs.begin() + lo, h_cs.begin() + hi);
+            std::sort(h_ce.begin() + lo, h_ce.begin() + hi);
+        }
+    }
+
+    // ---- 3. LUT shift: smallest shift whose LUT families stay within the bin budget -------------------------
+    std::vector<uint32_t> max_s, max_p, max_cs, max_ce;
+    for (const auto& m : seg_meta) {
+        max_s.push_back(m.len ? h_starts[m.off + m.len - 1] : 0);
+        max_p.push_back(m.len ? h_pmax[m.off + m.len - 1] : 0);
+    }
+    for (const auto& c : chroms) {
+        max_cs.push_back(c.len ? h_cs[c.off + c.len - 1] : 0);
+        max_ce.push_back(c.len ? h_ce[c.off + c.len - 1] : 0);
+    }
+    uint64_t budget = std::max<uint64_t>(2 * total, 4096);
+    uint64_t cap = 8ull << 20;
+    if (const char* env = getenv("GTGPU_LUT_MAX_BINS")) cap = std::max<uint64_t>(strtoull(env, nullptr, 10), 1024);
+    budget = std::min(budget, cap);
+    uint32_t shift = 0;
+    while (shift < 31 && std::max(lut_entries(max_s, shift), lut_entries(max_p, shift)) > budget) ++shift;
+    if (const char* env = getenv("GTGPU_LUT_SHIFT")) shift = (uint32_t)std::min(31, std::max(0, atoi(env)));
+
+    std::vector<uint32_t> lut;
+    for (auto& m : seg_meta) {
+        build_lut(h_starts.data() + m.off, m.len, shift, lut, m.lut_s, m.nb_s);
+        build_lut(h_pmax.data() + m.off, m.len, shift, lut, m.lut_p, m.nb_p);
+    }
+    for (auto& c : chroms) {
+        build_lut(h_cs.data() + c.off, c.len, shift, lut, c.lut_cs, c.nb_cs);
+        build_lut(h_ce.data() + c.off, c.len, shift, lut, c.lut_ce, c.nb_ce);
+    }
+    if (lut.size() >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "index_build: LUT too large");
+
+    // ---- 4. upload ---------------------------------------------------------------------------------------------
+    gtgpu_index* ix = new gtgpu_index();
+    ix->ctx = ctx;
+    ix->kind = kind;
+    ix->n_intervals = total;
+    ix->n_segments = segs.size();
+    ix->max_components = max_components;
+    IndexView& v = ix->view;
+    int32_t st = GTGPU_OK;
+    auto up = [&](auto& vec, auto** dst) { if (st == GTGPU_OK) st = upload(ix, vec, dst); };
+    up(chroms, &v.chroms);
+    up(seg_meta, &v.segs);
+    up(h_starts, &v.starts);
+    up(h_ends, &v.ends);
+    up(h_pmax, &v.pmax);
+    up(h_vals, &v.vals);
+    up(h_cs, &v.cs_starts);
+    up(h_ce, &v.cs_ends);
+    up(lut, &v.lut);
+    if (st != GTGPU_OK) {
+        gtgpu_index_free(ix);
+        return st;
+    }
+    v.n_chroms = n_chroms;
+    v.shift = shift;
+    v.descending = kind == GTGPU_KIND_AILIST;
+    v.proper = proper;
+    *out_index = ix;
+    return GTGPU_OK;
+}
+
+extern "C" int32_t gtgpu_index_free(gtgpu_index* ix) {
+    if (!ix) return GTGPU_OK;
+    cudaSetDevice(ix->ctx->device);
+    for (void* p : ix->allocs) cudaFree(p);
+    delete ix;
+    return GTGPU_OK;
+}
+
+extern "C" int32_t gtgpu_index_info(const gtgpu_index* ix, uint64_t info[6]) {
+    if (!ix || !info) return fail(GTGPU_ERR_INVALID, "index_info: null argument");
+    info[0] = ix->n_intervals;
+    info[1] = ix->n_segments;
+    info[2] = ix->device_bytes;
+    info[3] = ix->view.shift;
+    info[4] = ix->max_components;
+    info[5] = ix->view.proper;
+    return GTGPU_OK;
+}

@@ -1,0 +1,239 @@
+"""ctypes binding of include/gtars_gpu.h (libgtars_gpu.so) — flat arrays in, flat arrays out.
+
+This is the same call surface a Rust `gtars-overlaprs-sys` crate would bind.  There is no CPU
+fallback: if the shared library is missing or no CUDA device is usable, everything here raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libgtars_gpu.so")
+
+KIND_BITS, KIND_AILIST = 0, 1
+UNKNOWN_CHROM = 0xFFFFFFFF
+
+# every symbol include/gtars_gpu.h declares: name -> (restype, argtypes)
+_vp, _u32, _u64, _i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
+SIGNATURES = {
+    "gtgpu_last_error": (C.c_char_p, []),
+    "gtgpu_version": (C.c_char_p, []),
+    "gtgpu_device_count": (_i32, [_vp]),
+    "gtgpu_init": (_i32, [_i32, _vp, _vp]),
+    "gtgpu_shutdown": (_i32, [_vp]),
+    "gtgpu_synchronize": (_i32, [_vp]),
+    "gtgpu_launch_count": (_i32, [_vp, _vp]),
+    "gtgpu_host_alloc": (_i32, [_u64, _vp]),
+    "gtgpu_host_free": (_i32, [_vp]),
+    "gtgpu_buf_data": (_vp, [_vp]),
+    "gtgpu_buf_len": (_u64, [_vp]),
+    "gtgpu_buf_free": (_i32, [_vp]),
+    "gtgpu_index_build": (_i32, [_vp, _i32, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "gtgpu_index_free": (_i32, [_vp]),
+    "gtgpu_index_info": (_i32, [_vp, _vp]),
+    "gtgpu_count": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _vp]),
+    "gtgpu_bits_count": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp]),
+    "gtgpu_any": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _vp]),
+    "gtgpu_find": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "gtgpu_tokenize_files": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
+    "gtgpu_count_dev": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _vp]),
+    "gtgpu_find_dev": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _u64, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "gtgpu_unk_rule_dev": (_i32, [_vp, _u64, _vp, _vp, _u32, _vp, _vp, _vp]),
+}
+
+
+class GtarsGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gtars_gpu error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libgtars_gpu.so (built by __graft_entry__.build() / `make -C gtars_b200/csrc`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `make -C gtars_b200/csrc` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise GtarsGpuError(status, lib().gtgpu_last_error().decode(errors="replace"))
+
+
+def _arr(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def device_count() -> int:
+    n = C.c_int32(0)
+    check(lib().gtgpu_device_count(C.byref(n)))
+    return n.value
+
+
+def pinned_empty(n, dtype) -> np.ndarray:
+    """numpy array backed by pinned host memory (gtgpu_host_alloc); freed when the array is collected."""
+    dtype = np.dtype(dtype)
+    ptr = C.c_void_p()
+    check(lib().gtgpu_host_alloc(max(int(n) * dtype.itemsize, 64), C.byref(ptr)))
+    buf = (C.c_char * max(int(n) * dtype.itemsize, 1)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    class _Owner:
+        def __init__(self, p):
+            self.p = p
+
+        def __del__(self):
+            try:
+                lib().gtgpu_host_free(self.p)
+            except Exception:
+                pass
+
+    _OWNERS[ptr.value] = _Owner(ptr.value)
+    return arr
+
+
+_OWNERS = {}
+
+
+def pinned_free(arr: np.ndarray):
+    o = _OWNERS.pop(arr.ctypes.data, None)
+    if o is not None:
+        lib().gtgpu_host_free(o.p)
+        o.p = None
+
+
+def _take(buf_handle, dtype=np.uint32, copy=True) -> np.ndarray:
+    L = lib()
+    n = L.gtgpu_buf_len(buf_handle)
+    out = np.empty(n, dtype=dtype)
+    if n:
+        C.memmove(out.ctypes.data, L.gtgpu_buf_data(buf_handle), n * out.itemsize)
+    L.gtgpu_buf_free(buf_handle)
+    return out
+
+
+class Context:
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._h = C.c_void_p()
+        check(lib().gtgpu_init(device, C.c_void_p(stream) if stream else None, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().gtgpu_shutdown(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(lib().gtgpu_synchronize(self._h))
+
+    def launch_count(self) -> int:
+        n = C.c_uint64(0)
+        check(lib().gtgpu_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def unk_rule_dev(self, n_files, d_raw_tok, d_raw_ids, unk_id, d_out_tok, d_out_ids, d_n_empty):
+        check(lib().gtgpu_unk_rule_dev(self._h, n_files, d_raw_tok, d_raw_ids, unk_id, d_out_tok, d_out_ids, d_n_empty))
+
+
+class Index:
+    """gtgpu_index: per-chromosome Bits / AIList on the device."""
+
+    def __init__(self, ctx: Context, kind: int, chrom_offsets, starts, ends, vals=None):
+        self.ctx = ctx
+        self.kind = kind
+        co = _arr(chrom_offsets, np.uint64)
+        s, e = _arr(starts, np.uint32), _arr(ends, np.uint32)
+        v = _arr(vals, np.uint32) if vals is not None else None
+        if len(s) != len(e) or (v is not None and len(v) != len(s)) or (len(co) and int(co[-1]) != len(s)):
+            raise ValueError("index arrays disagree in length")
+        self.n_chroms = max(len(co) - 1, 0)
+        self._h = C.c_void_p()
+        check(lib().gtgpu_index_build(ctx._h, kind, self.n_chroms, _p(co), _p(s), _p(e), _p(v), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            lib().gtgpu_index_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        a = (C.c_uint64 * 6)()
+        check(lib().gtgpu_index_info(self._h, a))
+        return dict(n_intervals=a[0], n_segments=a[1], device_bytes=a[2], lut_shift=a[3], max_components=a[4],
+                    proper=bool(a[5]))
+
+    # ---- host-buffer entry points -------------------------------------------------------------------------------
+    def count(self, chr, start, end, min_overlap=0) -> np.ndarray:
+        chr, start, end = _arr(chr, np.uint32), _arr(start, np.uint32), _arr(end, np.uint32)
+        out = np.empty(len(chr), dtype=np.uint32)
+        check(lib().gtgpu_count(self._h, len(chr), _p(chr), _p(start), _p(end), min_overlap, _p(out)))
+        return out
+
+    def bits_count(self, chr, start, end) -> np.ndarray:
+        chr, start, end = _arr(chr, np.uint32), _arr(start, np.uint32), _arr(end, np.uint32)
+        out = np.empty(len(chr), dtype=np.uint64)
+        check(lib().gtgpu_bits_count(self._h, len(chr), _p(chr), _p(start), _p(end), _p(out)))
+        return out
+
+    def any(self, chr, start, end, min_overlap=0) -> np.ndarray:
+        chr, start, end = _arr(chr, np.uint32), _arr(start, np.uint32), _arr(end, np.uint32)
+        out = np.empty(len(chr), dtype=np.uint8)
+        check(lib().gtgpu_any(self._h, len(chr), _p(chr), _p(start), _p(end), min_overlap, _p(out)))
+        return out.astype(bool)
+
+    def find(self, chr, start, end, min_overlap=0):
+        chr, start, end = _arr(chr, np.uint32), _arr(start, np.uint32), _arr(end, np.uint32)
+        off = np.empty(len(chr) + 1, dtype=np.uint64)
+        h = C.c_void_p()
+        check(lib().gtgpu_find(self._h, len(chr), _p(chr), _p(start), _p(end), min_overlap, _p(off), C.byref(h)))
+        return off, _take(h)
+
+    def tokenize_files(self, file_offsets, chr, start, end, unk_id, keep_buf=False):
+        fo = _arr(file_offsets, np.uint64)
+        chr, start, end = _arr(chr, np.uint32), _arr(start, np.uint32), _arr(end, np.uint32)
+        out_off = np.empty(len(fo), dtype=np.uint64)
+        h = C.c_void_p()
+        check(lib().gtgpu_tokenize_files(self._h, len(fo) - 1, _p(fo), _p(chr), _p(start), _p(end), unk_id,
+                                         _p(out_off), C.byref(h)))
+        if keep_buf:
+            return out_off, h
+        return out_off, _take(h)
+
+    # ---- device-resident entry points (raw device pointers as ints) ----------------------------------------------------
+    def count_dev(self, n, d_chr, d_start, d_end, min_overlap, d_out):
+        check(lib().gtgpu_count_dev(self._h, n, d_chr, d_start, d_end, min_overlap, d_out))
+
+    def find_dev(self, n, d_chr, d_start, d_end, min_overlap, n_files, d_file_offsets, d_out_ids, ids_capacity,
+                 d_out_offsets, d_out_file_tok, d_out_total):
+        check(lib().gtgpu_find_dev(self._h, n, d_chr, d_start, d_end, min_overlap, n_files, d_file_offsets, d_out_ids,
+                                   ids_capacity, d_out_offsets, d_out_file_tok, d_out_total))

@@ -1,0 +1,134 @@
+/* gtars_gpu.h — C ABI of the B200-native interval-overlap engine (libgtars_gpu.so).
+ *
+ * This is the drop-in boundary for gtars' data-parallel hot path: the bodies of the batch-shaped Rust APIs
+ * cited on each entry point below would, under a `cuda` cargo feature, marshal their inputs into flat SoA
+ * arrays and call these functions (binding sketch: INTEGRATION.md, bindings/rust/).  The reference has no FFI
+ * seam today, so every entry point names the reference function whose body it replaces.
+ *
+ * Conventions
+ *  - every function returns an int32 status (GTGPU_OK = 0); nothing throws or unwinds across the boundary;
+ *    gtgpu_last_error() returns a thread-local message for the last failing call on this thread.
+ *  - one gtgpu_ctx = one CUDA device (one process per GPU; multi-GPU runs give each rank its own ctx).
+ *  - chromosome names are mapped to dense uint32 ids by the caller; GTGPU_UNKNOWN_CHROM (or any id >= n_chroms)
+ *    means "chromosome not in the index" and contributes no hits, exactly like the reference's map lookups
+ *    (gtars-tokenizers/src/tokenizer.rs:144, gtars-overlaprs/src/multi_chrom_overlapper.rs:231-234,
+ *    gtars-igd/src/igd.rs:519-522).
+ *  - coordinates are half-open [start,end), uint32 for overlaprs/tokenizers (Interval<u32,u32>), int32 semantics
+ *    for IGD (the reference casts u32→i32, igd.rs:295-296,549-550; values must be < 2^31).
+ *  - "host" entry points take caller-owned host arrays (pinned memory — see gtgpu_host_alloc — makes the copies
+ *    true DMA) and include H2D/D2H; "_dev" entry points take device pointers, are asynchronous on the ctx stream
+ *    and move no data.  Outputs of unknown size are returned as library-owned pinned buffers (gtgpu_buf).
+ *  - there is NO CPU fallback: without a usable CUDA device gtgpu_init fails.
+ */
+#ifndef GTARS_GPU_H
+#define GTARS_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTGPU_OK 0
+#define GTGPU_ERR_INVALID 1   /* bad argument */
+#define GTGPU_ERR_CUDA 2      /* CUDA runtime error (message has the cudaError string) */
+#define GTGPU_ERR_NOMEM 3     /* host or device allocation failed */
+#define GTGPU_ERR_CAPACITY 4  /* caller-provided device output buffer too small; *out_total has the need */
+#define GTGPU_ERR_NCCL 5      /* NCCL not loadable / collective failed */
+#define GTGPU_ERR_UNSUPPORTED 6
+
+#define GTGPU_KIND_BITS 0   /* gtars_overlaprs::Bits   — hits in ascending (start,end,insertion) order */
+#define GTGPU_KIND_AILIST 1 /* gtars_overlaprs::AIList — component-major, descending position         */
+
+#define GTGPU_UNKNOWN_CHROM 0xFFFFFFFFu
+
+typedef struct gtgpu_ctx gtgpu_ctx;
+typedef struct gtgpu_index gtgpu_index; /* immutable after build; usable from several host threads */
+typedef struct gtgpu_igd gtgpu_igd;
+typedef struct gtgpu_buf gtgpu_buf;     /* library-owned pinned host result buffer */
+
+/* ---- library / context ------------------------------------------------------------------------------- */
+const char* gtgpu_last_error(void);
+const char* gtgpu_version(void);
+int32_t gtgpu_device_count(int32_t* out_n);
+/* stream_or_null: a cudaStream_t to run on (e.g. the caller's / torch's current stream) or NULL for an
+ * internal non-blocking stream. */
+int32_t gtgpu_init(int32_t device, void* stream_or_null, gtgpu_ctx** out_ctx);
+int32_t gtgpu_shutdown(gtgpu_ctx* ctx);
+int32_t gtgpu_synchronize(gtgpu_ctx* ctx);
+/* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
+int32_t gtgpu_launch_count(gtgpu_ctx* ctx, uint64_t* out_n);
+
+/* pinned host memory for caller-side SoA arrays */
+int32_t gtgpu_host_alloc(uint64_t bytes, void** out_ptr);
+int32_t gtgpu_host_free(void* ptr);
+
+/* result buffers */
+const void* gtgpu_buf_data(const gtgpu_buf* buf);
+uint64_t gtgpu_buf_len(const gtgpu_buf* buf); /* elements, not bytes */
+int32_t gtgpu_buf_free(gtgpu_buf* buf);       /* returns the pinned block to the ctx cache */
+
+/* ---- index: Overlapper::build per chromosome -------------------------------------------------------------
+ * Replaces Bits::build (gtars-overlaprs/src/bits.rs:101-128) / AIList::build (ailist.rs:105-151) for every
+ * chromosome of a MultiChromOverlapper (multi_chrom_overlapper.rs:130-200) or of a tokenizer core
+ * (gtars-tokenizers/src/utils/mod.rs:49-99).  Chromosome c owns intervals [chrom_offsets[c], chrom_offsets[c+1])
+ * given in the caller's INSERTION order; the library performs the reference's stable sort / decomposition so
+ * hit order semantics live in one place.  vals may be NULL (val = global insertion index).
+ * A chromosome with no intervals behaves as "absent". */
+int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_chroms, const uint64_t* chrom_offsets,
+                          const uint32_t* starts, const uint32_t* ends, const uint32_t* vals,
+                          gtgpu_index** out_index);
+int32_t gtgpu_index_free(gtgpu_index* index);
+/* info[0]=n_intervals, [1]=n_segments (chromosome×AIList component), [2]=device bytes, [3]=lut shift,
+ * [4]=max components on one chromosome, [5]=1 if every interval has start<=end */
+int32_t gtgpu_index_info(const gtgpu_index* index, uint64_t info[6]);
+
+/* ---- batch queries, host buffers ------------------------------------------------------------------------ */
+/* MultiChromOverlapper::count_overlaps (multi_chrom_overlapper.rs:483-498): out_counts[i] = number of indexed
+ * intervals overlapping query i; min_overlap is applied only when > 1 (bp of overlap), as in the reference. */
+int32_t gtgpu_count(gtgpu_index* index, uint64_t n, const uint32_t* chr, const uint32_t* start,
+                    const uint32_t* end, int32_t min_overlap, uint32_t* out_counts);
+/* Bits::count (bits.rs:337-344), the two-binary-search identity, with the reference's wrapping usize
+ * arithmetic (`start+1` wraps in u32; the difference wraps in u64).  Index must be GTGPU_KIND_BITS. */
+int32_t gtgpu_bits_count(gtgpu_index* index, uint64_t n, const uint32_t* chr, const uint32_t* start,
+                         const uint32_t* end, uint64_t* out_counts);
+/* MultiChromOverlapper::any_overlaps (multi_chrom_overlapper.rs:501-516). */
+int32_t gtgpu_any(gtgpu_index* index, uint64_t n, const uint32_t* chr, const uint32_t* start,
+                  const uint32_t* end, int32_t min_overlap, uint8_t* out_any);
+/* Overlapper::find for a batch (bits.rs:141-156, ailist.rs:153-178; callers: find_overlaps_regions
+ * multi_chrom_overlapper.rs:524-550, IndexedRegionSet::find_overlaps indexed_region_set.rs:145-263):
+ * out_offsets[n+1] (caller-allocated), *out_vals = the hits' vals, query-major, in the reference's per-backend
+ * iteration order. */
+int32_t gtgpu_find(gtgpu_index* index, uint64_t n, const uint32_t* chr, const uint32_t* start,
+                   const uint32_t* end, int32_t min_overlap, uint64_t* out_offsets, gtgpu_buf** out_vals);
+/* Tokenizer::encode for a batch of calls (gtars-tokenizers/src/tokenizer.rs:140-171): "file" f is one encode()
+ * call over queries [file_offsets[f], file_offsets[f+1]); its ids are the concatenated vals of every query's
+ * hits, or the single id unk_id when the whole call produced none.  out_file_token_offsets has n_files+1
+ * entries.  (Duplicate-universe remapping, SURVEY.md §8a A9, is folded into vals by the caller at build time.) */
+int32_t gtgpu_tokenize_files(gtgpu_index* index, uint64_t n_files, const uint64_t* file_offsets,
+                             const uint32_t* chr, const uint32_t* start, const uint32_t* end, uint32_t unk_id,
+                             uint64_t* out_file_token_offsets, gtgpu_buf** out_ids);
+
+/* ---- batch queries, device-resident (asynchronous on the ctx stream) --------------------------------------- */
+int32_t gtgpu_count_dev(gtgpu_index* index, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
+                        const uint32_t* d_end, int32_t min_overlap, uint32_t* d_out_counts);
+/* Fused count → device-wide exclusive scan → emit in ONE pass over the queries (the device-resident core of
+ * gtgpu_find / gtgpu_tokenize_files).  d_out_ids has room for ids_capacity ids; d_out_offsets (n+1 u64, per query)
+ * and d_out_file_token_offsets (n_files+1 u64, RAW: before the [unk] rule; needs d_file_offsets) may each be NULL.
+ * *d_out_total (device u64) receives the number of ids the call produces; when it exceeds ids_capacity the
+ * surplus is not written (the host entry points then re-run with an exact buffer). */
+int32_t gtgpu_find_dev(gtgpu_index* index, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
+                       const uint32_t* d_end, int32_t min_overlap, uint64_t n_files, const uint64_t* d_file_offsets,
+                       uint32_t* d_out_ids, uint64_t ids_capacity, uint64_t* d_out_offsets,
+                       uint64_t* d_out_file_token_offsets, uint64_t* d_out_total);
+/* The per-call [unk] rule of Tokenizer::tokenize (tokenizer.rs:158-160) applied to raw per-file id runs:
+ * d_out_file_token_offsets[f] = raw[f] + #empty files before f; d_out_ids gets every file's ids, or unk_id for a
+ * file with none (capacity >= raw total + n_files); *d_out_n_empty (device u64) = number of such files. */
+int32_t gtgpu_unk_rule_dev(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* d_raw_file_token_offsets,
+                           const uint32_t* d_raw_ids, uint32_t unk_id, uint64_t* d_out_file_token_offsets,
+                           uint32_t* d_out_ids, uint64_t* d_out_n_empty);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTARS_GPU_H */

@@ -1,0 +1,246 @@
+"""GPU parity: the CUDA path (through the C ABI of include/gtars_gpu.h) against the CPU oracle, bit-exact.
+
+Run on a B200 with `pytest -m gpu`.  Inputs are seeded; sizes are chosen so the oracle finishes in seconds;
+full-size properties live in test_gpu_scale.py.
+"""
+import numpy as np
+import pytest
+
+from tests import helpers
+from tests.helpers import KINDS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from gtars_b200 import ffi
+    c = ffi.Context(0)
+    yield c
+    c.close()
+
+
+def _both(ctx, kind, offs, s, e, v=None):
+    from gtars_b200 import ffi
+    from oracle import oracle as orc
+    return ffi.Index(ctx, KINDS[kind], offs, s, e, v), orc.Index(KINDS[kind], offs, s, e, v)
+
+
+def _assert_same_find(g, o, qc, qs, qe, m=0):
+    go, gv = g.find(qc, qs, qe, m)
+    oo, ov = o.find(qc, qs, qe, m)
+    assert np.array_equal(go, oo)
+    assert np.array_equal(gv, ov)
+    assert np.array_equal(g.count(qc, qs, qe, m), o.count(qc, qs, qe, m))
+    assert np.array_equal(g.any(qc, qs, qe, m), o.any(qc, qs, qe, m))
+
+
+# ---- the reference's own KATs, replayed through the C ABI --------------------------------------------------------
+@pytest.mark.parametrize("name", ["K1_abcd", "K1_empty", "K1_single", "K2_nested26"])
+def test_overlapper_kats_gpu(ctx, golden, name):
+    case = golden[1][name]
+    ivs = case["intervals"]
+    offs = np.array([0, len(ivs)], dtype=np.uint64)
+    s = np.array([iv[0] for iv in ivs], dtype=np.uint32)
+    e = np.array([iv[1] for iv in ivs], dtype=np.uint32)
+    for kind in case["kinds"]:
+        g, o = _both(ctx, kind, offs, s, e)
+        if kind == "ailist" and "ailist_components" in case:
+            assert g.info()["max_components"] == case["ailist_components"]
+        for q in case["queries"]:
+            qc = np.zeros(1, dtype=np.uint32)
+            qs = np.array([q["q"][0]], dtype=np.uint32)
+            qe = np.array([q["q"][1]], dtype=np.uint32)
+            off, vals = g.find(qc, qs, qe)
+            got = sorted((int(s[v]), int(e[v])) for v in vals)
+            if "set" in q:
+                assert got == sorted(tuple(x) for x in q["set"]), (name, kind, q)
+            if "n" in q:
+                assert len(vals) == q["n"] and g.count(qc, qs, qe)[0] == q["n"], (name, kind, q)
+            _assert_same_find(g, o, qc, qs, qe)
+
+
+def test_bits_count_and_order_gpu(ctx, golden):
+    case = golden[1]["K3_bits_count"]
+    ivs = case["intervals"]
+    offs = np.array([0, len(ivs)], dtype=np.uint64)
+    s = np.array([iv[0] for iv in ivs], dtype=np.uint32)
+    e = np.array([iv[1] for iv in ivs], dtype=np.uint32)
+    g, o = _both(ctx, "bits", offs, s, e)
+    for q in case["queries"]:
+        qc, qs, qe = np.zeros(1, np.uint32), np.array([q["q"][0]], np.uint32), np.array([q["q"][1]], np.uint32)
+        assert g.bits_count(qc, qs, qe)[0] == q["count"]
+        assert g.count(qc, qs, qe)[0] == q["find_n"]
+    case = golden[1]["K3_bits_order"]
+    ivs = case["intervals_val"]
+    offs = np.array([0, len(ivs)], dtype=np.uint64)
+    s = np.array([iv[0] for iv in ivs], dtype=np.uint32)
+    e = np.array([iv[1] for iv in ivs], dtype=np.uint32)
+    v = np.array([iv[2] for iv in ivs], dtype=np.uint32)
+    g, o = _both(ctx, "bits", offs, s, e, v)
+    for q in case["queries"]:
+        qc, qs, qe = np.zeros(1, np.uint32), np.array([q["q"][0]], np.uint32), np.array([q["q"][1]], np.uint32)
+        _, vals = g.find(qc, qs, qe)
+        assert [int(x) for x in vals] == [t[2] for t in q["ordered"]]
+
+
+@pytest.mark.parametrize("kind", ["bits", "ailist"])
+def test_mco_kats_gpu(ctx, golden, kind):
+    for case in golden[1]["K4_mco"]:
+        cmap, offs, s, e, v = helpers.flatten_source(case["source"])
+        g, o = _both(ctx, kind, offs, s, e, v)
+        qc, qs, qe = helpers.flatten_queries(case["query"], cmap)
+        m = case["min_overlap"] if case["min_overlap"] is not None else 0
+        if "count" in case:
+            assert list(g.count(qc, qs, qe, m)) == case["count"], case["cite"]
+        if "any" in case:
+            assert list(g.any(qc, qs, qe, m)) == case["any"], case["cite"]
+        off, vals = g.find(qc, qs, qe, m)
+        if "find" in case:
+            src = case["source"]
+            got = [sorted([src[int(x)][1], src[int(x)][2]] for x in vals[int(off[i]):int(off[i + 1])])
+                   for i in range(len(qc))]
+            assert got == [sorted(x) for x in case["find"]], case["cite"]
+        if "find_idx" in case:
+            got = [sorted(int(x) for x in vals[int(off[i]):int(off[i + 1])]) for i in range(len(qc))]
+            assert got == case["find_idx"], case["cite"]
+        _assert_same_find(g, o, qc, qs, qe, m)
+
+
+# ---- randomized differential tests ------------------------------------------------------------------------------------
+def _random_index(rng, n_chroms, n, style):
+    chr_ = np.sort(rng.integers(0, n_chroms, n))
+    span = 200_000
+    if style == "peaks":  # non-overlapping
+        s = np.empty(n, dtype=np.int64)
+        e = np.empty(n, dtype=np.int64)
+        for c in range(n_chroms):
+            idx = np.where(chr_ == c)[0]
+            k = len(idx)
+            if k == 0:
+                continue
+            slot = max(span // k, 4)
+            base = np.arange(k) * slot
+            w = rng.integers(1, max(slot - 1, 2), k)
+            perm = rng.permutation(k)
+            s[idx] = base[perm]
+            e[idx] = (base + w)[perm]
+    elif style == "overlap":
+        s = rng.integers(0, span, n)
+        e = s + rng.integers(1, 3000, n)
+    elif style == "nested":
+        s = rng.integers(0, span, n)
+        w = np.where(rng.random(n) < 0.08, rng.integers(5000, 60000, n), rng.integers(1, 400, n))
+        e = s + w
+    elif style == "dups":
+        s = rng.integers(0, 500, n) * 100
+        e = s + rng.integers(0, 3, n) * 150  # zero-length and duplicates
+    elif style == "degenerate":
+        s = rng.integers(0, span, n)
+        e = s + rng.integers(-500, 2000, n)  # some start > end
+        e = np.maximum(e, 0)
+    else:
+        raise ValueError(style)
+    counts = np.bincount(chr_, minlength=n_chroms)
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
+    return offs, s.astype(np.uint32), e.astype(np.uint32), rng.permutation(n).astype(np.uint32)
+
+
+def _random_queries(rng, n_chroms, nq, degenerate=False):
+    qc = rng.integers(0, n_chroms + 2, nq).astype(np.uint32)  # ids >= n_chroms are unknown
+    qc[rng.random(nq) < 0.02] = 0xFFFFFFFF
+    qs = rng.integers(0, 210_000, nq)
+    qe = qs + rng.integers(1, 2500, nq)
+    if degenerate:
+        k = rng.random(nq)
+        qe = np.where(k < 0.1, qs, qe)          # empty
+        qe = np.where((k >= 0.1) & (k < 0.2), np.maximum(qs - rng.integers(1, 900, nq), 0), qe)  # reversed
+        qs = np.where(k > 0.97, 0xFFFFFFFF, qs)
+        qe = np.where(k > 0.985, 0xFFFFFFFF, qe)
+    return qc, qs.astype(np.uint32), qe.astype(np.uint32)
+
+
+@pytest.mark.parametrize("kind", ["bits", "ailist"])
+@pytest.mark.parametrize("style", ["peaks", "overlap", "nested", "dups", "degenerate"])
+def test_random_differential(ctx, kind, style):
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(f"{kind}/{style}".encode()))
+    n_chroms = 5
+    offs, s, e, v = _random_index(rng, n_chroms, 6000, style)
+    g, o = _both(ctx, kind, offs, s, e, v)
+    if kind == "ailist" and style == "nested":
+        assert g.info()["max_components"] >= 2
+    for degenerate in (False, True):
+        qc, qs, qe = _random_queries(rng, n_chroms, 5000, degenerate)
+        for m in (0, 1, 2, 50):
+            _assert_same_find(g, o, qc, qs, qe, m)
+        if kind == "bits":
+            assert np.array_equal(g.bits_count(qc, qs, qe), o.bits_count(qc, qs, qe))
+
+
+@pytest.mark.parametrize("kind", ["bits", "ailist"])
+def test_tokenize_files_unk_rule_and_ragged(ctx, kind):
+    rng = np.random.default_rng(11)
+    n_chroms = 4
+    offs, s, e, v = _random_index(rng, n_chroms, 3000, "overlap")
+    g, o = _both(ctx, kind, offs, s, e, v)
+    # ragged files: empty files, files with only misses (→ [unk]), files crossing tile boundaries
+    sizes = [0, 3, 0, 1500, 1, 0, 700, 2500, 0, 0, 5, 1024, 1023, 1025, 0]
+    qc_l, qs_l, qe_l = [], [], []
+    for i, k in enumerate(sizes):
+        qc, qs, qe = _random_queries(rng, n_chroms, k)
+        if i in (1, 4, 10):  # force misses
+            qc[:] = 0xFFFFFFFF
+        qc_l.append(qc); qs_l.append(qs); qe_l.append(qe)
+    qc, qs, qe = np.concatenate(qc_l), np.concatenate(qs_l), np.concatenate(qe_l)
+    fo = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    unk = 3000
+    g_off, g_ids = g.tokenize_files(fo, qc, qs, qe, unk)
+    o_off, o_ids = o.tokenize_files(fo, qc, qs, qe, unk)
+    assert np.array_equal(g_off, o_off)
+    assert np.array_equal(g_ids, o_ids)
+    assert (g_ids == unk).sum() >= 8  # the empty and all-miss files
+    # no files at all / no queries at all
+    g_off, g_ids = g.tokenize_files(np.zeros(1, np.uint64), qc[:0], qs[:0], qe[:0], unk)
+    assert list(g_off) == [0] and len(g_ids) == 0
+    g_off, g_ids = g.tokenize_files(np.zeros(4, np.uint64), qc[:0], qs[:0], qe[:0], unk)
+    assert list(g_off) == [0, 1, 2, 3] and list(g_ids) == [unk] * 3
+
+
+def test_output_capacity_rerun(ctx):
+    """Far more hits than the optimistic output capacity (n + n/4 + 1024): the host wrapper must re-run exactly."""
+    n = 4000
+    offs = np.array([0, n], dtype=np.uint64)
+    s = np.arange(n, dtype=np.uint32)
+    e = s + 5000
+    g, o = _both(ctx, "bits", offs, s, e)
+    nq = 300
+    qc = np.zeros(nq, np.uint32)
+    qs = np.arange(nq, dtype=np.uint32) * 10
+    qe = qs + 3000
+    _assert_same_find(g, o, qc, qs, qe)
+    fo = np.array([0, 100, 300], dtype=np.uint64)
+    g_off, g_ids = g.tokenize_files(fo, qc, qs, qe, n)
+    o_off, o_ids = o.tokenize_files(fo, qc, qs, qe, n)
+    assert np.array_equal(g_off, o_off) and np.array_equal(g_ids, o_ids)
+
+
+@pytest.mark.parametrize("kind,nested", [("bits", 0.0), ("ailist", 0.0), ("bits", 0.01), ("ailist", 0.01)])
+def test_synthetic_c2_shape_vs_oracle(ctx, kind, nested):
+    """The bench workload at 1/1000 scale: 100 k-region hg38 universe (optionally the nested C2n variant),
+    40 sorted files x 5 000 regions, 0.1 % unknown chromosomes."""
+    from gtars_b200 import synth
+    u = synth.make_universe(100_000, nested_frac=nested)
+    q = synth.make_query_files(u, 40, 5000, unknown_frac_ppm=1000)
+    offs = u["chrom_offsets"].numpy().astype(np.uint64)
+    s, e, v = (u[k].numpy().view(np.uint32) for k in ("g_start", "g_end", "g_val"))
+    g, o = _both(ctx, kind, offs, s, e, v)
+    qc, qs, qe = (q[k].numpy().view(np.uint32) for k in ("chr", "start", "end"))
+    fo = q["file_offsets"].numpy().astype(np.uint64)
+    g_off, g_ids = g.tokenize_files(fo, qc, qs, qe, u["unk_id"])
+    o_off, o_ids = o.tokenize_files(fo, qc, qs, qe, u["unk_id"])
+    assert np.array_equal(g_off, o_off)
+    assert np.array_equal(g_ids, o_ids)
+    assert np.array_equal(g.count(qc, qs, qe), o.count(qc, qs, qe))
+    if nested and kind == "ailist":
+        assert g.info()["max_components"] >= 2
