@@ -80,7 +80,45 @@ void gtgpu_ctx::pinned_put(PinnedBlock b) {
     }
 }
 
+void gtgpu_ctx::time_begin() {
+    if (!timing || ev_used >= 256) return;
+    if (ev_begin.size() <= ev_used) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        ev_begin.push_back(a);
+        ev_end.push_back(b);
+    }
+    cudaEventRecord(ev_begin[ev_used], stream);
+}
+
+void gtgpu_ctx::time_end() {
+    if (!timing || ev_used >= 256) return;
+    cudaEventRecord(ev_end[ev_used], stream);
+    ev_used++;
+}
+
 extern "C" {
+
+int32_t gtgpu_timing_enable(gtgpu_ctx* ctx, int32_t on) {
+    if (!ctx) return fail(GTGPU_ERR_INVALID, "timing_enable: null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->timing = on != 0;
+    ctx->ev_used = 0;
+    return GTGPU_OK;
+}
+
+int32_t gtgpu_timing_read(gtgpu_ctx* ctx, float* out_ms, uint32_t cap, uint32_t* out_n) {
+    if (!ctx || !out_n || (cap && !out_ms)) return fail(GTGPU_ERR_INVALID, "timing_read: null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    GT_CUDA(cudaSetDevice(ctx->device));
+    GT_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < ctx->ev_used && i < cap; ++i)
+        GT_CUDA(cudaEventElapsedTime(out_ms + i, ctx->ev_begin[i], ctx->ev_end[i]));
+    *out_n = ctx->ev_used;
+    ctx->ev_used = 0;
+    return GTGPU_OK;
+}
 
 const char* gtgpu_last_error(void) { return g_last_error.c_str(); }
 const char* gtgpu_version(void) { return "gtars-b200 0.1 (sm_100a)"; }
@@ -134,6 +172,8 @@ int32_t gtgpu_shutdown(gtgpu_ctx* ctx) {
     for (auto& b : ctx->scratch)
         if (b.ptr) cudaFree(b.ptr);
     for (auto& b : ctx->pinned_free) cudaFreeHost(b.ptr);
+    for (auto e : ctx->ev_begin) cudaEventDestroy(e);
+    for (auto e : ctx->ev_end) cudaEventDestroy(e);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_in);

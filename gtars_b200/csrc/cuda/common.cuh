@@ -93,6 +93,11 @@ struct gtgpu_ctx {
     std::vector<gtgpu::DevBuffer> scratch;       // grow-only device scratch, indexed by role
     std::vector<gtgpu::PinnedBlock> pinned_free;  // cache of pinned result blocks
     uint64_t* h_scalars = nullptr;                // small pinned mailbox
+    bool timing = false;                          // bracket dominant kernels with events
+    std::vector<cudaEvent_t> ev_begin, ev_end;
+    uint32_t ev_used = 0;
+    void time_begin();
+    void time_end();
     int32_t scratch_get(int role, size_t bytes, void** out);
     int32_t pinned_get(size_t bytes, gtgpu::PinnedBlock* out);
     void pinned_put(gtgpu::PinnedBlock b);

@@ -141,6 +141,7 @@ int32_t launch_count(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const u
     gtgpu_ctx* ctx = ix->ctx;
     uint64_t blocks_needed = (n + 255) / 256;
     int grid = (int)std::min<uint64_t>(blocks_needed, (uint64_t)ctx->sm_count * 32);
+    ctx->time_begin();
     switch (mode) {
         case COUNT_U32:
             count_kernel<COUNT_U32><<<grid, 256, 0, ctx->stream>>>(ix->view, n, d_chr, d_start, d_end, min_overlap, d_out);
@@ -152,6 +153,7 @@ int32_t launch_count(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const u
             count_kernel<COUNT_BITS_RAW_U64><<<grid, 256, 0, ctx->stream>>>(ix->view, n, d_chr, d_start, d_end, min_overlap, d_out);
             break;
     }
+    ctx->time_end();
     ctx->launches++;
     GT_CUDA(cudaGetLastError());
     return GTGPU_OK;
@@ -436,9 +438,11 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * blocks_per_sm);
+    ctx->time_begin();
     fused_find_kernel<FUSED_BLOCK, FUSED_ITEMS><<<grid, FUSED_BLOCK, 0, st>>>(
         ix->view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end, min_overlap, vec_ok, d_out_ids,
         ids_capacity, d_out_offsets, d_out_file_tok, ws, d_base, d_total_out, d_errflag);
+    ctx->time_end();
     ctx->launches++;
     GT_CUDA(cudaGetLastError());
     return GTGPU_OK;

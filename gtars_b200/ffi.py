@@ -26,6 +26,8 @@ SIGNATURES = {
     "gtgpu_shutdown": (_i32, [_vp]),
     "gtgpu_synchronize": (_i32, [_vp]),
     "gtgpu_launch_count": (_i32, [_vp, _vp]),
+    "gtgpu_timing_enable": (_i32, [_vp, _i32]),
+    "gtgpu_timing_read": (_i32, [_vp, _vp, _u32, _vp]),
     "gtgpu_host_alloc": (_i32, [_u64, _vp]),
     "gtgpu_host_free": (_i32, [_vp]),
     "gtgpu_buf_data": (_vp, [_vp]),
@@ -155,6 +157,15 @@ class Context:
         n = C.c_uint64(0)
         check(lib().gtgpu_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def timing_enable(self, on=True):
+        check(lib().gtgpu_timing_enable(self._h, 1 if on else 0))
+
+    def timing_read(self, cap=256):
+        ms = (C.c_float * cap)()
+        n = C.c_uint32(0)
+        check(lib().gtgpu_timing_read(self._h, ms, cap, C.byref(n)))
+        return [ms[i] for i in range(min(cap, n.value))]
 
     def unk_rule_dev(self, n_files, d_raw_tok, d_raw_ids, unk_id, d_out_tok, d_out_ids, d_n_empty):
         check(lib().gtgpu_unk_rule_dev(self._h, n_files, d_raw_tok, d_raw_ids, unk_id, d_out_tok, d_out_ids, d_n_empty))

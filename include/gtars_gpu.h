@@ -59,6 +59,13 @@ int32_t gtgpu_synchronize(gtgpu_ctx* ctx);
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 int32_t gtgpu_launch_count(gtgpu_ctx* ctx, uint64_t* out_n);
 
+/* Kernel timing: when enabled, every launch of a dominant kernel (fused find / count / IGD count) is bracketed by
+ * CUDA events on the ctx stream (up to 256 launches are kept, then recording stops).  gtgpu_timing_read
+ * synchronises the stream, writes the elapsed milliseconds of the first min(cap, recorded) launches, returns how
+ * many were recorded in *out_n and clears the log. */
+int32_t gtgpu_timing_enable(gtgpu_ctx* ctx, int32_t on);
+int32_t gtgpu_timing_read(gtgpu_ctx* ctx, float* out_ms, uint32_t cap, uint32_t* out_n);
+
 /* pinned host memory for caller-side SoA arrays */
 int32_t gtgpu_host_alloc(uint64_t bytes, void** out_ptr);
 int32_t gtgpu_host_free(void* ptr);
