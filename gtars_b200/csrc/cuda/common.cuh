@@ -53,7 +53,32 @@ struct ChromMeta {    // 32 bytes
     uint32_t lut_ce, nb_ce;       // LUT over the chromosome's independently sorted ends
 };
 
+// Bin table (the fast path of find/tokenize).  Bin b of a chromosome covers positions [b << bt_shift, (b+1) << bt_shift)
+// and lists, in segment order, every interval that touches it.  A query whose [start,end) lies in one or two bins
+// finds all its candidates, in reference order, with one 16-byte load per bin (two when the bin holds two
+// candidates); an interval spanning two bins is taken from the first and skipped in the second (start < bin start).
+// Bins with more than two candidates, chromosomes with several AIList components or with start > end intervals,
+// wide or degenerate queries all fall back to the LUT + walk path below, so results never depend on the table.
+struct BinA {            // 16 bytes
+    uint32_t n;          // 0, 1, 2 candidates inline; BT_OVERFLOW = use the generic path
+    uint32_t start0, end0, val0;
+};
+struct BinB {            // 16 bytes, only read when n == 2
+    uint32_t start1, end1, val1, pad;
+};
+#define BT_OVERFLOW 0xFFFFFFFFu
+#define BT_GENERIC_CHROM 0x80000000u  // in ChromBT.n_bins: this chromosome always takes the generic path
+
+struct ChromBT {         // 8 bytes
+    uint32_t off;        // first bin record of this chromosome
+    uint32_t n_bins;     // bins beyond this hold nothing; BT_GENERIC_CHROM = no table
+};
+
 struct IndexView {
+    const ChromBT* chrom_bt;
+    const BinA* bt_a;
+    const BinB* bt_b;
+    uint32_t bt_shift;
     const ChromMeta* chroms;
     const SegMeta* segs;
     const uint32_t* starts;
@@ -116,6 +141,7 @@ struct gtgpu_index {
     gtgpu::IndexView view{};
     std::vector<void*> allocs;
     uint64_t n_intervals = 0, n_segments = 0, device_bytes = 0, max_components = 0;
+    uint64_t bt_bins = 0, bt_overflow_bins = 0;
 };
 
 namespace gtgpu {
@@ -127,9 +153,10 @@ enum ScratchRole {
 };
 
 // kernels.cu
-constexpr int FUSED_BLOCK = 256;
-constexpr int FUSED_ITEMS = 4;
-constexpr int FUSED_TILE = FUSED_BLOCK * FUSED_ITEMS;
+constexpr int FUSED_BLOCK = 256;             // 8 warps per tile
+constexpr int FUSED_ROWS = 4;                // queries per thread per tile (striped inside each warp)
+constexpr int FUSED_TILE = FUSED_BLOCK * FUSED_ROWS;
+constexpr int CHROM_CACHE = 256;             // per-chromosome table entries staged in shared memory
 
 enum CountMode { COUNT_U32 = 0, COUNT_ANY_U8 = 1, COUNT_BITS_RAW_U64 = 2 };
 

@@ -185,6 +185,78 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
     }
     if (lut.size() >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "index_build: LUT too large");
 
+    // ---- 3b. bin table (fast path of find/tokenize; see common.cuh) ------------------------------------------
+    std::vector<ChromBT> chrom_bt(n_chroms);
+    std::vector<BinA> bt_a;
+    std::vector<BinB> bt_b;
+    uint32_t bt_shift = 0;
+    uint64_t bt_overflow = 0;
+    {
+        std::vector<uint64_t> cover_end(n_chroms, 0);  // exclusive end of the positions the chromosome's intervals touch
+        std::vector<char> eligible(n_chroms, 0);
+        for (uint32_t c = 0; c < n_chroms; ++c) {
+            if (chroms[c].seg_end - chroms[c].seg_begin != 1) continue;
+            const SegMeta& m = seg_meta[chroms[c].seg_begin];
+            bool ok = true;
+            uint64_t ce = 0;
+            for (uint32_t i = m.off; i < m.off + m.len; ++i) {
+                if (h_starts[i] > h_ends[i]) { ok = false; break; }
+                ce = std::max<uint64_t>(ce, std::max<uint64_t>(h_ends[i], (uint64_t)h_starts[i] + 1));
+            }
+            eligible[c] = ok;
+            cover_end[c] = ok ? ce : 0;
+        }
+        auto total_bins = [&](uint32_t sh) {
+            uint64_t t = 0;
+            for (uint32_t c = 0; c < n_chroms; ++c)
+                if (cover_end[c]) t += ((cover_end[c] - 1) >> sh) + 1;
+            return t;
+        };
+        uint64_t bt_budget = std::max<uint64_t>(2 * total, 4096);
+        uint64_t bt_cap = 3ull << 20;
+        if (const char* env = getenv("GTGPU_BT_MAX_BINS")) bt_cap = strtoull(env, nullptr, 10);
+        bt_budget = std::min(bt_budget, bt_cap);
+        while (bt_shift < 31 && total_bins(bt_shift) > bt_budget) ++bt_shift;
+        if (const char* env = getenv("GTGPU_BT_SHIFT")) bt_shift = (uint32_t)std::min(31, std::max(0, atoi(env)));
+        // A table only pays off while most bins hold at most two candidates: skip it for dense databases.
+        bool enabled = bt_cap > 0 && total_bins(bt_shift) <= (64ull << 20) && 2 * total <= 3 * total_bins(bt_shift);
+        uint64_t pos = 0;
+        for (uint32_t c = 0; c < n_chroms; ++c) {
+            chrom_bt[c].off = (uint32_t)pos;
+            if (chroms[c].seg_end == chroms[c].seg_begin) {
+                chrom_bt[c].n_bins = 0;  // absent chromosome: nothing can hit
+            } else if (!eligible[c] || !enabled) {
+                chrom_bt[c].n_bins = BT_GENERIC_CHROM;
+            } else {
+                uint64_t nb = ((cover_end[c] - 1) >> bt_shift) + 1;
+                chrom_bt[c].n_bins = (uint32_t)nb;
+                pos += nb;
+            }
+        }
+        bt_a.assign(pos, BinA{0, 0, 0, 0});
+        bt_b.assign(pos, BinB{0, 0, 0, 0});
+        for (uint32_t c = 0; c < n_chroms; ++c) {
+            if (chrom_bt[c].n_bins == 0 || chrom_bt[c].n_bins == BT_GENERIC_CHROM) continue;
+            const SegMeta& m = seg_meta[chroms[c].seg_begin];
+            for (uint32_t i = m.off; i < m.off + m.len; ++i) {
+                uint64_t last_pos = std::max<uint64_t>(h_ends[i], (uint64_t)h_starts[i] + 1) - 1;
+                uint64_t b0 = h_starts[i] >> bt_shift, b1 = last_pos >> bt_shift;
+                for (uint64_t b = b0; b <= b1; ++b) {
+                    BinA& a = bt_a[chrom_bt[c].off + b];
+                    if (a.n == 0) {
+                        a.n = 1; a.start0 = h_starts[i]; a.end0 = h_ends[i]; a.val0 = h_vals[i];
+                    } else if (a.n == 1) {
+                        a.n = 2;
+                        bt_b[chrom_bt[c].off + b] = BinB{h_starts[i], h_ends[i], h_vals[i], 0};
+                    } else if (a.n == 2) {
+                        a.n = BT_OVERFLOW;
+                        ++bt_overflow;
+                    }
+                }
+            }
+        }
+    }
+
     // ---- 4. upload ---------------------------------------------------------------------------------------------
     gtgpu_index* ix = new gtgpu_index();
     ix->ctx = ctx;
@@ -195,6 +267,12 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
     IndexView& v = ix->view;
     int32_t st = GTGPU_OK;
     auto up = [&](auto& vec, auto** dst) { if (st == GTGPU_OK) st = upload(ix, vec, dst); };
+    up(chrom_bt, &v.chrom_bt);
+    up(bt_a, &v.bt_a);
+    up(bt_b, &v.bt_b);
+    v.bt_shift = bt_shift;
+    ix->bt_bins = bt_a.size();
+    ix->bt_overflow_bins = bt_overflow;
     up(chroms, &v.chroms);
     up(seg_meta, &v.segs);
     up(h_starts, &v.starts);
@@ -224,7 +302,7 @@ extern "C" int32_t gtgpu_index_free(gtgpu_index* ix) {
     return GTGPU_OK;
 }
 
-extern "C" int32_t gtgpu_index_info(const gtgpu_index* ix, uint64_t info[6]) {
+extern "C" int32_t gtgpu_index_info(const gtgpu_index* ix, uint64_t info[10]) {
     if (!ix || !info) return fail(GTGPU_ERR_INVALID, "index_info: null argument");
     info[0] = ix->n_intervals;
     info[1] = ix->n_segments;
@@ -232,5 +310,9 @@ extern "C" int32_t gtgpu_index_info(const gtgpu_index* ix, uint64_t info[6]) {
     info[3] = ix->view.shift;
     info[4] = ix->max_components;
     info[5] = ix->view.proper;
+    info[6] = ix->bt_bins;
+    info[7] = ix->bt_overflow_bins;
+    info[8] = ix->view.bt_shift;
+    info[9] = 0;
     return GTGPU_OK;
 }

@@ -160,12 +160,17 @@ int32_t launch_count(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const u
 }
 
 // ================================================================================================================
-// fused find: count → block scan → decoupled look-back → emit
+// fused find: count → scan → decoupled look-back across tiles → emit, one pass over the queries
 // ================================================================================================================
+// A tile is FUSED_BLOCK x ROWS consecutive queries.  Inside a tile each WARP owns 32 x ROWS consecutive queries in
+// a striped layout (lane l holds queries l, l+32, …), so every query load and every id store of a row is one fully
+// coalesced 128-byte access.  Tiles are handed out in order by an atomic counter (persistent grid), which is what
+// makes the look-back deadlock-free.  The look-back is BLOCK-wide: all 256 threads inspect the 256 preceding tiles
+// in one L2 round trip, because at >1e11 queries/s tiles retire faster than a 32-wide window can follow
+// ("look-back arithmetic").
 #define ST_FLAG_AGG (1ull << 62)
 #define ST_FLAG_PREFIX (2ull << 62)
 #define ST_MASK ((1ull << 62) - 1)
-#define MULTI_SEG 0xFFFFFFFFu
 
 struct FusedWorkspace {
     uint64_t* status;      // [n_tiles] flag<<62 | value
@@ -177,7 +182,7 @@ static inline uint64_t n_tiles_for(uint64_t n) { return (n + FUSED_TILE - 1) / F
 
 size_t fused_workspace_bytes(uint64_t n) {
     uint64_t t = n_tiles_for(n);
-    return (size_t)(t * 8 + ((t * 4 + 7) / 8) * 8 + 64);
+    return (size_t)(t * 8 + ((t * 4 + 15) / 16) * 16 + 64);
 }
 
 static FusedWorkspace carve(void* ws, uint64_t n) {
@@ -185,7 +190,7 @@ static FusedWorkspace carve(void* ws, uint64_t n) {
     FusedWorkspace w;
     w.status = reinterpret_cast<uint64_t*>(ws);
     w.tile_file = reinterpret_cast<uint32_t*>(w.status + t);
-    w.counter = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + t * 8 + ((t * 4 + 7) / 8) * 8);
+    w.counter = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + t * 8 + ((t * 4 + 15) / 16) * 16);
     return w;
 }
 
@@ -203,196 +208,326 @@ __global__ void fill_from_base_kernel(uint64_t count, uint64_t* __restrict__ out
     if (i < count) out[i] = base ? *base : 0;
 }
 
-template <int BLOCK, int ITEMS>
-__global__ void __launch_bounds__(BLOCK)
+__device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+__device__ __forceinline__ bool cand_hit(uint32_t cs, uint32_t ce, uint32_t s, uint32_t e, int32_t min_bp) {
+    bool h = cs < e && ce > s;
+    if (min_bp > 1) h = h && ((int64_t)min(e, ce) - (int64_t)max(s, cs) >= (int64_t)min_bp);
+    return h;
+}
+
+// Emits every hit of one query through the generic LUT + walk path, in reference order; returns the count.
+__device__ __noinline__ uint32_t emit_query_walk(const IndexView& ix, uint32_t c, uint32_t s, uint32_t e, int32_t min_bp,
+                                                 uint32_t* __restrict__ out_ids, uint64_t pos, uint64_t capacity) {
+    if (c >= ix.n_chroms) return 0;
+    const uint2 sr = __ldg(reinterpret_cast<const uint2*>(ix.chroms + c));
+    uint32_t written = 0;
+    for (uint32_t si = sr.x; si < sr.y; ++si) {
+        SegMeta m = load_seg(ix, si);
+        uint32_t l, u;
+        seg_range(ix, m, s, e, l, u);
+        const bool mono = m.mono != 0;
+        if (!ix.descending) {
+            for (uint32_t i = l; i < u; ++i)
+                if (is_hit(ix, i, s, e, min_bp, mono)) {
+                    if (pos + written < capacity) out_ids[pos + written] = __ldg(ix.vals + i);
+                    ++written;
+                }
+        } else {
+            for (uint32_t i = u; i > l; --i)
+                if (is_hit(ix, i - 1, s, e, min_bp, mono)) {
+                    if (pos + written < capacity) out_ids[pos + written] = __ldg(ix.vals + i - 1);
+                    ++written;
+                }
+        }
+    }
+    return written;
+}
+
+__device__ __noinline__ uint32_t count_query_walk_noinline(const IndexView& ix, uint32_t c, uint32_t s, uint32_t e,
+                                                           int32_t min_bp) {
+    return count_query_walk(ix, c, s, e, min_bp);
+}
+
+__device__ __forceinline__ uint64_t ld_status(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Per-thread result of resolving ROWS queries of one tile, kept in registers while the NEXT tile is resolved
+// (software pipeline, lag 1): by the time a tile's look-back runs, its predecessors published their aggregates a
+// whole resolve phase ago, so the look-back is one L2 round trip and (almost) never spins.
+template <int ROWS>
+struct TileState {
+    uint32_t tile;
+    uint32_t cnt[ROWS], v0[ROWS], v1[ROWS], off[ROWS];
+    uint32_t slow;
+    uint32_t warp_excl, tile_agg;
+};
+
+template <int ROWS>
+__global__ void __launch_bounds__(FUSED_BLOCK)
 fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, const uint64_t* __restrict__ file_offsets,
                   const uint32_t* __restrict__ chr, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
-                  int32_t min_bp, int vec_ok, uint32_t* __restrict__ out_ids, uint64_t capacity,
-                  uint64_t* __restrict__ out_offsets, uint64_t* __restrict__ out_file_tok, FusedWorkspace ws,
-                  const uint64_t* __restrict__ d_base, uint64_t* __restrict__ d_total, uint32_t* __restrict__ d_err) {
-    constexpr int TILE = BLOCK * ITEMS;
-    constexpr int WARPS = BLOCK / 32;
-    static_assert(ITEMS == 4, "query loads are written for one uint4 per array per thread");
-    __shared__ uint32_t s_qoff[TILE + 1];
-    __shared__ uint32_t s_warp[WARPS];
-    __shared__ uint64_t s_tile_excl;
-    __shared__ uint32_t s_tile;
+                  int32_t min_bp, uint32_t* __restrict__ out_ids, uint64_t capacity, uint64_t* __restrict__ out_offsets,
+                  uint64_t* __restrict__ out_file_tok, FusedWorkspace ws, const uint64_t* __restrict__ d_base,
+                  uint64_t* __restrict__ d_total, uint32_t* __restrict__ d_err) {
+    constexpr int WARPS = FUSED_BLOCK / 32;
+    constexpr int WTILE = 32 * ROWS;          // queries per warp
+    constexpr int TILE = FUSED_BLOCK * ROWS;  // queries per block tile
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    constexpr uint32_t NO_TILE = 0xFFFFFFFFu;
+    __shared__ uint2 s_chrom[CHROM_CACHE];
+    __shared__ uint32_t s_wtot[2][WARPS];      // per-warp hit totals, double-buffered by iteration parity
+    __shared__ uint64_t s_lb_sum[2][WARPS];    // look-back partial sums per 32-tile window
+    __shared__ uint32_t s_lb_p[2][WARPS];      // 1 when the window contains an inclusive prefix
+    __shared__ uint32_t s_tile[2];             // tile index for this / the next iteration
+    __shared__ uint32_t s_qoff[TILE + 1];      // per-query offsets, only filled for tiles with a file boundary
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        const uint32_t nc = min(ix.n_chroms, (uint32_t)CHROM_CACHE);
+        for (uint32_t i = tid; i < nc; i += FUSED_BLOCK) s_chrom[i] = __ldg(reinterpret_cast<const uint2*>(ix.chrom_bt + i));
+        if (tid == 0) s_tile[0] = atomicAdd(ws.counter, 1u);
+    }
+    __syncthreads();
+
     const uint64_t base = d_base ? *d_base : 0;
-    volatile uint64_t* status = ws.status;
+    uint64_t* status = ws.status;
+    const uint32_t shift = ix.bt_shift;
 
-    for (;;) {
-        if (tid == 0) s_tile = atomicAdd(ws.counter, 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= n_tiles) break;
-        const uint64_t tile_start = (uint64_t)tile * TILE;
-        const uint32_t first = tid * ITEMS;
+    TileState<ROWS> prev;
+    prev.tile = NO_TILE;
 
-        // ---- load 4 queries per thread -----------------------------------------------------------------------
-        uint32_t qc[ITEMS], qs[ITEMS], qe[ITEMS];
-        if (vec_ok && tile_start + TILE <= n) {
-            uint4 c4 = __ldcs(reinterpret_cast<const uint4*>(chr + tile_start) + tid);
-            uint4 s4 = __ldcs(reinterpret_cast<const uint4*>(start + tile_start) + tid);
-            uint4 e4 = __ldcs(reinterpret_cast<const uint4*>(end + tile_start) + tid);
-            qc[0] = c4.x; qc[1] = c4.y; qc[2] = c4.z; qc[3] = c4.w;
-            qs[0] = s4.x; qs[1] = s4.y; qs[2] = s4.z; qs[3] = s4.w;
-            qe[0] = e4.x; qe[1] = e4.y; qe[2] = e4.z; qe[3] = e4.w;
-        } else {
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t par = it & 1;
+        uint32_t tile = s_tile[par];
+        if (tile >= n_tiles) tile = NO_TILE;
+        TileState<ROWS> cur;
+        cur.tile = tile;
+        cur.slow = 0;
+
+        if (tile != NO_TILE) {
+            const uint64_t warp_start = (uint64_t)tile * TILE + (uint64_t)warp * WTILE;
+            // ---- queries: ROWS coalesced rows per array ---------------------------------------------------------
+            uint32_t qc[ROWS], qs[ROWS], qe[ROWS];
 #pragma unroll
-            for (int k = 0; k < ITEMS; ++k) {
-                uint64_t q = tile_start + first + k;
-                bool ok = q < n;
-                qc[k] = ok ? __ldg(chr + q) : 0xFFFFFFFFu;
-                qs[k] = ok ? __ldg(start + q) : 0;
-                qe[k] = ok ? __ldg(end + q) : 0;
+            for (int k = 0; k < ROWS; ++k) {
+                const uint64_t q = warp_start + 32 * k + lane;
+                const bool ok = q < n;
+                qc[k] = ok ? __ldcs(chr + q) : 0xFFFFFFFFu;
+                qs[k] = ok ? __ldcs(start + q) : 0;
+                qe[k] = ok ? __ldcs(end + q) : 0;
             }
-        }
-
-        // ---- resolve: candidate range + hit count per query -----------------------------------------------------
-        uint32_t lo[ITEMS], ub[ITEMS], cnt[ITEMS];
-        uint32_t mono_bits = 0;
+            // ---- resolve through the bin table: first bin of every query -----------------------------------------
+            uint32_t two = 0;  // bit k: query k also has to look at a second bin
+            uint32_t boff[ROWS];
+            uint4 A[ROWS];
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            lo[k] = ub[k] = cnt[k] = 0;
-            if (qc[k] < ix.n_chroms) {
-                const uint2 sr = __ldg(reinterpret_cast<const uint2*>(ix.chroms + qc[k]));
-                if (sr.y - sr.x == 1) {
-                    SegMeta m = load_seg(ix, sr.x);
-                    seg_range(ix, m, qs[k], qe[k], lo[k], ub[k]);
-                    cnt[k] = count_range(ix, lo[k], ub[k], qs[k], qe[k], min_bp, m.mono != 0);
-                    mono_bits |= (m.mono != 0) << k;
-                } else if (sr.y > sr.x) {
-                    cnt[k] = count_query_walk(ix, qc[k], qs[k], qe[k], min_bp);
-                    ub[k] = MULTI_SEG;
-                }
-            }
-        }
-
-        // ---- block exclusive scan of per-thread totals ---------------------------------------------------------
-        uint64_t wide = (uint64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3];
-        uint32_t thread_total = (uint32_t)wide;
-        uint32_t incl = thread_total;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        // 64-bit block total, only to detect tiles whose local offsets would not fit 32 bits.
-        uint64_t wsum = wide;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) wsum += __shfl_down_sync(0xFFFFFFFFu, wsum, d);
-        if (lane == 0 && wsum > 0xFFFFFFFFull) atomicExch(d_err, 1u);
-        __syncthreads();
-        uint32_t warp_excl = 0, tile_agg = 0;
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            uint32_t t = s_warp[w];
-            if (w < warp) warp_excl += t;
-            tile_agg += t;
-        }
-        uint32_t running = warp_excl + incl - thread_total;
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            s_qoff[first + k] = running;
-            running += cnt[k];
-        }
-        if (tid == BLOCK - 1) s_qoff[TILE] = tile_agg;
-
-        // ---- decoupled look-back (warp 0): exclusive prefix of this tile ----------------------------------------
-        if (warp == 0) {
-            if (lane == 0) status[tile] = ST_FLAG_AGG | (uint64_t)tile_agg;
-            uint64_t excl = 0;
-            int64_t j = (int64_t)tile - 1 - lane;
-            for (;;) {
-                uint64_t v = j >= 0 ? status[j] : ST_FLAG_PREFIX;
-                while (__any_sync(0xFFFFFFFFu, (v >> 62) == 0)) {
-                    if ((v >> 62) == 0) v = status[j];
-                }
-                uint32_t pmask = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
-                uint64_t val = v & ST_MASK;
-                if (pmask && lane > (__ffs(pmask) - 1)) val = 0;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xFFFFFFFFu, val, d);
-                val = __shfl_sync(0xFFFFFFFFu, val, 0);
-                excl += val;
-                if (pmask) break;
-                j -= 32;
-            }
-            if (lane == 0) {
-                status[tile] = ST_FLAG_PREFIX | (excl + tile_agg);
-                s_tile_excl = excl;
-                if (tile == n_tiles - 1) {
-                    *d_total = base + excl + tile_agg;
-                    if (out_offsets) out_offsets[n] = base + excl + tile_agg;
-                }
-            }
-        }
-        __syncthreads();
-        const uint64_t tile_base = base + s_tile_excl;
-
-        // ---- emit --------------------------------------------------------------------------------------------------
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            uint64_t q = tile_start + first + k;
-            uint64_t pos = tile_base + s_qoff[first + k];
-            if (out_offsets && q < n) out_offsets[q] = pos;
-            if (cnt[k] == 0) continue;
-            const uint32_t s = qs[k], e = qe[k];
-            if (ub[k] != MULTI_SEG) {
-                const bool mono = (mono_bits >> k) & 1;
-                if (!ix.descending) {
-                    for (uint32_t i = lo[k]; i < ub[k]; ++i)
-                        if (is_hit(ix, i, s, e, min_bp, mono)) {
-                            if (pos < capacity) out_ids[pos] = __ldg(ix.vals + i);
-                            ++pos;
-                        }
-                } else {
-                    for (uint32_t i = ub[k]; i > lo[k]; --i)
-                        if (is_hit(ix, i - 1, s, e, min_bp, mono)) {
-                            if (pos < capacity) out_ids[pos] = __ldg(ix.vals + i - 1);
-                            ++pos;
-                        }
-                }
-            } else {
-                const uint2 sr = __ldg(reinterpret_cast<const uint2*>(ix.chroms + qc[k]));
-                for (uint32_t si = sr.x; si < sr.y; ++si) {
-                    SegMeta m = load_seg(ix, si);
-                    uint32_t l, u;
-                    seg_range(ix, m, s, e, l, u);
-                    const bool mono = m.mono != 0;
-                    if (!ix.descending) {
-                        for (uint32_t i = l; i < u; ++i)
-                            if (is_hit(ix, i, s, e, min_bp, mono)) {
-                                if (pos < capacity) out_ids[pos] = __ldg(ix.vals + i);
-                                ++pos;
-                            }
-                    } else {
-                        for (uint32_t i = u; i > l; --i)
-                            if (is_hit(ix, i - 1, s, e, min_bp, mono)) {
-                                if (pos < capacity) out_ids[pos] = __ldg(ix.vals + i - 1);
-                                ++pos;
-                            }
+            for (int k = 0; k < ROWS; ++k) {
+                cur.cnt[k] = 0; cur.v0[k] = 0; cur.v1[k] = 0; boff[k] = 0;
+                A[k] = make_uint4(0, 0, 0, 0);
+                const uint32_t c = qc[k];
+                if (c < ix.n_chroms) {
+                    const uint2 cb = c < CHROM_CACHE ? s_chrom[c] : __ldg(reinterpret_cast<const uint2*>(ix.chrom_bt + c));
+                    const uint32_t s = qs[k], e = qe[k];
+                    const uint32_t b1 = s >> shift, b2 = (e - 1) >> shift;
+                    if (cb.y == BT_GENERIC_CHROM || s >= e || b2 - b1 > 1) {
+                        cur.slow |= 1u << k;
+                    } else if (b1 < cb.y) {
+                        boff[k] = cb.x + b1;
+                        A[k] = ldg128(ix.bt_a + boff[k]);
+                        if (b2 != b1 && b2 < cb.y) two |= 1u << k;
                     }
                 }
             }
-        }
-
-        // ---- file boundaries that fall into this tile: raw token offset of each file's first query -------------
-        if (out_file_tok) {
-            uint32_t mark = ws.tile_file[tile];
-            if (mark != 0) {
-                const uint64_t limit = (tile == n_tiles - 1) ? n + 1 : tile_start + TILE;
-                for (uint64_t f = (uint64_t)(0xFFFFFFFFu - mark) + tid; f <= n_files; f += BLOCK) {
-                    uint64_t qi = file_offsets[f];
-                    if (qi >= limit) break;
-                    out_file_tok[f] = tile_base + s_qoff[qi - tile_start];
+#pragma unroll
+            for (int k = 0; k < ROWS; ++k) {
+                const uint32_t s = qs[k], e = qe[k];
+                const uint32_t nA = A[k].x;
+                if (nA == BT_OVERFLOW) {
+                    cur.slow |= 1u << k;
+                } else if (nA != 0) {
+                    if (cand_hit(A[k].y, A[k].z, s, e, min_bp)) { cur.v0[k] = A[k].w; cur.cnt[k] = 1; }
+                    if (nA == 2) {
+                        const uint4 B = ldg128(ix.bt_b + boff[k]);
+                        if (cand_hit(B.x, B.y, s, e, min_bp)) {
+                            if (cur.cnt[k] == 0) cur.v0[k] = B.z; else cur.v1[k] = B.z;
+                            cur.cnt[k]++;
+                        }
+                    }
                 }
             }
+            // ---- second bin (queries straddling a bin boundary): skip candidates already seen in the first bin --
+            if (__any_sync(FULL, two != 0)) {
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k) {
+                    if (((two >> k) & 1) && !((cur.slow >> k) & 1)) {
+                        const uint32_t s = qs[k], e = qe[k];
+                        const uint32_t bstart = ((e - 1) >> shift) << shift;
+                        const uint4 A2 = ldg128(ix.bt_a + boff[k] + 1);
+                        if (A2.x == BT_OVERFLOW) {
+                            cur.slow |= 1u << k;
+                        } else if (A2.x != 0) {
+                            uint32_t extra[2];
+                            int ne = 0;
+                            if (A2.y >= bstart && cand_hit(A2.y, A2.z, s, e, min_bp)) extra[ne++] = A2.w;
+                            if (A2.x == 2) {
+                                const uint4 B2 = ldg128(ix.bt_b + boff[k] + 1);
+                                if (B2.x >= bstart && cand_hit(B2.x, B2.y, s, e, min_bp)) extra[ne++] = B2.z;
+                            }
+                            if (cur.cnt[k] + ne > 2) {
+                                cur.slow |= 1u << k;  // more hits than the two value registers: re-walk generically
+                            } else {
+                                for (int j = 0; j < ne; ++j) {
+                                    if (cur.cnt[k] == 0) cur.v0[k] = extra[j]; else cur.v1[k] = extra[j];
+                                    cur.cnt[k]++;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // ---- generic path counts -----------------------------------------------------------------------------------
+            if (__any_sync(FULL, cur.slow != 0)) {
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k)
+                    if ((cur.slow >> k) & 1) cur.cnt[k] = count_query_walk_noinline(ix, qc[k], qs[k], qe[k], min_bp);
+            }
+            // ---- warp scan: exclusive offset of every query inside the warp's slice -----------------------------------
+            uint32_t warp_total = 0;
+            uint64_t wide = 0;
+#pragma unroll
+            for (int k = 0; k < ROWS; ++k) {
+                uint32_t incl = cur.cnt[k];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t t = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                cur.off[k] = warp_total + incl - cur.cnt[k];
+                warp_total += __shfl_sync(FULL, incl, 31);
+                wide += cur.cnt[k];
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) wide += __shfl_down_sync(FULL, wide, d);
+            if (lane == 0) {
+                s_wtot[par][warp] = warp_total;
+                if (wide > 0x1FFFFFFFull) atomicExch(d_err, 1u);  // keeps every tile-local offset inside 32 bits
+            }
         }
-        __syncthreads();  // s_qoff / s_tile are reused by the next tile
+        __syncthreads();  // B2: warp totals of `cur` visible; s_tile[par] consumed by everyone
+
+        if (tile != NO_TILE) {
+            uint32_t warp_excl = 0, tile_agg = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t t = s_wtot[par][w];
+                if (w < (int)warp) warp_excl += t;
+                tile_agg += t;
+            }
+            cur.warp_excl = warp_excl;
+            cur.tile_agg = tile_agg;
+            if (tid == 0) {
+                st_status(status + tile, ST_FLAG_AGG | (uint64_t)tile_agg);
+                s_tile[par ^ 1] = atomicAdd(ws.counter, 1u);
+            }
+        } else if (tid == 0) {
+            s_tile[par ^ 1] = NO_TILE;
+        }
+
+        if (prev.tile != NO_TILE) {
+            // ---- block-wide decoupled look-back for the PREVIOUS tile: warp w inspects 32 predecessors ---------------
+            uint64_t excl = 0;
+            for (int64_t win = (int64_t)prev.tile - 1;; win -= FUSED_BLOCK) {
+                const int64_t j = win - (int64_t)tid;
+                uint64_t v = j >= 0 ? ld_status(status + j) : ST_FLAG_PREFIX;
+                while (__any_sync(FULL, (v >> 62) == 0)) {
+                    if ((v >> 62) == 0) {
+                        __nanosleep(64);
+                        v = ld_status(status + j);
+                    }
+                }
+                const uint32_t pmask = __ballot_sync(FULL, (v >> 62) == 2);
+                uint64_t val = v & ST_MASK;
+                if (pmask && lane > (uint32_t)(__ffs(pmask) - 1)) val = 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(FULL, val, d);
+                if (lane == 0) {
+                    s_lb_sum[par][warp] = val;
+                    s_lb_p[par][warp] = pmask != 0;
+                }
+                __syncthreads();  // B3
+                bool done = false;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) {
+                    if (!done) {
+                        excl += s_lb_sum[par][w];
+                        done = s_lb_p[par][w] != 0;
+                    }
+                }
+                if (done) break;
+                __syncthreads();  // the partials are rewritten by the next window
+            }
+            const uint64_t tile_start = (uint64_t)prev.tile * TILE;
+            const uint64_t warp_start = tile_start + (uint64_t)warp * WTILE;
+            if (tid == 0) {
+                st_status(status + prev.tile, ST_FLAG_PREFIX | (excl + prev.tile_agg));
+                if (prev.tile == n_tiles - 1) {
+                    *d_total = base + excl + prev.tile_agg;
+                    if (out_offsets) out_offsets[n] = base + excl + prev.tile_agg;
+                }
+            }
+            const uint64_t warp_base = base + excl + prev.warp_excl;
+
+            // ---- emit ------------------------------------------------------------------------------------------------------
+#pragma unroll
+            for (int k = 0; k < ROWS; ++k) {
+                const uint64_t q = warp_start + 32 * k + lane;
+                const uint64_t pos = warp_base + prev.off[k];
+                if (out_offsets && q < n) out_offsets[q] = pos;
+                if (!((prev.slow >> k) & 1)) {
+                    const uint32_t c = prev.cnt[k];
+                    if (c >= 1 && pos < capacity) out_ids[pos] = (ix.descending && c == 2) ? prev.v1[k] : prev.v0[k];
+                    if (c == 2 && pos + 1 < capacity) out_ids[pos + 1] = ix.descending ? prev.v0[k] : prev.v1[k];
+                }
+            }
+            if (__any_sync(FULL, prev.slow != 0)) {
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k)
+                    if (((prev.slow >> k) & 1) && prev.cnt[k]) {
+                        const uint64_t q = warp_start + 32 * k + lane;  // q < n: an out-of-range query has cnt == 0
+                        emit_query_walk(ix, __ldg(chr + q), __ldg(start + q), __ldg(end + q), min_bp, out_ids,
+                                        warp_base + prev.off[k], capacity);
+                    }
+            }
+
+            // ---- file boundaries inside this tile: raw token offset of each file's first query ------------------------
+            if (out_file_tok) {
+                const uint32_t mark = __ldg(ws.tile_file + prev.tile);  // block-uniform
+                if (mark != 0) {
+#pragma unroll
+                    for (int k = 0; k < ROWS; ++k) s_qoff[warp * WTILE + 32 * k + lane] = prev.warp_excl + prev.off[k];
+                    if (tid == 0) s_qoff[TILE] = prev.tile_agg;
+                    __syncthreads();
+                    const uint64_t limit = (prev.tile == n_tiles - 1) ? n + 1 : tile_start + TILE;
+                    for (uint64_t f = (uint64_t)(0xFFFFFFFFu - mark) + tid; f <= n_files; f += FUSED_BLOCK) {
+                        const uint64_t qi = file_offsets[f];
+                        if (qi >= limit) break;
+                        out_file_tok[f] = base + excl + s_qoff[qi - tile_start];
+                    }
+                    __syncthreads();
+                }
+            }
+        } else {
+            __syncthreads();  // s_tile[par ^ 1] must be visible before the next iteration reads it
+        }
+        if (tile == NO_TILE) break;
+        prev = cur;
     }
 }
 
@@ -429,19 +564,16 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
         mark_file_tiles_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(n_files, d_file_offsets, n_tiles, ws.tile_file);
         ctx->launches++;
     }
-    int vec_ok = ((reinterpret_cast<uintptr_t>(d_chr) | reinterpret_cast<uintptr_t>(d_start) |
-                   reinterpret_cast<uintptr_t>(d_end)) & 15) == 0;
     static int blocks_per_sm = 0;
     if (!blocks_per_sm) {
-        GT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fused_find_kernel<FUSED_BLOCK, FUSED_ITEMS>,
-                                                              FUSED_BLOCK, 0));
+        GT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fused_find_kernel<FUSED_ROWS>, FUSED_BLOCK, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * blocks_per_sm);
     ctx->time_begin();
-    fused_find_kernel<FUSED_BLOCK, FUSED_ITEMS><<<grid, FUSED_BLOCK, 0, st>>>(
-        ix->view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end, min_overlap, vec_ok, d_out_ids,
-        ids_capacity, d_out_offsets, d_out_file_tok, ws, d_base, d_total_out, d_errflag);
+    fused_find_kernel<FUSED_ROWS><<<grid, FUSED_BLOCK, 0, st>>>(
+        ix->view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end, min_overlap, d_out_ids, ids_capacity,
+        d_out_offsets, d_out_file_tok, ws, d_base, d_total_out, d_errflag);
     ctx->time_end();
     ctx->launches++;
     GT_CUDA(cudaGetLastError());

@@ -87,8 +87,9 @@ int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_chroms, const
                           gtgpu_index** out_index);
 int32_t gtgpu_index_free(gtgpu_index* index);
 /* info[0]=n_intervals, [1]=n_segments (chromosome×AIList component), [2]=device bytes, [3]=lut shift,
- * [4]=max components on one chromosome, [5]=1 if every interval has start<=end */
-int32_t gtgpu_index_info(const gtgpu_index* index, uint64_t info[6]);
+ * [4]=max components on one chromosome, [5]=1 if every interval has start<=end, [6]=bin-table bins,
+ * [7]=bin-table bins with more than two candidates (served by the generic path), [8]=bin-table shift, [9]=0 */
+int32_t gtgpu_index_info(const gtgpu_index* index, uint64_t info[10]);
 
 /* ---- batch queries, host buffers ------------------------------------------------------------------------ */
 /* MultiChromOverlapper::count_overlaps (multi_chrom_overlapper.rs:483-498): out_counts[i] = number of indexed
