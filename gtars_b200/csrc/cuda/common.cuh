@@ -53,12 +53,12 @@ struct ChromMeta {    // 32 bytes
     uint32_t lut_ce, nb_ce;       // LUT over the chromosome's independently sorted ends
 };
 
-// Bin table (the fast path of find/tokenize).  Bin b of a chromosome covers positions [b << bt_shift, (b+1) << bt_shift)
-// and lists, in segment order, every interval that touches it.  A query whose [start,end) lies in one or two bins
-// finds all its candidates, in reference order, with one 16-byte load per bin (two when the bin holds two
-// candidates); an interval spanning two bins is taken from the first and skipped in the second (start < bin start).
-// Bins with more than two candidates, chromosomes with several AIList components or with start > end intervals,
-// wide or degenerate queries all fall back to the LUT + walk path below, so results never depend on the table.
+// Bin table (the fast path of find/tokenize).  Bin b of a chromosome lists, in segment order, every interval that
+// touches the two-bin window [b << bt_shift, (b+2) << bt_shift).  A query that STARTS in bin b and ends inside that
+// window (any query up to one bin wide) therefore finds all its candidates, already in reference order, with one
+// 16-byte load (two when the window holds two candidates).  Windows with more than two candidates, chromosomes with
+// several AIList components or with start > end intervals, wider or degenerate queries all fall back to the
+// LUT + walk path below, so results never depend on the table.
 struct BinA {            // 16 bytes
     uint32_t n;          // 0, 1, 2 candidates inline; BT_OVERFLOW = use the generic path
     uint32_t start0, end0, val0;

@@ -212,14 +212,16 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
                 if (cover_end[c]) t += ((cover_end[c] - 1) >> sh) + 1;
             return t;
         };
-        uint64_t bt_budget = std::max<uint64_t>(2 * total, 4096);
-        uint64_t bt_cap = 3ull << 20;
+        uint64_t per_iv = 4;  // bins per interval: narrow enough that a two-bin window rarely holds > 2 candidates
+        if (const char* env = getenv("GTGPU_BT_BINS_PER_INTERVAL")) per_iv = std::max<uint64_t>(strtoull(env, nullptr, 10), 1);
+        uint64_t bt_budget = std::max<uint64_t>(per_iv * total, 4096);
+        uint64_t bt_cap = 6ull << 20;
         if (const char* env = getenv("GTGPU_BT_MAX_BINS")) bt_cap = strtoull(env, nullptr, 10);
         bt_budget = std::min(bt_budget, bt_cap);
         while (bt_shift < 31 && total_bins(bt_shift) > bt_budget) ++bt_shift;
         if (const char* env = getenv("GTGPU_BT_SHIFT")) bt_shift = (uint32_t)std::min(31, std::max(0, atoi(env)));
         // A table only pays off while most bins hold at most two candidates: skip it for dense databases.
-        bool enabled = bt_cap > 0 && total_bins(bt_shift) <= (64ull << 20) && 2 * total <= 3 * total_bins(bt_shift);
+        bool enabled = bt_cap > 0 && total_bins(bt_shift) <= (64ull << 20) && total <= total_bins(bt_shift);
         uint64_t pos = 0;
         for (uint32_t c = 0; c < n_chroms; ++c) {
             chrom_bt[c].off = (uint32_t)pos;
@@ -240,7 +242,9 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
             const SegMeta& m = seg_meta[chroms[c].seg_begin];
             for (uint32_t i = m.off; i < m.off + m.len; ++i) {
                 uint64_t last_pos = std::max<uint64_t>(h_ends[i], (uint64_t)h_starts[i] + 1) - 1;
+                // bin b serves queries that START in b and end before bin b+2: it lists what touches that window
                 uint64_t b0 = h_starts[i] >> bt_shift, b1 = last_pos >> bt_shift;
+                if (b0 > 0) --b0;
                 for (uint64_t b = b0; b <= b1; ++b) {
                     BinA& a = bt_a[chrom_bt[c].off + b];
                     if (a.n == 0) {

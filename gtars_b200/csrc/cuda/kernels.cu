@@ -210,11 +210,6 @@ __global__ void fill_from_base_kernel(uint64_t count, uint64_t* __restrict__ out
 
 __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
-__device__ __forceinline__ bool cand_hit(uint32_t cs, uint32_t ce, uint32_t s, uint32_t e, int32_t min_bp) {
-    bool h = cs < e && ce > s;
-    if (min_bp > 1) h = h && ((int64_t)min(e, ce) - (int64_t)max(s, cs) >= (int64_t)min_bp);
-    return h;
-}
 
 // Emits every hit of one query through the generic LUT + walk path, in reference order; returns the count.
 __device__ __noinline__ uint32_t emit_query_walk(const IndexView& ix, uint32_t c, uint32_t s, uint32_t e, int32_t min_bp,
@@ -265,17 +260,27 @@ template <int ROWS>
 struct TileState {
     uint32_t tile;
     uint32_t cnt[ROWS], v0[ROWS], v1[ROWS], off[ROWS];
-    uint32_t slow;
+    uint32_t slow;  // bit k: query k goes through the generic LUT + walk path (count and emit)
     uint32_t warp_excl, tile_agg;
 };
 
-template <int ROWS>
+template <bool FILTER>
+__device__ __forceinline__ bool cand_hit(uint32_t cs, uint32_t ce, uint32_t s, uint32_t e, int32_t min_bp) {
+    bool h = cs < e && ce > s;
+    // multi_chrom_overlapper.rs:489-494: the bp filter only exists for min_overlap > 1
+    if (FILTER) h = h && ((int64_t)min(e, ce) - (int64_t)max(s, cs) >= (int64_t)min_bp);
+    return h;
+}
+
+// DESC: AIList emission order; FILTER: min_overlap > 1; OFFS: per-query offsets are written (gtgpu_find).
+template <int ROWS, bool DESC, bool FILTER, bool OFFS>
 __global__ void __launch_bounds__(FUSED_BLOCK)
 fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, const uint64_t* __restrict__ file_offsets,
                   const uint32_t* __restrict__ chr, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
                   int32_t min_bp, uint32_t* __restrict__ out_ids, uint64_t capacity, uint64_t* __restrict__ out_offsets,
                   uint64_t* __restrict__ out_file_tok, FusedWorkspace ws, const uint64_t* __restrict__ d_base,
                   uint64_t* __restrict__ d_total, uint32_t* __restrict__ d_err) {
+    static_assert(ROWS % 4 == 0, "the packed warp scan handles four rows per word");
     constexpr int WARPS = FUSED_BLOCK / 32;
     constexpr int WTILE = 32 * ROWS;          // queries per warp
     constexpr int TILE = FUSED_BLOCK * ROWS;  // queries per block tile
@@ -289,8 +294,9 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
     __shared__ uint32_t s_qoff[TILE + 1];      // per-query offsets, only filled for tiles with a file boundary
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nchr = ix.n_chroms;
     {
-        const uint32_t nc = min(ix.n_chroms, (uint32_t)CHROM_CACHE);
+        const uint32_t nc = min(nchr, (uint32_t)CHROM_CACHE);
         for (uint32_t i = tid; i < nc; i += FUSED_BLOCK) s_chrom[i] = __ldg(reinterpret_cast<const uint2*>(ix.chrom_bt + i));
         if (tid == 0) s_tile[0] = atomicAdd(ws.counter, 1u);
     }
@@ -312,27 +318,37 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
         cur.slow = 0;
 
         if (tile != NO_TILE) {
-            const uint64_t warp_start = (uint64_t)tile * TILE + (uint64_t)warp * WTILE;
+            const uint64_t tile_start = (uint64_t)tile * TILE;
+            const uint64_t lane_start = tile_start + (uint64_t)warp * WTILE + lane;
             // ---- queries: ROWS coalesced rows per array ---------------------------------------------------------
             uint32_t qc[ROWS], qs[ROWS], qe[ROWS];
+            if (tile_start + TILE <= n) {
+                const uint32_t *pc = chr + lane_start, *ps = start + lane_start, *pe = end + lane_start;
 #pragma unroll
-            for (int k = 0; k < ROWS; ++k) {
-                const uint64_t q = warp_start + 32 * k + lane;
-                const bool ok = q < n;
-                qc[k] = ok ? __ldcs(chr + q) : 0xFFFFFFFFu;
-                qs[k] = ok ? __ldcs(start + q) : 0;
-                qe[k] = ok ? __ldcs(end + q) : 0;
+                for (int k = 0; k < ROWS; ++k) {
+                    qc[k] = __ldcs(pc + 32 * k);
+                    qs[k] = __ldcs(ps + 32 * k);
+                    qe[k] = __ldcs(pe + 32 * k);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k) {
+                    const uint64_t q = lane_start + 32 * k;
+                    const bool ok = q < n;
+                    qc[k] = ok ? __ldcs(chr + q) : 0xFFFFFFFFu;
+                    qs[k] = ok ? __ldcs(start + q) : 0;
+                    qe[k] = ok ? __ldcs(end + q) : 0;
+                }
             }
-            // ---- resolve through the bin table: first bin of every query -----------------------------------------
-            uint32_t two = 0;  // bit k: query k also has to look at a second bin
+            // ---- resolve through the bin table: one 16-byte record for the bin the query starts in ----------------
             uint32_t boff[ROWS];
             uint4 A[ROWS];
 #pragma unroll
             for (int k = 0; k < ROWS; ++k) {
-                cur.cnt[k] = 0; cur.v0[k] = 0; cur.v1[k] = 0; boff[k] = 0;
                 A[k] = make_uint4(0, 0, 0, 0);
+                boff[k] = 0;
                 const uint32_t c = qc[k];
-                if (c < ix.n_chroms) {
+                if (c < nchr) {
                     const uint2 cb = c < CHROM_CACHE ? s_chrom[c] : __ldg(reinterpret_cast<const uint2*>(ix.chrom_bt + c));
                     const uint32_t s = qs[k], e = qe[k];
                     const uint32_t b1 = s >> shift, b2 = (e - 1) >> shift;
@@ -341,7 +357,6 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     } else if (b1 < cb.y) {
                         boff[k] = cb.x + b1;
                         A[k] = ldg128(ix.bt_a + boff[k]);
-                        if (b2 != b1 && b2 < cb.y) two |= 1u << k;
                     }
                 }
             }
@@ -349,76 +364,71 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             for (int k = 0; k < ROWS; ++k) {
                 const uint32_t s = qs[k], e = qe[k];
                 const uint32_t nA = A[k].x;
+                cur.cnt[k] = 0;
+                cur.v0[k] = A[k].w;
+                cur.v1[k] = 0;
                 if (nA == BT_OVERFLOW) {
                     cur.slow |= 1u << k;
                 } else if (nA != 0) {
-                    if (cand_hit(A[k].y, A[k].z, s, e, min_bp)) { cur.v0[k] = A[k].w; cur.cnt[k] = 1; }
+                    const bool h0 = cand_hit<FILTER>(A[k].y, A[k].z, s, e, min_bp);
+                    cur.cnt[k] = h0;
                     if (nA == 2) {
                         const uint4 B = ldg128(ix.bt_b + boff[k]);
-                        if (cand_hit(B.x, B.y, s, e, min_bp)) {
-                            if (cur.cnt[k] == 0) cur.v0[k] = B.z; else cur.v1[k] = B.z;
+                        if (cand_hit<FILTER>(B.x, B.y, s, e, min_bp)) {
+                            if (h0) cur.v1[k] = B.z; else cur.v0[k] = B.z;
                             cur.cnt[k]++;
                         }
                     }
                 }
             }
-            // ---- second bin (queries straddling a bin boundary): skip candidates already seen in the first bin --
-            if (__any_sync(FULL, two != 0)) {
-#pragma unroll
-                for (int k = 0; k < ROWS; ++k) {
-                    if (((two >> k) & 1) && !((cur.slow >> k) & 1)) {
-                        const uint32_t s = qs[k], e = qe[k];
-                        const uint32_t bstart = ((e - 1) >> shift) << shift;
-                        const uint4 A2 = ldg128(ix.bt_a + boff[k] + 1);
-                        if (A2.x == BT_OVERFLOW) {
-                            cur.slow |= 1u << k;
-                        } else if (A2.x != 0) {
-                            uint32_t extra[2];
-                            int ne = 0;
-                            if (A2.y >= bstart && cand_hit(A2.y, A2.z, s, e, min_bp)) extra[ne++] = A2.w;
-                            if (A2.x == 2) {
-                                const uint4 B2 = ldg128(ix.bt_b + boff[k] + 1);
-                                if (B2.x >= bstart && cand_hit(B2.x, B2.y, s, e, min_bp)) extra[ne++] = B2.z;
-                            }
-                            if (cur.cnt[k] + ne > 2) {
-                                cur.slow |= 1u << k;  // more hits than the two value registers: re-walk generically
-                            } else {
-                                for (int j = 0; j < ne; ++j) {
-                                    if (cur.cnt[k] == 0) cur.v0[k] = extra[j]; else cur.v1[k] = extra[j];
-                                    cur.cnt[k]++;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            // ---- generic path counts -----------------------------------------------------------------------------------
-            if (__any_sync(FULL, cur.slow != 0)) {
-#pragma unroll
-                for (int k = 0; k < ROWS; ++k)
-                    if ((cur.slow >> k) & 1) cur.cnt[k] = count_query_walk_noinline(ix, qc[k], qs[k], qe[k], min_bp);
-            }
             // ---- warp scan: exclusive offset of every query inside the warp's slice -----------------------------------
             uint32_t warp_total = 0;
-            uint64_t wide = 0;
+            if (!__any_sync(FULL, cur.slow != 0)) {
+                // every count is 0, 1 or 2: scan four rows at once, one byte per row (row sums <= 64)
 #pragma unroll
-            for (int k = 0; k < ROWS; ++k) {
-                uint32_t incl = cur.cnt[k];
+                for (int g = 0; g < ROWS / 4; ++g) {
+                    const uint32_t mine = cur.cnt[4 * g] | (cur.cnt[4 * g + 1] << 8) | (cur.cnt[4 * g + 2] << 16) |
+                                          (cur.cnt[4 * g + 3] << 24);
+                    uint32_t incl = mine;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    uint32_t t = __shfl_up_sync(FULL, incl, d);
-                    if (lane >= d) incl += t;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        uint32_t t = __shfl_up_sync(FULL, incl, d);
+                        if (lane >= d) incl += t;
+                    }
+                    const uint32_t tot = __shfl_sync(FULL, incl, 31);
+                    const uint32_t excl = incl - mine;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        cur.off[4 * g + r] = warp_total + ((excl >> (8 * r)) & 0xFF);
+                        warp_total += (tot >> (8 * r)) & 0xFF;
+                    }
                 }
-                cur.off[k] = warp_total + incl - cur.cnt[k];
-                warp_total += __shfl_sync(FULL, incl, 31);
-                wide += cur.cnt[k];
-            }
+            } else {
+                // generic path counts, then one 32-bit scan per row
+                uint32_t qc2[ROWS];
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) wide += __shfl_down_sync(FULL, wide, d);
-            if (lane == 0) {
-                s_wtot[par][warp] = warp_total;
-                if (wide > 0x1FFFFFFFull) atomicExch(d_err, 1u);  // keeps every tile-local offset inside 32 bits
+                for (int k = 0; k < ROWS; ++k) qc2[k] = qc[k];
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k)
+                    if ((cur.slow >> k) & 1) cur.cnt[k] = count_query_walk_noinline(ix, qc2[k], qs[k], qe[k], min_bp);
+                uint64_t wide = 0;
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k) {
+                    uint32_t incl = cur.cnt[k];
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        uint32_t t = __shfl_up_sync(FULL, incl, d);
+                        if (lane >= d) incl += t;
+                    }
+                    cur.off[k] = warp_total + incl - cur.cnt[k];
+                    warp_total += __shfl_sync(FULL, incl, 31);
+                    wide += cur.cnt[k];
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) wide += __shfl_down_sync(FULL, wide, d);
+                if (lane == 0 && wide > 0x1FFFFFFFull) atomicExch(d_err, 1u);  // tile-local offsets must fit 32 bits
             }
+            if (lane == 0) s_wtot[par][warp] = warp_total;
         }
         __syncthreads();  // B2: warp totals of `cur` visible; s_tile[par] consumed by everyone
 
@@ -474,33 +484,50 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 __syncthreads();  // the partials are rewritten by the next window
             }
             const uint64_t tile_start = (uint64_t)prev.tile * TILE;
-            const uint64_t warp_start = tile_start + (uint64_t)warp * WTILE;
+            const uint64_t tile_base = base + excl;
             if (tid == 0) {
                 st_status(status + prev.tile, ST_FLAG_PREFIX | (excl + prev.tile_agg));
                 if (prev.tile == n_tiles - 1) {
-                    *d_total = base + excl + prev.tile_agg;
-                    if (out_offsets) out_offsets[n] = base + excl + prev.tile_agg;
+                    *d_total = tile_base + prev.tile_agg;
+                    if (OFFS) out_offsets[n] = tile_base + prev.tile_agg;
                 }
             }
-            const uint64_t warp_base = base + excl + prev.warp_excl;
 
-            // ---- emit ------------------------------------------------------------------------------------------------------
+            // ---- emit: a row's ids land in consecutive words ------------------------------------------------------------
+            const uint64_t warp_base = tile_base + prev.warp_excl;
+            uint32_t* const outp = out_ids + warp_base;
+            if (OFFS) {
+                const uint64_t lane_start = tile_start + (uint64_t)warp * WTILE + lane;
 #pragma unroll
-            for (int k = 0; k < ROWS; ++k) {
-                const uint64_t q = warp_start + 32 * k + lane;
-                const uint64_t pos = warp_base + prev.off[k];
-                if (out_offsets && q < n) out_offsets[q] = pos;
-                if (!((prev.slow >> k) & 1)) {
+                for (int k = 0; k < ROWS; ++k)
+                    if (lane_start + 32 * k < n) out_offsets[lane_start + 32 * k] = warp_base + prev.off[k];
+            }
+            if (tile_base + prev.tile_agg <= capacity) {
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k) {
+                    const uint32_t c = prev.cnt[k], o = prev.off[k];
+                    if (!((prev.slow >> k) & 1)) {
+                        if (c >= 1) outp[o] = (DESC && c == 2) ? prev.v1[k] : prev.v0[k];
+                        if (c == 2) outp[o + 1] = DESC ? prev.v0[k] : prev.v1[k];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k) {
                     const uint32_t c = prev.cnt[k];
-                    if (c >= 1 && pos < capacity) out_ids[pos] = (ix.descending && c == 2) ? prev.v1[k] : prev.v0[k];
-                    if (c == 2 && pos + 1 < capacity) out_ids[pos + 1] = ix.descending ? prev.v0[k] : prev.v1[k];
+                    const uint64_t pos = warp_base + prev.off[k];
+                    if (!((prev.slow >> k) & 1)) {
+                        if (c >= 1 && pos < capacity) out_ids[pos] = (DESC && c == 2) ? prev.v1[k] : prev.v0[k];
+                        if (c == 2 && pos + 1 < capacity) out_ids[pos + 1] = DESC ? prev.v0[k] : prev.v1[k];
+                    }
                 }
             }
             if (__any_sync(FULL, prev.slow != 0)) {
+                const uint64_t lane_start = tile_start + (uint64_t)warp * WTILE + lane;
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k)
                     if (((prev.slow >> k) & 1) && prev.cnt[k]) {
-                        const uint64_t q = warp_start + 32 * k + lane;  // q < n: an out-of-range query has cnt == 0
+                        const uint64_t q = lane_start + 32 * k;  // q < n: an out-of-range query has cnt == 0
                         emit_query_walk(ix, __ldg(chr + q), __ldg(start + q), __ldg(end + q), min_bp, out_ids,
                                         warp_base + prev.off[k], capacity);
                     }
@@ -518,7 +545,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     for (uint64_t f = (uint64_t)(0xFFFFFFFFu - mark) + tid; f <= n_files; f += FUSED_BLOCK) {
                         const uint64_t qi = file_offsets[f];
                         if (qi >= limit) break;
-                        out_file_tok[f] = base + excl + s_qoff[qi - tile_start];
+                        out_file_tok[f] = tile_base + s_qoff[qi - tile_start];
                     }
                     __syncthreads();
                 }
@@ -529,6 +556,19 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
         if (tile == NO_TILE) break;
         prev = cur;
     }
+}
+
+template <bool DESC, bool FILTER, bool OFFS>
+static cudaError_t launch_variant(int grid, cudaStream_t st, const IndexView& view, uint64_t n, uint32_t n_tiles,
+                                  uint64_t n_files, const uint64_t* d_file_offsets, const uint32_t* d_chr,
+                                  const uint32_t* d_start, const uint32_t* d_end, int32_t min_overlap, uint32_t* d_out_ids,
+                                  uint64_t cap, uint64_t* d_out_offsets, uint64_t* d_out_file_tok, FusedWorkspace ws,
+                                  const uint64_t* d_base, uint64_t* d_total_out, uint32_t* d_errflag, int* blocks_per_sm) {
+    auto kern = fused_find_kernel<FUSED_ROWS, DESC, FILTER, OFFS>;
+    if (blocks_per_sm) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, FUSED_BLOCK, 0);
+    kern<<<grid, FUSED_BLOCK, 0, st>>>(view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end, min_overlap,
+                                       d_out_ids, cap, d_out_offsets, d_out_file_tok, ws, d_base, d_total_out, d_errflag);
+    return cudaGetLastError();
 }
 
 int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const uint64_t* d_file_offsets,
@@ -564,17 +604,39 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
         mark_file_tiles_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(n_files, d_file_offsets, n_tiles, ws.tile_file);
         ctx->launches++;
     }
-    static int blocks_per_sm = 0;
-    if (!blocks_per_sm) {
-        GT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fused_find_kernel<FUSED_ROWS>, FUSED_BLOCK, 0));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    const bool desc = ix->view.descending != 0, filt = min_overlap > 1, offs = d_out_offsets != nullptr;
+    const int variant = (desc ? 4 : 0) | (filt ? 2 : 0) | (offs ? 1 : 0);
+    static int blocks_per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int grid = 0;
+    cudaError_t err = cudaSuccess;
+#define GT_VARIANT(D, F, O)                                                                                          \
+    case ((D ? 4 : 0) | (F ? 2 : 0) | (O ? 1 : 0)):                                                                  \
+        if (!blocks_per_sm[variant]) {                                                                               \
+            err = launch_variant<D, F, O>(0, st, ix->view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end,  \
+                                          min_overlap, d_out_ids, ids_capacity, d_out_offsets, d_out_file_tok, ws,    \
+                                          d_base, d_total_out, d_errflag, &blocks_per_sm[variant]);                    \
+            if (err != cudaSuccess) break;                                                                           \
+            if (blocks_per_sm[variant] < 1) blocks_per_sm[variant] = 1;                                              \
+        }                                                                                                            \
+        grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * blocks_per_sm[variant]);                   \
+        ctx->time_begin();                                                                                           \
+        err = launch_variant<D, F, O>(grid, st, ix->view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end,   \
+                                      min_overlap, d_out_ids, ids_capacity, d_out_offsets, d_out_file_tok, ws, d_base, \
+                                      d_total_out, d_errflag, nullptr);                                                \
+        ctx->time_end();                                                                                             \
+        break;
+    switch (variant) {
+        GT_VARIANT(false, false, false)
+        GT_VARIANT(false, false, true)
+        GT_VARIANT(false, true, false)
+        GT_VARIANT(false, true, true)
+        GT_VARIANT(true, false, false)
+        GT_VARIANT(true, false, true)
+        GT_VARIANT(true, true, false)
+        GT_VARIANT(true, true, true)
     }
-    int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * blocks_per_sm);
-    ctx->time_begin();
-    fused_find_kernel<FUSED_ROWS><<<grid, FUSED_BLOCK, 0, st>>>(
-        ix->view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end, min_overlap, d_out_ids, ids_capacity,
-        d_out_offsets, d_out_file_tok, ws, d_base, d_total_out, d_errflag);
-    ctx->time_end();
+#undef GT_VARIANT
+    if (err != cudaSuccess) return fail(GTGPU_ERR_CUDA, std::string("fused_find launch: ") + cudaGetErrorString(err));
     ctx->launches++;
     GT_CUDA(cudaGetLastError());
     return GTGPU_OK;
