@@ -53,19 +53,14 @@ struct ChromMeta {    // 32 bytes
     uint32_t lut_ce, nb_ce;       // LUT over the chromosome's independently sorted ends
 };
 
-// Bin table (the fast path of find/tokenize).  Bin b of a chromosome lists, in segment order, every interval that
-// touches the two-bin window [b << bt_shift, (b+2) << bt_shift).  A query that STARTS in bin b and ends inside that
-// window (any query up to one bin wide) therefore finds all its candidates, already in reference order, with one
-// 16-byte load (two when the window holds two candidates).  Windows with more than two candidates, chromosomes with
-// several AIList components or with start > end intervals, wider or degenerate queries all fall back to the
-// LUT + walk path below, so results never depend on the table.
-struct BinA {            // 16 bytes
-    uint32_t n;          // 0, 1, 2 candidates inline; BT_OVERFLOW = use the generic path
-    uint32_t start0, end0, val0;
-};
-struct BinB {            // 16 bytes, only read when n == 2
-    uint32_t start1, end1, val1, pad;
-};
+// Bin table (the fast path of find/tokenize).  Window b of a chromosome is the two-bin range
+// [b << bt_shift, (b+2) << bt_shift); bt_lut[b] names the run of start-sorted intervals that touch it as
+// (first << 2) | n.  A query that STARTS in bin b and ends inside that window (any query up to one bin wide) finds
+// all its candidates, already in reference order, with one 4-byte LUT load and one or two adjacent 16-byte entry
+// loads.  The LUT (4 B/bin) plus the entries (16 B/interval) of a 1 M-region universe are 28 MB and stay resident
+// in one die's half of the L2.  Windows with more than two candidates or a non-contiguous candidate run,
+// chromosomes with several AIList components or with start > end intervals, wider or degenerate queries all fall
+// back to the LUT + walk path below, so results never depend on the table.
 #define BT_OVERFLOW 0xFFFFFFFFu
 #define BT_GENERIC_CHROM 0x80000000u  // in ChromBT.n_bins: this chromosome always takes the generic path
 
@@ -76,8 +71,8 @@ struct ChromBT {         // 8 bytes
 
 struct IndexView {
     const ChromBT* chrom_bt;
-    const BinA* bt_a;
-    const BinB* bt_b;
+    const uint32_t* bt_lut;
+    const uint4* bt_ent;
     uint32_t bt_shift;
     const ChromMeta* chroms;
     const SegMeta* segs;
@@ -142,6 +137,7 @@ struct gtgpu_index {
     std::vector<void*> allocs;
     uint64_t n_intervals = 0, n_segments = 0, device_bytes = 0, max_components = 0;
     uint64_t bt_bins = 0, bt_overflow_bins = 0;
+    bool l2_window_set = false;
 };
 
 namespace gtgpu {
@@ -153,8 +149,14 @@ enum ScratchRole {
 };
 
 // kernels.cu
+#ifndef GT_FUSED_ROWS
+#define GT_FUSED_ROWS 4
+#endif
+#ifndef GT_FUSED_MINBLOCKS
+#define GT_FUSED_MINBLOCKS 4
+#endif
 constexpr int FUSED_BLOCK = 256;             // 8 warps per tile
-constexpr int FUSED_ROWS = 4;                // queries per thread per tile (striped inside each warp)
+constexpr int FUSED_ROWS = GT_FUSED_ROWS;    // queries per thread per tile (striped inside each warp)
 constexpr int FUSED_TILE = FUSED_BLOCK * FUSED_ROWS;
 constexpr int CHROM_CACHE = 256;             // per-chromosome table entries staged in shared memory
 

@@ -187,8 +187,8 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
 
     // ---- 3b. bin table (fast path of find/tokenize; see common.cuh) ------------------------------------------
     std::vector<ChromBT> chrom_bt(n_chroms);
-    std::vector<BinA> bt_a;
-    std::vector<BinB> bt_b;
+    std::vector<uint32_t> bt_lut;  // per window: (first entry << 2) | n, 0 = empty, BT_OVERFLOW = generic path
+    std::vector<uint4> bt_ent;     // {start, end, val, 0} per interval, segment order (padded by two)
     uint32_t bt_shift = 0;
     uint64_t bt_overflow = 0;
     {
@@ -222,21 +222,24 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
         if (const char* env = getenv("GTGPU_BT_SHIFT")) bt_shift = (uint32_t)std::min(31, std::max(0, atoi(env)));
         // A table only pays off while most bins hold at most two candidates: skip it for dense databases.
         bool enabled = bt_cap > 0 && total_bins(bt_shift) <= (64ull << 20) && total <= total_bins(bt_shift);
-        uint64_t pos = 0;
+        uint64_t pos = 1;  // record 0 is an always-empty sentinel: unknown chromosomes and out-of-range bins read it
         for (uint32_t c = 0; c < n_chroms; ++c) {
             chrom_bt[c].off = (uint32_t)pos;
             if (chroms[c].seg_end == chroms[c].seg_begin) {
                 chrom_bt[c].n_bins = 0;  // absent chromosome: nothing can hit
             } else if (!eligible[c] || !enabled) {
                 chrom_bt[c].n_bins = BT_GENERIC_CHROM;
+                chrom_bt[c].off = 0;
             } else {
                 uint64_t nb = ((cover_end[c] - 1) >> bt_shift) + 1;
                 chrom_bt[c].n_bins = (uint32_t)nb;
                 pos += nb;
             }
         }
-        bt_a.assign(pos, BinA{0, 0, 0, 0});
-        bt_b.assign(pos, BinB{0, 0, 0, 0});
+        // Candidates of a window are a run [first, first + n) of the start-sorted segment whenever no interval is
+        // nested around a non-candidate; windows with n > 2 or a broken run go to the generic path.
+        bt_lut.assign(pos, 0);
+        std::vector<uint8_t> cnt(pos, 0);
         for (uint32_t c = 0; c < n_chroms; ++c) {
             if (chrom_bt[c].n_bins == 0 || chrom_bt[c].n_bins == BT_GENERIC_CHROM) continue;
             const SegMeta& m = seg_meta[chroms[c].seg_begin];
@@ -246,19 +249,32 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
                 uint64_t b0 = h_starts[i] >> bt_shift, b1 = last_pos >> bt_shift;
                 if (b0 > 0) --b0;
                 for (uint64_t b = b0; b <= b1; ++b) {
-                    BinA& a = bt_a[chrom_bt[c].off + b];
-                    if (a.n == 0) {
-                        a.n = 1; a.start0 = h_starts[i]; a.end0 = h_ends[i]; a.val0 = h_vals[i];
-                    } else if (a.n == 1) {
-                        a.n = 2;
-                        bt_b[chrom_bt[c].off + b] = BinB{h_starts[i], h_ends[i], h_vals[i], 0};
-                    } else if (a.n == 2) {
-                        a.n = BT_OVERFLOW;
-                        ++bt_overflow;
+                    const uint64_t k = chrom_bt[c].off + b;
+                    if (cnt[k] == 0) {
+                        bt_lut[k] = i;
+                        cnt[k] = 1;
+                    } else if (cnt[k] < 3 && bt_lut[k] + cnt[k] == i) {
+                        cnt[k]++;
+                    } else {
+                        cnt[k] = 255;
                     }
                 }
             }
         }
+        for (uint64_t k = 0; k < pos; ++k) {
+            if (cnt[k] > 2) {
+                bt_lut[k] = BT_OVERFLOW;
+                ++bt_overflow;
+            } else {
+                bt_lut[k] = cnt[k] ? (bt_lut[k] << 2) | cnt[k] : 0;
+            }
+        }
+        if (total >= (1ull << 30))  // index + count must fit one word
+            for (auto& cb : chrom_bt)
+                if (cb.n_bins != 0) { cb.n_bins = BT_GENERIC_CHROM; cb.off = 0; }
+        bt_ent.resize(total + 2);
+        for (uint64_t i = 0; i < total; ++i) bt_ent[i] = make_uint4(h_starts[i], h_ends[i], h_vals[i], 0);
+        bt_ent[total] = bt_ent[total + 1] = make_uint4(0xFFFFFFFFu, 0, 0, 0);
     }
 
     // ---- 4. upload ---------------------------------------------------------------------------------------------
@@ -272,10 +288,10 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
     int32_t st = GTGPU_OK;
     auto up = [&](auto& vec, auto** dst) { if (st == GTGPU_OK) st = upload(ix, vec, dst); };
     up(chrom_bt, &v.chrom_bt);
-    up(bt_a, &v.bt_a);
-    up(bt_b, &v.bt_b);
+    up(bt_lut, &v.bt_lut);
+    up(bt_ent, &v.bt_ent);
     v.bt_shift = bt_shift;
-    ix->bt_bins = bt_a.size();
+    ix->bt_bins = bt_lut.size();
     ix->bt_overflow_bins = bt_overflow;
     up(chroms, &v.chroms);
     up(seg_meta, &v.segs);

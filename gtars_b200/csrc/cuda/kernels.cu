@@ -6,6 +6,8 @@
 // queries for enumeration: count → block scan → decoupled look-back across tiles → emit, so no per-query
 // count/offset array ever round-trips through HBM, and (4) a persistent grid sized to the SM count.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -253,6 +255,66 @@ __device__ __forceinline__ void st_status(uint64_t* p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// ---- TMA (bulk async copy) staging of a tile's query rows into shared memory ------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
+}
+// L2 residency: the bin table is re-read by every tile (evict_last), queries and ids are touched once (evict_first).
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint32_t ldg32_keep(const void* p, uint64_t policy) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg128_keep(const void* p, uint64_t policy) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
+
+#ifdef GT_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE_MARK(i)                                                            \
+    do {                                                                         \
+        long long _now = clock64();                                              \
+        if (lane == 0) s_acc[warp][i] += (unsigned long long)(_now - _t);        \
+        _t = _now;                                                               \
+    } while (0)
+#define PHASE_START() long long _t = clock64()
+#else
+#define PHASE_MARK(i)
+#define PHASE_START()
+#endif
+
 // Per-thread result of resolving ROWS queries of one tile, kept in registers while the NEXT tile is resolved
 // (software pipeline, lag 1): by the time a tile's look-back runs, its predecessors published their aggregates a
 // whole resolve phase ago, so the look-back is one L2 round trip and (almost) never spins.
@@ -274,113 +336,143 @@ __device__ __forceinline__ bool cand_hit(uint32_t cs, uint32_t ce, uint32_t s, u
 
 // DESC: AIList emission order; FILTER: min_overlap > 1; OFFS: per-query offsets are written (gtgpu_find).
 template <int ROWS, bool DESC, bool FILTER, bool OFFS>
-__global__ void __launch_bounds__(FUSED_BLOCK)
+__global__ void __launch_bounds__(FUSED_BLOCK, GT_FUSED_MINBLOCKS)
 fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, const uint64_t* __restrict__ file_offsets,
                   const uint32_t* __restrict__ chr, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
-                  int32_t min_bp, uint32_t* __restrict__ out_ids, uint64_t capacity, uint64_t* __restrict__ out_offsets,
-                  uint64_t* __restrict__ out_file_tok, FusedWorkspace ws, const uint64_t* __restrict__ d_base,
-                  uint64_t* __restrict__ d_total, uint32_t* __restrict__ d_err) {
+                  int32_t min_bp, int tma_ok, uint32_t* __restrict__ out_ids, uint64_t capacity,
+                  uint64_t* __restrict__ out_offsets, uint64_t* __restrict__ out_file_tok, FusedWorkspace ws,
+                  const uint64_t* __restrict__ d_base, uint64_t* __restrict__ d_total, uint32_t* __restrict__ d_err) {
     static_assert(ROWS % 4 == 0, "the packed warp scan handles four rows per word");
     constexpr int WARPS = FUSED_BLOCK / 32;
     constexpr int WTILE = 32 * ROWS;          // queries per warp
     constexpr int TILE = FUSED_BLOCK * ROWS;  // queries per block tile
     constexpr uint32_t FULL = 0xFFFFFFFFu;
     constexpr uint32_t NO_TILE = 0xFFFFFFFFu;
+    __shared__ __align__(128) uint32_t s_q[2][3][TILE];  // TMA-staged query rows (chr, start, end), double-buffered
+    __shared__ __align__(8) uint64_t s_bar[2];           // one mbarrier per staging buffer
     __shared__ uint2 s_chrom[CHROM_CACHE];
     __shared__ uint32_t s_wtot[2][WARPS];      // per-warp hit totals, double-buffered by iteration parity
     __shared__ uint64_t s_lb_sum[2][WARPS];    // look-back partial sums per 32-tile window
     __shared__ uint32_t s_lb_p[2][WARPS];      // 1 when the window contains an inclusive prefix
     __shared__ uint32_t s_tile[2];             // tile index for this / the next iteration
+    __shared__ uint32_t s_staged[2];           // 1 when the tile's queries were requested through TMA
     __shared__ uint32_t s_qoff[TILE + 1];      // per-query offsets, only filled for tiles with a file boundary
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef GT_PHASE_TIMING
+    __shared__ unsigned long long s_acc[WARPS][10];
+    if (lane < 10) s_acc[warp][lane] = 0;
+#endif
     const uint32_t nchr = ix.n_chroms;
-    {
-        const uint32_t nc = min(nchr, (uint32_t)CHROM_CACHE);
-        for (uint32_t i = tid; i < nc; i += FUSED_BLOCK) s_chrom[i] = __ldg(reinterpret_cast<const uint2*>(ix.chrom_bt + i));
-        if (tid == 0) s_tile[0] = atomicAdd(ws.counter, 1u);
+    const bool chrom_cached = nchr < CHROM_CACHE;  // the last cached entry is then an "unknown chromosome" sentinel
+
+    // One thread claims a tile and, when it is a full aligned tile, starts the bulk copies of its three query rows.
+    auto claim_and_stage = [&](uint32_t buf) {
+        const uint32_t t = atomicAdd(ws.counter, 1u);
+        s_tile[buf] = t;
+        uint32_t staged = 0;
+        if (tma_ok && t < n_tiles && (uint64_t)(t + 1) * TILE <= n) {
+            staged = 1;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this buffer are done
+            mbar_expect_tx(&s_bar[buf], 3 * TILE * 4);
+            const uint64_t q0 = (uint64_t)t * TILE;
+            const uint64_t pol = policy_evict_first();
+            bulk_g2s(&s_q[buf][0][0], chr + q0, TILE * 4, &s_bar[buf], pol);
+            bulk_g2s(&s_q[buf][1][0], start + q0, TILE * 4, &s_bar[buf], pol);
+            bulk_g2s(&s_q[buf][2][0], end + q0, TILE * 4, &s_bar[buf], pol);
+        }
+        s_staged[buf] = staged;
+    };
+
+    for (uint32_t i = tid; i < CHROM_CACHE; i += FUSED_BLOCK)
+        s_chrom[i] = i < nchr ? __ldg(reinterpret_cast<const uint2*>(ix.chrom_bt + i)) : make_uint2(0, 0);
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        claim_and_stage(0);
     }
     __syncthreads();
 
     const uint64_t base = d_base ? *d_base : 0;
     uint64_t* status = ws.status;
     const uint32_t shift = ix.bt_shift;
+    uint32_t bar_phase = 0;  // bit b: parity to wait for on s_bar[b]
+    const uint64_t keep = policy_evict_last();
 
-    TileState<ROWS> prev;
-    prev.tile = NO_TILE;
-
-    for (uint32_t it = 0;; ++it) {
-        const uint32_t par = it & 1;
+    // One pipeline step: resolve `cur` (tile of this iteration), then look back + emit `prev` (tile of the last one).
+    auto step = [&](TileState<ROWS>& cur, TileState<ROWS>& prev, const uint32_t par) -> bool {
+        PHASE_START();
         uint32_t tile = s_tile[par];
         if (tile >= n_tiles) tile = NO_TILE;
-        TileState<ROWS> cur;
         cur.tile = tile;
         cur.slow = 0;
 
         if (tile != NO_TILE) {
             const uint64_t tile_start = (uint64_t)tile * TILE;
-            const uint64_t lane_start = tile_start + (uint64_t)warp * WTILE + lane;
-            // ---- queries: ROWS coalesced rows per array ---------------------------------------------------------
+            const uint32_t wl = warp * WTILE + lane;
+            // ---- queries: ROWS coalesced rows per array, from the TMA-staged copy when there is one -----------------
             uint32_t qc[ROWS], qs[ROWS], qe[ROWS];
-            if (tile_start + TILE <= n) {
-                const uint32_t *pc = chr + lane_start, *ps = start + lane_start, *pe = end + lane_start;
+            if (s_staged[par]) {
+                mbar_wait(&s_bar[par], (bar_phase >> par) & 1);
+                bar_phase ^= 1u << par;
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k) {
-                    qc[k] = __ldcs(pc + 32 * k);
-                    qs[k] = __ldcs(ps + 32 * k);
-                    qe[k] = __ldcs(pe + 32 * k);
+                    qc[k] = s_q[par][0][wl + 32 * k];
+                    qs[k] = s_q[par][1][wl + 32 * k];
+                    qe[k] = s_q[par][2][wl + 32 * k];
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k) {
-                    const uint64_t q = lane_start + 32 * k;
+                    const uint64_t q = tile_start + wl + 32 * k;
                     const bool ok = q < n;
                     qc[k] = ok ? __ldcs(chr + q) : 0xFFFFFFFFu;
                     qs[k] = ok ? __ldcs(start + q) : 0;
                     qe[k] = ok ? __ldcs(end + q) : 0;
                 }
             }
-            // ---- resolve through the bin table: one 16-byte record for the bin the query starts in ----------------
-            uint32_t boff[ROWS];
-            uint4 A[ROWS];
+            if (qc[0] == 0x12345678u && qs[0] == 0x9abcdefu) atomicExch(d_err, 2u);  // forces the loads before the mark
+            PHASE_MARK(0);
+            // ---- resolve through the bin table: window LUT word, then the one or two candidate entries ------------
+            uint32_t w[ROWS];
 #pragma unroll
             for (int k = 0; k < ROWS; ++k) {
-                A[k] = make_uint4(0, 0, 0, 0);
-                boff[k] = 0;
-                const uint32_t c = qc[k];
-                if (c < nchr) {
-                    const uint2 cb = c < CHROM_CACHE ? s_chrom[c] : __ldg(reinterpret_cast<const uint2*>(ix.chrom_bt + c));
-                    const uint32_t s = qs[k], e = qe[k];
-                    const uint32_t b1 = s >> shift, b2 = (e - 1) >> shift;
-                    if (cb.y == BT_GENERIC_CHROM || s >= e || b2 - b1 > 1) {
-                        cur.slow |= 1u << k;
-                    } else if (b1 < cb.y) {
-                        boff[k] = cb.x + b1;
-                        A[k] = ldg128(ix.bt_a + boff[k]);
-                    }
+                const uint32_t c = qc[k], s = qs[k], e = qe[k];
+                uint2 cb;
+                if (chrom_cached) cb = s_chrom[min(c, (uint32_t)CHROM_CACHE - 1)];
+                else cb = c < nchr ? __ldg(reinterpret_cast<const uint2*>(ix.chrom_bt + c)) : make_uint2(0, 0);
+                const uint32_t b1 = s >> shift, b2 = (e - 1) >> shift;
+                if ((cb.y == BT_GENERIC_CHROM) | (s >= e) | (b2 - b1 > 1)) cur.slow |= 1u << k;
+                const uint32_t li = b1 < (cb.y & 0x7FFFFFFFu) ? cb.x + b1 : 0u;  // word 0 is the empty sentinel
+                w[k] = ldg32_keep(ix.bt_lut + li, keep);
+            }
+            uint4 E0[ROWS];
+#pragma unroll
+            for (int k = 0; k < ROWS; ++k) {
+                if (w[k] == BT_OVERFLOW) {
+                    cur.slow |= 1u << k;
+                    w[k] = 0;
                 }
+                E0[k] = make_uint4(0xFFFFFFFFu, 0, 0, 0);
+                if (w[k] & 3) E0[k] = ldg128_keep(ix.bt_ent + (w[k] >> 2), keep);
             }
 #pragma unroll
             for (int k = 0; k < ROWS; ++k) {
                 const uint32_t s = qs[k], e = qe[k];
-                const uint32_t nA = A[k].x;
-                cur.cnt[k] = 0;
-                cur.v0[k] = A[k].w;
+                const bool h0 = cand_hit<FILTER>(E0[k].x, E0[k].y, s, e, min_bp);
+                cur.cnt[k] = h0;
+                cur.v0[k] = E0[k].z;
                 cur.v1[k] = 0;
-                if (nA == BT_OVERFLOW) {
-                    cur.slow |= 1u << k;
-                } else if (nA != 0) {
-                    const bool h0 = cand_hit<FILTER>(A[k].y, A[k].z, s, e, min_bp);
-                    cur.cnt[k] = h0;
-                    if (nA == 2) {
-                        const uint4 B = ldg128(ix.bt_b + boff[k]);
-                        if (cand_hit<FILTER>(B.x, B.y, s, e, min_bp)) {
-                            if (h0) cur.v1[k] = B.z; else cur.v0[k] = B.z;
-                            cur.cnt[k]++;
-                        }
+                if ((w[k] & 3) == 2) {
+                    const uint4 E1 = ldg128_keep(ix.bt_ent + (w[k] >> 2) + 1, keep);
+                    if (cand_hit<FILTER>(E1.x, E1.y, s, e, min_bp)) {
+                        if (h0) cur.v1[k] = E1.z; else cur.v0[k] = E1.z;
+                        cur.cnt[k]++;
                     }
                 }
             }
+            PHASE_MARK(1);
             // ---- warp scan: exclusive offset of every query inside the warp's slice -----------------------------------
             uint32_t warp_total = 0;
             if (!__any_sync(FULL, cur.slow != 0)) {
@@ -405,12 +497,9 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 }
             } else {
                 // generic path counts, then one 32-bit scan per row
-                uint32_t qc2[ROWS];
-#pragma unroll
-                for (int k = 0; k < ROWS; ++k) qc2[k] = qc[k];
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k)
-                    if ((cur.slow >> k) & 1) cur.cnt[k] = count_query_walk_noinline(ix, qc2[k], qs[k], qe[k], min_bp);
+                    if ((cur.slow >> k) & 1) cur.cnt[k] = count_query_walk_noinline(ix, qc[k], qs[k], qe[k], min_bp);
                 uint64_t wide = 0;
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k) {
@@ -429,8 +518,10 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 if (lane == 0 && wide > 0x1FFFFFFFull) atomicExch(d_err, 1u);  // tile-local offsets must fit 32 bits
             }
             if (lane == 0) s_wtot[par][warp] = warp_total;
+            PHASE_MARK(2);
         }
-        __syncthreads();  // B2: warp totals of `cur` visible; s_tile[par] consumed by everyone
+        __syncthreads();  // B2: warp totals of `cur` visible; s_tile[par] / s_q[par] consumed by everyone
+        PHASE_MARK(3);
 
         if (tile != NO_TILE) {
             uint32_t warp_excl = 0, tile_agg = 0;
@@ -444,15 +535,20 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             cur.tile_agg = tile_agg;
             if (tid == 0) {
                 st_status(status + tile, ST_FLAG_AGG | (uint64_t)tile_agg);
-                s_tile[par ^ 1] = atomicAdd(ws.counter, 1u);
+                claim_and_stage(par ^ 1);  // next tile: the claim and the query copies hide behind the look-back
             }
         } else if (tid == 0) {
             s_tile[par ^ 1] = NO_TILE;
+            s_staged[par ^ 1] = 0;
         }
 
+        PHASE_MARK(4);
         if (prev.tile != NO_TILE) {
             // ---- block-wide decoupled look-back for the PREVIOUS tile: warp w inspects 32 predecessors ---------------
             uint64_t excl = 0;
+#ifdef GT_PHASE_TIMING
+            int _windows = 0;
+#endif
             for (int64_t win = (int64_t)prev.tile - 1;; win -= FUSED_BLOCK) {
                 const int64_t j = win - (int64_t)tid;
                 uint64_t v = j >= 0 ? ld_status(status + j) : ST_FLAG_PREFIX;
@@ -472,6 +568,9 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     s_lb_p[par][warp] = pmask != 0;
                 }
                 __syncthreads();  // B3
+#ifdef GT_PHASE_TIMING
+                ++_windows;
+#endif
                 bool done = false;
 #pragma unroll
                 for (int w = 0; w < WARPS; ++w) {
@@ -483,6 +582,10 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 if (done) break;
                 __syncthreads();  // the partials are rewritten by the next window
             }
+            PHASE_MARK(5);
+#ifdef GT_PHASE_TIMING
+            if (lane == 0) { s_acc[warp][8] += _windows; s_acc[warp][9] += 1; }
+#endif
             const uint64_t tile_start = (uint64_t)prev.tile * TILE;
             const uint64_t tile_base = base + excl;
             if (tid == 0) {
@@ -507,8 +610,8 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 for (int k = 0; k < ROWS; ++k) {
                     const uint32_t c = prev.cnt[k], o = prev.off[k];
                     if (!((prev.slow >> k) & 1)) {
-                        if (c >= 1) outp[o] = (DESC && c == 2) ? prev.v1[k] : prev.v0[k];
-                        if (c == 2) outp[o + 1] = DESC ? prev.v0[k] : prev.v1[k];
+                        if (c >= 1) __stcs(outp + o, (DESC && c == 2) ? prev.v1[k] : prev.v0[k]);
+                        if (c == 2) __stcs(outp + o + 1, DESC ? prev.v0[k] : prev.v1[k]);
                     }
                 }
             } else {
@@ -533,6 +636,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     }
             }
 
+            PHASE_MARK(6);
             // ---- file boundaries inside this tile: raw token offset of each file's first query ------------------------
             if (out_file_tok) {
                 const uint32_t mark = __ldg(ws.tile_file + prev.tile);  // block-uniform
@@ -550,12 +654,24 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     __syncthreads();
                 }
             }
+            PHASE_MARK(7);
         } else {
             __syncthreads();  // s_tile[par ^ 1] must be visible before the next iteration reads it
         }
-        if (tile == NO_TILE) break;
-        prev = cur;
+        return tile != NO_TILE;
+    };
+
+    // Ping-pong the two tile states so nothing is copied between iterations.
+    TileState<ROWS> ta, tb;
+    tb.tile = NO_TILE;
+    for (;;) {
+        if (!step(ta, tb, 0)) break;
+        if (!step(tb, ta, 1)) break;
     }
+#ifdef GT_PHASE_TIMING
+    __syncwarp();
+    if (lane < 10) atomicAdd(&g_phase_cycles[lane], s_acc[warp][lane]);
+#endif
 }
 
 template <bool DESC, bool FILTER, bool OFFS>
@@ -566,10 +682,24 @@ static cudaError_t launch_variant(int grid, cudaStream_t st, const IndexView& vi
                                   const uint64_t* d_base, uint64_t* d_total_out, uint32_t* d_errflag, int* blocks_per_sm) {
     auto kern = fused_find_kernel<FUSED_ROWS, DESC, FILTER, OFFS>;
     if (blocks_per_sm) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, FUSED_BLOCK, 0);
-    kern<<<grid, FUSED_BLOCK, 0, st>>>(view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end, min_overlap,
+    // bulk copies need 16-byte aligned sources; tile starts are multiples of 4 KiB, so only the bases matter
+    const int tma_ok = ((reinterpret_cast<uintptr_t>(d_chr) | reinterpret_cast<uintptr_t>(d_start) |
+                         reinterpret_cast<uintptr_t>(d_end)) & 15) == 0;
+    kern<<<grid, FUSED_BLOCK, 0, st>>>(view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end, min_overlap, tma_ok,
                                        d_out_ids, cap, d_out_offsets, d_out_file_tok, ws, d_base, d_total_out, d_errflag);
     return cudaGetLastError();
 }
+
+#ifdef GT_PHASE_TIMING
+extern "C" void gtgpu_debug_phase_cycles(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z);
+    }
+}
+#endif
 
 int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const uint64_t* d_file_offsets,
                           const uint32_t* d_chr, const uint32_t* d_start, const uint32_t* d_end,
@@ -603,6 +733,30 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
         uint64_t cnt = n_files + 1;
         mark_file_tiles_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(n_files, d_file_offsets, n_tiles, ws.tile_file);
         ctx->launches++;
+    }
+    // Keep the bin table resident in L2 while 12 B/query of streaming input flows past it.
+    if (!ix->l2_window_set) {
+        ix->l2_window_set = true;
+        const char* env = getenv("GTGPU_L2_PERSIST");
+        if (ix->bt_bins && !(env && env[0] == '0')) {
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+            size_t bytes = (size_t)ix->bt_bins * sizeof(uint32_t);
+            size_t win = std::min<size_t>(bytes, (size_t)std::max(max_window, 0));
+            if (max_persist > 0 && win > 0) {
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(win, (size_t)max_persist));
+                cudaStreamAttrValue attr;
+                memset(&attr, 0, sizeof attr);
+                attr.accessPolicyWindow.base_ptr = const_cast<uint32_t*>(ix->view.bt_lut);
+                attr.accessPolicyWindow.num_bytes = win;
+                attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float)max_persist / (float)win);
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+                cudaGetLastError();
+            }
+        }
     }
     const bool desc = ix->view.descending != 0, filt = min_overlap > 1, offs = d_out_offsets != nullptr;
     const int variant = (desc ? 4 : 0) | (filt ? 2 : 0) | (offs ? 1 : 0);

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libgtars_gpu.so")
+# GTGPU_LIB selects an experimental build of the same library (tuning sweeps); the default is the in-tree product.
+LIB_PATH = os.environ.get("GTGPU_LIB") or os.path.join(_PKG, "libgtars_gpu.so")
 
 KIND_BITS, KIND_AILIST = 0, 1
 UNKNOWN_CHROM = 0xFFFFFFFF
