@@ -321,8 +321,10 @@ __device__ unsigned long long g_phase_cycles[16];
 template <int ROWS>
 struct TileState {
     uint32_t tile;
-    uint32_t cnt[ROWS], v0[ROWS], v1[ROWS], off[ROWS];
-    uint32_t slow;  // bit k: query k goes through the generic LUT + walk path (count and emit)
+    uint32_t v0[ROWS];   // first hit's val per query (second one, when there is one, waits in s_v1)
+    uint32_t cntpack;    // 2 bits per row: min(count, 3)
+    uint32_t offpack;    // 8 bits per row: offset inside the warp slice, valid when the warp had no generic query
+    uint32_t slow;       // bit k: query k goes through the generic LUT + walk path (count and emit); bit 31: warp-wide
     uint32_t warp_excl, tile_agg;
 };
 
@@ -342,21 +344,23 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                   int32_t min_bp, int tma_ok, uint32_t* __restrict__ out_ids, uint64_t capacity,
                   uint64_t* __restrict__ out_offsets, uint64_t* __restrict__ out_file_tok, FusedWorkspace ws,
                   const uint64_t* __restrict__ d_base, uint64_t* __restrict__ d_total, uint32_t* __restrict__ d_err) {
-    static_assert(ROWS % 4 == 0, "the packed warp scan handles four rows per word");
+    static_assert(ROWS == 4, "state packing (2-bit counts, 8-bit offsets) is written for four rows per thread");
     constexpr int WARPS = FUSED_BLOCK / 32;
     constexpr int WTILE = 32 * ROWS;          // queries per warp
     constexpr int TILE = FUSED_BLOCK * ROWS;  // queries per block tile
     constexpr uint32_t FULL = 0xFFFFFFFFu;
     constexpr uint32_t NO_TILE = 0xFFFFFFFFu;
+    constexpr uint32_t WARP_SLOW = 1u << 31;
     __shared__ __align__(128) uint32_t s_q[2][3][TILE];  // TMA-staged query rows (chr, start, end), double-buffered
     __shared__ __align__(8) uint64_t s_bar[2];           // one mbarrier per staging buffer
+    __shared__ uint32_t s_v1[2][TILE];         // second hit's val (queries with two hits), by iteration parity
+    __shared__ uint32_t s_off[2][TILE];        // full offsets for warps that had a generic query, by iteration parity
     __shared__ uint2 s_chrom[CHROM_CACHE];
     __shared__ uint32_t s_wtot[2][WARPS];      // per-warp hit totals, double-buffered by iteration parity
     __shared__ uint64_t s_lb_sum[2][WARPS];    // look-back partial sums per 32-tile window
     __shared__ uint32_t s_lb_p[2][WARPS];      // 1 when the window contains an inclusive prefix
     __shared__ uint32_t s_tile[2];             // tile index for this / the next iteration
     __shared__ uint32_t s_staged[2];           // 1 when the tile's queries were requested through TMA
-    __shared__ uint32_t s_qoff[TILE + 1];      // per-query offsets, only filled for tiles with a file boundary
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #ifdef GT_PHASE_TIMING
@@ -408,6 +412,11 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
         cur.tile = tile;
         cur.slow = 0;
 
+        // The status words of prev's 256 predecessors were published about one resolve phase ago: fetch them now so
+        // the look-back below normally finds them in registers instead of paying an L2 round trip after the barrier.
+        uint64_t lb_pre = ST_FLAG_PREFIX;
+        if (prev.tile != NO_TILE && (int64_t)prev.tile - 1 - (int64_t)tid >= 0) lb_pre = ld_status(status + prev.tile - 1 - tid);
+
         if (tile != NO_TILE) {
             const uint64_t tile_start = (uint64_t)tile * TILE;
             const uint32_t wl = warp * WTILE + lane;
@@ -432,7 +441,6 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     qe[k] = ok ? __ldcs(end + q) : 0;
                 }
             }
-            if (qc[0] == 0x12345678u && qs[0] == 0x9abcdefu) atomicExch(d_err, 2u);  // forces the loads before the mark
             PHASE_MARK(0);
             // ---- resolve through the bin table: window LUT word, then the one or two candidate entries ------------
             uint32_t w[ROWS];
@@ -447,72 +455,72 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 const uint32_t li = b1 < (cb.y & 0x7FFFFFFFu) ? cb.x + b1 : 0u;  // word 0 is the empty sentinel
                 w[k] = ldg32_keep(ix.bt_lut + li, keep);
             }
-            uint4 E0[ROWS];
+            uint32_t cnt[ROWS];
+            {
+                uint4 E0[ROWS], E1[ROWS];
 #pragma unroll
-            for (int k = 0; k < ROWS; ++k) {
-                if (w[k] == BT_OVERFLOW) {
-                    cur.slow |= 1u << k;
-                    w[k] = 0;
-                }
-                E0[k] = make_uint4(0xFFFFFFFFu, 0, 0, 0);
-                if (w[k] & 3) E0[k] = ldg128_keep(ix.bt_ent + (w[k] >> 2), keep);
-            }
-#pragma unroll
-            for (int k = 0; k < ROWS; ++k) {
-                const uint32_t s = qs[k], e = qe[k];
-                const bool h0 = cand_hit<FILTER>(E0[k].x, E0[k].y, s, e, min_bp);
-                cur.cnt[k] = h0;
-                cur.v0[k] = E0[k].z;
-                cur.v1[k] = 0;
-                if ((w[k] & 3) == 2) {
-                    const uint4 E1 = ldg128_keep(ix.bt_ent + (w[k] >> 2) + 1, keep);
-                    if (cand_hit<FILTER>(E1.x, E1.y, s, e, min_bp)) {
-                        if (h0) cur.v1[k] = E1.z; else cur.v0[k] = E1.z;
-                        cur.cnt[k]++;
+                for (int k = 0; k < ROWS; ++k) {
+                    if (w[k] == BT_OVERFLOW) {
+                        cur.slow |= 1u << k;
+                        w[k] = 0;
                     }
+                    E0[k] = make_uint4(0xFFFFFFFFu, 0, 0, 0);  // start = max: can never hit
+                    E1[k] = make_uint4(0xFFFFFFFFu, 0, 0, 0);
+                    const uint4* ep = ix.bt_ent + (w[k] >> 2);
+                    if (w[k] & 3) E0[k] = ldg128_keep(ep, keep);
+                    if ((w[k] & 3) == 2) E1[k] = ldg128_keep(ep + 1, keep);
+                }
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k) {
+                    const uint32_t s = qs[k], e = qe[k];
+                    const bool h0 = cand_hit<FILTER>(E0[k].x, E0[k].y, s, e, min_bp);
+                    const bool h1 = cand_hit<FILTER>(E1[k].x, E1[k].y, s, e, min_bp);
+                    cnt[k] = (uint32_t)h0 + (uint32_t)h1;
+                    cur.v0[k] = h0 ? E0[k].z : E1[k].z;
+                    if (h0 & h1) s_v1[par][wl + 32 * k] = E1[k].z;
                 }
             }
             PHASE_MARK(1);
             // ---- warp scan: exclusive offset of every query inside the warp's slice -----------------------------------
             uint32_t warp_total = 0;
             if (!__any_sync(FULL, cur.slow != 0)) {
-                // every count is 0, 1 or 2: scan four rows at once, one byte per row (row sums <= 64)
+                // every count is 0, 1 or 2: scan the four rows at once, one byte per row (row sums <= 64)
+                const uint32_t mine = cnt[0] | (cnt[1] << 8) | (cnt[2] << 16) | (cnt[3] << 24);
+                uint32_t incl = mine;
 #pragma unroll
-                for (int g = 0; g < ROWS / 4; ++g) {
-                    const uint32_t mine = cur.cnt[4 * g] | (cur.cnt[4 * g + 1] << 8) | (cur.cnt[4 * g + 2] << 16) |
-                                          (cur.cnt[4 * g + 3] << 24);
-                    uint32_t incl = mine;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        uint32_t t = __shfl_up_sync(FULL, incl, d);
-                        if (lane >= d) incl += t;
-                    }
-                    const uint32_t tot = __shfl_sync(FULL, incl, 31);
-                    const uint32_t excl = incl - mine;
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        cur.off[4 * g + r] = warp_total + ((excl >> (8 * r)) & 0xFF);
-                        warp_total += (tot >> (8 * r)) & 0xFF;
-                    }
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t t = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl += t;
                 }
+                const uint32_t tot = __shfl_sync(FULL, incl, 31);
+                const uint32_t excl = incl - mine;
+                // row bases: 0, t0, t0+t1, t0+t1+t2 (each <= 192), added bytewise
+                const uint32_t t0 = tot & 0xFF, t1 = (tot >> 8) & 0xFF, t2 = (tot >> 16) & 0xFF, t3 = tot >> 24;
+                cur.offpack = excl + ((t0 << 8) | ((t0 + t1) << 16) | ((t0 + t1 + t2) << 24));
+                warp_total = t0 + t1 + t2 + t3;
+                cur.cntpack = cnt[0] | (cnt[1] << 2) | (cnt[2] << 4) | (cnt[3] << 6);
             } else {
-                // generic path counts, then one 32-bit scan per row
+                // generic path counts, then one 32-bit scan per row; full offsets go to shared memory
+                cur.slow |= WARP_SLOW;
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k)
-                    if ((cur.slow >> k) & 1) cur.cnt[k] = count_query_walk_noinline(ix, qc[k], qs[k], qe[k], min_bp);
+                    if ((cur.slow >> k) & 1) cnt[k] = count_query_walk_noinline(ix, qc[k], qs[k], qe[k], min_bp);
                 uint64_t wide = 0;
+                cur.cntpack = 0;
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k) {
-                    uint32_t incl = cur.cnt[k];
+                    uint32_t incl = cnt[k];
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
                         uint32_t t = __shfl_up_sync(FULL, incl, d);
                         if (lane >= d) incl += t;
                     }
-                    cur.off[k] = warp_total + incl - cur.cnt[k];
+                    s_off[par][wl + 32 * k] = warp_total + incl - cnt[k];
                     warp_total += __shfl_sync(FULL, incl, 31);
-                    wide += cur.cnt[k];
+                    wide += cnt[k];
+                    cur.cntpack |= min(cnt[k], 3u) << (2 * k);
                 }
+                cur.offpack = 0;
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) wide += __shfl_down_sync(FULL, wide, d);
                 if (lane == 0 && wide > 0x1FFFFFFFull) atomicExch(d_err, 1u);  // tile-local offsets must fit 32 bits
@@ -541,20 +549,23 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             s_tile[par ^ 1] = NO_TILE;
             s_staged[par ^ 1] = 0;
         }
-
         PHASE_MARK(4);
+
         if (prev.tile != NO_TILE) {
             // ---- block-wide decoupled look-back for the PREVIOUS tile: warp w inspects 32 predecessors ---------------
+            const uint32_t ppar = par ^ 1;  // parity under which prev's shared-memory side state was written
             uint64_t excl = 0;
 #ifdef GT_PHASE_TIMING
             int _windows = 0;
 #endif
             for (int64_t win = (int64_t)prev.tile - 1;; win -= FUSED_BLOCK) {
                 const int64_t j = win - (int64_t)tid;
-                uint64_t v = j >= 0 ? ld_status(status + j) : ST_FLAG_PREFIX;
+                uint64_t v = lb_pre;
+                lb_pre = 0;
+                if (win != (int64_t)prev.tile - 1) v = j >= 0 ? ld_status(status + j) : ST_FLAG_PREFIX;
                 while (__any_sync(FULL, (v >> 62) == 0)) {
                     if ((v >> 62) == 0) {
-                        __nanosleep(64);
+                        __nanosleep(32);
                         v = ld_status(status + j);
                     }
                 }
@@ -597,59 +608,71 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             }
 
             // ---- emit: a row's ids land in consecutive words ------------------------------------------------------------
+            const uint32_t wl = warp * WTILE + lane;
             const uint64_t warp_base = tile_base + prev.warp_excl;
             uint32_t* const outp = out_ids + warp_base;
-            if (OFFS) {
-                const uint64_t lane_start = tile_start + (uint64_t)warp * WTILE + lane;
-#pragma unroll
-                for (int k = 0; k < ROWS; ++k)
-                    if (lane_start + 32 * k < n) out_offsets[lane_start + 32 * k] = warp_base + prev.off[k];
-            }
-            if (tile_base + prev.tile_agg <= capacity) {
+            const bool fits = tile_base + prev.tile_agg <= capacity;
+            if (!(prev.slow & WARP_SLOW)) {
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k) {
-                    const uint32_t c = prev.cnt[k], o = prev.off[k];
-                    if (!((prev.slow >> k) & 1)) {
-                        if (c >= 1) __stcs(outp + o, (DESC && c == 2) ? prev.v1[k] : prev.v0[k]);
-                        if (c == 2) __stcs(outp + o + 1, DESC ? prev.v0[k] : prev.v1[k]);
+                    const uint32_t c = (prev.cntpack >> (2 * k)) & 3, o = (prev.offpack >> (8 * k)) & 0xFF;
+                    if (OFFS && tile_start + wl + 32 * k < n) out_offsets[tile_start + wl + 32 * k] = warp_base + o;
+                    if (c == 0) continue;
+                    uint32_t a = prev.v0[k], b = 0;
+                    if (c == 2) {
+                        b = s_v1[ppar][wl + 32 * k];
+                        if (DESC) { const uint32_t t = a; a = b; b = t; }
+                    }
+                    if (fits) {
+                        __stcs(outp + o, a);
+                        if (c == 2) __stcs(outp + o + 1, b);
+                    } else {
+                        if (warp_base + o < capacity) out_ids[warp_base + o] = a;
+                        if (c == 2 && warp_base + o + 1 < capacity) out_ids[warp_base + o + 1] = b;
                     }
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k) {
-                    const uint32_t c = prev.cnt[k];
-                    const uint64_t pos = warp_base + prev.off[k];
-                    if (!((prev.slow >> k) & 1)) {
-                        if (c >= 1 && pos < capacity) out_ids[pos] = (DESC && c == 2) ? prev.v1[k] : prev.v0[k];
-                        if (c == 2 && pos + 1 < capacity) out_ids[pos + 1] = DESC ? prev.v0[k] : prev.v1[k];
+                    const uint32_t c = (prev.cntpack >> (2 * k)) & 3, o = s_off[ppar][wl + 32 * k];
+                    const uint64_t pos = warp_base + o;
+                    const uint64_t q = tile_start + wl + 32 * k;
+                    if (OFFS && q < n) out_offsets[q] = pos;
+                    if (c == 0) continue;
+                    if ((prev.slow >> k) & 1) {
+                        // q < n here: an out-of-range query has count 0
+                        emit_query_walk(ix, __ldg(chr + q), __ldg(start + q), __ldg(end + q), min_bp, out_ids, pos, capacity);
+                    } else {
+                        uint32_t a = prev.v0[k], b = 0;
+                        if (c == 2) {
+                            b = s_v1[ppar][wl + 32 * k];
+                            if (DESC) { const uint32_t t = a; a = b; b = t; }
+                        }
+                        if (pos < capacity) out_ids[pos] = a;
+                        if (c == 2 && pos + 1 < capacity) out_ids[pos + 1] = b;
                     }
                 }
             }
-            if (__any_sync(FULL, prev.slow != 0)) {
-                const uint64_t lane_start = tile_start + (uint64_t)warp * WTILE + lane;
-#pragma unroll
-                for (int k = 0; k < ROWS; ++k)
-                    if (((prev.slow >> k) & 1) && prev.cnt[k]) {
-                        const uint64_t q = lane_start + 32 * k;  // q < n: an out-of-range query has cnt == 0
-                        emit_query_walk(ix, __ldg(chr + q), __ldg(start + q), __ldg(end + q), min_bp, out_ids,
-                                        warp_base + prev.off[k], capacity);
-                    }
-            }
-
             PHASE_MARK(6);
+
             // ---- file boundaries inside this tile: raw token offset of each file's first query ------------------------
             if (out_file_tok) {
                 const uint32_t mark = __ldg(ws.tile_file + prev.tile);  // block-uniform
                 if (mark != 0) {
+                    // every warp publishes full offsets (tile-relative) for this rare tile, then boundaries are looked up
+                    __syncthreads();
 #pragma unroll
-                    for (int k = 0; k < ROWS; ++k) s_qoff[warp * WTILE + 32 * k + lane] = prev.warp_excl + prev.off[k];
-                    if (tid == 0) s_qoff[TILE] = prev.tile_agg;
+                    for (int k = 0; k < ROWS; ++k) {
+                        const uint32_t o = (prev.slow & WARP_SLOW) ? s_off[ppar][wl + 32 * k] : (prev.offpack >> (8 * k)) & 0xFF;
+                        s_off[ppar][wl + 32 * k] = prev.warp_excl + o;
+                    }
                     __syncthreads();
                     const uint64_t limit = (prev.tile == n_tiles - 1) ? n + 1 : tile_start + TILE;
                     for (uint64_t f = (uint64_t)(0xFFFFFFFFu - mark) + tid; f <= n_files; f += FUSED_BLOCK) {
                         const uint64_t qi = file_offsets[f];
                         if (qi >= limit) break;
-                        out_file_tok[f] = tile_base + s_qoff[qi - tile_start];
+                        const uint32_t r = (uint32_t)(qi - tile_start);
+                        out_file_tok[f] = tile_base + (r < (uint32_t)TILE ? s_off[ppar][r] : prev.tile_agg);
                     }
                     __syncthreads();
                 }
