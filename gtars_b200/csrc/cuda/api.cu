@@ -168,6 +168,7 @@ int32_t gtgpu_init(int32_t device, void* stream_or_null, gtgpu_ctx** out_ctx) {
 int32_t gtgpu_shutdown(gtgpu_ctx* ctx) {
     if (!ctx) return GTGPU_OK;
     cudaSetDevice(ctx->device);
+    gtgpu_comm_free(ctx);
     cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->scratch)
         if (b.ptr) cudaFree(b.ptr);

@@ -113,6 +113,7 @@ struct gtgpu_ctx {
     std::vector<gtgpu::DevBuffer> scratch;       // grow-only device scratch, indexed by role
     std::vector<gtgpu::PinnedBlock> pinned_free;  // cache of pinned result blocks
     uint64_t* h_scalars = nullptr;                // small pinned mailbox
+    void* comm = nullptr;                         // gtgpu::Comm (NCCL), set by gtgpu_comm_init
     bool timing = false;                          // bracket dominant kernels with events
     std::vector<cudaEvent_t> ev_begin, ev_end;
     uint32_t ev_used = 0;
@@ -177,6 +178,7 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
 // Per-call [unk] rule: expands raw per-file id runs into d_out, inserting unk_id for files with no ids.
 int32_t launch_unk_offsets(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* d_raw_file_tok,
                            uint64_t* d_out_file_tok, uint64_t* d_n_empty);
+int32_t launch_fill_set_ids(gtgpu_ctx* ctx, uint64_t n_sets, const uint64_t* d_set_offsets, uint32_t* d_set_of);
 int32_t launch_unk_expand(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* d_raw_file_tok,
                           const uint64_t* d_out_file_tok, const uint32_t* d_raw_ids, uint32_t unk_id,
                           uint32_t* d_out_ids);

@@ -1,0 +1,169 @@
+// fragments.cu — tokenize_fragment_file on the device (gtars-tokenizers/src/utils/fragments.rs:12-82).
+//
+// Every fragment is its own Tokenizer::tokenize call, so a fragment without a hit (or on an unknown chromosome)
+// contributes one unk id; ids are appended to the fragment's barcode list in input order.  Device plan:
+//   1. fused find over all fragments with per-fragment offsets            (kernels.cu, our kernel)
+//   2. stable LSD radix sort of (barcode id, fragment index) by barcode   (CUB DeviceRadixSort — library code)
+//   3. tokens per fragment in sorted order = max(hits, 1); exclusive sum  (CUB DeviceScan — library code)
+//   4. barcode offsets by binary search over the sorted keys; scatter-copy of every fragment's ids (our kernels)
+// Output is barcode-major: out_barcode_offsets[n_barcodes + 1] + ids.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+namespace gtgpu {
+
+__global__ void iota_kernel(uint64_t n, uint32_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (uint32_t)i;
+}
+
+// tokens of the k-th fragment in barcode order
+__global__ void frag_token_counts_kernel(uint64_t n, const uint32_t* __restrict__ order, const uint64_t* __restrict__ offsets,
+                                         uint64_t* __restrict__ counts) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const uint32_t i = order[k];
+        const uint64_t c = offsets[i + 1] - offsets[i];
+        counts[k] = c ? c : 1;
+    }
+}
+
+__global__ void frag_barcode_offsets_kernel(uint32_t n_barcodes, uint64_t n, const uint32_t* __restrict__ sorted_bc,
+                                            const uint64_t* __restrict__ dst, const uint64_t* __restrict__ last_count,
+                                            uint64_t* __restrict__ out) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_barcodes) return;
+    uint64_t lo = 0, hi = n;  // first k with sorted_bc[k] >= b
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (sorted_bc[mid] < b) lo = mid + 1;
+        else hi = mid;
+    }
+    out[b] = lo < n ? dst[lo] : (n ? dst[n - 1] + last_count[n - 1] : 0);
+}
+
+__global__ void frag_scatter_kernel(uint64_t n, const uint32_t* __restrict__ order, const uint64_t* __restrict__ offsets,
+                                    const uint64_t* __restrict__ dst, const uint32_t* __restrict__ raw_ids, uint32_t unk_id,
+                                    uint32_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const uint32_t i = order[k];
+        const uint64_t a = offsets[i], b = offsets[i + 1];
+        uint64_t d = dst[k];
+        if (a == b) {
+            out[d] = unk_id;
+        } else {
+            for (uint64_t j = a; j < b; ++j) out[d++] = raw_ids[j];
+        }
+    }
+}
+
+}  // namespace gtgpu
+
+using namespace gtgpu;
+
+extern "C" int32_t gtgpu_tokenize_fragments(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start,
+                                            const uint32_t* end, const uint32_t* barcode_id, uint32_t n_barcodes,
+                                            uint32_t unk_id, uint64_t* out_barcode_offsets, gtgpu_buf** out_ids) {
+    if (!ix || !out_barcode_offsets || !out_ids || (n && (!chr || !start || !end || !barcode_id)))
+        return fail(GTGPU_ERR_INVALID, "tokenize_fragments: null argument");
+    if (n >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "tokenize_fragments: more than 2^32-2 fragments per call");
+    for (uint64_t i = 0; i < n; ++i)
+        if (barcode_id[i] >= n_barcodes) return fail(GTGPU_ERR_INVALID, "tokenize_fragments: barcode id out of range");
+    gtgpu_ctx* ctx = ix->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    GT_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+
+    uint32_t *d_chr, *d_start, *d_end, *d_bc, *d_bc_sorted, *d_idx, *d_order, *d_raw = nullptr, *d_out = nullptr;
+    uint64_t *d_off, *d_cnt, *d_dst, *d_bco, *d_misc;
+    void* d_ws;
+    GT_TRY(ctx->scratch_get(SC_CHR, n * 4, (void**)&d_chr));
+    GT_TRY(ctx->scratch_get(SC_START, n * 4, (void**)&d_start));
+    GT_TRY(ctx->scratch_get(SC_END, n * 4, (void**)&d_end));
+    GT_TRY(ctx->scratch_get(SC_BARCODE, n * 4, (void**)&d_bc));
+    GT_TRY(ctx->scratch_get(SC_IN2_CHR, n * 4, (void**)&d_bc_sorted));
+    GT_TRY(ctx->scratch_get(SC_IN2_START, n * 4, (void**)&d_idx));
+    GT_TRY(ctx->scratch_get(SC_IN2_END, n * 4, (void**)&d_order));
+    GT_TRY(ctx->scratch_get(SC_OUT_OFFS, (n + 1) * 8, (void**)&d_off));
+    GT_TRY(ctx->scratch_get(SC_COUNTS, (n + 1) * 8, (void**)&d_cnt));
+    GT_TRY(ctx->scratch_get(SC_IN3_CHR, (n + 1) * 8, (void**)&d_dst));
+    GT_TRY(ctx->scratch_get(SC_FILE_TOK, ((uint64_t)n_barcodes + 1) * 8, (void**)&d_bco));
+    GT_TRY(ctx->scratch_get(SC_TILE_STATUS, fused_workspace_bytes(n), &d_ws));
+    GT_TRY(ctx->scratch_get(SC_MISC, 64, (void**)&d_misc));
+    if (n) {
+        GT_CUDA(cudaMemcpyAsync(d_chr, chr, n * 4, cudaMemcpyHostToDevice, st));
+        GT_CUDA(cudaMemcpyAsync(d_start, start, n * 4, cudaMemcpyHostToDevice, st));
+        GT_CUDA(cudaMemcpyAsync(d_end, end, n * 4, cudaMemcpyHostToDevice, st));
+        GT_CUDA(cudaMemcpyAsync(d_bc, barcode_id, n * 4, cudaMemcpyHostToDevice, st));
+    }
+
+    // 1. hits of every fragment, raw (no unk yet), with per-fragment offsets
+    uint64_t cap = n + n / 4 + 1024, total = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        GT_TRY(ctx->scratch_get(SC_OUT_IDS, cap * 4, (void**)&d_raw));
+        GT_CUDA(cudaMemsetAsync(d_misc, 0, 64, st));
+        GT_TRY(launch_fused_find(ix, n, 0, nullptr, d_chr, d_start, d_end, 0, d_raw, cap, d_off, nullptr, d_ws, nullptr, d_misc,
+                                 (uint32_t*)(d_misc + 2)));
+        GT_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_misc, 24, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+        total = ctx->h_scalars[0];
+        if ((uint32_t)ctx->h_scalars[2] != 0) return fail(GTGPU_ERR_UNSUPPORTED, "tokenize_fragments: tile overflow");
+        if (total <= cap) break;
+        if (attempt == 1) return fail(GTGPU_ERR_CAPACITY, "tokenize_fragments: output capacity exceeded twice");
+        cap = total;
+    }
+
+    uint64_t final_total = 0;
+    if (n) {
+        // 2. stable sort of fragment indices by barcode
+        const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 16);
+        iota_kernel<<<grid, 256, 0, st>>>(n, d_idx);
+        ctx->launches++;
+        int bits = 1;
+        while (bits < 32 && (1ull << bits) < n_barcodes) ++bits;
+        size_t tmp_sort = 0, tmp_scan = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, d_bc, d_bc_sorted, d_idx, d_order, (int64_t)n, 0, bits, st);
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, d_cnt, d_dst, (int64_t)n, st);
+        void* d_tmp = nullptr;
+        GT_TRY(ctx->scratch_get(SC_IN3_START, std::max(tmp_sort, tmp_scan), &d_tmp));
+        GT_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_sort, d_bc, d_bc_sorted, d_idx, d_order, (int64_t)n, 0, bits, st));
+        // 3. tokens per fragment (per-fragment unk rule) and their destinations
+        frag_token_counts_kernel<<<grid, 256, 0, st>>>(n, d_order, d_off, d_cnt);
+        ctx->launches++;
+        GT_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_scan, d_cnt, d_dst, (int64_t)n, st));
+        // 4. barcode offsets + scatter
+        frag_barcode_offsets_kernel<<<(n_barcodes + 1 + 255) / 256, 256, 0, st>>>(n_barcodes, n, d_bc_sorted, d_dst, d_cnt, d_bco);
+        ctx->launches++;
+        GT_CUDA(cudaMemcpyAsync(out_barcode_offsets, d_bco, ((uint64_t)n_barcodes + 1) * 8, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+        final_total = out_barcode_offsets[n_barcodes];
+        GT_TRY(ctx->scratch_get(SC_OUT_IDS2, final_total * 4, (void**)&d_out));
+        frag_scatter_kernel<<<grid, 256, 0, st>>>(n, d_order, d_off, d_dst, d_raw, unk_id, d_out);
+        ctx->launches++;
+        GT_CUDA(cudaGetLastError());
+    } else {
+        for (uint32_t b = 0; b <= n_barcodes; ++b) out_barcode_offsets[b] = 0;
+    }
+
+    gtgpu_buf* buf = new gtgpu_buf();
+    buf->ctx = ctx;
+    buf->len = final_total;
+    int32_t s = ctx->pinned_get(final_total * 4, &buf->block);
+    if (s != GTGPU_OK) {
+        delete buf;
+        return s;
+    }
+    cudaError_t e = cudaSuccess;
+    if (final_total) e = cudaMemcpyAsync(buf->block.ptr, d_out, final_total * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        ctx->pinned_put(buf->block);
+        delete buf;
+        return fail(GTGPU_ERR_CUDA, std::string("tokenize_fragments: D2H: ") + cudaGetErrorString(e));
+    }
+    *out_ids = buf;
+    return GTGPU_OK;
+}

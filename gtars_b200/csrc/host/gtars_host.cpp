@@ -1,0 +1,576 @@
+// gtars_host.cpp — implementation of gtars_host.hpp (host-side mirror of the reference API; all overlap work goes
+// through the C ABI of include/gtars_gpu.h).
+#include "gtars_host.hpp"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstring>
+#include <fstream>
+#include <set>
+#include <sstream>
+
+namespace gtars {
+
+namespace {
+
+[[noreturn]] void throw_gpu(const char* what) { throw Error(std::string(what) + ": " + gtgpu_last_error()); }
+void check(int32_t status, const char* what) {
+    if (status != GTGPU_OK) throw_gpu(what);
+}
+
+// get_dynamic_reader (gtars-core/src/utils.rs:115-126): gzip iff the extension is "gz"; BufRead::lines() semantics.
+std::vector<std::string> read_lines(const std::string& path) {
+    std::string data;
+    const bool gz = path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0;
+    if (gz) {
+        gzFile f = gzopen(path.c_str(), "rb");
+        if (!f) throw Error("Failed to open file: \"" + path + "\"");
+        char buf[1 << 16];
+        int n;
+        while ((n = gzread(f, buf, sizeof buf)) > 0) data.append(buf, n);
+        gzclose(f);
+    } else {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw Error("Failed to open file: \"" + path + "\"");
+        std::stringstream ss;
+        ss << f.rdbuf();
+        data = ss.str();
+    }
+    std::vector<std::string> lines;
+    size_t pos = 0;
+    while (pos < data.size()) {
+        size_t nl = data.find('\n', pos);
+        size_t end = nl == std::string::npos ? data.size() : nl;
+        lines.emplace_back(data, pos, end - pos);
+        if (!lines.back().empty() && lines.back().back() == '\r') lines.back().pop_back();
+        pos = nl == std::string::npos ? data.size() : nl + 1;
+    }
+    return lines;
+}
+
+std::vector<std::string> split_on(const std::string& s, char sep) {
+    std::vector<std::string> out;
+    size_t pos = 0;
+    for (;;) {
+        size_t k = s.find(sep, pos);
+        if (k == std::string::npos) {
+            out.emplace_back(s, pos);
+            return out;
+        }
+        out.emplace_back(s, pos, k - pos);
+        pos = k + 1;
+    }
+}
+
+std::vector<std::string> split_whitespace(const std::string& s) {
+    std::vector<std::string> out;
+    size_t i = 0;
+    while (i < s.size()) {
+        while (i < s.size() && isspace((unsigned char)s[i])) ++i;
+        size_t j = i;
+        while (j < s.size() && !isspace((unsigned char)s[j])) ++j;
+        if (j > i) out.emplace_back(s, i, j - i);
+        i = j;
+    }
+    return out;
+}
+
+bool parse_u32(const std::string& s, uint32_t& out) {  // Rust's str::parse::<u32>()
+    size_t i = (!s.empty() && s[0] == '+') ? 1 : 0;
+    if (i >= s.size()) return false;
+    uint64_t v = 0;
+    for (; i < s.size(); ++i) {
+        if (s[i] < '0' || s[i] > '9') return false;
+        v = v * 10 + (uint64_t)(s[i] - '0');
+        if (v > 0xFFFFFFFFull) return false;
+    }
+    out = (uint32_t)v;
+    return true;
+}
+
+bool has_prefix(const std::string& s, const char* p) { return s.rfind(p, 0) == 0; }
+
+std::string trim(const std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && isspace((unsigned char)s[a])) ++a;
+    while (b > a && isspace((unsigned char)s[b - 1])) --b;
+    return s.substr(a, b - a);
+}
+
+struct PinnedResult {  // RAII over gtgpu_buf
+    gtgpu_buf* buf = nullptr;
+    ~PinnedResult() { gtgpu_buf_free(buf); }
+    const uint32_t* data() const { return (const uint32_t*)gtgpu_buf_data(buf); }
+    uint64_t len() const { return gtgpu_buf_len(buf); }
+};
+
+}  // namespace
+
+// ---- RegionSet ---------------------------------------------------------------------------------------------------------
+RegionSet RegionSet::from_file(const std::string& path) {
+    RegionSet rs;
+    bool first_line = true;
+    for (const auto& line : read_lines(path)) {
+        auto parts = split_on(line, '\t');
+        if (has_prefix(line, "browser") || has_prefix(line, "track") || has_prefix(line, "#")) {
+            rs.header += line;
+            first_line = false;
+            continue;
+        }
+        if (first_line) {
+            first_line = false;
+            uint32_t tmp;
+            if (parts.size() >= 3 && !parse_u32(parts[1], tmp)) {  // column header row without '#'
+                rs.header += line;
+                continue;
+            }
+        }
+        Region r;
+        if (parts.size() < 3 || !parse_u32(parts[1], r.start)) throw Error("Error in parsing start position: " + line);
+        if (!parse_u32(parts[2], r.end)) throw Error("Error in parsing end position: " + line);
+        r.chr = parts[0];
+        for (size_t k = 3; k < parts.size(); ++k) r.rest += (k > 3 ? "\t" : "") + parts[k];
+        rs.regions.push_back(std::move(r));
+    }
+    if (rs.regions.empty()) throw Error("Corrupted file. 0 regions found in the file: " + path);
+    rs.sort();
+    return rs;
+}
+
+void RegionSet::sort() {
+    std::stable_sort(regions.begin(), regions.end(), [](const Region& a, const Region& b) {
+        int c = a.chr.compare(b.chr);
+        return c != 0 ? c < 0 : a.start < b.start;
+    });
+}
+
+// ---- Device / ChromMap -----------------------------------------------------------------------------------------------------
+Device::Device(int device) { check(gtgpu_init(device, nullptr, &ctx_), "gtgpu_init"); }
+Device::~Device() { gtgpu_shutdown(ctx_); }
+
+uint32_t ChromMap::add(const std::string& name) {
+    auto it = ids_.find(name);
+    if (it != ids_.end()) return it->second;
+    uint32_t id = (uint32_t)names_.size();
+    ids_.emplace(name, id);
+    names_.push_back(name);
+    return id;
+}
+uint32_t ChromMap::get(const std::string& name) const {
+    auto it = ids_.find(name);
+    return it == ids_.end() ? GTGPU_UNKNOWN_CHROM : it->second;
+}
+
+FlatQueries flatten(const std::vector<Region>& regions, const ChromMap& cmap) {
+    FlatQueries q;
+    q.chr.reserve(regions.size());
+    q.start.reserve(regions.size());
+    q.end.reserve(regions.size());
+    for (const auto& r : regions) {
+        q.chr.push_back(cmap.get(r.chr));
+        q.start.push_back(r.start);
+        q.end.push_back(r.end);
+    }
+    return q;
+}
+
+namespace {
+
+// Intervals in insertion order -> chromosome-grouped arrays (insertion order kept inside a chromosome).
+struct Grouped {
+    std::vector<uint64_t> offsets;
+    std::vector<uint32_t> start, end, val;
+};
+Grouped group_by_chrom(const std::vector<uint32_t>& chr, const std::vector<uint32_t>& start, const std::vector<uint32_t>& end,
+                       const std::vector<uint32_t>& val, size_t n_chroms) {
+    Grouped g;
+    g.offsets.assign(n_chroms + 1, 0);
+    for (uint32_t c : chr) g.offsets[c + 1]++;
+    for (size_t c = 0; c < n_chroms; ++c) g.offsets[c + 1] += g.offsets[c];
+    std::vector<uint64_t> cursor(g.offsets.begin(), g.offsets.end() - 1);
+    g.start.resize(chr.size());
+    g.end.resize(chr.size());
+    g.val.resize(chr.size());
+    for (size_t i = 0; i < chr.size(); ++i) {
+        uint64_t p = cursor[chr[i]]++;
+        g.start[p] = start[i];
+        g.end[p] = end[i];
+        g.val[p] = val[i];
+    }
+    return g;
+}
+
+}  // namespace
+
+// ---- MultiChromOverlapper ---------------------------------------------------------------------------------------------------
+MultiChromOverlapper::MultiChromOverlapper(std::shared_ptr<Device> dev, const RegionSet& source, OverlapperType kind)
+    : dev_(std::move(dev)) {
+    std::vector<uint32_t> chr, start, end, val;
+    for (size_t i = 0; i < source.regions.size(); ++i) {
+        const Region& r = source.regions[i];
+        chr.push_back(cmap_.add(r.chr));
+        start.push_back(r.start);
+        end.push_back(r.end);
+        val.push_back((uint32_t)i);
+        source_.push_back(Region{r.chr, r.start, r.end, ""});
+    }
+    Grouped g = group_by_chrom(chr, start, end, val, cmap_.size());
+    check(gtgpu_index_build(dev_->ctx(), (int32_t)kind, (uint32_t)cmap_.size(), g.offsets.data(), g.start.data(), g.end.data(),
+                            g.val.data(), &index_),
+          "gtgpu_index_build");
+}
+MultiChromOverlapper::~MultiChromOverlapper() { gtgpu_index_free(index_); }
+
+std::vector<uint64_t> MultiChromOverlapper::count_overlaps(const RegionSet& query, int32_t min_overlap) const {
+    FlatQueries q = flatten(query.regions, cmap_);
+    std::vector<uint32_t> counts(q.chr.size());
+    check(gtgpu_count(index_, q.chr.size(), q.chr.data(), q.start.data(), q.end.data(), std::max(min_overlap, 0), counts.data()),
+          "gtgpu_count");
+    return std::vector<uint64_t>(counts.begin(), counts.end());
+}
+
+std::vector<bool> MultiChromOverlapper::any_overlaps(const RegionSet& query, int32_t min_overlap) const {
+    FlatQueries q = flatten(query.regions, cmap_);
+    std::vector<uint8_t> any(q.chr.size());
+    check(gtgpu_any(index_, q.chr.size(), q.chr.data(), q.start.data(), q.end.data(), std::max(min_overlap, 0), any.data()),
+          "gtgpu_any");
+    return std::vector<bool>(any.begin(), any.end());
+}
+
+std::vector<std::vector<uint32_t>> MultiChromOverlapper::find_overlaps_indices(const RegionSet& query, int32_t min_overlap) const {
+    FlatQueries q = flatten(query.regions, cmap_);
+    std::vector<uint64_t> offsets(q.chr.size() + 1);
+    PinnedResult res;
+    check(gtgpu_find(index_, q.chr.size(), q.chr.data(), q.start.data(), q.end.data(), std::max(min_overlap, 0), offsets.data(),
+                     &res.buf),
+          "gtgpu_find");
+    std::vector<std::vector<uint32_t>> out(q.chr.size());
+    for (size_t i = 0; i < out.size(); ++i) out[i].assign(res.data() + offsets[i], res.data() + offsets[i + 1]);
+    return out;
+}
+
+std::vector<std::vector<Region>> MultiChromOverlapper::find_overlaps_regions(const RegionSet& query, int32_t min_overlap) const {
+    auto idx = find_overlaps_indices(query, min_overlap);
+    std::vector<std::vector<Region>> out(idx.size());
+    for (size_t i = 0; i < idx.size(); ++i)
+        for (uint32_t v : idx[i]) out[i].push_back(Region{query.regions[i].chr, source_[v].start, source_[v].end, ""});
+    return out;
+}
+
+RegionSet MultiChromOverlapper::subset_by(const RegionSet& query, int32_t min_overlap) const {
+    std::set<std::tuple<std::string, uint32_t, uint32_t>> hits;  // BTreeSet<(String, u32, u32)>
+    auto idx = find_overlaps_indices(query, min_overlap);
+    for (size_t i = 0; i < idx.size(); ++i)
+        for (uint32_t v : idx[i]) hits.emplace(query.regions[i].chr, source_[v].start, source_[v].end);
+    RegionSet rs;
+    for (const auto& h : hits) rs.regions.push_back(Region{std::get<0>(h), std::get<1>(h), std::get<2>(h), ""});
+    return rs;
+}
+
+// ---- Universe ---------------------------------------------------------------------------------------------------------------
+Universe Universe::from_file(const std::string& path) {
+    Universe u;
+    auto lines = read_lines(path);
+    if (lines.empty()) throw Error("Unable to determine universe type");
+    int ftype = 0;  // universe/utils.rs:7-19
+    if (!has_prefix(lines[0], "track")) {
+        size_t nf = split_on(lines[0], '\t').size();
+        if (nf == 3) ftype = 3;
+        else if (nf >= 5) ftype = 5;
+    }
+    if (!ftype) throw Error("Unable to determine universe type");
+    for (const auto& line : lines) {
+        auto parts = ftype == 3 ? split_whitespace(line) : split_on(line, '\t');
+        if (ftype == 3 ? parts.size() != 3 : parts.size() < 5) throw Error("Error parsing line: " + line);
+        u.regions.push_back(parts[0] + ":" + parts[1] + "-" + parts[2]);
+    }
+    for (const auto& r : u.regions) u.region_to_id.emplace(r, (uint32_t)u.region_to_id.size());
+    for (size_t i = 0; i < u.regions.size(); ++i) u.id_to_region[(uint32_t)i] = u.regions[i];
+    return u;
+}
+
+void Universe::add_token_to_universe(const std::string& tok) {
+    uint32_t id = (uint32_t)region_to_id.size();
+    region_to_id[tok] = id;
+    id_to_region[id] = tok;
+    regions.push_back(tok);
+}
+
+// ---- Tokenizer ----------------------------------------------------------------------------------------------------------------
+void Tokenizer::build(std::shared_ptr<Device> dev, Universe universe, SpecialTokens special, OverlapperType kind) {
+    dev_ = std::move(dev);
+    universe_ = std::move(universe);
+    special_ = std::move(special);
+    kind_ = kind;
+    universe_.special_tokens = special_.as_vec();  // universe/mod.rs:114-120
+    for (const auto& t : universe_.special_tokens) universe_.add_token_to_universe(t);
+    unk_id_ = universe_.region_to_id.at(special_.unk);
+    id_to_first_token_.resize(universe_.region_to_id.size());
+    for (const auto& kv : universe_.region_to_id) id_to_first_token_[kv.second] = kv.first;
+
+    // create_tokenize_core_from_universe (utils/mod.rs:49-99).  The reference's tokenize() maps each hit's val to a
+    // string (id_to_region, positional) and encode() maps that back (region_to_id, first appearance); the composition
+    // is folded into val here so the device emits final ids (identity unless the universe has duplicate lines).
+    std::vector<uint32_t> chr, start, end, val;
+    for (const auto& region : universe_.regions) {
+        if (std::find(universe_.special_tokens.begin(), universe_.special_tokens.end(), region) != universe_.special_tokens.end())
+            continue;
+        auto parts = split_on(region, ':');
+        auto se = parts.size() > 1 ? split_on(parts[1], '-') : std::vector<std::string>{};
+        uint32_t s, e;
+        if (se.size() < 2 || !parse_u32(se[0], s) || !parse_u32(se[1], e)) throw Error("cannot parse universe region " + region);
+        uint32_t v = universe_.region_to_id.at(region);
+        uint32_t folded = universe_.region_to_id.at(universe_.id_to_region.at(v));
+        chr.push_back(cmap_.add(parts[0]));
+        start.push_back(s);
+        end.push_back(e);
+        val.push_back(folded);
+    }
+    Grouped g = group_by_chrom(chr, start, end, val, cmap_.size());
+    check(gtgpu_index_build(dev_->ctx(), (int32_t)kind, (uint32_t)cmap_.size(), g.offsets.data(), g.start.data(), g.end.data(),
+                            g.val.data(), &index_),
+          "gtgpu_index_build");
+}
+
+Tokenizer::~Tokenizer() { gtgpu_index_free(index_); }
+
+std::unique_ptr<Tokenizer> Tokenizer::from_bed(std::shared_ptr<Device> dev, const std::string& path) {
+    std::unique_ptr<Tokenizer> t(new Tokenizer());
+    t->build(std::move(dev), Universe::from_file(path), SpecialTokens{}, OverlapperType::Bits);
+    return t;
+}
+
+std::unique_ptr<Tokenizer> Tokenizer::from_config(std::shared_ptr<Device> dev, const std::string& path) {
+    // The subset of TOML the reference's TokenizerConfig uses (config.rs:36-41): universe = "...",
+    // tokenizer_type = "bits" | "ailist", special_tokens = [ {name="unk", token="..."}, ... ].
+    std::ifstream f(path);
+    if (!f) throw Error("No such file: " + path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string text = ss.str();
+    std::string universe_file;
+    OverlapperType kind = OverlapperType::Bits;
+    SpecialTokens special;
+    auto value_of = [&](const std::string& key) -> std::string {
+        size_t pos = 0;
+        while ((pos = text.find(key, pos)) != std::string::npos) {
+            bool at_line_start = pos == 0 || text[pos - 1] == '\n';
+            size_t eq = text.find('=', pos);
+            if (at_line_start && eq != std::string::npos && trim(text.substr(pos + key.size(), eq - pos - key.size())).empty()) {
+                size_t q1 = text.find('"', eq), q2 = q1 == std::string::npos ? q1 : text.find('"', q1 + 1);
+                if (q2 != std::string::npos) return text.substr(q1 + 1, q2 - q1 - 1);
+            }
+            pos += key.size();
+        }
+        return "";
+    };
+    universe_file = value_of("universe");
+    if (universe_file.empty()) throw Error("missing field `universe` in " + path);
+    std::string tt = value_of("tokenizer_type");
+    if (!tt.empty()) {
+        if (tt == "bits") kind = OverlapperType::Bits;
+        else if (tt == "ailist") kind = OverlapperType::AIList;
+        else throw Error("unknown variant `" + tt + "`, expected `bits` or `ailist`");
+    }
+    size_t st = text.find("special_tokens");
+    if (st != std::string::npos) {
+        size_t pos = st;
+        while ((pos = text.find('{', pos)) != std::string::npos) {
+            size_t close = text.find('}', pos);
+            if (close == std::string::npos) break;
+            std::string item = text.substr(pos + 1, close - pos - 1);
+            std::string name, token;
+            for (const auto& kv : split_on(item, ',')) {
+                size_t eq = kv.find('=');
+                if (eq == std::string::npos) continue;
+                std::string k = trim(kv.substr(0, eq)), v = trim(kv.substr(eq + 1));
+                if (v.size() >= 2 && v.front() == '"' && v.back() == '"') v = v.substr(1, v.size() - 2);
+                if (k == "name") name = v;
+                if (k == "token") token = v;
+            }
+            if (name == "unk") special.unk = token;
+            else if (name == "pad") special.pad = token;
+            else if (name == "mask") special.mask = token;
+            else if (name == "cls") special.cls = token;
+            else if (name == "bos") special.bos = token;
+            else if (name == "eos") special.eos = token;
+            else if (name == "sep") special.sep = token;
+            else throw Error("unknown special token name `" + name + "`");
+            pos = close + 1;
+        }
+    }
+    size_t slash = path.find_last_of('/');
+    std::string dir = slash == std::string::npos ? "" : path.substr(0, slash + 1);
+    std::unique_ptr<Tokenizer> t(new Tokenizer());
+    t->build(std::move(dev), Universe::from_file(dir + universe_file), special, kind);
+    return t;
+}
+
+std::unique_ptr<Tokenizer> Tokenizer::from_auto(std::shared_ptr<Device> dev, const std::string& path) {
+    auto ends_with = [&](const char* suf) {
+        size_t n = strlen(suf);
+        return path.size() >= n && path.compare(path.size() - n, n, suf) == 0;
+    };
+    if (ends_with(".toml")) return from_config(std::move(dev), path);
+    if (ends_with(".bed") || ends_with(".bed.gz")) return from_bed(std::move(dev), path);
+    throw Error("Missing or invalid file extension in tokenizer config file. It must be `toml`, `bed` or `bed.gz`");
+}
+
+std::vector<std::vector<uint32_t>> Tokenizer::encode_batch(const std::vector<const std::vector<Region>*>& calls) const {
+    std::vector<uint64_t> file_offsets(calls.size() + 1, 0);
+    FlatQueries q;
+    for (size_t f = 0; f < calls.size(); ++f) {
+        for (const auto& r : *calls[f]) {
+            q.chr.push_back(cmap_.get(r.chr));
+            q.start.push_back(r.start);
+            q.end.push_back(r.end);
+        }
+        file_offsets[f + 1] = q.chr.size();
+    }
+    std::vector<uint64_t> tok_offsets(calls.size() + 1);
+    PinnedResult res;
+    check(gtgpu_tokenize_files(index_, calls.size(), file_offsets.data(), q.chr.data(), q.start.data(), q.end.data(), unk_id_,
+                               tok_offsets.data(), &res.buf),
+          "gtgpu_tokenize_files");
+    std::vector<std::vector<uint32_t>> out(calls.size());
+    for (size_t f = 0; f < calls.size(); ++f) out[f].assign(res.data() + tok_offsets[f], res.data() + tok_offsets[f + 1]);
+    return out;
+}
+
+std::vector<uint32_t> Tokenizer::encode(const std::vector<Region>& regions) const { return encode_batch({&regions})[0]; }
+
+std::vector<std::string> Tokenizer::tokenize(const std::vector<Region>& regions) const {
+    std::vector<std::string> out;
+    for (uint32_t id : encode(regions)) out.push_back(id_to_first_token_.at(id));
+    return out;
+}
+
+std::vector<std::string> Tokenizer::decode(const std::vector<uint32_t>& ids) const {
+    std::vector<std::string> out;
+    for (uint32_t id : ids) {
+        auto it = universe_.id_to_region.find(id);
+        out.push_back(it == universe_.id_to_region.end() ? special_.unk : it->second);  // tokenizer.rs:173-181
+    }
+    return out;
+}
+
+int64_t Tokenizer::convert_token_to_id(const std::string& tok) const {
+    auto it = universe_.region_to_id.find(tok);
+    return it == universe_.region_to_id.end() ? -1 : (int64_t)it->second;
+}
+const std::string* Tokenizer::convert_id_to_token(uint32_t id) const {
+    auto it = universe_.id_to_region.find(id);
+    return it == universe_.id_to_region.end() ? nullptr : &it->second;
+}
+
+std::vector<std::pair<std::string, std::vector<uint32_t>>> Tokenizer::tokenize_fragment_file(const std::string& path) const {
+    // parse_fragment_line (fragments.rs:12-56): split_whitespace, >= 5 fields, chr start end barcode
+    std::vector<std::string> barcodes;
+    std::unordered_map<std::string, uint32_t> bc_ids;
+    FlatQueries q;
+    std::vector<uint32_t> bc;
+    auto lines = read_lines(path);
+    for (size_t i = 0; i < lines.size(); ++i) {
+        if (has_prefix(lines[i], "#")) continue;
+        auto parts = split_whitespace(lines[i]);
+        if (parts.size() < 5) throw Error("Invalid fragment file detected at line: " + std::to_string(i));
+        uint32_t s, e;
+        if (!parse_u32(parts[1], s)) throw Error("Failed to parse start position at line " + std::to_string(i));
+        if (!parse_u32(parts[2], e)) throw Error("Failed to parse end position at line " + std::to_string(i));
+        auto it = bc_ids.find(parts[3]);
+        if (it == bc_ids.end()) {
+            it = bc_ids.emplace(parts[3], (uint32_t)barcodes.size()).first;
+            barcodes.push_back(parts[3]);
+        }
+        q.chr.push_back(cmap_.get(parts[0]));
+        q.start.push_back(s);
+        q.end.push_back(e);
+        bc.push_back(it->second);
+    }
+    std::vector<uint64_t> offsets(barcodes.size() + 1);
+    PinnedResult res;
+    check(gtgpu_tokenize_fragments(index_, q.chr.size(), q.chr.data(), q.start.data(), q.end.data(), bc.data(),
+                                   (uint32_t)barcodes.size(), unk_id_, offsets.data(), &res.buf),
+          "gtgpu_tokenize_fragments");
+    std::vector<std::pair<std::string, std::vector<uint32_t>>> out;
+    for (size_t b = 0; b < barcodes.size(); ++b)
+        out.emplace_back(barcodes[b], std::vector<uint32_t>(res.data() + offsets[b], res.data() + offsets[b + 1]));
+    return out;
+}
+
+std::vector<std::pair<std::string, std::map<uint32_t, uint32_t>>> Tokenizer::count_fragments_by_barcode(const std::string& path) const {
+    std::vector<std::pair<std::string, std::map<uint32_t, uint32_t>>> out;
+    for (auto& kv : tokenize_fragment_file(path)) {
+        std::map<uint32_t, uint32_t> counts;
+        for (uint32_t id : kv.second) counts[id]++;
+        out.emplace_back(kv.first, std::move(counts));
+    }
+    return out;
+}
+
+// ---- Igd / LOLA -----------------------------------------------------------------------------------------------------------------
+Igd::Igd(std::shared_ptr<Device> dev, const std::vector<const RegionSet*>& sets) : dev_(std::move(dev)), n_files_(sets.size()) {
+    std::vector<uint64_t> file_offsets(sets.size() + 1, 0);
+    FlatQueries r;
+    for (size_t f = 0; f < sets.size(); ++f) {
+        for (const auto& reg : sets[f]->regions) {
+            r.chr.push_back(cmap_.add(reg.chr));
+            r.start.push_back(reg.start);
+            r.end.push_back(reg.end);
+        }
+        file_offsets[f + 1] = r.chr.size();
+    }
+    check(gtgpu_igd_build(dev_->ctx(), sets.size(), file_offsets.data(), (uint32_t)cmap_.size(), r.chr.data(), r.start.data(),
+                          r.end.data(), &igd_),
+          "gtgpu_igd_build");
+}
+Igd::~Igd() { gtgpu_igd_free(igd_); }
+
+std::vector<uint64_t> Igd::count_region_hits_batch(const std::vector<const RegionSet*>& sets, int32_t min_overlap, bool pairwise) const {
+    std::vector<uint64_t> set_offsets(sets.size() + 1, 0);
+    FlatQueries q;
+    for (size_t s = 0; s < sets.size(); ++s) {
+        for (const auto& reg : sets[s]->regions) {
+            q.chr.push_back(cmap_.get(reg.chr));
+            q.start.push_back(reg.start);
+            q.end.push_back(reg.end);
+        }
+        set_offsets[s + 1] = q.chr.size();
+    }
+    std::vector<uint64_t> out(sets.size() * n_files_);
+    auto fn = pairwise ? gtgpu_igd_count_set_overlaps : gtgpu_igd_count_region_hits;
+    check(fn(igd_, sets.size(), set_offsets.data(), q.chr.data(), q.start.data(), q.end.data(), min_overlap, out.data()),
+          pairwise ? "gtgpu_igd_count_set_overlaps" : "gtgpu_igd_count_region_hits");
+    return out;
+}
+
+std::vector<uint64_t> Igd::count_set_overlaps(const RegionSet& regions, int32_t min_overlap) const {
+    return count_region_hits_batch({&regions}, min_overlap, true);
+}
+std::vector<uint64_t> Igd::count_region_hits(const RegionSet& regions, int32_t min_overlap) const {
+    return count_region_hits_batch({&regions}, min_overlap, false);
+}
+
+std::vector<std::vector<ContingencyCounts>> lola_contingency(const Igd& igd, const std::vector<const RegionSet*>& user_sets,
+                                                             const RegionSet& universe, int32_t min_overlap) {
+    if (igd.num_files() == 0) throw Error("Database is empty");       // LolaError::EmptyDatabase, enrichment.rs:189-191
+    if (universe.regions.empty()) throw Error("Universe is empty");   // LolaError::EmptyUniverse, enrichment.rs:194-196
+    std::vector<const RegionSet*> all(user_sets);
+    all.push_back(&universe);
+    const size_t nf = igd.num_files();
+    std::vector<uint64_t> hits = igd.count_region_hits_batch(all, min_overlap, false);  // one device pass
+    const uint64_t* universe_hits = hits.data() + user_sets.size() * nf;
+    std::vector<std::vector<ContingencyCounts>> out(user_sets.size(), std::vector<ContingencyCounts>(nf));
+    for (size_t u = 0; u < user_sets.size(); ++u)
+        for (size_t f = 0; f < nf; ++f) {
+            int64_t a = (int64_t)hits[u * nf + f];
+            int64_t b = (int64_t)universe_hits[f] - a;
+            int64_t c = (int64_t)user_sets[u]->regions.size() - a;
+            int64_t d = (int64_t)universe.regions.size() - a - b - c;
+            out[u][f] = ContingencyCounts{a, b, c, d};
+        }
+    return out;
+}
+
+}  // namespace gtars

@@ -42,6 +42,17 @@ SIGNATURES = {
     "gtgpu_any": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _vp]),
     "gtgpu_find": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _vp, _vp]),
     "gtgpu_tokenize_files": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
+    "gtgpu_tokenize_fragments": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp]),
+    "gtgpu_igd_build": (_i32, [_vp, _u64, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "gtgpu_igd_free": (_i32, [_vp]),
+    "gtgpu_igd_info": (_i32, [_vp, _vp]),
+    "gtgpu_igd_count_set_overlaps": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "gtgpu_igd_count_region_hits": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "gtgpu_igd_count_dev": (_i32, [_vp, _i32, _u64, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "gtgpu_comm_unique_id": (_i32, [_vp]),
+    "gtgpu_comm_init": (_i32, [_vp, _i32, _i32, _vp]),
+    "gtgpu_comm_free": (_i32, [_vp]),
+    "gtgpu_igd_count_sharded": (_i32, [_vp, _vp, _i32, _u64, _u64, _vp, _vp, _vp, _vp, _i32, _vp]),
     "gtgpu_count_dev": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _vp]),
     "gtgpu_find_dev": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _u64, _vp, _vp, _u64, _vp, _vp, _vp]),
     "gtgpu_unk_rule_dev": (_i32, [_vp, _u64, _vp, _vp, _u32, _vp, _vp, _vp]),
@@ -241,6 +252,14 @@ class Index:
             return out_off, h
         return out_off, _take(h)
 
+    def tokenize_fragments(self, chr, start, end, barcode, n_barcodes, unk_id):
+        chr, start, end, barcode = (_arr(a, np.uint32) for a in (chr, start, end, barcode))
+        out_off = np.empty(n_barcodes + 1, dtype=np.uint64)
+        h = C.c_void_p()
+        check(lib().gtgpu_tokenize_fragments(self._h, len(chr), _p(chr), _p(start), _p(end), _p(barcode), n_barcodes,
+                                             unk_id, _p(out_off), C.byref(h)))
+        return out_off, _take(h)
+
     # ---- device-resident entry points (raw device pointers as ints) ----------------------------------------------------
     def count_dev(self, n, d_chr, d_start, d_end, min_overlap, d_out):
         check(lib().gtgpu_count_dev(self._h, n, d_chr, d_start, d_end, min_overlap, d_out))
@@ -249,3 +268,63 @@ class Index:
                  d_out_offsets, d_out_file_tok, d_out_total):
         check(lib().gtgpu_find_dev(self._h, n, d_chr, d_start, d_end, min_overlap, n_files, d_file_offsets, d_out_ids,
                                    ids_capacity, d_out_offsets, d_out_file_tok, d_out_total))
+
+
+def comm_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    check(lib().gtgpu_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_init(ctx: Context, world: int, rank: int, uid: bytes):
+    buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+    check(lib().gtgpu_comm_init(ctx._h, world, rank, buf))
+
+
+class Igd:
+    """gtgpu_igd: pooled start-sorted database records on the device (gtars-igd/src/igd.rs)."""
+
+    def __init__(self, ctx: Context, file_offsets, n_chroms, chr, start, end):
+        self.ctx = ctx
+        fo = _arr(file_offsets, np.uint64)
+        chr, start, end = _arr(chr, np.uint32), _arr(start, np.uint32), _arr(end, np.uint32)
+        self.n_files = len(fo) - 1
+        self._h = C.c_void_p()
+        check(lib().gtgpu_igd_build(ctx._h, self.n_files, _p(fo), n_chroms, _p(chr), _p(start), _p(end), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            lib().gtgpu_igd_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        a = (C.c_uint64 * 4)()
+        check(lib().gtgpu_igd_info(self._h, a))
+        return dict(n_files=a[0], n_records=a[1], device_bytes=a[2], lut_shift=a[3])
+
+    def _count(self, fn, set_offsets, chr, start, end, min_overlap):
+        so = _arr(set_offsets, np.uint64)
+        chr, start, end = _arr(chr, np.uint32), _arr(start, np.uint32), _arr(end, np.uint32)
+        out = np.zeros((len(so) - 1, self.n_files), dtype=np.uint64)
+        check(fn(self._h, len(so) - 1, _p(so), _p(chr), _p(start), _p(end), min_overlap, _p(out)))
+        return out
+
+    def count_set_overlaps(self, set_offsets, chr, start, end, min_overlap=1):
+        return self._count(lib().gtgpu_igd_count_set_overlaps, set_offsets, chr, start, end, min_overlap)
+
+    def count_region_hits(self, set_offsets, chr, start, end, min_overlap=1):
+        return self._count(lib().gtgpu_igd_count_region_hits, set_offsets, chr, start, end, min_overlap)
+
+    def count_sharded(self, binary, n_files_global, set_offsets, chr, start, end, min_overlap=1):
+        so = _arr(set_offsets, np.uint64)
+        chr, start, end = _arr(chr, np.uint32), _arr(start, np.uint32), _arr(end, np.uint32)
+        out = np.zeros((len(so) - 1, n_files_global), dtype=np.uint64)
+        check(lib().gtgpu_igd_count_sharded(self.ctx._h, self._h, 1 if binary else 0, n_files_global, len(so) - 1, _p(so),
+                                            _p(chr), _p(start), _p(end), min_overlap, _p(out)))
+        return out

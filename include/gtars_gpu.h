@@ -117,6 +117,49 @@ int32_t gtgpu_tokenize_files(gtgpu_index* index, uint64_t n_files, const uint64_
                              const uint32_t* chr, const uint32_t* start, const uint32_t* end, uint32_t unk_id,
                              uint64_t* out_file_token_offsets, gtgpu_buf** out_ids);
 
+/* tokenize_fragment_file (gtars-tokenizers/src/utils/fragments.rs:12-82) over pre-parsed fragments: every fragment
+ * is one Tokenizer::tokenize call (a fragment with no hit, or on an unknown chromosome, yields unk_id), ids are
+ * appended to the fragment's barcode list in input order.  barcode_id[i] < n_barcodes (dense ids, mapped by the
+ * caller); output is barcode-major: out_barcode_offsets[n_barcodes + 1] + ids. */
+int32_t gtgpu_tokenize_fragments(gtgpu_index* index, uint64_t n, const uint32_t* chr, const uint32_t* start,
+                                 const uint32_t* end, const uint32_t* barcode_id, uint32_t n_barcodes, uint32_t unk_id,
+                                 uint64_t* out_barcode_offsets, gtgpu_buf** out_ids);
+
+/* ---- IGD / LOLA overlap-count matrices ------------------------------------------------------------------------------
+ * gtgpu_igd_build replaces Igd::from_named_region_sets / from_region_sets (gtars-igd/src/igd.rs:249-317): file f owns
+ * records [file_offsets[f], file_offsets[f+1]); records with start >= end, or negative as int32, are dropped as
+ * Igd::add does (igd.rs:109-116).  chr ids must be < n_chroms. */
+int32_t gtgpu_igd_build(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* file_offsets, uint32_t n_chroms,
+                        const uint32_t* chr, const uint32_t* start, const uint32_t* end, gtgpu_igd** out_igd);
+int32_t gtgpu_igd_free(gtgpu_igd* igd);
+/* info[0]=n_files, [1]=records kept, [2]=device bytes, [3]=lut shift */
+int32_t gtgpu_igd_info(const gtgpu_igd* igd, uint64_t info[4]);
+/* Igd::count_set_overlaps (igd.rs:544-556) / Igd::count_region_hits (igd.rs:563-590) for n_sets query sets at once:
+ * set s owns queries [set_offsets[s], set_offsets[s+1]); out is [n_sets x n_files] row-major (caller-allocated).
+ * Queries follow Igd::count_overlaps (igd.rs:504-540): int32 semantics, start >= end or end <= 0 -> nothing, negative
+ * start clamps to 0.  min_overlap must be >= 1 (values <= 0 depend on the reference's tile layout). */
+int32_t gtgpu_igd_count_set_overlaps(gtgpu_igd* igd, uint64_t n_sets, const uint64_t* set_offsets, const uint32_t* chr,
+                                     const uint32_t* start, const uint32_t* end, int32_t min_overlap, uint64_t* out);
+int32_t gtgpu_igd_count_region_hits(gtgpu_igd* igd, uint64_t n_sets, const uint64_t* set_offsets, const uint32_t* chr,
+                                    const uint32_t* start, const uint32_t* end, int32_t min_overlap, uint64_t* out);
+/* device-resident core: d_set_of[i] = set index of query i; d_out ([n_sets x n_files] u64) is accumulated into */
+int32_t gtgpu_igd_count_dev(gtgpu_igd* igd, int32_t binary, uint64_t n, const uint32_t* d_set_of, const uint32_t* d_chr,
+                            const uint32_t* d_start, const uint32_t* d_end, int32_t min_overlap, uint64_t* d_out);
+
+/* ---- multi-GPU: the LOLA database sharded by region set, one ncclAllGather (run_lola's count matrices,
+ * gtars-lola/src/enrichment.rs:198-211) ------------------------------------------------------------------------------
+ * One process per GPU.  Rank 0 calls gtgpu_comm_unique_id and ships the 128 bytes to the other ranks by any means
+ * (MPI, torch.distributed, a file); every rank then calls gtgpu_comm_init on its ctx.  NCCL is dlopen'ed on first
+ * use.  With world W and n_files_global sets, rank r must have built its gtgpu_igd over global sets
+ * [r*C, min((r+1)*C, n_files_global)), C = ceil(n_files_global / W); every rank passes the SAME query sets and
+ * receives the full [n_sets x n_files_global] matrix.  Without a communicator (W = 1) it equals the local call. */
+int32_t gtgpu_comm_unique_id(uint8_t out_id[128]);
+int32_t gtgpu_comm_init(gtgpu_ctx* ctx, int32_t world, int32_t rank, const uint8_t id[128]);
+int32_t gtgpu_comm_free(gtgpu_ctx* ctx);
+int32_t gtgpu_igd_count_sharded(gtgpu_ctx* ctx, gtgpu_igd* igd, int32_t binary, uint64_t n_files_global,
+                                uint64_t n_sets, const uint64_t* set_offsets, const uint32_t* chr, const uint32_t* start,
+                                const uint32_t* end, int32_t min_overlap, uint64_t* out);
+
 /* ---- batch queries, device-resident (asynchronous on the ctx stream) --------------------------------------- */
 int32_t gtgpu_count_dev(gtgpu_index* index, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
                         const uint32_t* d_end, int32_t min_overlap, uint32_t* d_out_counts);

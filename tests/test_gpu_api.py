@@ -1,0 +1,175 @@
+"""The reference's own tests for this path, replayed through the host-side API mirror (gtars_b200.api → C++ host layer →
+C ABI → CUDA).  Expected values come from tests/golden/kats.json (reference file:line in each entry)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import helpers
+from tests.helpers import KINDS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from gtars_b200 import api as a
+    a.device(0)
+    return a
+
+
+def _toml(fixture_dir, kind):
+    p = os.path.join(fixture_dir, "tokenizers", f"tokenizer_{kind}.toml")
+    with open(p, "w") as f:
+        f.write('universe = "peaks.bed.gz"\n' + (f'tokenizer_type = "{kind}"\n' if kind != "default" else ""))
+    return p
+
+
+def test_tokenizer_kats(api, golden, fixture_dir):
+    """gtars-tokenizers/src/tokenizer.rs:294-496 and gtars-python/tests/test_tokenizers.py."""
+    for case in golden[1]["K5_tokenizer"]:
+        for kind in case["kinds"]:
+            if case["universe"].endswith("peaks.bed") and kind == "ailist":
+                tok = api.Tokenizer.from_config(_toml(fixture_dir, "ailist"))
+            elif kind == "ailist":
+                continue
+            else:
+                tok = api.Tokenizer(os.path.join(fixture_dir, case["universe"]))
+            if "vocab_size" in case:
+                assert tok.get_vocab_size() == case["vocab_size"]
+                assert tok.unk_token_id == case["unk_id"]
+            if "regions" in case:
+                regions = [api.Region(*r) for r in case["regions"]]
+                if "ids" in case:
+                    assert tok.encode(regions) == case["ids"], (case["cite"], kind)
+                    assert tok(regions)["input_ids"] == case["ids"]
+                if "tokens" in case:
+                    assert tok.tokenize(regions) == case["tokens"], (case["cite"], kind)
+
+
+def test_tokenizer_config_variants(api, fixture_dir):
+    """tokenizer.rs:294-358: from_config / from_auto, bad tokenizer type, custom special tokens."""
+    d = os.path.join(fixture_dir, "tokenizers")
+    assert api.Tokenizer.from_auto(_toml(fixture_dir, "bits")).get_vocab_size() == 32
+    assert api.Tokenizer.from_auto(_toml(fixture_dir, "default")).get_vocab_size() == 32
+    assert api.Tokenizer.from_auto(os.path.join(d, "peaks.bed.gz")).get_vocab_size() == 32
+    bad = os.path.join(d, "bad.toml")
+    open(bad, "w").write('universe = "peaks.bed.gz"\ntokenizer_type = "i-dont-exist"\n')
+    with pytest.raises(api.GtarsError):
+        api.Tokenizer.from_config(bad)
+    custom = os.path.join(d, "custom.toml")
+    open(custom, "w").write('universe = "peaks.bed.gz"\nspecial_tokens = [\n    {name="unk", token="<UNKNOWN>"},\n]\n')
+    tok = api.Tokenizer.from_config(custom)
+    assert tok.get_vocab_size() == 32 and tok.unk_token == "<UNKNOWN>" and tok.pad_token == "<pad>"
+    assert tok.tokenize([api.Region("chr1", 50, 150)]) == ["<UNKNOWN>"]
+    with pytest.raises(api.GtarsError):
+        api.Tokenizer.from_auto(os.path.join(d, "peaks.txt"))
+
+
+def test_tokenizer_derived_and_duplicates(api, golden, fixture_dir, tmp_path):
+    d = golden[1]["D_derived"]
+    for kind in ("bits", "ailist"):
+        tok = api.Tokenizer.from_config(_toml(fixture_dir, kind))
+        assert tok.encode(os.path.join(fixture_dir, d["D1"]["query_file"])) == d["D1"][kind]
+        assert tok.encode([api.Region(*r) for r in d["D2"]["regions"]]) == d["D2"][kind]
+    # duplicate universe lines: ids round-trip through strings, same as the oracle
+    from oracle import oracle as orc
+    p = tmp_path / "dup.bed"
+    p.write_text("chr1\t10\t20\nchr1\t30\t40\nchr1\t10\t20\nchr1\t50\t60\n")
+    tok, o = api.Tokenizer(str(p)), orc.Tokenizer(str(p))
+    for q in ([("chr1", 55, 58)], [("chr1", 12, 14)], [("chr1", 0, 100)], [("chr2", 1, 2)]):
+        assert tok.encode([api.Region(*r) for r in q]) == o.encode(q)
+    assert tok.encode_batch([[api.Region("chr1", 55, 58)], [], [api.Region("chr9", 1, 2)]]) == [[0], [tok.unk_token_id], [tok.unk_token_id]]
+
+
+def test_fragment_tokenization(api, golden, fixture_dir):
+    """utils/fragments.rs:114-156 asserts 2 barcodes; exact vectors are the derived D3 (and the oracle's)."""
+    from oracle import oracle as orc
+    d3 = golden[1]["D_derived"]["D3"]
+    tok = api.Tokenizer(os.path.join(fixture_dir, d3["universe"]))
+    for frag in ("fragments/region_scoring/fragments1.bed.gz", "fragments/region_scoring/fragments2.bed.gz"):
+        got = api.tokenize_fragment_file(os.path.join(fixture_dir, frag), tok)
+        assert len(got) == 2
+        assert got == orc.Tokenizer(os.path.join(fixture_dir, d3["universe"])).tokenize_fragment_file(os.path.join(fixture_dir, frag))
+    assert api.tokenize_fragment_file(os.path.join(fixture_dir, d3["fragments"]), tok) == d3["expect"]
+
+
+@pytest.mark.parametrize("kind", ["bits", "ailist"])
+def test_mco_kats(api, golden, kind):
+    """gtars-overlaprs/src/multi_chrom_overlapper.rs:715-1157 and gtars-python/tests/test_regionset.py:37-55."""
+    for case in golden[1]["K4_mco"]:
+        src = [api.Region(*r) for r in case["source"]]
+        query = [api.Region(*r) for r in case["query"]]
+        mco = api.MultiChromOverlapper(src, KINDS[kind])
+        m = case["min_overlap"]
+        if "count" in case:
+            assert mco.count_overlaps(query, m) == case["count"], case["cite"]
+        if "any" in case:
+            assert mco.any_overlaps(query, m) == case["any"], case["cite"]
+        if "find" in case:
+            got = [sorted([r.start, r.end] for r in hits) for hits in mco.find_overlaps_regions(query, m)]
+            assert got == [sorted(x) for x in case["find"]], case["cite"]
+        if "find_idx" in case:
+            assert [sorted(h) for h in mco.find_overlaps(query, m)] == case["find_idx"], case["cite"]
+    # subset_by / intersect_all: deduplicated and sorted (multi_chrom_overlapper.rs:1044-1068)
+    mco = api.MultiChromOverlapper([("chr1", 100, 200), ("chr1", 300, 400), ("chr2", 500, 600)], KINDS[kind])
+    sub = mco.subset_by([("chr1", 150, 250), ("chr2", 550, 650), ("chr1", 160, 170)])
+    assert [(r.chr, r.start, r.end) for r in sub] == [("chr1", 100, 200), ("chr2", 500, 600)]
+
+
+def test_regionset_binding_ops(api, fixture_dir):
+    """gtars-python/tests/test_regionset.py:37-55: self = queries, other = index."""
+    a = api.RegionSet([("chr1", 100, 200), ("chr1", 300, 400), ("chr1", 500, 600)])
+    b = api.RegionSet([("chr1", 150, 250), ("chr1", 550, 650)])
+    assert a.count_overlaps(b) == [1, 0, 1]
+    assert a.any_overlaps(b) == [True, False, True]
+    assert a.find_overlaps(b) == [[0], [], [1]]
+    rs = api.RegionSet(os.path.join(fixture_dir, "to_tokenize.bed"))  # parsed, then sorted by (chr, start)
+    assert [(r.chr, r.start, r.end) for r in rs] == [("chr13", 74550222, 74550611), ("chr15", 49155456, 49155487),
+                                                      ("chr15", 49155846, 49156192)]
+    with pytest.raises(api.GtarsError):
+        api.RegionSet(os.path.join(fixture_dir, "does_not_exist.bed"))
+
+
+def test_igd_and_lola_kats(api, golden):
+    """gtars-igd/src/igd.rs:1160-1221 and gtars-lola/src/enrichment.rs:830-1104."""
+    for case in golden[1]["K7_igd_sets"]:
+        if "db" not in case:
+            db = [helpers.parse_bed_text(golden[0][f]["text"]) for f in case["db_files"]]
+        else:
+            db = [[tuple(r) for r in st] for st in case["db"]]
+        igd = api.Igd(db)
+        q = [tuple(r) for r in case["query"]]
+        if "set_overlaps" in case:
+            assert igd.count_set_overlaps(q, case["min_overlap"]) == case["set_overlaps"], case["cite"]
+    for case in golden[1]["K9_lola"]:
+        igd = api.Igd([[tuple(r) for r in st] for st in case["db"]])
+        t = api.lola_contingency(igd, [[tuple(r) for r in st] for st in case["user"]], [tuple(r) for r in case["universe"]],
+                                 case["min_overlap"])
+        if "abcd" in case:
+            assert t.tolist() == case["abcd"], case["cite"]
+        if "support" in case:
+            assert t[:, :, 0].tolist() == case["support"], case["cite"]
+    with pytest.raises(api.GtarsError):  # enrichment.rs:855-877: empty universe is an error
+        api.lola_contingency(api.Igd([[("chr1", 100, 200)]]), [[("chr1", 100, 200)]], [])
+
+
+def test_igd_unit_kats_through_c_abi(golden):
+    """gtars-igd/src/igd.rs:914-1461 (count_overlaps on hand-built databases), via gtgpu_igd_*."""
+    from gtars_b200 import ffi
+    ctx = ffi.Context(0)
+    for case in golden[1]["K7_igd"]:
+        cmap = helpers.ChromMap()
+        per_file = [[] for _ in range(case["n_files"])]
+        for chr_, s, e, _val, f in case["adds"]:
+            per_file[f].append((cmap.add(chr_), s & 0xFFFFFFFF, e & 0xFFFFFFFF))
+        fo = np.cumsum([0] + [len(x) for x in per_file]).astype(np.uint64)
+        flat = [r for x in per_file for r in x]
+        g = ffi.Igd(ctx, fo, max(len(cmap), 1), [r[0] for r in flat], [r[1] for r in flat], [r[2] for r in flat])
+        for q in case["queries"]:
+            chr_, s, e, m = q["q"]
+            so = np.array([0, 1], dtype=np.uint64)
+            hits = g.count_set_overlaps(so, [cmap.get(chr_)], [s & 0xFFFFFFFF], [e & 0xFFFFFFFF], m)[0]
+            assert list(hits) == q["hits"], (case["cite"], q)
+        g.close()
+    ctx.close()

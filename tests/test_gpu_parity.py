@@ -244,3 +244,59 @@ def test_synthetic_c2_shape_vs_oracle(ctx, kind, nested):
     assert np.array_equal(g.count(qc, qs, qe), o.count(qc, qs, qe))
     if nested and kind == "ailist":
         assert g.info()["max_components"] >= 2
+
+
+# ---- IGD / LOLA count matrices and fragment tokenization vs the oracle --------------------------------------------------
+@pytest.mark.parametrize("min_overlap", [1, 2, 40])
+def test_igd_random_differential(ctx, min_overlap):
+    from gtars_b200 import ffi
+    from oracle import oracle as orc
+    rng = np.random.default_rng(100 + min_overlap)
+    n_chroms, n_files = 4, 37
+    sizes = rng.integers(0, 400, n_files)
+    sizes[5] = 0
+    n = int(sizes.sum())
+    fo = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    dc = rng.integers(0, n_chroms, n).astype(np.uint32)
+    ds = rng.integers(0, 300_000, n).astype(np.uint32)
+    de = (ds + rng.integers(-20, 40_000, n).clip(-20, None)).astype(np.int64).clip(0, None).astype(np.uint32)  # some empty / reversed
+    wide = rng.random(n) < 0.05
+    de = np.where(wide, ds + rng.integers(20_000, 120_000, n), de).astype(np.uint32)  # spans many 16 kb tiles
+    g = ffi.Igd(ctx, fo, n_chroms, dc, ds, de)
+    o = orc.Igd(fo, dc, ds, de)
+    set_sizes = [0, 700, 1, 1300, 0, 450]
+    nq = sum(set_sizes)
+    so = np.concatenate([[0], np.cumsum(set_sizes)]).astype(np.uint64)
+    qc = rng.integers(0, n_chroms + 1, nq).astype(np.uint32)
+    qc[rng.random(nq) < 0.02] = 0xFFFFFFFF
+    qs = rng.integers(0, 320_000, nq).astype(np.uint32)
+    qe = (qs + rng.integers(1, 30_000, nq)).astype(np.uint32)
+    qe = np.where(rng.random(nq) < 0.05, qs, qe).astype(np.uint32)  # empty queries contribute nothing
+    assert np.array_equal(g.count_set_overlaps(so, qc, qs, qe, min_overlap), o.count_set_overlaps(so, qc, qs, qe, min_overlap))
+    assert np.array_equal(g.count_region_hits(so, qc, qs, qe, min_overlap), o.count_region_hits(so, qc, qs, qe, min_overlap))
+    # single-rank sharded entry point == unsharded
+    assert np.array_equal(g.count_sharded(True, n_files, so, qc, qs, qe, min_overlap), o.count_region_hits(so, qc, qs, qe, min_overlap))
+    from gtars_b200.ffi import GtarsGpuError
+    with pytest.raises(GtarsGpuError):
+        g.count_region_hits(so, qc, qs, qe, 0)
+    g.close()
+
+
+@pytest.mark.parametrize("kind", ["bits", "ailist"])
+def test_fragments_random_differential(ctx, kind):
+    rng = np.random.default_rng(77)
+    n_chroms = 3
+    offs, s, e, v = _random_index(rng, n_chroms, 4000, "overlap")
+    g, o = _both(ctx, kind, offs, s, e, v)
+    n, n_bc = 20_000, 300
+    qc, qs, qe = _random_queries(rng, n_chroms, n)
+    bc = (rng.zipf(1.5, n) % n_bc).astype(np.uint32)
+    bc[bc == 7] = 8  # barcode 7 never appears: empty list
+    unk = 4000
+    g_off, g_ids = g.tokenize_fragments(qc, qs, qe, bc, n_bc, unk)
+    o_off, o_ids = o.tokenize_fragments(qc, qs, qe, bc, n_bc, unk)
+    assert np.array_equal(g_off, o_off)
+    assert np.array_equal(g_ids, o_ids)
+    assert g_off[7] == g_off[8]
+    g_off, g_ids = g.tokenize_fragments(qc[:0], qs[:0], qe[:0], bc[:0], 5, unk)
+    assert list(g_off) == [0] * 6 and len(g_ids) == 0
