@@ -203,7 +203,8 @@ class MultiChromOverlapper:
                 for i, hits in enumerate(self.find_overlaps(q, min_overlap))]
 
     def subset_by(self, query, min_overlap=None):
-        h = lib().gth_mco_subset_by(self._h, _as_rs(query)._h, self._m(min_overlap))
+        q = _as_rs(query)  # keep the temporary alive across the call
+        h = lib().gth_mco_subset_by(self._h, q._h, self._m(min_overlap))
         if not h:
             _fail()
         return RegionSet._wrap(h)
