@@ -1,0 +1,145 @@
+#!/usr/bin/env python
+"""Secondary measurements for BASELINE.json configs C3 / C4 / C5 (bench.py is the contract benchmark for C2).
+
+One JSON line per config: device-resident kernel throughput (CUDA events on the launching stream), algorithmic bytes,
+fraction of the measured HBM peak, and a bit-exact spot check against the CPU oracle on a sample.
+Sizes are per GPU; pass --scale 1.0 for the full single-GPU share of each config (defaults keep the run short).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="c3,c4,c5")
+    ap.add_argument("--scale", type=float, default=0.2)
+    ap.add_argument("--steps", type=int, default=5)
+    args = ap.parse_args()
+    import torch
+    from gtars_b200 import ffi, synth
+    from oracle import oracle as orc
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        peak = 6650.0
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    ctx = ffi.Context(0, stream=stream.cuda_stream)
+    u32 = lambda t: t.cpu().numpy().view(np.uint32)
+
+    def timed(fn):
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                fn()
+            stream.synchronize()
+            ctx.timing_enable(True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.steps):
+                fn()
+            e1.record(stream)
+            stream.synchronize()
+            k = ctx.timing_read()
+            ctx.timing_enable(False)
+        return e0.elapsed_time(e1) / args.steps, (sum(k) / len(k) if k else None)
+
+    for cfg in args.configs.split(","):
+        t_setup = time.time()
+        if cfg == "c3":
+            n_db, n_q = int(50_000_000 * args.scale), int(100_000_000 * args.scale)
+            db = synth.make_uniform_intervals(n_db, synth.SEED_LOLA_DB, device=dev, min_w=100, max_w=10_000)
+            g = synth.group_by_chrom(db["chr"], db["start"], db["end"])
+            offs = g["chrom_offsets"].cpu().numpy().astype(np.uint64)
+            s, e = u32(g["g_start"]), u32(g["g_end"])
+            ix = ffi.Index(ctx, ffi.KIND_BITS, offs, s, e)
+            q = synth.make_uniform_intervals(n_q, synth.SEED_QUERIES, device=dev, min_w=100, max_w=2000, log_uniform=False)
+            d_out = torch.empty(n_q, dtype=torch.int32, device=dev)
+            fn = lambda: ix.count_dev(n_q, q["chr"].data_ptr(), q["start"].data_ptr(), q["end"].data_ptr(), 0, d_out.data_ptr())
+            ms, kms = timed(fn)
+            m = min(n_q, 200_000)
+            ok = bool(np.array_equal(u32(d_out[:m]), orc.Index(orc.BITS, offs, s, e).count(
+                u32(q["chr"][:m]), u32(q["start"][:m]), u32(q["end"][:m]), threads=orc.max_threads())))
+            algo = 16 * n_q + 8 * n_db
+            out = dict(config="C3 Bits count", queries=n_q, db_intervals=n_db, ms_per_step=ms, value=n_q / (ms * 1e-3),
+                       unit="queries/s", kernel_ms=kms, algorithmic_bytes=algo, index=ix.info(),
+                       roofline_frac=algo / ((kms or ms) * 1e-3) / 1e9 / peak, parity_sample_vs_oracle=ok,
+                       note="unsorted queries; the 400 MB sorted arrays + LUTs exceed L2, so every search pays DRAM sectors")
+        elif cfg == "c4":
+            n_db = max(int(10_000 * args.scale), 8)
+            per_db, n_user, per_user = 20_000, max(int(1000 * args.scale), 4), 10_000
+            db = synth.make_uniform_intervals(n_db * per_db, synth.SEED_LOLA_DB, device=dev, min_w=200, max_w=5000)
+            dfo = (np.arange(n_db + 1) * per_db).astype(np.uint64)
+            dc, ds, de = u32(db["chr"]), u32(db["start"]), u32(db["end"])
+            g = ffi.Igd(ctx, dfo, synth.N_CHROMS, dc, ds, de)
+            u = synth.make_universe(1_000_000, device=dev)
+            pick = synth.rand_u63(synth.SEED_LOLA_USER, 1, torch.arange(n_user * per_user, device=dev)) % u["n"]
+            qc = torch.cat([u["chr"][pick], u["chr"]]).contiguous()
+            qs = torch.cat([u["start"][pick], u["start"]]).contiguous()
+            qe = torch.cat([u["end"][pick], u["end"]]).contiguous()
+            n_q = qc.numel()
+            set_of = torch.cat([torch.arange(n_user, device=dev).repeat_interleave(per_user),
+                                torch.full((u["n"],), n_user, device=dev)]).int().contiguous()
+            d_out = torch.zeros((n_user + 1) * n_db, dtype=torch.int64, device=dev)
+
+            def fn():
+                d_out.zero_()
+                ffi.check(ffi.lib().gtgpu_igd_count_dev(g._h, 1, n_q, set_of.data_ptr(), qc.data_ptr(), qs.data_ptr(),
+                                                        qe.data_ptr(), 1, d_out.data_ptr()))
+            ms, kms = timed(fn)
+            hits = d_out.view(n_user + 1, n_db).cpu().numpy().astype(np.uint64)
+            k = 2
+            so = (np.arange(k + 1) * per_user).astype(np.uint64)
+            ref = orc.Igd(dfo, dc, ds, de).count_region_hits(so, u32(qc[:k * per_user]), u32(qs[:k * per_user]),
+                                                             u32(qe[:k * per_user]), 1, threads=orc.max_threads())
+            ok = bool(np.array_equal(hits[:k], ref))
+            pair_hits = int(hits.sum())
+            algo = 12 * n_q + 12 * n_db * per_db + 8 * (n_user + 1) * n_db
+            out = dict(config="C4 LOLA region-hit matrix", db_sets=n_db, db_records=n_db * per_db, user_sets=n_user,
+                       query_regions=n_q, ms_per_step=ms, kernel_ms=kms, value=n_q / (ms * 1e-3), unit="query regions/s",
+                       region_file_hits=pair_hits, hits_per_s=pair_hits / ((kms or ms) * 1e-3), algorithmic_bytes=algo,
+                       roofline_frac=algo / ((kms or ms) * 1e-3) / 1e9 / peak, parity_sample_vs_oracle=ok, igd=g.info(),
+                       note="atomic / L2-bound by construction; the HBM fraction is low on purpose (SURVEY §8d)")
+        elif cfg == "c5":
+            n = int(125_000_000 * args.scale)  # one GPU's share of the 1 B-fragment, 8-GPU configuration
+            n_bc = 100_000
+            u = synth.make_universe(1_000_000, device=dev)
+            offs = u["chrom_offsets"].cpu().numpy().astype(np.uint64)
+            s, e, v = (u32(u[k]) for k in ("g_start", "g_end", "g_val"))
+            ix = ffi.Index(ctx, ffi.KIND_BITS, offs, s, e, v)
+            q = synth.make_query_files(u, 1, n, seed=synth.SEED_FRAGMENTS, device=dev, sort_files=False)
+            qc, qs, qe = u32(q["chr"]), u32(q["start"]), u32(q["end"])
+            bc = (synth.rand_u63(synth.SEED_FRAGMENTS, 9, torch.arange(n, device=dev)) % n_bc)
+            bc = ((bc * bc) // n_bc).int()  # skewed barcode sizes
+            bc_h = u32(bc)
+            t0 = time.perf_counter()
+            off, ids = ix.tokenize_fragments(qc, qs, qe, bc_h, n_bc, u["unk_id"])
+            t1 = time.perf_counter()
+            off, ids = ix.tokenize_fragments(qc, qs, qe, bc_h, n_bc, u["unk_id"])
+            t2 = time.perf_counter()
+            m = min(n, 2_000_000)
+            o_off, o_ids = orc.Index(orc.BITS, offs, s, e, v).tokenize_fragments(qc[:m], qs[:m], qe[:m], bc_h[:m], n_bc, u["unk_id"])
+            g_off, g_ids = ix.tokenize_fragments(qc[:m], qs[:m], qe[:m], bc_h[:m], n_bc, u["unk_id"])
+            ok = bool(np.array_equal(o_off, g_off) and np.array_equal(o_ids, g_ids))
+            out = dict(config="C5 fragment tokenization (host buffers in/out, pageable)", fragments=n, barcodes=n_bc, ids=int(len(ids)),
+                       seconds_first_call=t1 - t0, seconds_warm_call=t2 - t1, value=n / (t2 - t1), unit="fragments/s (end to end)",
+                       parity_sample_vs_oracle=ok,
+                       note="end-to-end through gtgpu_tokenize_fragments incl. H2D/D2H; group-by uses CUB sort + scan")
+        else:
+            continue
+        out["setup_seconds"] = time.time() - t_setup
+        print(json.dumps(out), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
