@@ -1,6 +1,7 @@
 // api.cu — extern "C" entry points of include/gtars_gpu.h: context, memory, and the host-buffer wrappers
 // (H2D → kernels → D2H) around the device-resident launches in kernels.cu.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -339,6 +340,135 @@ int32_t find_host(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32
     return GTGPU_OK;
 }
 
+// gtgpu_tokenize_files for large batches: the queries stream through two device buffers in chunks, so the H2D copy of
+// chunk k+1, the fused kernel of chunk k and the D2H copy of chunk k-1's ids overlap (PCIe is full duplex and the
+// kernel is ~20x faster than either copy).  Every chunk's kernel starts its ids where the previous one stopped (a
+// device-side running total chained through d_base / d_total), so the result is identical to a single launch.
+// Returns 1 in *fallback (and no result) for the rare cases the simple path handles: output larger than the
+// optimistic capacity, a file with no token at all ([unk] insertion shifts the ids), or a tile overflow.
+int32_t tokenize_files_pipelined(gtgpu_index* ix, uint64_t n, uint64_t n_files, const uint64_t* file_offsets,
+                                 const uint32_t* chr, const uint32_t* start, const uint32_t* end, uint64_t chunk,
+                                 uint64_t* out_file_tok, gtgpu_buf** out_ids, int* fallback) {
+    *fallback = 0;
+    gtgpu_ctx* ctx = ix->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    GT_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    const uint64_t cap = n + n / 4 + 1024;
+
+    uint32_t* in[2][3];
+    const int roles[2][3] = {{SC_CHR, SC_START, SC_END}, {SC_IN2_CHR, SC_IN2_START, SC_IN2_END}};
+    for (int b = 0; b < 2; ++b)
+        for (int a = 0; a < 3; ++a) GT_TRY(ctx->scratch_get(roles[b][a], chunk * 4, (void**)&in[b][a]));
+    uint32_t* d_ids;
+    uint64_t *d_fo, *d_raw_tok, *d_out_tok, *d_run, *d_misc;
+    void* d_ws;
+    GT_TRY(ctx->scratch_get(SC_OUT_IDS, cap * 4, (void**)&d_ids));
+    GT_TRY(ctx->scratch_get(SC_FILE_OFFS, (n_files + 1) * 8, (void**)&d_fo));
+    GT_TRY(ctx->scratch_get(SC_FILE_TOK, (n_files + 1) * 8, (void**)&d_raw_tok));
+    GT_TRY(ctx->scratch_get(SC_FILE_TOK2, (n_files + 1) * 8, (void**)&d_out_tok));
+    GT_TRY(ctx->scratch_get(SC_COUNTS, (n_chunks + 1) * 8, (void**)&d_run));
+    GT_TRY(ctx->scratch_get(SC_MISC, 64, (void**)&d_misc));
+    GT_TRY(ctx->scratch_get(SC_TILE_STATUS, fused_workspace_bytes(chunk), &d_ws));
+
+    // every file boundary belongs to the chunk that holds its first query; offsets are rebased to that chunk
+    std::vector<uint64_t> rebased(n_files + 1), first_f(n_chunks + 1, 0);
+    {
+        uint64_t f = 0;
+        for (uint64_t k = 0; k < n_chunks; ++k) {
+            first_f[k] = f;
+            const uint64_t q0 = k * chunk, q1 = std::min(n, q0 + chunk);
+            while (f <= n_files && (file_offsets[f] < q1 || k + 1 == n_chunks)) {
+                rebased[f] = file_offsets[f] - q0;
+                ++f;
+            }
+        }
+        first_f[n_chunks] = n_files + 1;
+    }
+    GT_CUDA(cudaMemcpyAsync(d_fo, rebased.data(), (n_files + 1) * 8, cudaMemcpyHostToDevice, st));
+    GT_CUDA(cudaMemsetAsync(d_run, 0, (n_chunks + 1) * 8, st));
+    GT_CUDA(cudaMemsetAsync(d_misc, 0, 64, st));
+    GT_CUDA(cudaStreamSynchronize(st));  // `rebased` is pageable: the copy must have consumed it
+
+    gtgpu_buf* buf = new gtgpu_buf();
+    buf->ctx = ctx;
+    int32_t status = ctx->pinned_get(cap * 4, &buf->block);
+    if (status != GTGPU_OK) {
+        delete buf;
+        return status;
+    }
+    uint32_t* h_ids = (uint32_t*)buf->block.ptr;
+    volatile uint64_t* h_run = ctx->h_scalars;  // [k] = ids before chunk k
+    h_run[0] = 0;
+
+    std::vector<cudaEvent_t> ev_done(n_chunks);
+    cudaEvent_t ev_in[2], ev_free[2];
+    for (int b = 0; b < 2; ++b) {
+        cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_free[b], cudaEventDisableTiming);
+    }
+    for (auto& e : ev_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    bool overflow = false;
+    cudaError_t cerr = cudaSuccess;
+    auto drain = [&](uint64_t j) {  // ids of chunk j: device -> pinned host, on the copy-out stream
+        if (cerr != cudaSuccess) return;
+        cerr = cudaEventSynchronize(ev_done[j]);
+        const uint64_t lo = h_run[j], hi = h_run[j + 1];
+        if (hi > cap) overflow = true;
+        if (cerr == cudaSuccess && !overflow && hi > lo)
+            cerr = cudaMemcpyAsync(h_ids + lo, d_ids + lo, (hi - lo) * 4, cudaMemcpyDeviceToHost, ctx->copy_out);
+    };
+    for (uint64_t k = 0; k < n_chunks && status == GTGPU_OK && cerr == cudaSuccess; ++k) {
+        const int b = (int)(k & 1);
+        const uint64_t q0 = k * chunk, cn = std::min(chunk, n - q0);
+        if (k >= 2) cudaStreamWaitEvent(ctx->copy_in, ev_free[b], 0);
+        cudaMemcpyAsync(in[b][0], chr + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in);
+        cudaMemcpyAsync(in[b][1], start + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in);
+        cerr = cudaMemcpyAsync(in[b][2], end + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in);
+        cudaEventRecord(ev_in[b], ctx->copy_in);
+        cudaStreamWaitEvent(st, ev_in[b], 0);
+        const uint64_t L = first_f[k + 1] - first_f[k];  // file boundaries owned by this chunk
+        status = launch_fused_find(ix, cn, L ? L - 1 : 0, d_fo + first_f[k], in[b][0], in[b][1], in[b][2], 0, d_ids, cap, nullptr,
+                                   L ? d_raw_tok + first_f[k] : nullptr, d_ws, d_run + k, d_run + k + 1, (uint32_t*)(d_misc + 2));
+        cudaEventRecord(ev_free[b], st);
+        cudaMemcpyAsync((void*)(h_run + k + 1), d_run + k + 1, 8, cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(ev_done[k], st);
+        if (k >= 1) drain(k - 1);
+    }
+    if (status == GTGPU_OK) drain(n_chunks - 1);
+    uint64_t total = 0, n_empty = 0;
+    if (status == GTGPU_OK && cerr == cudaSuccess && !overflow) {
+        status = launch_unk_offsets(ctx, n_files, d_raw_tok, d_out_tok, d_misc + 1);
+        cudaMemcpyAsync((void*)(h_run + 60), d_misc, 24, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_file_tok, d_out_tok, (n_files + 1) * 8, cudaMemcpyDeviceToHost, st);
+        cerr = cudaStreamSynchronize(st);
+        if (cerr == cudaSuccess) cerr = cudaStreamSynchronize(ctx->copy_out);
+        total = h_run[n_chunks];
+        n_empty = h_run[61];
+        if ((uint32_t)h_run[62] != 0) overflow = true;
+    } else {
+        cudaStreamSynchronize(st);
+        cudaStreamSynchronize(ctx->copy_out);
+    }
+    for (int b = 0; b < 2; ++b) {
+        cudaEventDestroy(ev_in[b]);
+        cudaEventDestroy(ev_free[b]);
+    }
+    for (auto& e : ev_done) cudaEventDestroy(e);
+    if (status != GTGPU_OK || cerr != cudaSuccess || overflow || n_empty > 0) {
+        ctx->pinned_put(buf->block);
+        delete buf;
+        if (status != GTGPU_OK) return status;
+        if (cerr != cudaSuccess) return fail(GTGPU_ERR_CUDA, std::string("tokenize_files (pipelined): ") + cudaGetErrorString(cerr));
+        *fallback = 1;
+        return GTGPU_OK;
+    }
+    buf->len = total;
+    *out_ids = buf;
+    return GTGPU_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -376,6 +506,14 @@ int32_t gtgpu_tokenize_files(gtgpu_index* ix, uint64_t n_files, const uint64_t* 
             return fail(GTGPU_ERR_INVALID, "tokenize_files: file_offsets not monotone");
     uint64_t n = file_offsets[n_files];
     if (n && (!chr || !start || !end)) return fail(GTGPU_ERR_INVALID, "tokenize_files: null query arrays");
+    uint64_t chunk = 32ull << 20;  // queries per pipeline chunk (a multiple of the tile size)
+    if (const char* env = getenv("GTGPU_PIPE_CHUNK")) chunk = strtoull(env, nullptr, 10) / FUSED_TILE * FUSED_TILE;
+    if (chunk >= (uint64_t)FUSED_TILE && n > chunk && (n + chunk - 1) / chunk <= 56) {
+        int fallback = 0;
+        GT_TRY(tokenize_files_pipelined(ix, n, n_files, file_offsets, chr, start, end, chunk, out_file_token_offsets, out_ids,
+                                        &fallback));
+        if (!fallback) return GTGPU_OK;
+    }
     return find_host(ix, n, chr, start, end, 0, nullptr, true, n_files, file_offsets, unk_id, out_file_token_offsets,
                      out_ids);
 }

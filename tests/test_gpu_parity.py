@@ -300,3 +300,37 @@ def test_fragments_random_differential(ctx, kind):
     assert g_off[7] == g_off[8]
     g_off, g_ids = g.tokenize_fragments(qc[:0], qs[:0], qe[:0], bc[:0], 5, unk)
     assert list(g_off) == [0] * 6 and len(g_ids) == 0
+
+
+@pytest.mark.parametrize("kind", ["bits", "ailist"])
+def test_tokenize_files_pipelined_chunks(ctx, kind, monkeypatch):
+    """The chunked H2D / kernel / D2H pipeline of gtgpu_tokenize_files (forced here with 4 096-query chunks) is
+    bit-identical to the single-launch path, with file boundaries on, before and after chunk boundaries."""
+    rng = np.random.default_rng(321)
+    n_chroms = 4
+    offs, s, e, v = _random_index(rng, n_chroms, 5000, "overlap")
+    g, o = _both(ctx, kind, offs, s, e, v)
+    sizes = [4096, 1, 4095, 8192, 3000, 5192, 10, 12278, 4096 * 3, 777]
+    qc, qs, qe = _random_queries(rng, n_chroms, sum(sizes))
+    qc[:] = qc % n_chroms  # every file has hits: the pipelined path is taken end to end
+    fo = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    want_off, want_ids = o.tokenize_files(fo, qc, qs, qe, 5000)
+    monkeypatch.setenv("GTGPU_PIPE_CHUNK", "4096")
+    got_off, got_ids = g.tokenize_files(fo, qc, qs, qe, 5000)
+    assert np.array_equal(got_off, want_off) and np.array_equal(got_ids, want_ids)
+    # an empty file forces the [unk] fallback: still exact
+    sizes2 = sizes[:3] + [0] + sizes[3:]
+    fo2 = np.concatenate([[0], np.cumsum(sizes2)]).astype(np.uint64)
+    got_off, got_ids = g.tokenize_files(fo2, qc, qs, qe, 5000)
+    want_off, want_ids = o.tokenize_files(fo2, qc, qs, qe, 5000)
+    assert np.array_equal(got_off, want_off) and np.array_equal(got_ids, want_ids)
+    # far more hits than the optimistic capacity: overflow fallback
+    monkeypatch.setenv("GTGPU_PIPE_CHUNK", "1024")
+    n = 3000
+    g2, o2 = _both(ctx, kind, np.array([0, n], dtype=np.uint64), np.arange(n, dtype=np.uint32), np.arange(n, dtype=np.uint32) + 4000)
+    q = 5000
+    c0, s0 = np.zeros(q, np.uint32), (np.arange(q) % 2500).astype(np.uint32)
+    fo3 = np.array([0, 2000, q], dtype=np.uint64)
+    a = g2.tokenize_files(fo3, c0, s0, s0 + 300, n)
+    b = o2.tokenize_files(fo3, c0, s0, s0 + 300, n)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
