@@ -49,8 +49,8 @@ struct SegMeta {      // 32 bytes, read as two 128-bit loads
 struct ChromMeta {    // 32 bytes
     uint32_t seg_begin, seg_end;  // segments of this chromosome (component order)
     uint32_t off, len;            // chromosome range in cs_starts / cs_ends
-    uint32_t lut_cs, nb_cs;       // LUT over the chromosome's independently sorted starts
-    uint32_t lut_ce, nb_ce;       // LUT over the chromosome's independently sorted ends
+    uint32_t lut_cs, nb_cs;       // rank LUT (64-bit entries) over the chromosome's independently sorted starts
+    uint32_t lut_ce, nb_ce;       // rank LUT over the chromosome's independently sorted ends
 };
 
 // Bin table (the fast path of find/tokenize).  Window b of a chromosome is the two-bin range
@@ -83,6 +83,12 @@ struct IndexView {
     const uint32_t* cs_starts;
     const uint32_t* cs_ends;
     const uint32_t* lut;
+    // Rank LUT for the counting identity: one 64-bit word per bin = base index (32) | count (3; 7 = more than fit) |
+    // the in-bin offsets of up to rank_inline entries (rank_shift bits each).  lower_bound(key) is ONE 8-byte load:
+    // base + #{inline offsets < key's in-bin offset}.  With about one bin per interval a 50 M-interval database costs
+    // one DRAM sector per search instead of a LUT read plus a bisection over 32-byte sectors of the sorted array.
+    const unsigned long long* rank_lut;
+    uint32_t rank_shift, rank_inline;
     uint32_t n_chroms;
     uint32_t shift;
     uint32_t descending;  // 1 = AIList emission order (descending position inside a segment)

@@ -179,10 +179,41 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
         build_lut(h_starts.data() + m.off, m.len, shift, lut, m.lut_s, m.nb_s);
         build_lut(h_pmax.data() + m.off, m.len, shift, lut, m.lut_p, m.nb_p);
     }
-    for (auto& c : chroms) {
-        build_lut(h_cs.data() + c.off, c.len, shift, lut, c.lut_cs, c.nb_cs);
-        build_lut(h_ce.data() + c.off, c.len, shift, lut, c.lut_ce, c.nb_ce);
+    // rank LUTs (see IndexView::rank_lut) over the chromosome-level sorted starts / ends
+    uint32_t rank_shift = 0;
+    {
+        uint64_t rbudget = std::max<uint64_t>(2 * total, 4096);
+        if (const char* env = getenv("GTGPU_RANK_BINS_PER_INTERVAL")) rbudget = std::max<uint64_t>(strtoull(env, nullptr, 10) * total, 4096);
+        while (rank_shift < 29 && std::max(lut_entries(max_cs, rank_shift), lut_entries(max_ce, rank_shift)) > rbudget) ++rank_shift;
     }
+    const uint32_t rank_inline = rank_shift == 0 ? 4 : std::min<uint32_t>(4, 29 / rank_shift);
+    std::vector<unsigned long long> rank_lut;
+    auto build_rank = [&](const uint32_t* arr, uint32_t n, uint32_t& off, uint32_t& nb) {
+        off = (uint32_t)rank_lut.size();
+        nb = n ? (arr[n - 1] >> rank_shift) + 1 : 0;
+        rank_lut.resize(rank_lut.size() + (size_t)nb + 1);
+        unsigned long long* L = rank_lut.data() + off;
+        uint32_t i = 0;
+        for (uint32_t b = 0; b < nb; ++b) {
+            const uint32_t base = i;
+            unsigned long long word = base;
+            uint32_t cnt = 0;
+            while (i < n && (arr[i] >> rank_shift) == b) {
+                if (cnt < rank_inline)
+                    word |= (unsigned long long)(arr[i] & ((1u << rank_shift) - 1)) << (35 + cnt * rank_shift);
+                ++cnt;
+                ++i;
+            }
+            word |= (unsigned long long)(cnt <= rank_inline ? cnt : 7u) << 32;
+            L[b] = word;
+        }
+        L[nb] = n;  // sentinel: base = n, count 0
+    };
+    for (auto& c : chroms) {
+        build_rank(h_cs.data() + c.off, c.len, c.lut_cs, c.nb_cs);
+        build_rank(h_ce.data() + c.off, c.len, c.lut_ce, c.nb_ce);
+    }
+    if (rank_lut.size() >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "index_build: rank LUT too large");
     if (lut.size() >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "index_build: LUT too large");
 
     // ---- 3b. bin table (fast path of find/tokenize; see common.cuh) ------------------------------------------
@@ -302,6 +333,9 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
     up(h_cs, &v.cs_starts);
     up(h_ce, &v.cs_ends);
     up(lut, &v.lut);
+    up(rank_lut, &v.rank_lut);
+    v.rank_shift = rank_shift;
+    v.rank_inline = rank_inline;
     if (st != GTGPU_OK) {
         gtgpu_index_free(ix);
         return st;

@@ -29,6 +29,32 @@ __device__ __forceinline__ uint32_t lut_lower_bound(const uint32_t* __restrict__
     return lo;
 }
 
+// lower_bound over a chromosome-level sorted array through its rank LUT: one 8-byte load in the common case.
+__device__ __forceinline__ uint32_t rank_lower_bound(const uint32_t* __restrict__ arr, const unsigned long long* __restrict__ rl,
+                                                     uint32_t nb, uint32_t n, uint32_t shift, uint32_t ninl, uint32_t key) {
+    const uint32_t b = key >> shift;
+    if (b >= nb) return n;
+    const unsigned long long w = __ldg(rl + b);
+    const uint32_t base = (uint32_t)w, cnt = (uint32_t)(w >> 32) & 7u;
+    const uint32_t r = key & ((1u << shift) - 1);
+    if (cnt != 7u) {
+        uint32_t below = 0;
+        unsigned long long offs = w >> 35;
+        for (uint32_t j = 0; j < cnt; ++j) {
+            below += (uint32_t)(offs & ((1u << shift) - 1)) < r;
+            offs >>= shift;
+        }
+        return base + below;
+    }
+    uint32_t lo = base, hi = (uint32_t)__ldg(rl + b + 1);  // crowded bin: bisect inside it
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(arr + mid) < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
 // Candidate range of one segment for query [s,e): positions [lo, ub) (global), where ub = #starts < e and
 // lo = first position whose running max end exceeds s.  Everything outside cannot overlap; inside, an interval
 // overlaps iff its own end > s (always true when the segment's ends are monotone).
@@ -112,8 +138,8 @@ __global__ void __launch_bounds__(256) count_kernel(IndexView ix, uint64_t n, co
             uint64_t r = 0;
             if (c < ix.n_chroms) {
                 ChromMeta cm = load_chrom(ix, c);
-                uint64_t last = lut_lower_bound(ix.cs_starts + cm.off, ix.lut + cm.lut_cs, cm.nb_cs, cm.len, ix.shift, e);
-                uint64_t first = lut_lower_bound(ix.cs_ends + cm.off, ix.lut + cm.lut_ce, cm.nb_ce, cm.len, ix.shift, s + 1u);
+                uint64_t last = rank_lower_bound(ix.cs_starts + cm.off, ix.rank_lut + cm.lut_cs, cm.nb_cs, cm.len, ix.rank_shift, ix.rank_inline, e);
+                uint64_t first = rank_lower_bound(ix.cs_ends + cm.off, ix.rank_lut + cm.lut_ce, cm.nb_ce, cm.len, ix.rank_shift, ix.rank_inline, s + 1u);
                 r = last - first;
             }
             reinterpret_cast<uint64_t*>(out)[i] = r;
@@ -124,8 +150,8 @@ __global__ void __launch_bounds__(256) count_kernel(IndexView ix, uint64_t n, co
                     // The BITS identity equals the enumerated count whenever every interval has start <= end and
                     // the query has start < end (no interval can both end <= s and start >= e).
                     ChromMeta cm = load_chrom(ix, c);
-                    uint32_t last = lut_lower_bound(ix.cs_starts + cm.off, ix.lut + cm.lut_cs, cm.nb_cs, cm.len, ix.shift, e);
-                    uint32_t first = lut_lower_bound(ix.cs_ends + cm.off, ix.lut + cm.lut_ce, cm.nb_ce, cm.len, ix.shift, s + 1u);
+                    uint32_t last = rank_lower_bound(ix.cs_starts + cm.off, ix.rank_lut + cm.lut_cs, cm.nb_cs, cm.len, ix.rank_shift, ix.rank_inline, e);
+                    uint32_t first = rank_lower_bound(ix.cs_ends + cm.off, ix.rank_lut + cm.lut_ce, cm.nb_ce, cm.len, ix.rank_shift, ix.rank_inline, s + 1u);
                     cnt = last - first;
                 } else {
                     cnt = count_query_walk(ix, c, s, e, min_bp);
