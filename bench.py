@@ -288,8 +288,19 @@ def main():
     k_ms = statistics.mean(kernel_ms) if kernel_ms else ms_per_step
     peak, peak_src = peaks()
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None  # dram__bytes_read + dram__bytes_write of this kernel from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f)
+        w = tr["workload"]
+        if (w["files_per_gpu"], w["regions_per_file"], w["universe_regions"], w["backend"], w["nested_frac"]) == (
+                args.files, args.per_file, args.universe, args.kind, args.nested):
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "fused_find_kernel", "kernel_ms": k_ms,
+                "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu, same command)" if traffic else None,
+                "peak_source": peak_src, "kernel": "fused_find_kernel", "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_query": algo_bytes / n,
                 "kernel_share_of_step": k_ms / (ev0.elapsed_time(ev1) / args.steps)}
 
