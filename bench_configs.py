@@ -133,7 +133,7 @@ def main():
             out = dict(config="C5 fragment tokenization (host buffers in/out, pageable)", fragments=n, barcodes=n_bc, ids=int(len(ids)),
                        seconds_first_call=t1 - t0, seconds_warm_call=t2 - t1, value=n / (t2 - t1), unit="fragments/s (end to end)",
                        parity_sample_vs_oracle=ok,
-                       note="end-to-end through gtgpu_tokenize_fragments incl. H2D/D2H; group-by uses CUB sort + scan")
+                       note="end-to-end through gtgpu_tokenize_fragments incl. H2D/D2H; group-by uses the hand-written radix sort + scan of sort.cu")
         else:
             continue
         out["setup_seconds"] = time.time() - t_setup

@@ -50,6 +50,8 @@ def lib():
             "gth_tokenizer_id_to_token": (cp, [vp, u32]), "gth_tokenizer_special": (cp, [vp, C.c_int]),
             "gth_tokenizer_kind": (C.c_int, [vp]), "gth_tokenizer_encode_batch": (vp, [vp, u64, vp]),
             "gth_tokenizer_fragments": (vp, [vp, cp]),
+            "gth_igd_single": (vp, [vp, vp]), "gth_igd_find_pairs": (vp, [vp, vp, i32]),
+            "gth_igd_count_per_query": (vp, [vp, vp, i32]),
             "gth_igd_new": (vp, [vp, u64, vp]), "gth_igd_free": (None, [vp]), "gth_igd_num_files": (u64, [vp]),
             "gth_igd_count": (C.c_int, [vp, u64, vp, i32, C.c_int, vp]),
             "gth_lola_contingency": (C.c_int, [vp, u64, vp, vp, i32, vp]),
@@ -326,6 +328,27 @@ class Igd:
         if getattr(self, "_h", None):
             lib().gth_igd_free(self._h)
             self._h = None
+
+    @classmethod
+    def from_single_region_set(cls, subject):
+        """Igd::from_single_region_set (igd.rs:609-634): the subject side of two-set overlap queries."""
+        obj = cls.__new__(cls)
+        obj._sets = [_as_rs(subject)]
+        obj._h = lib().gth_igd_single(device(), obj._sets[0]._h)
+        if not obj._h:
+            _fail()
+        return obj
+
+    def find_overlaps_regionset(self, query, min_overlap=1):
+        """igd.rs:645-678: sorted (query idx, subject idx) pairs."""
+        q = _as_rs(query)
+        flat = _take_lists(lib().gth_igd_find_pairs(self._h, q._h, min_overlap))[0]
+        return list(zip(flat[0::2], flat[1::2]))
+
+    def count_overlaps_per_query(self, query, min_overlap=1):
+        """igd.rs:690-722: distinct subject regions overlapping each query region."""
+        q = _as_rs(query)
+        return _take_lists(lib().gth_igd_count_per_query(self._h, q._h, min_overlap))[0]
 
     def num_files(self):
         return lib().gth_igd_num_files(self._h)

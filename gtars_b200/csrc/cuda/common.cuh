@@ -189,4 +189,12 @@ int32_t launch_unk_expand(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* d_ra
                           const uint64_t* d_out_file_tok, const uint32_t* d_raw_ids, uint32_t unk_id,
                           uint32_t* d_out_ids);
 
+// sort.cu — hand-written scan / radix sort
+size_t exclusive_scan_temp_bytes(uint64_t n, size_t elem);
+template <typename T>
+int32_t exclusive_scan(gtgpu_ctx* ctx, const T* d_in, T* d_out, uint64_t n, void* d_temp);
+size_t radix_sort_temp_bytes(uint64_t n);
+int32_t radix_sort_pairs(gtgpu_ctx* ctx, uint64_t n, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
+                         int bits, void* d_temp, int* result_in_b);
+
 }  // namespace gtgpu

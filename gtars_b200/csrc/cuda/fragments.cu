@@ -3,12 +3,11 @@
 // Every fragment is its own Tokenizer::tokenize call, so a fragment without a hit (or on an unknown chromosome)
 // contributes one unk id; ids are appended to the fragment's barcode list in input order.  Device plan:
 //   1. fused find over all fragments with per-fragment offsets            (kernels.cu, our kernel)
-//   2. stable LSD radix sort of (barcode id, fragment index) by barcode   (CUB DeviceRadixSort — library code)
-//   3. tokens per fragment in sorted order = max(hits, 1); exclusive sum  (CUB DeviceScan — library code)
-//   4. barcode offsets by binary search over the sorted keys; scatter-copy of every fragment's ids (our kernels)
+//   2. stable LSD radix sort of (barcode id, fragment index) by barcode   (sort.cu, hand-written)
+//   3. tokens per fragment in sorted order = max(hits, 1); exclusive scan (sort.cu, hand-written)
+//   4. barcode offsets by binary search over the sorted keys; scatter-copy of every fragment's ids
 // Output is barcode-major: out_barcode_offsets[n_barcodes + 1] + ids.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -21,7 +20,7 @@ __global__ void iota_kernel(uint64_t n, uint32_t* __restrict__ out) {
 
 // tokens of the k-th fragment in barcode order
 __global__ void frag_token_counts_kernel(uint64_t n, const uint32_t* __restrict__ order, const uint64_t* __restrict__ offsets,
-                                         uint64_t* __restrict__ counts) {
+                                         unsigned long long* __restrict__ counts) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
         const uint32_t i = order[k];
@@ -31,8 +30,8 @@ __global__ void frag_token_counts_kernel(uint64_t n, const uint32_t* __restrict_
 }
 
 __global__ void frag_barcode_offsets_kernel(uint32_t n_barcodes, uint64_t n, const uint32_t* __restrict__ sorted_bc,
-                                            const uint64_t* __restrict__ dst, const uint64_t* __restrict__ last_count,
-                                            uint64_t* __restrict__ out) {
+                                            const unsigned long long* __restrict__ dst,
+                                            const unsigned long long* __restrict__ last_count, uint64_t* __restrict__ out) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b > n_barcodes) return;
     uint64_t lo = 0, hi = n;  // first k with sorted_bc[k] >= b
@@ -45,7 +44,7 @@ __global__ void frag_barcode_offsets_kernel(uint32_t n_barcodes, uint64_t n, con
 }
 
 __global__ void frag_scatter_kernel(uint64_t n, const uint32_t* __restrict__ order, const uint64_t* __restrict__ offsets,
-                                    const uint64_t* __restrict__ dst, const uint32_t* __restrict__ raw_ids, uint32_t unk_id,
+                                    const unsigned long long* __restrict__ dst, const uint32_t* __restrict__ raw_ids, uint32_t unk_id,
                                     uint32_t* __restrict__ out) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
@@ -78,7 +77,8 @@ extern "C" int32_t gtgpu_tokenize_fragments(gtgpu_index* ix, uint64_t n, const u
     cudaStream_t st = ctx->stream;
 
     uint32_t *d_chr, *d_start, *d_end, *d_bc, *d_bc_sorted, *d_idx, *d_order, *d_raw = nullptr, *d_out = nullptr;
-    uint64_t *d_off, *d_cnt, *d_dst, *d_bco, *d_misc;
+    uint64_t *d_off, *d_bco, *d_misc;
+    unsigned long long *d_cnt, *d_dst;
     void* d_ws;
     GT_TRY(ctx->scratch_get(SC_CHR, n * 4, (void**)&d_chr));
     GT_TRY(ctx->scratch_get(SC_START, n * 4, (void**)&d_start));
@@ -124,16 +124,18 @@ extern "C" int32_t gtgpu_tokenize_fragments(gtgpu_index* ix, uint64_t n, const u
         ctx->launches++;
         int bits = 1;
         while (bits < 32 && (1ull << bits) < n_barcodes) ++bits;
-        size_t tmp_sort = 0, tmp_scan = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, d_bc, d_bc_sorted, d_idx, d_order, (int64_t)n, 0, bits, st);
-        cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, d_cnt, d_dst, (int64_t)n, st);
         void* d_tmp = nullptr;
-        GT_TRY(ctx->scratch_get(SC_IN3_START, std::max(tmp_sort, tmp_scan), &d_tmp));
-        GT_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_sort, d_bc, d_bc_sorted, d_idx, d_order, (int64_t)n, 0, bits, st));
+        GT_TRY(ctx->scratch_get(SC_IN3_START, std::max(radix_sort_temp_bytes(n), exclusive_scan_temp_bytes(n, 8)), &d_tmp));
+        int in_b = 0;
+        GT_TRY(radix_sort_pairs(ctx, n, d_bc, d_idx, d_bc_sorted, d_order, bits, d_tmp, &in_b));
+        if (!in_b) {  // even number of passes: the sorted data sits in the input buffers
+            std::swap(d_bc, d_bc_sorted);
+            std::swap(d_idx, d_order);
+        }
         // 3. tokens per fragment (per-fragment unk rule) and their destinations
         frag_token_counts_kernel<<<grid, 256, 0, st>>>(n, d_order, d_off, d_cnt);
         ctx->launches++;
-        GT_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_scan, d_cnt, d_dst, (int64_t)n, st));
+        GT_TRY(exclusive_scan<unsigned long long>(ctx, d_cnt, d_dst, n, d_tmp));
         // 4. barcode offsets + scatter
         frag_barcode_offsets_kernel<<<(n_barcodes + 1 + 255) / 256, 256, 0, st>>>(n_barcodes, n, d_bc_sorted, d_dst, d_cnt, d_bco);
         ctx->launches++;

@@ -1,0 +1,215 @@
+// sort.cu — hand-written device primitives: exclusive scan and a stable LSD radix sort of (key, value) pairs.
+//
+// Used by the barcode group-by of fragment tokenization (fragments.cu).  Both are plain multi-kernel designs (no
+// single-pass tricks): they run once per call over arrays that are small next to the fused find kernel's traffic.
+//
+//   exclusive_scan<T>:  reduce per 2 048-element tile -> scan of the tile sums by one block -> per-tile rescan + offset.
+//   radix_sort_pairs:   8 bits per pass; per pass  (1) per-tile digit histograms, stored digit-major,
+//                       (2) exclusive scan of that table = global start of every (digit, tile) bucket,
+//                       (3) scatter: each warp owns 512 consecutive elements, ranks them round by round with
+//                           __match_any_sync, so equal digits keep their input order (stable).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace gtgpu {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* s_warp, T& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    T warp_excl = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        const T t = s_warp[w];
+        if (w < warp) warp_excl += t;
+        tot += t;
+    }
+    __syncthreads();
+    total = tot;
+    return warp_excl + incl - v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const T* __restrict__ in, T* __restrict__ tile_sums, uint64_t n) {
+    __shared__ T s_warp[SCAN_THREADS / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+    T sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const uint64_t i = base + (uint64_t)k * SCAN_THREADS + threadIdx.x;
+        if (i < n) sum += in[i];
+    }
+    T total;
+    block_exclusive_scan<T>(sum, s_warp, total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(T* __restrict__ tile_sums, uint64_t n_tiles) {
+    __shared__ T s_warp[SCAN_THREADS / 32];
+    T carry = 0;
+    for (uint64_t base = 0; base < n_tiles; base += SCAN_THREADS) {
+        const uint64_t i = base + threadIdx.x;
+        const T v = i < n_tiles ? tile_sums[i] : 0;
+        T total;
+        const T excl = block_exclusive_scan<T>(v, s_warp, total);
+        if (i < n_tiles) tile_sums[i] = carry + excl;
+        carry += total;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_down_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                                  const T* __restrict__ tile_offsets, uint64_t n) {
+    __shared__ T s_warp[SCAN_THREADS / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;  // blocked: 8 consecutive
+    T v[SCAN_ITEMS];
+    T sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        sum += v[k];
+    }
+    T total;
+    T run = tile_offsets[blockIdx.x] + block_exclusive_scan<T>(sum, s_warp, total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
+
+size_t exclusive_scan_temp_bytes(uint64_t n, size_t elem) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE + 1) * elem; }
+
+template <typename T>
+int32_t exclusive_scan(gtgpu_ctx* ctx, const T* d_in, T* d_out, uint64_t n, void* d_temp) {
+    if (n == 0) return GTGPU_OK;
+    const uint64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (tiles > 0x7FFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "exclusive_scan: input too large");
+    T* sums = reinterpret_cast<T*>(d_temp);
+    scan_reduce_kernel<T><<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(d_in, sums, n);
+    scan_spine_kernel<T><<<1, SCAN_THREADS, 0, ctx->stream>>>(sums, tiles);
+    scan_down_kernel<T><<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(d_in, d_out, sums, n);
+    ctx->launches += 3;
+    GT_CUDA(cudaGetLastError());
+    return GTGPU_OK;
+}
+template int32_t exclusive_scan<uint32_t>(gtgpu_ctx*, const uint32_t*, uint32_t*, uint64_t, void*);
+template int32_t exclusive_scan<unsigned long long>(gtgpu_ctx*, const unsigned long long*, unsigned long long*, uint64_t, void*);
+
+// ---- radix sort -----------------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ROUNDS = 16;                          // elements per lane
+constexpr int RS_WARP_TILE = 32 * RS_ROUNDS;           // 512 consecutive elements per warp
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;        // 4 096 per block
+
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, int shift,
+                                                                uint32_t n_tiles, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_hist[256];
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int k = 0; k < RS_ROUNDS; ++k) {
+        const uint64_t i = base + (uint64_t)k * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&s_hist[(keys[i] >> shift) & 0xFF], 1u);
+    }
+    __syncthreads();
+    hist[(uint64_t)threadIdx.x * n_tiles + blockIdx.x] = s_hist[threadIdx.x];  // digit-major: one scan orders everything
+}
+
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
+                                                                   const uint32_t* __restrict__ vals_in, uint64_t n, int shift,
+                                                                   uint32_t n_tiles, const uint32_t* __restrict__ bucket_start,
+                                                                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+    constexpr int WARPS = RS_THREADS / 32;
+    __shared__ uint32_t s_count[WARPS][256];  // first per-warp digit counts, then the running output cursor per (warp, digit)
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < WARPS * 256; i += RS_THREADS) (&s_count[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE + (uint64_t)warp * RS_WARP_TILE + lane;
+    uint32_t key[RS_ROUNDS], val[RS_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const uint64_t i = base + 32 * r;
+        const bool ok = i < n;
+        key[r] = ok ? keys_in[i] : 0;
+        val[r] = ok ? vals_in[i] : 0;
+        if (ok) atomicAdd(&s_count[warp][(key[r] >> shift) & 0xFF], 1u);
+    }
+    __syncthreads();
+    {   // thread d turns the per-warp counts of digit d into output cursors (warp order = input order)
+        const uint32_t d = threadIdx.x;
+        uint32_t run = bucket_start[(uint64_t)d * n_tiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t c = s_count[w][d];
+            s_count[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const bool ok = base + 32 * r < n;
+        const uint32_t d = ok ? (key[r] >> shift) & 0xFF : 0x100u + lane;  // invalid lanes never match anyone
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+        uint32_t pos = 0;
+        if (ok) pos = s_count[warp][d] + rank;
+        __syncwarp();
+        if (ok && rank == 0) s_count[warp][d] += __popc(peers);
+        __syncwarp();
+        if (ok) {
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
+    }
+}
+
+size_t radix_sort_temp_bytes(uint64_t n) {
+    const uint64_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    const uint64_t table = 256 * tiles;
+    return (size_t)(table * 4 * 2 + exclusive_scan_temp_bytes(table, 4) + 256);
+}
+
+// Sorts by bits [0, bits) of the key.  keys/vals ping-pong between the a and b buffers; *result_in_b tells where the
+// sorted data ended up.  n < 2^32.
+int32_t radix_sort_pairs(gtgpu_ctx* ctx, uint64_t n, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
+                         int bits, void* d_temp, int* result_in_b) {
+    *result_in_b = 0;
+    if (n == 0 || bits <= 0) return GTGPU_OK;
+    if (n >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "radix_sort_pairs: too many elements");
+    const uint32_t tiles = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+    const uint64_t table = 256ull * tiles;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(d_temp);
+    uint32_t* starts = hist + table;
+    void* scan_tmp = starts + table;
+    uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
+    for (int shift = 0; shift < bits; shift += 8) {
+        radix_hist_kernel<<<tiles, RS_THREADS, 0, ctx->stream>>>(ki, n, shift, tiles, hist);
+        ctx->launches++;
+        GT_TRY(exclusive_scan<uint32_t>(ctx, hist, starts, table, scan_tmp));
+        radix_scatter_kernel<<<tiles, RS_THREADS, 0, ctx->stream>>>(ki, vi, n, shift, tiles, starts, ko, vo);
+        ctx->launches++;
+        std::swap(ki, ko);
+        std::swap(vi, vo);
+        *result_in_b ^= 1;
+    }
+    GT_CUDA(cudaGetLastError());
+    return GTGPU_OK;
+}
+
+}  // namespace gtgpu

@@ -525,7 +525,9 @@ Igd::Igd(std::shared_ptr<Device> dev, const std::vector<const RegionSet*>& sets)
                           r.end.data(), &igd_),
           "gtgpu_igd_build");
 }
-Igd::~Igd() { gtgpu_igd_free(igd_); }
+Igd::~Igd() {
+    if (igd_) gtgpu_igd_free(igd_);
+}
 
 std::vector<uint64_t> Igd::count_region_hits_batch(const std::vector<const RegionSet*>& sets, int32_t min_overlap, bool pairwise) const {
     std::vector<uint64_t> set_offsets(sets.size() + 1, 0);
@@ -543,6 +545,40 @@ std::vector<uint64_t> Igd::count_region_hits_batch(const std::vector<const Regio
     check(fn(igd_, sets.size(), set_offsets.data(), q.chr.data(), q.start.data(), q.end.data(), min_overlap, out.data()),
           pairwise ? "gtgpu_igd_count_set_overlaps" : "gtgpu_igd_count_region_hits");
     return out;
+}
+
+std::unique_ptr<Igd> Igd::from_single_region_set(std::shared_ptr<Device> dev, const RegionSet& subject) {
+    std::unique_ptr<Igd> g(new Igd());
+    g->dev_ = dev;
+    g->n_files_ = 1;
+    RegionSet kept;
+    for (size_t i = 0; i < subject.regions.size(); ++i) {
+        const Region& r = subject.regions[i];
+        const int32_t s = (int32_t)r.start, e = (int32_t)r.end;  // igd.rs:623-629 casts, Igd::add drops the rest
+        if (s < 0 || e < 0 || s >= e) continue;
+        kept.regions.push_back(Region{r.chr, r.start, r.end, ""});
+        g->single_src_.push_back((uint32_t)i);
+    }
+    g->single_.reset(new MultiChromOverlapper(dev, kept, OverlapperType::Bits));
+    return g;
+}
+
+std::vector<std::pair<uint32_t, uint32_t>> Igd::find_overlaps_regionset(const RegionSet& query, int32_t min_overlap) const {
+    if (!single_) throw Error("find_overlaps_regionset needs an Igd built with from_single_region_set");
+    if (min_overlap < 1) throw Error("min_overlap < 1 depends on the reference's tile layout and is not supported");
+    std::vector<std::pair<uint32_t, uint32_t>> pairs;
+    auto idx = single_->find_overlaps_indices(query, min_overlap);
+    for (size_t q = 0; q < idx.size(); ++q)
+        for (uint32_t v : idx[q]) pairs.emplace_back((uint32_t)q, single_src_[v]);
+    std::sort(pairs.begin(), pairs.end());
+    return pairs;
+}
+
+std::vector<uint32_t> Igd::count_overlaps_per_query(const RegionSet& query, int32_t min_overlap) const {
+    if (!single_) throw Error("count_overlaps_per_query needs an Igd built with from_single_region_set");
+    if (min_overlap < 1) throw Error("min_overlap < 1 depends on the reference's tile layout and is not supported");
+    auto c = single_->count_overlaps(query, min_overlap);
+    return std::vector<uint32_t>(c.begin(), c.end());
 }
 
 std::vector<uint64_t> Igd::count_set_overlaps(const RegionSet& regions, int32_t min_overlap) const {

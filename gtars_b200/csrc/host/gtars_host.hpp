@@ -174,11 +174,22 @@ class Igd {
     // Many query sets in one device pass: row-major [n_sets x n_files].
     std::vector<uint64_t> count_region_hits_batch(const std::vector<const RegionSet*>& sets, int32_t min_overlap, bool pairwise) const;
 
+    // Igd::from_single_region_set (igd.rs:609-634): two-set overlap queries; the subject index is kept per record.
+    static std::unique_ptr<Igd> from_single_region_set(std::shared_ptr<Device> dev, const RegionSet& subject);
+    // igd.rs:645-678: (query idx, subject idx) pairs, one per overlapping pair, sorted.
+    std::vector<std::pair<uint32_t, uint32_t>> find_overlaps_regionset(const RegionSet& query, int32_t min_overlap = 1) const;
+    // igd.rs:690-722: number of distinct subject regions overlapping each query region.
+    std::vector<uint32_t> count_overlaps_per_query(const RegionSet& query, int32_t min_overlap = 1) const;
+
    private:
+    Igd() = default;
     std::shared_ptr<Device> dev_;
     gtgpu_igd* igd_ = nullptr;
     ChromMap cmap_;
     size_t n_files_ = 0;
+    // single-set mode: the kept subjects (0 <= start < end as i32, like Igd::add) in an overlap index, val = subject idx
+    std::unique_ptr<MultiChromOverlapper> single_;
+    std::vector<uint32_t> single_src_;
 };
 
 // run_lola up to the contingency tables (enrichment.rs:198-220): [user set][db set].  Fisher / ranking stay with the caller.

@@ -144,6 +144,29 @@ void* gth_tokenizer_fragments(void* t, const char* path) {
 void* gth_igd_new(void* dev, uint64_t n, void** region_sets) {
     return guard([&]() -> void* { return new Igd(*(std::shared_ptr<Device>*)dev, as_sets(n, region_sets)); }, nullptr);
 }
+void* gth_igd_single(void* dev, void* subject) {
+    return guard([&]() -> void* { return Igd::from_single_region_set(*(std::shared_ptr<Device>*)dev, *(RegionSet*)subject).release(); },
+                 nullptr);
+}
+// pairs as one flat list [q0, s0, q1, s1, ...]
+void* gth_igd_find_pairs(void* g, void* query, int32_t min_overlap) {
+    return guard([&]() -> void* {
+        Lists* l = new Lists();
+        l->lists.emplace_back();
+        for (auto& p : ((Igd*)g)->find_overlaps_regionset(*(RegionSet*)query, min_overlap)) {
+            l->lists[0].push_back(p.first);
+            l->lists[0].push_back(p.second);
+        }
+        return l;
+    }, nullptr);
+}
+void* gth_igd_count_per_query(void* g, void* query, int32_t min_overlap) {
+    return guard([&]() -> void* {
+        Lists* l = new Lists();
+        l->lists.push_back(((Igd*)g)->count_overlaps_per_query(*(RegionSet*)query, min_overlap));
+        return l;
+    }, nullptr);
+}
 void gth_igd_free(void* g) { delete (Igd*)g; }
 uint64_t gth_igd_num_files(void* g) { return ((Igd*)g)->num_files(); }
 int gth_igd_count(void* g, uint64_t n_sets, void** region_sets, int32_t min_overlap, int pairwise, uint64_t* out) {

@@ -180,6 +180,22 @@ KATS = {
          "db": [[["chr1", 100, 200], ["chr1", 150, 250], ["chr1", 500, 600]]],
          "query": [["chr1", 160, 180], ["chr1", 550, 580], ["chr1", 700, 800]], "min_overlap": 1, "per_query": [2, 1, 0]},
     ],
+    # ---- K7b: two-set IGD queries (from_single_region_set) -------------------------------------------------
+    "K7_igd_single": [
+        {"cite": "igd.rs:1244-1262", "subject": [["chr1", 100, 200], ["chr1", 300, 400], ["chr1", 500, 600]],
+         "query": [["chr1", 150, 350], ["chr1", 550, 650], ["chr1", 700, 800]], "min_overlap": 1, "pairs": [[0, 0], [0, 1], [1, 2]]},
+        {"cite": "igd.rs:1264-1272", "subject": [["chr1", 100, 200]], "query": [["chr1", 300, 400]], "min_overlap": 1, "pairs": []},
+        {"cite": "igd.rs:1274-1286 (10 bp overlap, min_overlap 1)", "subject": [["chr1", 100, 200]], "query": [["chr1", 190, 300]],
+         "min_overlap": 1, "pairs": [[0, 0]]},
+        {"cite": "igd.rs:1274-1286 (10 bp overlap, min_overlap 50)", "subject": [["chr1", 100, 200]], "query": [["chr1", 190, 300]],
+         "min_overlap": 50, "pairs": []},
+        {"cite": "igd.rs:1288-1305 (multi chrom)", "subject": [["chr1", 100, 200], ["chr2", 100, 200]],
+         "query": [["chr1", 150, 180], ["chr2", 150, 180], ["chr3", 150, 180]], "min_overlap": 1, "pairs": [[0, 0], [1, 1]]},
+        {"cite": "igd.rs:1307-1325 (count_overlaps_per_query)", "subject": [["chr1", 100, 200], ["chr1", 150, 250], ["chr1", 500, 600]],
+         "query": [["chr1", 160, 180], ["chr1", 550, 580], ["chr1", 700, 800]], "min_overlap": 1, "per_query": [2, 1, 0]},
+        {"cite": "igd.rs:1337-1355 (multi-tile subject counted once)", "subject": [["chr1", 10000, 40000]],
+         "query": [["chr1", 15000, 35000]], "min_overlap": 1, "pairs": [[0, 0]], "per_query": [1]},
+    ],
     # ---- K9: LOLA contingency counts -------------------------------------------------------------------
     "K9_lola": [
         {"cite": "enrichment.rs:879-922 (a,b,c,d = 1,1,2,6)", "db": [[["chr1", 100, 200], ["chr1", 300, 400]]],

@@ -173,3 +173,17 @@ def test_igd_unit_kats_through_c_abi(golden):
             assert list(hits) == q["hits"], (case["cite"], q)
         g.close()
     ctx.close()
+
+
+def test_igd_single_region_set_kats(api, golden):
+    """gtars-igd/src/igd.rs:1244-1355: find_overlaps_regionset / count_overlaps_per_query."""
+    for case in golden[1]["K7_igd_single"]:
+        igd = api.Igd.from_single_region_set([tuple(r) for r in case["subject"]])
+        q = [tuple(r) for r in case["query"]]
+        if "pairs" in case:
+            assert igd.find_overlaps_regionset(q, case["min_overlap"]) == [tuple(p) for p in case["pairs"]], case["cite"]
+        if "per_query" in case:
+            assert igd.count_overlaps_per_query(q, case["min_overlap"]) == case["per_query"], case["cite"]
+    # subjects Igd::add would drop (empty / reversed) never count
+    igd = api.Igd.from_single_region_set([("chr1", 100, 100), ("chr1", 300, 200), ("chr1", 50, 150)])
+    assert igd.find_overlaps_regionset([("chr1", 0, 1000)], 1) == [(0, 2)]

@@ -234,3 +234,26 @@ def test_bits_count_equals_find_len_random():
     assert (ob == oa).all()
     for i in range(0, 2000, 37):
         assert sorted(vb[int(ob[i]):int(ob[i + 1])]) == sorted(va[int(oa[i]):int(oa[i + 1])])
+
+
+def test_igd_single_set_kats(golden):
+    """igd.rs:1244-1355 through the oracle's tile walk: distinct subjects per query (value = subject index)."""
+    for case in golden[1]["K7_igd_single"]:
+        cmap = helpers.ChromMap()
+        g = orc.Igd()
+        for i, (chr_, s, e) in enumerate(case["subject"]):
+            g.add(cmap.add(chr_), s, e, i, i)  # one "file" per subject: per-file hits > 0 <=> the pair overlaps
+        g.n_files = len(case["subject"])
+        orc.lib().orc_igd_set_n_files(g._h, g.n_files)
+        g.finalize()
+        pairs, per_query = [], []
+        for qi, (chr_, s, e) in enumerate(case["query"]):
+            hits = np.zeros(g.n_files, dtype=np.uint64)
+            if cmap.get(chr_) != helpers.UNKNOWN:
+                g.count_overlaps(cmap.get(chr_), s, e, case["min_overlap"], hits)
+            pairs += [[qi, int(j)] for j in np.flatnonzero(hits)]
+            per_query.append(int((hits > 0).sum()))
+        if "pairs" in case:
+            assert pairs == case["pairs"], case["cite"]
+        if "per_query" in case:
+            assert per_query == case["per_query"], case["cite"]
