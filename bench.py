@@ -307,15 +307,22 @@ def main():
     # ---- e2e: the C-ABI host entry point with pinned host buffers --------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        h_chr, h_start, h_end = (ffi.pinned_empty(n, np.uint32) for _ in range(3))
-        for h, d in ((h_chr, d_chr), (h_start, d_start), (h_end, d_end)):
+        # What a Rust caller holds after RegionSet::try_from: start / end arrays plus, because the files are sorted by
+        # chromosome, a handful of (offset, chromosome id) runs per file (gtgpu_tokenize_files_runs).
+        h_start, h_end = (ffi.pinned_empty(n, np.uint32) for _ in range(2))
+        for h, d in ((h_start, d_start), (h_end, d_end)):
             torch.from_numpy(h.view(np.int32)).copy_(d)
         h_fo = d_file_offsets.cpu().numpy().astype(np.uint64)
+        brk = torch.nonzero(d_chr[1:] != d_chr[:-1]).flatten() + 1
+        run_starts = torch.unique(torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), brk, d_file_offsets[:-1]]))
+        h_run_chr = d_chr[run_starts].cpu().numpy().view(np.uint32)
+        h_run_off = torch.cat([run_starts, torch.tensor([n], device=dev)]).cpu().numpy().astype(np.uint64)
+        del brk, run_starts
         torch.cuda.synchronize()
         L = ffi.lib()
 
         def e2e_step():
-            off, buf = index.tokenize_files(h_fo, h_chr, h_start, h_end, u["unk_id"], keep_buf=True)
+            off, buf = index.tokenize_files_runs(h_fo, h_run_off, h_run_chr, h_start, h_end, u["unk_id"], keep_buf=True)
             total = int(off[-1])  # the step's result is read on the host
             assert L.gtgpu_buf_len(buf) == total
             L.gtgpu_buf_free(buf)
@@ -330,9 +337,11 @@ def main():
         torch.cuda.synchronize()
         barrier()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
-        e2e = {"value": total_queries / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 12 * n + 8 * (n_files + 1),
+        e2e = {"value": total_queries / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": 8 * n + 8 * (n_files + 1) + 12 * len(h_run_chr) + 8,
                "d2h_bytes_per_step": 4 * e2e_total + 8 * (n_files + 1), "ms_per_step": e2e_s * 1e3,
-               "api": "gtgpu_tokenize_files (pinned host buffers in, pinned result buffer out)"}
+               "api": "gtgpu_tokenize_files_runs (pinned host start/end + chromosome runs in, pinned result buffer out)",
+               "chromosome_runs": int(len(h_run_chr))}
         assert e2e_total == hits + n_empty_files
 
     # ---- parity spot check + cpu baseline (rank 0, N = 1) ------------------------------------------------------------------

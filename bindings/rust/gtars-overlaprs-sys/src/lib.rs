@@ -44,6 +44,9 @@ extern "C" {
     pub fn gtgpu_tokenize_files(index: *mut gtgpu_index, n_files: u64, file_offsets: *const u64, chr: *const u32,
                                 start: *const u32, end: *const u32, unk_id: u32, out_file_token_offsets: *mut u64,
                                 out_ids: *mut *mut gtgpu_buf) -> i32;
+    pub fn gtgpu_tokenize_files_runs(index: *mut gtgpu_index, n_files: u64, file_offsets: *const u64, n_runs: u64,
+                                     run_offsets: *const u64, run_chr: *const u32, start: *const u32, end: *const u32,
+                                     unk_id: u32, out_file_token_offsets: *mut u64, out_ids: *mut *mut gtgpu_buf) -> i32;
     pub fn gtgpu_tokenize_fragments(index: *mut gtgpu_index, n: u64, chr: *const u32, start: *const u32, end: *const u32,
                                     barcode_id: *const u32, n_barcodes: u32, unk_id: u32, out_barcode_offsets: *mut u64,
                                     out_ids: *mut *mut gtgpu_buf) -> i32;

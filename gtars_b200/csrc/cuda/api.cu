@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -348,7 +349,8 @@ int32_t find_host(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32
 // optimistic capacity, a file with no token at all ([unk] insertion shifts the ids), or a tile overflow.
 int32_t tokenize_files_pipelined(gtgpu_index* ix, uint64_t n, uint64_t n_files, const uint64_t* file_offsets,
                                  const uint32_t* chr, const uint32_t* start, const uint32_t* end, uint64_t chunk,
-                                 uint64_t* out_file_tok, gtgpu_buf** out_ids, int* fallback) {
+                                 uint64_t* out_file_tok, gtgpu_buf** out_ids, int* fallback, uint64_t n_runs = 0,
+                                 const uint64_t* run_offsets = nullptr, const uint32_t* run_chr = nullptr) {
     *fallback = 0;
     gtgpu_ctx* ctx = ix->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -385,6 +387,15 @@ int32_t tokenize_files_pipelined(gtgpu_index* ix, uint64_t n, uint64_t n_files, 
             }
         }
         first_f[n_chunks] = n_files + 1;
+    }
+    // chromosome ids given as runs: ship the runs once, expand them per chunk on the device (no per-query chr H2D)
+    uint64_t* d_run_off = nullptr;
+    uint32_t* d_run_chr = nullptr;
+    if (run_offsets) {
+        GT_TRY(ctx->scratch_get(SC_IN3_CHR, (n_runs + 1) * 8, (void**)&d_run_off));
+        GT_TRY(ctx->scratch_get(SC_IN3_START, (n_runs + 1) * 4, (void**)&d_run_chr));
+        GT_CUDA(cudaMemcpyAsync(d_run_off, run_offsets, (n_runs + 1) * 8, cudaMemcpyHostToDevice, st));
+        GT_CUDA(cudaMemcpyAsync(d_run_chr, run_chr, n_runs * 4, cudaMemcpyHostToDevice, st));
     }
     GT_CUDA(cudaMemcpyAsync(d_fo, rebased.data(), (n_files + 1) * 8, cudaMemcpyHostToDevice, st));
     GT_CUDA(cudaMemsetAsync(d_run, 0, (n_chunks + 1) * 8, st));
@@ -423,11 +434,12 @@ int32_t tokenize_files_pipelined(gtgpu_index* ix, uint64_t n, uint64_t n_files, 
         const int b = (int)(k & 1);
         const uint64_t q0 = k * chunk, cn = std::min(chunk, n - q0);
         if (k >= 2) cudaStreamWaitEvent(ctx->copy_in, ev_free[b], 0);
-        cudaMemcpyAsync(in[b][0], chr + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in);
+        if (!run_offsets) cudaMemcpyAsync(in[b][0], chr + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in);
         cudaMemcpyAsync(in[b][1], start + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in);
         cerr = cudaMemcpyAsync(in[b][2], end + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in);
         cudaEventRecord(ev_in[b], ctx->copy_in);
         cudaStreamWaitEvent(st, ev_in[b], 0);
+        if (run_offsets && status == GTGPU_OK) status = launch_expand_runs(ctx, n_runs, d_run_off, d_run_chr, q0, cn, in[b][0]);
         const uint64_t L = first_f[k + 1] - first_f[k];  // file boundaries owned by this chunk
         status = launch_fused_find(ix, cn, L ? L - 1 : 0, d_fo + first_f[k], in[b][0], in[b][1], in[b][2], 0, d_ids, cap, nullptr,
                                    L ? d_raw_tok + first_f[k] : nullptr, d_ws, d_run + k, d_run + k + 1, (uint32_t*)(d_misc + 2));
@@ -515,6 +527,36 @@ int32_t gtgpu_tokenize_files(gtgpu_index* ix, uint64_t n_files, const uint64_t* 
         if (!fallback) return GTGPU_OK;
     }
     return find_host(ix, n, chr, start, end, 0, nullptr, true, n_files, file_offsets, unk_id, out_file_token_offsets,
+                     out_ids);
+}
+
+int32_t gtgpu_tokenize_files_runs(gtgpu_index* ix, uint64_t n_files, const uint64_t* file_offsets, uint64_t n_runs,
+                                  const uint64_t* run_offsets, const uint32_t* run_chr, const uint32_t* start,
+                                  const uint32_t* end, uint32_t unk_id, uint64_t* out_file_token_offsets,
+                                  gtgpu_buf** out_ids) {
+    if (!ix || !file_offsets || !run_offsets || !out_file_token_offsets || !out_ids || (n_runs && !run_chr))
+        return fail(GTGPU_ERR_INVALID, "tokenize_files_runs: null argument");
+    if (file_offsets[0] != 0 || run_offsets[0] != 0)
+        return fail(GTGPU_ERR_INVALID, "tokenize_files_runs: offsets must start at 0");
+    for (uint64_t f = 0; f < n_files; ++f)
+        if (file_offsets[f] > file_offsets[f + 1]) return fail(GTGPU_ERR_INVALID, "tokenize_files_runs: file_offsets not monotone");
+    for (uint64_t r = 0; r < n_runs; ++r)
+        if (run_offsets[r] > run_offsets[r + 1]) return fail(GTGPU_ERR_INVALID, "tokenize_files_runs: run_offsets not monotone");
+    const uint64_t n = file_offsets[n_files];
+    if (run_offsets[n_runs] != n) return fail(GTGPU_ERR_INVALID, "tokenize_files_runs: runs do not cover the queries");
+    if (n && (!start || !end)) return fail(GTGPU_ERR_INVALID, "tokenize_files_runs: null query arrays");
+    uint64_t chunk = 32ull << 20;
+    if (const char* env = getenv("GTGPU_PIPE_CHUNK")) chunk = strtoull(env, nullptr, 10) / FUSED_TILE * FUSED_TILE;
+    if (chunk >= (uint64_t)FUSED_TILE && n > chunk && (n + chunk - 1) / chunk <= 56) {
+        int fallback = 0;
+        GT_TRY(tokenize_files_pipelined(ix, n, n_files, file_offsets, nullptr, start, end, chunk, out_file_token_offsets, out_ids,
+                                        &fallback, n_runs, run_offsets, run_chr));
+        if (!fallback) return GTGPU_OK;
+    }
+    // small batches and the rare fallbacks: expand on the host and take the plain path
+    std::vector<uint32_t> chr(n);
+    for (uint64_t r = 0; r < n_runs; ++r) std::fill(chr.begin() + run_offsets[r], chr.begin() + run_offsets[r + 1], run_chr[r]);
+    return find_host(ix, n, chr.data(), start, end, 0, nullptr, true, n_files, file_offsets, unk_id, out_file_token_offsets,
                      out_ids);
 }
 

@@ -401,7 +401,11 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
         const uint32_t t = atomicAdd(ws.counter, 1u);
         s_tile[buf] = t;
         uint32_t staged = 0;
+#ifdef GT_L2_PREFETCH
+        if (false) {
+#else
         if (tma_ok && t < n_tiles && (uint64_t)(t + 1) * TILE <= n) {
+#endif
             staged = 1;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this buffer are done
             mbar_expect_tx(&s_bar[buf], 3 * TILE * 4);
@@ -623,6 +627,19 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
 #ifdef GT_PHASE_TIMING
             if (lane == 0) { s_acc[warp][8] += _windows; s_acc[warp][9] += 1; }
 #endif
+#ifdef GT_L2_PREFETCH
+            {   // next tile's query rows -> L2 (3 rows x 4 KiB = 384 sectors), so the loads at the top of the next step hit L2
+                const uint32_t nt = s_tile[par ^ 1];
+                if (nt < n_tiles) {
+                    const uint64_t q0 = (uint64_t)nt * TILE;
+                    for (uint32_t i = tid; i < 3 * (TILE / 8); i += FUSED_BLOCK) {
+                        const uint32_t a = i / (TILE / 8), o = (i % (TILE / 8)) * 8;
+                        const uint32_t* p = (a == 0 ? chr : a == 1 ? start : end) + q0 + o;
+                        if (q0 + o < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                    }
+                }
+            }
+#endif
             const uint64_t tile_start = (uint64_t)prev.tile * TILE;
             const uint64_t tile_base = base + excl;
             if (tid == 0) {
@@ -840,6 +857,42 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
     }
 #undef GT_VARIANT
     if (err != cudaSuccess) return fail(GTGPU_ERR_CUDA, std::string("fused_find launch: ") + cudaGetErrorString(err));
+    ctx->launches++;
+    GT_CUDA(cudaGetLastError());
+    return GTGPU_OK;
+}
+
+// ================================================================================================================
+// chromosome ids given as runs (sorted BED files): expand the runs that intersect [q0, q0 + cn) into out[0..cn)
+// ================================================================================================================
+__global__ void expand_runs_kernel(uint64_t n_runs, const uint64_t* __restrict__ run_offsets, const uint32_t* __restrict__ run_chr,
+                                   uint64_t q0, uint64_t cn, uint32_t* __restrict__ out) {
+    __shared__ uint64_t s_first;
+    const uint64_t per_block = (cn + gridDim.x - 1) / gridDim.x;
+    const uint64_t lo = q0 + (uint64_t)blockIdx.x * per_block, hi = min(q0 + cn, lo + per_block);
+    if (lo >= hi) return;
+    if (threadIdx.x == 0) {  // last run whose offset is <= lo
+        uint64_t a = 0, b = n_runs;
+        while (a < b) {
+            uint64_t m = (a + b + 1) >> 1;
+            if (m < n_runs && run_offsets[m] <= lo) a = m;
+            else b = m - 1;
+        }
+        s_first = a;
+    }
+    __syncthreads();
+    for (uint64_t r = s_first; r < n_runs && run_offsets[r] < hi; ++r) {
+        const uint64_t a = max(run_offsets[r], lo), b = min(run_offsets[r + 1], hi);
+        const uint32_t c = run_chr[r];
+        for (uint64_t i = a + threadIdx.x; i < b; i += blockDim.x) out[i - q0] = c;
+    }
+}
+
+int32_t launch_expand_runs(gtgpu_ctx* ctx, uint64_t n_runs, const uint64_t* d_run_offsets, const uint32_t* d_run_chr, uint64_t q0,
+                           uint64_t cn, uint32_t* d_out) {
+    if (cn == 0) return GTGPU_OK;
+    int grid = (int)std::min<uint64_t>((cn + 8191) / 8192, (uint64_t)ctx->sm_count * 16);
+    expand_runs_kernel<<<grid, 256, 0, ctx->stream>>>(n_runs, d_run_offsets, d_run_chr, q0, cn, d_out);
     ctx->launches++;
     GT_CUDA(cudaGetLastError());
     return GTGPU_OK;

@@ -418,21 +418,29 @@ std::unique_ptr<Tokenizer> Tokenizer::from_auto(std::shared_ptr<Device> dev, con
 }
 
 std::vector<std::vector<uint32_t>> Tokenizer::encode_batch(const std::vector<const std::vector<Region>*>& calls) const {
-    std::vector<uint64_t> file_offsets(calls.size() + 1, 0);
-    FlatQueries q;
+    // Chromosome ids are shipped as runs: region sets read from BED files are sorted by chromosome, so the device
+    // rebuilds the per-query chromosome array from a handful of (offset, id) pairs per file.
+    std::vector<uint64_t> file_offsets(calls.size() + 1, 0), run_offsets;
+    std::vector<uint32_t> run_chr, start, end;
     for (size_t f = 0; f < calls.size(); ++f) {
+        const std::string* last = nullptr;  // a run never spans two files
         for (const auto& r : *calls[f]) {
-            q.chr.push_back(cmap_.get(r.chr));
-            q.start.push_back(r.start);
-            q.end.push_back(r.end);
+            if (!last || r.chr != *last) {
+                run_offsets.push_back(start.size());
+                run_chr.push_back(cmap_.get(r.chr));
+                last = &r.chr;
+            }
+            start.push_back(r.start);
+            end.push_back(r.end);
         }
-        file_offsets[f + 1] = q.chr.size();
+        file_offsets[f + 1] = start.size();
     }
+    run_offsets.push_back(start.size());  // n_runs + 1 entries, the first one is 0
     std::vector<uint64_t> tok_offsets(calls.size() + 1);
     PinnedResult res;
-    check(gtgpu_tokenize_files(index_, calls.size(), file_offsets.data(), q.chr.data(), q.start.data(), q.end.data(), unk_id_,
-                               tok_offsets.data(), &res.buf),
-          "gtgpu_tokenize_files");
+    check(gtgpu_tokenize_files_runs(index_, calls.size(), file_offsets.data(), run_chr.size(), run_offsets.data(), run_chr.data(),
+                                    start.data(), end.data(), unk_id_, tok_offsets.data(), &res.buf),
+          "gtgpu_tokenize_files_runs");
     std::vector<std::vector<uint32_t>> out(calls.size());
     for (size_t f = 0; f < calls.size(); ++f) out[f].assign(res.data() + tok_offsets[f], res.data() + tok_offsets[f + 1]);
     return out;

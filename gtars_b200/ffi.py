@@ -42,6 +42,7 @@ SIGNATURES = {
     "gtgpu_any": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _vp]),
     "gtgpu_find": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _vp, _vp]),
     "gtgpu_tokenize_files": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
+    "gtgpu_tokenize_files_runs": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
     "gtgpu_tokenize_fragments": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "gtgpu_igd_build": (_i32, [_vp, _u64, _vp, _u32, _vp, _vp, _vp, _vp]),
     "gtgpu_igd_free": (_i32, [_vp]),
@@ -248,6 +249,17 @@ class Index:
         h = C.c_void_p()
         check(lib().gtgpu_tokenize_files(self._h, len(fo) - 1, _p(fo), _p(chr), _p(start), _p(end), unk_id,
                                          _p(out_off), C.byref(h)))
+        if keep_buf:
+            return out_off, h
+        return out_off, _take(h)
+
+    def tokenize_files_runs(self, file_offsets, run_offsets, run_chr, start, end, unk_id, keep_buf=False):
+        fo, ro = _arr(file_offsets, np.uint64), _arr(run_offsets, np.uint64)
+        rc, start, end = _arr(run_chr, np.uint32), _arr(start, np.uint32), _arr(end, np.uint32)
+        out_off = np.empty(len(fo), dtype=np.uint64)
+        h = C.c_void_p()
+        check(lib().gtgpu_tokenize_files_runs(self._h, len(fo) - 1, _p(fo), len(rc), _p(ro), _p(rc), _p(start), _p(end),
+                                              unk_id, _p(out_off), C.byref(h)))
         if keep_buf:
             return out_off, h
         return out_off, _take(h)

@@ -117,6 +117,16 @@ int32_t gtgpu_tokenize_files(gtgpu_index* index, uint64_t n_files, const uint64_
                              const uint32_t* chr, const uint32_t* start, const uint32_t* end, uint32_t unk_id,
                              uint64_t* out_file_token_offsets, gtgpu_buf** out_ids);
 
+/* gtgpu_tokenize_files for queries whose chromosome ids come as RUNS: run r covers queries
+ * [run_offsets[r], run_offsets[r+1]) and all of them lie on chromosome run_chr[r].  A BED file read by
+ * RegionSet::try_from is sorted by chromosome (gtars-core/src/models/region_set.rs:502-505), so a file contributes a
+ * handful of runs; the per-query chromosome array is then rebuilt on the device and never crosses PCIe (a third of
+ * the input bytes).  run_offsets has n_runs + 1 entries, starts at 0 and ends at file_offsets[n_files]. */
+int32_t gtgpu_tokenize_files_runs(gtgpu_index* index, uint64_t n_files, const uint64_t* file_offsets, uint64_t n_runs,
+                                  const uint64_t* run_offsets, const uint32_t* run_chr, const uint32_t* start,
+                                  const uint32_t* end, uint32_t unk_id, uint64_t* out_file_token_offsets,
+                                  gtgpu_buf** out_ids);
+
 /* tokenize_fragment_file (gtars-tokenizers/src/utils/fragments.rs:12-82) over pre-parsed fragments: every fragment
  * is one Tokenizer::tokenize call (a fragment with no hit, or on an unknown chromosome, yields unk_id), ids are
  * appended to the fragment's barcode list in input order.  barcode_id[i] < n_barcodes (dense ids, mapped by the

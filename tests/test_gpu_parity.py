@@ -334,3 +334,29 @@ def test_tokenize_files_pipelined_chunks(ctx, kind, monkeypatch):
     a = g2.tokenize_files(fo3, c0, s0, s0 + 300, n)
     b = o2.tokenize_files(fo3, c0, s0, s0 + 300, n)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_tokenize_files_runs_variant(ctx, monkeypatch):
+    """gtgpu_tokenize_files_runs (chromosome ids as runs) == gtgpu_tokenize_files, on the plain and the chunked path."""
+    from gtars_b200 import synth
+    u = synth.make_universe(60_000)
+    q = synth.make_query_files(u, 12, 3000, unknown_frac_ppm=2000)
+    offs = u["chrom_offsets"].numpy().astype(np.uint64)
+    s, e, v = (u[k].numpy().view(np.uint32) for k in ("g_start", "g_end", "g_val"))
+    g, o = _both(ctx, "bits", offs, s, e, v)
+    qc, qs, qe = (q[k].numpy().view(np.uint32) for k in ("chr", "start", "end"))
+    fo = q["file_offsets"].numpy().astype(np.uint64)
+    # runs: boundaries where the chromosome changes or a file starts
+    brk = np.flatnonzero(np.diff(qc.astype(np.int64)) != 0) + 1
+    starts = np.unique(np.concatenate([[0], brk, fo[:-1].astype(np.int64)]))
+    run_offsets = np.concatenate([starts, [len(qc)]]).astype(np.uint64)
+    run_chr = qc[starts]
+    want = o.tokenize_files(fo, qc, qs, qe, u["unk_id"])
+    for chunk in (None, "4096"):
+        if chunk:
+            monkeypatch.setenv("GTGPU_PIPE_CHUNK", chunk)
+        got = g.tokenize_files_runs(fo, run_offsets, run_chr, qs, qe, u["unk_id"])
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    from gtars_b200.ffi import GtarsGpuError
+    with pytest.raises(GtarsGpuError):
+        g.tokenize_files_runs(fo, run_offsets[:-1], run_chr[:-1], qs, qe, u["unk_id"])  # runs do not cover the queries
