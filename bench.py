@@ -249,6 +249,11 @@ def main():
                        d_total.data_ptr())
 
     with torch.cuda.stream(stream):
+        step()
+        stream.synchronize()
+        if int(d_total.item()) > cap:  # multi-hit universes (the nested variant): size the id buffer exactly and redo
+            cap = int(d_total.item())
+            d_ids = torch.empty(cap, dtype=torch.int32, device=dev)
         for _ in range(max(args.warmup, 3)):
             step()
         stream.synchronize()

@@ -162,7 +162,10 @@ enum ScratchRole {
 #ifndef GT_FUSED_MINBLOCKS
 #define GT_FUSED_MINBLOCKS 4
 #endif
-constexpr int FUSED_BLOCK = 256;             // 8 warps per tile
+#ifndef GT_FUSED_BLOCK
+#define GT_FUSED_BLOCK 256
+#endif
+constexpr int FUSED_BLOCK = GT_FUSED_BLOCK;  // threads (8 warps) per tile
 constexpr int FUSED_ROWS = GT_FUSED_ROWS;    // queries per thread per tile (striped inside each warp)
 constexpr int FUSED_TILE = FUSED_BLOCK * FUSED_ROWS;
 constexpr int CHROM_CACHE = 256;             // per-chromosome table entries staged in shared memory
