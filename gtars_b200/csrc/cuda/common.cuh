@@ -61,7 +61,12 @@ struct ChromMeta {    // 32 bytes
 // in one die's half of the L2.  Windows with more than two candidates or a non-contiguous candidate run,
 // chromosomes with several AIList components or with start > end intervals, wider or degenerate queries all fall
 // back to the LUT + walk path below, so results never depend on the table.
+// Window word encodings:  0 = empty;  (first << 2) | n, n in {1,2} = direct run;  BT_POOL_FLAG | (offset << 3) | n,
+// n in 1..BT_POOL_MAX = candidate list bt_pool[offset .. offset+n) of entry indices, stored in the backend's emission
+// order (covers nested intervals and multi-component AIList chromosomes);  BT_OVERFLOW = more candidates than that.
 #define BT_OVERFLOW 0xFFFFFFFFu
+#define BT_POOL_FLAG 0x80000000u
+#define BT_POOL_MAX 7u
 #define BT_GENERIC_CHROM 0x80000000u  // in ChromBT.n_bins: this chromosome always takes the generic path
 
 struct ChromBT {         // 8 bytes
@@ -72,6 +77,7 @@ struct ChromBT {         // 8 bytes
 struct IndexView {
     const ChromBT* chrom_bt;
     const uint32_t* bt_lut;
+    const uint32_t* bt_pool;
     const uint4* bt_ent;
     uint32_t bt_shift;
     const ChromMeta* chroms;
@@ -143,7 +149,7 @@ struct gtgpu_index {
     gtgpu::IndexView view{};
     std::vector<void*> allocs;
     uint64_t n_intervals = 0, n_segments = 0, device_bytes = 0, max_components = 0;
-    uint64_t bt_bins = 0, bt_overflow_bins = 0;
+    uint64_t bt_bins = 0, bt_overflow_bins = 0, bt_pool_windows = 0;
     bool l2_window_set = false;
 };
 

@@ -218,23 +218,23 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
 
     // ---- 3b. bin table (fast path of find/tokenize; see common.cuh) ------------------------------------------
     std::vector<ChromBT> chrom_bt(n_chroms);
-    std::vector<uint32_t> bt_lut;  // per window: (first entry << 2) | n, 0 = empty, BT_OVERFLOW = generic path
-    std::vector<uint4> bt_ent;     // {start, end, val, 0} per interval, segment order (padded by two)
+    std::vector<uint32_t> bt_lut;   // per window: direct run, pool list or overflow (encodings in common.cuh)
+    std::vector<uint32_t> bt_pool;  // candidate lists (entry indices, in emission order) of the pool windows
+    std::vector<uint4> bt_ent;      // {start, end, val, 0} per interval, segment order (padded by two)
     uint32_t bt_shift = 0;
-    uint64_t bt_overflow = 0;
+    uint64_t bt_overflow = 0, bt_pool_windows = 0;
     {
         std::vector<uint64_t> cover_end(n_chroms, 0);  // exclusive end of the positions the chromosome's intervals touch
-        std::vector<char> eligible(n_chroms, 0);
         for (uint32_t c = 0; c < n_chroms; ++c) {
-            if (chroms[c].seg_end - chroms[c].seg_begin != 1) continue;
-            const SegMeta& m = seg_meta[chroms[c].seg_begin];
-            bool ok = true;
+            bool ok = chroms[c].seg_end > chroms[c].seg_begin;
             uint64_t ce = 0;
-            for (uint32_t i = m.off; i < m.off + m.len; ++i) {
-                if (h_starts[i] > h_ends[i]) { ok = false; break; }
-                ce = std::max<uint64_t>(ce, std::max<uint64_t>(h_ends[i], (uint64_t)h_starts[i] + 1));
+            for (uint32_t si = chroms[c].seg_begin; ok && si < chroms[c].seg_end; ++si) {
+                const SegMeta& m = seg_meta[si];
+                for (uint32_t i = m.off; i < m.off + m.len; ++i) {
+                    if (h_starts[i] > h_ends[i]) { ok = false; break; }  // start > end intervals: generic path only
+                    ce = std::max<uint64_t>(ce, std::max<uint64_t>(h_ends[i], (uint64_t)h_starts[i] + 1));
+                }
             }
-            eligible[c] = ok;
             cover_end[c] = ok ? ce : 0;
         }
         auto total_bins = [&](uint32_t sh) {
@@ -251,14 +251,15 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
         bt_budget = std::min(bt_budget, bt_cap);
         while (bt_shift < 31 && total_bins(bt_shift) > bt_budget) ++bt_shift;
         if (const char* env = getenv("GTGPU_BT_SHIFT")) bt_shift = (uint32_t)std::min(31, std::max(0, atoi(env)));
-        // A table only pays off while most bins hold at most two candidates: skip it for dense databases.
-        bool enabled = bt_cap > 0 && total_bins(bt_shift) <= (64ull << 20) && total <= total_bins(bt_shift);
-        uint64_t pos = 1;  // record 0 is an always-empty sentinel: unknown chromosomes and out-of-range bins read it
+        // A table only pays off while most windows hold a few candidates: skip it for dense databases.
+        bool enabled = bt_cap > 0 && total_bins(bt_shift) <= (64ull << 20) && total <= total_bins(bt_shift) &&
+                       total < (1ull << 29);
+        uint64_t pos = 1;  // word 0 is an always-empty sentinel: unknown chromosomes and out-of-range bins read it
         for (uint32_t c = 0; c < n_chroms; ++c) {
             chrom_bt[c].off = (uint32_t)pos;
             if (chroms[c].seg_end == chroms[c].seg_begin) {
                 chrom_bt[c].n_bins = 0;  // absent chromosome: nothing can hit
-            } else if (!eligible[c] || !enabled) {
+            } else if (!cover_end[c] || !enabled) {
                 chrom_bt[c].n_bins = BT_GENERIC_CHROM;
                 chrom_bt[c].off = 0;
             } else {
@@ -267,42 +268,66 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
                 pos += nb;
             }
         }
-        // Candidates of a window are a run [first, first + n) of the start-sorted segment whenever no interval is
-        // nested around a non-candidate; windows with n > 2 or a broken run go to the generic path.
-        bt_lut.assign(pos, 0);
-        std::vector<uint8_t> cnt(pos, 0);
+        // Pass 1: per window, how many intervals touch it and the index range they span.
+        std::vector<uint32_t> w_min(pos, 0xFFFFFFFFu), w_max(pos, 0);
+        std::vector<uint8_t> w_cnt(pos, 0);
+        auto for_each_window = [&](uint32_t c, uint32_t i, auto&& fn) {
+            const uint64_t last_pos = std::max<uint64_t>(h_ends[i], (uint64_t)h_starts[i] + 1) - 1;
+            // window b serves queries that START in bin b and end before bin b+2: it lists what touches [b, b+2)
+            uint64_t b0 = h_starts[i] >> bt_shift, b1 = last_pos >> bt_shift;
+            if (b0 > 0) --b0;
+            for (uint64_t b = b0; b <= b1; ++b) fn(chrom_bt[c].off + b);
+        };
         for (uint32_t c = 0; c < n_chroms; ++c) {
             if (chrom_bt[c].n_bins == 0 || chrom_bt[c].n_bins == BT_GENERIC_CHROM) continue;
-            const SegMeta& m = seg_meta[chroms[c].seg_begin];
-            for (uint32_t i = m.off; i < m.off + m.len; ++i) {
-                uint64_t last_pos = std::max<uint64_t>(h_ends[i], (uint64_t)h_starts[i] + 1) - 1;
-                // bin b serves queries that START in b and end before bin b+2: it lists what touches that window
-                uint64_t b0 = h_starts[i] >> bt_shift, b1 = last_pos >> bt_shift;
-                if (b0 > 0) --b0;
-                for (uint64_t b = b0; b <= b1; ++b) {
-                    const uint64_t k = chrom_bt[c].off + b;
-                    if (cnt[k] == 0) {
-                        bt_lut[k] = i;
-                        cnt[k] = 1;
-                    } else if (cnt[k] < 3 && bt_lut[k] + cnt[k] == i) {
-                        cnt[k]++;
-                    } else {
-                        cnt[k] = 255;
-                    }
+            for (uint32_t si = chroms[c].seg_begin; si < chroms[c].seg_end; ++si)
+                for (uint32_t i = seg_meta[si].off; i < seg_meta[si].off + seg_meta[si].len; ++i)
+                    for_each_window(c, i, [&](uint64_t k) {
+                        w_min[k] = std::min(w_min[k], i);
+                        w_max[k] = std::max(w_max[k], i);
+                        if (w_cnt[k] < 255) w_cnt[k]++;
+                    });
+        }
+        // Classify: a contiguous run of <= 2 intervals on a single-segment chromosome is addressed directly; up to
+        // BT_POOL_MAX candidates of any shape (nested intervals, several AIList components) go to a pool list.
+        bt_lut.assign(pos, 0);
+        std::vector<uint8_t> fill(pos, 0);
+        uint64_t pool_size = 0;
+        for (uint32_t c = 0; c < n_chroms; ++c) {
+            if (chrom_bt[c].n_bins == 0 || chrom_bt[c].n_bins == BT_GENERIC_CHROM) continue;
+            const bool single = chroms[c].seg_end - chroms[c].seg_begin == 1;
+            for (uint64_t k = chrom_bt[c].off; k < (uint64_t)chrom_bt[c].off + chrom_bt[c].n_bins; ++k) {
+                const uint32_t n = w_cnt[k];
+                if (n == 0) continue;
+                if (single && n <= 2 && w_max[k] - w_min[k] + 1 == n) {
+                    bt_lut[k] = (w_min[k] << 2) | n;
+                } else if (n <= BT_POOL_MAX && pool_size + n < (1ull << 28) - 8) {
+                    bt_lut[k] = BT_POOL_FLAG | ((uint32_t)pool_size << 3) | n;
+                    pool_size += n;
+                    ++bt_pool_windows;
+                } else {
+                    bt_lut[k] = BT_OVERFLOW;
+                    ++bt_overflow;
                 }
             }
         }
-        for (uint64_t k = 0; k < pos; ++k) {
-            if (cnt[k] > 2) {
-                bt_lut[k] = BT_OVERFLOW;
-                ++bt_overflow;
-            } else {
-                bt_lut[k] = cnt[k] ? (bt_lut[k] << 2) | cnt[k] : 0;
+        // Pass 2: fill the pool lists in emission order — Bits: ascending sorted position; AIList: component-major,
+        // descending position inside a component (ailist.rs:153-178, 238-263).
+        bt_pool.assign(pool_size + 1, 0);
+        for (uint32_t c = 0; c < n_chroms; ++c) {
+            if (chrom_bt[c].n_bins == 0 || chrom_bt[c].n_bins == BT_GENERIC_CHROM) continue;
+            for (uint32_t si = chroms[c].seg_begin; si < chroms[c].seg_end; ++si) {
+                const SegMeta& m = seg_meta[si];
+                for (uint32_t t = 0; t < m.len; ++t) {
+                    const uint32_t i = kind == GTGPU_KIND_AILIST ? m.off + m.len - 1 - t : m.off + t;
+                    for_each_window(c, i, [&](uint64_t k) {
+                        const uint32_t w = bt_lut[k];
+                        if (w == BT_OVERFLOW || !(w & BT_POOL_FLAG)) return;
+                        bt_pool[((w & ~BT_POOL_FLAG) >> 3) + fill[k]++] = i;
+                    });
+                }
             }
         }
-        if (total >= (1ull << 30))  // index + count must fit one word
-            for (auto& cb : chrom_bt)
-                if (cb.n_bins != 0) { cb.n_bins = BT_GENERIC_CHROM; cb.off = 0; }
         bt_ent.resize(total + 2);
         for (uint64_t i = 0; i < total; ++i) bt_ent[i] = make_uint4(h_starts[i], h_ends[i], h_vals[i], 0);
         bt_ent[total] = bt_ent[total + 1] = make_uint4(0xFFFFFFFFu, 0, 0, 0);
@@ -320,6 +345,8 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
     auto up = [&](auto& vec, auto** dst) { if (st == GTGPU_OK) st = upload(ix, vec, dst); };
     up(chrom_bt, &v.chrom_bt);
     up(bt_lut, &v.bt_lut);
+    up(bt_pool, &v.bt_pool);
+    ix->bt_pool_windows = bt_pool_windows;
     up(bt_ent, &v.bt_ent);
     v.bt_shift = bt_shift;
     ix->bt_bins = bt_lut.size();
@@ -367,6 +394,6 @@ extern "C" int32_t gtgpu_index_info(const gtgpu_index* ix, uint64_t info[10]) {
     info[6] = ix->bt_bins;
     info[7] = ix->bt_overflow_bins;
     info[8] = ix->view.bt_shift;
-    info[9] = 0;
+    info[9] = ix->bt_pool_windows;
     return GTGPU_OK;
 }

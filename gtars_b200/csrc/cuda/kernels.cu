@@ -239,12 +239,44 @@ __global__ void fill_from_base_kernel(uint64_t count, uint64_t* __restrict__ out
 __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 
+// Pool window of a query (if it has one): the candidate list of the window its start falls in.
+__device__ __forceinline__ bool pool_window(const IndexView& ix, uint32_t c, uint32_t s, uint32_t e, uint32_t& off, uint32_t& n) {
+    if (c >= ix.n_chroms || s >= e) return false;
+    const uint2 cb = __ldg(reinterpret_cast<const uint2*>(ix.chrom_bt + c));
+    const uint32_t b1 = s >> ix.bt_shift, b2 = (e - 1) >> ix.bt_shift;
+    if (cb.y == BT_GENERIC_CHROM || b2 - b1 > 1 || b1 >= cb.y) return false;
+    const uint32_t w = __ldg(ix.bt_lut + cb.x + b1);
+    if (w == BT_OVERFLOW || !(w & BT_POOL_FLAG)) return false;
+    n = w & 7u;
+    off = (w & ~BT_POOL_FLAG) >> 3;
+    return true;
+}
+
+__device__ __forceinline__ bool hit_bp(uint32_t cs, uint32_t ce, uint32_t s, uint32_t e, int32_t min_bp) {
+    bool h = cs < e && ce > s;
+    if (min_bp > 1) h = h && ((int64_t)min(e, ce) - (int64_t)max(s, cs) >= (int64_t)min_bp);
+    return h;
+}
+
 // Emits every hit of one query through the generic LUT + walk path, in reference order; returns the count.
 __device__ __noinline__ uint32_t emit_query_walk(const IndexView& ix, uint32_t c, uint32_t s, uint32_t e, int32_t min_bp,
                                                  uint32_t* __restrict__ out_ids, uint64_t pos, uint64_t capacity) {
     if (c >= ix.n_chroms) return 0;
-    const uint2 sr = __ldg(reinterpret_cast<const uint2*>(ix.chroms + c));
     uint32_t written = 0;
+    {
+        uint32_t off, n;
+        if (pool_window(ix, c, s, e, off, n)) {  // the list is already in emission order
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint4 E = ldg128(ix.bt_ent + __ldg(ix.bt_pool + off + j));
+                if (hit_bp(E.x, E.y, s, e, min_bp)) {
+                    if (pos + written < capacity) out_ids[pos + written] = E.z;
+                    ++written;
+                }
+            }
+            return written;
+        }
+    }
+    const uint2 sr = __ldg(reinterpret_cast<const uint2*>(ix.chroms + c));
     for (uint32_t si = sr.x; si < sr.y; ++si) {
         SegMeta m = load_seg(ix, si);
         uint32_t l, u;
@@ -267,8 +299,18 @@ __device__ __noinline__ uint32_t emit_query_walk(const IndexView& ix, uint32_t c
     return written;
 }
 
+// Queries the direct window path cannot serve: pool list when the window has one, else the LUT + walk path.
 __device__ __noinline__ uint32_t count_query_walk_noinline(const IndexView& ix, uint32_t c, uint32_t s, uint32_t e,
                                                            int32_t min_bp) {
+    uint32_t off, n;
+    if (pool_window(ix, c, s, e, off, n)) {
+        uint32_t cnt = 0;
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint4 E = ldg128(ix.bt_ent + __ldg(ix.bt_pool + off + j));
+            cnt += hit_bp(E.x, E.y, s, e, min_bp);
+        }
+        return cnt;
+    }
     return count_query_walk(ix, c, s, e, min_bp);
 }
 
@@ -490,7 +532,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 uint4 E0[ROWS], E1[ROWS];
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k) {
-                    if (w[k] == BT_OVERFLOW) {
+                    if (w[k] & BT_POOL_FLAG) {  // pool list or overflow: resolved by the slow-path functions
                         cur.slow |= 1u << k;
                         w[k] = 0;
                     }

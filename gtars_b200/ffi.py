@@ -214,7 +214,7 @@ class Index:
         a = (C.c_uint64 * 10)()
         check(lib().gtgpu_index_info(self._h, a))
         return dict(n_intervals=a[0], n_segments=a[1], device_bytes=a[2], lut_shift=a[3], max_components=a[4],
-                    proper=bool(a[5]), bt_bins=a[6], bt_overflow_bins=a[7], bt_shift=a[8])
+                    proper=bool(a[5]), bt_bins=a[6], bt_overflow_bins=a[7], bt_shift=a[8], bt_pool_windows=a[9])
 
     # ---- host-buffer entry points -------------------------------------------------------------------------------
     def count(self, chr, start, end, min_overlap=0) -> np.ndarray:

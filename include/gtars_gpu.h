@@ -88,7 +88,8 @@ int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_chroms, const
 int32_t gtgpu_index_free(gtgpu_index* index);
 /* info[0]=n_intervals, [1]=n_segments (chromosome×AIList component), [2]=device bytes, [3]=lut shift,
  * [4]=max components on one chromosome, [5]=1 if every interval has start<=end, [6]=bin-table bins,
- * [7]=bin-table bins with more than two candidates (served by the generic path), [8]=bin-table shift, [9]=0 */
+ * [7]=bin-table windows served by the generic walk (too many candidates), [8]=bin-table shift,
+ * [9]=bin-table windows with a pooled candidate list (nested intervals / several AIList components) */
 int32_t gtgpu_index_info(const gtgpu_index* index, uint64_t info[10]);
 
 /* ---- batch queries, host buffers ------------------------------------------------------------------------ */

@@ -360,3 +360,29 @@ def test_tokenize_files_runs_variant(ctx, monkeypatch):
     from gtars_b200.ffi import GtarsGpuError
     with pytest.raises(GtarsGpuError):
         g.tokenize_files_runs(fo, run_offsets[:-1], run_chr[:-1], qs, qe, u["unk_id"])  # runs do not cover the queries
+
+
+@pytest.mark.parametrize("kind", ["bits", "ailist"])
+def test_pooled_windows_differential(ctx, kind):
+    """Moderately overlapping / nested universe and narrow queries: most windows hold 3-7 candidates, so the pooled
+    candidate lists of the window table (not the direct runs, not the generic walk) resolve them."""
+    rng = np.random.default_rng(4242)
+    n = 6000
+    chr_ = np.sort(rng.integers(0, 2, n))
+    offs = np.concatenate([[0], np.cumsum(np.bincount(chr_, minlength=2))]).astype(np.uint64)
+    s = rng.integers(0, 1_500_000, n).astype(np.uint32)
+    w = np.where(rng.random(n) < 0.1, rng.integers(3000, 20000, n), rng.integers(50, 1500, n))
+    e = (s + w).astype(np.uint32)
+    v = rng.permutation(n).astype(np.uint32)
+    g, o = _both(ctx, kind, offs, s, e, v)
+    info = g.info()
+    assert info["bt_pool_windows"] > 1000
+    nq = 20000
+    qc = rng.integers(0, 2, nq).astype(np.uint32)
+    qs = rng.integers(0, 1_520_000, nq).astype(np.uint32)
+    qe = (qs + rng.integers(1, 1 << max(int(info["bt_shift"]), 1), nq)).astype(np.uint32)
+    for m in (0, 2, 30):
+        _assert_same_find(g, o, qc, qs, qe, m)
+    fo = np.array([0, 5000, 5000, 12000, nq], dtype=np.uint64)
+    a, b = g.tokenize_files(fo, qc, qs, qe, n), o.tokenize_files(fo, qc, qs, qe, n)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])

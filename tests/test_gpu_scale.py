@@ -74,10 +74,9 @@ def test_c2_nested_universe_vs_oracle(ctx):
     for kind, okind in ((ffi.KIND_BITS, orc.BITS), (ffi.KIND_AILIST, orc.AILIST)):
         u, ix, arrays = _universe(ctx, kind, n=300_000, nested=0.01)
         info = ix.info()
-        if kind == ffi.KIND_BITS:
-            assert info["bt_overflow_bins"] > 0      # wide intervals break the candidate runs of the windows they span
-        else:
-            assert info["max_components"] >= 2       # multi-component chromosomes take the generic path
+        assert info["bt_pool_windows"] > 0           # wide intervals break the candidate runs: pooled lists
+        if kind == ffi.KIND_AILIST:
+            assert info["max_components"] >= 2       # several AIList components, still served by the window table
         q = synth.make_query_files(u, 30, 20_000, unknown_frac_ppm=500)
         qc, qs, qe = (_np(q[k]) for k in ("chr", "start", "end"))
         fo = q["file_offsets"].numpy().astype(np.uint64)
