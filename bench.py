@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--universe", type=int, default=1_000_000)
     ap.add_argument("--kind", default="bits", choices=["bits", "ailist"])
     ap.add_argument("--nested", type=float, default=0.0, help="fraction of wide intervals (C2n variant)")
+    ap.add_argument("--width-scale", type=int, default=1, help="multiply the 200-600 bp query widths (wide-query variant)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -55,7 +56,7 @@ def workload_config(args, world):
     return {
         "workload": f"C2: tokenize {args.files} files x {args.per_file} regions per GPU vs {args.universe}-region hg38 universe",
         "files_per_gpu": args.files, "regions_per_file": args.per_file, "universe_regions": args.universe,
-        "backend": args.kind, "nested_frac": args.nested, "sharding": f"files x{world} (universe replicated)",
+        "backend": args.kind, "nested_frac": args.nested, "query_width_scale": args.width_scale, "sharding": f"files x{world} (universe replicated)",
         "l2_policy": "inputs (12 B/query x 1e9) are far larger than the 126 MB L2; no flush needed",
     }
 
@@ -129,7 +130,7 @@ def cpu_oracle_rate(args, threads, seconds, universe=None):
     done_q, spent, first = 0, 0.0, 0
     while spent < seconds and first < args.files:
         nf = min(batch, args.files - first)
-        q = synth.make_query_files(u, nf, args.per_file, first_file=first)
+        q = synth.make_query_files(u, nf, args.per_file, first_file=first, width_scale=args.width_scale)
         qc, qs, qe = (q[k].numpy().view(np.uint32) for k in ("chr", "start", "end"))
         fo = q["file_offsets"].numpy().astype(np.uint64)
         t0 = time.perf_counter()
@@ -154,7 +155,7 @@ def run_reference(args, rank, world):
     s, e, v = (u[k].numpy().view(np.uint32) for k in ("g_start", "g_end", "g_val"))
     ix = orc.Index(kind, offs, s, e, v)
     sample_files = min(args.files, 8 * threads)
-    q = synth.make_query_files(u, sample_files, args.per_file)
+    q = synth.make_query_files(u, sample_files, args.per_file, width_scale=args.width_scale)
     qc, qs, qe = (q[k].numpy().view(np.uint32) for k in ("chr", "start", "end"))
     fo = q["file_offsets"].numpy().astype(np.uint64)
     for _ in range(max(args.warmup, 1)):
@@ -232,7 +233,7 @@ def main():
     chunk = max(1, min(n_files, (32 << 20) // per_file))
     for f0 in range(0, n_files, chunk):
         k = min(chunk, n_files - f0)
-        q = synth.make_query_files(u, k, per_file, device=dev, first_file=first_file + f0)
+        q = synth.make_query_files(u, k, per_file, device=dev, first_file=first_file + f0, width_scale=args.width_scale)
         sl = slice(f0 * per_file, (f0 + k) * per_file)
         d_chr[sl], d_start[sl], d_end[sl] = q["chr"], q["start"], q["end"]
         del q

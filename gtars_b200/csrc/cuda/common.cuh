@@ -68,6 +68,9 @@ struct ChromMeta {    // 32 bytes
 #define BT_POOL_FLAG 0x80000000u
 #define BT_POOL_MAX 7u
 #define BT_GENERIC_CHROM 0x80000000u  // in ChromBT.n_bins: this chromosome always takes the generic path
+#define BT_MULTI_COMP 0x40000000u     // in ChromBT.n_bins: several AIList components (lists of different windows cannot be merged)
+#define BT_NBINS_MASK 0x3FFFFFFFu
+#define BT_MAX_WINDOWS 8u             // a query may span this many two-bin windows before it goes to the generic walk
 
 struct ChromBT {         // 8 bytes
     uint32_t off;        // first bin record of this chromosome

@@ -264,6 +264,7 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
                 chrom_bt[c].off = 0;
             } else {
                 uint64_t nb = ((cover_end[c] - 1) >> bt_shift) + 1;
+                if (nb >= BT_NBINS_MASK) return fail(GTGPU_ERR_UNSUPPORTED, "index_build: too many bins on one chromosome");
                 chrom_bt[c].n_bins = (uint32_t)nb;
                 pos += nb;
             }
@@ -328,6 +329,9 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
                 }
             }
         }
+        for (uint32_t c = 0; c < n_chroms; ++c)
+            if (chrom_bt[c].n_bins != 0 && chrom_bt[c].n_bins != BT_GENERIC_CHROM && chroms[c].seg_end - chroms[c].seg_begin > 1)
+                chrom_bt[c].n_bins |= BT_MULTI_COMP;
         bt_ent.resize(total + 2);
         for (uint64_t i = 0; i < total; ++i) bt_ent[i] = make_uint4(h_starts[i], h_ends[i], h_vals[i], 0);
         bt_ent[total] = bt_ent[total + 1] = make_uint4(0xFFFFFFFFu, 0, 0, 0);

@@ -239,23 +239,55 @@ __global__ void fill_from_base_kernel(uint64_t count, uint64_t* __restrict__ out
 __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 
-// Pool window of a query (if it has one): the candidate list of the window its start falls in.
-__device__ __forceinline__ bool pool_window(const IndexView& ix, uint32_t c, uint32_t s, uint32_t e, uint32_t& off, uint32_t& n) {
-    if (c >= ix.n_chroms || s >= e) return false;
-    const uint2 cb = __ldg(reinterpret_cast<const uint2*>(ix.chrom_bt + c));
-    const uint32_t b1 = s >> ix.bt_shift, b2 = (e - 1) >> ix.bt_shift;
-    if (cb.y == BT_GENERIC_CHROM || b2 - b1 > 1 || b1 >= cb.y) return false;
-    const uint32_t w = __ldg(ix.bt_lut + cb.x + b1);
-    if (w == BT_OVERFLOW || !(w & BT_POOL_FLAG)) return false;
-    n = w & 7u;
-    off = (w & ~BT_POOL_FLAG) >> 3;
-    return true;
-}
-
 __device__ __forceinline__ bool hit_bp(uint32_t cs, uint32_t ce, uint32_t s, uint32_t e, int32_t min_bp) {
     bool h = cs < e && ce > s;
     if (min_bp > 1) h = h && ((int64_t)min(e, ce) - (int64_t)max(s, cs) >= (int64_t)min_bp);
     return h;
+}
+
+// Resolves one query through the window table when the direct path of the fused kernel could not: pooled candidate
+// lists, and queries that span several two-bin windows (up to BT_MAX_WINDOWS).  Windows are visited in emission order
+// (ascending for Bits, descending for AIList); an interval that touches several windows is taken from the lowest one
+// (it starts before every later window).  Returns false when the table cannot serve the query (no table on this
+// chromosome, degenerate or very wide query, an overflow window, several AIList components across windows): the caller
+// then falls back to the LUT + walk path.  With EMIT the hits' vals are written from `pos` on; `count` gets the hits.
+template <bool EMIT>
+__device__ __forceinline__ bool window_walk(const IndexView& ix, uint32_t c, uint32_t s, uint32_t e, int32_t min_bp,
+                                            uint32_t* __restrict__ out_ids, uint64_t pos, uint64_t capacity, uint32_t& count) {
+    count = 0;
+    if (c >= ix.n_chroms || s >= e) return false;
+    const uint2 cb = __ldg(reinterpret_cast<const uint2*>(ix.chrom_bt + c));
+    if (cb.y == BT_GENERIC_CHROM) return false;
+    const uint32_t nb = cb.y & BT_NBINS_MASK, sh = ix.bt_shift;
+    const uint32_t b1 = s >> sh, b2 = (e - 1) >> sh;
+    const uint32_t nwin = (b2 - b1) / 2 + 1;
+    if (nwin > BT_MAX_WINDOWS || (nwin > 1 && (cb.y & BT_MULTI_COMP))) return false;
+    const bool desc = ix.descending != 0;
+    // pass 1: no window may be an overflow window
+    for (uint32_t j = 0; j < nwin; ++j) {
+        const uint32_t b = b1 + 2 * j;
+        if (b < nb && __ldg(ix.bt_lut + cb.x + b) == BT_OVERFLOW) return false;
+    }
+    for (uint32_t jj = 0; jj < nwin; ++jj) {
+        const uint32_t j = desc ? nwin - 1 - jj : jj;
+        const uint32_t b = b1 + 2 * j;
+        if (b >= nb) continue;
+        const uint32_t w = __ldg(ix.bt_lut + cb.x + b);
+        if (w == 0) continue;
+        const uint32_t wstart = j == 0 ? 0u : b << sh;  // later windows skip what an earlier window already listed
+        const bool pool = (w & BT_POOL_FLAG) != 0;
+        const uint32_t n = pool ? (w & 7u) : (w & 3u);
+        const uint32_t first = pool ? (w & ~BT_POOL_FLAG) >> 3 : w >> 2;
+        for (uint32_t t = 0; t < n; ++t) {
+            // pool lists are stored in emission order; direct runs ascend, so AIList reads them backwards
+            const uint32_t idx = pool ? __ldg(ix.bt_pool + first + t) : (desc ? first + n - 1 - t : first + t);
+            const uint4 E = ldg128(ix.bt_ent + idx);
+            if (E.x < wstart || !hit_bp(E.x, E.y, s, e, min_bp)) continue;
+            if (EMIT && pos + count < capacity) out_ids[pos + count] = E.z;
+            ++count;
+        }
+    }
+    return true;
 }
 
 // Emits every hit of one query through the generic LUT + walk path, in reference order; returns the count.
@@ -263,19 +295,8 @@ __device__ __noinline__ uint32_t emit_query_walk(const IndexView& ix, uint32_t c
                                                  uint32_t* __restrict__ out_ids, uint64_t pos, uint64_t capacity) {
     if (c >= ix.n_chroms) return 0;
     uint32_t written = 0;
-    {
-        uint32_t off, n;
-        if (pool_window(ix, c, s, e, off, n)) {  // the list is already in emission order
-            for (uint32_t j = 0; j < n; ++j) {
-                const uint4 E = ldg128(ix.bt_ent + __ldg(ix.bt_pool + off + j));
-                if (hit_bp(E.x, E.y, s, e, min_bp)) {
-                    if (pos + written < capacity) out_ids[pos + written] = E.z;
-                    ++written;
-                }
-            }
-            return written;
-        }
-    }
+    if (window_walk<true>(ix, c, s, e, min_bp, out_ids, pos, capacity, written)) return written;
+    written = 0;
     const uint2 sr = __ldg(reinterpret_cast<const uint2*>(ix.chroms + c));
     for (uint32_t si = sr.x; si < sr.y; ++si) {
         SegMeta m = load_seg(ix, si);
@@ -302,15 +323,8 @@ __device__ __noinline__ uint32_t emit_query_walk(const IndexView& ix, uint32_t c
 // Queries the direct window path cannot serve: pool list when the window has one, else the LUT + walk path.
 __device__ __noinline__ uint32_t count_query_walk_noinline(const IndexView& ix, uint32_t c, uint32_t s, uint32_t e,
                                                            int32_t min_bp) {
-    uint32_t off, n;
-    if (pool_window(ix, c, s, e, off, n)) {
-        uint32_t cnt = 0;
-        for (uint32_t j = 0; j < n; ++j) {
-            const uint4 E = ldg128(ix.bt_ent + __ldg(ix.bt_pool + off + j));
-            cnt += hit_bp(E.x, E.y, s, e, min_bp);
-        }
-        return cnt;
-    }
+    uint32_t cnt;
+    if (window_walk<false>(ix, c, s, e, min_bp, nullptr, 0, 0, cnt)) return cnt;
     return count_query_walk(ix, c, s, e, min_bp);
 }
 
@@ -524,7 +538,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 else cb = c < nchr ? __ldg(reinterpret_cast<const uint2*>(ix.chrom_bt + c)) : make_uint2(0, 0);
                 const uint32_t b1 = s >> shift, b2 = (e - 1) >> shift;
                 if ((cb.y == BT_GENERIC_CHROM) | (s >= e) | (b2 - b1 > 1)) cur.slow |= 1u << k;
-                const uint32_t li = b1 < (cb.y & 0x7FFFFFFFu) ? cb.x + b1 : 0u;  // word 0 is the empty sentinel
+                const uint32_t li = b1 < (cb.y & BT_NBINS_MASK) ? cb.x + b1 : 0u;  // word 0 is the empty sentinel
                 w[k] = ldg32_keep(ix.bt_lut + li, keep);
             }
             uint32_t cnt[ROWS];

@@ -114,7 +114,7 @@ def _genome_pos(u: torch.Tensor, dev):
 
 
 def make_query_files(universe: dict, n_files: int, per_file: int, seed: int = SEED_QUERIES, device="cpu",
-                     first_file: int = 0, sort_files: bool = True, unknown_frac_ppm: int = 0) -> dict:
+                     first_file: int = 0, sort_files: bool = True, unknown_frac_ppm: int = 0, width_scale: int = 1) -> dict:
     """BED-file-like query batches: 80 % a universe peak jittered ±100 bp, 20 % uniform background, width
     200–600 bp; each file sorted by (chromosome name, start) like RegionSet::try_from.  Files
     [first_file, first_file + n_files) of the infinite stream, so ranks can shard by file."""
@@ -122,7 +122,7 @@ def make_query_files(universe: dict, n_files: int, per_file: int, seed: int = SE
     n = n_files * per_file
     idx = torch.arange(first_file * per_file, first_file * per_file + n, dtype=torch.int64, device=dev)
     kind = rand_u63(seed, 1, idx) % 5
-    width = 200 + rand_u63(seed, 2, idx) % 401
+    width = (200 + rand_u63(seed, 2, idx) % 401) * width_scale
     # peak-derived queries
     u_chr = universe["chr"].to(dev).long()
     u_start = universe["start"].to(dev).long()

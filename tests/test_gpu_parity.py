@@ -386,3 +386,27 @@ def test_pooled_windows_differential(ctx, kind):
     fo = np.array([0, 5000, 5000, 12000, nq], dtype=np.uint64)
     a, b = g.tokenize_files(fo, qc, qs, qe, n), o.tokenize_files(fo, qc, qs, qe, n)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("kind", ["bits", "ailist"])
+@pytest.mark.parametrize("nested", [0.0, 0.01])
+def test_wide_queries_multi_window(ctx, kind, nested):
+    """Queries wider than one bin walk several two-bin windows of the table (up to 8), beyond that the generic path;
+    hits must come out once, in the backend's order, whatever mix of direct / pooled / overflow windows they cross."""
+    from gtars_b200 import synth
+    u = synth.make_universe(200_000, nested_frac=nested)
+    offs = u["chrom_offsets"].numpy().astype(np.uint64)
+    s, e, v = (u[k].numpy().view(np.uint32) for k in ("g_start", "g_end", "g_val"))
+    g, o = _both(ctx, kind, offs, s, e, v)
+    sh = int(g.info()["bt_shift"])
+    rng = np.random.default_rng(99)
+    nq = 30_000
+    base = synth.make_query_files(u, 1, nq, sort_files=False, unknown_frac_ppm=1000)
+    qc, qs = base["chr"].numpy().view(np.uint32), base["start"].numpy().view(np.uint32)
+    width = np.where(rng.random(nq) < 0.9, rng.integers(1, 15 << sh, nq), rng.integers(15 << sh, 60 << sh, nq))
+    qe = (qs.astype(np.int64) + width).astype(np.uint32)
+    for m in (0, 3, 700):
+        _assert_same_find(g, o, qc, qs, qe, m)
+    fo = np.array([0, 10_000, nq], dtype=np.uint64)
+    a, b = g.tokenize_files(fo, qc, qs, qe, u["unk_id"]), o.tokenize_files(fo, qc, qs, qe, u["unk_id"])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
