@@ -221,6 +221,7 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
     std::vector<uint32_t> bt_lut;   // per window: direct run, pool list or overflow (encodings in common.cuh)
     std::vector<uint32_t> bt_pool;  // candidate lists (entry indices, in emission order) of the pool windows
     std::vector<uint4> bt_ent;      // {start, end, val, 0} per interval, segment order (padded by two)
+    std::vector<uint32_t> bt_rec;   // per window: the candidates inline, window-relative (fast path; common.cuh)
     uint32_t bt_shift = 0;
     uint64_t bt_overflow = 0, bt_pool_windows = 0;
     {
@@ -250,10 +251,12 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
         if (const char* env = getenv("GTGPU_BT_MAX_BINS")) bt_cap = strtoull(env, nullptr, 10);
         bt_budget = std::min(bt_budget, bt_cap);
         while (bt_shift < 31 && total_bins(bt_shift) > bt_budget) ++bt_shift;
+        // window records hold window-relative coordinates in 2 (bt_shift + 2) bits: sparse universes get narrower bins
+        if (bt_shift > BT_REC_MAX_SHIFT && total_bins(BT_REC_MAX_SHIFT) <= bt_cap) bt_shift = BT_REC_MAX_SHIFT;
         if (const char* env = getenv("GTGPU_BT_SHIFT")) bt_shift = (uint32_t)std::min(31, std::max(0, atoi(env)));
         // A table only pays off while most windows hold a few candidates: skip it for dense databases.
         bool enabled = bt_cap > 0 && total_bins(bt_shift) <= (64ull << 20) && total <= total_bins(bt_shift) &&
-                       total < (1ull << 29);
+                       total < (1ull << 29) && bt_shift <= BT_REC_MAX_SHIFT;
         uint64_t pos = 1;  // word 0 is an always-empty sentinel: unknown chromosomes and out-of-range bins read it
         for (uint32_t c = 0; c < n_chroms; ++c) {
             chrom_bt[c].off = (uint32_t)pos;
@@ -335,6 +338,36 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
         bt_ent.resize(total + 2);
         for (uint64_t i = 0; i < total; ++i) bt_ent[i] = make_uint4(h_starts[i], h_ends[i], h_vals[i], 0);
         bt_ent[total] = bt_ent[total + 1] = make_uint4(0xFFFFFFFFu, 0, 0, 0);
+        // Window records: the direct runs again, inline and window-relative (record 0 stays the empty sentinel).
+        bt_rec.assign(pos * BT_REC_WORDS, 0);
+        const uint32_t rel_bits = bt_shift + 2;
+        const uint64_t rel_max = 2ull << bt_shift;
+        auto rel = [&](uint32_t i, uint64_t base) {
+            const uint64_t s = h_starts[i] <= base ? 0 : std::min<uint64_t>(h_starts[i] - base, rel_max);
+            const uint64_t e = h_ends[i] <= base ? 0 : std::min<uint64_t>(h_ends[i] - base, rel_max);
+            return (uint32_t)(s | (e << rel_bits));
+        };
+        for (uint32_t c = 0; c < n_chroms; ++c) {
+            if (chrom_bt[c].n_bins == 0 || (chrom_bt[c].n_bins & BT_GENERIC_CHROM)) continue;
+            const uint64_t nb = chrom_bt[c].n_bins & BT_NBINS_MASK;
+            for (uint64_t b = 0; b < nb; ++b) {
+                const uint64_t k = chrom_bt[c].off + b, base = b << bt_shift;
+                const uint32_t w = bt_lut[k];
+                uint32_t* r = &bt_rec[k * BT_REC_WORDS];
+                if (w == 0) continue;
+                if (w & BT_POOL_FLAG) {  // pool list or overflow (BT_OVERFLOW has the flag bit too)
+                    r[0] = 3;
+                    continue;
+                }
+                const uint32_t first = w >> 2, cnt = w & 3;
+                r[0] = cnt | (rel(first, base) << 2);
+                r[1] = h_vals[first];
+                if (cnt == 2) {
+                    r[2] = rel(first + 1, base) << 2;
+                    r[3] = h_vals[first + 1];
+                }
+            }
+        }
     }
 
     // ---- 4. upload ---------------------------------------------------------------------------------------------
@@ -349,6 +382,7 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
     auto up = [&](auto& vec, auto** dst) { if (st == GTGPU_OK) st = upload(ix, vec, dst); };
     up(chrom_bt, &v.chrom_bt);
     up(bt_lut, &v.bt_lut);
+    up(bt_rec, &v.bt_rec);
     up(bt_pool, &v.bt_pool);
     ix->bt_pool_windows = bt_pool_windows;
     up(bt_ent, &v.bt_ent);
