@@ -394,7 +394,8 @@ __device__ __forceinline__ uint32_t ldg32_keep(const void* p, uint64_t policy) {
 }
 __device__ __forceinline__ uint4 ldg128_keep(const void* p, uint64_t policy) {
     uint4 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+    // one sector per lane and no reuse inside an SM: do not hold an L1 line for it (measured 7.44 -> 7.33 ms)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
     return v;
 }
@@ -419,7 +420,7 @@ __device__ unsigned long long g_phase_cycles[16];
 template <int ROWS>
 struct TileState {
     uint32_t tile;
-    uint32_t v0[ROWS];   // first hit's val per query (second one, when there is one, waits in s_v1)
+    uint32_t v0[ROWS];   // first hit's val per query (second one, when there is one, waits in s_aux)
     uint32_t cntpack;    // 2 bits per row: min(count, 3)
     uint32_t offpack;    // 8 bits per row: offset inside the warp slice, valid when the warp had no generic query
     uint32_t slow;       // bit k: query k goes through the generic LUT + walk path (count and emit); bit 31: warp-wide
@@ -449,10 +450,15 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
     constexpr uint32_t FULL = 0xFFFFFFFFu;
     constexpr uint32_t NO_TILE = 0xFFFFFFFFu;
     constexpr uint32_t WARP_SLOW = 1u << 31;
-    __shared__ __align__(128) uint32_t s_q[2][3][TILE];  // TMA-staged query rows (chr, start, end), double-buffered
-    __shared__ __align__(8) uint64_t s_bar[2];           // one mbarrier per staging buffer
-    __shared__ uint32_t s_v1[2][TILE];         // second hit's val (queries with two hits), by iteration parity
-    __shared__ uint32_t s_off[2][TILE];        // full offsets for warps that had a generic query, by iteration parity
+    // TMA-staged query rows (chr, start, end).  ONE buffer is enough: a tile's rows move to registers at the top of its
+    // resolve, and the next tile is only staged after barrier B2 of the same step.  Shared memory is deliberately kept
+    // small (32 KB per CTA): the unified L1 holds the in-flight gather lines, and a larger carve-out costs throughput.
+    __shared__ __align__(128) uint32_t s_q[3][TILE];
+    __shared__ __align__(8) uint64_t s_bar;
+    // Per-query side word, by iteration parity.  A warp on the packed path keeps the SECOND hit's val of its two-hit
+    // queries here; a warp that had a generic query keeps every query's full offset instead (its two-hit queries are
+    // then emitted by the generic walk too, so the two uses never meet in one warp).
+    __shared__ uint32_t s_aux[2][TILE];
     __shared__ uint2 s_chrom[CHROM_CACHE];
     __shared__ uint32_t s_wtot[2][WARPS];      // per-warp hit totals, double-buffered by iteration parity
     __shared__ uint64_t s_lb_sum[2][WARPS];    // look-back partial sums per 32-tile window
@@ -480,12 +486,12 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
 #endif
             staged = 1;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this buffer are done
-            mbar_expect_tx(&s_bar[buf], 3 * TILE * 4);
+            mbar_expect_tx(&s_bar, 3 * TILE * 4);
             const uint64_t q0 = (uint64_t)t * TILE;
             const uint64_t pol = policy_evict_first();
-            bulk_g2s(&s_q[buf][0][0], chr + q0, TILE * 4, &s_bar[buf], pol);
-            bulk_g2s(&s_q[buf][1][0], start + q0, TILE * 4, &s_bar[buf], pol);
-            bulk_g2s(&s_q[buf][2][0], end + q0, TILE * 4, &s_bar[buf], pol);
+            bulk_g2s(&s_q[0][0], chr + q0, TILE * 4, &s_bar, pol);
+            bulk_g2s(&s_q[1][0], start + q0, TILE * 4, &s_bar, pol);
+            bulk_g2s(&s_q[2][0], end + q0, TILE * 4, &s_bar, pol);
         }
         s_staged[buf] = staged;
     };
@@ -493,8 +499,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
     for (uint32_t i = tid; i < CHROM_CACHE; i += FUSED_BLOCK)
         s_chrom[i] = i < nchr ? __ldg(reinterpret_cast<const uint2*>(ix.chrom_bt + i)) : make_uint2(0, 0);
     if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         claim_and_stage(0);
     }
@@ -503,7 +508,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
     const uint64_t base = d_base ? *d_base : 0;
     uint64_t* status = ws.status;
     const uint32_t shift = ix.bt_shift;
-    uint32_t bar_phase = 0;  // bit b: parity to wait for on s_bar[b]
+    uint32_t bar_phase = 0;  // parity to wait for on s_bar
     const uint64_t keep = policy_evict_last();
 
     // One pipeline step: resolve `cur` (tile of this iteration), then look back + emit `prev` (tile of the last one).
@@ -535,13 +540,13 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             // ---- queries: ROWS coalesced rows per array, from the TMA-staged copy when there is one -----------------
             uint32_t qc[ROWS], qs[ROWS], qe[ROWS];
             if (s_staged[par]) {
-                mbar_wait(&s_bar[par], (bar_phase >> par) & 1);
-                bar_phase ^= 1u << par;
+                mbar_wait(&s_bar, bar_phase);
+                bar_phase ^= 1u;
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k) {
-                    qc[k] = s_q[par][0][wl + 32 * k];
-                    qs[k] = s_q[par][1][wl + 32 * k];
-                    qe[k] = s_q[par][2][wl + 32 * k];
+                    qc[k] = s_q[0][wl + 32 * k];
+                    qs[k] = s_q[1][wl + 32 * k];
+                    qe[k] = s_q[2][wl + 32 * k];
                 }
             } else {
 #pragma unroll
@@ -580,7 +585,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     const bool h1 = cand_hit<FILTER>(r1 & rel_mask, (r1 >> rel_bits) & rel_mask, s, e, min_bp);
                     cnt[k] = (uint32_t)h0 + (uint32_t)h1;
                     cur.v0[k] = h0 ? r[k].y : r[k].w;
-                    if (h0 & h1) s_v1[par][wl + 32 * k] = r[k].w;
+                    if (h0 & h1) s_aux[par][wl + 32 * k] = r[k].w;
                 }
             }
             PHASE_MARK(1);
@@ -618,7 +623,8 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                         uint32_t t = __shfl_up_sync(FULL, incl, d);
                         if (lane >= d) incl += t;
                     }
-                    s_off[par][wl + 32 * k] = warp_total + incl - cnt[k];
+                    s_aux[par][wl + 32 * k] = warp_total + incl - cnt[k];
+                    if (cnt[k] == 2) cur.slow |= 1u << k;  // its second val was just overwritten: emit through the walk
                     warp_total += __shfl_sync(FULL, incl, 31);
                     wide += cnt[k];
                     cur.cntpack |= min(cnt[k], 3u) << (2 * k);
@@ -631,7 +637,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             if (lane == 0) s_wtot[par][warp] = warp_total;
             PHASE_MARK(2);
         }
-        __syncthreads();  // B2: warp totals of `cur` visible; s_tile[par] / s_q[par] consumed by everyone
+        __syncthreads();  // B2: warp totals of `cur` visible; s_tile[par] / s_q consumed by everyone
         PHASE_MARK(3);
 
         if (tile != NO_TILE) {
@@ -749,7 +755,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     if (c == 0) continue;
                     uint32_t a = prev.v0[k], b = 0;
                     if (c == 2) {
-                        b = s_v1[ppar][wl + 32 * k];
+                        b = s_aux[ppar][wl + 32 * k];
                         if (DESC) { const uint32_t t = a; a = b; b = t; }
                     }
                     if (fits) {
@@ -763,7 +769,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             } else {
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k) {
-                    const uint32_t c = (prev.cntpack >> (2 * k)) & 3, o = s_off[ppar][wl + 32 * k];
+                    const uint32_t c = (prev.cntpack >> (2 * k)) & 3, o = s_aux[ppar][wl + 32 * k];
                     const uint64_t pos = warp_base + o;
                     const uint64_t q = tile_start + wl + 32 * k;
                     if (OFFS && q < n) out_offsets[q] = pos;
@@ -771,14 +777,8 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     if ((prev.slow >> k) & 1) {
                         // q < n here: an out-of-range query has count 0
                         emit_query_walk(ix, __ldg(chr + q), __ldg(start + q), __ldg(end + q), min_bp, out_ids, pos, capacity);
-                    } else {
-                        uint32_t a = prev.v0[k], b = 0;
-                        if (c == 2) {
-                            b = s_v1[ppar][wl + 32 * k];
-                            if (DESC) { const uint32_t t = a; a = b; b = t; }
-                        }
-                        if (pos < capacity) out_ids[pos] = a;
-                        if (c == 2 && pos + 1 < capacity) out_ids[pos + 1] = b;
+                    } else if (pos < capacity) {
+                        out_ids[pos] = prev.v0[k];  // exactly one hit: two-hit queries of this warp took the walk
                     }
                 }
             }
@@ -792,8 +792,8 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     __syncthreads();
 #pragma unroll
                     for (int k = 0; k < ROWS; ++k) {
-                        const uint32_t o = (prev.slow & WARP_SLOW) ? s_off[ppar][wl + 32 * k] : (prev.offpack >> (8 * k)) & 0xFF;
-                        s_off[ppar][wl + 32 * k] = prev.warp_excl + o;
+                        const uint32_t o = (prev.slow & WARP_SLOW) ? s_aux[ppar][wl + 32 * k] : (prev.offpack >> (8 * k)) & 0xFF;
+                        s_aux[ppar][wl + 32 * k] = prev.warp_excl + o;
                     }
                     __syncthreads();
                     const uint64_t limit = (prev.tile == n_tiles - 1) ? n + 1 : tile_start + TILE;
@@ -801,7 +801,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                         const uint64_t qi = file_offsets[f];
                         if (qi >= limit) break;
                         const uint32_t r = (uint32_t)(qi - tile_start);
-                        out_file_tok[f] = tile_base + (r < (uint32_t)TILE ? s_off[ppar][r] : prev.tile_agg);
+                        out_file_tok[f] = tile_base + (r < (uint32_t)TILE ? s_aux[ppar][r] : prev.tile_agg);
                     }
                     __syncthreads();
                 }
@@ -833,7 +833,13 @@ static cudaError_t launch_variant(int grid, cudaStream_t st, const IndexView& vi
                                   uint64_t cap, uint64_t* d_out_offsets, uint64_t* d_out_file_tok, FusedWorkspace ws,
                                   const uint64_t* d_base, uint64_t* d_total_out, uint32_t* d_errflag, int* blocks_per_sm) {
     auto kern = fused_find_kernel<FUSED_ROWS, DESC, FILTER, OFFS>;
-    if (blocks_per_sm) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, FUSED_BLOCK, 0);
+    if (blocks_per_sm) {
+        // 4 CTAs x 24 KB fit the 100 KB shared-memory configuration; the rest of the unified L1 serves the gathers
+        int carve = 40;
+        if (const char* env = getenv("GTGPU_CARVEOUT")) carve = atoi(env);  // tuning knob, percent
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, FUSED_BLOCK, 0);
+    }
     // bulk copies need 16-byte aligned sources; tile starts are multiples of 4 KiB, so only the bases matter
     const int tma_ok = ((reinterpret_cast<uintptr_t>(d_chr) | reinterpret_cast<uintptr_t>(d_start) |
                          reinterpret_cast<uintptr_t>(d_end)) & 15) == 0;
@@ -894,13 +900,13 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
             cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
-            size_t bytes = (size_t)ix->bt_bins * sizeof(uint32_t);
+            size_t bytes = (size_t)ix->bt_bins * sizeof(uint32_t) * BT_REC_WORDS;
             size_t win = std::min<size_t>(bytes, (size_t)std::max(max_window, 0));
             if (max_persist > 0 && win > 0) {
                 cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(win, (size_t)max_persist));
                 cudaStreamAttrValue attr;
                 memset(&attr, 0, sizeof attr);
-                attr.accessPolicyWindow.base_ptr = const_cast<uint32_t*>(ix->view.bt_lut);
+                attr.accessPolicyWindow.base_ptr = const_cast<uint32_t*>(ix->view.bt_rec);
                 attr.accessPolicyWindow.num_bytes = win;
                 attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float)max_persist / (float)win);
                 attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
