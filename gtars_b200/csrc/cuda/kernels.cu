@@ -361,6 +361,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
     asm volatile(
         "{\n"
@@ -401,7 +404,7 @@ __device__ __forceinline__ uint4 ldg128_keep(const void* p, uint64_t policy) {
 }
 
 #ifdef GT_PHASE_TIMING
-__device__ unsigned long long g_phase_cycles[16];
+__device__ unsigned long long g_phase_cycles[16 * 8];  // [warp][phase]
 #define PHASE_MARK(i)                                                            \
     do {                                                                         \
         long long _now = clock64();                                              \
@@ -464,6 +467,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
     __shared__ uint64_t s_lb_sum[2][WARPS];    // look-back partial sums per 32-tile window
     __shared__ uint32_t s_lb_p[2][WARPS];      // 1 when the window contains an inclusive prefix
     __shared__ uint32_t s_tile[2];             // tile index for this / the next iteration
+    __shared__ uint32_t s_mark;                // file-boundary mark of the tile being emitted
     __shared__ uint32_t s_staged[2];           // 1 when the tile's queries were requested through TMA
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -475,16 +479,14 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
     const bool chrom_cached = nchr < CHROM_CACHE;  // the last cached entry is then an "unknown chromosome" sentinel
 
     // One thread claims a tile and, when it is a full aligned tile, starts the bulk copies of its three query rows.
-    auto claim_and_stage = [&](uint32_t buf) {
-        const uint32_t t = atomicAdd(ws.counter, 1u);
+    // Hand the next tile to the CTA: its index and (when the rows are whole and aligned) the bulk copies of its query
+    // rows.  Every hand-over completes one phase of s_bar — with the copies' bytes or with a plain arrive — so the
+    // threads that wait on it at the top of the next step also see s_tile / s_staged (arrive releases, wait acquires).
+    auto stage_tile = [&](uint32_t buf, const uint32_t t) {
+        const bool staged = tma_ok && t < n_tiles && (uint64_t)(t + 1) * TILE <= n;
         s_tile[buf] = t;
-        uint32_t staged = 0;
-#ifdef GT_L2_PREFETCH
-        if (false) {
-#else
-        if (tma_ok && t < n_tiles && (uint64_t)(t + 1) * TILE <= n) {
-#endif
-            staged = 1;
+        s_staged[buf] = staged;
+        if (staged) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this buffer are done
             mbar_expect_tx(&s_bar, 3 * TILE * 4);
             const uint64_t q0 = (uint64_t)t * TILE;
@@ -492,8 +494,9 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             bulk_g2s(&s_q[0][0], chr + q0, TILE * 4, &s_bar, pol);
             bulk_g2s(&s_q[1][0], start + q0, TILE * 4, &s_bar, pol);
             bulk_g2s(&s_q[2][0], end + q0, TILE * 4, &s_bar, pol);
+        } else {
+            mbar_arrive(&s_bar);
         }
-        s_staged[buf] = staged;
     };
 
     for (uint32_t i = tid; i < CHROM_CACHE; i += FUSED_BLOCK)
@@ -501,7 +504,11 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
     if (tid == 0) {
         mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        claim_and_stage(0);
+#ifdef GT_STATIC_TILES
+        stage_tile(0, blockIdx.x);
+#else
+        stage_tile(0, atomicAdd(ws.counter, 1u));
+#endif
     }
     __syncthreads();
 
@@ -514,25 +521,32 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
     // One pipeline step: resolve `cur` (tile of this iteration), then look back + emit `prev` (tile of the last one).
     auto step = [&](TileState<ROWS>& cur, TileState<ROWS>& prev, const uint32_t par) -> bool {
         PHASE_START();
+        mbar_wait(&s_bar, bar_phase);  // the hand-over of this step's tile (and its query rows, when staged)
+        bar_phase ^= 1u;
         uint32_t tile = s_tile[par];
         if (tile >= n_tiles) tile = NO_TILE;
         cur.tile = tile;
         cur.slow = 0;
 
-        // prev's look-back words were published about one resolve phase ago: fetch them now so the look-back below
-        // normally finds them in registers instead of paying an L2 round trip after the barrier.  Warps 0-1: the tiles
-        // before prev inside its supertile (lanes past the supertile's first tile read as an empty aggregate);
-        // warp 2: the 32 supertiles before prev's (past the beginning: a zero prefix).
+        // prev's look-back words are fetched in the middle of this step — after the gathers of `cur` have landed, so the
+        // words are as fresh as possible (a stale "not ready" costs a reload between the barriers), early enough that the
+        // round trip hides behind the warp scan and barrier B2.  Warps 0-1: the tiles before prev inside its supertile
+        // (lanes past the supertile's first tile read as an empty aggregate); warp 2: the 32 supertiles before prev's
+        // (past the beginning: a zero prefix); one thread of warp 3: the file-boundary mark of prev.
+        constexpr uint32_t CLAIMER = FUSED_SUPER + 32;
         uint64_t lb_pre = 0;
-        if (prev.tile != NO_TILE && tid < FUSED_SUPER + 32) {
+        auto prefetch_lookback = [&]() {
+            if (prev.tile == NO_TILE) return;
             if (tid < FUSED_SUPER) {
                 const int64_t j = (int64_t)prev.tile - 1 - (int64_t)tid;
                 lb_pre = j >= (int64_t)(prev.tile & ~(FUSED_SUPER - 1)) ? ld_status(status + j) : ST_FLAG_AGG;
-            } else {
+            } else if (tid < FUSED_SUPER + 32) {
                 const int64_t sj = (int64_t)(prev.tile / FUSED_SUPER) - 1 - (int64_t)lane;
                 lb_pre = sj >= 0 ? ld_status(ws.super + sj) : (3ull << 62);
+            } else if (tid == CLAIMER + 1) {
+                if (out_file_tok) lb_pre = __ldg(ws.tile_file + prev.tile);
             }
-        }
+        };
 
         if (tile != NO_TILE) {
             const uint64_t tile_start = (uint64_t)tile * TILE;
@@ -540,8 +554,6 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             // ---- queries: ROWS coalesced rows per array, from the TMA-staged copy when there is one -----------------
             uint32_t qc[ROWS], qs[ROWS], qe[ROWS];
             if (s_staged[par]) {
-                mbar_wait(&s_bar, bar_phase);
-                bar_phase ^= 1u;
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k) {
                     qc[k] = s_q[0][wl + 32 * k];
@@ -588,6 +600,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     if (h0 & h1) s_aux[par][wl + 32 * k] = r[k].w;
                 }
             }
+            prefetch_lookback();
             PHASE_MARK(1);
             // ---- warp scan: exclusive offset of every query inside the warp's slice -----------------------------------
             uint32_t warp_total = 0;
@@ -636,6 +649,8 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             }
             if (lane == 0) s_wtot[par][warp] = warp_total;
             PHASE_MARK(2);
+        } else {
+            prefetch_lookback();
         }
         __syncthreads();  // B2: warp totals of `cur` visible; s_tile[par] / s_q consumed by everyone
         PHASE_MARK(3);
@@ -653,11 +668,15 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             if (tid == 0) {
                 st_status(status + tile, ST_FLAG_AGG | (uint64_t)tile_agg);
                 red_status(ws.super + tile / FUSED_SUPER, (1ull << 56) + (uint64_t)tile_agg);
-                claim_and_stage(par ^ 1);  // next tile: the claim and the query copies hide behind the look-back
+            } else if (tid == CLAIMER) {
+                // next tile: claimed by a thread outside the three look-back warps; nobody waits for the atomic's
+                // round trip before barrier B3 — the claimer picks the result up after it and stages the query copies
+#ifdef GT_STATIC_TILES
+                lb_pre = tile + gridDim.x;
+#else
+                lb_pre = atomicAdd(ws.counter, 1u);
+#endif
             }
-        } else if (tid == 0) {
-            s_tile[par ^ 1] = NO_TILE;
-            s_staged[par ^ 1] = 0;
         }
         PHASE_MARK(4);
 
@@ -668,6 +687,9 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 const int64_t j = (int64_t)prev.tile - 1 - (int64_t)tid;
                 uint64_t v = lb_pre;
                 for (uint32_t spin = 0; __any_sync(FULL, (v >> 62) == 0); ++spin) {
+#ifdef GT_PHASE_TIMING
+                    if (lane == 0) s_acc[warp][8] += 1;
+#endif
                     if ((v >> 62) == 0) {
                         __nanosleep(32);
                         v = ld_status(status + j);
@@ -688,6 +710,9 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 uint64_t v = lb_pre, acc = 0;
                 for (;;) {
                     for (uint32_t spin = 0; __any_sync(FULL, ((v >> 62) & 1) == 0); ++spin) {
+#ifdef GT_PHASE_TIMING
+                        if (lane == 0) s_acc[warp][8] += 1;
+#endif
                         if (((v >> 62) & 1) == 0) {
                             __nanosleep(32);
                             v = ld_status(ws.super + sj);
@@ -705,8 +730,11 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     v = sj >= 0 ? ld_status(ws.super + sj) : (3ull << 62);
                 }
                 if (lane == 0) s_lb_sum[par][warp] = acc;
+            } else if (tid == CLAIMER + 1) {
+                s_mark = (uint32_t)lb_pre;
             }
             __syncthreads();  // B3
+            if (tid == CLAIMER) stage_tile(par ^ 1, tile != NO_TILE ? (uint32_t)lb_pre : NO_TILE);
             uint64_t excl = s_lb_sum[par][0];
             if (!s_lb_p[par][0]) {
                 excl += s_lb_sum[par][1];
@@ -714,20 +742,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             }
             PHASE_MARK(5);
 #ifdef GT_PHASE_TIMING
-            if (lane == 0) { s_acc[warp][8] += 1; s_acc[warp][9] += 1; }
-#endif
-#ifdef GT_L2_PREFETCH
-            {   // next tile's query rows -> L2 (3 rows x 4 KiB = 384 sectors), so the loads at the top of the next step hit L2
-                const uint32_t nt = s_tile[par ^ 1];
-                if (nt < n_tiles) {
-                    const uint64_t q0 = (uint64_t)nt * TILE;
-                    for (uint32_t i = tid; i < 3 * (TILE / 8); i += FUSED_BLOCK) {
-                        const uint32_t a = i / (TILE / 8), o = (i % (TILE / 8)) * 8;
-                        const uint32_t* p = (a == 0 ? chr : a == 1 ? start : end) + q0 + o;
-                        if (q0 + o < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-                    }
-                }
-            }
+            if (lane == 0) s_acc[warp][9] += 1;
 #endif
             const uint64_t tile_start = (uint64_t)prev.tile * TILE;
             const uint64_t tile_base = base + excl;
@@ -786,7 +801,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
 
             // ---- file boundaries inside this tile: raw token offset of each file's first query ------------------------
             if (out_file_tok) {
-                const uint32_t mark = __ldg(ws.tile_file + prev.tile);  // block-uniform
+                const uint32_t mark = s_mark;  // block-uniform, prefetched before the resolve
                 if (mark != 0) {
                     // every warp publishes full offsets (tile-relative) for this rare tile, then boundaries are looked up
                     __syncthreads();
@@ -807,8 +822,8 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 }
             }
             PHASE_MARK(7);
-        } else {
-            __syncthreads();  // s_tile[par ^ 1] must be visible before the next iteration reads it
+        } else if (tid == CLAIMER) {
+            stage_tile(par ^ 1, tile != NO_TILE ? (uint32_t)lb_pre : NO_TILE);
         }
         return tile != NO_TILE;
     };
@@ -822,7 +837,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
     }
 #ifdef GT_PHASE_TIMING
     __syncwarp();
-    if (lane < 10) atomicAdd(&g_phase_cycles[lane], s_acc[warp][lane]);
+    if (lane < 10) atomicAdd(&g_phase_cycles[warp * 16 + lane], s_acc[warp][lane]);
 #endif
 }
 
@@ -851,9 +866,9 @@ static cudaError_t launch_variant(int grid, cudaStream_t st, const IndexView& vi
 #ifdef GT_PHASE_TIMING
 extern "C" void gtgpu_debug_phase_cycles(unsigned long long* out, int reset) {
     cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 16);
+    cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 16 * 8);
     if (reset) {
-        unsigned long long z[16] = {0};
+        unsigned long long z[16 * 8] = {0};
         cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z);
     }
 }
