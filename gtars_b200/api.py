@@ -45,6 +45,11 @@ def lib():
             "gth_mco_new": (vp, [vp, vp, C.c_int]), "gth_mco_free": (None, [vp]), "gth_mco_count": (C.c_int, [vp, vp, i32, vp]),
             "gth_mco_any": (C.c_int, [vp, vp, i32, vp]), "gth_mco_find": (vp, [vp, vp, i32]),
             "gth_mco_subset_by": (vp, [vp, vp, i32]),
+            "gth_irs_new": (vp, [vp, vp, C.c_int]), "gth_irs_free": (None, [vp]), "gth_irs_find": (vp, [vp, vp, i32]),
+            "gth_irs_subset_by_overlaps": (vp, [vp, vp, i32]), "gth_irs_count": (C.c_int, [vp, vp, i32, vp]),
+            "gth_irs_any": (C.c_int, [vp, vp, i32, vp]),
+            "gth_consensus_new": (vp, [vp, cp]), "gth_consensus_free": (None, [vp]), "gth_consensus_len": (u64, [vp]),
+            "gth_region_scoring": (C.c_int, [vp, u64, vp, C.c_int, vp]), "gth_barcode_scoring": (vp, [vp, cp]),
             "gth_tokenizer_new": (vp, [vp, cp, C.c_int]), "gth_tokenizer_free": (None, [vp]),
             "gth_tokenizer_vocab_size": (u64, [vp]), "gth_tokenizer_token_to_id": (i64, [vp, cp]),
             "gth_tokenizer_id_to_token": (cp, [vp, u32]), "gth_tokenizer_special": (cp, [vp, C.c_int]),
@@ -210,6 +215,89 @@ class MultiChromOverlapper:
         if not h:
             _fail()
         return RegionSet._wrap(h)
+
+
+class IndexedRegionSet:
+    """gtars_overlaprs::IndexedRegionSet (indexed_region_set.rs): a RegionSet with its overlap index."""
+
+    def __init__(self, regions, kind=AILIST):
+        self._src = _as_rs(regions)
+        self._h = lib().gth_irs_new(device(), self._src._h, kind)
+        if not self._h:
+            _fail()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().gth_irs_free(self._h)
+            self._h = None
+
+    def regions(self):
+        return self._src
+
+    def find_overlaps(self, query, min_overlap=None):
+        """Per query region: sorted, de-duplicated indices into the source set."""
+        q = _as_rs(query)
+        return _take_lists(lib().gth_irs_find(self._h, q._h, MultiChromOverlapper._m(min_overlap)))
+
+    def subset_by_overlaps(self, query, min_overlap=None):
+        q = _as_rs(query)
+        h = lib().gth_irs_subset_by_overlaps(self._h, q._h, MultiChromOverlapper._m(min_overlap))
+        if not h:
+            _fail()
+        return RegionSet._wrap(h)
+
+    def intersect_all(self, query):
+        return self.subset_by_overlaps(query, None)
+
+    def count_overlaps(self, query, min_overlap=None):
+        q = _as_rs(query)
+        out = np.zeros(len(q), dtype=np.uint64)
+        if lib().gth_irs_count(self._h, q._h, MultiChromOverlapper._m(min_overlap), out.ctypes.data):
+            _fail()
+        return [int(x) for x in out]
+
+    def any_overlaps(self, query, min_overlap=None):
+        q = _as_rs(query)
+        out = np.zeros(len(q), dtype=np.uint8)
+        if lib().gth_irs_any(self._h, q._h, MultiChromOverlapper._m(min_overlap), out.ctypes.data):
+            _fail()
+        return [bool(x) for x in out]
+
+
+SCORING_ATAC, SCORING_CHIP = 0, 1
+
+
+class ConsensusSet:
+    """gtars_scoring::ConsensusSet (files.rs:60-99): consensus peaks, one column of the count matrix each."""
+
+    def __init__(self, path):
+        self._h = lib().gth_consensus_new(device(), os.fsencode(path))
+        if not self._h:
+            _fail()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().gth_consensus_free(self._h)
+            self._h = None
+
+    def __len__(self):
+        return int(lib().gth_consensus_len(self._h))
+
+
+def region_scoring_from_fragments(fragment_files, consensus, mode=SCORING_ATAC):
+    """gtars_scoring::region_scoring_from_fragments: uint32 [n_files, len(consensus)] (files in the given order)."""
+    files = [os.fsencode(p) for p in fragment_files]
+    arr = (C.c_char_p * max(len(files), 1))(*files)
+    out = np.zeros((len(files), len(consensus)), dtype=np.uint32)
+    if lib().gth_region_scoring(consensus._h, len(files), arr, mode, out.ctypes.data):
+        _fail()
+    return out
+
+
+def barcode_scoring_from_fragments(fragment_file, consensus):
+    """gtars_scoring::barcode_scoring_from_fragments: {barcode: {peak index: count}}."""
+    named = _take_lists(lib().gth_barcode_scoring(consensus._h, os.fsencode(fragment_file)), named=True)
+    return {bc: dict(zip(flat[0::2], flat[1::2])) for bc, flat in named}
 
 
 class Tokenizer:

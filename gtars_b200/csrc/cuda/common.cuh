@@ -166,6 +166,7 @@ struct gtgpu_index {
     std::vector<void*> allocs;
     uint64_t n_intervals = 0, n_segments = 0, device_bytes = 0, max_components = 0;
     uint64_t bt_bins = 0, bt_overflow_bins = 0, bt_pool_windows = 0;
+    uint32_t max_val = 0;  // largest val of any interval (bounds the radix passes of the scoring group-by)
     bool l2_window_set = false;
 };
 

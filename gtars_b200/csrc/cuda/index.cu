@@ -395,6 +395,7 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
     up(h_ends, &v.ends);
     up(h_pmax, &v.pmax);
     up(h_vals, &v.vals);
+    for (uint32_t x : h_vals) ix->max_val = std::max(ix->max_val, x);
     up(h_cs, &v.cs_starts);
     up(h_ce, &v.cs_ends);
     up(lut, &v.lut);

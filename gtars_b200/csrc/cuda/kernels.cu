@@ -193,9 +193,8 @@ int32_t launch_count(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const u
 // A tile is FUSED_BLOCK x ROWS consecutive queries.  Inside a tile each WARP owns 32 x ROWS consecutive queries in
 // a striped layout (lane l holds queries l, l+32, …), so every query load and every id store of a row is one fully
 // coalesced 128-byte access.  Tiles are handed out in order by an atomic counter (persistent grid), which is what
-// makes the look-back deadlock-free.  The look-back is BLOCK-wide: all 256 threads inspect the 256 preceding tiles
-// in one L2 round trip, because at >1e11 queries/s tiles retire faster than a 32-wide window can follow
-// ("look-back arithmetic").
+// makes the look-back deadlock-free.  The look-back is two-level (supertiles of FUSED_SUPER tiles, see below): at
+// >1e11 queries/s about 600 tiles are in flight, far more than any single window of predecessors can follow.
 #define ST_FLAG_AGG (1ull << 62)
 #define ST_FLAG_PREFIX (2ull << 62)
 #define ST_MASK ((1ull << 62) - 1)

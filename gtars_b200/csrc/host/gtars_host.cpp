@@ -517,6 +517,132 @@ std::vector<std::pair<std::string, std::map<uint32_t, uint32_t>>> Tokenizer::cou
     return out;
 }
 
+// ---- IndexedRegionSet ---------------------------------------------------------------------------------------------------------
+IndexedRegionSet::IndexedRegionSet(std::shared_ptr<Device> dev, RegionSet regions, OverlapperType kind)
+    : source_(std::move(regions)), index_(new MultiChromOverlapper(std::move(dev), source_, kind)) {}
+
+std::vector<std::vector<uint32_t>> IndexedRegionSet::find_overlaps(const RegionSet& query, int32_t min_overlap) const {
+    // The reference maps hit coordinates back through a (chr, start, end) -> [source indices] table, so a hit on
+    // one of several identical regions reports all of them; identical regions overlap the same queries, so the
+    // union of the per-hit source indices is already that set.  Sorted, de-duplicated (:256-258).
+    auto hits = index_->find_overlaps_indices(query, min_overlap);
+    for (auto& v : hits) {
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+    }
+    return hits;
+}
+RegionSet IndexedRegionSet::subset_by_overlaps(const RegionSet& query, int32_t min_overlap) const {
+    std::set<uint32_t> keep;  // BTreeSet<usize>: ascending source index
+    for (const auto& v : find_overlaps(query, min_overlap)) keep.insert(v.begin(), v.end());
+    std::vector<Region> out;
+    for (uint32_t i : keep) out.push_back(source_.regions[i]);
+    return RegionSet::from_regions(std::move(out));
+}
+RegionSet IndexedRegionSet::intersect_all(const RegionSet& query) const { return subset_by_overlaps(query, -1); }
+std::vector<uint64_t> IndexedRegionSet::count_overlaps(const RegionSet& query, int32_t min_overlap) const {
+    return index_->count_overlaps(query, min_overlap);
+}
+std::vector<bool> IndexedRegionSet::any_overlaps(const RegionSet& query, int32_t min_overlap) const {
+    return index_->any_overlaps(query, min_overlap);
+}
+
+// ---- gtars_scoring ----------------------------------------------------------------------------------------------------------------
+ConsensusSet::ConsensusSet(std::shared_ptr<Device> dev, const std::string& path) : dev_(std::move(dev)) {
+    build(RegionSet::from_file(path));
+}
+ConsensusSet::ConsensusSet(std::shared_ptr<Device> dev, const RegionSet& regions) : dev_(std::move(dev)) { build(regions); }
+ConsensusSet::~ConsensusSet() { gtgpu_index_free(index_); }
+
+void ConsensusSet::build(const RegionSet& rs) {
+    len_ = rs.regions.size();
+    std::unordered_map<std::string, uint32_t> ids;  // generate_region_to_id_map (gtars-core utils.rs:202-214)
+    std::vector<uint32_t> chr, start, end, val;
+    for (const Region& r : rs.regions) {
+        std::string key = r.chr + '\x1f' + std::to_string(r.start) + '\x1f' + std::to_string(r.end) + '\x1f' + r.rest;
+        auto it = ids.find(key);
+        if (it == ids.end()) it = ids.emplace(std::move(key), (uint32_t)ids.size()).first;
+        chr.push_back(cmap_.add(r.chr));
+        start.push_back(r.start);
+        end.push_back(r.end);
+        val.push_back(it->second);
+    }
+    Grouped g = group_by_chrom(chr, start, end, val, cmap_.size());
+    check(gtgpu_index_build(dev_->ctx(), GTGPU_KIND_BITS, (uint32_t)cmap_.size(), g.offsets.data(), g.start.data(), g.end.data(),
+                            g.val.data(), &index_),
+          "gtgpu_index_build");
+}
+
+namespace {
+struct ParsedFragments {
+    FlatQueries q;
+    std::vector<std::string> barcode;
+};
+// Fragment::from_str (gtars-core/src/models/fragments.rs:16-44): split_whitespace; fields 1, 2 and 4 parse as u32.
+void parse_fragment_file(const std::string& path, const ChromMap& cmap, ParsedFragments& out) {
+    auto lines = read_lines(path);
+    for (size_t i = 0; i < lines.size(); ++i) {
+        if (has_prefix(lines[i], "#")) continue;
+        auto parts = split_whitespace(lines[i]);
+        uint32_t s, e, support;
+        if (parts.size() < 5 || !parse_u32(parts[1], s) || !parse_u32(parts[2], e) || !parse_u32(parts[4], support))
+            throw Error("Failed to parse fragment at line " + std::to_string(i) + " of " + path);
+        out.q.chr.push_back(cmap.get(parts[0]));
+        out.q.start.push_back(s);
+        out.q.end.push_back(e);
+        out.barcode.push_back(parts[3]);
+    }
+}
+}  // namespace
+
+CountMatrix region_scoring_from_fragments(const std::vector<std::string>& fragment_files, const ConsensusSet& consensus,
+                                          ScoringMode mode) {
+    ParsedFragments all;
+    std::vector<uint64_t> file_offsets{0};
+    for (const auto& path : fragment_files) {
+        parse_fragment_file(path, consensus.chroms(), all);
+        file_offsets.push_back(all.q.chr.size());
+    }
+    CountMatrix m;
+    m.rows = fragment_files.size();
+    m.cols = consensus.len();
+    m.data.assign(m.rows * m.cols, 0);
+    check(gtgpu_score_matrix(consensus.index(), m.rows, file_offsets.data(), all.q.chr.size(), all.q.chr.data(), all.q.start.data(),
+                             all.q.end.data(), (int32_t)mode, m.cols, m.data.data()),
+          "gtgpu_score_matrix");
+    return m;
+}
+
+std::vector<std::pair<std::string, std::map<uint32_t, uint32_t>>> barcode_scoring_from_fragments(const std::string& fragment_file,
+                                                                                                 const ConsensusSet& consensus) {
+    ParsedFragments pf;
+    parse_fragment_file(fragment_file, consensus.chroms(), pf);
+    std::vector<std::string> barcodes;
+    std::unordered_map<std::string, uint32_t> bc_ids;
+    std::vector<uint32_t> bc;
+    for (const auto& b : pf.barcode) {
+        auto it = bc_ids.find(b);
+        if (it == bc_ids.end()) {
+            it = bc_ids.emplace(b, (uint32_t)barcodes.size()).first;
+            barcodes.push_back(b);
+        }
+        bc.push_back(it->second);
+    }
+    std::vector<uint64_t> offsets(barcodes.size() + 1);
+    PinnedResult peaks, counts;
+    check(gtgpu_score_barcodes(consensus.index(), bc.size(), pf.q.chr.data(), pf.q.start.data(), pf.q.end.data(), bc.data(),
+                               (uint32_t)barcodes.size(), offsets.data(), &peaks.buf, &counts.buf),
+          "gtgpu_score_barcodes");
+    std::vector<std::pair<std::string, std::map<uint32_t, uint32_t>>> out;
+    for (size_t b = 0; b < barcodes.size(); ++b) {
+        if (offsets[b] == offsets[b + 1]) continue;  // the reference only creates an entry on the first overlap
+        std::map<uint32_t, uint32_t> m;
+        for (uint64_t k = offsets[b]; k < offsets[b + 1]; ++k) m[peaks.data()[k]] = counts.data()[k];
+        out.emplace_back(barcodes[b], std::move(m));
+    }
+    return out;
+}
+
 // ---- Igd / LOLA -----------------------------------------------------------------------------------------------------------------
 Igd::Igd(std::shared_ptr<Device> dev, const std::vector<const RegionSet*>& sets) : dev_(std::move(dev)), n_files_(sets.size()) {
     std::vector<uint64_t> file_offsets(sets.size() + 1, 0);

@@ -104,6 +104,63 @@ class MultiChromOverlapper {
     std::vector<Region> source_;  // coordinates only, to rebuild regions from vals
 };
 
+// gtars_overlaprs::IndexedRegionSet (indexed_region_set.rs:100-263): a RegionSet plus its overlap index; the
+// index-returning queries report positions in the source set, sorted and de-duplicated per query.
+class IndexedRegionSet {
+   public:
+    IndexedRegionSet(std::shared_ptr<Device> dev, RegionSet regions, OverlapperType kind = OverlapperType::AIList);  // :111-143
+    const RegionSet& regions() const { return source_; }                                                    // :168
+    RegionSet intersect_all(const RegionSet& query) const;                                                  // :201-216
+    RegionSet subset_by_overlaps(const RegionSet& query, int32_t min_overlap = -1) const;                   // :218-232
+    std::vector<uint64_t> count_overlaps(const RegionSet& query, int32_t min_overlap = -1) const;           // :234-238
+    std::vector<bool> any_overlaps(const RegionSet& query, int32_t min_overlap = -1) const;                 // :240-244
+    std::vector<std::vector<uint32_t>> find_overlaps(const RegionSet& query, int32_t min_overlap = -1) const;  // :246-263
+
+   private:
+    RegionSet source_;
+    std::unique_ptr<MultiChromOverlapper> index_;
+};
+
+// ---- gtars_scoring ---------------------------------------------------------------------------------------------------------
+enum class ScoringMode { Atac = GTGPU_SCORE_ATAC, Chip = GTGPU_SCORE_CHIP };  // scoring_modes.rs
+
+struct CountMatrix {  // counts.rs:9-56, row-major u32
+    std::vector<uint32_t> data;
+    size_t rows = 0, cols = 0;
+    const uint32_t* get(size_t row, size_t col) const { return row < rows && col < cols ? &data[row * cols + col] : nullptr; }
+};
+
+// ConsensusSet::new (files.rs:60-99): RegionSet::try_from(path); ids = rank of first appearance among distinct
+// regions (chr, start, end, rest); one Bits per chromosome.
+class ConsensusSet {
+   public:
+    ConsensusSet(std::shared_ptr<Device> dev, const std::string& path);
+    ConsensusSet(std::shared_ptr<Device> dev, const RegionSet& regions);
+    ~ConsensusSet();
+    ConsensusSet(const ConsensusSet&) = delete;
+    ConsensusSet& operator=(const ConsensusSet&) = delete;
+    size_t len() const { return len_; }
+    bool is_empty() const { return len_ == 0; }
+    gtgpu_index* index() const { return index_; }
+    const ChromMap& chroms() const { return cmap_; }
+
+   private:
+    void build(const RegionSet& rs);
+    std::shared_ptr<Device> dev_;
+    gtgpu_index* index_ = nullptr;
+    ChromMap cmap_;
+    size_t len_ = 0;
+};
+
+// region_scoring_from_fragments (fragment_scoring.rs:19-121): one row per fragment file (in the given order — the
+// reference's glob yields sorted paths), one column per consensus region.
+CountMatrix region_scoring_from_fragments(const std::vector<std::string>& fragment_files, const ConsensusSet& consensus,
+                                          ScoringMode mode);
+// barcode_scoring_from_fragments (fragment_scoring.rs:126-155): barcode -> (peak index -> count); barcodes in
+// first-appearance order (the reference's map is unordered), only barcodes with at least one overlap appear.
+std::vector<std::pair<std::string, std::map<uint32_t, uint32_t>>> barcode_scoring_from_fragments(const std::string& fragment_file,
+                                                                                                 const ConsensusSet& consensus);
+
 // ---- gtars_tokenizers ----------------------------------------------------------------------------------------------------
 struct SpecialTokens {
     std::string unk = "<unk>", pad = "<pad>", mask = "<mask>", cls = "<cls>", eos = "<eos>", bos = "<bos>", sep = "<sep>";

@@ -98,6 +98,67 @@ void* gth_mco_subset_by(void* m, void* query, int32_t min_overlap) {
                  nullptr);
 }
 
+// ---- IndexedRegionSet ---------------------------------------------------------------------------------------------------------
+void* gth_irs_new(void* dev, void* regions, int kind) {
+    return guard([&]() -> void* {
+        return new IndexedRegionSet(*(std::shared_ptr<Device>*)dev, *(RegionSet*)regions, (OverlapperType)kind);
+    }, nullptr);
+}
+void gth_irs_free(void* r) { delete (IndexedRegionSet*)r; }
+void* gth_irs_find(void* r, void* query, int32_t min_overlap) {
+    return guard([&]() -> void* {
+        Lists* l = new Lists();
+        l->lists = ((IndexedRegionSet*)r)->find_overlaps(*(RegionSet*)query, min_overlap);
+        return l;
+    }, nullptr);
+}
+void* gth_irs_subset_by_overlaps(void* r, void* query, int32_t min_overlap) {
+    return guard([&]() -> void* { return new RegionSet(((IndexedRegionSet*)r)->subset_by_overlaps(*(RegionSet*)query, min_overlap)); },
+                 nullptr);
+}
+int gth_irs_count(void* r, void* query, int32_t min_overlap, uint64_t* out) {
+    return guard([&]() -> int {
+        auto v = ((IndexedRegionSet*)r)->count_overlaps(*(RegionSet*)query, min_overlap);
+        std::copy(v.begin(), v.end(), out);
+        return 0;
+    }, 1);
+}
+int gth_irs_any(void* r, void* query, int32_t min_overlap, uint8_t* out) {
+    return guard([&]() -> int {
+        auto v = ((IndexedRegionSet*)r)->any_overlaps(*(RegionSet*)query, min_overlap);
+        for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+        return 0;
+    }, 1);
+}
+
+// ---- gtars_scoring ---------------------------------------------------------------------------------------------------------------
+void* gth_consensus_new(void* dev, const char* path) {
+    return guard([&]() -> void* { return new ConsensusSet(*(std::shared_ptr<Device>*)dev, std::string(path)); }, nullptr);
+}
+void gth_consensus_free(void* c) { delete (ConsensusSet*)c; }
+uint64_t gth_consensus_len(void* c) { return ((ConsensusSet*)c)->len(); }
+int gth_region_scoring(void* c, uint64_t n_files, const char** paths, int mode, uint32_t* out /* n_files x len */) {
+    return guard([&]() -> int {
+        std::vector<std::string> files(paths, paths + n_files);
+        CountMatrix m = region_scoring_from_fragments(files, *(ConsensusSet*)c, (ScoringMode)mode);
+        std::copy(m.data.begin(), m.data.end(), out);
+        return 0;
+    }, 1);
+}
+// barcode -> interleaved (peak, count) pairs
+void* gth_barcode_scoring(void* c, const char* path) {
+    return guard([&]() -> void* {
+        Lists* l = new Lists();
+        for (auto& kv : barcode_scoring_from_fragments(path, *(ConsensusSet*)c)) {
+            l->names.push_back(kv.first);
+            std::vector<uint32_t> flat;
+            for (auto& pc : kv.second) { flat.push_back(pc.first); flat.push_back(pc.second); }
+            l->lists.push_back(std::move(flat));
+        }
+        return l;
+    }, nullptr);
+}
+
 // ---- Tokenizer ------------------------------------------------------------------------------------------------------------------
 void* gth_tokenizer_new(void* dev, const char* path, int how /*0 auto, 1 bed, 2 config*/) {
     return guard([&]() -> void* {

@@ -14,6 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 # GTGPU_LIB selects an experimental build of the same library (tuning sweeps); the default is the in-tree product.
 LIB_PATH = os.environ.get("GTGPU_LIB") or os.path.join(_PKG, "libgtars_gpu.so")
 
+SCORE_ATAC, SCORE_CHIP = 0, 1
 KIND_BITS, KIND_AILIST = 0, 1
 UNKNOWN_CHROM = 0xFFFFFFFF
 
@@ -44,6 +45,9 @@ SIGNATURES = {
     "gtgpu_tokenize_files": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
     "gtgpu_tokenize_files_runs": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
     "gtgpu_tokenize_fragments": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp]),
+    "gtgpu_score_matrix": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _i32, _u64, _vp]),
+    "gtgpu_score_matrix_dev": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _i32, _u64, _vp]),
+    "gtgpu_score_barcodes": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp]),
     "gtgpu_igd_build": (_i32, [_vp, _u64, _vp, _u32, _vp, _vp, _vp, _vp]),
     "gtgpu_igd_free": (_i32, [_vp]),
     "gtgpu_igd_info": (_i32, [_vp, _vp]),
@@ -271,6 +275,26 @@ class Index:
         check(lib().gtgpu_tokenize_fragments(self._h, len(chr), _p(chr), _p(start), _p(end), _p(barcode), n_barcodes,
                                              unk_id, _p(out_off), C.byref(h)))
         return out_off, _take(h)
+
+    def score_matrix(self, file_offsets, chr, start, end, mode, n_cols):
+        """region_scoring_from_fragments: uint32 [n_files, n_cols]."""
+        fo = _arr(file_offsets, np.uint64)
+        chr, start, end = (_arr(a, np.uint32) for a in (chr, start, end))
+        out = np.empty((len(fo) - 1, n_cols), dtype=np.uint32)
+        check(lib().gtgpu_score_matrix(self._h, len(fo) - 1, _p(fo), len(chr), _p(chr), _p(start), _p(end), mode, n_cols, _p(out)))
+        return out
+
+    def score_matrix_dev(self, n_files, d_file_offsets, n, d_chr, d_start, d_end, mode, n_cols, d_out):
+        check(lib().gtgpu_score_matrix_dev(self._h, n_files, d_file_offsets, n, d_chr, d_start, d_end, mode, n_cols, d_out))
+
+    def score_barcodes(self, chr, start, end, barcode, n_barcodes):
+        """barcode_scoring_from_fragments: (offsets[n_barcodes + 1], peaks, counts) sorted by (barcode, peak)."""
+        chr, start, end, barcode = (_arr(a, np.uint32) for a in (chr, start, end, barcode))
+        out_off = np.empty(n_barcodes + 1, dtype=np.uint64)
+        hp, hc = C.c_void_p(), C.c_void_p()
+        check(lib().gtgpu_score_barcodes(self._h, len(chr), _p(chr), _p(start), _p(end), _p(barcode), n_barcodes,
+                                         _p(out_off), C.byref(hp), C.byref(hc)))
+        return out_off, _take(hp), _take(hc)
 
     # ---- device-resident entry points (raw device pointers as ints) ----------------------------------------------------
     def count_dev(self, n, d_chr, d_start, d_end, min_overlap, d_out):

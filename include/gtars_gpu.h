@@ -136,6 +136,30 @@ int32_t gtgpu_tokenize_fragments(gtgpu_index* index, uint64_t n, const uint32_t*
                                  const uint32_t* end, const uint32_t* barcode_id, uint32_t n_barcodes, uint32_t unk_id,
                                  uint64_t* out_barcode_offsets, gtgpu_buf** out_ids);
 
+/* ---- gtars-scoring: fragments x consensus peaks ------------------------------------------------------------------------
+ * gtgpu_score_matrix replaces region_scoring_from_fragments (gtars-scoring/src/fragment_scoring.rs:19-121) over
+ * pre-parsed fragments: file f owns fragments [file_offsets[f], file_offsets[f+1]); the index is the ConsensusSet
+ * (gtars-scoring/src/files.rs:60-99: one Bits per chromosome, val = id of the peak); out_counts is the row-major
+ * n_files x n_cols CountMatrix<u32> (counts.rs:9-56; a val >= n_cols is ignored like CountMatrix::increment does).
+ * GTGPU_SCORE_ATAC: every fragment is two lookups, the shifted start [start+4, start+5) and the end interval the
+ * reference builds as Region{start: end-5, end: end-6} (fragment_scoring.rs:59-84, consts.rs START_SHIFT/END_SHIFT);
+ * GTGPU_SCORE_CHIP: the fragment itself (:99-107).  u32 arithmetic wraps.  The _dev form takes device pointers. */
+#define GTGPU_SCORE_ATAC 0
+#define GTGPU_SCORE_CHIP 1
+int32_t gtgpu_score_matrix(gtgpu_index* index, uint64_t n_files, const uint64_t* file_offsets, uint64_t n,
+                           const uint32_t* chr, const uint32_t* start, const uint32_t* end, int32_t mode,
+                           uint64_t n_cols, uint32_t* out_counts);
+int32_t gtgpu_score_matrix_dev(gtgpu_index* index, uint64_t n_files, const uint64_t* d_file_offsets, uint64_t n,
+                               const uint32_t* d_chr, const uint32_t* d_start, const uint32_t* d_end, int32_t mode,
+                               uint64_t n_cols, uint32_t* d_out_counts);
+
+/* barcode_scoring_from_fragments (fragment_scoring.rs:126-155): whole fragments, sparse barcode x peak counts.  The
+ * reference returns HashMap<barcode, HashMap<peak, count>>; here the same content as CSR sorted by (barcode, peak):
+ * out_barcode_offsets[n_barcodes + 1] index the (peak, count) pairs in *out_peaks / *out_counts. */
+int32_t gtgpu_score_barcodes(gtgpu_index* index, uint64_t n, const uint32_t* chr, const uint32_t* start,
+                             const uint32_t* end, const uint32_t* barcode_id, uint32_t n_barcodes,
+                             uint64_t* out_barcode_offsets, gtgpu_buf** out_peaks, gtgpu_buf** out_counts);
+
 /* ---- IGD / LOLA overlap-count matrices ------------------------------------------------------------------------------
  * gtgpu_igd_build replaces Igd::from_named_region_sets / from_region_sets (gtars-igd/src/igd.rs:249-317): file f owns
  * records [file_offsets[f], file_offsets[f+1]); records with start >= end, or negative as int32, are dropped as

@@ -59,6 +59,12 @@ def lib():
         "orc_buf_free": (None, [vp]),
         "orc_tokenize_files": (vp, [vp, u64, vp, vp, vp, vp, u32, vp, vp, cint]),
         "orc_tokenize_fragments": (vp, [vp, u64, vp, vp, vp, vp, u32, u32, vp, vp]),
+        "orc_score_matrix": (None, [vp, u64, vp, vp, vp, vp, cint, u64, vp, cint]),
+        "orc_score_barcodes": (vp, [vp, u64, vp, vp, vp, vp, u32, vp]),
+        "orc_consensus_from_bed": (vp, [C.c_char_p]),
+        "orc_consensus_free": (None, [vp]),
+        "orc_consensus_len": (u64, [vp]),
+        "orc_region_scoring_files": (cint, [vp, u64, vp, cint, vp]),
         "orc_regionset_from_file": (vp, [C.c_char_p]),
         "orc_regionset_free": (None, [vp]),
         "orc_regionset_len": (u64, [vp]),
@@ -219,6 +225,44 @@ class Index:
         h = lib().orc_tokenize_fragments(self._h, len(chr), _ptr(chr), _ptr(start), _ptr(end), _ptr(barcode),
                                          n_barcodes, unk_id, _ptr(rm), _ptr(out_off))
         return out_off, _take_buf(h)
+
+
+SCORE_ATAC, SCORE_CHIP = 0, 1
+
+
+def score_matrix(index, file_offsets, chr, start, end, mode, n_cols, threads=1):
+    """region_scoring_from_fragments over dense-id fragments: uint32 [n_files, n_cols]."""
+    fo, chr, start, end = _u64(file_offsets), _u32(chr), _u32(start), _u32(end)
+    n_files = len(fo) - 1
+    out = np.empty((n_files, n_cols), dtype=np.uint32)
+    lib().orc_score_matrix(index._h, n_files, _ptr(fo), _ptr(chr), _ptr(start), _ptr(end), mode, n_cols, _ptr(out), threads)
+    return out
+
+
+def score_barcodes(index, chr, start, end, barcode, n_barcodes):
+    """barcode_scoring_from_fragments: (offsets[n_barcodes+1], peaks, counts), sorted by (barcode, peak)."""
+    chr, start, end, barcode = _u32(chr), _u32(start), _u32(end), _u32(barcode)
+    out_off = np.empty(n_barcodes + 1, dtype=np.uint64)
+    h = lib().orc_score_barcodes(index._h, len(chr), _ptr(chr), _ptr(start), _ptr(end), _ptr(barcode), n_barcodes, _ptr(out_off))
+    pairs = _take_buf(h).reshape(-1, 2)
+    return out_off, pairs[:, 0].copy(), pairs[:, 1].copy()
+
+
+def region_scoring_files(consensus_path, fragment_paths, mode=SCORE_ATAC):
+    """ConsensusSet::new(path) + region_scoring_from_fragments over the files, in the given order."""
+    L = lib()
+    h = L.orc_consensus_from_bed(os.fsencode(consensus_path))
+    if not h:
+        raise ValueError(_err())
+    try:
+        cols = L.orc_consensus_len(h)
+        out = np.empty((len(fragment_paths), cols), dtype=np.uint32)
+        arr = (C.c_char_p * len(fragment_paths))(*[os.fsencode(p) for p in fragment_paths])
+        if L.orc_region_scoring_files(h, len(fragment_paths), arr, mode, _ptr(out)) != 0:
+            raise ValueError(_err())
+        return out
+    finally:
+        L.orc_consensus_free(h)
 
 
 def regionset_from_file(path):

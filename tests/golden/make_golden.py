@@ -231,6 +231,34 @@ KATS = {
         },
         "queries": ["igd_query_files/query1.bed", "igd_query_files/query2.bed"],
     },
+    # ---- K10: gtars-scoring fragments x consensus count matrix (ATAC shifts incl. the reversed end interval) ----
+    "K10_scoring": {
+        "cite": "gtars-scoring/src/fragment_scoring.rs:180-210 (test_region_scoring_from_fragments_atac)",
+        "consensus": "consensus/consensus1.bed",
+        "fragment_files": ["fragments/region_scoring/fragments1.bed.gz", "fragments/region_scoring/fragments2.bed.gz"],
+        "mode": "atac", "rows": 2, "cols": 4, "matrix": [[2, 2, 1, 3], [4, 1, 3, 1]],
+    },
+    # ---- K12: IndexedRegionSet index-returning queries -------------------------------------------------------
+    "K12_indexed_region_set": {
+        "cite": "gtars-overlaprs/src/indexed_region_set.rs:396-545",
+        "cases": [
+            {"name": "intersect_all", "reference": [["chr1", 100, 200], ["chr1", 300, 400], ["chr2", 500, 600]],
+             "query": [["chr1", 150, 250], ["chr2", 550, 650]], "intersect_all": [["chr1", 100, 200], ["chr2", 500, 600]]},
+            {"name": "count", "reference": [["chr1", 100, 200], ["chr1", 150, 250], ["chr1", 300, 400]],
+             "query": [["chr1", 180, 220]], "count": [2]},
+            {"name": "any", "reference": [["chr1", 100, 200]], "query": [["chr1", 150, 250], ["chr1", 300, 400]],
+             "any": [True, False]},
+            {"name": "find", "reference": [["chr1", 100, 200], ["chr1", 300, 400]], "query": [["chr1", 150, 350]],
+             "find": [[0, 1]]},
+            {"name": "empty_reference", "reference": [], "query": [["chr1", 100, 200]], "count": [0], "any": [False],
+             "find": [[]], "intersect_all": []},
+            {"name": "empty_query", "reference": [["chr1", 100, 200]], "query": [], "count": [], "any": [], "find": [],
+             "intersect_all": []},
+            {"name": "multi_chrom", "reference": [["chr1", 100, 200], ["chr2", 100, 200], ["chr3", 100, 200]],
+             "query": [["chr1", 150, 250], ["chr2", 150, 250], ["chr4", 150, 250]], "count": [1, 1, 0],
+             "any": [True, True, False]},
+        ],
+    },
     # ---- derived vectors (NOT asserted by the reference; regression pins only) -------------------------
     "D_derived": {
         "D1": {"note": "to_tokenize.bed (sorted by RegionSet::try_from) vs peaks.bed", "universe": "tokenizers/peaks.bed",

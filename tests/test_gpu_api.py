@@ -187,3 +187,41 @@ def test_igd_single_region_set_kats(api, golden):
     # subjects Igd::add would drop (empty / reversed) never count
     igd = api.Igd.from_single_region_set([("chr1", 100, 100), ("chr1", 300, 200), ("chr1", 50, 150)])
     assert igd.find_overlaps_regionset([("chr1", 0, 1000)], 1) == [(0, 2)]
+
+
+def test_scoring_kat_through_api(api, golden, fixture_dir):
+    """K10 (gtars-scoring/src/fragment_scoring.rs:180-210) through ConsensusSet / region_scoring_from_fragments."""
+    k = golden[1]["K10_scoring"]
+    cons = api.ConsensusSet(os.path.join(fixture_dir, k["consensus"]))
+    assert len(cons) == k["cols"]
+    files = [os.path.join(fixture_dir, f) for f in k["fragment_files"]]
+    m = api.region_scoring_from_fragments(files, cons, api.SCORING_ATAC)
+    assert m.shape == (k["rows"], k["cols"]) and m.tolist() == k["matrix"]
+    from oracle import oracle as orc
+    chip = api.region_scoring_from_fragments(files, cons, api.SCORING_CHIP)
+    assert np.array_equal(chip, orc.region_scoring_files(os.path.join(fixture_dir, k["consensus"]), files, orc.SCORE_CHIP))
+    # sparse per-barcode counts of the first file: sums must equal the Chip row; every barcode listed has a hit
+    sparse = api.barcode_scoring_from_fragments(files[0], cons)
+    tot = np.zeros(k["cols"], dtype=np.int64)
+    for bc, counts in sparse.items():
+        assert counts
+        for peak, c in counts.items():
+            tot[peak] += c
+    assert tot.tolist() == chip[0].tolist()
+
+
+def test_indexed_region_set_kats(api, golden):
+    """K12: gtars-overlaprs/src/indexed_region_set.rs:396-545."""
+    for case in golden[1]["K12_indexed_region_set"]["cases"]:
+        for kind in (api.AILIST, api.BITS):
+            irs = api.IndexedRegionSet([api.Region(*r) for r in case["reference"]], kind)
+            q = [api.Region(*r) for r in case["query"]]
+            if "count" in case:
+                assert irs.count_overlaps(q) == case["count"], case["name"]
+            if "any" in case:
+                assert irs.any_overlaps(q) == case["any"], case["name"]
+            if "find" in case:
+                assert irs.find_overlaps(q) == case["find"], case["name"]
+            if "intersect_all" in case:
+                got = [[r.chr, r.start, r.end] for r in irs.intersect_all(q)]
+                assert got == case["intersect_all"], case["name"]

@@ -3,6 +3,8 @@
 Run on a B200 with `pytest -m gpu`.  Inputs are seeded; sizes are chosen so the oracle finishes in seconds;
 full-size properties live in test_gpu_scale.py.
 """
+import zlib
+
 import numpy as np
 import pytest
 
@@ -410,3 +412,57 @@ def test_wide_queries_multi_window(ctx, kind, nested):
     fo = np.array([0, 10_000, nq], dtype=np.uint64)
     a, b = g.tokenize_files(fo, qc, qs, qe, u["unk_id"]), o.tokenize_files(fo, qc, qs, qe, u["unk_id"])
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+# ---- gtars-scoring: count matrices ---------------------------------------------------------------------------
+@pytest.mark.parametrize("style", ["peaks", "overlap"])
+def test_score_matrix_vs_oracle(ctx, style):
+    from gtars_b200 import ffi
+    from oracle import oracle as orc
+    rng = np.random.default_rng(zlib.crc32(f"score-{style}".encode()))
+    n_chroms, n = 5, 6000
+    offs, s, e, v = _random_index(rng, n_chroms, n, style)
+    g, o = _both(ctx, "bits", offs, s, e, v)
+    sizes = [0, 4000, 1, 0, 9000, 2500, 0]
+    nf = sum(sizes)
+    fc, fs, fe = _random_queries(rng, n_chroms, nf)
+    fe = np.maximum(fe, fs + 6).astype(np.uint32)
+    fo = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    for mode in (ffi.SCORE_ATAC, ffi.SCORE_CHIP):
+        got = g.score_matrix(fo, fc, fs, fe, mode, n)
+        want = orc.score_matrix(o, fo, fc, fs, fe, mode, n)
+        assert got.dtype == np.uint32 and got.shape == (len(sizes), n)
+        assert np.array_equal(got, want), mode
+        assert int(got.sum()) > 0
+    # fewer columns than vals: out-of-range peaks are dropped exactly like CountMatrix::increment
+    got = g.score_matrix(fo, fc, fs, fe, ffi.SCORE_CHIP, n // 2)
+    assert np.array_equal(got, orc.score_matrix(o, fo, fc, fs, fe, orc.SCORE_CHIP, n // 2))
+    # fragments shorter than the shifts wrap in u32 like the reference's release build: still identical
+    fe2 = (fs + rng.integers(0, 12, nf)).astype(np.uint32)
+    assert np.array_equal(g.score_matrix(fo, fc, fs, fe2, ffi.SCORE_ATAC, n), orc.score_matrix(o, fo, fc, fs, fe2, orc.SCORE_ATAC, n))
+    # no fragments at all
+    z = np.zeros(3, np.uint64)
+    assert g.score_matrix(z, fc[:0], fs[:0], fe[:0], ffi.SCORE_ATAC, n).sum() == 0
+
+
+def test_score_barcodes_vs_oracle(ctx):
+    from oracle import oracle as orc
+    rng = np.random.default_rng(77)
+    n_chroms, n = 4, 5000
+    offs, s, e, v = _random_index(rng, n_chroms, n, "overlap")
+    g, o = _both(ctx, "bits", offs, s, e, v)
+    nf, n_bc = 30_000, 700
+    fc, fs, fe = _random_queries(rng, n_chroms, nf)
+    bc = (rng.integers(0, n_bc, nf) ** 2 // n_bc).astype(np.uint32)  # skewed, some barcodes empty
+    g_off, g_pk, g_ct = g.score_barcodes(fc, fs, fe, bc, n_bc)
+    o_off, o_pk, o_ct = orc.score_barcodes(o, fc, fs, fe, bc, n_bc)
+    assert np.array_equal(g_off, o_off)
+    assert np.array_equal(g_pk, o_pk)
+    assert np.array_equal(g_ct, o_ct)
+    assert int(g_ct.sum()) == int(o.count(fc, fs, fe).sum())
+    # empty input / input without a single hit
+    off, pk, ct = g.score_barcodes(fc[:0], fs[:0], fe[:0], bc[:0], 5)
+    assert list(off) == [0] * 6 and len(pk) == 0 and len(ct) == 0
+    none = np.full(10, 0xFFFFFFFF, np.uint32)
+    off, pk, ct = g.score_barcodes(none, fs[:10], fe[:10], bc[:10] % 5, 5)
+    assert list(off) == [0] * 6 and len(pk) == 0
