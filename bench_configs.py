@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Secondary measurements for BASELINE.json configs C3 / C4 / C5 (bench.py is the contract benchmark for C2).
+"""Secondary measurements for BASELINE.json configs C3 / C4 / C5 and the scoring matrix (bench.py is the contract
+benchmark for C2).
 
 One JSON line per config: device-resident kernel throughput (CUDA events on the launching stream), algorithmic bytes,
 fraction of the measured HBM peak, and a bit-exact spot check against the CPU oracle on a sample.
@@ -21,7 +22,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="c3,c4,c5")
+    ap.add_argument("--configs", default="c3,c4,c5,score")
     ap.add_argument("--scale", type=float, default=0.2)
     ap.add_argument("--steps", type=int, default=5)
     args = ap.parse_args()
@@ -134,6 +135,37 @@ def main():
                        seconds_first_call=t1 - t0, seconds_warm_call=t2 - t1, value=n / (t2 - t1), unit="fragments/s (end to end)",
                        parity_sample_vs_oracle=ok,
                        note="end-to-end through gtgpu_tokenize_fragments incl. H2D/D2H; group-by uses the hand-written radix sort + scan of sort.cu")
+        elif cfg == "score":
+            # gtars-scoring region_scoring_from_fragments, ATAC mode: 8 pseudo-bulk fragment files vs the 1 M-peak
+            # consensus (dense u32 [8 x 1 M] matrix); every fragment is two lookups, one of them a reversed interval
+            n_files, per_file = 8, int(25_000_000 * args.scale)
+            u = synth.make_universe(1_000_000, device=dev)
+            offs = u["chrom_offsets"].cpu().numpy().astype(np.uint64)
+            s, e, v = (u32(u[k]) for k in ("g_start", "g_end", "g_val"))
+            ix = ffi.Index(ctx, ffi.KIND_BITS, offs, s, e, v)
+            q = synth.make_query_files(u, n_files, per_file, seed=synth.SEED_FRAGMENTS, device=dev, sort_files=False)
+            n = n_files * per_file
+            n_cols = int(u["n"])
+            d_mat = torch.zeros(n_files * n_cols, dtype=torch.int32, device=dev)
+            fo = q["file_offsets"]
+            fn = lambda: ix.score_matrix_dev(n_files, fo.data_ptr(), n, q["chr"].data_ptr(), q["start"].data_ptr(),
+                                             q["end"].data_ptr(), ffi.SCORE_ATAC, n_cols, d_mat.data_ptr())
+            ms, kms = timed(fn)
+            m = min(per_file, 100_000)  # oracle on the head of the first two files
+            sub_fo = np.array([0, m, 2 * m], dtype=np.uint64)
+            sel = torch.cat([torch.arange(m, device=dev), per_file + torch.arange(m, device=dev)])
+            sc, ss, se = (u32(q[k][sel]) for k in ("chr", "start", "end"))
+            ref = orc.score_matrix(orc.Index(orc.BITS, offs, s, e, v), sub_fo, sc, ss, se, orc.SCORE_ATAC, n_cols, threads=orc.max_threads())
+            got = ix.score_matrix(sub_fo, sc, ss, se, ffi.SCORE_ATAC, n_cols)
+            ok = bool(np.array_equal(got, ref))
+            hits = int(d_mat.sum().item())
+            algo = 12 * n + 4 * n_files * n_cols
+            out = dict(config="scoring: ATAC count matrix (gtars-scoring)", fragment_files=n_files, fragments=n, peaks=n_cols,
+                       lookups=2 * n, matrix_increments=hits, ms_per_step=ms, fused_find_ms=kms, value=n / (ms * 1e-3),
+                       unit="fragments/s", algorithmic_bytes=algo, roofline_frac=algo / (ms * 1e-3) / 1e9 / peak,
+                       parity_sample_vs_oracle=ok,
+                       note="device-resident; step = query expansion + fused find (reversed end intervals take the walk) + "
+                            "(file, peak) histogram with 32-bit atomics")
         else:
             continue
         out["setup_seconds"] = time.time() - t_setup

@@ -583,8 +583,13 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     uint2 cb;
                     if (chrom_cached) cb = s_chrom[min(c, (uint32_t)CHROM_CACHE - 1)];
                     else cb = c < nchr ? __ldg(reinterpret_cast<const uint2*>(ix.chrom_bt + c)) : make_uint2(0, 0);
-                    const uint32_t b1 = s >> shift, b2 = (e - 1) >> shift;
-                    if ((cb.y == BT_GENERIC_CHROM) | (s >= e) | (b2 - b1 > 1)) cur.slow |= 1u << k;
+                    // Record path: the query starts in bin b1 and its last position e-1 lies inside window b1.  That also
+                    // admits empty and REVERSED queries (e <= s, as gtars-scoring builds them) whose e is past the window
+                    // base: a hit needs start < e <= s < end, so it contains position s, touches bin b1 and is listed in
+                    // the window; the window-relative comparison below is then exact for them too.
+                    const uint32_t b1 = s >> shift;
+                    const uint32_t d = e - 1u - (b1 << shift);  // wraps to a huge value when e-1 is before the window
+                    if ((cb.y == BT_GENERIC_CHROM) | (e == 0u) | (d >= (2u << shift))) cur.slow |= 1u << k;
                     const uint32_t li = b1 < (cb.y & BT_NBINS_MASK) ? cb.x + b1 : 0u;  // record 0 is the empty sentinel
                     r[k] = ldg128_keep(ix.bt_rec + (size_t)li * 4, keep);
                 }
