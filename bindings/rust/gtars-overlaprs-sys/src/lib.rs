@@ -50,6 +50,14 @@ extern "C" {
     pub fn gtgpu_tokenize_fragments(index: *mut gtgpu_index, n: u64, chr: *const u32, start: *const u32, end: *const u32,
                                     barcode_id: *const u32, n_barcodes: u32, unk_id: u32, out_barcode_offsets: *mut u64,
                                     out_ids: *mut *mut gtgpu_buf) -> i32;
+    pub fn gtgpu_score_matrix(index: *mut gtgpu_index, n_files: u64, file_offsets: *const u64, n: u64, chr: *const u32,
+                              start: *const u32, end: *const u32, mode: i32, n_cols: u64, out_counts: *mut u32) -> i32;
+    pub fn gtgpu_score_matrix_dev(index: *mut gtgpu_index, n_files: u64, d_file_offsets: *const u64, n: u64,
+                                  d_chr: *const u32, d_start: *const u32, d_end: *const u32, mode: i32, n_cols: u64,
+                                  d_out_counts: *mut u32) -> i32;
+    pub fn gtgpu_score_barcodes(index: *mut gtgpu_index, n: u64, chr: *const u32, start: *const u32, end: *const u32,
+                                barcode_id: *const u32, n_barcodes: u32, out_barcode_offsets: *mut u64,
+                                out_peaks: *mut *mut gtgpu_buf, out_counts: *mut *mut gtgpu_buf) -> i32;
     pub fn gtgpu_igd_build(ctx: *mut gtgpu_ctx, n_files: u64, file_offsets: *const u64, n_chroms: u32, chr: *const u32,
                            start: *const u32, end: *const u32, out_igd: *mut *mut gtgpu_igd) -> i32;
     pub fn gtgpu_igd_free(igd: *mut gtgpu_igd) -> i32;
