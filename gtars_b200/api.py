@@ -57,6 +57,7 @@ def lib():
             "gth_tokenizer_fragments": (vp, [vp, cp]),
             "gth_igd_single": (vp, [vp, vp]), "gth_igd_find_pairs": (vp, [vp, vp, i32]),
             "gth_igd_count_per_query": (vp, [vp, vp, i32]),
+            "gth_igd_save_sets": (C.c_int, [u64, vp, vp, cp]), "gth_igd_from_file": (vp, [vp, cp]),
             "gth_igd_new": (vp, [vp, u64, vp]), "gth_igd_free": (None, [vp]), "gth_igd_num_files": (u64, [vp]),
             "gth_igd_count": (C.c_int, [vp, u64, vp, i32, C.c_int, vp]),
             "gth_lola_contingency": (C.c_int, [vp, u64, vp, vp, i32, vp]),
@@ -416,6 +417,24 @@ class Igd:
         if getattr(self, "_h", None):
             lib().gth_igd_free(self._h)
             self._h = None
+
+    def save(self, path, names=None):
+        """Igd::save (igd.rs:418-486): `path` (.igd) plus the companion .tsv, byte-for-byte the reference's files."""
+        names = list(names) if names is not None else [f"set{i}" for i in range(len(self._sets))]
+        arr = (C.c_void_p * max(len(self._sets), 1))(*[s._h for s in self._sets])
+        nm = (C.c_char_p * max(len(names), 1))(*[n.encode() for n in names])
+        if lib().gth_igd_save_sets(len(self._sets), arr, nm, os.fsencode(path)):
+            _fail()
+
+    @classmethod
+    def from_igd_file(cls, path):
+        """Igd::from_igd_file (igd.rs:320-414): an existing .igd database straight into the device layout."""
+        obj = cls.__new__(cls)
+        obj._sets = []
+        obj._h = lib().gth_igd_from_file(device(), os.fsencode(path))
+        if not obj._h:
+            _fail()
+        return obj
 
     @classmethod
     def from_single_region_set(cls, subject):

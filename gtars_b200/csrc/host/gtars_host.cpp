@@ -5,6 +5,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <array>
 #include <cstring>
 #include <fstream>
 #include <set>
@@ -679,6 +680,152 @@ std::vector<uint64_t> Igd::count_region_hits_batch(const std::vector<const Regio
     check(fn(igd_, sets.size(), set_offsets.data(), q.chr.data(), q.start.data(), q.end.data(), min_overlap, out.data()),
           pairwise ? "gtgpu_igd_count_set_overlaps" : "gtgpu_igd_count_region_hits");
     return out;
+}
+
+// ---- .igd files ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct IgdRec {
+    int32_t file_idx, start, end, value;
+};
+void put_i32(std::string& b, int32_t v) {
+    const unsigned char c[4] = {(unsigned char)v, (unsigned char)(v >> 8), (unsigned char)(v >> 16), (unsigned char)(v >> 24)};
+    b.append((const char*)c, 4);
+}
+std::string with_extension(const std::string& path, const std::string& ext) {  // Path::with_extension
+    size_t slash = path.find_last_of('/');
+    size_t dot = path.find_last_of('.');
+    std::string stem = (dot == std::string::npos || (slash != std::string::npos && dot < slash) || dot == slash + 1) ? path : path.substr(0, dot);
+    return stem + "." + ext;
+}
+}  // namespace
+
+void Igd::save_named_region_sets(const std::vector<std::pair<std::string, const RegionSet*>>& sets, const std::string& path, int32_t nbp) {
+    // from_named_region_sets (igd.rs:285-317) + add (:109-153) + finalize (:157-167) + save (:418-486)
+    std::vector<std::string> names;                       // contigs in creation order
+    std::unordered_map<std::string, size_t> chrom_index;
+    std::vector<std::vector<std::vector<IgdRec>>> contigs;  // [contig][tile][record]
+    std::string tsv = "Index\tFile\tNumber of Regions\tAvg size\n";
+    for (size_t f = 0; f < sets.size(); ++f) {
+        uint32_t count = 0;
+        uint64_t total_width = 0;
+        for (const Region& r : sets[f].second->regions) {
+            if (!(r.start < r.end)) continue;
+            const int32_t start = (int32_t)r.start, end = (int32_t)r.end;  // `as i32` casts (:295-296)
+            count += 1;
+            total_width += (uint64_t)(int64_t)(end - start);
+            if (start < 0 || end < 0 || start >= end) continue;  // Igd::add skips these silently
+            auto it = chrom_index.find(r.chr);
+            if (it == chrom_index.end()) {
+                it = chrom_index.emplace(r.chr, contigs.size()).first;
+                names.push_back(r.chr);
+                contigs.emplace_back();
+            }
+            auto& tiles = contigs[it->second];
+            const int32_t n1 = start / nbp, n2 = (end - 1) / nbp;
+            if (tiles.size() < (size_t)(n2 + 1)) tiles.resize((size_t)(n2 + 1));
+            for (int32_t i = n1; i <= n2; ++i) tiles[i].push_back(IgdRec{(int32_t)f, start, end, 0});
+        }
+        char buf[64];
+        snprintf(buf, sizeof buf, "%.2f", count ? (double)total_width / (double)count : 0.0);
+        tsv += std::to_string(f) + "\t" + sets[f].first + "\t" + std::to_string(count) + "\t" + buf + "\n";
+    }
+    std::string b;
+    put_i32(b, nbp);
+    put_i32(b, 1);  // gType 1: 16-byte records
+    put_i32(b, (int32_t)contigs.size());
+    for (auto& tiles : contigs) put_i32(b, (int32_t)tiles.size());
+    for (auto& tiles : contigs)
+        for (auto& t : tiles) {
+            std::stable_sort(t.begin(), t.end(), [](const IgdRec& a, const IgdRec& c) { return a.start < c.start; });
+            put_i32(b, (int32_t)t.size());
+        }
+    for (const auto& nm : names) {
+        std::string padded = nm;
+        padded.resize(40, '\0');
+        b += padded;
+    }
+    for (auto& tiles : contigs)
+        for (auto& t : tiles)
+            for (const IgdRec& r : t) { put_i32(b, r.file_idx); put_i32(b, r.start); put_i32(b, r.end); put_i32(b, r.value); }
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw Error("cannot write " + path);
+    f.write(b.data(), (std::streamsize)b.size());
+    std::ofstream t(with_extension(path, "tsv"), std::ios::binary);
+    if (!t) throw Error("cannot write " + with_extension(path, "tsv"));
+    t << tsv;
+}
+
+std::unique_ptr<Igd> Igd::from_igd_file(std::shared_ptr<Device> dev, const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw Error("Failed to open file: " + path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string d = ss.str();
+    size_t pos = 0;
+    auto rd = [&]() -> int32_t {
+        if (pos + 4 > d.size()) throw Error("truncated .igd file: " + path);
+        const unsigned char* c = (const unsigned char*)d.data() + pos;
+        pos += 4;
+        return (int32_t)((uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24));
+    };
+    const int32_t nbp = rd(), g_type = rd(), n_ctg = rd();
+    if (nbp <= 0 || n_ctg < 0) throw Error("not an .igd file: " + path);
+    std::vector<int32_t> n_tiles((size_t)n_ctg);
+    for (auto& x : n_tiles) x = rd();
+    std::vector<std::vector<int32_t>> n_cnt((size_t)n_ctg);
+    for (int32_t i = 0; i < n_ctg; ++i) {
+        if (n_tiles[i] < 0) throw Error("not an .igd file: " + path);
+        n_cnt[i].resize((size_t)n_tiles[i]);
+        for (auto& x : n_cnt[i]) x = rd();
+    }
+    std::unique_ptr<Igd> g(new Igd());
+    g->dev_ = dev;
+    for (int32_t i = 0; i < n_ctg; ++i) {
+        if (pos + 40 > d.size()) throw Error("truncated .igd file: " + path);
+        std::string nm = d.substr(pos, 40);
+        pos += 40;
+        while (!nm.empty() && nm.back() == '\0') nm.pop_back();
+        while (!nm.empty() && nm.front() == '\0') nm.erase(nm.begin());
+        g->cmap_.add(nm);
+    }
+    // records: an interval sits in every tile it spans; its copy in the tile of its start is the one kept
+    std::vector<std::vector<std::array<uint32_t, 3>>> per_file;
+    for (int32_t i = 0; i < n_ctg; ++i)
+        for (int32_t j = 0; j < n_tiles[i]; ++j)
+            for (int32_t k = 0; k < n_cnt[i][j]; ++k) {
+                const int32_t idx = rd(), start = rd(), end = rd();
+                if (g_type != 0) rd();
+                if (idx < 0 || start < 0 || start / nbp != j) continue;
+                if ((size_t)idx >= per_file.size()) per_file.resize((size_t)idx + 1);
+                per_file[idx].push_back({(uint32_t)i, (uint32_t)start, (uint32_t)end});
+            }
+    size_t n_files = per_file.size();
+    {   // companion .tsv (igd.rs:870-893): one line per file after the header
+        std::ifstream t(with_extension(path, "tsv"));
+        if (t) {
+            std::string line;
+            size_t lines = 0, rows = 0;
+            while (std::getline(t, line))
+                if (lines++ > 0 && std::count(line.begin(), line.end(), '\t') >= 3) ++rows;
+            n_files = std::max(n_files, rows);
+        }
+    }
+    per_file.resize(n_files);
+    g->n_files_ = n_files;
+    std::vector<uint64_t> file_offsets(n_files + 1, 0);
+    FlatQueries r;
+    for (size_t fidx = 0; fidx < n_files; ++fidx) {
+        for (const auto& rec : per_file[fidx]) {
+            r.chr.push_back(rec[0]);
+            r.start.push_back(rec[1]);
+            r.end.push_back(rec[2]);
+        }
+        file_offsets[fidx + 1] = r.chr.size();
+    }
+    check(gtgpu_igd_build(dev->ctx(), n_files, file_offsets.data(), (uint32_t)g->cmap_.size(), r.chr.data(), r.start.data(), r.end.data(),
+                          &g->igd_),
+          "gtgpu_igd_build");
+    return g;
 }
 
 std::unique_ptr<Igd> Igd::from_single_region_set(std::shared_ptr<Device> dev, const RegionSet& subject) {

@@ -231,6 +231,15 @@ class Igd {
     // Many query sets in one device pass: row-major [n_sets x n_files].
     std::vector<uint64_t> count_region_hits_batch(const std::vector<const RegionSet*>& sets, int32_t min_overlap, bool pairwise) const;
 
+    // .igd on-disk format (igd.rs:320-486; header nbp, gType, nCtg; tiles per contig; records per tile; 40-byte
+    // names; 16-byte LE records).  save_named_region_sets = from_named_region_sets + save: byte-for-byte the file
+    // (and companion .tsv) the reference writes.  from_igd_file loads such a file straight into the device layout
+    // (the tile copies of an interval collapse to one record: the closed-form count does not need tiles); the
+    // number of files is taken from the companion .tsv when it exists, else from the largest file index.
+    static void save_named_region_sets(const std::vector<std::pair<std::string, const RegionSet*>>& sets, const std::string& path,
+                                       int32_t nbp = 16384);
+    static std::unique_ptr<Igd> from_igd_file(std::shared_ptr<Device> dev, const std::string& path);
+
     // Igd::from_single_region_set (igd.rs:609-634): two-set overlap queries; the subject index is kept per record.
     static std::unique_ptr<Igd> from_single_region_set(std::shared_ptr<Device> dev, const RegionSet& subject);
     // igd.rs:645-678: (query idx, subject idx) pairs, one per overlapping pair, sorted.

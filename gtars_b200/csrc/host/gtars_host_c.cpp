@@ -228,6 +228,17 @@ void* gth_igd_count_per_query(void* g, void* query, int32_t min_overlap) {
         return l;
     }, nullptr);
 }
+int gth_igd_save_sets(uint64_t n, void** region_sets, const char** names, const char* path) {
+    return guard([&]() -> int {
+        std::vector<std::pair<std::string, const RegionSet*>> sets;
+        for (uint64_t i = 0; i < n; ++i) sets.emplace_back(names[i], (const RegionSet*)region_sets[i]);
+        Igd::save_named_region_sets(sets, path);
+        return 0;
+    }, 1);
+}
+void* gth_igd_from_file(void* dev, const char* path) {
+    return guard([&]() -> void* { return Igd::from_igd_file(*(std::shared_ptr<Device>*)dev, path).release(); }, nullptr);
+}
 void gth_igd_free(void* g) { delete (Igd*)g; }
 uint64_t gth_igd_num_files(void* g) { return ((Igd*)g)->num_files(); }
 int gth_igd_count(void* g, uint64_t n_sets, void** region_sets, int32_t min_overlap, int pairwise, uint64_t* out) {

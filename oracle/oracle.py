@@ -65,6 +65,11 @@ def lib():
         "orc_consensus_free": (None, [vp]),
         "orc_consensus_len": (u64, [vp]),
         "orc_region_scoring_files": (cint, [vp, u64, vp, cint, vp]),
+        "orc_igd_save": (cint, [vp, u64, vp, C.c_char_p]),
+        "orc_igd_from_file": (vp, [C.c_char_p]),
+        "orc_igd_n_contigs": (u64, [vp]),
+        "orc_igd_contig_name": (C.c_char_p, [vp, u64]),
+        "orc_igd_n_files": (u64, [vp]),
         "orc_regionset_from_file": (vp, [C.c_char_p]),
         "orc_regionset_free": (None, [vp]),
         "orc_regionset_len": (u64, [vp]),
@@ -349,6 +354,25 @@ class Igd:
         if getattr(self, "_h", None):
             lib().orc_igd_free(self._h)
             self._h = None
+
+    def save(self, path, names_by_chr_id):
+        """Igd::save (igd.rs:418-486), the .igd file only; contig i is named names_by_chr_id[chr id]."""
+        arr = (C.c_char_p * max(len(names_by_chr_id), 1))(*[n.encode() for n in names_by_chr_id])
+        if lib().orc_igd_save(self._h, len(names_by_chr_id), arr, os.fsencode(path)) != 0:
+            raise ValueError(_err())
+
+    @classmethod
+    def from_igd_file(cls, path):
+        """Igd::from_igd_file (igd.rs:320-414): dense chromosome id = contig index; .contig_names lists them."""
+        L = lib()
+        h = L.orc_igd_from_file(os.fsencode(path))
+        if not h:
+            raise ValueError(_err())
+        self = cls.__new__(cls)
+        self._h = h
+        self.n_files = int(L.orc_igd_n_files(h))
+        self.contig_names = [L.orc_igd_contig_name(h, i).decode() for i in range(L.orc_igd_n_contigs(h))]
+        return self
 
     def add(self, chr, start, end, value, file_idx):
         lib().orc_igd_add(self._h, chr, start, end, value, file_idx)

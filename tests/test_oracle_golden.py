@@ -325,3 +325,33 @@ def test_scoring_dense_vs_bruteforce():
         for k in range(int(off[b]), int(off[b + 1])):
             got[(b, int(pk[k]))] = int(ct[k])
     assert got == want and int(off[-1]) == len(want)
+
+
+def test_igd_file_format_roundtrip(tmp_path):
+    """.igd layout (igd.rs:418-486) and loader (:320-414): sizes follow from the header, contigs come in creation
+    order, a multi-tile interval is stored once per tile, and the loaded database answers like the original."""
+    import struct
+    g = orc.Igd()
+    recs = [(1, 100, 200, 0), (0, 16000, 17000, 1), (1, 50, 60, 1), (1, 40000, 40010, 0), (0, 5, 6, 2), (2, -5, 10, 0), (2, 7, 7, 0)]
+    for c, s, e, f in recs:
+        g.add(c, s, e, 0, f)
+    g.finalize()
+    p = str(tmp_path / "t.igd")
+    g.save(p, ["chrA", "chrB", "chrC"])
+    b = open(p, "rb").read()
+    nbp, g_type, n_ctg = struct.unpack("<3i", b[:12])
+    assert (nbp, g_type, n_ctg) == (16384, 1, 2)            # chrC never got a valid record
+    n_tiles = struct.unpack("<2i", b[12:20])
+    assert n_tiles == (3, 2)                                 # creation order: chrB (tiles 0..2), then chrA (0..1)
+    cnt = struct.unpack("<5i", b[20:40])
+    assert cnt == (2, 0, 1, 2, 1)                            # 16000-17000 spans tiles 0 and 1 of chrA
+    assert b[40:44] == b"chrB" and b[80:84] == b"chrA" and len(b) == 40 + 80 + 16 * sum(cnt)
+    first = struct.unpack("<4i", b[120:136])
+    assert first == (1, 50, 60, 0)                           # tile records are sorted by start
+    h = orc.Igd.from_igd_file(p)
+    assert h.contig_names == ["chrB", "chrA"] and h.n_files == 3
+    for (c_old, c_new) in ((1, 0), (0, 1)):
+        for q in ((0, 70000), (55, 150), (16383, 16385), (16500, 16600), (5, 6)):
+            a = g.count_overlaps(c_old, q[0], q[1])
+            bb = h.count_overlaps(c_new, q[0], q[1])
+            assert a[0] == bb[0] and list(a[1]) == list(bb[1])
