@@ -54,7 +54,9 @@ def lib():
             "gth_tokenizer_vocab_size": (u64, [vp]), "gth_tokenizer_token_to_id": (i64, [vp, cp]),
             "gth_tokenizer_id_to_token": (cp, [vp, u32]), "gth_tokenizer_special": (cp, [vp, C.c_int]),
             "gth_tokenizer_kind": (C.c_int, [vp]), "gth_tokenizer_encode_batch": (vp, [vp, u64, vp]),
-            "gth_tokenizer_fragments": (vp, [vp, cp]),
+            "gth_tokenizer_fragments": (vp, [vp, cp]), "gth_tokenizer_encode_bed_file": (vp, [vp, cp]),
+            "gth_parse_bed_file": (vp, [vp, cp, u64, vp]), "gth_gtok_write": (C.c_int, [cp, u64, vp, C.c_int]),
+            "gth_gtok_read": (vp, [cp]),
             "gth_igd_single": (vp, [vp, vp]), "gth_igd_find_pairs": (vp, [vp, vp, i32]),
             "gth_igd_count_per_query": (vp, [vp, vp, i32]),
             "gth_igd_save_sets": (C.c_int, [u64, vp, vp, cp]), "gth_igd_from_file": (vp, [vp, cp]),
@@ -218,6 +220,37 @@ class MultiChromOverlapper:
         return RegionSet._wrap(h)
 
 
+def parse_bed_file(path, chrom_names):
+    """RegionSet::try_from's parse + sort run on the device: (chr ids, starts, ends) as uint32 arrays, ids index
+    `chrom_names` (0xFFFFFFFF = a name that is not listed; those regions sort last)."""
+    names = [n.encode() for n in chrom_names]
+    arr = (C.c_char_p * max(len(names), 1))(*names)
+    c, s, e = _take_lists(lib().gth_parse_bed_file(device(), os.fsencode(path), len(names), arr))
+    return np.asarray(c, dtype=np.uint32), np.asarray(s, dtype=np.uint32), np.asarray(e, dtype=np.uint32)
+
+
+def write_tokens_to_gtok(path, tokens):
+    """gtars_io::write_tokens_to_gtok (gtok.rs:126-163)."""
+    a = np.ascontiguousarray(tokens, dtype=np.uint32)
+    if lib().gth_gtok_write(os.fsencode(path), len(a), a.ctypes.data, 0):
+        _fail()
+
+
+def append_tokens_to_gtok_file(path, tokens):
+    a = np.ascontiguousarray(tokens, dtype=np.uint32)
+    if lib().gth_gtok_write(os.fsencode(path), len(a), a.ctypes.data, 1):
+        _fail()
+
+
+def init_gtok_file(path):
+    if lib().gth_gtok_write(os.fsencode(path), 0, None, 2):
+        _fail()
+
+
+def read_tokens_from_gtok(path):
+    return _take_lists(lib().gth_gtok_read(os.fsencode(path)))[0]
+
+
 class IndexedRegionSet:
     """gtars_overlaprs::IndexedRegionSet (indexed_region_set.rs): a RegionSet with its overlap index."""
 
@@ -371,6 +404,10 @@ class Tokenizer:
             else:
                 out.append(r)
         return RegionSet(out)
+
+    def encode_bed_file(self, path):
+        """encode(RegionSet(path)) with the BED text parsed, sorted and tokenized on the device."""
+        return _take_lists(lib().gth_tokenizer_encode_bed_file(self._h, os.fsencode(path)))[0]
 
     def encode_batch(self, batches):
         """One Tokenizer::encode per element, all resolved in a single device pass."""

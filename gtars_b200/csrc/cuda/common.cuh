@@ -217,6 +217,12 @@ int32_t launch_unk_expand(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* d_ra
                           const uint64_t* d_out_file_tok, const uint32_t* d_raw_ids, uint32_t unk_id,
                           uint32_t* d_out_ids);
 
+// scoring.cu: fused find over device-resident queries with the optimistic-capacity + exact re-run protocol; the raw
+// ids land in scratch SC_OUT_IDS (*d_ids), *total_out is their number.  d_offsets / d_file_tok may be null.
+int32_t fused_find_all(gtgpu_index* ix, uint64_t nq, uint64_t n_files, const uint64_t* d_qfo, const uint32_t* d_qc,
+                       const uint32_t* d_qs, const uint32_t* d_qe, uint64_t* d_offsets, uint64_t* d_file_tok,
+                       uint32_t** d_ids, uint64_t* total_out);
+
 // sort.cu — hand-written scan / radix sort
 size_t exclusive_scan_temp_bytes(uint64_t n, size_t elem);
 template <typename T>

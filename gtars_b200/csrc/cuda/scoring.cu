@@ -111,7 +111,7 @@ static int bits_for(uint64_t n_values) {
 
 // Shared front end: fused find over device-resident queries with the optimistic capacity + exact re-run protocol.
 // Returns the raw ids in SC_OUT_IDS (*d_ids) and their number.
-static int32_t find_all(gtgpu_index* ix, uint64_t nq, uint64_t n_files, const uint64_t* d_qfo, const uint32_t* d_qc,
+int32_t fused_find_all(gtgpu_index* ix, uint64_t nq, uint64_t n_files, const uint64_t* d_qfo, const uint32_t* d_qc,
                         const uint32_t* d_qs, const uint32_t* d_qe, uint64_t* d_offsets, uint64_t* d_file_tok,
                         uint32_t** d_ids, uint64_t* total_out) {
     gtgpu_ctx* ctx = ix->ctx;
@@ -167,7 +167,7 @@ static int32_t score_matrix_dev_locked(gtgpu_index* ix, uint64_t n_files, const 
     GT_TRY(ctx->scratch_get(SC_FILE_TOK, (n_files + 1) * 8, (void**)&d_file_tok));
     uint32_t* d_ids = nullptr;
     uint64_t total = 0;
-    GT_TRY(find_all(ix, nq, n_files, qfo, qc, qs, qe, nullptr, d_file_tok, &d_ids, &total));
+    GT_TRY(fused_find_all(ix, nq, n_files, qfo, qc, qs, qe, nullptr, d_file_tok, &d_ids, &total));
     if (total) {
         score_hist_kernel<<<grid_for(ctx, total), 256, 0, st>>>(total, d_ids, n_files, d_file_tok, n_cols, d_out_counts);
         ctx->launches++;
@@ -252,7 +252,7 @@ extern "C" int32_t gtgpu_score_barcodes(gtgpu_index* ix, uint64_t n, const uint3
         GT_CUDA(cudaMemcpyAsync(d_end, end, n * 4, cudaMemcpyHostToDevice, st));
         GT_CUDA(cudaMemcpyAsync(d_bc, barcode_id, n * 4, cudaMemcpyHostToDevice, st));
         uint32_t* d_ids = nullptr;
-        GT_TRY(find_all(ix, n, 0, nullptr, d_chr, d_start, d_end, d_off, nullptr, &d_ids, &total));
+        GT_TRY(fused_find_all(ix, n, 0, nullptr, d_chr, d_start, d_end, d_off, nullptr, &d_ids, &total));
         if (total >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "score_barcodes: more than 2^32-2 hits per call");
         if (total) {
             uint32_t *d_hbc, *d_k2, *d_v2;

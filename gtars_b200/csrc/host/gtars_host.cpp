@@ -22,22 +22,7 @@ void check(int32_t status, const char* what) {
 
 // get_dynamic_reader (gtars-core/src/utils.rs:115-126): gzip iff the extension is "gz"; BufRead::lines() semantics.
 std::vector<std::string> read_lines(const std::string& path) {
-    std::string data;
-    const bool gz = path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0;
-    if (gz) {
-        gzFile f = gzopen(path.c_str(), "rb");
-        if (!f) throw Error("Failed to open file: \"" + path + "\"");
-        char buf[1 << 16];
-        int n;
-        while ((n = gzread(f, buf, sizeof buf)) > 0) data.append(buf, n);
-        gzclose(f);
-    } else {
-        std::ifstream f(path, std::ios::binary);
-        if (!f) throw Error("Failed to open file: \"" + path + "\"");
-        std::stringstream ss;
-        ss << f.rdbuf();
-        data = ss.str();
-    }
+    const std::string data = gtars::read_file_bytes(path);
     std::vector<std::string> lines;
     size_t pos = 0;
     while (pos < data.size()) {
@@ -107,6 +92,117 @@ struct PinnedResult {  // RAII over gtgpu_buf
 };
 
 }  // namespace
+
+std::string read_file_bytes(const std::string& path) {
+    std::string data;
+    const bool gz = path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0;
+    if (gz) {
+        gzFile f = gzopen(path.c_str(), "rb");
+        if (!f) throw Error("Failed to open file: \"" + path + "\"");
+        char buf[1 << 16];
+        int n;
+        while ((n = gzread(f, buf, sizeof buf)) > 0) data.append(buf, n);
+        gzclose(f);
+    } else {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw Error("Failed to open file: \"" + path + "\"");
+        std::stringstream ss;
+        ss << f.rdbuf();
+        data = ss.str();
+    }
+    return data;
+}
+
+namespace {
+struct NameBlob {
+    std::string blob;
+    std::vector<uint32_t> offsets{0};
+    explicit NameBlob(const ChromMap& cmap) {
+        for (uint32_t i = 0; i < cmap.size(); ++i) {
+            blob += cmap.name(i);
+            offsets.push_back((uint32_t)blob.size());
+        }
+    }
+};
+}  // namespace
+
+FlatQueries parse_bed_text_device(const Device& dev, const std::string& text, const ChromMap& cmap) {
+    NameBlob nb(cmap);
+    uint64_t n = 0;
+    PinnedResult c, s, e;
+    check(gtgpu_parse_bed(dev.ctx(), text.data(), text.size(), (uint32_t)cmap.size(), nb.blob.data(), nb.offsets.data(), &n, &c.buf,
+                          &s.buf, &e.buf),
+          "gtgpu_parse_bed");
+    FlatQueries q;
+    q.chr.assign(c.data(), c.data() + n);
+    q.start.assign(s.data(), s.data() + n);
+    q.end.assign(e.data(), e.data() + n);
+    return q;
+}
+
+// ---- gtok ------------------------------------------------------------------------------------------------------------------
+namespace {
+void put_tokens(std::ofstream& f, const std::vector<uint32_t>& tokens, bool small) {
+    std::string b;
+    b.reserve(tokens.size() * (small ? 2 : 4));
+    for (uint32_t t : tokens) {
+        b.push_back((char)(t & 0xFF));
+        b.push_back((char)((t >> 8) & 0xFF));
+        if (!small) {
+            b.push_back((char)((t >> 16) & 0xFF));
+            b.push_back((char)((t >> 24) & 0xFF));
+        }
+    }
+    f.write(b.data(), (std::streamsize)b.size());
+}
+}  // namespace
+
+void write_tokens_to_gtok(const std::string& filename, const std::vector<uint32_t>& tokens) {
+    std::ofstream f(filename, std::ios::binary);
+    if (!f) throw Error("Failed to create gtok file!");
+    const bool small = std::all_of(tokens.begin(), tokens.end(), [](uint32_t x) { return x <= 0xFFFFu; });
+    f.write("GTOK", 4);
+    f.put(small ? (char)0x01 : (char)0x02);
+    put_tokens(f, tokens, small);
+}
+void init_gtok_file(const std::string& filename) {
+    std::ofstream f(filename, std::ios::binary);
+    if (!f) throw Error("Failed to create gtok file!");
+    f.write("GTOK", 4);
+    f.put((char)0x02);  // assume large (gtok.rs:238-240)
+}
+std::vector<uint32_t> read_tokens_from_gtok(const std::string& filename) {
+    std::ifstream f(filename, std::ios::binary);
+    if (!f) throw Error("Failed to open gtok file!");
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string d = ss.str();
+    if (d.size() < 5 || d.compare(0, 4, "GTOK") != 0) throw Error("File doesn't appear to be a valid .gtok file.");
+    const unsigned char flag = (unsigned char)d[4];
+    if (flag != 0x01 && flag != 0x02) throw Error("Invalid data format flag found in gtok file");
+    const size_t w = flag == 0x01 ? 2 : 4;
+    std::vector<uint32_t> tokens;
+    for (size_t pos = 5; pos + w <= d.size(); pos += w) {  // a trailing partial token is dropped, like read_exact failing
+        uint32_t v = 0;
+        for (size_t k = 0; k < w; ++k) v |= (uint32_t)(unsigned char)d[pos + k] << (8 * k);
+        tokens.push_back(v);
+    }
+    return tokens;
+}
+void append_tokens_to_gtok_file(const std::string& filename, const std::vector<uint32_t>& tokens) {
+    unsigned char flag;
+    {
+        std::ifstream f(filename, std::ios::binary);
+        if (!f) throw Error("Failed to open gtok file!");
+        char h[5];
+        if (!f.read(h, 5) || std::string(h, 4) != "GTOK") throw Error("File doesn't appear to be a valid .gtok file.");
+        flag = (unsigned char)h[4];
+    }
+    if (flag != 0x01 && flag != 0x02) throw Error("Invalid data format flag found in gtok file");
+    std::ofstream f(filename, std::ios::binary | std::ios::app);
+    if (!f) throw Error("Failed to open gtok file for appending");
+    put_tokens(f, tokens, flag == 0x01);  // tokens are truncated to u16 when the file says so (gtok.rs:278-284)
+}
 
 // ---- RegionSet ---------------------------------------------------------------------------------------------------------
 RegionSet RegionSet::from_file(const std::string& path) {
@@ -448,6 +544,16 @@ std::vector<std::vector<uint32_t>> Tokenizer::encode_batch(const std::vector<con
 }
 
 std::vector<uint32_t> Tokenizer::encode(const std::vector<Region>& regions) const { return encode_batch({&regions})[0]; }
+
+std::vector<uint32_t> Tokenizer::encode_bed_file(const std::string& path) const {
+    const std::string text = read_file_bytes(path);
+    NameBlob nb(cmap_);
+    PinnedResult ids;
+    check(gtgpu_tokenize_bed(index_, text.data(), text.size(), (uint32_t)cmap_.size(), nb.blob.data(), nb.offsets.data(), unk_id_,
+                             &ids.buf),
+          "gtgpu_tokenize_bed");
+    return std::vector<uint32_t>(ids.data(), ids.data() + ids.len());
+}
 
 std::vector<std::string> Tokenizer::tokenize(const std::vector<Region>& regions) const {
     std::vector<std::string> out;

@@ -79,6 +79,18 @@ struct FlatQueries {
 };
 FlatQueries flatten(const std::vector<Region>& regions, const ChromMap& cmap);
 
+// get_dynamic_reader (gtars-core/src/utils.rs:115-126): the whole file, gunzipped iff the extension is "gz".
+std::string read_file_bytes(const std::string& path);
+// RegionSet::try_from's parse + sort of BED text ON THE DEVICE (gtgpu_parse_bed): dense chromosome ids through `cmap`
+// (names it does not hold become GTGPU_UNKNOWN_CHROM and sort last), regions in the reference's sorted order.
+FlatQueries parse_bed_text_device(const Device& dev, const std::string& text, const ChromMap& cmap);
+
+// ---- gtars_io::gtok (gtok.rs:126-300): "GTOK", one flag byte (1 = u16 tokens, 2 = u32), little-endian tokens -----------------
+void write_tokens_to_gtok(const std::string& filename, const std::vector<uint32_t>& tokens);   // u16 iff every token fits
+std::vector<uint32_t> read_tokens_from_gtok(const std::string& filename);
+void init_gtok_file(const std::string& filename);                                              // header + u32 flag
+void append_tokens_to_gtok_file(const std::string& filename, const std::vector<uint32_t>& tokens);
+
 // ---- gtars_overlaprs::MultiChromOverlapper / IndexedRegionSet ------------------------------------------------------
 class MultiChromOverlapper {
    public:
@@ -186,6 +198,8 @@ class Tokenizer {
 
     std::vector<std::string> tokenize(const std::vector<Region>& regions) const;  // tokenizer.rs:140-163
     std::vector<uint32_t> encode(const std::vector<Region>& regions) const;       // tokenizer.rs:165-171
+    // encode(RegionSet::try_from(path)) with the file's text parsed, sorted and tokenized on the device (gtgpu_tokenize_bed).
+    std::vector<uint32_t> encode_bed_file(const std::string& path) const;
     // One encode() per region set, resolved in ONE device pass (the batch shape the GPU serves).
     std::vector<std::vector<uint32_t>> encode_batch(const std::vector<const std::vector<Region>*>& calls) const;
     std::vector<std::string> decode(const std::vector<uint32_t>& ids) const;      // tokenizer.rs:173-181

@@ -190,6 +190,40 @@ void* gth_tokenizer_encode_batch(void* t, uint64_t n, void** region_sets) {
         return l;
     }, nullptr);
 }
+void* gth_tokenizer_encode_bed_file(void* t, const char* path) {
+    return guard([&]() -> void* {
+        Lists* l = new Lists();
+        l->lists.push_back(((Tokenizer*)t)->encode_bed_file(path));
+        return l;
+    }, nullptr);
+}
+// BED text -> (chr ids, starts, ends) through the device parser; chromosome names in `names` (n of them) get ids 0..n-1
+void* gth_parse_bed_file(void* dev, const char* path, uint64_t n_names, const char** names) {
+    return guard([&]() -> void* {
+        ChromMap cmap;
+        for (uint64_t i = 0; i < n_names; ++i) cmap.add(names[i]);
+        FlatQueries q = parse_bed_text_device(**(std::shared_ptr<Device>*)dev, read_file_bytes(path), cmap);
+        Lists* l = new Lists();
+        l->lists = {std::move(q.chr), std::move(q.start), std::move(q.end)};
+        return l;
+    }, nullptr);
+}
+int gth_gtok_write(const char* path, uint64_t n, const uint32_t* tokens, int mode /*0 write, 1 append, 2 init*/) {
+    return guard([&]() -> int {
+        std::vector<uint32_t> v(tokens, tokens + n);
+        if (mode == 0) write_tokens_to_gtok(path, v);
+        else if (mode == 1) append_tokens_to_gtok_file(path, v);
+        else init_gtok_file(path);
+        return 0;
+    }, 1);
+}
+void* gth_gtok_read(const char* path) {
+    return guard([&]() -> void* {
+        Lists* l = new Lists();
+        l->lists.push_back(read_tokens_from_gtok(path));
+        return l;
+    }, nullptr);
+}
 void* gth_tokenizer_fragments(void* t, const char* path) {
     return guard([&]() -> void* {
         Lists* l = new Lists();

@@ -136,6 +136,22 @@ int32_t gtgpu_tokenize_fragments(gtgpu_index* index, uint64_t n, const uint32_t*
                                  const uint32_t* end, const uint32_t* barcode_id, uint32_t n_barcodes, uint32_t unk_id,
                                  uint64_t* out_barcode_offsets, gtgpu_buf** out_ids);
 
+/* ---- BED text ingest ----------------------------------------------------------------------------------------------------
+ * gtgpu_parse_bed replaces the parse + sort of RegionSet::try_from (gtars-core/src/models/region_set.rs:60-185,
+ * :502-505) for query files: `text` is the (decompressed) file, n_bytes < 4 GiB.  Lines are split on '\n' (a trailing
+ * '\r' is dropped); lines starting with "browser", "track" or "#" are skipped, and so is a first line whose second
+ * field is not a number; every other line needs three tab-separated fields with start and end accepted by Rust's
+ * str::parse::<u32>() — otherwise GTGPU_ERR_INVALID with the 1-based line number; no region at all is an error too
+ * (EmptyRegionSet).  Chromosome names are mapped through the caller's table (names back to back, name_offsets has
+ * n_names + 1 entries); a name that is not in it becomes GTGPU_UNKNOWN_CHROM.  Output: the regions in the reference's
+ * sorted order — stable, by chromosome STRING then start — with unknown names after all known ones (they cannot
+ * produce output).  gtgpu_tokenize_bed = parse + sort + Tokenizer::encode of that one file, text in, token ids out. */
+int32_t gtgpu_parse_bed(gtgpu_ctx* ctx, const char* text, uint64_t n_bytes, uint32_t n_names, const char* names,
+                        const uint32_t* name_offsets, uint64_t* out_n, gtgpu_buf** out_chr, gtgpu_buf** out_start,
+                        gtgpu_buf** out_end);
+int32_t gtgpu_tokenize_bed(gtgpu_index* index, const char* text, uint64_t n_bytes, uint32_t n_names, const char* names,
+                           const uint32_t* name_offsets, uint32_t unk_id, gtgpu_buf** out_ids);
+
 /* ---- gtars-scoring: fragments x consensus peaks ------------------------------------------------------------------------
  * gtgpu_score_matrix replaces region_scoring_from_fragments (gtars-scoring/src/fragment_scoring.rs:19-121) over
  * pre-parsed fragments: file f owns fragments [file_offsets[f], file_offsets[f+1]); the index is the ConsensusSet

@@ -259,6 +259,13 @@ KATS = {
              "any": [True, True, False]},
         ],
     },
+    # ---- K13: .gtok files shipped with the reference's test data (bytes as hex) ---------------------------------
+    "K13_gtok": {
+        "cite": "gtars-io/src/gtok.rs:126-210, consts.rs (GTOK header, 0x01 = u16, 0x02 = u32); tests/data/out/*.gtok",
+        "files": {name: {"hex": open(os.path.join(REF, "out", name), "rb").read().hex()}
+                  for name in ("tokens.gtok", "peaks.gtok", "to_tokenize.gtok")},
+        "tokens": {"tokens.gtok": [42, 101, 999], "peaks.gtok": list(range(25)), "to_tokenize.gtok": [22, 23, 24, 26]},
+    },
     # ---- derived vectors (NOT asserted by the reference; regression pins only) -------------------------
     "D_derived": {
         "D1": {"note": "to_tokenize.bed (sorted by RegionSet::try_from) vs peaks.bed", "universe": "tokenizers/peaks.bed",

@@ -49,3 +49,32 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in text.lower(), f"{os.path.join(dirpath, f)} mentions the oracle"
+
+
+def test_gtok_files_match_reference_bytes(golden, tmp_path):
+    """K13: the .gtok files under the reference's tests/data/out, byte for byte (gtars-io/src/gtok.rs:126-300).
+    Host-only code: runs without a GPU."""
+    from gtars_b200 import api
+    k = golden[1]["K13_gtok"]
+    for name, want in k["tokens"].items():
+        raw = bytes.fromhex(k["files"][name]["hex"])
+        p = str(tmp_path / name)
+        api.write_tokens_to_gtok(p, want)
+        assert open(p, "rb").read() == raw, name
+        open(p, "wb").write(raw)
+        assert api.read_tokens_from_gtok(p) == want
+    big = str(tmp_path / "big.gtok")
+    api.write_tokens_to_gtok(big, [1, 70000, 3])                     # one token above u16 -> u32 flag
+    assert open(big, "rb").read()[:5] == b"GTOK\x02" and api.read_tokens_from_gtok(big) == [1, 70000, 3]
+    api.init_gtok_file(big)
+    assert open(big, "rb").read() == b"GTOK\x02"
+    api.append_tokens_to_gtok_file(big, [5, 0x12345678])
+    assert api.read_tokens_from_gtok(big) == [5, 0x12345678]
+    small = str(tmp_path / "small.gtok")
+    api.write_tokens_to_gtok(small, [7])
+    api.append_tokens_to_gtok_file(small, [65537])                  # u16 file: appended tokens are truncated (gtok.rs:278-284)
+    assert api.read_tokens_from_gtok(small) == [7, 1]
+    bad = str(tmp_path / "bad.gtok")
+    open(bad, "wb").write(b"NOPE\x01\x00\x00")
+    with pytest.raises(api.GtarsError):
+        api.read_tokens_from_gtok(bad)

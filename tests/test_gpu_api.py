@@ -271,3 +271,89 @@ def test_igd_file_roundtrip(api, golden, fixture_dir, tmp_path):
     # and the oracle reading the file agrees with the device on a query set
     of = orc.Igd.from_igd_file(p)
     assert of.contig_names == list(chrom_ids) and of.n_files == len(sets)
+
+
+def _messy_bed(rng, names, n, sort=False, crlf=False, header=None, extra_cols=True):
+    rows = []
+    for _ in range(n):
+        c = names[rng.integers(0, len(names))]
+        s = int(rng.integers(0, 3_000_000))
+        e = s + int(rng.integers(0, 5000))
+        rows.append((c, s, e))
+    if sort:
+        rows.sort(key=lambda r: (r[0], r[1]))
+    lines = [header] if header else []
+    for i, (c, s, e) in enumerate(rows):
+        if i % 97 == 5:
+            lines.append("# a comment")
+        if i % 211 == 7:
+            lines.append("track name=x")
+        if i % 307 == 9:
+            lines.append("browser position chr1:1-2")
+        sfx = ""
+        if extra_cols and i % 3 == 0:
+            sfx = f"\tname{i}\t{i % 1000}\t+"
+        lines.append(f"{c}\t{'+' if i % 50 == 0 else ''}{s}\t{e}{sfx}")
+    nl = "\r\n" if crlf else "\n"
+    return nl.join(lines) + (nl if n % 2 else "")
+
+
+@pytest.mark.parametrize("variant", ["unsorted", "sorted", "crlf", "header", "gz"])
+def test_parse_bed_on_device_matches_region_set(api, tmp_path, variant):
+    """gtgpu_parse_bed vs the oracle's RegionSet::try_from (region_set.rs:60-185 parse, :502-505 sort)."""
+    import gzip
+    import zlib
+    from oracle import oracle as orc
+    rng = np.random.default_rng(zlib.crc32(variant.encode()))
+    known = ["chr1", "chr10", "chr2", "chrX", "chr1_KI270706v1_random", "chrM"]
+    names_in_file = known + ["chrUn_unknown", "zzz"]
+    text = _messy_bed(rng, names_in_file if variant != "sorted" else known, 20_000, sort=(variant == "sorted"),
+                      crlf=(variant == "crlf"), header="chrom\tchromStart\tchromEnd\tname" if variant == "header" else None)
+    p = str(tmp_path / ("q.bed.gz" if variant == "gz" else "q.bed"))
+    if variant == "gz":
+        with gzip.open(p, "wt", newline="") as f:
+            f.write(text)
+    else:
+        with open(p, "w", newline="") as f:
+            f.write(text)
+    table = ["chr2", "chrX", "chr1", "chrM", "chr10", "chr1_KI270706v1_random", "chrNeverSeen"]  # ids in THIS order
+    c, s, e = api.parse_bed_file(p, table)
+    ref = orc.regionset_from_file(p)
+    known_ref = [(table.index(r[0]), r[1], r[2]) for r in ref if r[0] in table]
+    unknown_ref = sorted((r[1], r[2]) for r in ref if r[0] not in table)
+    n_known = len(known_ref)
+    assert len(c) == len(ref)
+    got_known = list(zip(c[:n_known].tolist(), s[:n_known].tolist(), e[:n_known].tolist()))
+    assert got_known == known_ref                                   # reference order among the known chromosomes
+    assert (c[n_known:] == 0xFFFFFFFF).all()                         # unknown names sort last ...
+    assert sorted(zip(s[n_known:].tolist(), e[n_known:].tolist())) == unknown_ref
+    assert s[n_known:].tolist() == sorted(s[n_known:].tolist())      # ... by start
+
+
+def test_parse_bed_errors_and_tokenize_bed_file(api, fixture_dir, tmp_path):
+    from oracle import oracle as orc
+    def write(name, text):
+        p = str(tmp_path / name)
+        open(p, "w").write(text)
+        return p
+    for name, text in [("bad_start.bed", "chr1\t1\t2\nchr1\tx\t5\n"), ("neg.bed", "chr1\t-1\t2\n"),
+                       ("two_cols.bed", "chr1\t1\t2\nchr1\t7\n"), ("blank.bed", "chr1\t1\t2\n\nchr1\t3\t4\n"),
+                       ("overflow.bed", "chr1\t1\t4294967296\n"), ("only_comments.bed", "# nothing\ntrack x\n"),
+                       ("space.bed", "chr1\t 1\t2\n")]:
+        p = write(name, text)
+        with pytest.raises(api.GtarsError):
+            api.parse_bed_file(p, ["chr1"])
+        with pytest.raises(ValueError):
+            orc.regionset_from_file(p)                               # the reference rejects the same files
+    c, s, e = api.parse_bed_file(write("edge.bed", "chr1\t4294967295\t+0\nchr1\t0\t1"), ["chr1"])
+    assert (c.tolist(), s.tolist(), e.tolist()) == ([0, 0], [0, 4294967295], [1, 0])
+    # text -> token ids entirely on the device == encode(RegionSet(path))
+    uni = os.path.join(fixture_dir, "tokenizers", "peaks.bed")
+    tok = api.Tokenizer(uni)
+    q = os.path.join(fixture_dir, "to_tokenize.bed")
+    assert tok.encode_bed_file(q) == tok.encode(api.RegionSet(q)) == [22, 23, 24]
+    assert tok.encode_bed_file(uni) == tok.encode(api.RegionSet(uni))
+    gz = os.path.join(fixture_dir, "tokenizers", "peaks.bed.gz")
+    assert tok.encode_bed_file(gz) == tok.encode(api.RegionSet(gz))
+    miss = write("miss.bed", "chrNope\t1\t2\nchr1\t1\t2\n")
+    assert tok.encode_bed_file(miss) == tok.encode(api.RegionSet(miss)) == [tok.unk_token_id]
