@@ -278,6 +278,15 @@ class Index:
                                              unk_id, _p(out_off), C.byref(h)))
         return out_off, _take(h)
 
+    def tokenize_bed(self, text: bytes, chrom_names, unk_id):
+        """gtgpu_tokenize_bed: BED text in, token ids out (parse + sort + encode on the device)."""
+        blob = b"".join(n.encode() for n in chrom_names)
+        offs = np.zeros(len(chrom_names) + 1, dtype=np.uint32)
+        offs[1:] = np.cumsum([len(n.encode()) for n in chrom_names])
+        h = C.c_void_p()
+        check(lib().gtgpu_tokenize_bed(self._h, text, len(text), len(chrom_names), blob, _p(offs), unk_id, C.byref(h)))
+        return _take(h)
+
     def score_matrix(self, file_offsets, chr, start, end, mode, n_cols):
         """region_scoring_from_fragments: uint32 [n_files, n_cols]."""
         fo = _arr(file_offsets, np.uint64)
