@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")"
 name=$1; shift
 mkdir -p ../variants /tmp/gtv_$name
-for f in api index kernels igd fragments comm sort; do
+for f in $(ls cuda/*.cu | xargs -n1 basename | sed "s/\.cu$//"); do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --use_fast_math "$@" \
       -Xptxas -v -c -o /tmp/gtv_$name/$f.o cuda/$f.cu 2> /tmp/gtv_$name/$f.log &
 done
