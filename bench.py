@@ -17,6 +17,7 @@ sharded across ranks (rank r owns files [r*F, (r+1)*F)), universe replicated, no
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -48,6 +49,7 @@ def parse_args():
     ap.add_argument("--width-scale", type=int, default=1, help="multiply the 200-600 bp query widths (wide-query variant)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-api", default="compact", choices=["compact", "runs"], help="host entry point of the e2e leg")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -315,9 +317,23 @@ def main():
     if not args.no_e2e:
         # What a Rust caller holds after RegionSet::try_from: start / end arrays plus, because the files are sorted by
         # chromosome, a handful of (offset, chromosome id) runs per file (gtgpu_tokenize_files_runs).
-        h_start, h_end = (ffi.pinned_empty(n, np.uint32) for _ in range(2))
-        for h, d in ((h_start, d_start), (h_end, d_end)):
-            torch.from_numpy(h.view(np.int32)).copy_(d)
+        # Ends travel as 16-bit widths (gtgpu_tokenize_files_compact): peak-sized regions cost 6 B of PCIe each, not 8;
+        # regions wider than 65 534 bp (none in C2) go through the exception list.  --e2e-api runs = start / end arrays.
+        compact = args.e2e_api == "compact"
+        h_start = ffi.pinned_empty(n, np.uint32)
+        torch.from_numpy(h_start.view(np.int32)).copy_(d_start)
+        if compact:
+            h_w16 = ffi.pinned_empty(n, np.uint16)
+            width = d_end.to(torch.int64) - d_start.to(torch.int64)
+            is_exc = (width < 0) | (width > 65534)
+            torch.from_numpy(h_w16.view(np.int16)).copy_(torch.where(is_exc, torch.full_like(width, 0xFFFF), width).to(torch.int16))
+            exc = torch.nonzero(is_exc).flatten()
+            h_wide_idx = exc.cpu().numpy().astype(np.uint64)
+            h_wide_end = d_end[exc].cpu().numpy().view(np.uint32)
+            del width, is_exc, exc
+        else:
+            h_end = ffi.pinned_empty(n, np.uint32)
+            torch.from_numpy(h_end.view(np.int32)).copy_(d_end)
         h_fo = d_file_offsets.cpu().numpy().astype(np.uint64)
         brk = torch.nonzero(d_chr[1:] != d_chr[:-1]).flatten() + 1
         run_starts = torch.unique(torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), brk, d_file_offsets[:-1]]))
@@ -327,12 +343,27 @@ def main():
         torch.cuda.synchronize()
         L = ffi.lib()
 
+        def e2e_call():
+            if compact:
+                return index.tokenize_files_compact(h_fo, h_run_off, h_run_chr, h_start, h_w16, h_wide_idx, h_wide_end, u["unk_id"],
+                                                    keep_buf=True)
+            return index.tokenize_files_runs(h_fo, h_run_off, h_run_chr, h_start, h_end, u["unk_id"], keep_buf=True)
+
         def e2e_step():
-            off, buf = index.tokenize_files_runs(h_fo, h_run_off, h_run_chr, h_start, h_end, u["unk_id"], keep_buf=True)
+            off, buf = e2e_call()
             total = int(off[-1])  # the step's result is read on the host
             assert L.gtgpu_buf_len(buf) == total
             L.gtgpu_buf_free(buf)
             return total
+
+        # the host entry point must return exactly what the device-resident path produced
+        off_chk, buf_chk = e2e_call()
+        k_chk = min(int(off_chk[-1]), 4_000_000)
+        ids_chk = np.ctypeslib.as_array(C.cast(L.gtgpu_buf_data(buf_chk), C.POINTER(C.c_uint32)), shape=(int(off_chk[-1]),))
+        e2e_matches_device = bool(n_empty_files > 0 or (np.array_equal(ids_chk[:k_chk], d_ids[:k_chk].cpu().numpy().view(np.uint32))
+                                                        and np.array_equal(ids_chk[-k_chk:], d_ids[hits - k_chk:hits].cpu().numpy().view(np.uint32))))
+        del ids_chk
+        L.gtgpu_buf_free(buf_chk)
 
         for _ in range(2):
             e2e_total = e2e_step()
@@ -344,9 +375,11 @@ def main():
         barrier()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
         e2e = {"value": total_queries / e2e_s, "unit": UNIT,
-               "h2d_bytes_per_step": 8 * n + 8 * (n_files + 1) + 12 * len(h_run_chr) + 8,
+               "h2d_bytes_per_step": (6 * n + 12 * len(h_wide_idx) if compact else 8 * n) + 8 * (n_files + 1) + 12 * len(h_run_chr) + 8,
                "d2h_bytes_per_step": 4 * e2e_total + 8 * (n_files + 1), "ms_per_step": e2e_s * 1e3,
-               "api": "gtgpu_tokenize_files_runs (pinned host start/end + chromosome runs in, pinned result buffer out)",
+               "api": ("gtgpu_tokenize_files_compact (pinned host start u32 + width u16 + chromosome runs in, pinned result buffer out)"
+                       if compact else "gtgpu_tokenize_files_runs (pinned host start/end + chromosome runs in, pinned result buffer out)"),
+               "ids_match_device_resident_path": e2e_matches_device,
                "chromosome_runs": int(len(h_run_chr))}
         assert e2e_total == hits + n_empty_files
 

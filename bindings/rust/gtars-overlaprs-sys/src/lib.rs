@@ -47,6 +47,15 @@ extern "C" {
     pub fn gtgpu_tokenize_files_runs(index: *mut gtgpu_index, n_files: u64, file_offsets: *const u64, n_runs: u64,
                                      run_offsets: *const u64, run_chr: *const u32, start: *const u32, end: *const u32,
                                      unk_id: u32, out_file_token_offsets: *mut u64, out_ids: *mut *mut gtgpu_buf) -> i32;
+    pub fn gtgpu_tokenize_files_compact(index: *mut gtgpu_index, n_files: u64, file_offsets: *const u64, n_runs: u64,
+                                        run_offsets: *const u64, run_chr: *const u32, start: *const u32, width16: *const u16,
+                                        n_wide: u64, wide_index: *const u64, wide_end: *const u32, unk_id: u32,
+                                        out_file_token_offsets: *mut u64, out_ids: *mut *mut gtgpu_buf) -> i32;
+    pub fn gtgpu_parse_bed(ctx: *mut gtgpu_ctx, text: *const u8, n_bytes: u64, n_names: u32, names: *const u8,
+                           name_offsets: *const u32, out_n: *mut u64, out_chr: *mut *mut gtgpu_buf,
+                           out_start: *mut *mut gtgpu_buf, out_end: *mut *mut gtgpu_buf) -> i32;
+    pub fn gtgpu_tokenize_bed(index: *mut gtgpu_index, text: *const u8, n_bytes: u64, n_names: u32, names: *const u8,
+                              name_offsets: *const u32, unk_id: u32, out_ids: *mut *mut gtgpu_buf) -> i32;
     pub fn gtgpu_tokenize_fragments(index: *mut gtgpu_index, n: u64, chr: *const u32, start: *const u32, end: *const u32,
                                     barcode_id: *const u32, n_barcodes: u32, unk_id: u32, out_barcode_offsets: *mut u64,
                                     out_ids: *mut *mut gtgpu_buf) -> i32;

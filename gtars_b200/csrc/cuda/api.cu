@@ -350,7 +350,9 @@ int32_t find_host(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32
 int32_t tokenize_files_pipelined(gtgpu_index* ix, uint64_t n, uint64_t n_files, const uint64_t* file_offsets,
                                  const uint32_t* chr, const uint32_t* start, const uint32_t* end, uint64_t chunk,
                                  uint64_t* out_file_tok, gtgpu_buf** out_ids, int* fallback, uint64_t n_runs = 0,
-                                 const uint64_t* run_offsets = nullptr, const uint32_t* run_chr = nullptr) {
+                                 const uint64_t* run_offsets = nullptr, const uint32_t* run_chr = nullptr,
+                                 const uint16_t* width16 = nullptr, uint64_t n_wide = 0, const uint64_t* wide_index = nullptr,
+                                 const uint32_t* wide_end = nullptr) {
     *fallback = 0;
     gtgpu_ctx* ctx = ix->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -397,6 +399,20 @@ int32_t tokenize_files_pipelined(gtgpu_index* ix, uint64_t n, uint64_t n_files, 
         GT_CUDA(cudaMemcpyAsync(d_run_off, run_offsets, (n_runs + 1) * 8, cudaMemcpyHostToDevice, st));
         GT_CUDA(cudaMemcpyAsync(d_run_chr, run_chr, n_runs * 4, cudaMemcpyHostToDevice, st));
     }
+    // ends given as 16-bit widths (+ an exception list): 2 bytes per query cross PCIe instead of 4
+    uint16_t* d_w16[2] = {nullptr, nullptr};
+    uint64_t* d_wide_idx = nullptr;
+    uint32_t* d_wide_end = nullptr;
+    if (width16) {
+        GT_TRY(ctx->scratch_get(SC_BARCODE, chunk * 2, (void**)&d_w16[0]));
+        GT_TRY(ctx->scratch_get(SC_SET_ID, chunk * 2, (void**)&d_w16[1]));
+        if (n_wide) {
+            GT_TRY(ctx->scratch_get(SC_IN3_END, n_wide * 8, (void**)&d_wide_idx));
+            GT_TRY(ctx->scratch_get(SC_MATRIX, n_wide * 4, (void**)&d_wide_end));
+            GT_CUDA(cudaMemcpyAsync(d_wide_idx, wide_index, n_wide * 8, cudaMemcpyHostToDevice, st));
+            GT_CUDA(cudaMemcpyAsync(d_wide_end, wide_end, n_wide * 4, cudaMemcpyHostToDevice, st));
+        }
+    }
     GT_CUDA(cudaMemcpyAsync(d_fo, rebased.data(), (n_files + 1) * 8, cudaMemcpyHostToDevice, st));
     GT_CUDA(cudaMemsetAsync(d_run, 0, (n_chunks + 1) * 8, st));
     GT_CUDA(cudaMemsetAsync(d_misc, 0, 64, st));
@@ -436,9 +452,15 @@ int32_t tokenize_files_pipelined(gtgpu_index* ix, uint64_t n, uint64_t n_files, 
         if (k >= 2) cudaStreamWaitEvent(ctx->copy_in, ev_free[b], 0);
         if (!run_offsets) cudaMemcpyAsync(in[b][0], chr + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in);
         cudaMemcpyAsync(in[b][1], start + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in);
-        cerr = cudaMemcpyAsync(in[b][2], end + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in);
+        if (width16) cerr = cudaMemcpyAsync(d_w16[b], width16 + q0, cn * 2, cudaMemcpyHostToDevice, ctx->copy_in);
+        else cerr = cudaMemcpyAsync(in[b][2], end + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in);
         cudaEventRecord(ev_in[b], ctx->copy_in);
         cudaStreamWaitEvent(st, ev_in[b], 0);
+        if (width16 && status == GTGPU_OK) {
+            const uint64_t lo = std::lower_bound(wide_index, wide_index + n_wide, q0) - wide_index;
+            const uint64_t hi = std::lower_bound(wide_index, wide_index + n_wide, q0 + cn) - wide_index;
+            status = launch_expand_widths(ctx, cn, in[b][1], d_w16[b], in[b][2], hi - lo, d_wide_idx + lo, d_wide_end + lo, q0);
+        }
         if (run_offsets && status == GTGPU_OK) status = launch_expand_runs(ctx, n_runs, d_run_off, d_run_chr, q0, cn, in[b][0]);
         const uint64_t L = first_f[k + 1] - first_f[k];  // file boundaries owned by this chunk
         status = launch_fused_find(ix, cn, L ? L - 1 : 0, d_fo + first_f[k], in[b][0], in[b][1], in[b][2], 0, d_ids, cap, nullptr,
@@ -557,6 +579,43 @@ int32_t gtgpu_tokenize_files_runs(gtgpu_index* ix, uint64_t n_files, const uint6
     std::vector<uint32_t> chr(n);
     for (uint64_t r = 0; r < n_runs; ++r) std::fill(chr.begin() + run_offsets[r], chr.begin() + run_offsets[r + 1], run_chr[r]);
     return find_host(ix, n, chr.data(), start, end, 0, nullptr, true, n_files, file_offsets, unk_id, out_file_token_offsets,
+                     out_ids);
+}
+
+int32_t gtgpu_tokenize_files_compact(gtgpu_index* ix, uint64_t n_files, const uint64_t* file_offsets, uint64_t n_runs,
+                                     const uint64_t* run_offsets, const uint32_t* run_chr, const uint32_t* start,
+                                     const uint16_t* width16, uint64_t n_wide, const uint64_t* wide_index,
+                                     const uint32_t* wide_end, uint32_t unk_id, uint64_t* out_file_token_offsets,
+                                     gtgpu_buf** out_ids) {
+    if (!ix || !file_offsets || !run_offsets || !out_file_token_offsets || !out_ids || (n_runs && !run_chr) ||
+        (n_wide && (!wide_index || !wide_end)))
+        return fail(GTGPU_ERR_INVALID, "tokenize_files_compact: null argument");
+    if (file_offsets[0] != 0 || run_offsets[0] != 0)
+        return fail(GTGPU_ERR_INVALID, "tokenize_files_compact: offsets must start at 0");
+    for (uint64_t f = 0; f < n_files; ++f)
+        if (file_offsets[f] > file_offsets[f + 1]) return fail(GTGPU_ERR_INVALID, "tokenize_files_compact: file_offsets not monotone");
+    for (uint64_t r = 0; r < n_runs; ++r)
+        if (run_offsets[r] > run_offsets[r + 1]) return fail(GTGPU_ERR_INVALID, "tokenize_files_compact: run_offsets not monotone");
+    const uint64_t n = file_offsets[n_files];
+    if (run_offsets[n_runs] != n) return fail(GTGPU_ERR_INVALID, "tokenize_files_compact: runs do not cover the queries");
+    if (n && (!start || !width16)) return fail(GTGPU_ERR_INVALID, "tokenize_files_compact: null query arrays");
+    for (uint64_t i = 0; i < n_wide; ++i)
+        if (wide_index[i] >= n || (i && wide_index[i] <= wide_index[i - 1]))
+            return fail(GTGPU_ERR_INVALID, "tokenize_files_compact: wide_index must be strictly increasing and < n");
+    uint64_t chunk = 32ull << 20;
+    if (const char* env = getenv("GTGPU_PIPE_CHUNK")) chunk = strtoull(env, nullptr, 10) / FUSED_TILE * FUSED_TILE;
+    if (chunk >= (uint64_t)FUSED_TILE && n > chunk && (n + chunk - 1) / chunk <= 56) {
+        int fallback = 0;
+        GT_TRY(tokenize_files_pipelined(ix, n, n_files, file_offsets, nullptr, start, nullptr, chunk, out_file_token_offsets, out_ids,
+                                        &fallback, n_runs, run_offsets, run_chr, width16, n_wide, wide_index, wide_end));
+        if (!fallback) return GTGPU_OK;
+    }
+    // small batches and the rare fallbacks: expand on the host and take the plain path
+    std::vector<uint32_t> chr(n), end(n);
+    for (uint64_t r = 0; r < n_runs; ++r) std::fill(chr.begin() + run_offsets[r], chr.begin() + run_offsets[r + 1], run_chr[r]);
+    for (uint64_t i = 0; i < n; ++i) end[i] = start[i] + width16[i];
+    for (uint64_t i = 0; i < n_wide; ++i) end[wide_index[i]] = wide_end[i];
+    return find_host(ix, n, chr.data(), start, end.data(), 0, nullptr, true, n_files, file_offsets, unk_id, out_file_token_offsets,
                      out_ids);
 }
 

@@ -1054,6 +1054,33 @@ int32_t launch_expand_runs(gtgpu_ctx* ctx, uint64_t n_runs, const uint64_t* d_ru
     return GTGPU_OK;
 }
 
+// end = start + 16-bit width for a chunk of queries, then the exceptions (queries whose width does not fit, or whose end
+// precedes their start) are patched from the caller's list: 2 bytes per query cross PCIe instead of 4.
+__global__ void expand_widths_kernel(uint64_t n, const uint32_t* __restrict__ start, const uint16_t* __restrict__ w16,
+                                     uint32_t* __restrict__ end) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) end[i] = start[i] + (uint32_t)w16[i];
+}
+__global__ void patch_wide_kernel(uint64_t n_wide, const uint64_t* __restrict__ wide_index, const uint32_t* __restrict__ wide_end,
+                                  uint64_t q0, uint32_t* __restrict__ end) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_wide) end[wide_index[i] - q0] = wide_end[i];
+}
+int32_t launch_expand_widths(gtgpu_ctx* ctx, uint64_t n, const uint32_t* d_start, const uint16_t* d_w16, uint32_t* d_end,
+                             uint64_t n_wide, const uint64_t* d_wide_index, const uint32_t* d_wide_end, uint64_t q0) {
+    if (n) {
+        const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 16);
+        expand_widths_kernel<<<grid, 256, 0, ctx->stream>>>(n, d_start, d_w16, d_end);
+        ctx->launches++;
+    }
+    if (n_wide) {
+        patch_wide_kernel<<<(unsigned)((n_wide + 255) / 256), 256, 0, ctx->stream>>>(n_wide, d_wide_index, d_wide_end, q0, d_end);
+        ctx->launches++;
+    }
+    GT_CUDA(cudaGetLastError());
+    return GTGPU_OK;
+}
+
 // ================================================================================================================
 // per-call [unk] rule (tokenizer.rs:158-160): a file whose raw id run is empty becomes the single id unk
 // ================================================================================================================

@@ -44,6 +44,7 @@ SIGNATURES = {
     "gtgpu_find": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _vp, _vp]),
     "gtgpu_tokenize_files": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
     "gtgpu_tokenize_files_runs": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
+    "gtgpu_tokenize_files_compact": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _u32, _vp, _vp]),
     "gtgpu_tokenize_fragments": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "gtgpu_parse_bed": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gtgpu_tokenize_bed": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp, _u32, _vp]),
@@ -266,6 +267,19 @@ class Index:
         h = C.c_void_p()
         check(lib().gtgpu_tokenize_files_runs(self._h, len(fo) - 1, _p(fo), len(rc), _p(ro), _p(rc), _p(start), _p(end),
                                               unk_id, _p(out_off), C.byref(h)))
+        if keep_buf:
+            return out_off, h
+        return out_off, _take(h)
+
+    def tokenize_files_compact(self, file_offsets, run_offsets, run_chr, start, width16, wide_index, wide_end, unk_id,
+                               keep_buf=False):
+        fo, ro = _arr(file_offsets, np.uint64), _arr(run_offsets, np.uint64)
+        rc, start, w16 = _arr(run_chr, np.uint32), _arr(start, np.uint32), _arr(width16, np.uint16)
+        wi, we = _arr(wide_index, np.uint64), _arr(wide_end, np.uint32)
+        out_off = np.empty(len(fo), dtype=np.uint64)
+        h = C.c_void_p()
+        check(lib().gtgpu_tokenize_files_compact(self._h, len(fo) - 1, _p(fo), len(rc), _p(ro), _p(rc), _p(start), _p(w16),
+                                                 len(wi), _p(wi), _p(we), unk_id, _p(out_off), C.byref(h)))
         if keep_buf:
             return out_off, h
         return out_off, _take(h)

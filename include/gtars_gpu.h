@@ -128,6 +128,16 @@ int32_t gtgpu_tokenize_files_runs(gtgpu_index* index, uint64_t n_files, const ui
                                   const uint32_t* end, uint32_t unk_id, uint64_t* out_file_token_offsets,
                                   gtgpu_buf** out_ids);
 
+/* gtgpu_tokenize_files_runs with the ends as 16-bit widths: end[i] = start[i] + width16[i], except for the queries
+ * listed in wide_index (strictly increasing), whose end is wide_end[k] — regions wider than 65 535 bp, or with
+ * end < start.  Peak-sized regions then cost 6 bytes of PCIe traffic each instead of 8 (the host entry point is
+ * H2D-bound); results are identical to gtgpu_tokenize_files on the expanded arrays. */
+int32_t gtgpu_tokenize_files_compact(gtgpu_index* index, uint64_t n_files, const uint64_t* file_offsets, uint64_t n_runs,
+                                     const uint64_t* run_offsets, const uint32_t* run_chr, const uint32_t* start,
+                                     const uint16_t* width16, uint64_t n_wide, const uint64_t* wide_index,
+                                     const uint32_t* wide_end, uint32_t unk_id, uint64_t* out_file_token_offsets,
+                                     gtgpu_buf** out_ids);
+
 /* tokenize_fragment_file (gtars-tokenizers/src/utils/fragments.rs:12-82) over pre-parsed fragments: every fragment
  * is one Tokenizer::tokenize call (a fragment with no hit, or on an unknown chromosome, yields unk_id), ids are
  * appended to the fragment's barcode list in input order.  barcode_id[i] < n_barcodes (dense ids, mapped by the

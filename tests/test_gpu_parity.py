@@ -362,6 +362,25 @@ def test_tokenize_files_runs_variant(ctx, monkeypatch):
     from gtars_b200.ffi import GtarsGpuError
     with pytest.raises(GtarsGpuError):
         g.tokenize_files_runs(fo, run_offsets[:-1], run_chr[:-1], qs, qe, u["unk_id"])  # runs do not cover the queries
+    # compact wire format: ends as 16-bit widths + an exception list (wide and reversed regions)
+    rng = np.random.default_rng(9)
+    qe2 = qe.copy()
+    wide = rng.choice(len(qs), 300, replace=False)
+    qe2[wide[:200]] = qs[wide[:200]] + rng.integers(65535, 3_000_000, 200).astype(np.uint32)   # too wide for 16 bits
+    qe2[wide[200:]] = np.maximum(qs[wide[200:]].astype(np.int64) - rng.integers(0, 500, 100), 0).astype(np.uint32)  # end <= start
+    width = qe2.astype(np.int64) - qs.astype(np.int64)
+    exc = np.flatnonzero((width < 0) | (width > 65534))
+    w16 = np.where((width < 0) | (width > 65534), 0xFFFF, width).astype(np.uint16)
+    want2 = o.tokenize_files(fo, qc, qs, qe2, u["unk_id"])
+    assert not np.array_equal(want2[1], want[1])
+    for chunk in ("1000000000", "4096"):
+        monkeypatch.setenv("GTGPU_PIPE_CHUNK", chunk)
+        got = g.tokenize_files_compact(fo, run_offsets, run_chr, qs, w16, exc.astype(np.uint64), qe2[exc], u["unk_id"])
+        assert np.array_equal(got[0], want2[0]) and np.array_equal(got[1], want2[1])
+    got = g.tokenize_files_compact(fo, run_offsets, run_chr, qs, (qe - qs).astype(np.uint16), [], [], u["unk_id"])
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    with pytest.raises(GtarsGpuError):
+        g.tokenize_files_compact(fo, run_offsets, run_chr, qs, w16, [5, 5], [1, 2], u["unk_id"])  # not strictly increasing
 
 
 @pytest.mark.parametrize("kind", ["bits", "ailist"])
