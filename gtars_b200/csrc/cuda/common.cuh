@@ -167,6 +167,9 @@ struct gtgpu_index {
     uint64_t n_intervals = 0, n_segments = 0, device_bytes = 0, max_components = 0;
     uint64_t bt_bins = 0, bt_overflow_bins = 0, bt_pool_windows = 0;
     uint32_t max_val = 0;  // largest val of any interval (bounds the radix passes of the scoring group-by)
+    bool bt_clean = false;            // every window is a plain record: the lean find kernel can serve the index
+    bool lean_off = false;            // the lean kernel had to fall back on this index before
+    uint32_t* h_lean_probe = nullptr; // pinned copy of the last launch's lean flag (read lazily, never waited for)
     bool l2_window_set = false;
 };
 

@@ -389,6 +389,11 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
     v.bt_shift = bt_shift;
     ix->bt_bins = bt_lut.size();
     ix->bt_overflow_bins = bt_overflow;
+    ix->bt_clean = bt_overflow == 0 && bt_pool_windows == 0 && total > 0;
+    for (uint32_t c = 0; c < n_chroms; ++c)
+        if (chrom_bt[c].n_bins & BT_GENERIC_CHROM) ix->bt_clean = false;
+    if (ix->bt_clean && cudaHostAlloc((void**)&ix->h_lean_probe, 4, cudaHostAllocDefault) == cudaSuccess) *ix->h_lean_probe = 0;
+    else { ix->h_lean_probe = nullptr; cudaGetLastError(); }
     up(chroms, &v.chroms);
     up(seg_meta, &v.segs);
     up(h_starts, &v.starts);
@@ -418,11 +423,15 @@ extern "C" int32_t gtgpu_index_free(gtgpu_index* ix) {
     if (!ix) return GTGPU_OK;
     cudaSetDevice(ix->ctx->device);
     for (void* p : ix->allocs) cudaFree(p);
+    if (ix->h_lean_probe) {
+        cudaStreamSynchronize(ix->ctx->stream);  // a probe copy may still be in flight
+        cudaFreeHost(ix->h_lean_probe);
+    }
     delete ix;
     return GTGPU_OK;
 }
 
-extern "C" int32_t gtgpu_index_info(const gtgpu_index* ix, uint64_t info[10]) {
+extern "C" int32_t gtgpu_index_info(const gtgpu_index* ix, uint64_t info[12]) {
     if (!ix || !info) return fail(GTGPU_ERR_INVALID, "index_info: null argument");
     info[0] = ix->n_intervals;
     info[1] = ix->n_segments;
@@ -434,5 +443,7 @@ extern "C" int32_t gtgpu_index_info(const gtgpu_index* ix, uint64_t info[10]) {
     info[7] = ix->bt_overflow_bins;
     info[8] = ix->view.bt_shift;
     info[9] = ix->bt_pool_windows;
+    info[10] = ix->bt_clean;
+    info[11] = ix->lean_off || (ix->h_lean_probe && *ix->h_lean_probe);
     return GTGPU_OK;
 }

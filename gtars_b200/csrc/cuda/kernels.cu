@@ -215,22 +215,29 @@ struct FusedWorkspace {
     uint64_t* super;       // [n_tiles / FUSED_SUPER + 1] supertile accumulators
     uint32_t* tile_file;   // [n_tiles] 0 = no file boundary in this tile, else 0xFFFFFFFF - first file index
     uint32_t* counter;     // dynamic tile counter
+    uint32_t* lean_flag;   // raised by the lean kernel when the full kernel has to redo the launch
 };
 
 static inline uint64_t n_tiles_for(uint64_t n) { return (n + FUSED_TILE - 1) / FUSED_TILE; }
 
+// Two sets of status / accumulator words and counters (the lean launch and its fallback each need zeroed ones), one
+// tile_file array (read-only for both), one lean flag.
+static size_t fused_chain_bytes(uint64_t t) { return (size_t)(t * 8 + (t / FUSED_SUPER + 1) * 8 + 16); }
+
 size_t fused_workspace_bytes(uint64_t n) {
     uint64_t t = n_tiles_for(n);
-    return (size_t)(t * 8 + (t / FUSED_SUPER + 1) * 8 + ((t * 4 + 15) / 16) * 16 + 64);
+    return 2 * fused_chain_bytes(t) + (size_t)(((t * 4 + 15) / 16) * 16 + 64);
 }
 
-static FusedWorkspace carve(void* ws, uint64_t n) {
+static FusedWorkspace carve(void* ws, uint64_t n, int set) {
     uint64_t t = n_tiles_for(n);
+    char* base = reinterpret_cast<char*>(ws);
     FusedWorkspace w;
-    w.status = reinterpret_cast<uint64_t*>(ws);
+    w.status = reinterpret_cast<uint64_t*>(base + (size_t)set * fused_chain_bytes(t));
     w.super = w.status + t;
-    w.tile_file = reinterpret_cast<uint32_t*>(w.super + t / FUSED_SUPER + 1);
-    w.counter = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(w.tile_file) + ((t * 4 + 15) / 16) * 16);
+    w.counter = reinterpret_cast<uint32_t*>(w.super + t / FUSED_SUPER + 1);
+    w.tile_file = reinterpret_cast<uint32_t*>(base + 2 * fused_chain_bytes(t));
+    w.lean_flag = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(w.tile_file) + ((t * 4 + 15) / 16) * 16);
     return w;
 }
 
@@ -438,14 +445,20 @@ __device__ __forceinline__ bool cand_hit(uint32_t cs, uint32_t ce, uint32_t s, u
 }
 
 // DESC: AIList emission order; FILTER: min_overlap > 1; OFFS: per-query offsets are written (gtgpu_find).
-template <int ROWS, bool DESC, bool FILTER, bool OFFS>
+// LEAN: the record path only — no window walk, no generic walk, no call at all, which is worth 4 registers, every
+// spill and 5 % of the step.  A warp that meets a query the records cannot resolve raises *lean_flag; the launcher
+// queues the full kernel right behind the lean one with run_if = that flag, so the full kernel either exits at once
+// (the usual case) or redoes the whole launch — still one asynchronous sequence on the stream, no host round trip.
+template <int ROWS, bool DESC, bool FILTER, bool OFFS, bool LEAN>
 __global__ void __launch_bounds__(FUSED_BLOCK, GT_FUSED_MINBLOCKS)
 fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, const uint64_t* __restrict__ file_offsets,
                   const uint32_t* __restrict__ chr, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
                   int32_t min_bp, int tma_ok, uint32_t* __restrict__ out_ids, uint64_t capacity,
                   uint64_t* __restrict__ out_offsets, uint64_t* __restrict__ out_file_tok, FusedWorkspace ws,
-                  const uint64_t* __restrict__ d_base, uint64_t* __restrict__ d_total, uint32_t* __restrict__ d_err) {
+                  const uint64_t* __restrict__ d_base, uint64_t* __restrict__ d_total, uint32_t* __restrict__ d_err,
+                  uint32_t* __restrict__ lean_flag, const uint32_t* __restrict__ run_if) {
     static_assert(ROWS == 4, "state packing (2-bit counts, 8-bit offsets) is written for four rows per thread");
+    if (!LEAN && run_if && *run_if == 0) return;  // fallback launch, and the lean kernel resolved everything
     constexpr int WARPS = FUSED_BLOCK / 32;
     constexpr int WTILE = 32 * ROWS;          // queries per warp
     constexpr int TILE = FUSED_BLOCK * ROWS;  // queries per block tile
@@ -568,7 +581,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     const bool ok = q < n;
                     qc[k] = ok ? __ldcs(chr + q) : 0xFFFFFFFFu;
                     qs[k] = ok ? __ldcs(start + q) : 0;
-                    qe[k] = ok ? __ldcs(end + q) : 0;
+                    qe[k] = ok ? __ldcs(end + q) : 1;  // past the end: an unknown-chromosome query [0, 1) the records resolve to nothing
                 }
             }
             PHASE_MARK(0);
@@ -626,6 +639,12 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 cur.offpack = excl + ((t0 << 8) | ((t0 + t1) << 16) | ((t0 + t1 + t2) << 24));
                 warp_total = t0 + t1 + t2 + t3;
                 cur.cntpack = cnt[0] | (cnt[1] << 2) | (cnt[2] << 4) | (cnt[3] << 6);
+            } else if constexpr (LEAN) {
+                // not resolvable by records alone: this launch's output will be replaced by the full kernel's
+                if (lane == 0) *lean_flag = 1u;
+                cur.cntpack = 0;
+                cur.offpack = 0;
+                cur.slow = 0;
             } else {
                 // some queries left the record path: count them through the window walk / the generic LUT + walk
 #pragma unroll
@@ -788,7 +807,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             const uint64_t warp_base = tile_base + prev.warp_excl;
             uint32_t* const outp = out_ids + warp_base;
             const bool fits = tile_base + prev.tile_agg <= capacity;
-            if (prev.slow & WARP_SEMI) {
+            if (!LEAN && (prev.slow & WARP_SEMI)) {
                 const uint32_t rb = s_rowbase[ppar][warp];  // bases of rows 1..3, 10 bits each (row 0 starts at zero)
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k) {
@@ -810,7 +829,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                         if (c == 2 && pos + 1 < capacity) out_ids[pos + 1] = b;
                     }
                 }
-            } else if (!(prev.slow & WARP_SLOW)) {
+            } else if (LEAN || !(prev.slow & WARP_SLOW)) {
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k) {
                     const uint32_t c = (prev.cntpack >> (2 * k)) & 3, o = (prev.offpack >> (8 * k)) & 0xFF;
@@ -855,8 +874,8 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     __syncthreads();
 #pragma unroll
                     for (int k = 0; k < ROWS; ++k) {
-                        uint32_t o = (prev.slow & WARP_SLOW) ? s_aux[ppar][wl + 32 * k] : (prev.offpack >> (8 * k)) & 0xFF;
-                        if ((prev.slow & WARP_SEMI) && k > 0) o += (s_rowbase[ppar][warp] >> (10 * (k - 1))) & 0x3FF;
+                        uint32_t o = (!LEAN && (prev.slow & WARP_SLOW)) ? s_aux[ppar][wl + 32 * k] : (prev.offpack >> (8 * k)) & 0xFF;
+                        if (!LEAN && (prev.slow & WARP_SEMI) && k > 0) o += (s_rowbase[ppar][warp] >> (10 * (k - 1))) & 0x3FF;
                         s_aux[ppar][wl + 32 * k] = prev.warp_excl + o;
                     }
                     __syncthreads();
@@ -890,13 +909,14 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
 #endif
 }
 
-template <bool DESC, bool FILTER, bool OFFS>
+template <bool DESC, bool FILTER, bool OFFS, bool LEAN>
 static cudaError_t launch_variant(int grid, cudaStream_t st, const IndexView& view, uint64_t n, uint32_t n_tiles,
                                   uint64_t n_files, const uint64_t* d_file_offsets, const uint32_t* d_chr,
                                   const uint32_t* d_start, const uint32_t* d_end, int32_t min_overlap, uint32_t* d_out_ids,
                                   uint64_t cap, uint64_t* d_out_offsets, uint64_t* d_out_file_tok, FusedWorkspace ws,
-                                  const uint64_t* d_base, uint64_t* d_total_out, uint32_t* d_errflag, int* blocks_per_sm) {
-    auto kern = fused_find_kernel<FUSED_ROWS, DESC, FILTER, OFFS>;
+                                  const uint64_t* d_base, uint64_t* d_total_out, uint32_t* d_errflag, const uint32_t* run_if,
+                                  int* blocks_per_sm) {
+    auto kern = fused_find_kernel<FUSED_ROWS, DESC, FILTER, OFFS, LEAN>;
     if (blocks_per_sm) {
         // 4 CTAs x 24 KB fit the 100 KB shared-memory configuration; the rest of the unified L1 serves the gathers
         int carve = 40;
@@ -908,7 +928,8 @@ static cudaError_t launch_variant(int grid, cudaStream_t st, const IndexView& vi
     const int tma_ok = ((reinterpret_cast<uintptr_t>(d_chr) | reinterpret_cast<uintptr_t>(d_start) |
                          reinterpret_cast<uintptr_t>(d_end)) & 15) == 0;
     kern<<<grid, FUSED_BLOCK, 0, st>>>(view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end, min_overlap, tma_ok,
-                                       d_out_ids, cap, d_out_offsets, d_out_file_tok, ws, d_base, d_total_out, d_errflag);
+                                       d_out_ids, cap, d_out_offsets, d_out_file_tok, ws, d_base, d_total_out, d_errflag,
+                                       ws.lean_flag, run_if);
     return cudaGetLastError();
 }
 
@@ -949,7 +970,14 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
     uint64_t tiles64 = n_tiles_for(n);
     if (tiles64 > 0x7FFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "fused_find: too many queries for one launch");
     uint32_t n_tiles = (uint32_t)tiles64;
-    FusedWorkspace ws = carve(d_workspace, n);
+    // Lean kernel first when every window of the index is a plain record (no pool lists, no overflow windows, no
+    // chromosome without a table) and it has not failed on this index before; the full kernel follows as its
+    // on-device fallback (see fused_find_kernel).  GTGPU_LEAN=0 forces the full kernel.
+    if (ix->h_lean_probe && *ix->h_lean_probe) ix->lean_off = true;  // a previous launch had to fall back: stop trying
+    static const bool lean_env = !(getenv("GTGPU_LEAN") && getenv("GTGPU_LEAN")[0] == '0');
+    const bool use_lean = lean_env && ix->bt_clean && !ix->lean_off;
+    FusedWorkspace ws = carve(d_workspace, n, 0);
+    const FusedWorkspace ws_fallback = carve(d_workspace, n, 1);
     GT_CUDA(cudaMemsetAsync(d_workspace, 0, fused_workspace_bytes(n), st));
     if (d_out_file_tok) {
         uint64_t cnt = n_files + 1;
@@ -982,24 +1010,35 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
     }
     const bool desc = ix->view.descending != 0, filt = min_overlap > 1, offs = d_out_offsets != nullptr;
     const int variant = (desc ? 4 : 0) | (filt ? 2 : 0) | (offs ? 1 : 0);
-    static int blocks_per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    static int blocks_per_sm[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
     int grid = 0;
     cudaError_t err = cudaSuccess;
-#define GT_VARIANT(D, F, O)                                                                                          \
-    case ((D ? 4 : 0) | (F ? 2 : 0) | (O ? 1 : 0)):                                                                  \
-        if (!blocks_per_sm[variant]) {                                                                               \
-            err = launch_variant<D, F, O>(0, st, ix->view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end,  \
-                                          min_overlap, d_out_ids, ids_capacity, d_out_offsets, d_out_file_tok, ws,    \
-                                          d_base, d_total_out, d_errflag, &blocks_per_sm[variant]);                    \
-            if (err != cudaSuccess) break;                                                                           \
-            if (blocks_per_sm[variant] < 1) blocks_per_sm[variant] = 1;                                              \
-        }                                                                                                            \
-        grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * blocks_per_sm[variant]);                   \
-        ctx->time_begin();                                                                                           \
-        err = launch_variant<D, F, O>(grid, st, ix->view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end,   \
-                                      min_overlap, d_out_ids, ids_capacity, d_out_offsets, d_out_file_tok, ws, d_base, \
-                                      d_total_out, d_errflag, nullptr);                                                \
-        ctx->time_end();                                                                                             \
+#define GT_LAUNCH(D, F, O, LEAN, WS, RUN_IF)                                                                             \
+    do {                                                                                                                \
+        int& bps = blocks_per_sm[LEAN ? 1 : 0][variant];                                                                \
+        if (!bps) {                                                                                                     \
+            err = launch_variant<D, F, O, LEAN>(0, st, ix->view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end, \
+                                                min_overlap, d_out_ids, ids_capacity, d_out_offsets, d_out_file_tok, WS,  \
+                                                d_base, d_total_out, d_errflag, RUN_IF, &bps);                          \
+            if (err != cudaSuccess) break;                                                                              \
+            if (bps < 1) bps = 1;                                                                                       \
+        }                                                                                                               \
+        grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * bps);                                         \
+        err = launch_variant<D, F, O, LEAN>(grid, st, ix->view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end,  \
+                                            min_overlap, d_out_ids, ids_capacity, d_out_offsets, d_out_file_tok, WS, d_base, \
+                                            d_total_out, d_errflag, RUN_IF, nullptr);                                    \
+        ctx->launches++;                                                                                                \
+    } while (0)
+#define GT_VARIANT(D, F, O)                                                                                              \
+    case ((D ? 4 : 0) | (F ? 2 : 0) | (O ? 1 : 0)):                                                                      \
+        ctx->time_begin();                                                                                              \
+        if (use_lean) {                                                                                                 \
+            GT_LAUNCH(D, F, O, true, ws, nullptr);                                                                      \
+            if (err == cudaSuccess) GT_LAUNCH(D, F, O, false, ws_fallback, ws.lean_flag);                               \
+        } else {                                                                                                        \
+            GT_LAUNCH(D, F, O, false, ws, nullptr);                                                                     \
+        }                                                                                                               \
+        ctx->time_end();                                                                                                \
         break;
     switch (variant) {
         GT_VARIANT(false, false, false)
@@ -1012,8 +1051,9 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
         GT_VARIANT(true, true, true)
     }
 #undef GT_VARIANT
+#undef GT_LAUNCH
     if (err != cudaSuccess) return fail(GTGPU_ERR_CUDA, std::string("fused_find launch: ") + cudaGetErrorString(err));
-    ctx->launches++;
+    if (use_lean && ix->h_lean_probe) cudaMemcpyAsync(ix->h_lean_probe, ws.lean_flag, 4, cudaMemcpyDeviceToHost, st);
     GT_CUDA(cudaGetLastError());
     return GTGPU_OK;
 }

@@ -218,10 +218,11 @@ class Index:
             pass
 
     def info(self) -> dict:
-        a = (C.c_uint64 * 10)()
+        a = (C.c_uint64 * 12)()
         check(lib().gtgpu_index_info(self._h, a))
         return dict(n_intervals=a[0], n_segments=a[1], device_bytes=a[2], lut_shift=a[3], max_components=a[4],
-                    proper=bool(a[5]), bt_bins=a[6], bt_overflow_bins=a[7], bt_shift=a[8], bt_pool_windows=a[9])
+                    proper=bool(a[5]), bt_bins=a[6], bt_overflow_bins=a[7], bt_shift=a[8], bt_pool_windows=a[9],
+                    lean_kernel=bool(a[10]), lean_fell_back=bool(a[11]))
 
     # ---- host-buffer entry points -------------------------------------------------------------------------------
     def count(self, chr, start, end, min_overlap=0) -> np.ndarray:

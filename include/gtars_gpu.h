@@ -89,8 +89,11 @@ int32_t gtgpu_index_free(gtgpu_index* index);
 /* info[0]=n_intervals, [1]=n_segments (chromosome×AIList component), [2]=device bytes, [3]=lut shift,
  * [4]=max components on one chromosome, [5]=1 if every interval has start<=end, [6]=bin-table bins,
  * [7]=bin-table windows served by the generic walk (too many candidates), [8]=bin-table shift,
- * [9]=bin-table windows with a pooled candidate list (nested intervals / several AIList components) */
-int32_t gtgpu_index_info(const gtgpu_index* index, uint64_t info[10]);
+ * [9]=bin-table windows with a pooled candidate list (nested intervals / several AIList components),
+ * [10]=1 if every window is a plain record (the lean find kernel serves the index, the full kernel is queued behind it
+ * as an on-device fallback), [11]=1 once a launch on this index had to take that fallback (the lean kernel is then no
+ * longer tried; the flag is read lazily, so it shows at the latest after the launch following the fallback) */
+int32_t gtgpu_index_info(const gtgpu_index* index, uint64_t info[12]);
 
 /* ---- batch queries, host buffers ------------------------------------------------------------------------ */
 /* MultiChromOverlapper::count_overlaps (multi_chrom_overlapper.rs:483-498): out_counts[i] = number of indexed

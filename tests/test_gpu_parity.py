@@ -485,3 +485,42 @@ def test_score_barcodes_vs_oracle(ctx):
     none = np.full(10, 0xFFFFFFFF, np.uint32)
     off, pk, ct = g.score_barcodes(none, fs[:10], fe[:10], bc[:10] % 5, 5)
     assert list(off) == [0] * 6 and len(pk) == 0
+
+
+def test_lean_kernel_and_on_device_fallback(ctx):
+    """A universe whose windows are all plain records is served by the lean kernel with the full kernel queued behind it
+    as an on-device fallback: narrow queries never need it, a batch with wide / degenerate queries is redone by it within
+    the same stream sequence (results identical), and the index then stops trying the lean kernel."""
+    from gtars_b200 import synth
+    u = synth.make_universe(50_000)
+    offs = u["chrom_offsets"].numpy().astype(np.uint64)
+    s, e, v = (u[k].numpy().view(np.uint32) for k in ("g_start", "g_end", "g_val"))
+    g, o = _both(ctx, "bits", offs, s, e, v)
+    info = g.info()
+    assert info["bt_pool_windows"] == 0 and info["bt_overflow_bins"] == 0
+    q = synth.make_query_files(u, 6, 5000)
+    qc, qs, qe = (q[k].numpy().view(np.uint32) for k in ("chr", "start", "end"))
+    fo = q["file_offsets"].numpy().astype(np.uint64)
+
+    want = o.tokenize_files(fo, qc, qs, qe, u["unk_id"])
+    assert info["lean_kernel"] and not info["lean_fell_back"]
+    got = g.tokenize_files(fo, qc, qs, qe, u["unk_id"])
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    ctx.synchronize()
+    assert not g.info()["lean_fell_back"]                   # narrow queries: the records resolved everything
+    # wide and reversed queries: the lean kernel cannot resolve them, its fallback does
+    qe_w = qe.copy()
+    qe_w[::7] = qs[::7] + 50_000
+    qe_w[3::11] = qs[3::11] - np.minimum(qs[3::11], 3)
+    want_w = o.tokenize_files(fo, qc, qs, qe_w, u["unk_id"])
+    got_w = g.tokenize_files(fo, qc, qs, qe_w, u["unk_id"])
+    assert np.array_equal(got_w[0], want_w[0]) and np.array_equal(got_w[1], want_w[1])
+    ctx.synchronize()
+    assert g.info()["lean_fell_back"]                       # ... and the index remembers
+    _assert_same_find(g, o, qc, qs, qe_w)
+    got2 = g.tokenize_files(fo, qc, qs, qe, u["unk_id"])    # full kernel only from here on: still exact
+    assert np.array_equal(got2[0], want[0]) and np.array_equal(got2[1], want[1])
+    # a nested universe never uses the lean kernel
+    un = synth.make_universe(20_000, nested_frac=0.02)
+    gn = _both(ctx, "bits", un["chrom_offsets"].numpy().astype(np.uint64), *(un[k].numpy().view(np.uint32) for k in ("g_start", "g_end", "g_val")))[0]
+    assert not gn.info()["lean_kernel"]
