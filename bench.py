@@ -279,11 +279,20 @@ def main():
         stream.synchronize()
         torch.cuda.synchronize()
         barrier()
-        clocks = sampler.stop()
-        ms_per_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
         kernel_ms = ctx.timing_read()
         ctx.timing_enable(False)
         launches = ctx.launch_count() - launches0
+        # K steps of a few ms are shorter than one nvidia-smi sampling period: keep the identical load running (untimed)
+        # until the sampler has covered at least half a second, so that the clocks line reflects this workload.
+        t_probe = time.perf_counter()
+        while time.perf_counter() - t_probe < 0.5:
+            for _ in range(8):
+                step()
+            stream.synchronize()
+        clocks = sampler.stop()
+        clocks["window"] = "timed region + 0.5 s of the identical steps right behind it"
+        ms_per_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+
 
     total_queries = sum_over_ranks(float(n))
     value = total_queries / (ms_per_step * 1e-3)
