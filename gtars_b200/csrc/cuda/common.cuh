@@ -80,6 +80,7 @@ struct ChromMeta {    // 32 bytes
 // absolute ones.  rel = s_rel | e_rel << (bt_shift + 2); needs 2 + 2 (bt_shift + 2) <= 32 bits: bt_shift <= 13.
 //   word 0 = kind | rel0 << 2,  kind 0 = empty, 1 = one candidate inline, 2 = two candidates, 3 = pool list / overflow
 //   word 1 = val0,  word 2 = rel1 << 2,  word 3 = val1 (second candidate, kind 2)
+//   kind 3: word 1 = the window's bt_lut word (pool list offset and length, or BT_OVERFLOW)
 // bt_lut / bt_ent / bt_pool stay the slow path's view of the same windows (pool lists, multi-window queries).
 #define BT_REC_WORDS 4
 #define BT_REC_MAX_SHIFT 13u

@@ -357,6 +357,7 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
                 if (w == 0) continue;
                 if (w & BT_POOL_FLAG) {  // pool list or overflow (BT_OVERFLOW has the flag bit too)
                     r[0] = 3;
+                    r[1] = w;  // the full kernel walks the pool list straight from the record
                     continue;
                 }
                 const uint32_t first = w >> 2, cnt = w & 3;

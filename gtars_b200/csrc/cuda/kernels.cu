@@ -347,6 +347,16 @@ __device__ __noinline__ uint32_t count_query_walk_noinline(const IndexView& ix, 
     return count_query_walk(ix, c, s, e, min_bp);
 }
 
+// Count for a query that left the record path, plus its first two hits' vals (emission order) in ab[] when the window
+// table could serve it (multi-window queries, pool lists): bit 31 of the result says so.
+__device__ __noinline__ uint32_t count_query_first2(const IndexView& ix, uint32_t c, uint32_t s, uint32_t e, int32_t min_bp,
+                                                    uint32_t* ab) {
+    uint32_t cnt;
+    ab[0] = ab[1] = 0;
+    if (window_walk<true>(ix, c, s, e, min_bp, ab, 0, 2, cnt)) return cnt | 0x80000000u;
+    return count_query_walk(ix, c, s, e, min_bp);
+}
+
 __device__ __forceinline__ uint64_t ld_status(const uint64_t* p) {
     uint64_t v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -607,13 +617,13 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     // the window; the window-relative comparison below is then exact for them too.
                     const uint32_t b1 = s >> shift;
                     const uint32_t d = e - 1u - (b1 << shift);  // wraps to a huge value when e-1 is before the window
-                    if ((cb.y == BT_GENERIC_CHROM) | (e == 0u) | (d >= (2u << shift))) cur.slow |= 1u << k;
+                    if ((cb.y == BT_GENERIC_CHROM) | (e == 0u) | (d >= (2u << shift))) cur.slow |= (LEAN ? 1u : 0x11u) << k;  // bit k+4: not a window query
                     const uint32_t li = b1 < (cb.y & BT_NBINS_MASK) ? cb.x + b1 : 0u;  // record 0 is the empty sentinel
                     r[k] = ldg128_keep(ix.bt_rec + (size_t)li * 4, keep);
                 }
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k) {
-                    if ((r[k].x & 3) == 3) cur.slow |= 1u << k;  // pool list or overflow: resolved by the slow-path functions
+
                     const uint32_t s = qs[k] & bin_mask, e = qe[k] - (qs[k] - s);  // a slow query's values are never used
                     const uint32_t r0 = r[k].x >> 2, r1 = r[k].z >> 2;
                     // an absent candidate is all zeros: relative end 0 can never exceed a relative query start
@@ -622,6 +632,10 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     cnt[k] = (uint32_t)h0 + (uint32_t)h1;
                     cur.v0[k] = h0 ? r[k].y : r[k].w;
                     if (h0 & h1) s_aux[par][wl + 32 * k] = r[k].w;
+                    if ((r[k].x & 3) == 3) {  // pool list or overflow (all-zero candidates: no hit above)
+                        cur.slow |= 1u << k;
+                        if (!LEAN) cur.v0[k] = r[k].y;  // the full kernel walks the list from this word
+                    }
                 }
             }
             prefetch_lookback();
@@ -651,10 +665,43 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 cur.offpack = 0;
                 cur.slow = 0;
             } else {
-                // some queries left the record path: count them through the window walk / the generic LUT + walk
+                // Some queries left the record path.  Pool-list windows (nested intervals, several AIList components) are
+                // walked right here from the window word the record carried; everything else goes through the window walk /
+                // the generic LUT + walk.  Either way a query with at most two hits rejoins the register path (its vals are in
+                // emission order, so an AIList pair is stored swapped for the emit's swap); longer ones are walked again at emit.
 #pragma unroll
-                for (int k = 0; k < ROWS; ++k)
-                    if ((cur.slow >> k) & 1) cnt[k] = count_query_walk_noinline(ix, qc[k], qs[k], qe[k], min_bp);
+                for (int k = 0; k < ROWS; ++k) {
+                    if (!((cur.slow >> k) & 1)) continue;
+                    uint32_t c, a = 0, b = 0;
+                    bool ordered;
+                    const uint32_t w = cur.v0[k];
+                    if (((cur.slow >> k) & 0x10u) == 0 && w != BT_OVERFLOW && qs[k] < qe[k]) {
+                        const uint32_t nl = w & 7u, first = (w & ~BT_POOL_FLAG) >> 3;
+                        c = 0;
+                        for (uint32_t t = 0; t < nl; ++t) {
+                            const uint4 E = ldg128(ix.bt_ent + __ldg(ix.bt_pool + first + t));
+                            if (!cand_hit<FILTER>(E.x, E.y, qs[k], qe[k], min_bp)) continue;
+                            if (c == 0) a = E.z;
+                            else if (c == 1) b = E.z;
+                            ++c;
+                        }
+                        ordered = true;
+                    } else {
+                        uint32_t ab[2];
+                        const uint32_t r = count_query_first2(ix, qc[k], qs[k], qe[k], min_bp, ab);
+                        c = r & 0x7FFFFFFFu;
+                        ordered = (r >> 31) != 0;
+                        a = ab[0];
+                        b = ab[1];
+                    }
+                    cnt[k] = c;
+                    if (ordered && c <= 2) {
+                        cur.slow &= ~(1u << k);
+                        cur.v0[k] = (DESC && c == 2) ? b : a;
+                        if (c == 2) s_aux[par][wl + 32 * k] = DESC ? a : b;
+                    }
+                }
+                cur.slow &= 0xFu;
                 cur.cntpack = min(cnt[0], 3u) | (min(cnt[1], 3u) << 2) | (min(cnt[2], 3u) << 4) | (min(cnt[3], 3u) << 6);
                 if (!__any_sync(FULL, (cnt[0] | cnt[1] | cnt[2] | cnt[3]) > BT_POOL_MAX)) {
                     // pool-list windows (nested intervals, several AIList components): every count is at most 7, so a row
