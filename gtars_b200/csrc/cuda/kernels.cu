@@ -433,6 +433,15 @@ __device__ unsigned long long g_phase_cycles[16 * 8];  // [warp][phase]
 #define PHASE_START()
 #endif
 
+// Warp sum of 64-bit values below 2^63: three hardware warp reductions (REDUX.SUM) over 21-bit limbs instead of ten
+// dependent shuffles — this sits on the critical path between the two barriers of a step.
+__device__ __forceinline__ uint64_t warp_sum_u63(uint64_t v) {
+    const uint32_t a = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(v & 0x1FFFFFu));
+    const uint32_t b = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)((v >> 21) & 0x1FFFFFu));
+    const uint32_t c = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(v >> 42));
+    return (uint64_t)a + ((uint64_t)b << 21) + ((uint64_t)c << 42);
+}
+
 // Per-thread result of resolving ROWS queries of one tile, kept in registers while the NEXT tile is resolved
 // (software pipeline, lag 1): by the time a tile's look-back runs, its predecessors published their aggregates a
 // whole resolve phase ago, so the look-back is one L2 round trip and (almost) never spins.
@@ -752,7 +761,12 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
         __syncthreads();  // B2: warp totals of `cur` visible; s_tile[par] / s_q consumed by everyone
         PHASE_MARK(3);
 
-        if (tile != NO_TILE) {
+        // Between the two barriers only the look-back warps (0-2) have real work; everything that talks to L2 with a
+        // "strong" operation (each holds its warp for hundreds of cycles) is given to one thread of an otherwise idle
+        // warp: the claim to warp 3, the aggregate's publication to warp 4, the prefix's (after B3) to warp 5.
+        constexpr uint32_t PUBLISH_AGG = 128, PUBLISH_PREFIX = 160;
+        static_assert(FUSED_BLOCK >= 192, "role threads");
+        auto aggregate = [&]() {
             uint32_t warp_excl = 0, tile_agg = 0;
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) {
@@ -762,17 +776,16 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             }
             cur.warp_excl = warp_excl;
             cur.tile_agg = tile_agg;
-            if (tid == 0) {
-                st_status(status + tile, ST_FLAG_AGG | (uint64_t)tile_agg);
-                red_status(ws.super + tile / FUSED_SUPER, (1ull << 56) + (uint64_t)tile_agg);
+        };
+        if (tile != NO_TILE && warp > FUSED_SUPER / 32) {
+            aggregate();
+            if (tid == PUBLISH_AGG) {
+                st_status(status + tile, ST_FLAG_AGG | (uint64_t)cur.tile_agg);
+                red_status(ws.super + tile / FUSED_SUPER, (1ull << 56) + (uint64_t)cur.tile_agg);
             } else if (tid == CLAIMER) {
-                // next tile: claimed by a thread outside the three look-back warps; nobody waits for the atomic's
-                // round trip before barrier B3 — the claimer picks the result up after it and stages the query copies
-#ifdef GT_STATIC_TILES
-                lb_pre = tile + gridDim.x;
-#else
+                // next tile: nobody waits for the atomic's round trip before barrier B3 — the claimer picks the result
+                // up after it and stages the query copies
                 lb_pre = atomicAdd(ws.counter, 1u);
-#endif
             }
         }
         PHASE_MARK(4);
@@ -796,8 +809,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 const uint32_t pmask = __ballot_sync(FULL, (v >> 62) == 2);
                 uint64_t val = v & ST_MASK;
                 if (pmask && lane > (uint32_t)(__ffs(pmask) - 1)) val = 0;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(FULL, val, d);
+                val = warp_sum_u63(val);
                 if (lane == 0) {
                     s_lb_sum[par][warp] = val;
                     s_lb_p[par][warp] = pmask != 0;
@@ -819,9 +831,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     const uint32_t pmask = __ballot_sync(FULL, (v >> 62) == 3);
                     uint64_t val = v & SUPER_MASK;
                     if (pmask && lane > (uint32_t)(__ffs(pmask) - 1)) val = 0;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(FULL, val, d);
-                    acc += val;
+                    acc += warp_sum_u63(val);
                     if (pmask) break;
                     sj -= 32;  // rare: no finished supertile among the last 32 (2 048 tiles)
                     v = sj >= 0 ? ld_status(ws.super + sj) : (3ull << 62);
@@ -832,6 +842,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             }
             __syncthreads();  // B3
             if (tid == CLAIMER) stage_tile(par ^ 1, tile != NO_TILE ? (uint32_t)lb_pre : NO_TILE);
+            if (tile != NO_TILE && warp <= FUSED_SUPER / 32) aggregate();  // the look-back warps catch up on `cur`
             uint64_t excl = s_lb_sum[par][0];
             if (!s_lb_p[par][0]) {
                 excl += s_lb_sum[par][1];
@@ -843,7 +854,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
 #endif
             const uint64_t tile_start = (uint64_t)prev.tile * TILE;
             const uint64_t tile_base = base + excl;
-            if (tid == 0) {
+            if (tid == PUBLISH_PREFIX) {
                 st_status(status + prev.tile, ST_FLAG_PREFIX | (excl + prev.tile_agg));
                 // the supertile's first tile contributes the prefix in front of the supertile, exactly once
                 if ((prev.tile & (FUSED_SUPER - 1)) == 0) red_status(ws.super + prev.tile / FUSED_SUPER, (1ull << 63) + excl);
@@ -942,8 +953,9 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 }
             }
             PHASE_MARK(7);
-        } else if (tid == CLAIMER) {
-            stage_tile(par ^ 1, tile != NO_TILE ? (uint32_t)lb_pre : NO_TILE);
+        } else {
+            if (tid == CLAIMER) stage_tile(par ^ 1, tile != NO_TILE ? (uint32_t)lb_pre : NO_TILE);
+            if (tile != NO_TILE && warp <= FUSED_SUPER / 32) aggregate();
         }
         return tile != NO_TILE;
     };
