@@ -357,3 +357,50 @@ def test_parse_bed_errors_and_tokenize_bed_file(api, fixture_dir, tmp_path):
     assert tok.encode_bed_file(gz) == tok.encode(api.RegionSet(gz))
     miss = write("miss.bed", "chrNope\t1\t2\nchr1\t1\t2\n")
     assert tok.encode_bed_file(miss) == tok.encode(api.RegionSet(miss)) == [tok.unk_token_id]
+
+
+def test_parse_bed_fuzz_vs_oracle(api, tmp_path):
+    """Randomised small BED texts (odd separators, empty fields, signs, overflow, comments anywhere, missing final
+    newline): the device parser accepts exactly the files the restated RegionSet::try_from accepts, with the same regions."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(20261017)
+    names = ["chr1", "chr2", "chrX", "c"]
+    starts = ["0", "5", "+7", "12", "4294967295", "4294967296", "-1", "", " 3", "3 ", "1e3", "0x10", "007"]
+    tails = ["", "\tname", "\tname\t0\t+", "\t", "\t\t"]
+    n_ok = n_bad = 0
+    for it in range(300):
+        lines = []
+        for _ in range(int(rng.integers(1, 7))):
+            k = rng.random()
+            if k < 0.08:
+                lines.append(["#c", "track t", "browser b", "# chr1\t1\t2"][int(rng.integers(0, 4))])
+            elif k < 0.12:
+                lines.append(["", "chr1", "chr1\t5", "chr1 5 9"][int(rng.integers(0, 4))])
+            else:
+                # mostly well-formed numbers, sometimes one of the odd spellings
+                s = starts[int(rng.integers(0, len(starts)))] if rng.random() < 0.15 else str(int(rng.integers(0, 1000)))
+                e = starts[int(rng.integers(0, len(starts)))] if rng.random() < 0.15 else str(int(rng.integers(0, 2000)))
+                lines.append(names[int(rng.integers(0, len(names)))] + "\t" + s + "\t" + e + tails[int(rng.integers(0, len(tails)))])
+        if rng.random() < 0.1:
+            lines.insert(0, "chrom\tstart\tend")
+        nl = "\r\n" if rng.random() < 0.2 else "\n"
+        text = nl.join(lines) + (nl if rng.random() < 0.7 else "")
+        p = str(tmp_path / f"f{it}.bed")
+        with open(p, "w", newline="") as f:
+            f.write(text)
+        try:
+            ref = orc.regionset_from_file(p)
+        except ValueError:
+            ref = None
+        try:
+            c, s_, e_ = api.parse_bed_file(p, names)
+            got = list(zip([names[i] for i in c.tolist()], s_.tolist(), e_.tolist()))
+        except api.GtarsError:
+            got = None
+        if ref is None:
+            assert got is None, (it, text)
+            n_bad += 1
+        else:
+            assert got == [tuple(r) for r in ref], (it, text)
+            n_ok += 1
+    assert n_ok > 50 and n_bad > 50
