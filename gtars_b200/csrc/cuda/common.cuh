@@ -61,12 +61,14 @@ struct ChromMeta {    // 32 bytes
 // in one die's half of the L2.  Windows with more than two candidates or a non-contiguous candidate run,
 // chromosomes with several AIList components or with start > end intervals, wider or degenerate queries all fall
 // back to the LUT + walk path below, so results never depend on the table.
-// Window word encodings:  0 = empty;  (first << 2) | n, n in {1,2} = direct run;  BT_POOL_FLAG | (offset << 3) | n,
-// n in 1..BT_POOL_MAX = candidate list bt_pool[offset .. offset+n) of entry indices, stored in the backend's emission
+// Window word encodings:  0 = empty;  (first << 2) | n, n in {1,2} = direct run;  BT_POOL_FLAG | (offset << 4) | n,
+// n in 1..BT_POOL_MAX (15) = candidate list bt_pool[offset .. offset+n) of entry indices, stored in the backend's emission
 // order (covers nested intervals and multi-component AIList chromosomes);  BT_OVERFLOW = more candidates than that.
 #define BT_OVERFLOW 0xFFFFFFFFu
 #define BT_POOL_FLAG 0x80000000u
-#define BT_POOL_MAX 7u
+#define BT_POOL_MAX 15u   // candidates a pool list may hold (4-bit length field)
+#define BT_POOL_SHIFT 4   // word = BT_POOL_FLAG | offset << BT_POOL_SHIFT | n
+#define BT_SEMI_MAX 7u    // per-query hit count up to which a warp keeps packed offsets (row sums fit a byte)
 #define BT_GENERIC_CHROM 0x80000000u  // in ChromBT.n_bins: this chromosome always takes the generic path
 #define BT_MULTI_COMP 0x40000000u     // in ChromBT.n_bins: several AIList components (lists of different windows cannot be merged)
 #define BT_NBINS_MASK 0x3FFFFFFFu

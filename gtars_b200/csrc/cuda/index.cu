@@ -305,8 +305,8 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
                 if (n == 0) continue;
                 if (single && n <= 2 && w_max[k] - w_min[k] + 1 == n) {
                     bt_lut[k] = (w_min[k] << 2) | n;
-                } else if (n <= BT_POOL_MAX && pool_size + n < (1ull << 28) - 8) {
-                    bt_lut[k] = BT_POOL_FLAG | ((uint32_t)pool_size << 3) | n;
+                } else if (n <= BT_POOL_MAX && pool_size + n < (1ull << (31 - BT_POOL_SHIFT)) - 16) {
+                    bt_lut[k] = BT_POOL_FLAG | ((uint32_t)pool_size << BT_POOL_SHIFT) | n;
                     pool_size += n;
                     ++bt_pool_windows;
                 } else {
@@ -327,7 +327,7 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
                     for_each_window(c, i, [&](uint64_t k) {
                         const uint32_t w = bt_lut[k];
                         if (w == BT_OVERFLOW || !(w & BT_POOL_FLAG)) return;
-                        bt_pool[((w & ~BT_POOL_FLAG) >> 3) + fill[k]++] = i;
+                        bt_pool[((w & ~BT_POOL_FLAG) >> BT_POOL_SHIFT) + fill[k]++] = i;
                     });
                 }
             }

@@ -295,8 +295,8 @@ __device__ __forceinline__ bool window_walk(const IndexView& ix, uint32_t c, uin
         if (w == 0) continue;
         const uint32_t wstart = j == 0 ? 0u : b << sh;  // later windows skip what an earlier window already listed
         const bool pool = (w & BT_POOL_FLAG) != 0;
-        const uint32_t n = pool ? (w & 7u) : (w & 3u);
-        const uint32_t first = pool ? (w & ~BT_POOL_FLAG) >> 3 : w >> 2;
+        const uint32_t n = pool ? (w & BT_POOL_MAX) : (w & 3u);
+        const uint32_t first = pool ? (w & ~BT_POOL_FLAG) >> BT_POOL_SHIFT : w >> 2;
         for (uint32_t t = 0; t < n; ++t) {
             // pool lists are stored in emission order; direct runs ascend, so AIList reads them backwards
             const uint32_t idx = pool ? __ldg(ix.bt_pool + first + t) : (desc ? first + n - 1 - t : first + t);
@@ -685,8 +685,9 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     bool ordered;
                     const uint32_t w = cur.v0[k];
                     if (((cur.slow >> k) & 0x10u) == 0 && w != BT_OVERFLOW && qs[k] < qe[k]) {
-                        const uint32_t nl = w & 7u, first = (w & ~BT_POOL_FLAG) >> 3;
+                        const uint32_t nl = w & BT_POOL_MAX, first = (w & ~BT_POOL_FLAG) >> BT_POOL_SHIFT;
                         c = 0;
+#pragma unroll 1
                         for (uint32_t t = 0; t < nl; ++t) {
                             const uint4 E = ldg128(ix.bt_ent + __ldg(ix.bt_pool + first + t));
                             if (!cand_hit<FILTER>(E.x, E.y, qs[k], qe[k], min_bp)) continue;
@@ -712,7 +713,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 }
                 cur.slow &= 0xFu;
                 cur.cntpack = min(cnt[0], 3u) | (min(cnt[1], 3u) << 2) | (min(cnt[2], 3u) << 4) | (min(cnt[3], 3u) << 6);
-                if (!__any_sync(FULL, (cnt[0] | cnt[1] | cnt[2] | cnt[3]) > BT_POOL_MAX)) {
+                if (!__any_sync(FULL, (cnt[0] | cnt[1] | cnt[2] | cnt[3]) > BT_SEMI_MAX)) {
                     // pool-list windows (nested intervals, several AIList components): every count is at most 7, so a row
                     // sums to at most 224 — two scans of 16-bit fields; offsets inside a row stay packed in a register,
                     // the three row bases (warp-uniform) go to shared memory, and s_aux keeps the two-hit second vals
