@@ -384,15 +384,17 @@ def test_tokenize_files_runs_variant(ctx, monkeypatch):
 
 
 @pytest.mark.parametrize("kind", ["bits", "ailist"])
-def test_pooled_windows_differential(ctx, kind):
-    """Moderately overlapping / nested universe and narrow queries: most windows hold 3-7 candidates, so the pooled
-    candidate lists of the window table (not the direct runs, not the generic walk) resolve them."""
+@pytest.mark.parametrize("wide_frac", [0.1, 0.3])
+def test_pooled_windows_differential(ctx, kind, wide_frac):
+    """Moderately (most windows hold 3-7 candidates) and heavily (8-15, some beyond) overlapping / nested universes and
+    narrow queries: the pooled candidate lists of the window table (not the direct runs, rarely the generic walk)
+    resolve them; counts above 7 per query also exercise the unpacked-offset warps."""
     rng = np.random.default_rng(4242)
     n = 6000
     chr_ = np.sort(rng.integers(0, 2, n))
     offs = np.concatenate([[0], np.cumsum(np.bincount(chr_, minlength=2))]).astype(np.uint64)
     s = rng.integers(0, 1_500_000, n).astype(np.uint32)
-    w = np.where(rng.random(n) < 0.1, rng.integers(3000, 20000, n), rng.integers(50, 1500, n))
+    w = np.where(rng.random(n) < wide_frac, rng.integers(3000, 20000, n), rng.integers(50, 1500, n))
     e = (s + w).astype(np.uint32)
     v = rng.permutation(n).astype(np.uint32)
     g, o = _both(ctx, kind, offs, s, e, v)
