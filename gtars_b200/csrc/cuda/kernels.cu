@@ -1,10 +1,11 @@
 // kernels.cu — sm_100a kernels for count / any / find / tokenize.
 //
 // Nothing here is a dense contraction, so tensor cores are deliberately unused: the work is HBM-bound integer
-// search + stream compaction.  What matters is (1) 128-bit coalesced query loads (blocked 4 queries / thread),
-// (2) O(1) searches through L2-resident bin LUTs instead of 17–26-level bisections, (3) a single pass over the
-// queries for enumeration: count → block scan → decoupled look-back across tiles → emit, so no per-query
-// count/offset array ever round-trips through HBM, and (4) a persistent grid sized to the SM count.
+// search + stream compaction.  What matters is (1) query rows staged by TMA bulk copies, coalesced everywhere else,
+// (2) O(1) resolution through L2-resident tables (window records for find / tokenize, rank LUTs for counting) instead
+// of 17–26-level bisections, (3) a single pass over the queries for enumeration: count → scan → two-level decoupled
+// look-back across tiles → emit, so no per-query count/offset array ever round-trips through HBM, and (4) a
+// persistent grid sized to the SM count (a lean record-only kernel with the full kernel as its on-device fallback).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -542,11 +543,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
     if (tid == 0) {
         mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#ifdef GT_STATIC_TILES
-        stage_tile(0, blockIdx.x);
-#else
         stage_tile(0, atomicAdd(ws.counter, 1u));
-#endif
     }
     __syncthreads();
 
