@@ -284,6 +284,38 @@ def test_igd_random_differential(ctx, min_overlap):
     g.close()
 
 
+@pytest.mark.parametrize("min_overlap", [1, 25])
+def test_igd_large_batch_many_sets(ctx, min_overlap):
+    """A larger IGD batch (40 k queries, 90 files, 11 query sets incl. empty and one-query sets): both count semantics
+    identical to the oracle."""
+    from gtars_b200 import ffi
+    from oracle import oracle as orc
+    rng = np.random.default_rng(555 + min_overlap)
+    n_chroms, n_files = 3, 90
+    sizes = rng.integers(50, 400, n_files)
+    n = int(sizes.sum())
+    fo = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    dc = rng.integers(0, n_chroms, n).astype(np.uint32)
+    ds = rng.integers(0, 2_000_000, n).astype(np.uint32)
+    de = (ds + rng.integers(1, 30_000, n)).astype(np.uint32)
+    g = ffi.Igd(ctx, fo, n_chroms, dc, ds, de)
+    o = orc.Igd(fo, dc, ds, de)
+    set_sizes = [5000, 0, 1, 2047, 2048, 2049, 12000, 3, 0, 9000, 7000]
+    nq = sum(set_sizes)
+    assert nq >= 32768
+    so = np.concatenate([[0], np.cumsum(set_sizes)]).astype(np.uint64)
+    qc = rng.integers(0, n_chroms + 1, nq).astype(np.uint32)
+    qs = rng.integers(0, 2_010_000, nq).astype(np.uint32)
+    qe = (qs + rng.integers(1, 20_000, nq)).astype(np.uint32)
+    th = orc.max_threads()
+    want_pairs = o.count_set_overlaps(so, qc, qs, qe, min_overlap, threads=th)
+    want_hits = o.count_region_hits(so, qc, qs, qe, min_overlap, threads=th)
+    assert np.array_equal(g.count_set_overlaps(so, qc, qs, qe, min_overlap), want_pairs)
+    assert np.array_equal(g.count_region_hits(so, qc, qs, qe, min_overlap), want_hits)
+    assert int(want_pairs.sum()) > 100_000
+    g.close()
+
+
 @pytest.mark.parametrize("kind", ["bits", "ailist"])
 def test_fragments_random_differential(ctx, kind):
     rng = np.random.default_rng(77)
