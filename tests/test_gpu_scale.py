@@ -156,3 +156,64 @@ def test_c5_fragments_unsorted(ctx):
     assert np.array_equal(off, oo) and np.array_equal(ids, oi)
     counts = ix.count(qc, qs, qe)
     assert len(ids) == int(np.maximum(counts, 1).sum(dtype=np.uint64))  # per-fragment [unk]
+
+
+def test_scoring_matrix_properties_20m_fragments(ctx):
+    """gtars-scoring at scale (4 files x 5 M unsorted fragments vs the 1 M-peak universe): the count matrix must agree
+    with the independent counting kernel on the same lookups (ATAC: shifted start + reversed end interval; ChIP: the
+    fragment), file by file, and with the oracle on the head of a file."""
+    from gtars_b200 import ffi, synth
+    from oracle import oracle as orc
+    u, bits, (offs, s, e, v) = _universe(ctx, ffi.KIND_BITS)
+    n_files, per_file = 4, 5_000_000
+    q = synth.make_query_files(u, n_files, per_file, seed=synth.SEED_FRAGMENTS, device="cuda", sort_files=False)
+    qc, qs, qe = (_np(q[k]) for k in ("chr", "start", "end"))
+    fo = q["file_offsets"].cpu().numpy().astype(np.uint64)
+    n_cols = int(u["n"])
+    for mode in (ffi.SCORE_ATAC, ffi.SCORE_CHIP):
+        mat = bits.score_matrix(fo, qc, qs, qe, mode, n_cols)
+        if mode == ffi.SCORE_ATAC:
+            ns, ne = qs + np.uint32(4), qe - np.uint32(5)
+            counts = bits.count(qc, ns, ns + np.uint32(1)).astype(np.uint64) + bits.count(qc, ne, ne - np.uint32(1)).astype(np.uint64)
+        else:
+            counts = bits.count(qc, qs, qe).astype(np.uint64)
+        per_file_counts = np.add.reduceat(counts, fo[:-1].astype(np.int64))
+        assert np.array_equal(mat.sum(axis=1, dtype=np.uint64), per_file_counts), mode
+        assert int(mat.sum(dtype=np.uint64)) > per_file
+        m = 200_000
+        sub = np.array([0, m], dtype=np.uint64)
+        want = orc.score_matrix(orc.Index(orc.BITS, offs, s, e, v), sub, qc[:m], qs[:m], qe[:m], mode, n_cols, threads=orc.max_threads())
+        assert np.array_equal(bits.score_matrix(sub, qc[:m], qs[:m], qe[:m], mode, n_cols), want), mode
+
+
+def test_bed_ingest_properties_5m_lines(ctx, tmp_path):
+    """Device BED ingest at scale: 5 M lines written in shuffled order with comments sprinkled in come back as exactly
+    the source regions in RegionSet::sort order (stable: chromosome string, then start), and the tokens of the text
+    equal the tokens of the arrays."""
+    import torch
+    from gtars_b200 import ffi, synth
+    u, bits, _ = _universe(ctx, ffi.KIND_BITS)
+    n = 5_000_000
+    q = synth.make_query_files(u, 1, n, device="cuda", sort_files=False)
+    qc, qs, qe = (_np(q[k]) for k in ("chr", "start", "end"))
+    names = np.array(synth.CHROM_NAMES)
+    lines = np.char.add(np.char.add(np.char.add(np.char.add(names[qc], "\t"), qs.astype(str)), "\t"), qe.astype(str))
+    text = "# header comment\n" + "\n".join(lines.tolist()) + "\n"
+    blob = "".join(synth.CHROM_NAMES).encode()
+    name_off = np.zeros(len(synth.CHROM_NAMES) + 1, dtype=np.uint32)
+    name_off[1:] = np.cumsum([len(x) for x in synth.CHROM_NAMES])
+    import ctypes as C
+    L = ffi.lib()
+    n_out = C.c_uint64(0)
+    hc, hs, he = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    raw = text.encode()
+    ffi.check(L.gtgpu_parse_bed(ctx._h, raw, len(raw), len(synth.CHROM_NAMES), blob, name_off.ctypes.data_as(C.c_void_p),
+                                C.byref(n_out), C.byref(hc), C.byref(hs), C.byref(he)))
+    gc, gs, ge = ffi._take(hc), ffi._take(hs), ffi._take(he)
+    assert n_out.value == n == len(gc)
+    rank = np.argsort(np.argsort(names, kind="stable"), kind="stable")       # lexicographic rank of every chromosome name
+    order = np.lexsort((qs, rank[qc]))                                         # stable: rank, then start
+    assert np.array_equal(gc, qc[order]) and np.array_equal(gs, qs[order]) and np.array_equal(ge, qe[order])
+    ids_text = bits.tokenize_bed(raw, list(synth.CHROM_NAMES), int(u["unk_id"]))
+    off, ids_arr = bits.tokenize_files(np.array([0, n], dtype=np.uint64), gc, gs, ge, u["unk_id"])
+    assert np.array_equal(ids_text, ids_arr)
