@@ -104,11 +104,12 @@ std::string read_file_bytes(const std::string& path) {
         while ((n = gzread(f, buf, sizeof buf)) > 0) data.append(buf, n);
         gzclose(f);
     } else {
-        std::ifstream f(path, std::ios::binary);
+        std::ifstream f(path, std::ios::binary | std::ios::ate);
         if (!f) throw Error("Failed to open file: \"" + path + "\"");
-        std::stringstream ss;
-        ss << f.rdbuf();
-        data = ss.str();
+        const std::streamsize size = f.tellg();
+        f.seekg(0);
+        data.resize((size_t)std::max<std::streamsize>(size, 0));
+        if (size > 0 && !f.read(&data[0], size)) throw Error("Failed to read file: \"" + path + "\"");
     }
     return data;
 }
@@ -205,30 +206,64 @@ void append_tokens_to_gtok_file(const std::string& filename, const std::vector<u
 }
 
 // ---- RegionSet ---------------------------------------------------------------------------------------------------------
+namespace {
+// str::parse::<u32>() over [a, b): optional '+', at least one digit, digits only, no overflow
+bool parse_u32_range(const char* a, const char* b, uint32_t& out) {
+    if (a < b && *a == '+') ++a;
+    if (a >= b) return false;
+    uint64_t v = 0;
+    for (; a < b; ++a) {
+        if (*a < '0' || *a > '9') return false;
+        v = v * 10 + (uint64_t)(*a - '0');
+        if (v > 0xFFFFFFFFull) return false;
+    }
+    out = (uint32_t)v;
+    return true;
+}
+bool starts_with(const char* a, const char* b, const char* p) {
+    const size_t n = strlen(p);
+    return (size_t)(b - a) >= n && memcmp(a, p, n) == 0;
+}
+}  // namespace
+
 RegionSet RegionSet::from_file(const std::string& path) {
+    // One pass over the file's bytes (no per-line strings): BufRead::lines() splitting, then region_set.rs:60-185.
     RegionSet rs;
+    const std::string data = read_file_bytes(path);
+    const char* p = data.data();
+    const char* const end = p + data.size();
     bool first_line = true;
-    for (const auto& line : read_lines(path)) {
-        auto parts = split_on(line, '\t');
-        if (has_prefix(line, "browser") || has_prefix(line, "track") || has_prefix(line, "#")) {
-            rs.header += line;
+    while (p < end) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        const char* le = nl ? nl : end;              // line = [p, le)
+        const char* next = nl ? nl + 1 : end;
+        if (le > p && le[-1] == '\r') --le;
+        if (starts_with(p, le, "browser") || starts_with(p, le, "track") || starts_with(p, le, "#")) {
+            rs.header.append(p, le);
             first_line = false;
+            p = next;
             continue;
         }
+        const char* t1 = (const char*)memchr(p, '\t', (size_t)(le - p));
+        const char* t2 = t1 ? (const char*)memchr(t1 + 1, '\t', (size_t)(le - t1 - 1)) : nullptr;
+        const char* t3 = t2 ? (const char*)memchr(t2 + 1, '\t', (size_t)(le - t2 - 1)) : nullptr;
+        const bool three = t1 && t2;
+        Region r;
+        const bool s_ok = three && parse_u32_range(t1 + 1, t2, r.start);
         if (first_line) {
             first_line = false;
-            uint32_t tmp;
-            if (parts.size() >= 3 && !parse_u32(parts[1], tmp)) {  // column header row without '#'
-                rs.header += line;
+            if (three && !s_ok) {  // column header row without '#'
+                rs.header.append(p, le);
+                p = next;
                 continue;
             }
         }
-        Region r;
-        if (parts.size() < 3 || !parse_u32(parts[1], r.start)) throw Error("Error in parsing start position: " + line);
-        if (!parse_u32(parts[2], r.end)) throw Error("Error in parsing end position: " + line);
-        r.chr = parts[0];
-        for (size_t k = 3; k < parts.size(); ++k) r.rest += (k > 3 ? "\t" : "") + parts[k];
+        if (!s_ok) throw Error("Error in parsing start position: " + std::string(p, le));
+        if (!parse_u32_range(t2 + 1, t3 ? t3 : le, r.end)) throw Error("Error in parsing end position: " + std::string(p, le));
+        r.chr.assign(p, t1);
+        if (t3) r.rest.assign(t3 + 1, le);  // parts[3..].join("\t") is the remainder of the line as written
         rs.regions.push_back(std::move(r));
+        p = next;
     }
     if (rs.regions.empty()) throw Error("Corrupted file. 0 regions found in the file: " + path);
     rs.sort();
@@ -236,10 +271,40 @@ RegionSet RegionSet::from_file(const std::string& path) {
 }
 
 void RegionSet::sort() {
-    std::stable_sort(regions.begin(), regions.end(), [](const Region& a, const Region& b) {
-        int c = a.chr.compare(b.chr);
-        return c != 0 ? c < 0 : a.start < b.start;
-    });
+    // region_set.rs:502-505: stable, by (chromosome string, start).  Chromosome names repeat millions of times, so they
+    // are ranked once and the sort runs on (rank, start, original position) integers.
+    const size_t n = regions.size();
+    std::unordered_map<std::string, uint32_t> ids;
+    std::vector<uint32_t> cid(n);
+    std::vector<const std::string*> names;
+    for (size_t i = 0; i < n; ++i) {
+        auto it = ids.find(regions[i].chr);
+        if (it == ids.end()) {
+            it = ids.emplace(regions[i].chr, (uint32_t)names.size()).first;
+            names.push_back(&it->first);
+        }
+        cid[i] = it->second;
+    }
+    std::vector<uint32_t> by_name(names.size()), rank(names.size());
+    for (uint32_t k = 0; k < by_name.size(); ++k) by_name[k] = k;
+    std::sort(by_name.begin(), by_name.end(), [&](uint32_t a, uint32_t b) { return *names[a] < *names[b]; });
+    for (uint32_t r = 0; r < by_name.size(); ++r) rank[by_name[r]] = r;
+    struct Key {
+        uint64_t k;   // rank << 32 | start
+        uint64_t pos; // original position: the tie-break that makes the sort stable
+    };
+    std::vector<Key> keys(n);
+    bool sorted = true;
+    for (size_t i = 0; i < n; ++i) {
+        keys[i] = Key{((uint64_t)rank[cid[i]] << 32) | regions[i].start, i};
+        if (i && keys[i].k < keys[i - 1].k) sorted = false;
+    }
+    if (sorted) return;
+    std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.k != b.k ? a.k < b.k : a.pos < b.pos; });
+    std::vector<Region> out;
+    out.reserve(n);
+    for (const Key& key : keys) out.push_back(std::move(regions[key.pos]));
+    regions = std::move(out);
 }
 
 // ---- Device / ChromMap -----------------------------------------------------------------------------------------------------
