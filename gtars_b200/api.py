@@ -512,6 +512,16 @@ class Igd:
         return [int(x) for x in self._count([regions], min_overlap, False)[0]]
 
 
+def write_igd_file(region_sets, names, path):
+    """Igd::from_named_region_sets + Igd::save (igd.rs:285-317, 418-486) without building a device index: `path`
+    (.igd) and the companion .tsv, byte for byte what the reference writes.  Host-only."""
+    sets = [_as_rs(s) for s in region_sets]
+    arr = (C.c_void_p * max(len(sets), 1))(*[s._h for s in sets])
+    nm = (C.c_char_p * max(len(names), 1))(*[n.encode() for n in names])
+    if lib().gth_igd_save_sets(len(sets), arr, nm, os.fsencode(path)):
+        _fail()
+
+
 def lola_contingency(igd: Igd, user_sets, universe, min_overlap=1) -> np.ndarray:
     """run_lola up to the 2x2 tables (gtars-lola/src/enrichment.rs:198-220): int64 [n_user, n_db, 4] = a, b, c, d."""
     sets = [_as_rs(s) for s in user_sets]

@@ -78,3 +78,92 @@ def test_gtok_files_match_reference_bytes(golden, tmp_path):
     open(bad, "wb").write(b"NOPE\x01\x00\x00")
     with pytest.raises(api.GtarsError):
         api.read_tokens_from_gtok(bad)
+
+
+def test_host_regionset_parser_matches_oracle(tmp_path, fixture_dir):
+    """The host layer's RegionSet::try_from (one pass over the bytes, integer-key stable sort) against the oracle's
+    line-by-line restatement: fixture files, a large shuffled file with many ties, and fuzzed / malformed texts.
+    Host-only code: runs without a GPU."""
+    import numpy as np
+    from gtars_b200 import api
+    from oracle import oracle as orc
+
+    def same(p):
+        try:
+            ref = orc.regionset_from_file(p)
+        except ValueError:
+            ref = None
+        try:
+            got = [(r.chr, r.start, r.end) for r in api.RegionSet(p)]
+        except api.GtarsError:
+            got = None
+        assert (ref is None) == (got is None), p
+        if ref is not None:
+            assert got == [tuple(r) for r in ref], p
+        return ref is not None
+
+    for rel in ("to_tokenize.bed", "tokenizers/peaks.bed", "tokenizers/peaks.bed.gz", "tokenizers/peaks.scored.bed",
+                "igd_file_list_01/igd_bed_file_1.bed", "consensus/consensus1.bed"):
+        assert same(os.path.join(fixture_dir, rel))
+    rng = np.random.default_rng(3)
+    names = ["chr1", "chr10", "chr2", "chrX", "chr1_alt"]
+    p = str(tmp_path / "ties.bed")
+    with open(p, "w") as f:
+        f.write("\n".join(f"{names[int(a)]}\t{int(b)}\t{int(b) + i % 7}\tn{i}" for i, (a, b) in
+                          enumerate(zip(rng.integers(0, 5, 50_000), rng.integers(0, 2_000, 50_000)))) + "\n")
+    assert same(p)
+    rs = api.RegionSet(p)
+    assert len(rs) == 50_000
+    starts = ["0", "5", "+7", "12", "4294967295", "4294967296", "-1", "", " 3", "3 ", "007"]
+    tails = ["", "\tname", "\tname\t0\t+", "\t", "\t\t", "\ta b"]
+    n_ok = n_bad = 0
+    for it in range(300):
+        lines = []
+        for _ in range(int(rng.integers(1, 7))):
+            k = rng.random()
+            if k < 0.08:
+                lines.append(["#c", "track t", "browser b"][int(rng.integers(0, 3))])
+            elif k < 0.12:
+                lines.append(["", "chr1", "chr1\t5", "chr1 5 9"][int(rng.integers(0, 4))])
+            else:
+                a = starts[int(rng.integers(0, len(starts)))] if rng.random() < 0.15 else str(int(rng.integers(0, 1000)))
+                b = starts[int(rng.integers(0, len(starts)))] if rng.random() < 0.15 else str(int(rng.integers(0, 2000)))
+                lines.append(names[int(rng.integers(0, 5))] + "\t" + a + "\t" + b + tails[int(rng.integers(0, len(tails)))])
+        if rng.random() < 0.1:
+            lines.insert(0, "chrom\tstart\tend")
+        nl = "\r\n" if rng.random() < 0.2 else "\n"
+        q = str(tmp_path / f"f{it}.bed")
+        with open(q, "w", newline="") as f:
+            f.write(nl.join(lines) + (nl if rng.random() < 0.7 else ""))
+        if same(q):
+            n_ok += 1
+        else:
+            n_bad += 1
+    assert n_ok > 50 and n_bad > 50
+
+
+def test_host_igd_writer_matches_oracle_bytes(golden, fixture_dir, tmp_path):
+    """Igd::save (igd.rs:418-486) as written by the host layer == the oracle's restatement, byte for byte, for the
+    reference's LOLA / IGD fixture databases; the .tsv carries index, name, region count and the two-decimal average."""
+    from gtars_b200 import api
+    from oracle import oracle as orc
+    k = golden[1]["K8_inputs"]
+    for db, rels in k["dbs"].items():
+        sets = [api.RegionSet(os.path.join(fixture_dir, r)) for r in rels]
+        names = [f"{i}_{os.path.basename(r)}" for i, r in enumerate(rels)]
+        p = str(tmp_path / f"{db}.igd")
+        api.write_igd_file(sets, names, p)
+        chrom_ids, o = {}, orc.Igd()
+        for f, rs in enumerate(sets):
+            for r in rs:
+                if r.start < r.end:
+                    o.add(chrom_ids.setdefault(r.chr, len(chrom_ids)), r.start, r.end, 0, f)
+        o.finalize()
+        po = str(tmp_path / f"{db}.oracle.igd")
+        o.save(po, list(chrom_ids))
+        assert open(p, "rb").read() == open(po, "rb").read(), db
+        tsv = open(str(tmp_path / f"{db}.tsv")).read().splitlines()
+        assert tsv[0] == "Index\tFile\tNumber of Regions\tAvg size" and len(tsv) == 1 + len(sets)
+        for i, rs in enumerate(sets):
+            kept = [r for r in rs if r.start < r.end]
+            assert tsv[1 + i] == "%d\t%s\t%d\t%.2f" % (i, names[i], len(kept), sum(r.end - r.start for r in kept) / len(kept))
