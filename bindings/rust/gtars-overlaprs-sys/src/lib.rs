@@ -56,6 +56,10 @@ extern "C" {
                            out_start: *mut *mut gtgpu_buf, out_end: *mut *mut gtgpu_buf) -> i32;
     pub fn gtgpu_tokenize_bed(index: *mut gtgpu_index, text: *const u8, n_bytes: u64, n_names: u32, names: *const u8,
                               name_offsets: *const u32, unk_id: u32, out_ids: *mut *mut gtgpu_buf) -> i32;
+    pub fn gtgpu_tokenize_fragments_text(index: *mut gtgpu_index, text: *const u8, n_bytes: u64, n_names: u32, names: *const u8,
+                                         name_offsets: *const u32, unk_id: u32, out_n_barcodes: *mut u32,
+                                         out_barcode_spans: *mut *mut gtgpu_buf, out_barcode_offsets: *mut *mut gtgpu_buf,
+                                         out_ids: *mut *mut gtgpu_buf) -> i32;
     pub fn gtgpu_tokenize_fragments(index: *mut gtgpu_index, n: u64, chr: *const u32, start: *const u32, end: *const u32,
                                     barcode_id: *const u32, n_barcodes: u32, unk_id: u32, out_barcode_offsets: *mut u64,
                                     out_ids: *mut *mut gtgpu_buf) -> i32;

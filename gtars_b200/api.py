@@ -54,7 +54,7 @@ def lib():
             "gth_tokenizer_vocab_size": (u64, [vp]), "gth_tokenizer_token_to_id": (i64, [vp, cp]),
             "gth_tokenizer_id_to_token": (cp, [vp, u32]), "gth_tokenizer_special": (cp, [vp, C.c_int]),
             "gth_tokenizer_kind": (C.c_int, [vp]), "gth_tokenizer_encode_batch": (vp, [vp, u64, vp]),
-            "gth_tokenizer_fragments": (vp, [vp, cp]), "gth_tokenizer_encode_bed_file": (vp, [vp, cp]),
+            "gth_tokenizer_fragments": (vp, [vp, cp]), "gth_tokenizer_fragments_device": (vp, [vp, cp]), "gth_tokenizer_encode_bed_file": (vp, [vp, cp]),
             "gth_parse_bed_file": (vp, [vp, cp, u64, vp]), "gth_gtok_write": (C.c_int, [cp, u64, vp, C.c_int]),
             "gth_gtok_read": (vp, [cp]),
             "gth_igd_single": (vp, [vp, vp]), "gth_igd_find_pairs": (vp, [vp, vp, i32]),
@@ -435,9 +435,11 @@ class Tokenizer:
         return {"input_ids": ids, "attention_mask": [1] * len(ids)}
 
 
-def tokenize_fragment_file(path, tokenizer: Tokenizer) -> dict:
-    """gtars.tokenizers.tokenize_fragment_file (gtars-tokenizers/src/utils/fragments.rs:61-82): barcode -> token ids."""
-    return dict(_take_lists(lib().gth_tokenizer_fragments(tokenizer._h, os.fsencode(path)), named=True))
+def tokenize_fragment_file(path, tokenizer: Tokenizer, device_parse: bool = False) -> dict:
+    """gtars.tokenizers.tokenize_fragment_file (gtars-tokenizers/src/utils/fragments.rs:61-82): barcode -> token ids.
+    device_parse=True also parses the text and numbers the barcodes on the device (gtgpu_tokenize_fragments_text)."""
+    fn = lib().gth_tokenizer_fragments_device if device_parse else lib().gth_tokenizer_fragments
+    return dict(_take_lists(fn(tokenizer._h, os.fsencode(path)), named=True))
 
 
 class Igd:

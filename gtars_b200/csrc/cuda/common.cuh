@@ -181,7 +181,8 @@ namespace gtgpu {
 enum ScratchRole {
     SC_CHR = 0, SC_START, SC_END, SC_BARCODE, SC_OUT_IDS, SC_OUT_IDS2, SC_OUT_OFFS, SC_FILE_OFFS, SC_FILE_TOK,
     SC_FILE_TOK2, SC_TILE_STATUS, SC_TILE_FILE, SC_MISC, SC_COUNTS, SC_IN2_CHR, SC_IN2_START, SC_IN2_END,
-    SC_IN3_CHR, SC_IN3_START, SC_IN3_END, SC_SET_ID, SC_MATRIX, SC_N_ROLES
+    SC_IN3_CHR, SC_IN3_START, SC_IN3_END, SC_SET_ID, SC_MATRIX, SC_ING_0, SC_ING_1, SC_ING_2, SC_ING_3, SC_ING_4, SC_ING_5,
+    SC_ING_6, SC_ING_7, SC_N_ROLES
 };
 
 // kernels.cu
@@ -230,6 +231,11 @@ int32_t launch_unk_expand(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* d_ra
 int32_t fused_find_all(gtgpu_index* ix, uint64_t nq, uint64_t n_files, const uint64_t* d_qfo, const uint32_t* d_qc,
                        const uint32_t* d_qs, const uint32_t* d_qe, uint64_t* d_offsets, uint64_t* d_file_tok,
                        uint32_t** d_ids, uint64_t* total_out);
+
+// fragments.cu: tokenize_fragment_file over device-resident fragments with dense barcode ids (caller holds ctx->mu)
+int32_t tokenize_fragments_core(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start, const uint32_t* d_end,
+                                uint32_t* d_bc, uint32_t n_barcodes, uint32_t unk_id, uint64_t* out_barcode_offsets,
+                                gtgpu_buf** out_ids);
 
 // sort.cu — hand-written scan / radix sort
 size_t exclusive_scan_temp_bytes(uint64_t n, size_t elem);

@@ -63,27 +63,18 @@ __global__ void frag_scatter_kernel(uint64_t n, const uint32_t* __restrict__ ord
 
 using namespace gtgpu;
 
-extern "C" int32_t gtgpu_tokenize_fragments(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start,
-                                            const uint32_t* end, const uint32_t* barcode_id, uint32_t n_barcodes,
-                                            uint32_t unk_id, uint64_t* out_barcode_offsets, gtgpu_buf** out_ids) {
-    if (!ix || !out_barcode_offsets || !out_ids || (n && (!chr || !start || !end || !barcode_id)))
-        return fail(GTGPU_ERR_INVALID, "tokenize_fragments: null argument");
-    if (n >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "tokenize_fragments: more than 2^32-2 fragments per call");
-    for (uint64_t i = 0; i < n; ++i)
-        if (barcode_id[i] >= n_barcodes) return fail(GTGPU_ERR_INVALID, "tokenize_fragments: barcode id out of range");
-    gtgpu_ctx* ctx = ix->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    GT_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
+namespace gtgpu {
 
-    uint32_t *d_chr, *d_start, *d_end, *d_bc, *d_bc_sorted, *d_idx, *d_order, *d_raw = nullptr, *d_out = nullptr;
+// Device-resident core (the caller holds ctx->mu): fragments in d_chr / d_start / d_end, dense barcode ids in d_bc.
+int32_t tokenize_fragments_core(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start, const uint32_t* d_end,
+                                uint32_t* d_bc, uint32_t n_barcodes, uint32_t unk_id, uint64_t* out_barcode_offsets,
+                                gtgpu_buf** out_ids) {
+    gtgpu_ctx* ctx = ix->ctx;
+    cudaStream_t st = ctx->stream;
+    uint32_t *d_bc_sorted, *d_idx, *d_order, *d_raw = nullptr, *d_out = nullptr;
     uint64_t *d_off, *d_bco, *d_misc;
     unsigned long long *d_cnt, *d_dst;
     void* d_ws;
-    GT_TRY(ctx->scratch_get(SC_CHR, n * 4, (void**)&d_chr));
-    GT_TRY(ctx->scratch_get(SC_START, n * 4, (void**)&d_start));
-    GT_TRY(ctx->scratch_get(SC_END, n * 4, (void**)&d_end));
-    GT_TRY(ctx->scratch_get(SC_BARCODE, n * 4, (void**)&d_bc));
     GT_TRY(ctx->scratch_get(SC_IN2_CHR, n * 4, (void**)&d_bc_sorted));
     GT_TRY(ctx->scratch_get(SC_IN2_START, n * 4, (void**)&d_idx));
     GT_TRY(ctx->scratch_get(SC_IN2_END, n * 4, (void**)&d_order));
@@ -93,12 +84,6 @@ extern "C" int32_t gtgpu_tokenize_fragments(gtgpu_index* ix, uint64_t n, const u
     GT_TRY(ctx->scratch_get(SC_FILE_TOK, ((uint64_t)n_barcodes + 1) * 8, (void**)&d_bco));
     GT_TRY(ctx->scratch_get(SC_TILE_STATUS, fused_workspace_bytes(n), &d_ws));
     GT_TRY(ctx->scratch_get(SC_MISC, 64, (void**)&d_misc));
-    if (n) {
-        GT_CUDA(cudaMemcpyAsync(d_chr, chr, n * 4, cudaMemcpyHostToDevice, st));
-        GT_CUDA(cudaMemcpyAsync(d_start, start, n * 4, cudaMemcpyHostToDevice, st));
-        GT_CUDA(cudaMemcpyAsync(d_end, end, n * 4, cudaMemcpyHostToDevice, st));
-        GT_CUDA(cudaMemcpyAsync(d_bc, barcode_id, n * 4, cudaMemcpyHostToDevice, st));
-    }
 
     // 1. hits of every fragment, raw (no unk yet), with per-fragment offsets
     uint64_t cap = n + n / 4 + 1024, total = 0;
@@ -168,4 +153,32 @@ extern "C" int32_t gtgpu_tokenize_fragments(gtgpu_index* ix, uint64_t n, const u
     }
     *out_ids = buf;
     return GTGPU_OK;
+}
+
+}  // namespace gtgpu
+
+extern "C" int32_t gtgpu_tokenize_fragments(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start,
+                                            const uint32_t* end, const uint32_t* barcode_id, uint32_t n_barcodes,
+                                            uint32_t unk_id, uint64_t* out_barcode_offsets, gtgpu_buf** out_ids) {
+    if (!ix || !out_barcode_offsets || !out_ids || (n && (!chr || !start || !end || !barcode_id)))
+        return fail(GTGPU_ERR_INVALID, "tokenize_fragments: null argument");
+    if (n >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "tokenize_fragments: more than 2^32-2 fragments per call");
+    for (uint64_t i = 0; i < n; ++i)
+        if (barcode_id[i] >= n_barcodes) return fail(GTGPU_ERR_INVALID, "tokenize_fragments: barcode id out of range");
+    gtgpu_ctx* ctx = ix->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    GT_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    uint32_t *d_chr, *d_start, *d_end, *d_bc;
+    GT_TRY(ctx->scratch_get(SC_CHR, n * 4, (void**)&d_chr));
+    GT_TRY(ctx->scratch_get(SC_START, n * 4, (void**)&d_start));
+    GT_TRY(ctx->scratch_get(SC_END, n * 4, (void**)&d_end));
+    GT_TRY(ctx->scratch_get(SC_BARCODE, n * 4, (void**)&d_bc));
+    if (n) {
+        GT_CUDA(cudaMemcpyAsync(d_chr, chr, n * 4, cudaMemcpyHostToDevice, st));
+        GT_CUDA(cudaMemcpyAsync(d_start, start, n * 4, cudaMemcpyHostToDevice, st));
+        GT_CUDA(cudaMemcpyAsync(d_end, end, n * 4, cudaMemcpyHostToDevice, st));
+        GT_CUDA(cudaMemcpyAsync(d_bc, barcode_id, n * 4, cudaMemcpyHostToDevice, st));
+    }
+    return tokenize_fragments_core(ix, n, d_chr, d_start, d_end, d_bc, n_barcodes, unk_id, out_barcode_offsets, out_ids);
 }

@@ -679,6 +679,23 @@ std::vector<std::pair<std::string, std::vector<uint32_t>>> Tokenizer::tokenize_f
     return out;
 }
 
+std::vector<std::pair<std::string, std::vector<uint32_t>>> Tokenizer::tokenize_fragment_file_device(const std::string& path) const {
+    const std::string text = read_file_bytes(path);
+    NameBlob nb(cmap_);
+    uint32_t n_barcodes = 0;
+    PinnedResult spans, offs, ids;
+    check(gtgpu_tokenize_fragments_text(index_, text.data(), text.size(), (uint32_t)cmap_.size(), nb.blob.data(), nb.offsets.data(),
+                                        unk_id_, &n_barcodes, &spans.buf, &offs.buf, &ids.buf),
+          "gtgpu_tokenize_fragments_text");
+    const uint64_t* off = (const uint64_t*)gtgpu_buf_data(offs.buf);
+    std::vector<std::pair<std::string, std::vector<uint32_t>>> out;
+    out.reserve(n_barcodes);
+    for (uint32_t b = 0; b < n_barcodes; ++b)
+        out.emplace_back(text.substr(spans.data()[2 * b], spans.data()[2 * b + 1]),
+                         std::vector<uint32_t>(ids.data() + off[b], ids.data() + off[b + 1]));
+    return out;
+}
+
 std::vector<std::pair<std::string, std::map<uint32_t, uint32_t>>> Tokenizer::count_fragments_by_barcode(const std::string& path) const {
     std::vector<std::pair<std::string, std::map<uint32_t, uint32_t>>> out;
     for (auto& kv : tokenize_fragment_file(path)) {

@@ -224,6 +224,16 @@ void* gth_gtok_read(const char* path) {
         return l;
     }, nullptr);
 }
+void* gth_tokenizer_fragments_device(void* t, const char* path) {
+    return guard([&]() -> void* {
+        Lists* l = new Lists();
+        for (auto& kv : ((Tokenizer*)t)->tokenize_fragment_file_device(path)) {
+            l->names.push_back(kv.first);
+            l->lists.push_back(std::move(kv.second));
+        }
+        return l;
+    }, nullptr);
+}
 void* gth_tokenizer_fragments(void* t, const char* path) {
     return guard([&]() -> void* {
         Lists* l = new Lists();

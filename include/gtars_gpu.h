@@ -165,6 +165,19 @@ int32_t gtgpu_parse_bed(gtgpu_ctx* ctx, const char* text, uint64_t n_bytes, uint
 int32_t gtgpu_tokenize_bed(gtgpu_index* index, const char* text, uint64_t n_bytes, uint32_t n_names, const char* names,
                            const uint32_t* name_offsets, uint32_t unk_id, gtgpu_buf** out_ids);
 
+/* tokenize_fragment_file (gtars-tokenizers/src/utils/fragments.rs:12-82) from the file's (decompressed) text: lines
+ * starting with '#' are skipped, every other line needs at least five whitespace-separated fields (chr start end
+ * barcode ...) with start and end accepted by str::parse::<u32>() — otherwise GTGPU_ERR_INVALID with the 0-based line
+ * number the reference reports.  Barcodes become dense ids in first-appearance order through a device hash table
+ * (64-bit FNV-1a + byte comparison against the first appearance; a true hash collision is reported as
+ * GTGPU_ERR_UNSUPPORTED).  Outputs: *out_n_barcodes; *out_barcode_spans = (byte offset, length) of each barcode's first
+ * occurrence in `text` (u32 pairs, so the caller recovers the strings); *out_barcode_offsets = n_barcodes + 1 u64
+ * offsets into *out_ids (gtgpu_buf_len counts 8-byte elements); ids as gtgpu_tokenize_fragments returns them. */
+int32_t gtgpu_tokenize_fragments_text(gtgpu_index* index, const char* text, uint64_t n_bytes, uint32_t n_names,
+                                      const char* names, const uint32_t* name_offsets, uint32_t unk_id,
+                                      uint32_t* out_n_barcodes, gtgpu_buf** out_barcode_spans,
+                                      gtgpu_buf** out_barcode_offsets, gtgpu_buf** out_ids);
+
 /* ---- gtars-scoring: fragments x consensus peaks ------------------------------------------------------------------------
  * gtgpu_score_matrix replaces region_scoring_from_fragments (gtars-scoring/src/fragment_scoring.rs:19-121) over
  * pre-parsed fragments: file f owns fragments [file_offsets[f], file_offsets[f+1]); the index is the ConsensusSet

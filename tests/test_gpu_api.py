@@ -404,3 +404,51 @@ def test_parse_bed_fuzz_vs_oracle(api, tmp_path):
             assert got == [tuple(r) for r in ref], (it, text)
             n_ok += 1
     assert n_ok > 50 and n_bad > 50
+
+
+def test_fragment_file_text_ingest_on_device(api, golden, fixture_dir, tmp_path):
+    """gtgpu_tokenize_fragments_text (text -> per-barcode token ids on the device) == the host-parsed path == the
+    oracle, on the reference's fixture (D3) and on a generated file with '#' lines, mixed whitespace, unknown
+    chromosomes, empty-hit fragments and many barcodes; malformed lines are rejected with the reference's line number."""
+    import gzip
+    from oracle import oracle as orc
+    d3 = golden[1]["D_derived"]["D3"]
+    uni = os.path.join(fixture_dir, d3["universe"])
+    frag = os.path.join(fixture_dir, d3["fragments"])
+    tok = api.Tokenizer(uni)
+    assert api.tokenize_fragment_file(frag, tok, device_parse=True) == d3["expect"]
+    rng = np.random.default_rng(31)
+    peaks = os.path.join(fixture_dir, "tokenizers", "peaks.bed")
+    tok2 = api.Tokenizer(peaks)
+    regions = [l.split()[:3] for l in open(peaks).read().splitlines() if l.strip()]
+    lines = ["# fragments"]
+    for i in range(30_000):
+        if i % 977 == 3:
+            lines.append("#comment in the middle")
+        c, s, e = regions[int(rng.integers(0, len(regions)))]
+        s, e = int(s), int(e)
+        if rng.random() < 0.3:
+            c = ["chrNope", "chr1", "chrUn"][int(rng.integers(0, 3))]
+        a = max(s + int(rng.integers(-300, 300)), 0)
+        b = a + int(rng.integers(1, 800))
+        bc = "BC%05d" % int(rng.integers(0, 1500) ** 2 // 1500)
+        sep = ["\t", " ", "  \t"][int(rng.integers(0, 3))]
+        lines.append(sep.join([c, str(a), str(b), bc, str(int(rng.integers(1, 9)))]) + ("\textra" if i % 5 == 0 else ""))
+    p = str(tmp_path / "frags.tsv.gz")
+    with gzip.open(p, "wt", newline="") as f:
+        f.write("\n".join(lines) + "\n")
+    host = api.tokenize_fragment_file(p, tok2)
+    dev = api.tokenize_fragment_file(p, tok2, device_parse=True)
+    assert dev == host and list(dev) == list(host)                      # same lists, same (first-appearance) barcode order
+    assert dev == orc.Tokenizer(peaks).tokenize_fragment_file(p)
+    assert len(dev) > 500
+    for bad in ("chr1\t5\t9\tBC\n", "chr1\tx\t9\tBC\t1\n", "chr1\t5\t-9\tBC\t1\n"):
+        q = str(tmp_path / "bad.tsv")
+        open(q, "w").write("chr1\t1\t2\tB\t1\n" + bad)
+        with pytest.raises(api.GtarsError):
+            api.tokenize_fragment_file(q, tok2, device_parse=True)
+        with pytest.raises(api.GtarsError):
+            api.tokenize_fragment_file(q, tok2)
+    q = str(tmp_path / "only_comments.tsv")
+    open(q, "w").write("# nothing here\n")
+    assert api.tokenize_fragment_file(q, tok2, device_parse=True) == api.tokenize_fragment_file(q, tok2) == {}
