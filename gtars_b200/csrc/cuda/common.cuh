@@ -169,6 +169,7 @@ struct gtgpu_index {
     std::vector<void*> allocs;
     uint64_t n_intervals = 0, n_segments = 0, device_bytes = 0, max_components = 0;
     uint64_t bt_bins = 0, bt_overflow_bins = 0, bt_pool_windows = 0;
+    uint64_t rank_lut_len = 0;  // 64-bit words in view.rank_lut (bucket boundaries of the partitioned count)
     uint32_t max_val = 0;  // largest val of any interval (bounds the radix passes of the scoring group-by)
     bool bt_clean = false;            // every window is a plain record: the lean find kernel can serve the index
     bool lean_off = false;            // the lean kernel had to fall back on this index before
@@ -182,7 +183,7 @@ enum ScratchRole {
     SC_CHR = 0, SC_START, SC_END, SC_BARCODE, SC_OUT_IDS, SC_OUT_IDS2, SC_OUT_OFFS, SC_FILE_OFFS, SC_FILE_TOK,
     SC_FILE_TOK2, SC_TILE_STATUS, SC_TILE_FILE, SC_MISC, SC_COUNTS, SC_IN2_CHR, SC_IN2_START, SC_IN2_END,
     SC_IN3_CHR, SC_IN3_START, SC_IN3_END, SC_SET_ID, SC_MATRIX, SC_ING_0, SC_ING_1, SC_ING_2, SC_ING_3, SC_ING_4, SC_ING_5,
-    SC_ING_6, SC_ING_7, SC_N_ROLES
+    SC_ING_6, SC_ING_7, SC_CNT_CHR, SC_CNT_START, SC_CNT_END, SC_CNT_SLOT, SC_CNT_TMP, SC_CNT_CURSORS, SC_N_ROLES
 };
 
 // kernels.cu

@@ -407,6 +407,7 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
     up(lut, &v.lut);
     up(rank_lut, &v.rank_lut);
     v.rank_shift = rank_shift;
+    ix->rank_lut_len = rank_lut.size();
     v.rank_inline = rank_inline;
     if (st != GTGPU_OK) {
         gtgpu_index_free(ix);

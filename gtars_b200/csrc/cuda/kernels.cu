@@ -164,23 +164,439 @@ __global__ void __launch_bounds__(256) count_kernel(IndexView ix, uint64_t n, co
     }
 }
 
+// Four consecutive queries per thread (128-bit query loads): the rank-LUT words of all four are requested before any
+// of them is consumed, so a thread keeps eight table loads in flight instead of two one after the other.  Same
+// results as count_kernel; needs 16-byte aligned query arrays (the launcher checks).
+__device__ __forceinline__ unsigned long long rank_fetch(const unsigned long long* __restrict__ rl, uint32_t nb, uint32_t shift,
+                                                         uint32_t key) {
+    const uint32_t b = key >> shift;
+    return __ldg(rl + min(b, nb));  // word nb is the sentinel (base = n, no inline entries)
+}
+
+__device__ __forceinline__ uint32_t rank_resolve(unsigned long long w, const uint32_t* __restrict__ arr,
+                                                 const unsigned long long* __restrict__ rl, uint32_t nb, uint32_t n, uint32_t shift,
+                                                 uint32_t key) {
+    const uint32_t b = key >> shift;
+    if (b >= nb) return n;
+    const uint32_t base = (uint32_t)w, cnt = (uint32_t)(w >> 32) & 7u;
+    const uint32_t r = key & ((1u << shift) - 1);
+    if (cnt != 7u) {
+        uint32_t below = 0;
+        unsigned long long offs = w >> 35;
+        for (uint32_t j = 0; j < cnt; ++j) {
+            below += (uint32_t)(offs & ((1u << shift) - 1)) < r;
+            offs >>= shift;
+        }
+        return base + below;
+    }
+    uint32_t lo = base, hi = (uint32_t)__ldg(rl + b + 1);
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(arr + mid) < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <int MODE>
+__device__ __forceinline__ void count_store(void* __restrict__ out, uint64_t i, uint64_t r) {
+    if (MODE == COUNT_BITS_RAW_U64) reinterpret_cast<uint64_t*>(out)[i] = r;
+    else if (MODE == COUNT_ANY_U8) reinterpret_cast<uint8_t*>(out)[i] = r != 0;
+    else reinterpret_cast<uint32_t*>(out)[i] = (uint32_t)r;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) count_kernel_x4(IndexView ix, uint64_t n, const uint32_t* __restrict__ chr,
+                                                       const uint32_t* __restrict__ start,
+                                                       const uint32_t* __restrict__ end, int32_t min_bp,
+                                                       void* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, n4 = n / 4;
+    const bool identity_ok = MODE == COUNT_BITS_RAW_U64 || (min_bp <= 1 && ix.proper);
+    // queries and results stream (evict-first): the L2 is for the LUT words.  The next step's queries are requested
+    // before this step's LUT words are consumed, so the DRAM latency of the stream hides behind the table look-ups.
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint4 nc = make_uint4(0, 0, 0, 0), ns = nc, ne = nc;
+    if (g < n4) {
+        nc = __ldcs(reinterpret_cast<const uint4*>(chr) + g);
+        ns = __ldcs(reinterpret_cast<const uint4*>(start) + g);
+        ne = __ldcs(reinterpret_cast<const uint4*>(end) + g);
+    }
+    for (; g < n4; g += stride) {
+        const uint4 c4 = nc, s4 = ns, e4 = ne;
+        if (g + stride < n4) {
+            nc = __ldcs(reinterpret_cast<const uint4*>(chr) + g + stride);
+            ns = __ldcs(reinterpret_cast<const uint4*>(start) + g + stride);
+            ne = __ldcs(reinterpret_cast<const uint4*>(end) + g + stride);
+        }
+        const uint32_t c[4] = {c4.x, c4.y, c4.z, c4.w}, s[4] = {s4.x, s4.y, s4.z, s4.w}, e[4] = {e4.x, e4.y, e4.z, e4.w};
+        bool fast[4];
+        uint4 off_len[4];  // cm.off, cm.len, lut_cs | nb_cs, lut_ce | nb_ce are re-read below; keep what resolve needs
+        uint4 luts[4];
+        unsigned long long wl[4], wf[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            fast[k] = c[k] < ix.n_chroms && identity_ok && (MODE == COUNT_BITS_RAW_U64 || s[k] < e[k]);
+            wl[k] = wf[k] = 0;
+            if (fast[k]) {
+                const uint4* p = reinterpret_cast<const uint4*>(ix.chroms + c[k]);
+                off_len[k] = __ldg(p);
+                luts[k] = __ldg(p + 1);
+                wl[k] = rank_fetch(ix.rank_lut + luts[k].x, luts[k].y, ix.rank_shift, e[k]);
+                wf[k] = rank_fetch(ix.rank_lut + luts[k].z, luts[k].w, ix.rank_shift, s[k] + 1u);
+            }
+        }
+        uint64_t r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (fast[k]) {
+                const uint64_t last = rank_resolve(wl[k], ix.cs_starts + off_len[k].z, ix.rank_lut + luts[k].x, luts[k].y,
+                                                   off_len[k].w, ix.rank_shift, e[k]);
+                const uint64_t first = rank_resolve(wf[k], ix.cs_ends + off_len[k].z, ix.rank_lut + luts[k].z, luts[k].w,
+                                                    off_len[k].w, ix.rank_shift, s[k] + 1u);
+                r[k] = MODE == COUNT_BITS_RAW_U64 ? last - first : (uint64_t)((uint32_t)last - (uint32_t)first);
+            } else {
+                r[k] = (MODE == COUNT_BITS_RAW_U64 || c[k] >= ix.n_chroms) ? 0 : count_query_walk(ix, c[k], s[k], e[k], min_bp);
+            }
+        }
+        if (MODE == COUNT_U32) {
+            __stcs(reinterpret_cast<uint4*>(out) + g, make_uint4((uint32_t)r[0], (uint32_t)r[1], (uint32_t)r[2], (uint32_t)r[3]));
+        } else if (MODE == COUNT_ANY_U8) {
+            __stcs(reinterpret_cast<uchar4*>(out) + g, make_uchar4(r[0] != 0, r[1] != 0, r[2] != 0, r[3] != 0));
+        } else {
+            __stcs(reinterpret_cast<ulonglong2*>(out) + 2 * g, make_ulonglong2(r[0], r[1]));
+            __stcs(reinterpret_cast<ulonglong2*>(out) + 2 * g + 1, make_ulonglong2(r[2], r[3]));
+        }
+    }
+    // the last n % 4 queries: one thread each, same arithmetic as count_kernel
+    if (blockIdx.x == 0 && threadIdx.x < (uint32_t)(n - n4 * 4)) {
+        const uint64_t i = n4 * 4 + threadIdx.x;
+        const uint32_t c = __ldg(chr + i), s = __ldg(start + i), e = __ldg(end + i);
+        uint64_t r = 0;
+        if (c < ix.n_chroms) {
+            if (identity_ok && (MODE == COUNT_BITS_RAW_U64 || s < e)) {
+                ChromMeta cm = load_chrom(ix, c);
+                uint64_t last = rank_lower_bound(ix.cs_starts + cm.off, ix.rank_lut + cm.lut_cs, cm.nb_cs, cm.len, ix.rank_shift, ix.rank_inline, e);
+                uint64_t first = rank_lower_bound(ix.cs_ends + cm.off, ix.rank_lut + cm.lut_ce, cm.nb_ce, cm.len, ix.rank_shift, ix.rank_inline, s + 1u);
+                r = MODE == COUNT_BITS_RAW_U64 ? last - first : (uint64_t)((uint32_t)last - (uint32_t)first);
+            } else if (MODE != COUNT_BITS_RAW_U64) {
+                r = count_query_walk(ix, c, s, e, min_bp);
+            }
+        }
+        count_store<MODE>(out, i, r);
+    }
+}
+
+// ---- partitioned counting: databases whose rank LUTs exceed the L2 ------------------------------------------
+// A search through the rank LUT is one 8-byte load, but with unsorted queries over a 50 M-interval database (C3:
+// 1.5 GB of LUT words) every one of them is a random DRAM sector.  One coarse radix pass over the queries (the
+// bucket = the position of the query's LUT word >> bucket_shift, 32 to CP_MAX_BUCKETS of them) makes the counting pass
+// sweep the LUT once, slice by slice, each slice small enough to stay in the L2 while its bucket is being resolved.
+//   1. count_bucket_hist_kernel + one exclusive scan: where each tile's run of each bucket starts;
+//   2. count_partition_kernel: a tile of CP_TILE queries is grouped by bucket in shared memory and written as
+//      coalesced runs of (chr, start, end), plus, per query in input order, the slot it went to (tiles keep their order inside a bucket);
+//   3. the counting kernel over the bucketed queries (slot order), on a grid that is resident all at once;
+//   4. count_gather_kernel out[i] = tmp[slot[i]] reads one slowly advancing front per bucket: every sector once.
+// Results do not depend on the slots: out[] is identical to the direct pass.
+constexpr int CP_MAX_BUCKETS = 256;  // bucket ids fit a byte; the actual number (a power of two >= 32) is chosen per launch
+#ifndef GT_CP_THREADS
+#define GT_CP_THREADS 512
+#endif
+#ifndef GT_CP_ITEMS
+#define GT_CP_ITEMS 8
+#endif
+#ifndef GT_CP_MINBLOCKS
+#define GT_CP_MINBLOCKS 2
+#endif
+constexpr int CP_THREADS = GT_CP_THREADS;  // >= CP_MAX_BUCKETS
+constexpr int CP_ITEMS = GT_CP_ITEMS;
+constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
+constexpr int CP_STAGE_BYTES = CP_TILE * 13;        // (chr, start, end) + bucket byte per staged query
+
+__device__ __forceinline__ uint32_t count_bucket_of(const IndexView& ix, uint32_t bucket_shift, uint32_t nb, uint32_t c, uint32_t e) {
+    if (c >= ix.n_chroms) return 0;
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(ix.chroms + c) + 2);  // lut_cs, nb_cs
+    const uint32_t bin = min(e >> ix.rank_shift, w.y);
+    // the chromosome's starts LUT and ends LUT lie back to back: 2 x bin is about where both words of this query are
+    const uint64_t pos = (uint64_t)w.x + 2ull * bin;
+    return (uint32_t)min(pos >> bucket_shift, (uint64_t)(nb - 1));
+}
+
+// Per-tile bucket histogram, bucket-major ([bucket][tile]) so that ONE exclusive scan over the whole array yields the
+// slot where each tile's run of each bucket starts: no atomics on shared cursors (48 k tiles x 128 buckets adding to
+// the same 128 words serialised in the L2 and made the partition 6x slower at 1e8 queries), and a stable partition.
+__global__ void __launch_bounds__(CP_THREADS) count_bucket_hist_kernel(IndexView ix, uint64_t n, uint32_t bucket_shift, uint32_t nb,
+                                                                        const uint32_t* __restrict__ chr,
+                                                                        const uint32_t* __restrict__ end,
+                                                                        uint32_t* __restrict__ tile_hist) {
+    __shared__ uint32_t s_cnt[CP_MAX_BUCKETS];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t n_tiles = (n + CP_TILE - 1) / CP_TILE;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t t0 = tile * CP_TILE;
+        const uint32_t tn = (uint32_t)min((uint64_t)CP_TILE, n - t0);
+        if (tid < CP_MAX_BUCKETS) s_cnt[tid] = 0;
+        __syncthreads();
+        uint32_t qc[CP_ITEMS], qe[CP_ITEMS];
+#pragma unroll
+        for (int k = 0; k < CP_ITEMS; ++k) {
+            const uint32_t j = k * CP_THREADS + tid;
+            if (j < tn) {
+                qc[k] = __ldg(chr + t0 + j);
+                qe[k] = __ldg(end + t0 + j);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CP_ITEMS; ++k)
+            if (k * CP_THREADS + tid < tn) atomicAdd(&s_cnt[count_bucket_of(ix, bucket_shift, nb, qc[k], qe[k])], 1u);
+        __syncthreads();
+        if (tid < nb) tile_hist[(uint64_t)tid * n_tiles + tile] = s_cnt[tid];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(CP_THREADS, GT_CP_MINBLOCKS) count_partition_kernel(IndexView ix, uint64_t n, uint32_t bucket_shift, uint32_t nb,
+                                                                         const uint32_t* __restrict__ chr,
+                                                                         const uint32_t* __restrict__ start,
+                                                                         const uint32_t* __restrict__ end,
+                                                                         const uint32_t* __restrict__ tile_base,
+                                                                         uint32_t* __restrict__ o_chr, uint32_t* __restrict__ o_start,
+                                                                         uint32_t* __restrict__ o_end, uint32_t* __restrict__ o_slot) {
+    __shared__ uint32_t s_cnt[CP_MAX_BUCKETS];    // tile histogram = rank dispenser
+    __shared__ uint32_t s_base[CP_MAX_BUCKETS];   // first staged position of each bucket
+    __shared__ uint32_t s_gbase[CP_MAX_BUCKETS];  // global slot of staged position 0 of each bucket (wrapping)
+    extern __shared__ __align__(16) uint32_t s_stage[];  // CP_STAGE_BYTES: the tile grouped by bucket
+    uint32_t *s_c = s_stage, *s_s = s_stage + CP_TILE, *s_e = s_stage + 2 * CP_TILE;
+    uint8_t* s_bk = reinterpret_cast<uint8_t*>(s_stage + 3 * CP_TILE);
+    const uint32_t tid = threadIdx.x;
+    const uint64_t n_tiles = (n + CP_TILE - 1) / CP_TILE;
+    // The queries (and run starts) of the block's NEXT tile are requested while this tile is written out: the phases
+    // of a tile are separated by block barriers, so without this only the co-resident blocks hide the load latency.
+    uint32_t qc[CP_ITEMS], qs[CP_ITEMS], qe[CP_ITEMS], br[CP_ITEMS];  // br = bucket << 16 | rank inside the tile's bucket
+    uint32_t my_base = 0;
+    auto request = [&](uint64_t tile) {
+        const uint64_t t0 = tile * CP_TILE;
+        const uint32_t tn = (uint32_t)min((uint64_t)CP_TILE, n - t0);
+        if (tid < nb) my_base = __ldg(tile_base + (uint64_t)tid * n_tiles + tile);
+#pragma unroll
+        for (int k = 0; k < CP_ITEMS; ++k) {
+            const uint32_t j = k * CP_THREADS + tid;
+            if (j < tn) {
+                qc[k] = __ldcs(chr + t0 + j);
+                qs[k] = __ldcs(start + t0 + j);
+                qe[k] = __ldcs(end + t0 + j);
+            }
+        }
+    };
+    if (blockIdx.x < n_tiles) request(blockIdx.x);
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t t0 = tile * CP_TILE;
+        const uint32_t tn = (uint32_t)min((uint64_t)CP_TILE, n - t0);
+        if (tid < CP_MAX_BUCKETS) s_cnt[tid] = 0;
+        const uint32_t this_base = my_base;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < CP_ITEMS; ++k) {
+            const uint32_t j = k * CP_THREADS + tid;
+            if (j < tn) {
+                const uint32_t b = count_bucket_of(ix, bucket_shift, nb, qc[k], qe[k]);
+                br[k] = b << 16 | atomicAdd(&s_cnt[b], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {  // exclusive scan of the bucket sizes (eight per lane)
+            uint32_t v[8], s = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                v[k] = s_cnt[8 * tid + k];
+                s += v[k];
+            }
+            uint32_t incl = s;
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (tid >= (uint32_t)d) incl += t;
+            }
+            uint32_t run = incl - s;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                s_base[8 * tid + k] = run;
+                run += v[k];
+            }
+        }
+        __syncthreads();
+        if (tid < CP_MAX_BUCKETS) s_gbase[tid] = this_base - s_base[tid];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < CP_ITEMS; ++k) {
+            const uint32_t j = k * CP_THREADS + tid;
+            if (j < tn) {
+                const uint32_t b = br[k] >> 16, p = s_base[b] + (br[k] & 0xFFFFu);
+                s_c[p] = qc[k];
+                s_s[p] = qs[k];
+                s_e[p] = qe[k];
+                s_bk[p] = (uint8_t)b;
+                __stcs(o_slot + t0 + j, s_gbase[b] + p);
+            }
+        }
+        if (tile + gridDim.x < n_tiles) request(tile + gridDim.x);
+        __syncthreads();
+        for (uint32_t p = tid; p < tn; p += CP_THREADS) {
+            const uint32_t dst = s_gbase[s_bk[p]] + p;
+            o_chr[dst] = s_c[p];
+            o_start[dst] = s_s[p];
+            o_end[dst] = s_e[p];
+        }
+        __syncthreads();
+    }
+}
+
+// Sixteen results per thread: four 128-bit slot loads, then sixteen independent gathers in flight (a thread that
+// chains one slot load and four gathers at DRAM latency moved 2e11 elements/s, a third of what the traffic allows).
+template <typename T>
+__global__ void __launch_bounds__(256) count_gather_kernel(uint64_t n, const uint32_t* __restrict__ slot,
+                                                           const T* __restrict__ tmp, T* __restrict__ out) {
+    const uint64_t n16 = n / 16, groups_per_block = blockDim.x;  // a block covers 256 x 16 consecutive results per step
+    for (uint64_t blk = blockIdx.x; blk * groups_per_block < n16; blk += gridDim.x) {
+        const uint64_t g0 = blk * groups_per_block * 4;  // first uint4 of this block's span
+        uint4 p[4];
+        bool ok[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // lane-contiguous 128-bit loads: k-th quarter of the span
+            const uint64_t q = g0 + (uint64_t)k * blockDim.x + threadIdx.x;
+            ok[k] = q < n16 * 4;
+            if (ok[k]) p[k] = __ldcs(reinterpret_cast<const uint4*>(slot) + q);
+        }
+        T v[16];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (ok[k]) {
+                v[4 * k] = __ldg(tmp + p[k].x);
+                v[4 * k + 1] = __ldg(tmp + p[k].y);
+                v[4 * k + 2] = __ldg(tmp + p[k].z);
+                v[4 * k + 3] = __ldg(tmp + p[k].w);
+            }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (ok[k]) {
+                const uint64_t i = (g0 + (uint64_t)k * blockDim.x + threadIdx.x) * 4;
+                __stcs(out + i, v[4 * k]);
+                __stcs(out + i + 1, v[4 * k + 1]);
+                __stcs(out + i + 2, v[4 * k + 2]);
+                __stcs(out + i + 3, v[4 * k + 3]);
+            }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (uint32_t)(n - n16 * 16)) {
+        const uint64_t i = n16 * 16 + threadIdx.x;
+        out[i] = tmp[__ldg(slot + i)];
+    }
+}
+
+// A grid that is resident all at once (blocks per SM from the occupancy calculator): every block then walks the
+// queries in step with the others, which is what keeps one bucket's LUT slice in the L2 while it is being used.
+template <typename K>
+static int resident_grid(const gtgpu_ctx* ctx, K kernel, int threads, uint64_t blocks_needed, size_t dyn_smem = 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, dyn_smem) != cudaSuccess || occ < 1) occ = 1;
+    return (int)std::min<uint64_t>(std::max<uint64_t>(blocks_needed, 1), (uint64_t)ctx->sm_count * occ);
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// One counting pass: four queries per thread when the arrays allow 128-bit accesses, else one.
+template <int MODE>
+static void launch_count_mode(const gtgpu_ctx* ctx, const IndexView& v, uint64_t n, const uint32_t* c, const uint32_t* s,
+                              const uint32_t* e, int32_t min_bp, void* out, bool resident) {
+    cudaStream_t st = ctx->stream;
+    if (aligned16(c) && aligned16(s) && aligned16(e) && aligned16(out)) {
+        const uint64_t blocks = (n / 4 + 255) / 256;
+        const int grid = resident ? resident_grid(ctx, count_kernel_x4<MODE>, 256, blocks)
+                                  : (int)std::min<uint64_t>(std::max<uint64_t>(blocks, 1), (uint64_t)ctx->sm_count * 32);
+        count_kernel_x4<MODE><<<grid, 256, 0, st>>>(v, n, c, s, e, min_bp, out);
+    } else {
+        const uint64_t blocks = (n + 255) / 256;
+        const int grid = resident ? resident_grid(ctx, count_kernel<MODE>, 256, blocks)
+                                  : (int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 32);
+        count_kernel<MODE><<<grid, 256, 0, st>>>(v, n, c, s, e, min_bp, out);
+    }
+}
+
+// Whether this launch goes through the partition: the identity path only, LUTs well beyond what stays in the L2,
+// enough queries to pay for the extra passes.  GTGPU_COUNT_PARTITION=0 / 1 forces it off / on (tests, measurements).
+static bool count_wants_partition(const gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_end,
+                                  int32_t min_overlap) {
+    if (min_overlap > 1 || !ix->view.proper || n >= 0xFFFFFFFFull || ix->rank_lut_len == 0) return false;
+    if (!aligned16(d_chr) || !aligned16(d_end)) return false;
+    if (const char* env = getenv("GTGPU_COUNT_PARTITION")) return env[0] == '1';
+    return ix->rank_lut_len * 8 > (64ull << 20) && n >= (4ull << 20);
+}
+
+static int32_t launch_count_partitioned(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
+                                        const uint32_t* d_end, int32_t min_overlap, int mode, void* d_out) {
+    gtgpu_ctx* ctx = ix->ctx;
+    cudaStream_t st = ctx->stream;
+    const size_t elem = mode == COUNT_BITS_RAW_U64 ? 8 : mode == COUNT_ANY_U8 ? 1 : 4;
+    uint32_t *b_chr, *b_start, *b_end, *slot;
+    void* tmp;
+    // Slices of about 16 MB of LUT words per bucket (an eighth of the L2), between 32 and 256 buckets.
+    uint32_t nb = 32;
+    while (nb < (uint32_t)CP_MAX_BUCKETS && ix->rank_lut_len * 8 / nb > (16ull << 20)) nb *= 2;
+    if (const char* env = getenv("GTGPU_COUNT_BUCKETS")) nb = (uint32_t)std::min(CP_MAX_BUCKETS, std::max(2, atoi(env)));
+    uint32_t bucket_shift = 0;
+    while (((ix->rank_lut_len + 2) >> bucket_shift) >= (uint64_t)nb) ++bucket_shift;
+    const uint64_t n_tiles = (n + CP_TILE - 1) / CP_TILE, n_hist = n_tiles * nb;
+    const size_t hist_bytes = (size_t)((n_hist * 4 + 255) / 256 * 256);
+    char* hist_ws;
+    GT_TRY(ctx->scratch_get(SC_CNT_CHR, n * 4, (void**)&b_chr));
+    GT_TRY(ctx->scratch_get(SC_CNT_START, n * 4, (void**)&b_start));
+    GT_TRY(ctx->scratch_get(SC_CNT_END, n * 4, (void**)&b_end));
+    GT_TRY(ctx->scratch_get(SC_CNT_SLOT, n * 4, (void**)&slot));
+    GT_TRY(ctx->scratch_get(SC_CNT_TMP, n * elem, &tmp));
+    GT_TRY(ctx->scratch_get(SC_CNT_CURSORS, 2 * hist_bytes + exclusive_scan_temp_bytes(n_hist, 4), (void**)&hist_ws));
+    uint32_t* tile_hist = reinterpret_cast<uint32_t*>(hist_ws);
+    uint32_t* tile_base = reinterpret_cast<uint32_t*>(hist_ws + hist_bytes);
+    const int hist_grid = resident_grid(ctx, count_bucket_hist_kernel, CP_THREADS, n_tiles);
+    GT_CUDA(cudaFuncSetAttribute(count_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_STAGE_BYTES));
+    const int part_grid = resident_grid(ctx, count_partition_kernel, CP_THREADS, n_tiles, CP_STAGE_BYTES);
+    ctx->time_begin();
+    count_bucket_hist_kernel<<<hist_grid, CP_THREADS, 0, st>>>(ix->view, n, bucket_shift, nb, d_chr, d_end, tile_hist);
+    GT_TRY(exclusive_scan<uint32_t>(ctx, tile_hist, tile_base, n_hist, hist_ws + 2 * hist_bytes));
+    count_partition_kernel<<<part_grid, CP_THREADS, CP_STAGE_BYTES, st>>>(ix->view, n, bucket_shift, nb, d_chr, d_start, d_end, tile_base,
+                                                            b_chr, b_start, b_end, slot);
+    const uint64_t gblocks = (n / 16 + 255) / 256;
+    switch (mode) {
+        case COUNT_U32:
+            launch_count_mode<COUNT_U32>(ctx, ix->view, n, b_chr, b_start, b_end, min_overlap, tmp, true);
+            count_gather_kernel<uint32_t><<<resident_grid(ctx, count_gather_kernel<uint32_t>, 256, gblocks), 256, 0, st>>>(
+                n, slot, (const uint32_t*)tmp, (uint32_t*)d_out);
+            break;
+        case COUNT_ANY_U8:
+            launch_count_mode<COUNT_ANY_U8>(ctx, ix->view, n, b_chr, b_start, b_end, min_overlap, tmp, true);
+            count_gather_kernel<uint8_t><<<resident_grid(ctx, count_gather_kernel<uint8_t>, 256, gblocks), 256, 0, st>>>(
+                n, slot, (const uint8_t*)tmp, (uint8_t*)d_out);
+            break;
+        default:
+            launch_count_mode<COUNT_BITS_RAW_U64>(ctx, ix->view, n, b_chr, b_start, b_end, min_overlap, tmp, true);
+            count_gather_kernel<uint64_t><<<resident_grid(ctx, count_gather_kernel<uint64_t>, 256, gblocks), 256, 0, st>>>(
+                n, slot, (const uint64_t*)tmp, (uint64_t*)d_out);
+            break;
+    }
+    ctx->time_end();
+    ctx->launches += 4;  // + 3 counted by the scan
+    GT_CUDA(cudaGetLastError());
+    return GTGPU_OK;
+}
+
 int32_t launch_count(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
                      const uint32_t* d_end, int32_t min_overlap, int mode, void* d_out) {
     if (n == 0) return GTGPU_OK;
     gtgpu_ctx* ctx = ix->ctx;
-    uint64_t blocks_needed = (n + 255) / 256;
-    int grid = (int)std::min<uint64_t>(blocks_needed, (uint64_t)ctx->sm_count * 32);
+    if (const char* env = getenv("GTGPU_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(env));  // tuning knob
+    if (count_wants_partition(ix, n, d_chr, d_end, min_overlap))
+        return launch_count_partitioned(ix, n, d_chr, d_start, d_end, min_overlap, mode, d_out);
     ctx->time_begin();
     switch (mode) {
-        case COUNT_U32:
-            count_kernel<COUNT_U32><<<grid, 256, 0, ctx->stream>>>(ix->view, n, d_chr, d_start, d_end, min_overlap, d_out);
-            break;
-        case COUNT_ANY_U8:
-            count_kernel<COUNT_ANY_U8><<<grid, 256, 0, ctx->stream>>>(ix->view, n, d_chr, d_start, d_end, min_overlap, d_out);
-            break;
-        default:
-            count_kernel<COUNT_BITS_RAW_U64><<<grid, 256, 0, ctx->stream>>>(ix->view, n, d_chr, d_start, d_end, min_overlap, d_out);
-            break;
+        case COUNT_U32: launch_count_mode<COUNT_U32>(ctx, ix->view, n, d_chr, d_start, d_end, min_overlap, d_out, false); break;
+        case COUNT_ANY_U8: launch_count_mode<COUNT_ANY_U8>(ctx, ix->view, n, d_chr, d_start, d_end, min_overlap, d_out, false); break;
+        default: launch_count_mode<COUNT_BITS_RAW_U64>(ctx, ix->view, n, d_chr, d_start, d_end, min_overlap, d_out, false); break;
     }
     ctx->time_end();
     ctx->launches++;

@@ -181,6 +181,31 @@ def test_random_differential(ctx, kind, style):
 
 
 @pytest.mark.parametrize("kind", ["bits", "ailist"])
+@pytest.mark.parametrize("style", ["peaks", "overlap", "nested", "dups"])
+def test_partitioned_count_matches_direct_and_oracle(ctx, kind, style, monkeypatch):
+    """The bucketed counting pass (queries grouped by rank-LUT slice, used for databases beyond the L2) returns what the
+    direct pass and the oracle return, for every output type, tile remainders and unknown / degenerate queries."""
+    rng = np.random.default_rng(zlib.crc32(f"part/{kind}/{style}".encode()))
+    n_chroms = 5
+    offs, s, e, v = _random_index(rng, n_chroms, 6000, style)
+    g, o = _both(ctx, kind, offs, s, e, v)
+    for nq, degenerate in ((1, False), (15, True), (4095, False), (4096, True), (4097, False), (70_001, True)):
+        qc, qs, qe = _random_queries(rng, n_chroms, nq, degenerate)
+        monkeypatch.setenv("GTGPU_COUNT_PARTITION", "0")
+        direct = g.count(qc, qs, qe), g.any(qc, qs, qe), (g.bits_count(qc, qs, qe) if kind == "bits" else None)
+        monkeypatch.setenv("GTGPU_COUNT_PARTITION", "1")
+        n0 = ctx.launch_count()
+        part = g.count(qc, qs, qe), g.any(qc, qs, qe), (g.bits_count(qc, qs, qe) if kind == "bits" else None)
+        per_call = 7 if g.info()["proper"] else 1                        # hist, scan x 3, partition, count, gather
+        assert ctx.launch_count() - n0 == per_call * (3 if kind == "bits" else 2)
+        assert np.array_equal(part[0], o.count(qc, qs, qe))
+        assert np.array_equal(part[0], direct[0]) and np.array_equal(part[1], direct[1])
+        if kind == "bits":
+            assert np.array_equal(part[2], o.bits_count(qc, qs, qe)) and np.array_equal(part[2], direct[2])
+        assert np.array_equal(g.count(qc, qs, qe, 2), o.count(qc, qs, qe, 2))  # min_overlap > 1 never partitions
+
+
+@pytest.mark.parametrize("kind", ["bits", "ailist"])
 def test_tokenize_files_unk_rule_and_ragged(ctx, kind):
     rng = np.random.default_rng(11)
     n_chroms = 4

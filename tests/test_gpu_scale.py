@@ -85,7 +85,7 @@ def test_c2_nested_universe_vs_oracle(ctx):
         assert np.array_equal(off, oo) and np.array_equal(ids, oi)
 
 
-def test_c3_bits_count_database(ctx):
+def test_c3_bits_count_database(ctx, monkeypatch):
     """C3 at 1/10 scale: 10 M unsorted queries vs a 5 M-interval overlapping database (count only)."""
     from gtars_b200 import ffi, synth
     from oracle import oracle as orc
@@ -96,7 +96,10 @@ def test_c3_bits_count_database(ctx):
     ix = ffi.Index(ctx, ffi.KIND_BITS, offs, s, e)
     q = synth.make_uniform_intervals(10_000_000, synth.SEED_QUERIES, min_w=100, max_w=2000, log_uniform=False)
     qc, qs, qe = (_np(q[k]) for k in ("chr", "start", "end"))
-    counts = ix.count(qc, qs, qe)
+    counts = ix.count(qc, qs, qe)                                  # 160 MB of rank LUTs: the bucketed pass
+    monkeypatch.setenv("GTGPU_COUNT_PARTITION", "0")
+    assert np.array_equal(ix.count(qc, qs, qe), counts)            # ... agrees with the direct pass
+    monkeypatch.delenv("GTGPU_COUNT_PARTITION")
     raw = ix.bits_count(qc, qs, qe)
     assert np.array_equal(raw, counts.astype(np.uint64))           # proper inputs: identity == enumerated count
     assert np.array_equal(ix.any(qc, qs, qe), counts > 0)
