@@ -97,7 +97,9 @@ int32_t gtgpu_index_info(const gtgpu_index* index, uint64_t info[12]);
 
 /* ---- batch queries, host buffers ------------------------------------------------------------------------ */
 /* MultiChromOverlapper::count_overlaps (multi_chrom_overlapper.rs:483-498): out_counts[i] = number of indexed
- * intervals overlapping query i; min_overlap is applied only when > 1 (bp of overlap), as in the reference. */
+ * intervals overlapping query i; min_overlap is applied only when > 1 (bp of overlap), as in the reference.
+ * Databases whose search tables exceed the L2 (tens of millions of intervals) are served by bucketing the batch by
+ * table slice on the device first; the output is the same array in the caller's query order. */
 int32_t gtgpu_count(gtgpu_index* index, uint64_t n, const uint32_t* chr, const uint32_t* start,
                     const uint32_t* end, int32_t min_overlap, uint32_t* out_counts);
 /* Bits::count (bits.rs:337-344), the two-binary-search identity, with the reference's wrapping usize
