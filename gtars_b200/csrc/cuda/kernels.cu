@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(256) count_kernel_x4(IndexView ix, uint64_t n,
         }
         const uint32_t c[4] = {c4.x, c4.y, c4.z, c4.w}, s[4] = {s4.x, s4.y, s4.z, s4.w}, e[4] = {e4.x, e4.y, e4.z, e4.w};
         bool fast[4];
-        uint4 off_len[4];  // cm.off, cm.len, lut_cs | nb_cs, lut_ce | nb_ce are re-read below; keep what resolve needs
-        uint4 luts[4];
+        uint4 off_len[4];  // ChromMeta words 0-3: seg_begin, seg_end, off (.z), len (.w)
+        uint4 luts[4];     // ChromMeta words 4-7: lut_cs, nb_cs, lut_ce, nb_ce
         unsigned long long wl[4], wf[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
