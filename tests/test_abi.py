@@ -167,3 +167,33 @@ def test_host_igd_writer_matches_oracle_bytes(golden, fixture_dir, tmp_path):
         for i, rs in enumerate(sets):
             kept = [r for r in rs if r.start < r.end]
             assert tsv[1 + i] == "%d\t%s\t%d\t%.2f" % (i, names[i], len(kept), sum(r.end - r.start for r in kept) / len(kept))
+
+
+def test_device_code_is_sm100a_and_keeps_its_resource_budgets():
+    """The shipped library embeds sm_100a code only, contains the kernels the design names, and the kernels whose
+    occupancy the measured numbers rest on keep their register / stack budgets (a silent spill costs a CTA per SM)."""
+    import shutil
+    import subprocess
+    from gtars_b200 import ffi
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    elfs = subprocess.run([tool, "-lelf", ffi.LIB_PATH], capture_output=True, text=True, check=True).stdout.split("\n")
+    cubins = [l.split()[-1] for l in elfs if l.strip().startswith("ELF file")]
+    assert cubins and all(".sm_100a." in c for c in cubins), cubins
+    usage = subprocess.run([tool, "-res-usage", ffi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    res = {}
+    for m in re.finditer(r"Function (\S+):\n\s+REG:(\d+) STACK:(\d+) SHARED:(\d+)", usage):
+        res[m.group(1)] = tuple(int(x) for x in m.groups()[1:])
+    for name in ("fused_find_kernel", "count_kernel_x4", "count_partition_kernel", "count_bucket_hist_kernel",
+                 "count_gather_kernel", "igd_count_kernel", "radix_scatter_kernel", "scan_down_kernel", "score_hist_kernel",
+                 "ingest_parse_lines_kernel", "untranspose_blocks_kernel"):
+        assert any(name in k for k in res), f"{name} missing from the device code"
+    # lean fused find kernel: template flags <ROWS=4, DESC, FILTER, OFFS, LEAN=1>; 48 registers, no stack = 5 CTAs per SM
+    lean = [v for k, v in res.items() if "fused_find_kernelILi4E" in k and k.split("fused_find_kernelILi4E")[1].startswith("Lb") and
+            re.match(r"(Lb[01]E){3}Lb1E", k.split("fused_find_kernelILi4E")[1])]
+    assert lean, "no lean instantiation of the fused kernel"
+    for reg, stack, shared in lean:
+        assert reg <= 48 and stack == 0 and shared <= 24 * 1024, (reg, stack, shared)
+    part = [v for k, v in res.items() if "count_partition_kernel" in k]
+    assert all(reg <= 64 and stack == 0 for reg, stack, _ in part), part   # two 512-thread CTAs per SM
