@@ -197,3 +197,11 @@ def test_device_code_is_sm100a_and_keeps_its_resource_budgets():
         assert reg <= 48 and stack == 0 and shared <= 24 * 1024, (reg, stack, shared)
     part = [v for k, v in res.items() if "count_partition_kernel" in k]
     assert all(reg <= 64 and stack == 0 for reg, stack, _ in part), part   # two 512-thread CTAs per SM
+
+
+def test_rust_sys_stub_declares_every_entry_point():
+    """bindings/rust/gtars-overlaprs-sys (what a gtars maintainer would vendor; cannot be compiled here) stays in step
+    with the header: every exported entry point has an `extern "C"` declaration."""
+    rs = open(os.path.join(ROOT, "bindings", "rust", "gtars-overlaprs-sys", "src", "lib.rs")).read()
+    missing = [s for s in _declared_symbols() if not re.search(r"\bfn\s+" + s + r"\b", rs)]
+    assert not missing, missing
