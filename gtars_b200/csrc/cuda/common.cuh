@@ -242,8 +242,31 @@ int32_t tokenize_fragments_core(gtgpu_index* ix, uint64_t n, const uint32_t* d_c
 size_t exclusive_scan_temp_bytes(uint64_t n, size_t elem);
 template <typename T>
 int32_t exclusive_scan(gtgpu_ctx* ctx, const T* d_in, T* d_out, uint64_t n, void* d_temp);
+int32_t inclusive_max_scan_u64(gtgpu_ctx* ctx, const unsigned long long* d_in, unsigned long long* d_out, uint64_t n, void* d_temp);
 size_t radix_sort_temp_bytes(uint64_t n);
 int32_t radix_sort_pairs(gtgpu_ctx* ctx, uint64_t n, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
                          int bits, void* d_temp, int* result_in_b);
+
+// build.cu — device-side primitives of the index builders
+struct LutDesc {       // one bin LUT over arr[arr_off .. arr_off + len): nb + 1 entries written at lut[lut_off ..]
+    uint32_t arr_off, len, lut_off, nb;
+};
+int bits_for_value(uint64_t max_value);
+int32_t launch_gather_u32(gtgpu_ctx* ctx, uint64_t n, const uint32_t* d_src, const uint32_t* d_perm, uint32_t* d_out);
+int32_t launch_key_offsets(gtgpu_ctx* ctx, uint64_t n, const uint32_t* d_sorted, uint32_t n_keys, uint32_t* d_out);
+int32_t launch_build_luts(gtgpu_ctx* ctx, uint32_t n_desc, const LutDesc* d_desc, const uint64_t* d_bin_prefix, uint64_t total_bins,
+                          const uint32_t* d_arr, uint32_t shift, uint32_t* d_lut);
+// Stable LSD radix sort of a permutation of [0, n) by successive key arrays (least significant key first).
+struct PermSorter {
+    gtgpu_ctx* ctx = nullptr;
+    uint64_t n = 0;
+    uint32_t *perm = nullptr, *perm_alt = nullptr;  // perm: the current order
+    uint32_t *key = nullptr, *key_alt = nullptr;    // key: the last pass's keys, in the current order
+    void* tmp = nullptr;
+    uint32_t* d_max = nullptr;
+    int32_t init(gtgpu_ctx* ctx, uint64_t n);
+    int32_t pass(const uint32_t* d_src, int bits);
+    ~PermSorter();
+};
 
 }  // namespace gtgpu

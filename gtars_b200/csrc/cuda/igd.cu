@@ -28,10 +28,7 @@ struct gtgpu_igd {
     uint32_t *d_off = nullptr, *d_lut_s_off = nullptr, *d_nb_s = nullptr, *d_lut_p_off = nullptr, *d_nb_p = nullptr;
     int32_t *d_start = nullptr, *d_end = nullptr, *d_pmax = nullptr, *d_psame1 = nullptr;
     uint32_t *d_file = nullptr, *d_lut = nullptr;
-    // host copies kept to derive psame for other min_overlap values on demand
-    std::vector<int32_t> h_start, h_end;
-    std::vector<uint32_t> h_file;
-    std::map<int32_t, int32_t*> psame_by_m;
+    std::map<int32_t, int32_t*> psame_by_m;  // psame for every min_overlap asked for so far (derived on the device)
     std::vector<void*> allocs;
     uint64_t device_bytes = 0;
 };
@@ -41,50 +38,146 @@ namespace gtgpu {
 namespace {
 
 template <class T>
-int32_t up(gtgpu_igd* g, const std::vector<T>& v, T** out) {
+int32_t dev_alloc(gtgpu_igd* g, uint64_t count, T** out) {
     void* d = nullptr;
-    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    size_t bytes = std::max<size_t>(count * sizeof(T), 16);
     cudaError_t e = cudaMalloc(&d, bytes);
     if (e != cudaSuccess) return fail(GTGPU_ERR_NOMEM, std::string("cudaMalloc(igd): ") + cudaGetErrorString(e));
     g->allocs.push_back(d);
     g->device_bytes += bytes;
-    if (!v.empty()) GT_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     *out = (T*)d;
     return GTGPU_OK;
 }
 
-void build_lut_i32(const int32_t* arr, uint32_t n, uint32_t shift, std::vector<uint32_t>& lut, uint32_t& off, uint32_t& nb) {
-    off = (uint32_t)lut.size();
-    if (n == 0) {
-        nb = 0;
-        lut.push_back(0);
-        return;
-    }
-    nb = ((uint32_t)arr[n - 1] >> shift) + 1;
-    lut.resize(lut.size() + (size_t)nb + 1);
-    uint32_t* L = lut.data() + off;
-    uint32_t i = 0;
-    for (uint32_t b = 0; b < nb; ++b) {
-        int64_t key = (int64_t)b << shift;
-        while (i < n && arr[i] < key) ++i;
-        L[b] = i;
-    }
-    L[nb] = n;
+template <class T>
+int32_t up(gtgpu_igd* g, const std::vector<T>& v, T** out) {
+    GT_TRY(dev_alloc(g, v.size(), out));
+    if (!v.empty()) GT_CUDA(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return GTGPU_OK;
 }
 
-// psame[i] = max end over earlier same-file records (pooled order) with end - start >= m; -1 when there is none.
-std::vector<int32_t> compute_psame(const gtgpu_igd* g, int32_t m) {
-    std::vector<int32_t> ps(g->n_records);
-    std::vector<int32_t> last(g->n_files);
-    for (uint32_t c = 0; c < g->n_chroms; ++c) {
-        std::fill(last.begin(), last.end(), -1);
-        for (uint32_t i = g->h_off[c]; i < g->h_off[c + 1]; ++i) {
-            uint32_t f = g->h_file[i];
-            ps[i] = last[f];
-            if ((int64_t)g->h_end[i] - g->h_start[i] >= m) last[f] = std::max(last[f], g->h_end[i]);
-        }
+// temporaries of a build: freed when the builder leaves
+struct TempPool {
+    std::vector<void*> ptrs;
+    template <class T>
+    int32_t get(uint64_t count, T** out) {
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, std::max<size_t>(count * sizeof(T), 16));
+        if (e != cudaSuccess) return fail(GTGPU_ERR_NOMEM, std::string("cudaMalloc(igd build): ") + cudaGetErrorString(e));
+        ptrs.push_back(d);
+        *out = (T*)d;
+        return GTGPU_OK;
     }
-    return ps;
+    ~TempPool() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+};
+
+int grid_for(const gtgpu_ctx* ctx, uint64_t n) {
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 16));
+}
+
+}  // namespace
+
+// ---- build kernels ---------------------------------------------------------------------------------------------------
+// Sort key of an input record: its chromosome when Igd::add keeps it (igd.rs:109-116, 285-301: start < end as u32, then
+// 0 <= start < end as i32), else n_chroms — dropped records sort behind every chromosome and are cut off.
+__global__ void igd_chrom_keys_kernel(uint64_t n, uint32_t n_chroms, const uint32_t* __restrict__ chr, const uint32_t* __restrict__ start,
+                                      const uint32_t* __restrict__ end, uint32_t* __restrict__ key) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t c = chr[i], s = start[i], e = end[i];
+        const bool keep = c < n_chroms && s < e && (int32_t)s >= 0 && (int32_t)e >= 0;
+        key[i] = keep ? c : n_chroms;
+    }
+}
+
+// packed[k] = segment << 32 | value: the running maximum of the low word inside a segment is a plain 64-bit max-scan
+__global__ void igd_pack_pmax_kernel(uint64_t n, const uint32_t* __restrict__ chrkey, const int32_t* __restrict__ end,
+                                     unsigned long long* __restrict__ packed) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+        packed[k] = ((unsigned long long)chrkey[k] << 32) | (uint32_t)end[k];
+}
+__global__ void igd_low_words_kernel(uint64_t n, const unsigned long long* __restrict__ packed, int32_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) out[k] = (int32_t)(uint32_t)packed[k];
+}
+
+// Records in (chromosome, file, pooled position) order: head[k] = 1 where a (chromosome, file) group starts
+__global__ void igd_group_heads_kernel(uint64_t n, const uint32_t* __restrict__ order, const uint32_t* __restrict__ chrkey,
+                                       const uint32_t* __restrict__ file, uint32_t* __restrict__ head) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        uint32_t h = 1;
+        if (k) {
+            const uint32_t a = order[k], b = order[k - 1];
+            h = chrkey[a] != chrkey[b] || file[a] != file[b];
+        }
+        head[k] = h;
+    }
+}
+// packed[k] = group number << 32 | (end + 1 when the record is at least m long, else 0)
+__global__ void igd_pack_psame_kernel(uint64_t n, const uint32_t* __restrict__ order, const uint32_t* __restrict__ head,
+                                      const uint32_t* __restrict__ groups_before, const int32_t* __restrict__ start,
+                                      const int32_t* __restrict__ end, int32_t m, unsigned long long* __restrict__ packed) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const uint32_t i = order[k];
+        const int32_t s = start[i], e = end[i];
+        const uint32_t v = (e - s >= m) ? (uint32_t)e + 1u : 0u;
+        packed[k] = ((unsigned long long)(groups_before[k] + head[k]) << 32) | v;
+    }
+}
+// psame of the k-th record of a group = the running maximum up to its predecessor in the group (-1: none)
+__global__ void igd_scatter_psame_kernel(uint64_t n, const uint32_t* __restrict__ order, const uint32_t* __restrict__ head,
+                                         const unsigned long long* __restrict__ running, int32_t* __restrict__ psame) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+        psame[order[k]] = head[k] ? -1 : (int32_t)(uint32_t)running[k - 1] - 1;
+}
+
+int32_t launch_fill_set_ids(gtgpu_ctx* ctx, uint64_t n_sets, const uint64_t* d_set_offsets, uint32_t* d_set_of);
+
+namespace {
+
+// psame[i] = max end over EARLIER records (pooled order) of the same file on the same chromosome with end - start >= m;
+// -1 when there is none.  Pooled positions are regrouped by (chromosome, file) with two stable radix passes, the running
+// maximum inside a group is one max-scan, and the result goes back to the pooled positions.
+int32_t device_psame(gtgpu_igd* g, int32_t m, int32_t* d_psame) {
+    gtgpu_ctx* ctx = g->ctx;
+    const uint64_t n = g->n_records;
+    if (n == 0) return GTGPU_OK;
+    cudaStream_t st = ctx->stream;
+    TempPool tp;
+    uint32_t *d_chrkey, *d_head, *d_before;
+    uint64_t* d_off64;
+    unsigned long long* d_packed;
+    char* d_scan_tmp;
+    GT_TRY(tp.get(n, &d_chrkey));
+    GT_TRY(tp.get(n, &d_head));
+    GT_TRY(tp.get(n, &d_before));
+    GT_TRY(tp.get(g->n_chroms + 1, &d_off64));
+    GT_TRY(tp.get(n, &d_packed));
+    GT_TRY(tp.get(exclusive_scan_temp_bytes(n, 8), &d_scan_tmp));
+    std::vector<uint64_t> off64(g->h_off.begin(), g->h_off.end());
+    GT_CUDA(cudaMemcpyAsync(d_off64, off64.data(), off64.size() * 8, cudaMemcpyHostToDevice, st));
+    GT_CUDA(cudaStreamSynchronize(st));
+    GT_TRY(launch_fill_set_ids(ctx, g->n_chroms, d_off64, d_chrkey));
+    PermSorter by_group;
+    GT_TRY(by_group.init(ctx, n));
+    GT_TRY(by_group.pass(g->d_file, bits_for_value(g->n_files ? g->n_files - 1 : 0)));
+    GT_TRY(by_group.pass(d_chrkey, bits_for_value(g->n_chroms)));
+    const int grid = grid_for(ctx, n);
+    igd_group_heads_kernel<<<grid, 256, 0, st>>>(n, by_group.perm, d_chrkey, g->d_file, d_head);
+    GT_TRY(exclusive_scan<uint32_t>(ctx, d_head, d_before, n, d_scan_tmp));
+    igd_pack_psame_kernel<<<grid, 256, 0, st>>>(n, by_group.perm, d_head, d_before, g->d_start, g->d_end, m, d_packed);
+    GT_TRY(inclusive_max_scan_u64(ctx, d_packed, d_packed, n, d_scan_tmp));
+    igd_scatter_psame_kernel<<<grid, 256, 0, st>>>(n, by_group.perm, d_head, d_packed, d_psame);
+    ctx->launches += 3;
+    GT_CUDA(cudaGetLastError());
+    GT_CUDA(cudaStreamSynchronize(st));
+    return GTGPU_OK;
 }
 
 }  // namespace
@@ -159,90 +252,146 @@ using namespace gtgpu;
 extern "C" int32_t gtgpu_igd_build(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* file_offsets, uint32_t n_chroms,
                                    const uint32_t* chr, const uint32_t* start, const uint32_t* end, gtgpu_igd** out_igd) {
     if (!ctx || !out_igd || !file_offsets) return fail(GTGPU_ERR_INVALID, "igd_build: null argument");
-    uint64_t total = file_offsets[n_files];
+    for (uint64_t f = 0; f < n_files; ++f)
+        if (file_offsets[f] > file_offsets[f + 1]) return fail(GTGPU_ERR_INVALID, "igd_build: file_offsets not monotone");
+    if (file_offsets[0] != 0) return fail(GTGPU_ERR_INVALID, "igd_build: file_offsets[0] must be 0");
+    const uint64_t total = file_offsets[n_files];
     if (total && (!chr || !start || !end)) return fail(GTGPU_ERR_INVALID, "igd_build: null record arrays");
-    if (total >= 0xFFFFFFFFull || n_files >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "igd_build: too many records");
+    if (total >= 0xFFFFFFFFull || n_files >= 0xFFFFFFFFull || n_chroms >= 0x7FFFFFFFu)
+        return fail(GTGPU_ERR_UNSUPPORTED, "igd_build: too many records");
+    std::lock_guard<std::mutex> lk(ctx->mu);
     GT_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
     gtgpu_igd* g = new gtgpu_igd();
     g->ctx = ctx;
     g->n_files = n_files;
     g->n_chroms = n_chroms;
+    struct Guard {  // a failed build frees what it allocated
+        gtgpu_igd* g;
+        ~Guard() { if (g) gtgpu_igd_free(g); }
+    } guard{g};
 
-    // keep what Igd::add keeps (igd.rs:109-116, 285-301): start < end as u32, then 0 <= start < end as i32
-    std::vector<uint32_t> keep;
-    keep.reserve(total);
-    std::vector<uint32_t> file_of(total);
-    for (uint64_t f = 0; f < n_files; ++f)
-        for (uint64_t i = file_offsets[f]; i < file_offsets[f + 1]; ++i) file_of[i] = (uint32_t)f;
-    for (uint64_t i = 0; i < total; ++i) {
-        if (chr[i] >= n_chroms || !(start[i] < end[i])) continue;
-        int32_t s = (int32_t)start[i], e = (int32_t)end[i];
-        if (s < 0 || e < 0 || s >= e) continue;
-        keep.push_back((uint32_t)i);
+    // ---- 1. records to the device; pooled order = stable sort by (chromosome, start) --------------------------------
+    // ties keep (file, insertion) order = the order Igd::add saw them (igd.rs:285-301); records Igd::add drops get the
+    // key n_chroms, land behind the last chromosome and are cut off
+    TempPool tp;
+    uint32_t *t_chr, *t_start, *t_end, *t_file, *t_key, *t_off;
+    uint64_t* t_fo;
+    GT_TRY(tp.get(total, &t_chr));
+    GT_TRY(tp.get(total, &t_start));
+    GT_TRY(tp.get(total, &t_end));
+    GT_TRY(tp.get(total, &t_file));
+    GT_TRY(tp.get(total, &t_key));
+    GT_TRY(tp.get(n_chroms + 2, &t_off));
+    GT_TRY(tp.get(n_files + 1, &t_fo));
+    if (total) {
+        GT_CUDA(cudaMemcpyAsync(t_chr, chr, total * 4, cudaMemcpyHostToDevice, st));
+        GT_CUDA(cudaMemcpyAsync(t_start, start, total * 4, cudaMemcpyHostToDevice, st));
+        GT_CUDA(cudaMemcpyAsync(t_end, end, total * 4, cudaMemcpyHostToDevice, st));
     }
-    // pooled order: by chromosome, then start; ties keep (file, insertion) order = the order Igd::add saw them
-    std::stable_sort(keep.begin(), keep.end(), [&](uint32_t a, uint32_t b) {
-        return chr[a] != chr[b] ? chr[a] < chr[b] : start[a] < start[b];
-    });
-    g->n_records = keep.size();
-    g->h_start.resize(keep.size());
-    g->h_end.resize(keep.size());
-    g->h_file.resize(keep.size());
+    GT_CUDA(cudaMemcpyAsync(t_fo, file_offsets, (n_files + 1) * 8, cudaMemcpyHostToDevice, st));
+    GT_CUDA(cudaStreamSynchronize(st));  // the caller's arrays may be pageable
+    PermSorter pooled;
+    GT_TRY(pooled.init(ctx, total));
+    if (total) {
+        GT_TRY(launch_fill_set_ids(ctx, n_files, t_fo, t_file));
+        igd_chrom_keys_kernel<<<grid_for(ctx, total), 256, 0, st>>>(total, n_chroms, t_chr, t_start, t_end, t_key);
+        ctx->launches++;
+        GT_TRY(pooled.pass(t_start, 0));
+        GT_TRY(pooled.pass(t_key, bits_for_value(n_chroms)));
+    }
     g->h_off.assign(n_chroms + 1, 0);
-    std::vector<int32_t> pmax(keep.size());
-    for (size_t k = 0; k < keep.size(); ++k) {
-        uint32_t i = keep[k];
-        g->h_start[k] = (int32_t)start[i];
-        g->h_end[k] = (int32_t)end[i];
-        g->h_file[k] = file_of[i];
-        g->h_off[chr[i] + 1]++;
+    if (total) {
+        GT_TRY(launch_key_offsets(ctx, total, pooled.key, n_chroms, t_off));
+        GT_CUDA(cudaMemcpyAsync(g->h_off.data(), t_off, (n_chroms + 1) * 4, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
     }
-    for (uint32_t c = 0; c < n_chroms; ++c) g->h_off[c + 1] += g->h_off[c];
-    int32_t max_coord = 0;
-    for (uint32_t c = 0; c < n_chroms; ++c) {
-        int32_t mx = 0;
-        for (uint32_t k = g->h_off[c]; k < g->h_off[c + 1]; ++k) {
-            mx = std::max(mx, g->h_end[k]);
-            pmax[k] = mx;
-            max_coord = std::max(max_coord, mx);
+    const uint64_t n_rec = g->h_off[n_chroms];
+    g->n_records = n_rec;
+
+    // ---- 2. the kept records in pooled order, running max of ends per chromosome ------------------------------------
+    GT_TRY(dev_alloc(g, n_rec, &g->d_start));
+    GT_TRY(dev_alloc(g, n_rec, &g->d_end));
+    GT_TRY(dev_alloc(g, n_rec, &g->d_file));
+    GT_TRY(dev_alloc(g, n_rec, &g->d_pmax));
+    GT_TRY(dev_alloc(g, n_rec, &g->d_psame1));
+    std::vector<uint32_t> last_start(n_chroms, 0), last_pmax(n_chroms, 0);
+    if (n_rec) {
+        GT_TRY(launch_gather_u32(ctx, n_rec, t_start, pooled.perm, (uint32_t*)g->d_start));
+        GT_TRY(launch_gather_u32(ctx, n_rec, t_end, pooled.perm, (uint32_t*)g->d_end));
+        GT_TRY(launch_gather_u32(ctx, n_rec, t_file, pooled.perm, g->d_file));
+        unsigned long long* d_packed;
+        char* d_scan_tmp;
+        GT_TRY(tp.get(n_rec, &d_packed));
+        GT_TRY(tp.get(exclusive_scan_temp_bytes(n_rec, 8), &d_scan_tmp));
+        igd_pack_pmax_kernel<<<grid_for(ctx, n_rec), 256, 0, st>>>(n_rec, pooled.key, g->d_end, d_packed);
+        GT_TRY(inclusive_max_scan_u64(ctx, d_packed, d_packed, n_rec, d_scan_tmp));
+        igd_low_words_kernel<<<grid_for(ctx, n_rec), 256, 0, st>>>(n_rec, d_packed, g->d_pmax);
+        ctx->launches += 2;
+        GT_CUDA(cudaGetLastError());
+        // the last start / running max of every chromosome size the LUTs
+        for (uint32_t c = 0; c < n_chroms; ++c) {
+            if (g->h_off[c + 1] == g->h_off[c]) continue;
+            GT_CUDA(cudaMemcpyAsync(&last_start[c], g->d_start + g->h_off[c + 1] - 1, 4, cudaMemcpyDeviceToHost, st));
+            GT_CUDA(cudaMemcpyAsync(&last_pmax[c], g->d_pmax + g->h_off[c + 1] - 1, 4, cudaMemcpyDeviceToHost, st));
         }
+        GT_CUDA(cudaStreamSynchronize(st));
     }
-    // LUT shift: at most ~8 M bins per family
+
+    // ---- 3. bin LUTs over starts and running maxima: at most ~8 M bins per family --------------------------------------
     uint32_t shift = 0;
     auto bins = [&](uint32_t sh) {
         uint64_t t = 0;
         for (uint32_t c = 0; c < n_chroms; ++c)
-            if (g->h_off[c + 1] > g->h_off[c]) t += ((uint32_t)pmax[g->h_off[c + 1] - 1] >> sh) + 2;
+            if (g->h_off[c + 1] > g->h_off[c]) t += (last_pmax[c] >> sh) + 2;
         return t;
     };
-    uint64_t budget = std::min<uint64_t>(std::max<uint64_t>(keep.size(), 4096), 8ull << 20);
+    const uint64_t budget = std::min<uint64_t>(std::max<uint64_t>(n_rec, 4096), 8ull << 20);
     while (shift < 31 && bins(shift) > budget) ++shift;
     g->shift = shift;
-    std::vector<uint32_t> lut, lso(n_chroms), nbs(n_chroms), lpo(n_chroms), nbp(n_chroms);
+    std::vector<uint32_t> lso(n_chroms), nbs(n_chroms), lpo(n_chroms), nbp(n_chroms);
+    std::vector<LutDesc> desc_s(n_chroms), desc_p(n_chroms);
+    std::vector<uint64_t> pre_s(n_chroms + 1, 0), pre_p(n_chroms + 1, 0);
+    uint64_t lut_len = 0;
     for (uint32_t c = 0; c < n_chroms; ++c) {
-        uint32_t o = g->h_off[c], len = g->h_off[c + 1] - o;
-        build_lut_i32(g->h_start.data() + o, len, shift, lut, lso[c], nbs[c]);
-        build_lut_i32(pmax.data() + o, len, shift, lut, lpo[c], nbp[c]);
+        const uint32_t o = g->h_off[c], len = g->h_off[c + 1] - o;
+        nbs[c] = len ? (last_start[c] >> shift) + 1 : 0;
+        nbp[c] = len ? (last_pmax[c] >> shift) + 1 : 0;
+        lso[c] = (uint32_t)lut_len;
+        lut_len += (uint64_t)nbs[c] + 1;
+        lpo[c] = (uint32_t)lut_len;
+        lut_len += (uint64_t)nbp[c] + 1;
+        desc_s[c] = LutDesc{o, len, lso[c], nbs[c]};
+        desc_p[c] = LutDesc{o, len, lpo[c], nbp[c]};
+        pre_s[c + 1] = pre_s[c] + nbs[c] + 1;
+        pre_p[c + 1] = pre_p[c] + nbp[c] + 1;
     }
-    std::vector<int32_t> psame1 = compute_psame(g, 1);
-    int32_t st = GTGPU_OK;
-    auto U = [&](auto& vec, auto** dst) { if (st == GTGPU_OK) st = up(g, vec, dst); };
-    U(g->h_off, &g->d_off);
-    U(lso, &g->d_lut_s_off);
-    U(nbs, &g->d_nb_s);
-    U(lpo, &g->d_lut_p_off);
-    U(nbp, &g->d_nb_p);
-    U(g->h_start, &g->d_start);
-    U(g->h_end, &g->d_end);
-    U(pmax, &g->d_pmax);
-    U(psame1, &g->d_psame1);
-    U(g->h_file, &g->d_file);
-    U(lut, &g->d_lut);
-    if (st != GTGPU_OK) {
-        gtgpu_igd_free(g);
-        return st;
+    if (lut_len >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "igd_build: LUT too large");
+    GT_TRY(dev_alloc(g, lut_len, &g->d_lut));
+    if (n_chroms) {
+        LutDesc *d_desc_s, *d_desc_p;
+        uint64_t *d_pre_s, *d_pre_p;
+        GT_TRY(tp.get(n_chroms, &d_desc_s));
+        GT_TRY(tp.get(n_chroms, &d_desc_p));
+        GT_TRY(tp.get(n_chroms + 1, &d_pre_s));
+        GT_TRY(tp.get(n_chroms + 1, &d_pre_p));
+        GT_CUDA(cudaMemcpyAsync(d_desc_s, desc_s.data(), n_chroms * sizeof(LutDesc), cudaMemcpyHostToDevice, st));
+        GT_CUDA(cudaMemcpyAsync(d_desc_p, desc_p.data(), n_chroms * sizeof(LutDesc), cudaMemcpyHostToDevice, st));
+        GT_CUDA(cudaMemcpyAsync(d_pre_s, pre_s.data(), (n_chroms + 1) * 8, cudaMemcpyHostToDevice, st));
+        GT_CUDA(cudaMemcpyAsync(d_pre_p, pre_p.data(), (n_chroms + 1) * 8, cudaMemcpyHostToDevice, st));
+        GT_TRY(launch_build_luts(ctx, n_chroms, d_desc_s, d_pre_s, pre_s[n_chroms], (const uint32_t*)g->d_start, shift, g->d_lut));
+        GT_TRY(launch_build_luts(ctx, n_chroms, d_desc_p, d_pre_p, pre_p[n_chroms], (const uint32_t*)g->d_pmax, shift, g->d_lut));
+        GT_CUDA(cudaStreamSynchronize(st));  // the descriptor vectors are pageable
     }
+    GT_TRY(device_psame(g, 1, g->d_psame1));
+    GT_TRY(up(g, g->h_off, &g->d_off));
+    GT_TRY(up(g, lso, &g->d_lut_s_off));
+    GT_TRY(up(g, nbs, &g->d_nb_s));
+    GT_TRY(up(g, lpo, &g->d_lut_p_off));
+    GT_TRY(up(g, nbp, &g->d_nb_p));
+    GT_CUDA(cudaStreamSynchronize(st));
     g->psame_by_m[1] = g->d_psame1;
+    guard.g = nullptr;
     *out_igd = g;
     return GTGPU_OK;
 }
@@ -276,9 +425,9 @@ int32_t igd_count_dev_impl(gtgpu_igd* g, bool binary, uint64_t n, const uint32_t
     if (binary) {
         auto it = g->psame_by_m.find(m);
         if (it == g->psame_by_m.end()) {
-            std::vector<int32_t> ps = compute_psame(g, m);
             int32_t* d = nullptr;
-            GT_TRY(up(g, ps, &d));
+            GT_TRY(dev_alloc(g, g->n_records, &d));
+            GT_TRY(device_psame(g, m, d));
             it = g->psame_by_m.emplace(m, d).first;
         }
         d_psame = it->second;

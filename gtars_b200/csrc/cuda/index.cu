@@ -1,4 +1,4 @@
-// index.cu — host-side build of the device index (gtgpu_index_build).
+// index.cu — build of the device index (gtgpu_index_build).
 //
 // Order semantics of the reference are fixed here, once:
 //   Bits   (gtars-overlaprs/src/bits.rs:101-128):   stable sort by (start,end); one segment per chromosome.
@@ -6,37 +6,53 @@
 //          "long" intervals (>= 10 of the next 19 end earlier) into further components; no cap on components.
 // Both get the same device layout: start-sorted SoA segments + running max of ends + bin LUTs, so the kernels
 // locate candidates identically and only the emission direction differs.
+//
+// The O(n log n) part — the stable sorts and the independently sorted start / end arrays of the counting identity —
+// runs on the device for anything but small inputs (PermSorter, build.cu: stable LSD radix passes over a permutation;
+// a 50 M-interval database is ordered in tens of milliseconds instead of ~20 s of std::stable_sort).  What follows is
+// linear: AIList peeling, flattening, LUTs and the window table are filled per chromosome by a pool of host threads
+// from the sorted order, once, into a HostIndex that can be uploaded to any number of devices (multi-device contexts
+// replicate the index).
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include "common.cuh"
 
 namespace gtgpu {
 
+int32_t launch_fill_set_ids(gtgpu_ctx* ctx, uint64_t n_sets, const uint64_t* d_set_offsets, uint32_t* d_set_of);
+
 namespace {
 
-struct HostSeg {
-    uint32_t chrom;
-    std::vector<uint32_t> order;  // indices into the caller's arrays
-};
-
-// lut[b] = lower_bound(arr, b << shift) for b in [0, nb], nb = (max >> shift) + 1, lut[nb] = n.
-void build_lut(const uint32_t* arr, uint32_t n, uint32_t shift, std::vector<uint32_t>& lut, uint32_t& lut_off,
-               uint32_t& nb) {
-    lut_off = (uint32_t)lut.size();
-    if (n == 0) {
-        nb = 0;
-        lut.push_back(0);
+// fn(i) for i in [0, n) on up to hardware_concurrency threads (dynamic hand-out: chromosomes differ 10 000x in size)
+template <class F>
+void parallel_for(uint64_t n, F&& fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char* env = getenv("GTGPU_BUILD_THREADS")) hw = (unsigned)std::max(1, atoi(env));
+    const unsigned nt = (unsigned)std::min<uint64_t>(std::max(1u, std::min(hw, 32u)), n);
+    if (nt <= 1) {
+        for (uint64_t i = 0; i < n; ++i) fn(i);
         return;
     }
-    nb = (arr[n - 1] >> shift) + 1;
-    lut.resize(lut.size() + (size_t)nb + 1);
-    uint32_t* L = lut.data() + lut_off;
+    std::atomic<uint64_t> next{0};
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+        th.emplace_back([&]() {
+            for (uint64_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+        });
+    for (auto& t : th) t.join();
+}
+
+// lut[b] = lower_bound(arr, b << shift) for b in [0, nb], nb = (max >> shift) + 1, lut[nb] = n (n == 0: one entry).
+uint32_t lut_bins(const uint32_t* arr, uint32_t n, uint32_t shift) { return n ? (arr[n - 1] >> shift) + 1 : 0; }
+void fill_lut(const uint32_t* arr, uint32_t n, uint32_t shift, uint32_t nb, uint32_t* L) {
     uint32_t i = 0;
     for (uint32_t b = 0; b < nb; ++b) {
-        uint64_t key = (uint64_t)b << shift;
+        const uint64_t key = (uint64_t)b << shift;
         while (i < n && arr[i] < key) ++i;
         L[b] = i;
     }
@@ -49,110 +65,214 @@ uint64_t lut_entries(const std::vector<uint32_t>& maxima, uint32_t shift) {
     return t;
 }
 
-template <class T>
-int32_t upload(gtgpu_index* ix, const std::vector<T>& v, const T** out) {
-    void* d = nullptr;
-    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
-    cudaError_t e = cudaMalloc(&d, bytes);
-    if (e != cudaSuccess) return fail(GTGPU_ERR_NOMEM, std::string("cudaMalloc(index): ") + cudaGetErrorString(e));
-    ix->allocs.push_back(d);
-    ix->device_bytes += bytes;
-    if (!v.empty()) GT_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    *out = (const T*)d;
+struct DevTemp {  // device temporaries of the sort stage
+    std::vector<void*> ptrs;
+    template <class T>
+    int32_t get(uint64_t count, T** out) {
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, std::max<size_t>(count * sizeof(T), 16));
+        if (e != cudaSuccess) return fail(GTGPU_ERR_NOMEM, std::string("cudaMalloc(index build): ") + cudaGetErrorString(e));
+        ptrs.push_back(d);
+        *out = (T*)d;
+        return GTGPU_OK;
+    }
+    ~DevTemp() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+};
+
+// Device stage: order[] = every chromosome's intervals in the backend's sorted order (global indices, chromosome c in
+// [offs[c], offs[c+1])), cs[] / ce[] = each chromosome's starts / ends sorted independently.
+int32_t device_order(gtgpu_ctx* ctx, int32_t kind, uint32_t n_chroms, const uint64_t* chrom_offsets, uint64_t total,
+                     const uint32_t* starts, const uint32_t* ends, uint32_t* order, uint32_t* cs, uint32_t* ce) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    DevTemp tp;
+    uint32_t *d_s, *d_e, *d_chr, *d_tmp;
+    uint64_t* d_co;
+    GT_TRY(tp.get(total, &d_s));
+    GT_TRY(tp.get(total, &d_e));
+    GT_TRY(tp.get(total, &d_chr));
+    GT_TRY(tp.get(total, &d_tmp));
+    GT_TRY(tp.get(n_chroms + 1, &d_co));
+    GT_CUDA(cudaMemcpyAsync(d_s, starts, total * 4, cudaMemcpyHostToDevice, st));
+    GT_CUDA(cudaMemcpyAsync(d_e, ends, total * 4, cudaMemcpyHostToDevice, st));
+    GT_CUDA(cudaMemcpyAsync(d_co, chrom_offsets, (n_chroms + 1) * 8, cudaMemcpyHostToDevice, st));
+    GT_CUDA(cudaStreamSynchronize(st));
+    GT_TRY(launch_fill_set_ids(ctx, n_chroms, d_co, d_chr));
+    const int chr_bits = bits_for_value(n_chroms);
+    {
+        PermSorter by_start;
+        GT_TRY(by_start.init(ctx, total));
+        if (kind == GTGPU_KIND_BITS) GT_TRY(by_start.pass(d_e, 0));  // Bits: ties on start are ordered by end (interval.rs:18-31)
+        GT_TRY(by_start.pass(d_s, 0));
+        GT_TRY(by_start.pass(d_chr, chr_bits));
+        GT_CUDA(cudaMemcpyAsync(order, by_start.perm, total * 4, cudaMemcpyDeviceToHost, st));
+        GT_TRY(launch_gather_u32(ctx, total, d_s, by_start.perm, d_tmp));  // starts in that order = sorted per chromosome
+        GT_CUDA(cudaMemcpyAsync(cs, d_tmp, total * 4, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+    }
+    {
+        PermSorter by_end;
+        GT_TRY(by_end.init(ctx, total));
+        GT_TRY(by_end.pass(d_e, 0));
+        GT_TRY(by_end.pass(d_chr, chr_bits));
+        GT_TRY(launch_gather_u32(ctx, total, d_e, by_end.perm, d_tmp));
+        GT_CUDA(cudaMemcpyAsync(ce, d_tmp, total * 4, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+    }
     return GTGPU_OK;
 }
 
+struct HostSeg {
+    std::vector<uint32_t> order;  // indices into the caller's arrays
+};
+
 }  // namespace
 
-}  // namespace gtgpu
+// Everything gtgpu_index needs, in host memory: built once, uploaded to one device or to every device of a group.
+struct HostIndex {
+    int32_t kind = 0;
+    uint32_t n_chroms = 0;
+    uint64_t total = 0, n_segments = 0, max_components = 0;
+    bool proper = true;
+    std::vector<ChromMeta> chroms;
+    std::vector<SegMeta> seg_meta;
+    std::vector<uint32_t> h_starts, h_ends, h_pmax, h_vals, h_cs, h_ce, lut;
+    std::vector<unsigned long long> rank_lut;
+    uint32_t shift = 0, rank_shift = 0, rank_inline = 0, bt_shift = 0, max_val = 0;
+    std::vector<ChromBT> chrom_bt;
+    std::vector<uint32_t> bt_lut, bt_pool, bt_rec;
+    std::vector<uint4> bt_ent;
+    uint64_t bt_overflow = 0, bt_pool_windows = 0;
+};
 
-using namespace gtgpu;
+void host_index_free(HostIndex* h) { delete h; }
 
-extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_chroms, const uint64_t* chrom_offsets,
-                                     const uint32_t* starts, const uint32_t* ends, const uint32_t* vals,
-                                     gtgpu_index** out_index) {
-    if (!ctx || !out_index || (n_chroms && !chrom_offsets)) return fail(GTGPU_ERR_INVALID, "index_build: null argument");
+int32_t host_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_chroms, const uint64_t* chrom_offsets, const uint32_t* starts,
+                         const uint32_t* ends, const uint32_t* vals, HostIndex** out) {
+    if (!ctx || !out || (n_chroms && !chrom_offsets)) return fail(GTGPU_ERR_INVALID, "index_build: null argument");
     if (kind != GTGPU_KIND_BITS && kind != GTGPU_KIND_AILIST) return fail(GTGPU_ERR_INVALID, "index_build: bad kind");
-    uint64_t total = n_chroms ? chrom_offsets[n_chroms] : 0;
+    const uint64_t total = n_chroms ? chrom_offsets[n_chroms] : 0;
     if (total >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "index_build: more than 2^32-2 intervals");
     if (total && (!starts || !ends)) return fail(GTGPU_ERR_INVALID, "index_build: null coordinate arrays");
     for (uint32_t c = 0; c < n_chroms; ++c)
         if (chrom_offsets[c] > chrom_offsets[c + 1]) return fail(GTGPU_ERR_INVALID, "index_build: chrom_offsets not monotone");
+    if (n_chroms && chrom_offsets[0] != 0) return fail(GTGPU_ERR_INVALID, "index_build: chrom_offsets[0] must be 0");
     GT_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<HostIndex> hp(new HostIndex());
+    HostIndex& H = *hp;
+    H.kind = kind;
+    H.n_chroms = n_chroms;
+    H.total = total;
 
-    // ---- 1. per-chromosome ordering + AIList decomposition ------------------------------------------------
-    std::vector<HostSeg> segs;
-    std::vector<ChromMeta> chroms(n_chroms);
-    uint64_t max_components = 0;
-    bool proper = true;
-    for (uint32_t c = 0; c < n_chroms; ++c) {
-        uint64_t lo = chrom_offsets[c], hi = chrom_offsets[c + 1];
-        chroms[c].seg_begin = (uint32_t)segs.size();
-        if (hi > lo) {
-            std::vector<uint32_t> order(hi - lo);
-            std::iota(order.begin(), order.end(), (uint32_t)lo);
-            if (kind == GTGPU_KIND_BITS) {
-                std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    // ---- 1. per-chromosome ordering (device radix sort, or the host's stable sort for small inputs) ---------------------
+    std::vector<uint32_t> order_all(total);
+    H.h_cs.resize(total);
+    H.h_ce.resize(total);
+    bool on_device = total >= (1u << 16);
+    if (const char* env = getenv("GTGPU_BUILD_SORT")) on_device = total > 0 && env[0] == 'd';  // "device" / "host"
+    if (on_device) {
+        GT_TRY(device_order(ctx, kind, n_chroms, chrom_offsets, total, starts, ends, order_all.data(), H.h_cs.data(), H.h_ce.data()));
+    } else {
+        parallel_for(n_chroms, [&](uint64_t c) {
+            const uint64_t lo = chrom_offsets[c], hi = chrom_offsets[c + 1];
+            std::iota(order_all.begin() + lo, order_all.begin() + hi, (uint32_t)lo);
+            if (kind == GTGPU_KIND_BITS)
+                std::stable_sort(order_all.begin() + lo, order_all.begin() + hi, [&](uint32_t a, uint32_t b) {
                     return starts[a] != starts[b] ? starts[a] < starts[b] : ends[a] < ends[b];
                 });
-                segs.push_back(HostSeg{c, std::move(order)});
-            } else {
-                std::stable_sort(order.begin(), order.end(),
+            else
+                std::stable_sort(order_all.begin() + lo, order_all.begin() + hi,
                                  [&](uint32_t a, uint32_t b) { return starts[a] < starts[b]; });
-                const size_t min_cov = 10;
-                std::vector<uint32_t> next;
-                while (!order.empty()) {
-                    HostSeg seg{c, {}};
-                    next.clear();
-                    for (size_t i = 0; i < order.size(); ++i) {
-                        size_t covered = 0;
-                        uint32_t e_i = ends[order[i]];
-                        for (size_t j = 1; j < 2 * min_cov && i + j < order.size(); ++j)
-                            covered += e_i > ends[order[i + j]];
-                        if (covered >= min_cov) next.push_back(order[i]);
-                        else seg.order.push_back(order[i]);
-                    }
-                    // A pass that keeps nothing cannot happen: the last interval of a list always has covered == 0.
-                    segs.push_back(std::move(seg));
-                    order.swap(next);
-                }
-            }
-        }
-        chroms[c].seg_end = (uint32_t)segs.size();
-        max_components = std::max<uint64_t>(max_components, chroms[c].seg_end - chroms[c].seg_begin);
+            std::copy(starts + lo, starts + hi, H.h_cs.begin() + lo);
+            std::copy(ends + lo, ends + hi, H.h_ce.begin() + lo);
+            std::sort(H.h_cs.begin() + lo, H.h_cs.begin() + hi);
+            std::sort(H.h_ce.begin() + lo, H.h_ce.begin() + hi);
+        });
     }
 
+    // ---- 1b. segments: Bits = the chromosome; AIList = repeated peeling of the sorted list (ailist.rs:128-142, 198-236) --
+    std::vector<std::vector<HostSeg>> chrom_segs(n_chroms);
+    parallel_for(n_chroms, [&](uint64_t c) {
+        const uint64_t lo = chrom_offsets[c], hi = chrom_offsets[c + 1];
+        if (hi == lo) return;
+        std::vector<uint32_t> order(order_all.begin() + lo, order_all.begin() + hi);
+        if (kind == GTGPU_KIND_BITS) {
+            chrom_segs[c].push_back(HostSeg{std::move(order)});
+            return;
+        }
+        const size_t min_cov = 10;
+        std::vector<uint32_t> next;
+        while (!order.empty()) {
+            HostSeg seg;
+            next.clear();
+            for (size_t i = 0; i < order.size(); ++i) {
+                size_t covered = 0;
+                const uint32_t e_i = ends[order[i]];
+                for (size_t j = 1; j < 2 * min_cov && i + j < order.size(); ++j) covered += e_i > ends[order[i + j]];
+                if (covered >= min_cov) next.push_back(order[i]);
+                else seg.order.push_back(order[i]);
+            }
+            // A pass that keeps nothing cannot happen: the last interval of a list always has covered == 0.
+            chrom_segs[c].push_back(std::move(seg));
+            order.swap(next);
+        }
+    });
+    std::vector<uint32_t>().swap(order_all);
+    std::vector<ChromMeta>& chroms = H.chroms;
+    chroms.assign(n_chroms, ChromMeta{});
+    std::vector<HostSeg*> segs;
+    for (uint32_t c = 0; c < n_chroms; ++c) {
+        chroms[c].seg_begin = (uint32_t)segs.size();
+        for (auto& s : chrom_segs[c]) segs.push_back(&s);
+        chroms[c].seg_end = (uint32_t)segs.size();
+        chroms[c].off = (uint32_t)chrom_offsets[c];
+        chroms[c].len = (uint32_t)(chrom_offsets[c + 1] - chrom_offsets[c]);
+        H.max_components = std::max<uint64_t>(H.max_components, chroms[c].seg_end - chroms[c].seg_begin);
+    }
+    H.n_segments = segs.size();
+
     // ---- 2. flatten to SoA ---------------------------------------------------------------------------------
-    std::vector<uint32_t> h_starts(total), h_ends(total), h_pmax(total), h_vals(total), h_cs(total), h_ce(total);
-    std::vector<SegMeta> seg_meta(segs.size());
+    std::vector<uint32_t>&h_starts = H.h_starts, &h_ends = H.h_ends, &h_pmax = H.h_pmax, &h_vals = H.h_vals, &h_cs = H.h_cs, &h_ce = H.h_ce;
+    h_starts.resize(total);
+    h_ends.resize(total);
+    h_pmax.resize(total);
+    h_vals.resize(total);
+    std::vector<SegMeta>& seg_meta = H.seg_meta;
+    seg_meta.assign(segs.size(), SegMeta{});
     {
         uint64_t pos = 0;
         for (size_t s = 0; s < segs.size(); ++s) {
+            seg_meta[s].off = (uint32_t)pos;
+            seg_meta[s].len = (uint32_t)segs[s]->order.size();
+            pos += segs[s]->order.size();
+        }
+        std::vector<uint8_t> improper(segs.size(), 0);
+        std::vector<uint32_t> seg_max_val(segs.size(), 0);
+        parallel_for(segs.size(), [&](uint64_t s) {
             SegMeta& m = seg_meta[s];
-            m.off = (uint32_t)pos;
-            m.len = (uint32_t)segs[s].order.size();
             m.mono = 1;
             m.pad = 0;
-            uint32_t mx = 0;
-            for (uint32_t id : segs[s].order) {
-                h_starts[pos] = starts[id];
-                h_ends[pos] = ends[id];
-                h_vals[pos] = vals ? vals[id] : id;
+            uint32_t mx = 0, mv = 0;
+            uint64_t p = m.off;
+            for (uint32_t id : segs[s]->order) {
+                h_starts[p] = starts[id];
+                h_ends[p] = ends[id];
+                h_vals[p] = vals ? vals[id] : id;
+                mv = std::max(mv, h_vals[p]);
                 if (ends[id] < mx) m.mono = 0;
                 mx = std::max(mx, ends[id]);
-                h_pmax[pos] = mx;
-                if (starts[id] > ends[id]) proper = false;
-                ++pos;
+                h_pmax[p] = mx;
+                if (starts[id] > ends[id]) improper[s] = 1;
+                ++p;
             }
-        }
-        for (uint32_t c = 0; c < n_chroms; ++c) {
-            uint64_t lo = chrom_offsets[c], hi = chrom_offsets[c + 1];
-            chroms[c].off = (uint32_t)lo;
-            chroms[c].len = (uint32_t)(hi - lo);
-            std::copy(starts + lo, starts + hi, h_cs.begin() + lo);
-            std::copy(ends + lo, ends + hi, h_ce.begin() + lo);
-            std::sort(h_cs.begin() + lo, h_cs.begin() + hi);
-            std::sort(h_ce.begin() + lo, h_ce.begin() + hi);
+            seg_max_val[s] = mv;
+            std::vector<uint32_t>().swap(segs[s]->order);
+        });
+        for (size_t s = 0; s < segs.size(); ++s) {
+            if (improper[s]) H.proper = false;
+            H.max_val = std::max(H.max_val, seg_max_val[s]);
         }
     }
 
@@ -173,11 +293,26 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
     uint32_t shift = 0;
     while (shift < 31 && std::max(lut_entries(max_s, shift), lut_entries(max_p, shift)) > budget) ++shift;
     if (const char* env = getenv("GTGPU_LUT_SHIFT")) shift = (uint32_t)std::min(31, std::max(0, atoi(env)));
+    H.shift = shift;
 
-    std::vector<uint32_t> lut;
-    for (auto& m : seg_meta) {
-        build_lut(h_starts.data() + m.off, m.len, shift, lut, m.lut_s, m.nb_s);
-        build_lut(h_pmax.data() + m.off, m.len, shift, lut, m.lut_p, m.nb_p);
+    std::vector<uint32_t>& lut = H.lut;
+    {
+        uint64_t len = 0;
+        for (auto& m : seg_meta) {
+            m.nb_s = lut_bins(h_starts.data() + m.off, m.len, shift);
+            m.nb_p = lut_bins(h_pmax.data() + m.off, m.len, shift);
+            m.lut_s = (uint32_t)len;
+            len += (uint64_t)m.nb_s + 1;
+            m.lut_p = (uint32_t)len;
+            len += (uint64_t)m.nb_p + 1;
+        }
+        if (len >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "index_build: LUT too large");
+        lut.resize(len);
+        parallel_for(seg_meta.size(), [&](uint64_t s) {
+            const SegMeta& m = seg_meta[s];
+            fill_lut(h_starts.data() + m.off, m.len, shift, m.nb_s, lut.data() + m.lut_s);
+            fill_lut(h_pmax.data() + m.off, m.len, shift, m.nb_p, lut.data() + m.lut_p);
+        });
     }
     // rank LUTs (see IndexView::rank_lut) over the chromosome-level sorted starts / ends
     uint32_t rank_shift = 0;
@@ -187,12 +322,10 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
         while (rank_shift < 29 && std::max(lut_entries(max_cs, rank_shift), lut_entries(max_ce, rank_shift)) > rbudget) ++rank_shift;
     }
     const uint32_t rank_inline = rank_shift == 0 ? 4 : std::min<uint32_t>(4, 29 / rank_shift);
-    std::vector<unsigned long long> rank_lut;
-    auto build_rank = [&](const uint32_t* arr, uint32_t n, uint32_t& off, uint32_t& nb) {
-        off = (uint32_t)rank_lut.size();
-        nb = n ? (arr[n - 1] >> rank_shift) + 1 : 0;
-        rank_lut.resize(rank_lut.size() + (size_t)nb + 1);
-        unsigned long long* L = rank_lut.data() + off;
+    H.rank_shift = rank_shift;
+    H.rank_inline = rank_inline;
+    std::vector<unsigned long long>& rank_lut = H.rank_lut;
+    auto fill_rank = [&](const uint32_t* arr, uint32_t n, uint32_t nb, unsigned long long* L) {
         uint32_t i = 0;
         for (uint32_t b = 0; b < nb; ++b) {
             const uint32_t base = i;
@@ -209,24 +342,36 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
         }
         L[nb] = n;  // sentinel: base = n, count 0
     };
-    for (auto& c : chroms) {
-        build_rank(h_cs.data() + c.off, c.len, c.lut_cs, c.nb_cs);
-        build_rank(h_ce.data() + c.off, c.len, c.lut_ce, c.nb_ce);
+    {
+        uint64_t len = 0;
+        for (auto& c : chroms) {
+            c.nb_cs = lut_bins(h_cs.data() + c.off, c.len, rank_shift);
+            c.nb_ce = lut_bins(h_ce.data() + c.off, c.len, rank_shift);
+            c.lut_cs = (uint32_t)len;
+            len += (uint64_t)c.nb_cs + 1;
+            c.lut_ce = (uint32_t)len;
+            len += (uint64_t)c.nb_ce + 1;
+        }
+        if (len >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "index_build: rank LUT too large");
+        rank_lut.resize(len);
+        parallel_for(2 * (uint64_t)chroms.size(), [&](uint64_t k) {
+            const ChromMeta& c = chroms[k >> 1];
+            if (k & 1) fill_rank(h_ce.data() + c.off, c.len, c.nb_ce, rank_lut.data() + c.lut_ce);
+            else fill_rank(h_cs.data() + c.off, c.len, c.nb_cs, rank_lut.data() + c.lut_cs);
+        });
     }
-    if (rank_lut.size() >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "index_build: rank LUT too large");
-    if (lut.size() >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "index_build: LUT too large");
 
     // ---- 3b. bin table (fast path of find/tokenize; see common.cuh) ------------------------------------------
-    std::vector<ChromBT> chrom_bt(n_chroms);
-    std::vector<uint32_t> bt_lut;   // per window: direct run, pool list or overflow (encodings in common.cuh)
-    std::vector<uint32_t> bt_pool;  // candidate lists (entry indices, in emission order) of the pool windows
-    std::vector<uint4> bt_ent;      // {start, end, val, 0} per interval, segment order (padded by two)
-    std::vector<uint32_t> bt_rec;   // per window: the candidates inline, window-relative (fast path; common.cuh)
+    std::vector<ChromBT>& chrom_bt = H.chrom_bt;
+    chrom_bt.assign(n_chroms, ChromBT{});
+    std::vector<uint32_t>& bt_lut = H.bt_lut;    // per window: direct run, pool list or overflow (encodings in common.cuh)
+    std::vector<uint32_t>& bt_pool = H.bt_pool;  // candidate lists (entry indices, in emission order) of the pool windows
+    std::vector<uint4>& bt_ent = H.bt_ent;       // {start, end, val, 0} per interval, segment order (padded by two)
+    std::vector<uint32_t>& bt_rec = H.bt_rec;    // per window: the candidates inline, window-relative (fast path; common.cuh)
     uint32_t bt_shift = 0;
-    uint64_t bt_overflow = 0, bt_pool_windows = 0;
     {
         std::vector<uint64_t> cover_end(n_chroms, 0);  // exclusive end of the positions the chromosome's intervals touch
-        for (uint32_t c = 0; c < n_chroms; ++c) {
+        parallel_for(n_chroms, [&](uint64_t c) {
             bool ok = chroms[c].seg_end > chroms[c].seg_begin;
             uint64_t ce = 0;
             for (uint32_t si = chroms[c].seg_begin; ok && si < chroms[c].seg_end; ++si) {
@@ -237,7 +382,7 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
                 }
             }
             cover_end[c] = ok ? ce : 0;
-        }
+        });
         auto total_bins = [&](uint32_t sh) {
             uint64_t t = 0;
             for (uint32_t c = 0; c < n_chroms; ++c)
@@ -254,6 +399,7 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
         // window records hold window-relative coordinates in 2 (bt_shift + 2) bits: sparse universes get narrower bins
         if (bt_shift > BT_REC_MAX_SHIFT && total_bins(BT_REC_MAX_SHIFT) <= bt_cap) bt_shift = BT_REC_MAX_SHIFT;
         if (const char* env = getenv("GTGPU_BT_SHIFT")) bt_shift = (uint32_t)std::min(31, std::max(0, atoi(env)));
+        H.bt_shift = bt_shift;
         // A table only pays off while most windows hold a few candidates: skip it for dense databases.
         bool enabled = bt_cap > 0 && total_bins(bt_shift) <= (64ull << 20) && total <= total_bins(bt_shift) &&
                        total < (1ull << 29) && bt_shift <= BT_REC_MAX_SHIFT;
@@ -272,7 +418,8 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
                 pos += nb;
             }
         }
-        // Pass 1: per window, how many intervals touch it and the index range they span.
+        auto has_table = [&](uint32_t c) { return chrom_bt[c].n_bins != 0 && !(chrom_bt[c].n_bins & BT_GENERIC_CHROM); };
+        // Pass 1: per window, how many intervals touch it and the index range they span (chromosomes own disjoint windows).
         std::vector<uint32_t> w_min(pos, 0xFFFFFFFFu), w_max(pos, 0);
         std::vector<uint8_t> w_cnt(pos, 0);
         auto for_each_window = [&](uint32_t c, uint32_t i, auto&& fn) {
@@ -282,8 +429,9 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
             if (b0 > 0) --b0;
             for (uint64_t b = b0; b <= b1; ++b) fn(chrom_bt[c].off + b);
         };
-        for (uint32_t c = 0; c < n_chroms; ++c) {
-            if (chrom_bt[c].n_bins == 0 || chrom_bt[c].n_bins == BT_GENERIC_CHROM) continue;
+        parallel_for(n_chroms, [&](uint64_t cc) {
+            const uint32_t c = (uint32_t)cc;
+            if (!has_table(c)) return;
             for (uint32_t si = chroms[c].seg_begin; si < chroms[c].seg_end; ++si)
                 for (uint32_t i = seg_meta[si].off; i < seg_meta[si].off + seg_meta[si].len; ++i)
                     for_each_window(c, i, [&](uint64_t k) {
@@ -291,35 +439,69 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
                         w_max[k] = std::max(w_max[k], i);
                         if (w_cnt[k] < 255) w_cnt[k]++;
                     });
-        }
+        });
         // Classify: a contiguous run of <= 2 intervals on a single-segment chromosome is addressed directly; up to
-        // BT_POOL_MAX candidates of any shape (nested intervals, several AIList components) go to a pool list.
+        // BT_POOL_MAX candidates of any shape (nested intervals, several AIList components) go to a pool list.  Pool
+        // offsets follow window order across chromosomes; once the pool is full the remaining windows overflow.
         bt_lut.assign(pos, 0);
         std::vector<uint8_t> fill(pos, 0);
-        uint64_t pool_size = 0;
-        for (uint32_t c = 0; c < n_chroms; ++c) {
-            if (chrom_bt[c].n_bins == 0 || chrom_bt[c].n_bins == BT_GENERIC_CHROM) continue;
-            const bool single = chroms[c].seg_end - chroms[c].seg_begin == 1;
+        const uint64_t pool_limit = (1ull << (31 - BT_POOL_SHIFT)) - 16;
+        auto is_direct = [&](uint32_t c, uint64_t k) {
+            const uint32_t n = w_cnt[k];
+            return chroms[c].seg_end - chroms[c].seg_begin == 1 && n <= 2 && w_max[k] - w_min[k] + 1 == n;
+        };
+        std::vector<uint64_t> pool_need(n_chroms + 1, 0);  // pool entries per chromosome when nothing overflows the pool
+        parallel_for(n_chroms, [&](uint64_t cc) {
+            const uint32_t c = (uint32_t)cc;
+            if (!has_table(c)) return;
+            uint64_t need = 0;
+            for (uint64_t k = chrom_bt[c].off; k < (uint64_t)chrom_bt[c].off + chrom_bt[c].n_bins; ++k) {
+                const uint32_t n = w_cnt[k];
+                if (n && !is_direct(c, k) && n <= BT_POOL_MAX) need += n;
+            }
+            pool_need[c + 1] = need;
+        });
+        for (uint32_t c = 0; c < n_chroms; ++c) pool_need[c + 1] += pool_need[c];
+        const bool pool_fits = pool_need[n_chroms] < pool_limit;
+        std::vector<uint64_t> c_overflow(n_chroms, 0), c_poolw(n_chroms, 0);
+        auto classify = [&](uint32_t c, uint64_t& pool_size) {
             for (uint64_t k = chrom_bt[c].off; k < (uint64_t)chrom_bt[c].off + chrom_bt[c].n_bins; ++k) {
                 const uint32_t n = w_cnt[k];
                 if (n == 0) continue;
-                if (single && n <= 2 && w_max[k] - w_min[k] + 1 == n) {
+                if (is_direct(c, k)) {
                     bt_lut[k] = (w_min[k] << 2) | n;
-                } else if (n <= BT_POOL_MAX && pool_size + n < (1ull << (31 - BT_POOL_SHIFT)) - 16) {
+                } else if (n <= BT_POOL_MAX && pool_size + n < pool_limit) {
                     bt_lut[k] = BT_POOL_FLAG | ((uint32_t)pool_size << BT_POOL_SHIFT) | n;
                     pool_size += n;
-                    ++bt_pool_windows;
+                    ++c_poolw[c];
                 } else {
                     bt_lut[k] = BT_OVERFLOW;
-                    ++bt_overflow;
+                    ++c_overflow[c];
                 }
             }
+        };
+        uint64_t pool_size = 0;
+        if (pool_fits) {
+            parallel_for(n_chroms, [&](uint64_t cc) {
+                if (!has_table((uint32_t)cc)) return;
+                uint64_t ps = pool_need[cc];
+                classify((uint32_t)cc, ps);
+            });
+            pool_size = pool_need[n_chroms];
+        } else {
+            for (uint32_t c = 0; c < n_chroms; ++c)
+                if (has_table(c)) classify(c, pool_size);
+        }
+        for (uint32_t c = 0; c < n_chroms; ++c) {
+            H.bt_overflow += c_overflow[c];
+            H.bt_pool_windows += c_poolw[c];
         }
         // Pass 2: fill the pool lists in emission order — Bits: ascending sorted position; AIList: component-major,
         // descending position inside a component (ailist.rs:153-178, 238-263).
         bt_pool.assign(pool_size + 1, 0);
-        for (uint32_t c = 0; c < n_chroms; ++c) {
-            if (chrom_bt[c].n_bins == 0 || chrom_bt[c].n_bins == BT_GENERIC_CHROM) continue;
+        parallel_for(n_chroms, [&](uint64_t cc) {
+            const uint32_t c = (uint32_t)cc;
+            if (!has_table(c)) return;
             for (uint32_t si = chroms[c].seg_begin; si < chroms[c].seg_end; ++si) {
                 const SegMeta& m = seg_meta[si];
                 for (uint32_t t = 0; t < m.len; ++t) {
@@ -331,12 +513,12 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
                     });
                 }
             }
-        }
-        for (uint32_t c = 0; c < n_chroms; ++c)
-            if (chrom_bt[c].n_bins != 0 && chrom_bt[c].n_bins != BT_GENERIC_CHROM && chroms[c].seg_end - chroms[c].seg_begin > 1)
-                chrom_bt[c].n_bins |= BT_MULTI_COMP;
+        });
         bt_ent.resize(total + 2);
-        for (uint64_t i = 0; i < total; ++i) bt_ent[i] = make_uint4(h_starts[i], h_ends[i], h_vals[i], 0);
+        parallel_for((total + (1 << 20) - 1) >> 20, [&](uint64_t blk) {
+            const uint64_t lo = blk << 20, hi = std::min<uint64_t>(total, lo + (1 << 20));
+            for (uint64_t i = lo; i < hi; ++i) bt_ent[i] = make_uint4(h_starts[i], h_ends[i], h_vals[i], 0);
+        });
         bt_ent[total] = bt_ent[total + 1] = make_uint4(0xFFFFFFFFu, 0, 0, 0);
         // Window records: the direct runs again, inline and window-relative (record 0 stays the empty sentinel).
         bt_rec.assign(pos * BT_REC_WORDS, 0);
@@ -347,8 +529,9 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
             const uint64_t e = h_ends[i] <= base ? 0 : std::min<uint64_t>(h_ends[i] - base, rel_max);
             return (uint32_t)(s | (e << rel_bits));
         };
-        for (uint32_t c = 0; c < n_chroms; ++c) {
-            if (chrom_bt[c].n_bins == 0 || (chrom_bt[c].n_bins & BT_GENERIC_CHROM)) continue;
+        parallel_for(n_chroms, [&](uint64_t cc) {
+            const uint32_t c = (uint32_t)cc;
+            if (!has_table(c)) return;
             const uint64_t nb = chrom_bt[c].n_bins & BT_NBINS_MASK;
             for (uint64_t b = 0; b < nb; ++b) {
                 const uint64_t k = chrom_bt[c].off + b, base = b << bt_shift;
@@ -368,60 +551,85 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
                     r[3] = h_vals[first + 1];
                 }
             }
-        }
+        });
+        for (uint32_t c = 0; c < n_chroms; ++c)
+            if (has_table(c) && chroms[c].seg_end - chroms[c].seg_begin > 1) chrom_bt[c].n_bins |= BT_MULTI_COMP;
     }
+    *out = hp.release();
+    return GTGPU_OK;
+}
 
-    // ---- 4. upload ---------------------------------------------------------------------------------------------
+namespace {
+
+template <class T>
+int32_t upload(gtgpu_index* ix, const std::vector<T>& v, const T** out) {
+    void* d = nullptr;
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) return fail(GTGPU_ERR_NOMEM, std::string("cudaMalloc(index): ") + cudaGetErrorString(e));
+    ix->allocs.push_back(d);
+    ix->device_bytes += bytes;
+    if (!v.empty()) GT_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)d;
+    return GTGPU_OK;
+}
+
+}  // namespace
+
+int32_t index_free_impl(gtgpu_index* ix);
+
+int32_t host_index_upload(gtgpu_ctx* ctx, const HostIndex& H, gtgpu_index** out_index) {
+    GT_CUDA(cudaSetDevice(ctx->device));
     gtgpu_index* ix = new gtgpu_index();
     ix->ctx = ctx;
-    ix->kind = kind;
-    ix->n_intervals = total;
-    ix->n_segments = segs.size();
-    ix->max_components = max_components;
+    ix->kind = H.kind;
+    ix->n_intervals = H.total;
+    ix->n_segments = H.n_segments;
+    ix->max_components = H.max_components;
     IndexView& v = ix->view;
     int32_t st = GTGPU_OK;
     auto up = [&](auto& vec, auto** dst) { if (st == GTGPU_OK) st = upload(ix, vec, dst); };
-    up(chrom_bt, &v.chrom_bt);
-    up(bt_lut, &v.bt_lut);
-    up(bt_rec, &v.bt_rec);
-    up(bt_pool, &v.bt_pool);
-    ix->bt_pool_windows = bt_pool_windows;
-    up(bt_ent, &v.bt_ent);
-    v.bt_shift = bt_shift;
-    ix->bt_bins = bt_lut.size();
-    ix->bt_overflow_bins = bt_overflow;
-    ix->bt_clean = bt_overflow == 0 && bt_pool_windows == 0 && total > 0;
-    for (uint32_t c = 0; c < n_chroms; ++c)
-        if (chrom_bt[c].n_bins & BT_GENERIC_CHROM) ix->bt_clean = false;
+    up(H.chrom_bt, &v.chrom_bt);
+    up(H.bt_lut, &v.bt_lut);
+    up(H.bt_rec, &v.bt_rec);
+    up(H.bt_pool, &v.bt_pool);
+    ix->bt_pool_windows = H.bt_pool_windows;
+    up(H.bt_ent, &v.bt_ent);
+    v.bt_shift = H.bt_shift;
+    ix->bt_bins = H.bt_lut.size();
+    ix->bt_overflow_bins = H.bt_overflow;
+    ix->bt_clean = H.bt_overflow == 0 && H.bt_pool_windows == 0 && H.total > 0;
+    for (uint32_t c = 0; c < H.n_chroms; ++c)
+        if (H.chrom_bt[c].n_bins & BT_GENERIC_CHROM) ix->bt_clean = false;
     if (ix->bt_clean && cudaHostAlloc((void**)&ix->h_lean_probe, 4, cudaHostAllocDefault) == cudaSuccess) *ix->h_lean_probe = 0;
     else { ix->h_lean_probe = nullptr; cudaGetLastError(); }
-    up(chroms, &v.chroms);
-    up(seg_meta, &v.segs);
-    up(h_starts, &v.starts);
-    up(h_ends, &v.ends);
-    up(h_pmax, &v.pmax);
-    up(h_vals, &v.vals);
-    for (uint32_t x : h_vals) ix->max_val = std::max(ix->max_val, x);
-    up(h_cs, &v.cs_starts);
-    up(h_ce, &v.cs_ends);
-    up(lut, &v.lut);
-    up(rank_lut, &v.rank_lut);
-    v.rank_shift = rank_shift;
-    ix->rank_lut_len = rank_lut.size();
-    v.rank_inline = rank_inline;
+    up(H.chroms, &v.chroms);
+    up(H.seg_meta, &v.segs);
+    up(H.h_starts, &v.starts);
+    up(H.h_ends, &v.ends);
+    up(H.h_pmax, &v.pmax);
+    up(H.h_vals, &v.vals);
+    ix->max_val = H.max_val;
+    up(H.h_cs, &v.cs_starts);
+    up(H.h_ce, &v.cs_ends);
+    up(H.lut, &v.lut);
+    up(H.rank_lut, &v.rank_lut);
+    v.rank_shift = H.rank_shift;
+    ix->rank_lut_len = H.rank_lut.size();
+    v.rank_inline = H.rank_inline;
     if (st != GTGPU_OK) {
-        gtgpu_index_free(ix);
+        index_free_impl(ix);
         return st;
     }
-    v.n_chroms = n_chroms;
-    v.shift = shift;
-    v.descending = kind == GTGPU_KIND_AILIST;
-    v.proper = proper;
+    v.n_chroms = H.n_chroms;
+    v.shift = H.shift;
+    v.descending = H.kind == GTGPU_KIND_AILIST;
+    v.proper = H.proper;
     *out_index = ix;
     return GTGPU_OK;
 }
 
-extern "C" int32_t gtgpu_index_free(gtgpu_index* ix) {
+int32_t index_free_impl(gtgpu_index* ix) {
     if (!ix) return GTGPU_OK;
     cudaSetDevice(ix->ctx->device);
     for (void* p : ix->allocs) cudaFree(p);
@@ -432,6 +640,23 @@ extern "C" int32_t gtgpu_index_free(gtgpu_index* ix) {
     delete ix;
     return GTGPU_OK;
 }
+
+}  // namespace gtgpu
+
+using namespace gtgpu;
+
+extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_chroms, const uint64_t* chrom_offsets,
+                                     const uint32_t* starts, const uint32_t* ends, const uint32_t* vals,
+                                     gtgpu_index** out_index) {
+    if (!ctx || !out_index) return fail(GTGPU_ERR_INVALID, "index_build: null argument");
+    HostIndex* H = nullptr;
+    GT_TRY(host_index_build(ctx, kind, n_chroms, chrom_offsets, starts, ends, vals, &H));
+    const int32_t s = host_index_upload(ctx, *H, out_index);
+    host_index_free(H);
+    return s;
+}
+
+extern "C" int32_t gtgpu_index_free(gtgpu_index* ix) { return index_free_impl(ix); }
 
 extern "C" int32_t gtgpu_index_info(const gtgpu_index* ix, uint64_t info[12]) {
     if (!ix || !info) return fail(GTGPU_ERR_INVALID, "index_info: null argument");

@@ -109,6 +109,104 @@ int32_t exclusive_scan(gtgpu_ctx* ctx, const T* d_in, T* d_out, uint64_t n, void
 template int32_t exclusive_scan<uint32_t>(gtgpu_ctx*, const uint32_t*, uint32_t*, uint64_t, void*);
 template int32_t exclusive_scan<unsigned long long>(gtgpu_ctx*, const unsigned long long*, unsigned long long*, uint64_t, void*);
 
+// ---- inclusive running maximum (64-bit) ---------------------------------------------------------------------------------
+// Same three-kernel shape as exclusive_scan with max as the operator.  The index builders use it for segmented running
+// maxima: with the segment number in the high word and the value in the low word, a later segment always wins, so the
+// low word of the scan is the running maximum inside the element's own segment.
+__device__ __forceinline__ unsigned long long block_inclusive_max(unsigned long long v, unsigned long long* s_warp,
+                                                                  unsigned long long& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl = max(incl, t);
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        const unsigned long long t = s_warp[w];
+        if (w < warp) before = max(before, t);
+        tot = max(tot, t);
+    }
+    __syncthreads();
+    total = tot;
+    return max(before, incl);
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) max_reduce_kernel(const unsigned long long* __restrict__ in,
+                                                                  unsigned long long* __restrict__ tile_max, uint64_t n) {
+    __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+    unsigned long long m = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const uint64_t i = base + (uint64_t)k * SCAN_THREADS + threadIdx.x;
+        if (i < n) m = max(m, in[i]);
+    }
+    unsigned long long total;
+    block_inclusive_max(m, s_warp, total);
+    if (threadIdx.x == 0) tile_max[blockIdx.x] = total;
+}
+
+// tile_max[t] becomes the maximum over all tiles BEFORE t (0 for the first)
+__global__ void __launch_bounds__(SCAN_THREADS) max_spine_kernel(unsigned long long* __restrict__ tile_max, uint64_t n_tiles) {
+    __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
+    __shared__ unsigned long long s_prev[SCAN_THREADS];
+    unsigned long long carry = 0;
+    for (uint64_t base = 0; base < n_tiles; base += SCAN_THREADS) {
+        const uint64_t i = base + threadIdx.x;
+        const unsigned long long v = i < n_tiles ? tile_max[i] : 0;
+        unsigned long long total;
+        const unsigned long long incl = block_inclusive_max(v, s_warp, total);
+        s_prev[threadIdx.x] = incl;
+        __syncthreads();
+        const unsigned long long excl = threadIdx.x ? s_prev[threadIdx.x - 1] : 0;
+        if (i < n_tiles) tile_max[i] = max(carry, excl);
+        carry = max(carry, total);
+        __syncthreads();
+    }
+}
+
+// in and out may be the same array (every thread reads its own eight elements before it writes them): no __restrict__
+__global__ void __launch_bounds__(SCAN_THREADS) max_down_kernel(const unsigned long long* in, unsigned long long* out,
+                                                                const unsigned long long* __restrict__ tile_before, uint64_t n) {
+    __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
+    __shared__ unsigned long long s_prev[SCAN_THREADS];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    unsigned long long v[SCAN_ITEMS], m = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        m = max(m, v[k]);
+    }
+    unsigned long long total;
+    s_prev[threadIdx.x] = block_inclusive_max(m, s_warp, total);
+    __syncthreads();
+    unsigned long long run = max(tile_before[blockIdx.x], threadIdx.x ? s_prev[threadIdx.x - 1] : 0ull);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        run = max(run, v[k]);
+        if (base + k < n) out[base + k] = run;
+    }
+}
+
+// out[i] = max(in[0..i]); in and out may alias; d_temp needs exclusive_scan_temp_bytes(n, 8).
+int32_t inclusive_max_scan_u64(gtgpu_ctx* ctx, const unsigned long long* d_in, unsigned long long* d_out, uint64_t n, void* d_temp) {
+    if (n == 0) return GTGPU_OK;
+    const uint64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (tiles > 0x7FFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "inclusive_max_scan: input too large");
+    unsigned long long* tm = reinterpret_cast<unsigned long long*>(d_temp);
+    max_reduce_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(d_in, tm, n);
+    max_spine_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(tm, tiles);
+    max_down_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(d_in, d_out, tm, n);
+    ctx->launches += 3;
+    GT_CUDA(cudaGetLastError());
+    return GTGPU_OK;
+}
+
 // ---- radix sort -----------------------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 constexpr int RS_ROUNDS = 16;                          // elements per lane

@@ -181,6 +181,38 @@ def test_random_differential(ctx, kind, style):
 
 
 @pytest.mark.parametrize("kind", ["bits", "ailist"])
+@pytest.mark.parametrize("style", ["overlap", "nested", "dups", "degenerate"])
+def test_device_sorted_build_matches_host_sorted_build(ctx, kind, style, monkeypatch):
+    """gtgpu_index_build orders large inputs with stable radix passes on the device (build.cu) and small ones with the
+    host's stable sort: both must give the reference's order — ties on (start, end) / start keep insertion order, which
+    the duplicate-heavy styles exercise through the hits' vals — and the same search tables."""
+    rng = np.random.default_rng(zlib.crc32(f"devbuild/{kind}/{style}".encode()))
+    n_chroms = 7
+    offs, s, e, v = _random_index(rng, n_chroms, 9000, style)
+    from gtars_b200 import ffi
+    monkeypatch.setenv("GTGPU_BUILD_SORT", "device")
+    g_dev, o = _both(ctx, kind, offs, s, e, v)
+    monkeypatch.setenv("GTGPU_BUILD_SORT", "host")
+    g_host = ffi.Index(ctx, KINDS[kind], offs, s, e, v)
+    i_dev, i_host = g_dev.info(), g_host.info()
+    assert i_dev == i_host
+    qc, qs, qe = _random_queries(rng, n_chroms, 6000, style == "degenerate")
+    for m in (0, 2):
+        _assert_same_find(g_dev, o, qc, qs, qe, m)
+        a, b = g_dev.find(qc, qs, qe, m), g_host.find(qc, qs, qe, m)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    if kind == "bits":
+        assert np.array_equal(g_dev.bits_count(qc, qs, qe), o.bits_count(qc, qs, qe))
+    # chromosomes without intervals and an empty index go through the device path too
+    offs2 = np.array([0, 0, 3, 3], dtype=np.uint64)
+    s2, e2 = np.array([50, 10, 10], np.uint32), np.array([60, 30, 20], np.uint32)
+    monkeypatch.setenv("GTGPU_BUILD_SORT", "device")
+    g2, o2 = _both(ctx, kind, offs2, s2, e2)
+    q = (np.array([0, 1, 2, 1], np.uint32), np.array([0, 0, 0, 15], np.uint32), np.array([100, 100, 100, 55], np.uint32))
+    _assert_same_find(g2, o2, *q)
+
+
+@pytest.mark.parametrize("kind", ["bits", "ailist"])
 @pytest.mark.parametrize("style", ["peaks", "overlap", "nested", "dups"])
 def test_partitioned_count_matches_direct_and_oracle(ctx, kind, style, monkeypatch):
     """The bucketed counting pass (queries grouped by rank-LUT slice, used for databases beyond the L2) returns what the
