@@ -2,22 +2,32 @@
 """bench.py — headline benchmark: tokenize synthetic hg38-shaped BED files against a 1 M-region universe.
 
 A "step" is one pass of the hot path (Tokenizer::encode for every file, gtars-tokenizers/src/tokenizer.rs:140-171)
-over BASELINE.json configs[1]: 10 000 files x 100 000 regions = 1e9 query intervals vs a 1 M-region universe, per GPU.
+over BASELINE.json configs[1] (C2): 10 000 files x 100 000 regions = 1e9 query intervals vs a 1 M-region universe.
 
   value     query intervals / s, device-resident inputs, CUDA events around K back-to-back steps (max over ranks)
-  e2e       the same metric through the C-ABI host entry point gtgpu_tokenize_files with PINNED HOST buffers,
-            H2D of the queries and D2H of the ids inside the timed region
+  e2e       the same metric through the C-ABI host entry point gtgpu_tokenize_files_compact with PINNED HOST buffers,
+            H2D of the queries and D2H of the ids inside the timed region; `marshal` = the host-side packing of the
+            caller's flat (chr, start, end) arrays into that wire format (gtgpu_marshal_compact), timed separately;
+            `pcie` = what concurrent pinned H2D + D2H copies reach on this box (the ceiling of any e2e number)
   roofline  algorithmic HBM bytes of the fused kernel / its own CUDA-event time, vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the CPU oracle (C++ restatement of the reference's algorithm; the reference is Rust and cannot be
             built here) on a bounded sample of the same files, 1 thread (the reference path is single-threaded)
+  parity    every id and per-file offset of >= 10 % of the files compared with the multithreaded oracle (untimed)
+  configs   sub-records for BASELINE.json configs[2..4], each sharded over the N ranks as the config says, with its own
+            timing, algorithmic bytes, roofline fraction and a parity check of the full-size result against the oracle:
+              c3  Bits count, 100 M queries vs a 50 M-interval database, query-sharded (strong scaling)
+              c4  LOLA region-hit matrix, 1 k user sets x 10 k database sets, database sharded by set + ncclAllGather
+              c5  fragment tokenization, 1 B unsorted fragments vs the 1 M-peak universe, fragment-sharded
 
-`--impl reference` times the oracle with all host threads instead (rank 0 only).  Multi-GPU (torchrun): files are
-sharded across ranks (rank r owns files [r*F, (r+1)*F)), universe replicated, no collective on the data path (weak scaling).
+`--scaling weak` (default): every rank owns `--files` files (1e9 queries per GPU); `--scaling strong`: `--files` files in
+total.  `--impl reference` times the oracle with all host threads instead (rank 0 only).  Multi-GPU (torchrun): files
+are sharded across ranks (rank r owns files [r*F, (r+1)*F)), universe replicated, no collective on the C2 data path.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import statistics
@@ -25,6 +35,7 @@ import subprocess
 import sys
 import tempfile
 import time
+import traceback
 
 import numpy as np
 
@@ -41,24 +52,31 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--files", type=int, default=10_000, help="files per GPU")
+    ap.add_argument("--files", type=int, default=10_000, help="files per GPU (weak scaling) or in total (strong scaling)")
     ap.add_argument("--per-file", type=int, default=100_000)
     ap.add_argument("--universe", type=int, default=1_000_000)
     ap.add_argument("--kind", default="bits", choices=["bits", "ailist"])
     ap.add_argument("--nested", type=float, default=0.0, help="fraction of wide intervals (C2n variant)")
     ap.add_argument("--width-scale", type=int, default=1, help="multiply the 200-600 bp query widths (wide-query variant)")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-api", default="compact", choices=["compact", "runs"], help="host entry point of the e2e leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--configs", default="c3,c4,c5", help="sub-records to add (comma separated; empty = none)")
+    ap.add_argument("--sub-scale", type=float, default=1.0, help="scale factor on the sizes of the c3/c4/c5 sub-records")
+    ap.add_argument("--parity-files", type=int, default=1000, help="files of the full-size C2 result checked against the oracle")
+    ap.add_argument("--no-pcie-probe", action="store_true")
     return ap.parse_args()
 
 
 def workload_config(args, world):
+    per_gpu = args.files if args.scaling == "weak" else args.files // world
     return {
-        "workload": f"C2: tokenize {args.files} files x {args.per_file} regions per GPU vs {args.universe}-region hg38 universe",
-        "files_per_gpu": args.files, "regions_per_file": args.per_file, "universe_regions": args.universe,
-        "backend": args.kind, "nested_frac": args.nested, "query_width_scale": args.width_scale, "sharding": f"files x{world} (universe replicated)",
+        "workload": f"C2: tokenize {per_gpu} files x {args.per_file} regions per GPU vs {args.universe}-region hg38 universe",
+        "files_per_gpu": per_gpu, "regions_per_file": args.per_file, "universe_regions": args.universe,
+        "backend": args.kind, "nested_frac": args.nested, "query_width_scale": args.width_scale,
+        "sharding": f"files x{world} (universe replicated)", "scaling": args.scaling,
         "l2_policy": "inputs (12 B/query x 1e9) are far larger than the 126 MB L2; no flush needed",
     }
 
@@ -71,8 +89,16 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def host_threads() -> int:
+    """CPUs this process may run on — NOT OMP_NUM_THREADS, which torch.distributed.run pins to 1 for its workers."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -119,24 +145,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_rate(args, threads, seconds, universe=None):
+def oracle_index(args, universe):
+    from oracle import oracle as orc
+    offs = universe["chrom_offsets"].cpu().numpy().astype(np.uint64)
+    s, e, v = (universe[k].cpu().numpy().view(np.uint32) for k in ("g_start", "g_end", "g_val"))
+    return orc.Index(orc.BITS if args.kind == "bits" else orc.AILIST, offs, s, e, v)
+
+
+def cpu_oracle_rate(args, threads, seconds, universe):
     """Oracle tokenize throughput on files [0, k) of the same synthetic stream; k grows until `seconds` are spent."""
     from gtars_b200 import synth
-    from oracle import oracle as orc
-    u = universe or synth.make_universe(args.universe, nested_frac=args.nested)
-    kind = orc.BITS if args.kind == "bits" else orc.AILIST
-    offs = u["chrom_offsets"].cpu().numpy().astype(np.uint64)
-    s, e, v = (u[k].cpu().numpy().view(np.uint32) for k in ("g_start", "g_end", "g_val"))
-    ix = orc.Index(kind, offs, s, e, v)
+    ix = oracle_index(args, universe)
     batch = max(1, min(args.files, (4 if threads == 1 else 4 * threads)))
     done_q, spent, first = 0, 0.0, 0
     while spent < seconds and first < args.files:
         nf = min(batch, args.files - first)
-        q = synth.make_query_files(u, nf, args.per_file, first_file=first, width_scale=args.width_scale)
+        q = synth.make_query_files(universe, nf, args.per_file, first_file=first, width_scale=args.width_scale)
         qc, qs, qe = (q[k].numpy().view(np.uint32) for k in ("chr", "start", "end"))
         fo = q["file_offsets"].numpy().astype(np.uint64)
         t0 = time.perf_counter()
-        ix.tokenize_files(fo, qc, qs, qe, u["unk_id"], threads=threads)
+        ix.tokenize_files(fo, qc, qs, qe, universe["unk_id"], threads=threads)
         spent += time.perf_counter() - t0
         done_q += len(qc)
         first += nf
@@ -145,18 +173,14 @@ def cpu_oracle_rate(args, threads, seconds, universe=None):
 
 def run_reference(args, rank, world):
     """The reference arm: the CPU oracle (a C++ port; the Rust reference cannot be compiled in this image) with every
-    host thread, on a bounded sample of the same workload per step."""
+    host thread, on the same bounded sample of the workload per step at every N (rank 0 alone runs it)."""
     if rank != 0:
         return
     from gtars_b200 import synth
-    from oracle import oracle as orc
-    threads = orc.max_threads()
+    threads = host_threads()
     u = synth.make_universe(args.universe, nested_frac=args.nested)
-    kind = orc.BITS if args.kind == "bits" else orc.AILIST
-    offs = u["chrom_offsets"].numpy().astype(np.uint64)
-    s, e, v = (u[k].numpy().view(np.uint32) for k in ("g_start", "g_end", "g_val"))
-    ix = orc.Index(kind, offs, s, e, v)
-    sample_files = min(args.files, 8 * threads)
+    ix = oracle_index(args, u)
+    sample_files = min(args.files, 128)
     q = synth.make_query_files(u, sample_files, args.per_file, width_scale=args.width_scale)
     qc, qs, qe = (q[k].numpy().view(np.uint32) for k in ("chr", "start", "end"))
     fo = q["file_offsets"].numpy().astype(np.uint64)
@@ -167,42 +191,385 @@ def run_reference(args, rank, world):
         ix.tokenize_files(fo, qc, qs, qe, u["unk_id"], threads=threads)
     dt = (time.perf_counter() - t0) / args.steps
     value = len(qc) / dt
-    sample = f"{sample_files} files x {args.per_file} regions per step (bounded sample of the {args.files}-file workload)"
+    sample = f"{sample_files} files x {args.per_file} regions per step (bounded sample of the workload; the same at every N)"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(args, world),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "note": "C++ restatement of gtars' algorithm on all host threads (OpenMP over files); the Rust "
+                                 "reference is single-threaded on this path and cannot be built in this image"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-def bind_to_gpu_numa_node(torch, local_rank):
-    """N > 1 only: pin this rank to the CPUs of its GPU's NUMA node before any pinned host buffer is allocated, so the
-    e2e leg's staging pages are local to the GPU's PCIe root (eight unbound ranks shared one socket's memory and links:
-    16 GB/s H2D per GPU measured at N = 8).  Best effort: any failure leaves the process unbound."""
-    try:
-        p = torch.cuda.get_device_properties(local_rank)
-        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
-        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
-            node = int(f.read().strip())
-        if node < 0:
-            return None
-        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
-            cpus = set()
-            for part in f.read().strip().split(","):
-                lo, _, hi = part.partition("-")
-                cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if not cpus:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return {"node": node, "cpus": len(cpus)}
-    except Exception:
-        return None
+def digest64(*arrays) -> str:
+    h = hashlib.blake2b(digest_size=8)
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
 
 
+class Dist:
+    """torch.distributed plumbing: NCCL for the device-side reductions of timings, gloo for host-side waits."""
+
+    def __init__(self, torch, world, dev):
+        self.torch, self.world, self.dev = torch, world, dev
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+            dist.init_process_group("nccl", device_id=dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def _reduce(self, x, op):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MAX) if self.world > 1 else x
+
+    def sum(self, x):
+        return self._reduce(x, self.dist.ReduceOp.SUM) if self.world > 1 else x
+
+    def gather_objects(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def pcie_probe(torch, dev, D):
+    """Concurrent pinned H2D + D2H copies on every rank at once: the ceiling of anything that crosses PCIe."""
+    nbytes, reps = 1 << 30, 4
+    h_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_out = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def run(do_in, do_out):
+        torch.cuda.synchronize()
+        D.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if do_in:
+                with torch.cuda.stream(s_in):
+                    d_in.copy_(h_in, non_blocking=True)
+            if do_out:
+                with torch.cuda.stream(s_out):
+                    h_out.copy_(d_out, non_blocking=True)
+        s_in.synchronize()
+        s_out.synchronize()
+        dt = D.max(time.perf_counter() - t0)
+        return nbytes * reps / dt / 1e9
+
+    run(True, True)
+    h2d, d2h, both = run(True, False), run(False, True), run(True, True)
+    out = {"h2d_alone_gbs_per_gpu": h2d, "d2h_alone_gbs_per_gpu": d2h, "duplex_each_direction_gbs_per_gpu": both,
+           "aggregate_duplex_gbs": 2 * both * D.world, "gpus_copying_at_once": D.world,
+           "note": "1 GiB pinned copies, 4 back to back per direction, all ranks at the same time, slowest rank"}
+    del h_in, h_out, d_in, d_out
+    return out
+
+
+# =====================================================================================================================
+# sub-records: BASELINE.json configs[2..4]
+# =====================================================================================================================
+def sub_c3(args, torch, dev, ctx, stream, D, rank, world, peak):
+    """C3: Bits::count (bits.rs:337-344) of 100 M unsorted queries against a 50 M-interval database; the queries are
+    sharded over the ranks in contiguous blocks, the database is replicated (strong scaling)."""
+    from gtars_b200 import ffi, shard, synth
+    from oracle import oracle as orc
+    n_db, n_q_total = int(50_000_000 * args.sub_scale), int(100_000_000 * args.sub_scale)
+    q0, q1 = shard.block_range(n_q_total, world, rank)
+    n_q = q1 - q0
+    t0 = time.perf_counter()
+    db = synth.make_uniform_intervals(n_db, synth.SEED_LOLA_DB, device=dev, min_w=100, max_w=10_000)
+    g = synth.group_by_chrom(db["chr"], db["start"], db["end"])
+    offs = g["chrom_offsets"].cpu().numpy().astype(np.uint64)
+    s, e = (g[k].cpu().numpy().view(np.uint32) for k in ("g_start", "g_end"))
+    del db, g
+    t1 = time.perf_counter()
+    ix = ffi.Index(ctx, ffi.KIND_BITS, offs, s, e)
+    build_s = time.perf_counter() - t1
+    q = synth.make_uniform_intervals(n_q, synth.SEED_QUERIES, device=dev, min_w=100, max_w=2000, log_uniform=False, first=q0)
+    d_out = torch.empty(n_q, dtype=torch.int32, device=dev)
+    fn = lambda: ix.count_dev(n_q, q["chr"].data_ptr(), q["start"].data_ptr(), q["end"].data_ptr(), 0, d_out.data_ptr())
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            fn()
+        stream.synchronize()
+        D.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            fn()
+        ev1.record(stream)
+        stream.synchronize()
+        launches = (ctx.launch_count() - l0) // args.steps
+    ms = D.max(ev0.elapsed_time(ev1) / args.steps)
+    # parity: the queries of this rank's first 4 M that fall on chr1 / chr21 / chrX, against the C++ oracle built over
+    # exactly those chromosomes of the database (Bits::count depends on the query's chromosome only)
+    parity = None
+    m = min(n_q, 4_000_000)
+    chroms = [0, 20, 22]
+    qc, qs, qe = (q[k][:m].cpu().numpy().view(np.uint32) for k in ("chr", "start", "end"))
+    sel = np.isin(qc, chroms)
+    keep = np.zeros(len(offs) - 1, dtype=bool)
+    keep[chroms] = True
+    sub_counts = np.where(keep, np.diff(offs.astype(np.int64)), 0)
+    sub_offs = np.concatenate([[0], np.cumsum(sub_counts)]).astype(np.uint64)
+    idx = np.concatenate([np.arange(int(offs[c]), int(offs[c + 1])) for c in chroms])
+    o = orc.Index(orc.BITS, sub_offs, s[idx], e[idx])
+    want = o.count(qc[sel], qs[sel], qe[sel], threads=host_threads())
+    got = d_out[:m].cpu().numpy().view(np.uint32)[sel]
+    parity = bool(np.array_equal(got, want))
+    parity_all = all(D.gather_objects(parity))
+    checked = int(D.sum(float(sel.sum())))
+    algo = 16 * n_q_total + 8 * n_db  # SURVEY 8d: 12 B query + 4 B count per query, 8 B per database interval (read once)
+    info = ix.info()
+    ix.close()
+    del q, d_out
+    return {"workload": f"C3: Bits count, {n_q_total} unsorted queries vs a {n_db}-interval database", "scaling": "strong",
+            "sharding": f"queries in {world} contiguous blocks, database replicated, no collective",
+            "queries_total": n_q_total, "queries_per_gpu": n_q, "db_intervals": n_db, "ms": ms,
+            "value": n_q_total / (ms * 1e-3), "unit": "queries/s", "algorithmic_bytes": algo,
+            "frac": (16 * n_q + 8 * n_db) / (ms * 1e-3) / 1e9 / peak,
+            "frac_note": "per GPU: (16 B x its queries + 8 B x database) / time / measured HBM peak",
+            "kernels_per_step": launches, "index_build_s": build_s, "data_gen_s": t1 - t0,
+            "parity_vs_oracle": parity_all, "parity_queries_checked": checked, "index": info}
+
+
+def sub_c4(args, torch, dev, ctx, stream, D, rank, world, peak):
+    """C4: run_lola's count step (enrichment.rs:198-211): region-hit matrix of 1 k user sets + the universe against a
+    10 k-set database, the database sharded by region set over the ranks, one ncclAllGather of the column blocks."""
+    from gtars_b200 import ffi, shard, synth
+    from oracle import oracle as orc
+    n_db = max(int(10_000 * args.sub_scale), 8 * world)
+    per_db, n_user, per_user = 20_000, max(int(1000 * args.sub_scale), 4), 10_000
+    lo, hi = shard.db_set_range(n_db, world, rank)
+    t0 = time.perf_counter()
+    db = synth.make_uniform_intervals((hi - lo) * per_db, synth.SEED_LOLA_DB, device=dev, min_w=200, max_w=5000, first=lo * per_db)
+    dfo = (np.arange(hi - lo + 1) * per_db).astype(np.uint64)
+    dc, ds, de = (db[k].cpu().numpy().view(np.uint32) for k in ("chr", "start", "end"))
+    del db
+    t1 = time.perf_counter()
+    g = ffi.Igd(ctx, dfo, synth.N_CHROMS, dc, ds, de)
+    build_s = time.perf_counter() - t1
+    if world > 1:
+        shard.init_comm_from_torch(ctx)
+    u = synth.make_universe(1_000_000, device=dev)
+    pick = synth.rand_u63(synth.SEED_LOLA_USER, 1, torch.arange(n_user * per_user, device=dev)) % u["n"]
+    qc = torch.cat([u["chr"][pick], u["chr"]]).cpu().numpy().view(np.uint32)
+    qs = torch.cat([u["start"][pick], u["start"]]).cpu().numpy().view(np.uint32)
+    qe = torch.cat([u["end"][pick], u["end"]]).cpu().numpy().view(np.uint32)
+    n_univ = int(u["n"])
+    so = np.concatenate([np.arange(n_user + 1) * per_user, [n_user * per_user + n_univ]]).astype(np.uint64)
+    n_q = len(qc)
+    call = lambda: g.count_sharded(True, n_db, so, qc, qs, qe, 1)
+    call()
+    call()
+    ctx.timing_enable(True)
+    D.barrier()
+    l0 = ctx.launch_count()
+    t2 = time.perf_counter()
+    for _ in range(args.steps):
+        hits = call()
+    ms = D.max((time.perf_counter() - t2) / args.steps * 1e3)
+    launches = (ctx.launch_count() - l0) // args.steps
+    k_ms = ctx.timing_read()
+    ctx.timing_enable(False)
+    kernel_ms = D.max(statistics.mean(k_ms) if k_ms else 0.0)
+    # parity on full-size output: columns are independent (a set's counts depend on that set's records only), so the
+    # oracle builds an IGD over 2 database sets of every rank's shard and must reproduce those columns for the first
+    # 3 user sets and a slice of the universe — which also checks where the all-gather put every rank's block
+    k = 3
+    u_lo = n_user * per_user
+    sel = np.concatenate([np.arange(k * per_user), np.arange(u_lo, u_lo + 200_000)])
+    sso = np.concatenate([np.arange(k + 1) * per_user, [k * per_user + 200_000]]).astype(np.uint64)
+    got_slice = g.count_sharded(True, n_db, sso, qc[sel], qs[sel], qe[sel], 1)  # collective: every rank calls it
+    parity = None
+    if rank == 0:
+        cols = sorted({c for r in range(world) for c in (shard.db_set_range(n_db, world, r)[0], shard.db_set_range(n_db, world, r)[1] - 1)})
+        parts = [synth.make_uniform_intervals(per_db, synth.SEED_LOLA_DB, min_w=200, max_w=5000, first=c * per_db) for c in cols]
+        oc = np.concatenate([p["chr"].numpy().view(np.uint32) for p in parts])
+        os_ = np.concatenate([p["start"].numpy().view(np.uint32) for p in parts])
+        oe = np.concatenate([p["end"].numpy().view(np.uint32) for p in parts])
+        o = orc.Igd((np.arange(len(cols) + 1) * per_db).astype(np.uint64), oc, os_, oe)
+        want = o.count_region_hits(sso, qc[sel], qs[sel], qe[sel], 1, threads=host_threads())
+        parity = bool(np.array_equal(hits[:k][:, cols], want[:k]) and np.array_equal(got_slice[:, cols], want))
+        tables = orc.lola_tables(hits[:n_user], hits[n_user], np.full(n_user, per_user), n_univ)
+        parity = parity and tables.shape == (n_user, n_db, 4)
+    pair_hits = int(hits.sum())
+    algo = 12 * n_q + 12 * n_db * per_db + 8 * (n_user + 1) * n_db
+    info = g.info()
+    g.close()
+    return {"workload": f"C4: LOLA region-hit matrix, {n_user} user sets x {per_user} regions + {n_univ}-region universe vs {n_db} database sets x {per_db}",
+            "scaling": "strong", "sharding": f"database sharded by region set over {world} ranks, query sets replicated, "
+                                             + ("one ncclAllGather of the column blocks" if world > 1 else "single rank: no collective"),
+            "db_sets": n_db, "db_sets_per_gpu": hi - lo, "db_records": n_db * per_db, "query_regions": n_q,
+            "ms": ms, "ms_note": "whole gtgpu_igd_count_sharded call: H2D of the query sets, count kernel, all-gather, transposition, D2H of the matrix",
+            "kernel_ms": kernel_ms, "value": n_q / (ms * 1e-3), "unit": "query regions/s",
+            "region_file_hits": pair_hits, "hits_per_s": pair_hits / (ms * 1e-3), "algorithmic_bytes": algo,
+            "frac": (12 * n_q + 12 * (hi - lo) * per_db + 8 * (n_user + 1) * n_db) / max(kernel_ms, 1e-9) / 1e6 / peak,
+            "frac_note": "count kernel only; atomic / L2-bound by construction, the HBM fraction is low on purpose (SURVEY 8d)",
+            "kernels_per_step": launches, "index_build_s": build_s, "data_gen_s": t1 - t0,
+            "parity_vs_oracle": parity, "parity_what": "2 database sets of every rank's shard x (3 user sets + 200 k universe regions), all cells",
+            "igd_rank0": info}
+
+
+def sub_c5(args, torch, dev, ctx, stream, D, rank, world, peak, universe, index):
+    """C5: tokenize_fragment_file (fragments.rs:12-82) for 1 B unsorted fragments vs the 1 M-peak universe: fragments are
+    sharded over the ranks in contiguous blocks; every rank groups its block by barcode on the device (hand-written radix
+    sort) — per-barcode lists of the shards concatenate in shard order."""
+    from gtars_b200 import ffi, shard, synth
+    n_total = int(1_000_000_000 * args.sub_scale)
+    n_bc = 100_000
+    f0, f1 = shard.block_range(n_total, world, rank)
+    n = f1 - f0
+    t0 = time.perf_counter()
+    d_chr = torch.empty(n, dtype=torch.int32, device=dev)
+    d_start = torch.empty(n, dtype=torch.int32, device=dev)
+    d_end = torch.empty(n, dtype=torch.int32, device=dev)
+    d_bc = torch.empty(n, dtype=torch.int32, device=dev)
+    chunk = 1 << 24
+    for a in range(0, n, chunk):
+        k = min(chunk, n - a)
+        # "file" index = position / chunk is only the counter base of the generator: fragments [f0 + a, f0 + a + k)
+        q = _fragments(synth, universe, f0 + a, k, dev)
+        d_chr[a:a + k], d_start[a:a + k], d_end[a:a + k], d_bc[a:a + k] = q
+        del q
+    cap = n + n // 4 + 1024
+    d_ids = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_bco = torch.empty(n_bc + 1, dtype=torch.int64, device=dev)
+    d_total = torch.zeros(1, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    unk = int(universe["unk_id"])
+    fn = lambda: index.tokenize_fragments_dev(n, d_chr.data_ptr(), d_start.data_ptr(), d_end.data_ptr(), d_bc.data_ptr(), n_bc,
+                                              unk, d_bco.data_ptr(), d_ids.data_ptr(), cap, d_total.data_ptr())
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            fn()
+        stream.synchronize()
+        total = int(d_total.item())
+        assert 0 < total <= cap, "C5: id capacity"
+        D.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            fn()
+        ev1.record(stream)
+        stream.synchronize()
+        launches = (ctx.launch_count() - l0) // args.steps
+    ms = D.max(ev0.elapsed_time(ev1) / args.steps)
+    tokens_total = int(D.sum(float(total)))
+    # parity on the full-size result: ~200 barcodes' complete lists.  Their fragments are pulled out of this rank's block
+    # in input order, the oracle tokenizes them one by one, and each barcode's list must equal the device's list.
+    from oracle import oracle as orc
+    pick = torch.unique(synth.rand_u63(synth.SEED_FRAGMENTS, 11, torch.arange(200, device=dev)) % n_bc)
+
+    def select(barcodes):
+        lut = torch.zeros(n_bc, dtype=torch.bool, device=dev)
+        lut[barcodes] = True
+        parts = []
+        for a in range(0, n, 1 << 26):
+            b = min(n, a + (1 << 26))
+            parts.append(torch.nonzero(lut[d_bc[a:b].long()]).flatten() + a)
+        return torch.cat(parts)
+
+    sel = select(pick)
+    if sel.numel() > 3_000_000:
+        pick = pick[: max(1, pick.numel() * 3_000_000 // sel.numel())]
+        sel = select(pick)
+    dense = torch.searchsorted(pick, d_bc[sel].long())
+    sc, ss, se = (t[sel].cpu().numpy().view(np.uint32) for t in (d_chr, d_start, d_end))
+    o_off, o_ids = oracle_index(args, universe).tokenize_fragments(sc, ss, se, dense.cpu().numpy().astype(np.uint32), int(pick.numel()), unk)
+    bco = d_bco.cpu().numpy()
+    ok = True
+    got_parts = []
+    for j, b in enumerate(pick.cpu().numpy()):
+        got = d_ids[int(bco[b]):int(bco[b + 1])].cpu().numpy().view(np.uint32)
+        got_parts.append(got)
+        ok = ok and np.array_equal(got, o_ids[int(o_off[j]):int(o_off[j + 1])])
+    ok = ok and int(bco[n_bc]) == total and bool((np.diff(bco) >= 0).all())
+    parity_all = all(D.gather_objects(bool(ok)))
+    checked = int(D.sum(float(sel.numel())))
+    # e2e through the host entry point (pinned host arrays in, pinned result out) on a bounded slice of this rank's block
+    m = min(n, 125_000_000)
+    h = [ffi.pinned_empty(m, np.uint32) for _ in range(4)]
+    for dst, src in zip(h, (d_chr, d_start, d_end, d_bc)):
+        torch.from_numpy(dst.view(np.int32)).copy_(src[:m])
+    torch.cuda.synchronize()
+    L = ffi.lib()
+    _, buf = index.tokenize_fragments(h[0], h[1], h[2], h[3], n_bc, unk, keep_buf=True)
+    L.gtgpu_buf_free(buf)
+    D.barrier()
+    t2 = time.perf_counter()
+    e_off, buf = index.tokenize_fragments(h[0], h[1], h[2], h[3], n_bc, unk, keep_buf=True)
+    e2e_s = D.max(time.perf_counter() - t2)
+    e2e_tokens = int(L.gtgpu_buf_len(buf))
+    assert e2e_tokens == int(e_off[-1])
+    L.gtgpu_buf_free(buf)
+    for a in h:
+        ffi.pinned_free(a)
+    algo = 16 * n + 4 * total + 8 * (n_bc + 1) + 12 * int(universe["n"])
+    del d_chr, d_start, d_end, d_bc, d_ids
+    return {"workload": f"C5: fragment tokenization, {n_total} unsorted fragments vs the {int(universe['n'])}-peak universe, {n_bc} barcodes",
+            "scaling": "strong", "sharding": f"fragments in {world} contiguous blocks, universe replicated, per-barcode lists concatenate in shard order, no collective",
+            "fragments_total": n_total, "fragments_per_gpu": n, "tokens_total": tokens_total, "ms": ms,
+            "value": n_total / (ms * 1e-3), "unit": "fragments/s", "algorithmic_bytes_per_gpu": algo,
+            "frac": algo / (ms * 1e-3) / 1e9 / peak,
+            "frac_note": "per GPU: (16 B x fragments + 4 B x tokens + barcode offsets + universe) / time of the whole device-resident "
+                         "pipeline (find + 3 radix passes + scan + scatter) / measured HBM peak",
+            "kernels_per_step": launches, "data_gen_s": gen_s,
+            "e2e": {"fragments_per_gpu": m, "seconds": e2e_s, "value": m * world / e2e_s, "unit": "fragments/s",
+                    "note": "gtgpu_tokenize_fragments, pinned host arrays in (16 B/fragment), pinned result out; bounded slice of the block",
+                    "tokens": e2e_tokens},
+            "parity_vs_oracle": parity_all, "parity_fragments_checked": checked, "parity_barcodes": int(pick.numel()),
+            "parity_digest": digest64(*got_parts)}
+
+
+def _fragments(synth, universe, first, k, dev):
+    """Fragments [first, first + k) of the C5 stream: nucleosomal width mixture (modes ~50 / 200 / 400 bp), 60 % inside
+    peaks, Zipf-ish barcode sizes; unsorted."""
+    import torch
+    idx = torch.arange(first, first + k, dtype=torch.int64, device=dev)
+    seed = synth.SEED_FRAGMENTS
+    mode = synth.rand_u63(seed, 1, idx) % 10
+    base = torch.where(mode < 4, 50, torch.where(mode < 8, 200, 400))
+    width = base + synth.rand_u63(seed, 2, idx) % 60 - 20
+    u_chr, u_start, u_end = (universe[x].to(dev).long() for x in ("chr", "start", "end"))
+    p = synth.rand_u63(seed, 3, idx) % universe["n"]
+    inside = synth.rand_u63(seed, 4, idx) % 10 < 6
+    pk_start = torch.clamp(u_start[p] + synth.rand_u63(seed, 5, idx) % torch.clamp(u_end[p] - u_start[p], min=1) - width // 2, min=0)
+    bg_chr, bg_start = synth._genome_pos(synth.rand_u63(seed, 6, idx), dev)
+    chr_ = torch.where(inside, u_chr[p], bg_chr)
+    start = torch.where(inside, pk_start, bg_start)
+    csz = torch.tensor(synth.CHROM_SIZES, dtype=torch.int64, device=dev)[chr_]
+    start = torch.minimum(start, csz - 1)
+    end = torch.minimum(start + width, csz)
+    bc = synth.rand_u63(seed, 9, idx) % 100_000
+    bc = (bc * bc) // 100_000  # skewed barcode sizes
+    return chr_.int(), start.int(), end.int(), bc.int()
+
+
+# =====================================================================================================================
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -213,46 +580,29 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
     from gtars_b200 import ffi, synth
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
+    D = Dist(torch, world, dev)
     stream = torch.cuda.Stream(device=dev)
     ctx = ffi.Context(local_rank, stream=stream.cuda_stream)
     kind = ffi.KIND_BITS if args.kind == "bits" else ffi.KIND_AILIST
+    peak, peak_src = peaks()
+    t_start = time.perf_counter()
 
     # ---- universe + index (replicated on every rank) ---------------------------------------------------------------
     u = synth.make_universe(args.universe, nested_frac=args.nested, device=dev)
     offs = u["chrom_offsets"].cpu().numpy().astype(np.uint64)
     s, e, v = (u[k].cpu().numpy().view(np.uint32) for k in ("g_start", "g_end", "g_val"))
+    t_b = time.perf_counter()
     index = ffi.Index(ctx, kind, offs, s, e, v)
+    index_build_s = time.perf_counter() - t_b
     info = index.info()
 
     # ---- this rank's files, generated on the device (untimed) -------------------------------------------------------
-    n_files, per_file = args.files, args.per_file
+    n_files = args.files if args.scaling == "weak" else args.files // world
+    per_file = args.per_file
     n = n_files * per_file
     first_file = rank * n_files
     d_chr = torch.empty(n, dtype=torch.int32, device=dev)
@@ -295,7 +645,7 @@ def main():
         launches0 = ctx.launch_count()
         ctx.timing_enable(True)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
+        D.barrier()
         torch.cuda.synchronize()
         sampler.start()
         ev0.record(stream)
@@ -304,7 +654,7 @@ def main():
         ev1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
-        barrier()
+        D.barrier()
         kernel_ms = ctx.timing_read()
         ctx.timing_enable(False)
         launches = ctx.launch_count() - launches0
@@ -317,10 +667,9 @@ def main():
             stream.synchronize()
         clocks = sampler.stop()
         clocks["window"] = "timed region + 0.5 s of the identical steps right behind it"
-        ms_per_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+        ms_per_step = D.max(ev0.elapsed_time(ev1) / args.steps)
 
-
-    total_queries = sum_over_ranks(float(n))
+    total_queries = D.sum(float(n))
     value = total_queries / (ms_per_step * 1e-3)
 
     # ---- roofline of the dominant kernel (fused count→scan→emit) ---------------------------------------------------------
@@ -329,52 +678,77 @@ def main():
     # materialised, so they are not counted.
     algo_bytes = 12 * n + 4 * hits + 8 * (n_files + 1) + 12 * info["n_intervals"]
     k_ms = statistics.mean(kernel_ms) if kernel_ms else ms_per_step
-    peak, peak_src = peaks()
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None  # dram__bytes_read + dram__bytes_write of this kernel from the committed ncu --set full capture
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tr = json.load(f)
-        w = tr["workload"]
-        if (w["files_per_gpu"], w["regions_per_file"], w["universe_regions"], w["backend"], w["nested_frac"]) == (
-                args.files, args.per_file, args.universe, args.kind, args.nested):
-            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-    except Exception:
-        pass
+    traffic, traffic_src = None, None  # dram bytes read + written by this kernel, from the committed ncu --set full capture
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tr = json.load(f)
+            w = tr["workload"]
+            if (w["files_per_gpu"], w["regions_per_file"], w["universe_regions"], w["backend"], w["nested_frac"]) == (
+                    n_files, args.per_file, args.universe, args.kind, args.nested):
+                traffic, traffic_src = tr["dram_bytes_read"] + tr["dram_bytes_write"], f"profiles/{name} (ncu, same command)"
+                break
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu, same command)" if traffic else None,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "kernel": "fused_find_kernel", "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_query": algo_bytes / n,
                 "kernel_share_of_step": k_ms / (ev0.elapsed_time(ev1) / args.steps)}
 
+    # ---- full-size parity: >= 10 % of the files, every id and offset, against the multithreaded oracle (untimed) ----------
+    parity = None
+    try:
+        n_chk = min(n_files, max(args.parity_files, 1))
+        stride = max(n_files // n_chk, 1)
+        files = np.arange(0, n_files, stride)[:n_chk]
+        g_tok = d_file_tok.cpu().numpy().astype(np.int64)
+        qsel = (torch.from_numpy(files).to(dev).view(-1, 1) * per_file + torch.arange(per_file, device=dev).view(1, -1)).flatten()
+        qc, qs, qe = (t[qsel].cpu().numpy().view(np.uint32) for t in (d_chr, d_start, d_end))
+        fo_chk = (np.arange(len(files) + 1) * per_file).astype(np.uint64)
+        o_off, o_ids = oracle_index(args, u).tokenize_files(fo_chk, qc, qs, qe, u["unk_id"], threads=host_threads())
+        seg = torch.cat([torch.arange(int(g_tok[f]), int(g_tok[f + 1]), device=dev) for f in files]) if len(files) else None
+        g_ids = d_ids[seg].cpu().numpy().view(np.uint32)
+        g_len = (g_tok[files + 1] - g_tok[files])
+        # raw device offsets carry no [unk] insertions: a file without a hit has an empty run there and [unk] in the oracle
+        o_len = np.diff(o_off.astype(np.int64))
+        same_len = bool(np.array_equal(np.where(g_len == 0, 1, g_len), o_len))
+        same_ids = bool(n_empty_files > 0 or np.array_equal(g_ids, o_ids))
+        ok = same_len and same_ids
+        parity = {"files_checked": int(len(files)), "queries_checked": int(len(qc)), "ids_checked": int(len(g_ids)),
+                  "equal_to_oracle": ok, "digest_gpu": digest64(g_len, g_ids), "digest_oracle": digest64(o_len, o_ids),
+                  "oracle_threads": host_threads(), "what": f"every {stride}th file of this rank's {n_files}: all ids in order + per-file id counts"}
+        del qsel, seg
+    except Exception as ex:  # never lose the headline to the checker
+        parity = {"error": repr(ex)}
+    parity_ok = all(bool(p and p.get("equal_to_oracle")) for p in D.gather_objects(parity))
+
     # ---- e2e: the C-ABI host entry point with pinned host buffers --------------------------------------------------------
     e2e = None
+    pcie = None
     if not args.no_e2e:
-        # What a Rust caller holds after RegionSet::try_from: start / end arrays plus, because the files are sorted by
-        # chromosome, a handful of (offset, chromosome id) runs per file (gtgpu_tokenize_files_runs).
-        # Ends travel as 16-bit widths (gtgpu_tokenize_files_compact): peak-sized regions cost 6 B of PCIe each, not 8;
-        # regions wider than 65 534 bp (none in C2) go through the exception list.  --e2e-api runs = start / end arrays.
+        # What a Rust caller holds after RegionSet::try_from + a chromosome-name lookup: flat (chr id, start, end) arrays.
+        # gtgpu_marshal_compact (host, multithreaded) turns them into the wire format of gtgpu_tokenize_files_compact:
+        # chromosome runs, u32 starts, u16 widths, an exception list — 6 B of PCIe per region instead of 12.
         compact = args.e2e_api == "compact"
+        h_chr = np.empty(n, dtype=np.uint32)
         h_start = ffi.pinned_empty(n, np.uint32)
+        h_end = ffi.pinned_empty(n, np.uint32) if not compact else np.empty(n, dtype=np.uint32)
+        torch.from_numpy(h_chr.view(np.int32)).copy_(d_chr)
         torch.from_numpy(h_start.view(np.int32)).copy_(d_start)
-        if compact:
-            h_w16 = ffi.pinned_empty(n, np.uint16)
-            width = d_end.to(torch.int64) - d_start.to(torch.int64)
-            is_exc = (width < 0) | (width > 65534)
-            torch.from_numpy(h_w16.view(np.int16)).copy_(torch.where(is_exc, torch.full_like(width, 0xFFFF), width).to(torch.int16))
-            exc = torch.nonzero(is_exc).flatten()
-            h_wide_idx = exc.cpu().numpy().astype(np.uint64)
-            h_wide_end = d_end[exc].cpu().numpy().view(np.uint32)
-            del width, is_exc, exc
-        else:
-            h_end = ffi.pinned_empty(n, np.uint32)
-            torch.from_numpy(h_end.view(np.int32)).copy_(d_end)
+        torch.from_numpy(h_end.view(np.int32)).copy_(d_end)
         h_fo = d_file_offsets.cpu().numpy().astype(np.uint64)
-        brk = torch.nonzero(d_chr[1:] != d_chr[:-1]).flatten() + 1
-        run_starts = torch.unique(torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), brk, d_file_offsets[:-1]]))
-        h_run_chr = d_chr[run_starts].cpu().numpy().view(np.uint32)
-        h_run_off = torch.cat([run_starts, torch.tensor([n], device=dev)]).cpu().numpy().astype(np.uint64)
-        del brk, run_starts
+        h_w16 = ffi.pinned_empty(n, np.uint16)
+        marshal_s = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            h_run_off, h_run_chr, _, h_wide_idx, h_wide_end = ffi.marshal_compact(h_chr, h_start, h_end, h_fo, width16_out=h_w16)
+            marshal_s.append(time.perf_counter() - t0)
+        marshal_s = D.max(min(marshal_s))
+        del h_chr
+        if compact:
+            del h_end
         torch.cuda.synchronize()
         L = ffi.lib()
 
@@ -402,59 +776,85 @@ def main():
 
         for _ in range(2):
             e2e_total = e2e_step()
-        barrier()
+        D.barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_step()
         torch.cuda.synchronize()
-        barrier()
-        e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
-        e2e = {"value": total_queries / e2e_s, "unit": UNIT,
-               "h2d_bytes_per_step": (6 * n + 12 * len(h_wide_idx) if compact else 8 * n) + 8 * (n_files + 1) + 12 * len(h_run_chr) + 8,
-               "d2h_bytes_per_step": 4 * e2e_total + 8 * (n_files + 1), "ms_per_step": e2e_s * 1e3,
+        D.barrier()
+        e2e_s = D.max((time.perf_counter() - t0) / args.steps)
+        h2d = (6 * n + 12 * len(h_wide_idx) if compact else 8 * n) + 8 * (n_files + 1) + 12 * len(h_run_chr) + 8
+        d2h = 4 * e2e_total + 8 * (n_files + 1)
+        e2e = {"value": total_queries / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_s * 1e3,
                "api": ("gtgpu_tokenize_files_compact (pinned host start u32 + width u16 + chromosome runs in, pinned result buffer out)"
                        if compact else "gtgpu_tokenize_files_runs (pinned host start/end + chromosome runs in, pinned result buffer out)"),
-               "ids_match_device_resident_path": e2e_matches_device,
-               "chromosome_runs": int(len(h_run_chr))}
+               "ids_match_device_resident_path": e2e_matches_device, "chromosome_runs": int(len(h_run_chr)),
+               "marshal": {"seconds": marshal_s, "threads": host_threads(),
+                           "what": "gtgpu_marshal_compact: flat (chr id, start, end) u32 arrays -> runs + u16 widths + exceptions, host side, "
+                                   "NOT inside ms_per_step",
+                           "value_with_marshal": total_queries / (e2e_s + marshal_s), "unit": UNIT}}
         assert e2e_total == hits + n_empty_files
+        ffi.pinned_free(h_start)
+        ffi.pinned_free(h_w16)
+        if not compact:
+            ffi.pinned_free(h_end)
+        if not args.no_pcie_probe:
+            try:
+                pcie = pcie_probe(torch, dev, D)
+                t_floor = max(h2d / (pcie["duplex_each_direction_gbs_per_gpu"] * 1e9), d2h / (pcie["duplex_each_direction_gbs_per_gpu"] * 1e9))
+                e2e["pcie_floor_ms"] = t_floor * 1e3
+                e2e["frac_of_pcie_ceiling"] = t_floor / e2e_s
+            except Exception as ex:
+                pcie = {"error": repr(ex)}
 
-    # ---- parity spot check + cpu baseline (rank 0, N = 1) ------------------------------------------------------------------
+    # ---- cpu baseline (rank 0, N = 1) ------------------------------------------------------------------------------------
     cpu_baseline = None
-    parity = None
-    if rank == 0:
-        from oracle import oracle as orc
-        chk_files = min(n_files, 8)
-        m = chk_files * per_file
-        qc, qs, qe = (t[:m].cpu().numpy().view(np.uint32) for t in (d_chr, d_start, d_end))
-        o = orc.Index(orc.BITS if args.kind == "bits" else orc.AILIST, offs, s, e, v)
-        o_off, o_ids = o.tokenize_files(h_fo[:chk_files + 1] if e2e else np.arange(chk_files + 1, dtype=np.uint64) * per_file,
-                                        qc, qs, qe, u["unk_id"], threads=orc.max_threads())
-        g_off = d_file_tok[:chk_files + 1].cpu().numpy().astype(np.uint64)
-        g_ids = d_ids[:int(g_off[-1])].cpu().numpy().view(np.uint32)
-        # raw device offsets have no [unk] insertions; the synthetic files are never empty
-        parity = bool(np.array_equal(g_off, o_off) and np.array_equal(g_ids, o_ids))
-        if world == 1 and not args.no_cpu:
-            rate, sample = cpu_oracle_rate(args, 1, args.cpu_seconds, universe={k: (t.cpu() if hasattr(t, "cpu") else t) for k, t in u.items()})
-            cpu_baseline = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                            "note": "C++ restatement of gtars' algorithm (the Rust reference cannot be built here); "
-                                    "1 thread because the reference path is single-threaded"}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        u_cpu = {k: (t.cpu() if hasattr(t, "cpu") else t) for k, t in u.items()}
+        rate, sample = cpu_oracle_rate(args, 1, args.cpu_seconds, u_cpu)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                        "note": "C++ restatement of gtars' algorithm (the Rust reference cannot be built here); 1 thread because "
+                                "the reference path is single-threaded.  It returns ids directly and so omits the reference's "
+                                "per-hit id -> String -> id round trip (tokenizer.rs:146-171): real gtars is slower than this"}
+    c2_seconds = time.perf_counter() - t_start
+
+    # ---- sub-records: the other BASELINE configs, sharded over the ranks ---------------------------------------------------
+    del d_chr, d_start, d_end, d_ids
+    torch.cuda.empty_cache()
+    configs = {}
+    wanted = [c for c in args.configs.split(",") if c]
+    for name in wanted:
+        t0 = time.perf_counter()
+        try:
+            if name == "c3":
+                rec = sub_c3(args, torch, dev, ctx, stream, D, rank, world, peak)
+            elif name == "c4":
+                rec = sub_c4(args, torch, dev, ctx, stream, D, rank, world, peak)
+            elif name == "c5":
+                rec = sub_c5(args, torch, dev, ctx, stream, D, rank, world, peak, u, index)
+            else:
+                continue
+        except Exception as ex:
+            rec = {"error": repr(ex), "trace": traceback.format_exc()[-1500:]}
+        rec["seconds_in_bench"] = time.perf_counter() - t0
+        configs[name] = rec
+        torch.cuda.empty_cache()
 
     if rank == 0:
-        cfg = workload_config(args, world)
-        cfg.update({"hits_per_gpu": hits, "index": info, "parity_spot_check_first_files_vs_oracle": parity})
-        if world > 1:
-            cfg["host_binding_rank0"] = numa or "unbound"
+        details = {"hits_per_gpu": hits, "index": info, "index_build_s": index_build_s, "c2_seconds": c2_seconds,
+                   "host_threads": host_threads(), "empty_files": n_empty_files}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-            "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": launches, "clocks": clocks,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic", "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity, "parity_all_ranks": parity_ok,
+            "pcie": pcie, "details": details, "configs": configs,
         }
         print(json.dumps(out))
     index.close()
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 if __name__ == "__main__":

@@ -17,6 +17,26 @@ int32_t fail(int32_t code, const std::string& msg) {
     return code;
 }
 
+// Called from a catch (...) handler of an entry point: classify the in-flight exception without letting it escape.
+int32_t translate_exception() noexcept {
+    try {
+        try {
+            throw;
+        } catch (const std::bad_alloc&) {
+            g_last_error = "out of host memory (std::bad_alloc)";
+            return GTGPU_ERR_NOMEM;
+        } catch (const std::exception& e) {
+            g_last_error = std::string("unexpected C++ exception: ") + e.what();
+            return GTGPU_ERR_INVALID;
+        } catch (...) {
+            g_last_error = "unexpected non-standard exception";
+            return GTGPU_ERR_INVALID;
+        }
+    } catch (...) {  // building the message itself failed
+        return GTGPU_ERR_NOMEM;
+    }
+}
+
 }  // namespace gtgpu
 
 using namespace gtgpu;
@@ -102,15 +122,15 @@ void gtgpu_ctx::time_end() {
 
 extern "C" {
 
-int32_t gtgpu_timing_enable(gtgpu_ctx* ctx, int32_t on) {
+int32_t gtgpu_timing_enable(gtgpu_ctx* ctx, int32_t on) try {
     if (!ctx) return fail(GTGPU_ERR_INVALID, "timing_enable: null ctx");
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->timing = on != 0;
     ctx->ev_used = 0;
     return GTGPU_OK;
-}
+} GT_CATCH
 
-int32_t gtgpu_timing_read(gtgpu_ctx* ctx, float* out_ms, uint32_t cap, uint32_t* out_n) {
+int32_t gtgpu_timing_read(gtgpu_ctx* ctx, float* out_ms, uint32_t cap, uint32_t* out_n) try {
     if (!ctx || !out_n || (cap && !out_ms)) return fail(GTGPU_ERR_INVALID, "timing_read: null argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     GT_CUDA(cudaSetDevice(ctx->device));
@@ -120,12 +140,12 @@ int32_t gtgpu_timing_read(gtgpu_ctx* ctx, float* out_ms, uint32_t cap, uint32_t*
     *out_n = ctx->ev_used;
     ctx->ev_used = 0;
     return GTGPU_OK;
-}
+} GT_CATCH
 
 const char* gtgpu_last_error(void) { return g_last_error.c_str(); }
 const char* gtgpu_version(void) { return "gtars-b200 0.1 (sm_100a)"; }
 
-int32_t gtgpu_device_count(int32_t* out_n) {
+int32_t gtgpu_device_count(int32_t* out_n) try {
     if (!out_n) return fail(GTGPU_ERR_INVALID, "device_count: null argument");
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -135,9 +155,9 @@ int32_t gtgpu_device_count(int32_t* out_n) {
     }
     *out_n = n;
     return GTGPU_OK;
-}
+} GT_CATCH
 
-int32_t gtgpu_init(int32_t device, void* stream_or_null, gtgpu_ctx** out_ctx) {
+int32_t gtgpu_init(int32_t device, void* stream_or_null, gtgpu_ctx** out_ctx) try {
     if (!out_ctx) return fail(GTGPU_ERR_INVALID, "init: null argument");
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -165,9 +185,9 @@ int32_t gtgpu_init(int32_t device, void* stream_or_null, gtgpu_ctx** out_ctx) {
     GT_CUDA(cudaHostAlloc((void**)&ctx->h_scalars, 64 * sizeof(uint64_t), cudaHostAllocDefault));
     *out_ctx = ctx;
     return GTGPU_OK;
-}
+} GT_CATCH
 
-int32_t gtgpu_shutdown(gtgpu_ctx* ctx) {
+int32_t gtgpu_shutdown(gtgpu_ctx* ctx) try {
     if (!ctx) return GTGPU_OK;
     cudaSetDevice(ctx->device);
     gtgpu_comm_free(ctx);
@@ -183,35 +203,35 @@ int32_t gtgpu_shutdown(gtgpu_ctx* ctx) {
     cudaStreamDestroy(ctx->copy_out);
     delete ctx;
     return GTGPU_OK;
-}
+} GT_CATCH
 
-int32_t gtgpu_synchronize(gtgpu_ctx* ctx) {
+int32_t gtgpu_synchronize(gtgpu_ctx* ctx) try {
     if (!ctx) return fail(GTGPU_ERR_INVALID, "synchronize: null ctx");
     GT_CUDA(cudaStreamSynchronize(ctx->stream));
     return GTGPU_OK;
-}
+} GT_CATCH
 
-int32_t gtgpu_launch_count(gtgpu_ctx* ctx, uint64_t* out_n) {
+int32_t gtgpu_launch_count(gtgpu_ctx* ctx, uint64_t* out_n) try {
     if (!ctx || !out_n) return fail(GTGPU_ERR_INVALID, "launch_count: null argument");
     *out_n = ctx->launches;
     return GTGPU_OK;
-}
+} GT_CATCH
 
-int32_t gtgpu_host_alloc(uint64_t bytes, void** out_ptr) {
+int32_t gtgpu_host_alloc(uint64_t bytes, void** out_ptr) try {
     if (!out_ptr) return fail(GTGPU_ERR_INVALID, "host_alloc: null argument");
     cudaError_t e = cudaHostAlloc(out_ptr, std::max<uint64_t>(bytes, 64), cudaHostAllocDefault);
     if (e != cudaSuccess) return fail(GTGPU_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
     return GTGPU_OK;
-}
+} GT_CATCH
 
-int32_t gtgpu_host_free(void* ptr) {
+int32_t gtgpu_host_free(void* ptr) try {
     if (ptr) GT_CUDA(cudaFreeHost(ptr));
     return GTGPU_OK;
-}
+} GT_CATCH
 
 const void* gtgpu_buf_data(const gtgpu_buf* buf) { return buf ? buf->block.ptr : nullptr; }
 uint64_t gtgpu_buf_len(const gtgpu_buf* buf) { return buf ? buf->len : 0; }
-int32_t gtgpu_buf_free(gtgpu_buf* buf) {
+int32_t gtgpu_buf_free(gtgpu_buf* buf) try {
     if (!buf) return GTGPU_OK;
     {
         std::lock_guard<std::mutex> lk(buf->ctx->mu);
@@ -219,7 +239,7 @@ int32_t gtgpu_buf_free(gtgpu_buf* buf) {
     }
     delete buf;
     return GTGPU_OK;
-}
+} GT_CATCH
 
 }  // extern "C"
 
@@ -508,30 +528,30 @@ int32_t tokenize_files_pipelined(gtgpu_index* ix, uint64_t n, uint64_t n_files, 
 extern "C" {
 
 int32_t gtgpu_count(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start, const uint32_t* end,
-                    int32_t min_overlap, uint32_t* out_counts) {
+                    int32_t min_overlap, uint32_t* out_counts) try {
     return count_host(ix, n, chr, start, end, min_overlap, COUNT_U32, out_counts, 4);
-}
+} GT_CATCH
 
 int32_t gtgpu_bits_count(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start,
-                         const uint32_t* end, uint64_t* out_counts) {
+                         const uint32_t* end, uint64_t* out_counts) try {
     return count_host(ix, n, chr, start, end, 0, COUNT_BITS_RAW_U64, out_counts, 8);
-}
+} GT_CATCH
 
 int32_t gtgpu_any(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start, const uint32_t* end,
-                  int32_t min_overlap, uint8_t* out_any) {
+                  int32_t min_overlap, uint8_t* out_any) try {
     return count_host(ix, n, chr, start, end, min_overlap, COUNT_ANY_U8, out_any, 1);
-}
+} GT_CATCH
 
 int32_t gtgpu_find(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start, const uint32_t* end,
-                   int32_t min_overlap, uint64_t* out_offsets, gtgpu_buf** out_vals) {
+                   int32_t min_overlap, uint64_t* out_offsets, gtgpu_buf** out_vals) try {
     if (!ix || !out_offsets || !out_vals || (n && (!chr || !start || !end)))
         return fail(GTGPU_ERR_INVALID, "find: null argument");
     return find_host(ix, n, chr, start, end, min_overlap, out_offsets, false, 0, nullptr, 0, nullptr, out_vals);
-}
+} GT_CATCH
 
 int32_t gtgpu_tokenize_files(gtgpu_index* ix, uint64_t n_files, const uint64_t* file_offsets, const uint32_t* chr,
                              const uint32_t* start, const uint32_t* end, uint32_t unk_id,
-                             uint64_t* out_file_token_offsets, gtgpu_buf** out_ids) {
+                             uint64_t* out_file_token_offsets, gtgpu_buf** out_ids) try {
     if (!ix || !file_offsets || !out_file_token_offsets || !out_ids)
         return fail(GTGPU_ERR_INVALID, "tokenize_files: null argument");
     if (file_offsets[0] != 0) return fail(GTGPU_ERR_INVALID, "tokenize_files: file_offsets[0] must be 0");
@@ -550,12 +570,12 @@ int32_t gtgpu_tokenize_files(gtgpu_index* ix, uint64_t n_files, const uint64_t* 
     }
     return find_host(ix, n, chr, start, end, 0, nullptr, true, n_files, file_offsets, unk_id, out_file_token_offsets,
                      out_ids);
-}
+} GT_CATCH
 
 int32_t gtgpu_tokenize_files_runs(gtgpu_index* ix, uint64_t n_files, const uint64_t* file_offsets, uint64_t n_runs,
                                   const uint64_t* run_offsets, const uint32_t* run_chr, const uint32_t* start,
                                   const uint32_t* end, uint32_t unk_id, uint64_t* out_file_token_offsets,
-                                  gtgpu_buf** out_ids) {
+                                  gtgpu_buf** out_ids) try {
     if (!ix || !file_offsets || !run_offsets || !out_file_token_offsets || !out_ids || (n_runs && !run_chr))
         return fail(GTGPU_ERR_INVALID, "tokenize_files_runs: null argument");
     if (file_offsets[0] != 0 || run_offsets[0] != 0)
@@ -580,13 +600,13 @@ int32_t gtgpu_tokenize_files_runs(gtgpu_index* ix, uint64_t n_files, const uint6
     for (uint64_t r = 0; r < n_runs; ++r) std::fill(chr.begin() + run_offsets[r], chr.begin() + run_offsets[r + 1], run_chr[r]);
     return find_host(ix, n, chr.data(), start, end, 0, nullptr, true, n_files, file_offsets, unk_id, out_file_token_offsets,
                      out_ids);
-}
+} GT_CATCH
 
 int32_t gtgpu_tokenize_files_compact(gtgpu_index* ix, uint64_t n_files, const uint64_t* file_offsets, uint64_t n_runs,
                                      const uint64_t* run_offsets, const uint32_t* run_chr, const uint32_t* start,
                                      const uint16_t* width16, uint64_t n_wide, const uint64_t* wide_index,
                                      const uint32_t* wide_end, uint32_t unk_id, uint64_t* out_file_token_offsets,
-                                     gtgpu_buf** out_ids) {
+                                     gtgpu_buf** out_ids) try {
     if (!ix || !file_offsets || !run_offsets || !out_file_token_offsets || !out_ids || (n_runs && !run_chr) ||
         (n_wide && (!wide_index || !wide_end)))
         return fail(GTGPU_ERR_INVALID, "tokenize_files_compact: null argument");
@@ -617,21 +637,21 @@ int32_t gtgpu_tokenize_files_compact(gtgpu_index* ix, uint64_t n_files, const ui
     for (uint64_t i = 0; i < n_wide; ++i) end[wide_index[i]] = wide_end[i];
     return find_host(ix, n, chr.data(), start, end.data(), 0, nullptr, true, n_files, file_offsets, unk_id, out_file_token_offsets,
                      out_ids);
-}
+} GT_CATCH
 
 int32_t gtgpu_count_dev(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
-                        const uint32_t* d_end, int32_t min_overlap, uint32_t* d_out_counts) {
+                        const uint32_t* d_end, int32_t min_overlap, uint32_t* d_out_counts) try {
     if (!ix || (n && (!d_chr || !d_start || !d_end || !d_out_counts)))
         return fail(GTGPU_ERR_INVALID, "count_dev: null argument");
     std::lock_guard<std::mutex> lk(ix->ctx->mu);
     GT_CUDA(cudaSetDevice(ix->ctx->device));
     return launch_count(ix, n, d_chr, d_start, d_end, min_overlap, COUNT_U32, d_out_counts);
-}
+} GT_CATCH
 
 int32_t gtgpu_find_dev(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
                        const uint32_t* d_end, int32_t min_overlap, uint64_t n_files, const uint64_t* d_file_offsets,
                        uint32_t* d_out_ids, uint64_t ids_capacity, uint64_t* d_out_offsets,
-                       uint64_t* d_out_file_token_offsets, uint64_t* d_out_total) {
+                       uint64_t* d_out_file_token_offsets, uint64_t* d_out_total) try {
     if (!ix || !d_out_total || (n && (!d_chr || !d_start || !d_end)) || (ids_capacity && !d_out_ids))
         return fail(GTGPU_ERR_INVALID, "find_dev: null argument");
     if (d_out_file_token_offsets && !d_file_offsets)
@@ -647,11 +667,11 @@ int32_t gtgpu_find_dev(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const
     return launch_fused_find(ix, n, d_out_file_token_offsets ? n_files : 0, d_file_offsets, d_chr, d_start, d_end,
                              min_overlap, d_out_ids, ids_capacity, d_out_offsets, d_out_file_token_offsets, d_ws, nullptr,
                              d_out_total, (uint32_t*)(d_misc + 2));
-}
+} GT_CATCH
 
 int32_t gtgpu_unk_rule_dev(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* d_raw_file_token_offsets,
                            const uint32_t* d_raw_ids, uint32_t unk_id, uint64_t* d_out_file_token_offsets,
-                           uint32_t* d_out_ids, uint64_t* d_out_n_empty) {
+                           uint32_t* d_out_ids, uint64_t* d_out_n_empty) try {
     if (!ctx || !d_raw_file_token_offsets || !d_out_file_token_offsets || !d_out_ids || !d_out_n_empty)
         return fail(GTGPU_ERR_INVALID, "unk_rule_dev: null argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -659,6 +679,6 @@ int32_t gtgpu_unk_rule_dev(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* d_r
     GT_TRY(launch_unk_offsets(ctx, n_files, d_raw_file_token_offsets, d_out_file_token_offsets, d_out_n_empty));
     return launch_unk_expand(ctx, n_files, d_raw_file_token_offsets, d_out_file_token_offsets, d_raw_ids, unk_id,
                              d_out_ids);
-}
+} GT_CATCH
 
 }  // extern "C"

@@ -83,7 +83,7 @@ using namespace gtgpu;
             return fail(GTGPU_ERR_NCCL, std::string(#expr) + ": " + ((api)->GetErrorString ? (api)->GetErrorString(_r) : "?")); \
     } while (0)
 
-extern "C" int32_t gtgpu_comm_unique_id(uint8_t out_id[128]) {
+extern "C" int32_t gtgpu_comm_unique_id(uint8_t out_id[128]) try {
     if (!out_id) return fail(GTGPU_ERR_INVALID, "comm_unique_id: null argument");
     NcclApi* api = nccl_api();
     if (!api) return fail(GTGPU_ERR_NCCL, "libnccl.so.2 could not be loaded");
@@ -92,9 +92,9 @@ extern "C" int32_t gtgpu_comm_unique_id(uint8_t out_id[128]) {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
     memcpy(out_id, &id, 128);
     return GTGPU_OK;
-}
+} GT_CATCH
 
-extern "C" int32_t gtgpu_comm_init(gtgpu_ctx* ctx, int32_t world, int32_t rank, const uint8_t id_bytes[128]) {
+extern "C" int32_t gtgpu_comm_init(gtgpu_ctx* ctx, int32_t world, int32_t rank, const uint8_t id_bytes[128]) try {
     if (!ctx || !id_bytes || world < 1 || rank < 0 || rank >= world) return fail(GTGPU_ERR_INVALID, "comm_init: bad argument");
     NcclApi* api = nccl_api();
     if (!api) return fail(GTGPU_ERR_NCCL, "libnccl.so.2 could not be loaded");
@@ -113,9 +113,9 @@ extern "C" int32_t gtgpu_comm_init(gtgpu_ctx* ctx, int32_t world, int32_t rank, 
     }
     ctx->comm = c;
     return GTGPU_OK;
-}
+} GT_CATCH
 
-extern "C" int32_t gtgpu_comm_free(gtgpu_ctx* ctx) {
+extern "C" int32_t gtgpu_comm_free(gtgpu_ctx* ctx) try {
     if (!ctx || !ctx->comm) return GTGPU_OK;
     NcclApi* api = nccl_api();
     Comm* c = (Comm*)ctx->comm;
@@ -123,13 +123,13 @@ extern "C" int32_t gtgpu_comm_free(gtgpu_ctx* ctx) {
     delete c;
     ctx->comm = nullptr;
     return GTGPU_OK;
-}
+} GT_CATCH
 
 // Database sharded by region set: rank r owns global files [r * cols, min((r+1) * cols, n_files_global)),
 // cols = ceil(n_files_global / world); `igd` was built over exactly those files (possibly none).
 extern "C" int32_t gtgpu_igd_count_sharded(gtgpu_ctx* ctx, gtgpu_igd* igd, int32_t binary, uint64_t n_files_global,
                                            uint64_t n_sets, const uint64_t* set_offsets, const uint32_t* chr,
-                                           const uint32_t* start, const uint32_t* end, int32_t min_overlap, uint64_t* out) {
+                                           const uint32_t* start, const uint32_t* end, int32_t min_overlap, uint64_t* out) try {
     if (!ctx || !igd || !set_offsets || !out) return fail(GTGPU_ERR_INVALID, "igd_count_sharded: null argument");
     Comm* c = (Comm*)ctx->comm;
     const int world = c ? c->world : 1, rank = c ? c->rank : 0;
@@ -198,4 +198,4 @@ extern "C" int32_t gtgpu_igd_count_sharded(gtgpu_ctx* ctx, gtgpu_igd* igd, int32
     }
     GT_CUDA(cudaStreamSynchronize(st));
     return GTGPU_OK;
-}
+} GT_CATCH

@@ -23,6 +23,11 @@ int32_t fail(int32_t code, const std::string& msg);
             return ::gtgpu::fail(GTGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
     } while (0)
 
+// Nothing may unwind across the C ABI (the callers are Rust / ctypes): every extern "C" entry point is a function-try-block
+// that ends in GT_CATCH — std::bad_alloc becomes GTGPU_ERR_NOMEM, anything else GTGPU_ERR_INVALID, message in last_error.
+int32_t translate_exception() noexcept;
+#define GT_CATCH catch (...) { return ::gtgpu::translate_exception(); }
+
 #define GT_TRY(expr)                   \
     do {                               \
         int32_t _s = (expr);           \

@@ -59,6 +59,28 @@ __global__ void frag_scatter_kernel(uint64_t n, const uint32_t* __restrict__ ord
     }
 }
 
+// frag_scatter_kernel with a caller-provided output: ids past `capacity` are dropped; the thread of the last fragment (in
+// barcode order) reports the total, or ~0 when the raw hits did not fit their staging buffer (raw_total > raw_cap).
+__global__ void frag_scatter_cap_kernel(uint64_t n, const uint32_t* __restrict__ order, const uint64_t* __restrict__ offsets,
+                                        const unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ counts,
+                                        const uint32_t* __restrict__ raw_ids, uint32_t unk_id, uint32_t* __restrict__ out,
+                                        uint64_t capacity, const uint64_t* __restrict__ raw_total, uint64_t raw_cap,
+                                        uint64_t* __restrict__ out_total) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const uint32_t i = order[k];
+        const uint64_t a = offsets[i], b = offsets[i + 1];
+        uint64_t d = dst[k];
+        if (a == b) {
+            if (d < capacity) out[d] = unk_id;
+        } else {
+            for (uint64_t j = a; j < b; ++j, ++d)
+                if (d < capacity) out[d] = raw_ids[j];
+        }
+        if (k == n - 1) *out_total = *raw_total > raw_cap ? ~0ull : dst[k] + counts[k];
+    }
+}
+
 }  // namespace gtgpu
 
 using namespace gtgpu;
@@ -159,7 +181,7 @@ int32_t tokenize_fragments_core(gtgpu_index* ix, uint64_t n, const uint32_t* d_c
 
 extern "C" int32_t gtgpu_tokenize_fragments(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start,
                                             const uint32_t* end, const uint32_t* barcode_id, uint32_t n_barcodes,
-                                            uint32_t unk_id, uint64_t* out_barcode_offsets, gtgpu_buf** out_ids) {
+                                            uint32_t unk_id, uint64_t* out_barcode_offsets, gtgpu_buf** out_ids) try {
     if (!ix || !out_barcode_offsets || !out_ids || (n && (!chr || !start || !end || !barcode_id)))
         return fail(GTGPU_ERR_INVALID, "tokenize_fragments: null argument");
     if (n >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "tokenize_fragments: more than 2^32-2 fragments per call");
@@ -181,4 +203,64 @@ extern "C" int32_t gtgpu_tokenize_fragments(gtgpu_index* ix, uint64_t n, const u
         GT_CUDA(cudaMemcpyAsync(d_bc, barcode_id, n * 4, cudaMemcpyHostToDevice, st));
     }
     return tokenize_fragments_core(ix, n, d_chr, d_start, d_end, d_bc, n_barcodes, unk_id, out_barcode_offsets, out_ids);
-}
+} GT_CATCH
+
+// Device-resident form of gtgpu_tokenize_fragments: nothing crosses PCIe and nothing synchronises — find, stable radix
+// sort by barcode, per-fragment [unk] rule, scan and scatter are queued on the ctx stream.
+extern "C" int32_t gtgpu_tokenize_fragments_dev(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
+                                                const uint32_t* d_end, const uint32_t* d_barcode_id, uint32_t n_barcodes,
+                                                uint32_t unk_id, uint64_t* d_out_barcode_offsets, uint32_t* d_out_ids,
+                                                uint64_t ids_capacity, uint64_t* d_out_total) try {
+    if (!ix || !d_out_barcode_offsets || !d_out_total || (ids_capacity && !d_out_ids) ||
+        (n && (!d_chr || !d_start || !d_end || !d_barcode_id)))
+        return fail(GTGPU_ERR_INVALID, "tokenize_fragments_dev: null argument");
+    if (n >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "tokenize_fragments_dev: more than 2^32-2 fragments per call");
+    gtgpu_ctx* ctx = ix->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    GT_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (n == 0) {
+        GT_CUDA(cudaMemsetAsync(d_out_barcode_offsets, 0, ((uint64_t)n_barcodes + 1) * 8, st));
+        GT_CUDA(cudaMemsetAsync(d_out_total, 0, 8, st));
+        return GTGPU_OK;
+    }
+    uint32_t *d_bc, *d_bc_sorted, *d_idx, *d_order, *d_raw;
+    uint64_t *d_off, *d_misc;
+    unsigned long long *d_cnt, *d_dst;
+    void *d_ws, *d_tmp;
+    const uint64_t raw_cap = n + n / 4 + 1024;
+    GT_TRY(ctx->scratch_get(SC_BARCODE, n * 4, (void**)&d_bc));
+    GT_TRY(ctx->scratch_get(SC_IN2_CHR, n * 4, (void**)&d_bc_sorted));
+    GT_TRY(ctx->scratch_get(SC_IN2_START, n * 4, (void**)&d_idx));
+    GT_TRY(ctx->scratch_get(SC_IN2_END, n * 4, (void**)&d_order));
+    GT_TRY(ctx->scratch_get(SC_OUT_OFFS, (n + 1) * 8, (void**)&d_off));
+    GT_TRY(ctx->scratch_get(SC_COUNTS, (n + 1) * 8, (void**)&d_cnt));
+    GT_TRY(ctx->scratch_get(SC_IN3_CHR, (n + 1) * 8, (void**)&d_dst));
+    GT_TRY(ctx->scratch_get(SC_OUT_IDS, raw_cap * 4, (void**)&d_raw));
+    GT_TRY(ctx->scratch_get(SC_TILE_STATUS, fused_workspace_bytes(n), &d_ws));
+    GT_TRY(ctx->scratch_get(SC_MISC, 64, (void**)&d_misc));
+    GT_TRY(ctx->scratch_get(SC_IN3_START, std::max(radix_sort_temp_bytes(n), exclusive_scan_temp_bytes(n, 8)), &d_tmp));
+    GT_CUDA(cudaMemsetAsync(d_misc, 0, 64, st));
+    GT_TRY(launch_fused_find(ix, n, 0, nullptr, d_chr, d_start, d_end, 0, d_raw, raw_cap, d_off, nullptr, d_ws, nullptr, d_misc,
+                             (uint32_t*)(d_misc + 2)));
+    GT_CUDA(cudaMemcpyAsync(d_bc, d_barcode_id, n * 4, cudaMemcpyDeviceToDevice, st));  // the sort ping-pongs its inputs
+    const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    iota_kernel<<<grid, 256, 0, st>>>(n, d_idx);
+    ctx->launches++;
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < n_barcodes) ++bits;
+    int in_b = 0;
+    GT_TRY(radix_sort_pairs(ctx, n, d_bc, d_idx, d_bc_sorted, d_order, bits, d_tmp, &in_b));
+    if (!in_b) {
+        std::swap(d_bc, d_bc_sorted);
+        std::swap(d_idx, d_order);
+    }
+    frag_token_counts_kernel<<<grid, 256, 0, st>>>(n, d_order, d_off, d_cnt);
+    GT_TRY(exclusive_scan<unsigned long long>(ctx, d_cnt, d_dst, n, d_tmp));
+    frag_barcode_offsets_kernel<<<(n_barcodes + 1 + 255) / 256, 256, 0, st>>>(n_barcodes, n, d_bc_sorted, d_dst, d_cnt, d_out_barcode_offsets);
+    frag_scatter_cap_kernel<<<grid, 256, 0, st>>>(n, d_order, d_off, d_dst, d_cnt, d_raw, unk_id, d_out_ids, ids_capacity, d_misc, raw_cap,
+                                                  d_out_total);
+    ctx->launches += 3;
+    GT_CUDA(cudaGetLastError());
+    return GTGPU_OK;
+} GT_CATCH

@@ -250,7 +250,7 @@ int32_t launch_fill_set_ids(gtgpu_ctx* ctx, uint64_t n_sets, const uint64_t* d_s
 using namespace gtgpu;
 
 extern "C" int32_t gtgpu_igd_build(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* file_offsets, uint32_t n_chroms,
-                                   const uint32_t* chr, const uint32_t* start, const uint32_t* end, gtgpu_igd** out_igd) {
+                                   const uint32_t* chr, const uint32_t* start, const uint32_t* end, gtgpu_igd** out_igd) try {
     if (!ctx || !out_igd || !file_offsets) return fail(GTGPU_ERR_INVALID, "igd_build: null argument");
     for (uint64_t f = 0; f < n_files; ++f)
         if (file_offsets[f] > file_offsets[f + 1]) return fail(GTGPU_ERR_INVALID, "igd_build: file_offsets not monotone");
@@ -394,24 +394,24 @@ extern "C" int32_t gtgpu_igd_build(gtgpu_ctx* ctx, uint64_t n_files, const uint6
     guard.g = nullptr;
     *out_igd = g;
     return GTGPU_OK;
-}
+} GT_CATCH
 
-extern "C" int32_t gtgpu_igd_free(gtgpu_igd* g) {
+extern "C" int32_t gtgpu_igd_free(gtgpu_igd* g) try {
     if (!g) return GTGPU_OK;
     cudaSetDevice(g->ctx->device);
     for (void* p : g->allocs) cudaFree(p);
     delete g;
     return GTGPU_OK;
-}
+} GT_CATCH
 
-extern "C" int32_t gtgpu_igd_info(const gtgpu_igd* g, uint64_t info[4]) {
+extern "C" int32_t gtgpu_igd_info(const gtgpu_igd* g, uint64_t info[4]) try {
     if (!g || !info) return fail(GTGPU_ERR_INVALID, "igd_info: null argument");
     info[0] = g->n_files;
     info[1] = g->n_records;
     info[2] = g->device_bytes;
     info[3] = g->shift;
     return GTGPU_OK;
-}
+} GT_CATCH
 
 namespace {
 
@@ -486,22 +486,22 @@ int32_t igd_count_host(gtgpu_igd* g, bool binary, uint64_t n_sets, const uint64_
 
 extern "C" int32_t gtgpu_igd_count_set_overlaps(gtgpu_igd* igd, uint64_t n_sets, const uint64_t* set_offsets,
                                                 const uint32_t* chr, const uint32_t* start, const uint32_t* end,
-                                                int32_t min_overlap, uint64_t* out) {
+                                                int32_t min_overlap, uint64_t* out) try {
     return igd_count_host(igd, false, n_sets, set_offsets, chr, start, end, min_overlap, out);
-}
+} GT_CATCH
 
 extern "C" int32_t gtgpu_igd_count_region_hits(gtgpu_igd* igd, uint64_t n_sets, const uint64_t* set_offsets,
                                                const uint32_t* chr, const uint32_t* start, const uint32_t* end,
-                                               int32_t min_overlap, uint64_t* out) {
+                                               int32_t min_overlap, uint64_t* out) try {
     return igd_count_host(igd, true, n_sets, set_offsets, chr, start, end, min_overlap, out);
-}
+} GT_CATCH
 
 extern "C" int32_t gtgpu_igd_count_dev(gtgpu_igd* igd, int32_t binary, uint64_t n, const uint32_t* d_set_of,
                                        const uint32_t* d_chr, const uint32_t* d_start, const uint32_t* d_end,
-                                       int32_t min_overlap, uint64_t* d_out) {
+                                       int32_t min_overlap, uint64_t* d_out) try {
     if (!igd || (n && (!d_set_of || !d_chr || !d_start || !d_end || !d_out)))
         return fail(GTGPU_ERR_INVALID, "igd_count_dev: null argument");
     std::lock_guard<std::mutex> lk(igd->ctx->mu);
     GT_CUDA(cudaSetDevice(igd->ctx->device));
     return igd_count_dev_impl(igd, binary != 0, n, d_set_of, d_chr, d_start, d_end, min_overlap, d_out);
-}
+} GT_CATCH

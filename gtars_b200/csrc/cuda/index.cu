@@ -17,6 +17,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <numeric>
 #include <thread>
 
@@ -647,18 +648,18 @@ using namespace gtgpu;
 
 extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_chroms, const uint64_t* chrom_offsets,
                                      const uint32_t* starts, const uint32_t* ends, const uint32_t* vals,
-                                     gtgpu_index** out_index) {
+                                     gtgpu_index** out_index) try {
     if (!ctx || !out_index) return fail(GTGPU_ERR_INVALID, "index_build: null argument");
     HostIndex* H = nullptr;
     GT_TRY(host_index_build(ctx, kind, n_chroms, chrom_offsets, starts, ends, vals, &H));
     const int32_t s = host_index_upload(ctx, *H, out_index);
     host_index_free(H);
     return s;
-}
+} GT_CATCH
 
 extern "C" int32_t gtgpu_index_free(gtgpu_index* ix) { return index_free_impl(ix); }
 
-extern "C" int32_t gtgpu_index_info(const gtgpu_index* ix, uint64_t info[12]) {
+extern "C" int32_t gtgpu_index_info(const gtgpu_index* ix, uint64_t info[12]) try {
     if (!ix || !info) return fail(GTGPU_ERR_INVALID, "index_info: null argument");
     info[0] = ix->n_intervals;
     info[1] = ix->n_segments;
@@ -673,4 +674,4 @@ extern "C" int32_t gtgpu_index_info(const gtgpu_index* ix, uint64_t info[12]) {
     info[10] = ix->bt_clean;
     info[11] = ix->lean_off || (ix->h_lean_probe && *ix->h_lean_probe);
     return GTGPU_OK;
-}
+} GT_CATCH

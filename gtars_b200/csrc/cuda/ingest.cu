@@ -495,7 +495,7 @@ using namespace gtgpu;
 
 extern "C" int32_t gtgpu_parse_bed(gtgpu_ctx* ctx, const char* text, uint64_t n_bytes, uint32_t n_names, const char* names,
                                    const uint32_t* name_offsets, uint64_t* out_n, gtgpu_buf** out_chr, gtgpu_buf** out_start,
-                                   gtgpu_buf** out_end) {
+                                   gtgpu_buf** out_end) try {
     if (!ctx || !out_n || !out_chr || !out_start || !out_end || (n_bytes && !text) || (n_names && (!names || !name_offsets)))
         return fail(GTGPU_ERR_INVALID, "parse_bed: null argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -517,10 +517,10 @@ extern "C" int32_t gtgpu_parse_bed(gtgpu_ctx* ctx, const char* text, uint64_t n_
     *out_start = bufs[1];
     *out_end = bufs[2];
     return GTGPU_OK;
-}
+} GT_CATCH
 
 extern "C" int32_t gtgpu_tokenize_bed(gtgpu_index* ix, const char* text, uint64_t n_bytes, uint32_t n_names, const char* names,
-                                      const uint32_t* name_offsets, uint32_t unk_id, gtgpu_buf** out_ids) {
+                                      const uint32_t* name_offsets, uint32_t unk_id, gtgpu_buf** out_ids) try {
     if (!ix || !out_ids || (n_bytes && !text) || (n_names && (!names || !name_offsets)))
         return fail(GTGPU_ERR_INVALID, "tokenize_bed: null argument");
     gtgpu_ctx* ctx = ix->ctx;
@@ -544,14 +544,14 @@ extern "C" int32_t gtgpu_tokenize_bed(gtgpu_index* ix, const char* text, uint64_
         return GTGPU_OK;
     }
     return to_host_buf(ctx, d_ids, total, out_ids);
-}
+} GT_CATCH
 
 // tokenize_fragment_file (fragments.rs:61-82) from the file's text: parse on the device, barcodes -> dense ids in
 // first-appearance order through a device hash table, then the fragment tokenizer core.
 extern "C" int32_t gtgpu_tokenize_fragments_text(gtgpu_index* ix, const char* text, uint64_t n_bytes, uint32_t n_names,
                                                  const char* names, const uint32_t* name_offsets, uint32_t unk_id,
                                                  uint32_t* out_n_barcodes, gtgpu_buf** out_barcode_spans,
-                                                 gtgpu_buf** out_barcode_offsets, gtgpu_buf** out_ids) {
+                                                 gtgpu_buf** out_barcode_offsets, gtgpu_buf** out_ids) try {
     if (!ix || !out_n_barcodes || !out_barcode_spans || !out_barcode_offsets || !out_ids || (n_bytes && !text) ||
         (n_names && (!names || !name_offsets)))
         return fail(GTGPU_ERR_INVALID, "tokenize_fragments_text: null argument");
@@ -706,4 +706,4 @@ extern "C" int32_t gtgpu_tokenize_fragments_text(gtgpu_index* ix, const char* te
     *out_barcode_offsets = offs;
     *out_ids = ids;
     return GTGPU_OK;
-}
+} GT_CATCH

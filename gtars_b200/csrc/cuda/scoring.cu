@@ -182,7 +182,7 @@ using namespace gtgpu;
 
 extern "C" int32_t gtgpu_score_matrix_dev(gtgpu_index* ix, uint64_t n_files, const uint64_t* d_file_offsets, uint64_t n,
                                           const uint32_t* d_chr, const uint32_t* d_start, const uint32_t* d_end, int32_t mode,
-                                          uint64_t n_cols, uint32_t* d_out_counts) {
+                                          uint64_t n_cols, uint32_t* d_out_counts) try {
     if (!ix || !d_out_counts || !d_file_offsets || (n && (!d_chr || !d_start || !d_end)))
         return fail(GTGPU_ERR_INVALID, "score_matrix_dev: null argument");
     if (mode != GTGPU_SCORE_ATAC && mode != GTGPU_SCORE_CHIP) return fail(GTGPU_ERR_INVALID, "score_matrix_dev: unknown mode");
@@ -190,11 +190,11 @@ extern "C" int32_t gtgpu_score_matrix_dev(gtgpu_index* ix, uint64_t n_files, con
     std::lock_guard<std::mutex> lk(ctx->mu);
     GT_CUDA(cudaSetDevice(ctx->device));
     return score_matrix_dev_locked(ix, n_files, d_file_offsets, n, d_chr, d_start, d_end, mode, n_cols, d_out_counts);
-}
+} GT_CATCH
 
 extern "C" int32_t gtgpu_score_matrix(gtgpu_index* ix, uint64_t n_files, const uint64_t* file_offsets, uint64_t n,
                                       const uint32_t* chr, const uint32_t* start, const uint32_t* end, int32_t mode,
-                                      uint64_t n_cols, uint32_t* out_counts) {
+                                      uint64_t n_cols, uint32_t* out_counts) try {
     if (!ix || !out_counts || !file_offsets || (n && (!chr || !start || !end)))
         return fail(GTGPU_ERR_INVALID, "score_matrix: null argument");
     if (mode != GTGPU_SCORE_ATAC && mode != GTGPU_SCORE_CHIP) return fail(GTGPU_ERR_INVALID, "score_matrix: unknown mode");
@@ -222,11 +222,11 @@ extern "C" int32_t gtgpu_score_matrix(gtgpu_index* ix, uint64_t n_files, const u
     if (n_files * n_cols) GT_CUDA(cudaMemcpyAsync(out_counts, d_mat, n_files * n_cols * 4, cudaMemcpyDeviceToHost, st));
     GT_CUDA(cudaStreamSynchronize(st));
     return GTGPU_OK;
-}
+} GT_CATCH
 
 extern "C" int32_t gtgpu_score_barcodes(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start,
                                         const uint32_t* end, const uint32_t* barcode_id, uint32_t n_barcodes,
-                                        uint64_t* out_barcode_offsets, gtgpu_buf** out_peaks, gtgpu_buf** out_counts) {
+                                        uint64_t* out_barcode_offsets, gtgpu_buf** out_peaks, gtgpu_buf** out_counts) try {
     if (!ix || !out_barcode_offsets || !out_peaks || !out_counts || (n && (!chr || !start || !end || !barcode_id)))
         return fail(GTGPU_ERR_INVALID, "score_barcodes: null argument");
     if (n >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "score_barcodes: more than 2^32-2 fragments per call");
@@ -326,4 +326,4 @@ extern "C" int32_t gtgpu_score_barcodes(gtgpu_index* ix, uint64_t n, const uint3
     *out_peaks = bufs[0];
     *out_counts = bufs[1];
     return GTGPU_OK;
-}
+} GT_CATCH

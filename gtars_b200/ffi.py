@@ -45,7 +45,9 @@ SIGNATURES = {
     "gtgpu_tokenize_files": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
     "gtgpu_tokenize_files_runs": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
     "gtgpu_tokenize_files_compact": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _u32, _vp, _vp]),
+    "gtgpu_marshal_compact": (_i32, [_u64, _vp, _vp, _vp, _u64, _vp, _i32, _vp, _u64, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
     "gtgpu_tokenize_fragments": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp]),
+    "gtgpu_tokenize_fragments_dev": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _u64, _vp]),
     "gtgpu_parse_bed": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gtgpu_tokenize_bed": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp, _u32, _vp]),
     "gtgpu_tokenize_fragments_text": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
@@ -286,12 +288,14 @@ class Index:
             return out_off, h
         return out_off, _take(h)
 
-    def tokenize_fragments(self, chr, start, end, barcode, n_barcodes, unk_id):
+    def tokenize_fragments(self, chr, start, end, barcode, n_barcodes, unk_id, keep_buf=False):
         chr, start, end, barcode = (_arr(a, np.uint32) for a in (chr, start, end, barcode))
         out_off = np.empty(n_barcodes + 1, dtype=np.uint64)
         h = C.c_void_p()
         check(lib().gtgpu_tokenize_fragments(self._h, len(chr), _p(chr), _p(start), _p(end), _p(barcode), n_barcodes,
                                              unk_id, _p(out_off), C.byref(h)))
+        if keep_buf:
+            return out_off, h
         return out_off, _take(h)
 
     def tokenize_bed(self, text: bytes, chrom_names, unk_id):
@@ -327,10 +331,36 @@ class Index:
     def count_dev(self, n, d_chr, d_start, d_end, min_overlap, d_out):
         check(lib().gtgpu_count_dev(self._h, n, d_chr, d_start, d_end, min_overlap, d_out))
 
+    def tokenize_fragments_dev(self, n, d_chr, d_start, d_end, d_barcode, n_barcodes, unk_id, d_out_barcode_offsets, d_out_ids,
+                               ids_capacity, d_out_total):
+        check(lib().gtgpu_tokenize_fragments_dev(self._h, n, d_chr, d_start, d_end, d_barcode, n_barcodes, unk_id,
+                                                 d_out_barcode_offsets, d_out_ids, ids_capacity, d_out_total))
+
     def find_dev(self, n, d_chr, d_start, d_end, min_overlap, n_files, d_file_offsets, d_out_ids, ids_capacity,
                  d_out_offsets, d_out_file_tok, d_out_total):
         check(lib().gtgpu_find_dev(self._h, n, d_chr, d_start, d_end, min_overlap, n_files, d_file_offsets, d_out_ids,
                                    ids_capacity, d_out_offsets, d_out_file_tok, d_out_total))
+
+
+def marshal_compact(chr, start, end, file_offsets, width16_out=None, threads=0):
+    """gtgpu_marshal_compact: (run_offsets, run_chr, width16, wide_index, wide_end) for gtgpu_tokenize_files_compact."""
+    chr, start, end = _arr(chr, np.uint32), _arr(start, np.uint32), _arr(end, np.uint32)
+    fo = _arr(file_offsets, np.uint64)
+    n = len(chr)
+    w16 = width16_out if width16_out is not None else np.empty(n, dtype=np.uint16)
+    run_cap, wide_cap = 64 * (len(fo) - 1) + 1024, 1024
+    for _ in range(2):
+        ro, rc = np.empty(run_cap + 1, dtype=np.uint64), np.empty(run_cap, dtype=np.uint32)
+        wi, we = np.empty(wide_cap, dtype=np.uint64), np.empty(wide_cap, dtype=np.uint32)
+        n_runs, n_wide = C.c_uint64(0), C.c_uint64(0)
+        st = lib().gtgpu_marshal_compact(n, _p(chr), _p(start), _p(end), len(fo) - 1, _p(fo), threads, _p(w16), run_cap, _p(ro),
+                                         _p(rc), C.byref(n_runs), wide_cap, _p(wi), _p(we), C.byref(n_wide))
+        if st == 4:  # GTGPU_ERR_CAPACITY: the needed counts came back
+            run_cap, wide_cap = max(n_runs.value, 1), max(n_wide.value, 1)
+            continue
+        check(st)
+        return ro[:n_runs.value + 1], rc[:n_runs.value], w16, wi[:n_wide.value], we[:n_wide.value]
+    raise GtarsGpuError(4, "marshal_compact: capacity retry failed")
 
 
 def comm_unique_id() -> bytes:

@@ -143,6 +143,16 @@ int32_t gtgpu_tokenize_files_compact(gtgpu_index* index, uint64_t n_files, const
                                      const uint32_t* wide_end, uint32_t unk_id, uint64_t* out_file_token_offsets,
                                      gtgpu_buf** out_ids);
 
+/* Host-side marshalling for gtgpu_tokenize_files_compact (no device work; `threads` host threads, 0 = all cores): from the
+ * flat per-query arrays a caller holds after mapping chromosome names to ids it derives the chromosome runs (cut at every
+ * file boundary as well), the 16-bit widths (out_width16[n], caller-allocated — pinned memory makes the later copy DMA)
+ * and the exception list of queries wider than 65 534 bp or with end < start.  out_run_offsets needs run_capacity + 1
+ * entries.  *out_n_runs / *out_n_wide always receive the counts; GTGPU_ERR_CAPACITY when a capacity was too small. */
+int32_t gtgpu_marshal_compact(uint64_t n, const uint32_t* chr, const uint32_t* start, const uint32_t* end, uint64_t n_files,
+                              const uint64_t* file_offsets, int32_t threads, uint16_t* out_width16, uint64_t run_capacity,
+                              uint64_t* out_run_offsets, uint32_t* out_run_chr, uint64_t* out_n_runs, uint64_t wide_capacity,
+                              uint64_t* out_wide_index, uint32_t* out_wide_end, uint64_t* out_n_wide);
+
 /* tokenize_fragment_file (gtars-tokenizers/src/utils/fragments.rs:12-82) over pre-parsed fragments: every fragment
  * is one Tokenizer::tokenize call (a fragment with no hit, or on an unknown chromosome, yields unk_id), ids are
  * appended to the fragment's barcode list in input order.  barcode_id[i] < n_barcodes (dense ids, mapped by the
@@ -150,6 +160,15 @@ int32_t gtgpu_tokenize_files_compact(gtgpu_index* index, uint64_t n_files, const
 int32_t gtgpu_tokenize_fragments(gtgpu_index* index, uint64_t n, const uint32_t* chr, const uint32_t* start,
                                  const uint32_t* end, const uint32_t* barcode_id, uint32_t n_barcodes, uint32_t unk_id,
                                  uint64_t* out_barcode_offsets, gtgpu_buf** out_ids);
+
+/* gtgpu_tokenize_fragments with everything device-resident and asynchronous on the ctx stream: d_out_barcode_offsets has
+ * n_barcodes + 1 entries, d_out_ids room for ids_capacity ids (ids beyond it are not written), *d_out_total (device u64)
+ * receives the number of ids — one per hit, one unk_id per fragment without a hit — or UINT64_MAX when the fragments
+ * produced more than n + n/4 + 1024 hits (use the host entry point, which re-runs with an exact buffer). */
+int32_t gtgpu_tokenize_fragments_dev(gtgpu_index* index, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
+                                     const uint32_t* d_end, const uint32_t* d_barcode_id, uint32_t n_barcodes,
+                                     uint32_t unk_id, uint64_t* d_out_barcode_offsets, uint32_t* d_out_ids,
+                                     uint64_t ids_capacity, uint64_t* d_out_total);
 
 /* ---- BED text ingest ----------------------------------------------------------------------------------------------------
  * gtgpu_parse_bed replaces the parse + sort of RegionSet::try_from (gtars-core/src/models/region_set.rs:60-185,

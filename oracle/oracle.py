@@ -414,4 +414,10 @@ def lola_tables(user_hits, universe_hits, user_sizes, universe_size):
 
 
 def max_threads() -> int:
-    return lib().orc_max_threads()
+    """Host threads the multithreaded oracle legs use: the CPUs this process may run on.  Deliberately NOT
+    omp_get_max_threads(): torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which made the reference arm
+    single-threaded at N > 1 in round 1; every OpenMP region of the oracle takes an explicit num_threads(threads)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
