@@ -8,7 +8,8 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     let mut objs = vec![];
-    for f in ["api", "index", "kernels", "igd", "fragments", "comm", "sort"] {
+    // every source of gtars_b200/csrc/Makefile's SRCS (tests/test_abi.py keeps the two lists identical)
+    for f in ["api", "index", "kernels", "igd", "fragments", "scoring", "ingest", "comm", "sort", "build", "marshal"] {
         let src = root.join(format!("gtars_b200/csrc/cuda/{f}.cu"));
         let obj = out.join(format!("{f}.o"));
         let ok = Command::new(&nvcc)

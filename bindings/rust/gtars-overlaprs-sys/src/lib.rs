@@ -19,6 +19,8 @@ extern "C" {
     pub fn gtgpu_version() -> *const c_char;
     pub fn gtgpu_device_count(out_n: *mut i32) -> i32;
     pub fn gtgpu_init(device: i32, stream_or_null: *mut c_void, out_ctx: *mut *mut gtgpu_ctx) -> i32;
+    pub fn gtgpu_init_multi(n_devices: i32, device_ids: *const i32, out_ctx: *mut *mut gtgpu_ctx) -> i32;
+    pub fn gtgpu_ctx_devices(ctx: *const gtgpu_ctx, out_n: *mut i32, out_ids: *mut i32, cap: i32) -> i32;
     pub fn gtgpu_shutdown(ctx: *mut gtgpu_ctx) -> i32;
     pub fn gtgpu_synchronize(ctx: *mut gtgpu_ctx) -> i32;
     pub fn gtgpu_launch_count(ctx: *mut gtgpu_ctx, out_n: *mut u64) -> i32;
@@ -63,6 +65,13 @@ extern "C" {
     pub fn gtgpu_tokenize_fragments(index: *mut gtgpu_index, n: u64, chr: *const u32, start: *const u32, end: *const u32,
                                     barcode_id: *const u32, n_barcodes: u32, unk_id: u32, out_barcode_offsets: *mut u64,
                                     out_ids: *mut *mut gtgpu_buf) -> i32;
+    pub fn gtgpu_tokenize_fragments_dev(index: *mut gtgpu_index, n: u64, d_chr: *const u32, d_start: *const u32, d_end: *const u32,
+                                        d_barcode_id: *const u32, n_barcodes: u32, unk_id: u32, d_out_barcode_offsets: *mut u64,
+                                        d_out_ids: *mut u32, ids_capacity: u64, d_out_total: *mut u64) -> i32;
+    pub fn gtgpu_marshal_compact(n: u64, chr: *const u32, start: *const u32, end: *const u32, n_files: u64, file_offsets: *const u64,
+                                 threads: i32, out_width16: *mut u16, run_capacity: u64, out_run_offsets: *mut u64,
+                                 out_run_chr: *mut u32, out_n_runs: *mut u64, wide_capacity: u64, out_wide_index: *mut u64,
+                                 out_wide_end: *mut u32, out_n_wide: *mut u64) -> i32;
     pub fn gtgpu_score_matrix(index: *mut gtgpu_index, n_files: u64, file_offsets: *const u64, n: u64, chr: *const u32,
                               start: *const u32, end: *const u32, mode: i32, n_cols: u64, out_counts: *mut u32) -> i32;
     pub fn gtgpu_score_matrix_dev(index: *mut gtgpu_index, n_files: u64, d_file_offsets: *const u64, n: u64,

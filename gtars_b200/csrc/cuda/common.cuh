@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -150,6 +152,14 @@ struct gtgpu_ctx {
     std::vector<gtgpu::PinnedBlock> pinned_free;  // cache of pinned result blocks
     uint64_t* h_scalars = nullptr;                // small pinned mailbox
     void* comm = nullptr;                         // gtgpu::Comm (NCCL), set by gtgpu_comm_init
+    // Multi-device group (gtgpu_init_multi): peers[0] == this, one ctx per device; empty for a plain single-device ctx.
+    // Group-wide calls (index build, batch queries, IGD counts) shard their work over the peers; a peer that is not
+    // peers[0] is owned by the group and shut down with it.
+    std::vector<gtgpu_ctx*> peers;
+    std::mutex group_mu;                          // serialises group-wide calls
+    bool group_comm_tried = false;                // in-process NCCL communicators (ncclCommInitAll) were set up / attempted
+    int fused_bps[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};  // resident CTAs per SM of the fused find variants
+    const void* l2_window_owner = nullptr;        // the index whose window table the stream's access-policy window covers
     bool timing = false;                          // bracket dominant kernels with events
     std::vector<cudaEvent_t> ev_begin, ev_end;
     uint32_t ev_used = 0;
@@ -179,7 +189,25 @@ struct gtgpu_index {
     bool bt_clean = false;            // every window is a plain record: the lean find kernel can serve the index
     bool lean_off = false;            // the lean kernel had to fall back on this index before
     uint32_t* h_lean_probe = nullptr; // pinned copy of the last launch's lean flag (read lazily, never waited for)
-    bool l2_window_set = false;
+    // Group index (built on a multi-device ctx): replicas[r] lives on ctx->peers[r]; replicas[0] == this.
+    std::vector<gtgpu_index*> replicas;
+};
+
+// gtars-igd database on the device (igd.cu).  A group igd (built on a multi-device ctx) is a header without device data:
+// shards[r] holds the region sets [r * C, min((r + 1) * C, n_files)) on ctx->peers[r], C = ceil(n_files / devices).
+struct gtgpu_igd {
+    gtgpu_ctx* ctx = nullptr;
+    uint64_t n_files = 0, n_records = 0;
+    uint32_t n_chroms = 0, shift = 0;
+    // per chromosome (n_chroms + 1 offsets into the record arrays; LUT offsets / bin counts)
+    std::vector<uint32_t> h_off;
+    uint32_t *d_off = nullptr, *d_lut_s_off = nullptr, *d_nb_s = nullptr, *d_lut_p_off = nullptr, *d_nb_p = nullptr;
+    int32_t *d_start = nullptr, *d_end = nullptr, *d_pmax = nullptr, *d_psame1 = nullptr;
+    uint32_t *d_file = nullptr, *d_lut = nullptr;
+    std::map<int32_t, int32_t*> psame_by_m;  // psame for every min_overlap asked for so far (derived on the device)
+    std::vector<void*> allocs;
+    uint64_t device_bytes = 0;
+    std::vector<gtgpu_igd*> shards;
 };
 
 namespace gtgpu {
@@ -251,6 +279,17 @@ int32_t inclusive_max_scan_u64(gtgpu_ctx* ctx, const unsigned long long* d_in, u
 size_t radix_sort_temp_bytes(uint64_t n);
 int32_t radix_sort_pairs(gtgpu_ctx* ctx, uint64_t n, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
                          int bits, void* d_temp, int* result_in_b);
+
+// groups (api.cu, comm.cu, igd.cu)
+int32_t for_each_device(size_t n_devices, const std::function<int32_t(size_t)>& fn);
+void block_range(uint64_t n, uint64_t world, uint64_t r, uint64_t* lo, uint64_t* hi);
+int32_t group_comm_ensure(gtgpu_ctx* g);
+int32_t igd_count_sharded_impl(gtgpu_ctx* ctx, gtgpu_igd* igd, int32_t binary, uint64_t n_files_global, uint64_t n_sets,
+                               const uint64_t* set_offsets, const uint32_t* chr, const uint32_t* start, const uint32_t* end,
+                               int32_t min_overlap, uint64_t* out, const std::function<bool(bool)>* before_collective);
+// the caller holds igd->ctx->mu
+int32_t igd_count_dev_locked(gtgpu_igd* g, bool binary, uint64_t n, const uint32_t* d_set_of, const uint32_t* d_chr,
+                             const uint32_t* d_start, const uint32_t* d_end, int32_t m, uint64_t* d_out);
 
 // build.cu — device-side primitives of the index builders
 struct LutDesc {       // one bin LUT over arr[arr_off .. arr_off + len): nb + 1 entries written at lut[lut_off ..]

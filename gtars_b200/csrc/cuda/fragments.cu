@@ -8,6 +8,7 @@
 //   4. barcode offsets by binary search over the sorted keys; scatter-copy of every fragment's ids
 // Output is barcode-major: out_barcode_offsets[n_barcodes + 1] + ids.
 #include <algorithm>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -179,14 +180,9 @@ int32_t tokenize_fragments_core(gtgpu_index* ix, uint64_t n, const uint32_t* d_c
 
 }  // namespace gtgpu
 
-extern "C" int32_t gtgpu_tokenize_fragments(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start,
-                                            const uint32_t* end, const uint32_t* barcode_id, uint32_t n_barcodes,
-                                            uint32_t unk_id, uint64_t* out_barcode_offsets, gtgpu_buf** out_ids) try {
-    if (!ix || !out_barcode_offsets || !out_ids || (n && (!chr || !start || !end || !barcode_id)))
-        return fail(GTGPU_ERR_INVALID, "tokenize_fragments: null argument");
-    if (n >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "tokenize_fragments: more than 2^32-2 fragments per call");
-    for (uint64_t i = 0; i < n; ++i)
-        if (barcode_id[i] >= n_barcodes) return fail(GTGPU_ERR_INVALID, "tokenize_fragments: barcode id out of range");
+static int32_t tokenize_fragments_one(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start, const uint32_t* end,
+                                      const uint32_t* barcode_id, uint32_t n_barcodes, uint32_t unk_id,
+                                      uint64_t* out_barcode_offsets, gtgpu_buf** out_ids) {
     gtgpu_ctx* ctx = ix->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
     GT_CUDA(cudaSetDevice(ctx->device));
@@ -203,6 +199,78 @@ extern "C" int32_t gtgpu_tokenize_fragments(gtgpu_index* ix, uint64_t n, const u
         GT_CUDA(cudaMemcpyAsync(d_bc, barcode_id, n * 4, cudaMemcpyHostToDevice, st));
     }
     return tokenize_fragments_core(ix, n, d_chr, d_start, d_end, d_bc, n_barcodes, unk_id, out_barcode_offsets, out_ids);
+}
+
+// Multi-device group: the fragments are dealt to the devices in contiguous blocks, every device groups its block by
+// barcode, and each barcode's final list is the concatenation of its per-device lists in device order — file order inside
+// a barcode is preserved because the blocks are contiguous ranges of the file (no collective).
+static int32_t tokenize_fragments_group(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start, const uint32_t* end,
+                                        const uint32_t* barcode_id, uint32_t n_barcodes, uint32_t unk_id,
+                                        uint64_t* out_barcode_offsets, gtgpu_buf** out_ids) {
+    std::lock_guard<std::mutex> glk(ix->ctx->group_mu);
+    const size_t D = ix->replicas.size();
+    std::vector<gtgpu_buf*> parts(D, nullptr);
+    std::vector<std::vector<uint64_t>> offs(D, std::vector<uint64_t>((size_t)n_barcodes + 1, 0));
+    int32_t s = for_each_device(D, [&](size_t r) -> int32_t {
+        uint64_t lo, hi;
+        block_range(n, D, r, &lo, &hi);
+        return tokenize_fragments_one(ix->replicas[r], hi - lo, chr + lo, start + lo, end + lo, barcode_id + lo, n_barcodes, unk_id,
+                                      offs[r].data(), &parts[r]);
+    });
+    gtgpu_buf* buf = nullptr;
+    if (s == GTGPU_OK) {
+        out_barcode_offsets[0] = 0;
+        for (uint32_t b = 0; b < n_barcodes; ++b) {
+            uint64_t len = 0;
+            for (size_t r = 0; r < D; ++r) len += offs[r][b + 1] - offs[r][b];
+            out_barcode_offsets[b + 1] = out_barcode_offsets[b] + len;
+        }
+        buf = new gtgpu_buf();
+        buf->ctx = ix->ctx;
+        buf->len = out_barcode_offsets[n_barcodes];
+        {
+            std::lock_guard<std::mutex> lk(ix->ctx->mu);
+            cudaSetDevice(ix->ctx->device);
+            s = ix->ctx->pinned_get(buf->len * 4, &buf->block);
+        }
+        if (s != GTGPU_OK) {
+            delete buf;
+            buf = nullptr;
+        }
+    }
+    if (s == GTGPU_OK) {
+        uint32_t* dst = (uint32_t*)buf->block.ptr;
+        for_each_device(D, [&](size_t t) -> int32_t {  // D host threads, each a contiguous range of barcodes
+            uint64_t b0, b1;
+            block_range(n_barcodes, D, t, &b0, &b1);
+            for (uint64_t b = b0; b < b1; ++b) {
+                uint64_t pos = out_barcode_offsets[b];
+                for (size_t r = 0; r < D; ++r) {
+                    const uint64_t a = offs[r][b], len = offs[r][b + 1] - a;
+                    if (len) memcpy(dst + pos, (const uint32_t*)parts[r]->block.ptr + a, len * 4);
+                    pos += len;
+                }
+            }
+            return GTGPU_OK;
+        });
+        *out_ids = buf;
+    }
+    for (auto* p : parts)
+        if (p) gtgpu_buf_free(p);
+    return s;
+}
+
+extern "C" int32_t gtgpu_tokenize_fragments(gtgpu_index* ix, uint64_t n, const uint32_t* chr, const uint32_t* start,
+                                            const uint32_t* end, const uint32_t* barcode_id, uint32_t n_barcodes,
+                                            uint32_t unk_id, uint64_t* out_barcode_offsets, gtgpu_buf** out_ids) try {
+    if (!ix || !out_barcode_offsets || !out_ids || (n && (!chr || !start || !end || !barcode_id)))
+        return fail(GTGPU_ERR_INVALID, "tokenize_fragments: null argument");
+    if (n >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "tokenize_fragments: more than 2^32-2 fragments per call");
+    for (uint64_t i = 0; i < n; ++i)
+        if (barcode_id[i] >= n_barcodes) return fail(GTGPU_ERR_INVALID, "tokenize_fragments: barcode id out of range");
+    if (ix->replicas.size() > 1 && n >= (1u << 20))
+        return tokenize_fragments_group(ix, n, chr, start, end, barcode_id, n_barcodes, unk_id, out_barcode_offsets, out_ids);
+    return tokenize_fragments_one(ix, n, chr, start, end, barcode_id, n_barcodes, unk_id, out_barcode_offsets, out_ids);
 } GT_CATCH
 
 // Device-resident form of gtgpu_tokenize_fragments: nothing crosses PCIe and nothing synchronises — find, stable radix

@@ -14,24 +14,12 @@
 //       that replaces the reference's O(n_files) scratch zero + scan per region.
 // min_overlap <= 0 is tile-dependent in the reference (touching records count only when co-tiled) and is rejected.
 #include <algorithm>
+#include <condition_variable>
 #include <map>
+#include <memory>
 #include <numeric>
 
 #include "common.cuh"
-
-struct gtgpu_igd {
-    gtgpu_ctx* ctx = nullptr;
-    uint64_t n_files = 0, n_records = 0;
-    uint32_t n_chroms = 0, shift = 0;
-    // per chromosome (n_chroms + 1 offsets into the record arrays; LUT offsets / bin counts)
-    std::vector<uint32_t> h_off;
-    uint32_t *d_off = nullptr, *d_lut_s_off = nullptr, *d_nb_s = nullptr, *d_lut_p_off = nullptr, *d_nb_p = nullptr;
-    int32_t *d_start = nullptr, *d_end = nullptr, *d_pmax = nullptr, *d_psame1 = nullptr;
-    uint32_t *d_file = nullptr, *d_lut = nullptr;
-    std::map<int32_t, int32_t*> psame_by_m;  // psame for every min_overlap asked for so far (derived on the device)
-    std::vector<void*> allocs;
-    uint64_t device_bytes = 0;
-};
 
 namespace gtgpu {
 
@@ -249,6 +237,44 @@ int32_t launch_fill_set_ids(gtgpu_ctx* ctx, uint64_t n_sets, const uint64_t* d_s
 
 using namespace gtgpu;
 
+// Multi-device group: the database is sharded by region set (run_lola's database axis, enrichment.rs:198-211): device r
+// builds its own record pool over sets [r * C, min((r + 1) * C, n_files)), C = ceil(n_files / devices), all in parallel.
+static int32_t igd_build_one(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* file_offsets, uint32_t n_chroms, const uint32_t* chr,
+                             const uint32_t* start, const uint32_t* end, gtgpu_igd** out_igd);
+
+static int32_t igd_build_group(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* file_offsets, uint32_t n_chroms, const uint32_t* chr,
+                               const uint32_t* start, const uint32_t* end, gtgpu_igd** out_igd) {
+    std::lock_guard<std::mutex> glk(ctx->group_mu);
+    const size_t D = ctx->peers.size();
+    const uint64_t cols = (n_files + D - 1) / D;
+    std::unique_ptr<gtgpu_igd> g(new gtgpu_igd());
+    g->ctx = ctx;
+    g->n_files = n_files;
+    g->n_chroms = n_chroms;
+    g->shards.assign(D, nullptr);
+    const int32_t s = for_each_device(D, [&](size_t r) -> int32_t {
+        const uint64_t lo = std::min<uint64_t>(r * cols, n_files), hi = std::min<uint64_t>(lo + cols, n_files);
+        std::vector<uint64_t> fo(hi - lo + 1);
+        for (uint64_t f = lo; f <= hi; ++f) fo[f - lo] = file_offsets[f] - file_offsets[lo];
+        const uint64_t r0 = file_offsets[lo];
+        // (peers[0] is the group context itself: the single-device builder is called directly, not through the entry point)
+        return igd_build_one(ctx->peers[r], hi - lo, fo.data(), n_chroms, chr ? chr + r0 : nullptr, start ? start + r0 : nullptr,
+                             end ? end + r0 : nullptr, &g->shards[r]);
+    });
+    if (s != GTGPU_OK) {
+        const std::string msg = gtgpu_last_error();
+        for (auto* sh : g->shards) gtgpu_igd_free(sh);
+        return fail(s, msg);
+    }
+    for (auto* sh : g->shards) {
+        g->n_records += sh->n_records;
+        g->device_bytes += sh->device_bytes;
+    }
+    g->shift = g->shards[0]->shift;
+    *out_igd = g.release();
+    return GTGPU_OK;
+}
+
 extern "C" int32_t gtgpu_igd_build(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* file_offsets, uint32_t n_chroms,
                                    const uint32_t* chr, const uint32_t* start, const uint32_t* end, gtgpu_igd** out_igd) try {
     if (!ctx || !out_igd || !file_offsets) return fail(GTGPU_ERR_INVALID, "igd_build: null argument");
@@ -259,6 +285,13 @@ extern "C" int32_t gtgpu_igd_build(gtgpu_ctx* ctx, uint64_t n_files, const uint6
     if (total && (!chr || !start || !end)) return fail(GTGPU_ERR_INVALID, "igd_build: null record arrays");
     if (total >= 0xFFFFFFFFull || n_files >= 0xFFFFFFFFull || n_chroms >= 0x7FFFFFFFu)
         return fail(GTGPU_ERR_UNSUPPORTED, "igd_build: too many records");
+    if (ctx->peers.size() > 1) return igd_build_group(ctx, n_files, file_offsets, n_chroms, chr, start, end, out_igd);
+    return igd_build_one(ctx, n_files, file_offsets, n_chroms, chr, start, end, out_igd);
+} GT_CATCH
+
+static int32_t igd_build_one(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* file_offsets, uint32_t n_chroms, const uint32_t* chr,
+                             const uint32_t* start, const uint32_t* end, gtgpu_igd** out_igd) {
+    const uint64_t total = file_offsets[n_files];
     std::lock_guard<std::mutex> lk(ctx->mu);
     GT_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -394,10 +427,11 @@ extern "C" int32_t gtgpu_igd_build(gtgpu_ctx* ctx, uint64_t n_files, const uint6
     guard.g = nullptr;
     *out_igd = g;
     return GTGPU_OK;
-} GT_CATCH
+}
 
 extern "C" int32_t gtgpu_igd_free(gtgpu_igd* g) try {
     if (!g) return GTGPU_OK;
+    for (gtgpu_igd* sh : g->shards) gtgpu_igd_free(sh);
     cudaSetDevice(g->ctx->device);
     for (void* p : g->allocs) cudaFree(p);
     delete g;
@@ -415,7 +449,10 @@ extern "C" int32_t gtgpu_igd_info(const gtgpu_igd* g, uint64_t info[4]) try {
 
 namespace {
 
-int32_t igd_count_dev_impl(gtgpu_igd* g, bool binary, uint64_t n, const uint32_t* d_set_of, const uint32_t* d_chr,
+}  // namespace
+
+namespace gtgpu {
+int32_t igd_count_dev_locked(gtgpu_igd* g, bool binary, uint64_t n, const uint32_t* d_set_of, const uint32_t* d_chr,
                            const uint32_t* d_start, const uint32_t* d_end, int32_t m, uint64_t* d_out) {
     gtgpu_ctx* ctx = g->ctx;
     if (m < 1)
@@ -448,9 +485,37 @@ int32_t igd_count_dev_impl(gtgpu_igd* g, bool binary, uint64_t n, const uint32_t
     return GTGPU_OK;
 }
 
+// Group igd: every device counts the (replicated) query sets against its shard of the database, the column blocks are
+// combined with ONE ncclAllGather between the devices (in-process communicators, NVLink), and the first device returns
+// the [n_sets x n_files] matrix.  A barrier in front of the collective keeps device-memory allocation (implicitly
+// synchronising) out of the window in which another device's collective kernel already waits for its peers.
+int32_t igd_count_group(gtgpu_igd* g, bool binary, uint64_t n_sets, const uint64_t* set_offsets, const uint32_t* chr,
+                        const uint32_t* start, const uint32_t* end, int32_t m, uint64_t* out) {
+    gtgpu_ctx* ctx = g->ctx;
+    std::lock_guard<std::mutex> glk(ctx->group_mu);
+    GT_TRY(group_comm_ensure(ctx));
+    const size_t D = g->shards.size();
+    std::mutex bm;
+    std::condition_variable bcv;
+    size_t arrived = 0;
+    bool all_ok = true;
+    const std::function<bool(bool)> barrier = [&](bool ok) {
+        std::unique_lock<std::mutex> l(bm);
+        all_ok = all_ok && ok;
+        if (++arrived == D) bcv.notify_all();
+        else bcv.wait(l, [&] { return arrived == D; });
+        return all_ok;
+    };
+    return for_each_device(D, [&](size_t r) -> int32_t {
+        return igd_count_sharded_impl(ctx->peers[r], g->shards[r], binary ? 1 : 0, g->n_files, n_sets, set_offsets, chr, start, end, m,
+                                      r == 0 ? out : nullptr, &barrier);
+    });
+}
+
 int32_t igd_count_host(gtgpu_igd* g, bool binary, uint64_t n_sets, const uint64_t* set_offsets, const uint32_t* chr,
                        const uint32_t* start, const uint32_t* end, int32_t m, uint64_t* out) {
     if (!g || !set_offsets || !out) return fail(GTGPU_ERR_INVALID, "igd count: null argument");
+    if (!g->shards.empty()) return igd_count_group(g, binary, n_sets, set_offsets, chr, start, end, m, out);
     uint64_t n = set_offsets[n_sets];
     if (n && (!chr || !start || !end)) return fail(GTGPU_ERR_INVALID, "igd count: null query arrays");
     for (uint64_t s = 0; s < n_sets; ++s)
@@ -476,7 +541,7 @@ int32_t igd_count_host(gtgpu_igd* g, bool binary, uint64_t n_sets, const uint64_
     GT_CUDA(cudaMemcpyAsync(d_so, set_offsets, (n_sets + 1) * 8, cudaMemcpyHostToDevice, st));
     GT_CUDA(cudaMemsetAsync(d_out, 0, std::max<uint64_t>(cells * 8, 8), st));
     if (n_sets && n) GT_TRY(launch_fill_set_ids(ctx, n_sets, d_so, d_set));
-    GT_TRY(igd_count_dev_impl(g, binary, n, d_set, d_chr, d_start, d_end, m, d_out));
+    GT_TRY(igd_count_dev_locked(g, binary, n, d_set, d_chr, d_start, d_end, m, d_out));
     if (cells) GT_CUDA(cudaMemcpyAsync(out, d_out, cells * 8, cudaMemcpyDeviceToHost, st));
     GT_CUDA(cudaStreamSynchronize(st));
     return GTGPU_OK;
@@ -501,7 +566,9 @@ extern "C" int32_t gtgpu_igd_count_dev(gtgpu_igd* igd, int32_t binary, uint64_t 
                                        int32_t min_overlap, uint64_t* d_out) try {
     if (!igd || (n && (!d_set_of || !d_chr || !d_start || !d_end || !d_out)))
         return fail(GTGPU_ERR_INVALID, "igd_count_dev: null argument");
+    if (!igd->shards.empty())
+        return fail(GTGPU_ERR_UNSUPPORTED, "igd_count_dev: device pointers belong to one device; a multi-device igd takes host arrays");
     std::lock_guard<std::mutex> lk(igd->ctx->mu);
     GT_CUDA(cudaSetDevice(igd->ctx->device));
-    return igd_count_dev_impl(igd, binary != 0, n, d_set_of, d_chr, d_start, d_end, min_overlap, d_out);
+    return igd_count_dev_locked(igd, binary != 0, n, d_set_of, d_chr, d_start, d_end, min_overlap, d_out);
 } GT_CATCH

@@ -633,6 +633,13 @@ int32_t host_index_upload(gtgpu_ctx* ctx, const HostIndex& H, gtgpu_index** out_
 int32_t index_free_impl(gtgpu_index* ix) {
     if (!ix) return GTGPU_OK;
     cudaSetDevice(ix->ctx->device);
+    if (ix->ctx->l2_window_owner == ix) {  // the stream's access-policy window points into this index: drop it
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof attr);
+        cudaStreamSetAttribute(ix->ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaGetLastError();
+        ix->ctx->l2_window_owner = nullptr;
+    }
     for (void* p : ix->allocs) cudaFree(p);
     if (ix->h_lean_probe) {
         cudaStreamSynchronize(ix->ctx->stream);  // a probe copy may still be in flight
@@ -652,12 +659,29 @@ extern "C" int32_t gtgpu_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_ch
     if (!ctx || !out_index) return fail(GTGPU_ERR_INVALID, "index_build: null argument");
     HostIndex* H = nullptr;
     GT_TRY(host_index_build(ctx, kind, n_chroms, chrom_offsets, starts, ends, vals, &H));
-    const int32_t s = host_index_upload(ctx, *H, out_index);
-    host_index_free(H);
-    return s;
+    std::unique_ptr<HostIndex> hold(H);
+    const size_t D = ctx->peers.size();
+    if (D <= 1) return host_index_upload(ctx, *H, out_index);
+    // multi-device group: the index is replicated — built once on the host, uploaded to every device in parallel
+    std::lock_guard<std::mutex> glk(ctx->group_mu);
+    std::vector<gtgpu_index*> reps(D, nullptr);
+    const int32_t s = for_each_device(D, [&](size_t r) -> int32_t { return host_index_upload(ctx->peers[r], *H, &reps[r]); });
+    if (s != GTGPU_OK) {
+        const std::string msg = gtgpu_last_error();
+        for (gtgpu_index* r : reps) index_free_impl(r);
+        return fail(s, msg);
+    }
+    reps[0]->replicas = reps;
+    *out_index = reps[0];
+    return GTGPU_OK;
 } GT_CATCH
 
-extern "C" int32_t gtgpu_index_free(gtgpu_index* ix) { return index_free_impl(ix); }
+extern "C" int32_t gtgpu_index_free(gtgpu_index* ix) try {
+    if (!ix) return GTGPU_OK;
+    const std::vector<gtgpu_index*> reps = ix->replicas;
+    for (size_t r = 1; r < reps.size(); ++r) index_free_impl(reps[r]);
+    return index_free_impl(ix);
+} GT_CATCH
 
 extern "C" int32_t gtgpu_index_info(const gtgpu_index* ix, uint64_t info[12]) try {
     if (!ix || !info) return fail(GTGPU_ERR_INVALID, "index_info: null argument");

@@ -1463,10 +1463,13 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
         mark_file_tiles_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(n_files, d_file_offsets, n_tiles, ws.tile_file);
         ctx->launches++;
     }
-    // Keep the bin table resident in L2 while 12 B/query of streaming input flows past it.
-    if (!ix->l2_window_set) {
-        ix->l2_window_set = true;
+    // Keep the bin table resident in L2 while 12 B/query of streaming input flows past it: an access-policy window on
+    // the ctx stream, moved whenever another index launches and dropped when its index is freed.
+    if (ctx->l2_window_owner != ix) {
+        ctx->l2_window_owner = ix;
         const char* env = getenv("GTGPU_L2_PERSIST");
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof attr);
         if (ix->bt_bins && !(env && env[0] == '0')) {
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
@@ -1475,21 +1478,19 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
             size_t win = std::min<size_t>(bytes, (size_t)std::max(max_window, 0));
             if (max_persist > 0 && win > 0) {
                 cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(win, (size_t)max_persist));
-                cudaStreamAttrValue attr;
-                memset(&attr, 0, sizeof attr);
                 attr.accessPolicyWindow.base_ptr = const_cast<uint32_t*>(ix->view.bt_rec);
                 attr.accessPolicyWindow.num_bytes = win;
                 attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float)max_persist / (float)win);
                 attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
                 attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
-                cudaGetLastError();
             }
         }
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);  // num_bytes == 0 clears the window
+        cudaGetLastError();
     }
     const bool desc = ix->view.descending != 0, filt = min_overlap > 1, offs = d_out_offsets != nullptr;
     const int variant = (desc ? 4 : 0) | (filt ? 2 : 0) | (offs ? 1 : 0);
-    static int blocks_per_sm[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
+    int (&blocks_per_sm)[2][8] = ctx->fused_bps;  // per ctx = per device: carve-out and occupancy are set on this device
     int grid = 0;
     cudaError_t err = cudaSuccess;
 #define GT_LAUNCH(D, F, O, LEAN, WS, RUN_IF)                                                                             \

@@ -192,9 +192,9 @@ extern "C" int32_t gtgpu_score_matrix_dev(gtgpu_index* ix, uint64_t n_files, con
     return score_matrix_dev_locked(ix, n_files, d_file_offsets, n, d_chr, d_start, d_end, mode, n_cols, d_out_counts);
 } GT_CATCH
 
-extern "C" int32_t gtgpu_score_matrix(gtgpu_index* ix, uint64_t n_files, const uint64_t* file_offsets, uint64_t n,
+static int32_t score_matrix_one(gtgpu_index* ix, uint64_t n_files, const uint64_t* file_offsets, uint64_t n,
                                       const uint32_t* chr, const uint32_t* start, const uint32_t* end, int32_t mode,
-                                      uint64_t n_cols, uint32_t* out_counts) try {
+                                      uint64_t n_cols, uint32_t* out_counts) {
     if (!ix || !out_counts || !file_offsets || (n && (!chr || !start || !end)))
         return fail(GTGPU_ERR_INVALID, "score_matrix: null argument");
     if (mode != GTGPU_SCORE_ATAC && mode != GTGPU_SCORE_CHIP) return fail(GTGPU_ERR_INVALID, "score_matrix: unknown mode");
@@ -221,6 +221,41 @@ extern "C" int32_t gtgpu_score_matrix(gtgpu_index* ix, uint64_t n_files, const u
     GT_TRY(score_matrix_dev_locked(ix, n_files, d_fo, n, d_chr, d_start, d_end, mode, n_cols, d_mat));
     if (n_files * n_cols) GT_CUDA(cudaMemcpyAsync(out_counts, d_mat, n_files * n_cols * 4, cudaMemcpyDeviceToHost, st));
     GT_CUDA(cudaStreamSynchronize(st));
+    return GTGPU_OK;
+}
+
+
+// Multi-device group: counts are additive, so the fragments are dealt to the devices in contiguous blocks (each with the
+// file boundaries that fall inside its block), every device fills a full n_files x n_cols matrix and the host adds them.
+extern "C" int32_t gtgpu_score_matrix(gtgpu_index* ix, uint64_t n_files, const uint64_t* file_offsets, uint64_t n,
+                                      const uint32_t* chr, const uint32_t* start, const uint32_t* end, int32_t mode,
+                                      uint64_t n_cols, uint32_t* out_counts) try {
+    if (!ix || !out_counts || !file_offsets || (n && (!chr || !start || !end)))
+        return fail(GTGPU_ERR_INVALID, "score_matrix: null argument");
+    const size_t D = ix->replicas.size();
+    if (D <= 1 || n < (1u << 20)) return score_matrix_one(ix, n_files, file_offsets, n, chr, start, end, mode, n_cols, out_counts);
+    if (file_offsets[0] != 0 || file_offsets[n_files] != n) return fail(GTGPU_ERR_INVALID, "score_matrix: file_offsets must span [0, n]");
+    for (uint64_t f = 0; f < n_files; ++f)
+        if (file_offsets[f] > file_offsets[f + 1]) return fail(GTGPU_ERR_INVALID, "score_matrix: file_offsets must not decrease");
+    std::lock_guard<std::mutex> glk(ix->ctx->group_mu);
+    const uint64_t cells = n_files * n_cols;
+    std::vector<std::vector<uint32_t>> partial(D);
+    int32_t s = for_each_device(D, [&](size_t r) -> int32_t {
+        uint64_t lo, hi;
+        block_range(n, D, r, &lo, &hi);
+        std::vector<uint64_t> fo(n_files + 1);
+        for (uint64_t f = 0; f <= n_files; ++f) fo[f] = std::min(std::max(file_offsets[f], lo), hi) - lo;
+        uint32_t* dst = r == 0 ? out_counts : (partial[r].resize(cells), partial[r].data());
+        return score_matrix_one(ix->replicas[r], n_files, fo.data(), hi - lo, chr + lo, start + lo, end + lo, mode, n_cols, dst);
+    });
+    if (s != GTGPU_OK) return s;
+    for_each_device(D, [&](size_t t) -> int32_t {  // D host threads, each a contiguous range of cells
+        uint64_t c0, c1;
+        block_range(cells, D, t, &c0, &c1);
+        for (size_t r = 1; r < D; ++r)
+            for (uint64_t c = c0; c < c1; ++c) out_counts[c] += partial[r][c];
+        return GTGPU_OK;
+    });
     return GTGPU_OK;
 } GT_CATCH
 

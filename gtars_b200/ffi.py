@@ -25,6 +25,8 @@ SIGNATURES = {
     "gtgpu_version": (C.c_char_p, []),
     "gtgpu_device_count": (_i32, [_vp]),
     "gtgpu_init": (_i32, [_i32, _vp, _vp]),
+    "gtgpu_init_multi": (_i32, [_i32, _vp, _vp]),
+    "gtgpu_ctx_devices": (_i32, [_vp, _vp, _vp, _i32]),
     "gtgpu_shutdown": (_i32, [_vp]),
     "gtgpu_synchronize": (_i32, [_vp]),
     "gtgpu_launch_count": (_i32, [_vp, _vp]),
@@ -157,10 +159,24 @@ def _take(buf_handle, dtype=np.uint32, copy=True) -> np.ndarray:
 
 
 class Context:
-    def __init__(self, device: int = 0, stream: int | None = None):
+    """gtgpu_ctx: one device (`device`, optionally on the caller's `stream`) or, with `devices=[...]`, one context over
+    several devices of this process (gtgpu_init_multi) whose entry points shard their work internally."""
+
+    def __init__(self, device: int = 0, stream: int | None = None, devices=None):
         self._h = C.c_void_p()
-        check(lib().gtgpu_init(device, C.c_void_p(stream) if stream else None, C.byref(self._h)))
-        self.device = device
+        if devices is not None:
+            ids = np.ascontiguousarray(devices, dtype=np.int32)
+            check(lib().gtgpu_init_multi(len(ids), _p(ids), C.byref(self._h)))
+            self.device = int(ids[0])
+        else:
+            check(lib().gtgpu_init(device, C.c_void_p(stream) if stream else None, C.byref(self._h)))
+            self.device = device
+
+    def devices(self):
+        n = C.c_int32(0)
+        ids = np.zeros(64, dtype=np.int32)
+        check(lib().gtgpu_ctx_devices(self._h, C.byref(n), _p(ids), 64))
+        return [int(x) for x in ids[:n.value]]
 
     def close(self):
         if getattr(self, "_h", None):

@@ -8,7 +8,13 @@
  * Conventions
  *  - every function returns an int32 status (GTGPU_OK = 0); nothing throws or unwinds across the boundary;
  *    gtgpu_last_error() returns a thread-local message for the last failing call on this thread.
- *  - one gtgpu_ctx = one CUDA device (one process per GPU; multi-GPU runs give each rank its own ctx).
+ *  - gtgpu_init gives a context on ONE CUDA device; gtgpu_init_multi gives one context that owns SEVERAL devices of the
+ *    same process: indexes built on it are replicated, IGD databases sharded by region set, and the host
+ *    entry points shard their work over the devices internally — query blocks / files / fragments for count, find,
+ *    tokenize and scoring (no collective), database columns + one ncclAllGather between the devices for the IGD / LOLA
+ *    count matrices — and return exactly what a single device returns.  That is what makes all GPUs of a box reachable
+ *    behind the unchanged Tokenizer::encode / run_lola signatures of a single Python / R / Rust process.  The
+ *    process-per-GPU form (one ctx per rank + gtgpu_comm_*) stays available for MPI / torchrun style launches.
  *  - chromosome names are mapped to dense uint32 ids by the caller; GTGPU_UNKNOWN_CHROM (or any id >= n_chroms)
  *    means "chromosome not in the index" and contributes no hits, exactly like the reference's map lookups
  *    (gtars-tokenizers/src/tokenizer.rs:144, gtars-overlaprs/src/multi_chrom_overlapper.rs:231-234,
@@ -54,9 +60,14 @@ int32_t gtgpu_device_count(int32_t* out_n);
 /* stream_or_null: a cudaStream_t to run on (e.g. the caller's / torch's current stream) or NULL for an
  * internal non-blocking stream. */
 int32_t gtgpu_init(int32_t device, void* stream_or_null, gtgpu_ctx** out_ctx);
+/* One context over n_devices CUDA devices of this process (device_ids NULL = devices 0 .. n_devices-1), each with its own
+ * internal streams, scratch and pinned staging; n_devices == 1 equals gtgpu_init(device_ids[0], NULL).  "_dev" entry points
+ * (device pointers) and the text-ingest entry points run on the first device.  gtgpu_ctx_devices reports the devices. */
+int32_t gtgpu_init_multi(int32_t n_devices, const int32_t* device_ids, gtgpu_ctx** out_ctx);
+int32_t gtgpu_ctx_devices(const gtgpu_ctx* ctx, int32_t* out_n, int32_t* out_ids, int32_t cap);
 int32_t gtgpu_shutdown(gtgpu_ctx* ctx);
 int32_t gtgpu_synchronize(gtgpu_ctx* ctx);
-/* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
+/* Number of kernels this ctx (all its devices) has launched so far (bench.py's gpu_launches). */
 int32_t gtgpu_launch_count(gtgpu_ctx* ctx, uint64_t* out_n);
 
 /* Kernel timing: when enabled, every launch of a dominant kernel (fused find / count / IGD count) is bracketed by
@@ -246,6 +257,7 @@ int32_t gtgpu_igd_count_dev(gtgpu_igd* igd, int32_t binary, uint64_t n, const ui
 
 /* ---- multi-GPU: the LOLA database sharded by region set, one ncclAllGather (run_lola's count matrices,
  * gtars-lola/src/enrichment.rs:198-211) ------------------------------------------------------------------------------
+ * This is the process-per-GPU form (a multi-device context does the same internally, see gtgpu_init_multi).
  * One process per GPU.  Rank 0 calls gtgpu_comm_unique_id and ships the 128 bytes to the other ranks by any means
  * (MPI, torch.distributed, a file); every rank then calls gtgpu_comm_init on its ctx.  NCCL is dlopen'ed on first
  * use.  With world W and n_files_global sets, rank r must have built its gtgpu_igd over global sets

@@ -205,3 +205,10 @@ def test_rust_sys_stub_declares_every_entry_point():
     rs = open(os.path.join(ROOT, "bindings", "rust", "gtars-overlaprs-sys", "src", "lib.rs")).read()
     missing = [s for s in _declared_symbols() if not re.search(r"\bfn\s+" + s + r"\b", rs)]
     assert not missing, missing
+    # build.rs compiles exactly the sources the Makefile links into libgtars_gpu.so (a missing one is a link failure the
+    # day someone runs cargo)
+    mk = open(os.path.join(ROOT, "gtars_b200", "csrc", "Makefile")).read()
+    srcs = sorted(re.findall(r"cuda/(\w+)\.cu", re.search(r"^SRCS := (.*)$", mk, re.M).group(1)))
+    brs = open(os.path.join(ROOT, "bindings", "rust", "gtars-overlaprs-sys", "build.rs")).read()
+    listed = sorted(re.findall(r'"(\w+)"', re.search(r"for f in \[(.*?)\]", brs, re.S).group(1)))
+    assert listed == srcs, (listed, srcs)
