@@ -158,7 +158,7 @@ struct gtgpu_ctx {
     std::vector<gtgpu_ctx*> peers;
     std::mutex group_mu;                          // serialises group-wide calls
     bool group_comm_tried = false;                // in-process NCCL communicators (ncclCommInitAll) were set up / attempted
-    int fused_bps[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};  // resident CTAs per SM of the fused find variants
+    int fused_bps[2][10] = {{0}, {0}};  // resident CTAs per SM of the fused find variants
     const void* l2_window_owner = nullptr;        // the index whose window table the stream's access-policy window covers
     bool timing = false;                          // bracket dominant kernels with events
     std::vector<cudaEvent_t> ev_begin, ev_end;
@@ -247,7 +247,8 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
                           const uint32_t* d_chr, const uint32_t* d_start, const uint32_t* d_end,
                           int32_t min_overlap, uint32_t* d_out_ids, uint64_t ids_capacity,
                           uint64_t* d_out_offsets, uint64_t* d_out_file_tok, void* d_workspace,
-                          const uint64_t* d_base, uint64_t* d_total_out, uint32_t* d_errflag);
+                          const uint64_t* d_base, uint64_t* d_total_out, uint32_t* d_errflag, int unk_per_query = 0,
+                          uint32_t unk_id = 0);
 // Per-call [unk] rule: expands raw per-file id runs into d_out, inserting unk_id for files with no ids.
 int32_t launch_unk_offsets(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* d_raw_file_tok,
                            uint64_t* d_out_file_tok, uint64_t* d_n_empty);
@@ -278,7 +279,8 @@ int32_t exclusive_scan(gtgpu_ctx* ctx, const T* d_in, T* d_out, uint64_t n, void
 int32_t inclusive_max_scan_u64(gtgpu_ctx* ctx, const unsigned long long* d_in, unsigned long long* d_out, uint64_t n, void* d_temp);
 size_t radix_sort_temp_bytes(uint64_t n);
 int32_t radix_sort_pairs(gtgpu_ctx* ctx, uint64_t n, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
-                         int bits, void* d_temp, int* result_in_b);
+                         int bits, void* d_temp, int* result_in_b, const uint64_t* d_n = nullptr);
+void radix_plan(int bits, int* passes, int* width);
 
 // groups (api.cu, comm.cu, igd.cu)
 int32_t for_each_device(size_t n_devices, const std::function<int32_t(size_t)>& fn);

@@ -322,6 +322,7 @@ int32_t host_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_chroms, const 
         if (const char* env = getenv("GTGPU_RANK_BINS_PER_INTERVAL")) rbudget = std::max<uint64_t>(strtoull(env, nullptr, 10) * total, 4096);
         while (rank_shift < 29 && std::max(lut_entries(max_cs, rank_shift), lut_entries(max_ce, rank_shift)) > rbudget) ++rank_shift;
     }
+    if (const char* env = getenv("GTGPU_RANK_SHIFT_EXTRA")) rank_shift = (uint32_t)std::min(29, (int)rank_shift + std::max(0, atoi(env)));
     const uint32_t rank_inline = rank_shift == 0 ? 4 : std::min<uint32_t>(4, 29 / rank_shift);
     H.rank_shift = rank_shift;
     H.rank_inline = rank_inline;

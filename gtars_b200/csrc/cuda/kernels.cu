@@ -590,8 +590,20 @@ int32_t launch_count(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const u
     if (n == 0) return GTGPU_OK;
     gtgpu_ctx* ctx = ix->ctx;
     if (const char* env = getenv("GTGPU_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(env));  // tuning knob
-    if (count_wants_partition(ix, n, d_chr, d_end, min_overlap))
+    if (count_wants_partition(ix, n, d_chr, d_end, min_overlap)) {
+        // The bucketed pass lives on its LUT slices staying in the L2: give back what an earlier find on this ctx set aside
+        // for its window table (persisting lines + the stream's access-policy window; the next find re-establishes both).
+        if (ctx->l2_window_owner) {
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof attr);
+            cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+            cudaCtxResetPersistingL2Cache();
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+            cudaGetLastError();
+            ctx->l2_window_owner = nullptr;
+        }
         return launch_count_partitioned(ix, n, d_chr, d_start, d_end, min_overlap, mode, d_out);
+    }
     ctx->time_begin();
     switch (mode) {
         case COUNT_U32: launch_count_mode<COUNT_U32>(ctx, ix->view, n, d_chr, d_start, d_end, min_overlap, d_out, false); break;
@@ -890,14 +902,16 @@ __device__ __forceinline__ bool cand_hit(uint32_t cs, uint32_t ce, uint32_t s, u
 #ifndef GT_LEAN_MINBLOCKS
 #define GT_LEAN_MINBLOCKS 5
 #endif
-template <int ROWS, bool DESC, bool FILTER, bool OFFS, bool LEAN>
+// UNK1: the per-query [unk] rule of fragment tokenization (fragments.rs:42-47: every fragment is its own tokenize() call) —
+// a query without a hit emits the single id unk_id, so the id stream IS the token stream and the per-query offsets index it.
+template <int ROWS, bool DESC, bool FILTER, bool OFFS, bool LEAN, bool UNK1 = false>
 __global__ void __launch_bounds__(FUSED_BLOCK, LEAN ? GT_LEAN_MINBLOCKS : GT_FUSED_MINBLOCKS)
 fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, const uint64_t* __restrict__ file_offsets,
                   const uint32_t* __restrict__ chr, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
                   int32_t min_bp, int tma_ok, uint32_t* __restrict__ out_ids, uint64_t capacity,
                   uint64_t* __restrict__ out_offsets, uint64_t* __restrict__ out_file_tok, FusedWorkspace ws,
                   const uint64_t* __restrict__ d_base, uint64_t* __restrict__ d_total, uint32_t* __restrict__ d_err,
-                  uint32_t* __restrict__ lean_flag, const uint32_t* __restrict__ run_if) {
+                  uint32_t* __restrict__ lean_flag, const uint32_t* __restrict__ run_if, uint32_t unk_id) {
     static_assert(ROWS == 4, "state packing (2-bit counts, 8-bit offsets) is written for four rows per thread");
     if (!LEAN && run_if && *run_if == 0) return;  // fallback launch, and the lean kernel resolved everything
     constexpr int WARPS = FUSED_BLOCK / 32;
@@ -1004,6 +1018,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
             const uint32_t wl = warp * WTILE + lane;
             // ---- queries: ROWS coalesced rows per array, from the TMA-staged copy when there is one -----------------
             uint32_t qc[ROWS], qs[ROWS], qe[ROWS];
+            uint32_t vmask = (1u << ROWS) - 1;  // bit k: row k is a real query (only the last, partial tile has others)
             if (s_staged[par]) {
 #pragma unroll
                 for (int k = 0; k < ROWS; ++k) {
@@ -1016,6 +1031,7 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                 for (int k = 0; k < ROWS; ++k) {
                     const uint64_t q = tile_start + wl + 32 * k;
                     const bool ok = q < n;
+                    if (!ok) vmask &= ~(1u << k);
                     qc[k] = ok ? __ldcs(chr + q) : 0xFFFFFFFFu;
                     qs[k] = ok ? __ldcs(start + q) : 0;
                     qe[k] = ok ? __ldcs(end + q) : 1;  // past the end: an unknown-chromosome query [0, 1) the records resolve to nothing
@@ -1057,6 +1073,10 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     if ((r[k].x & 3) == 3) {  // pool list or overflow (all-zero candidates: no hit above)
                         cur.slow |= 1u << k;
                         if (!LEAN) cur.v0[k] = r[k].y;  // the full kernel walks the list from this word
+                    }
+                    if (UNK1 && cnt[k] == 0 && !((cur.slow >> k) & 1) && ((vmask >> k) & 1)) {
+                        cnt[k] = 1;  // no hit: the fragment's token is [unk]
+                        cur.v0[k] = unk_id;
                     }
                 }
             }
@@ -1116,6 +1136,11 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                         ordered = (r >> 31) != 0;
                         a = ab[0];
                         b = ab[1];
+                    }
+                    if (UNK1 && c == 0 && ((vmask >> k) & 1)) {
+                        c = 1;
+                        a = unk_id;
+                        ordered = true;
                     }
                     cnt[k] = c;
                     if (ordered && c <= 2) {
@@ -1387,14 +1412,14 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
 #endif
 }
 
-template <bool DESC, bool FILTER, bool OFFS, bool LEAN>
+template <bool DESC, bool FILTER, bool OFFS, bool LEAN, bool UNK1 = false>
 static cudaError_t launch_variant(int grid, cudaStream_t st, const IndexView& view, uint64_t n, uint32_t n_tiles,
                                   uint64_t n_files, const uint64_t* d_file_offsets, const uint32_t* d_chr,
                                   const uint32_t* d_start, const uint32_t* d_end, int32_t min_overlap, uint32_t* d_out_ids,
                                   uint64_t cap, uint64_t* d_out_offsets, uint64_t* d_out_file_tok, FusedWorkspace ws,
                                   const uint64_t* d_base, uint64_t* d_total_out, uint32_t* d_errflag, const uint32_t* run_if,
-                                  int* blocks_per_sm) {
-    auto kern = fused_find_kernel<FUSED_ROWS, DESC, FILTER, OFFS, LEAN>;
+                                  int* blocks_per_sm, uint32_t unk_id = 0) {
+    auto kern = fused_find_kernel<FUSED_ROWS, DESC, FILTER, OFFS, LEAN, UNK1>;
     if (blocks_per_sm) {
         // 4 CTAs x 24 KB fit the 100 KB shared-memory configuration (5 CTAs of the lean kernel: 132 KB); the rest of
         // the unified L1 serves the gathers
@@ -1404,11 +1429,12 @@ static cudaError_t launch_variant(int grid, cudaStream_t st, const IndexView& vi
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, FUSED_BLOCK, 0);
     }
     // bulk copies need 16-byte aligned sources; tile starts are multiples of 4 KiB, so only the bases matter
-    const int tma_ok = ((reinterpret_cast<uintptr_t>(d_chr) | reinterpret_cast<uintptr_t>(d_start) |
-                         reinterpret_cast<uintptr_t>(d_end)) & 15) == 0;
+    static const bool no_tma = getenv("GTGPU_NO_TMA") != nullptr;  // tuning knob: plain coalesced loads instead of bulk copies
+    const int tma_ok = !no_tma && ((reinterpret_cast<uintptr_t>(d_chr) | reinterpret_cast<uintptr_t>(d_start) |
+                                    reinterpret_cast<uintptr_t>(d_end)) & 15) == 0;
     kern<<<grid, FUSED_BLOCK, 0, st>>>(view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end, min_overlap, tma_ok,
                                        d_out_ids, cap, d_out_offsets, d_out_file_tok, ws, d_base, d_total_out, d_errflag,
-                                       ws.lean_flag, run_if);
+                                       ws.lean_flag, run_if, unk_id);
     return cudaGetLastError();
 }
 
@@ -1427,8 +1453,10 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
                           const uint32_t* d_chr, const uint32_t* d_start, const uint32_t* d_end,
                           int32_t min_overlap, uint32_t* d_out_ids, uint64_t ids_capacity,
                           uint64_t* d_out_offsets, uint64_t* d_out_file_tok, void* d_workspace,
-                          const uint64_t* d_base, uint64_t* d_total_out, uint32_t* d_errflag) {
+                          const uint64_t* d_base, uint64_t* d_total_out, uint32_t* d_errflag, int unk_per_query, uint32_t unk_id) {
     gtgpu_ctx* ctx = ix->ctx;
+    if (unk_per_query && (!d_out_offsets || min_overlap > 1 || d_out_file_tok || n == 0))
+        return fail(GTGPU_ERR_INVALID, "fused_find: the per-query [unk] rule needs per-query offsets, no bp filter, no files, n > 0");
     cudaStream_t st = ctx->stream;
     if (n == 0) {
         // No queries: every offset equals the base, the total is the base.
@@ -1489,37 +1517,38 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
         cudaGetLastError();
     }
     const bool desc = ix->view.descending != 0, filt = min_overlap > 1, offs = d_out_offsets != nullptr;
-    const int variant = (desc ? 4 : 0) | (filt ? 2 : 0) | (offs ? 1 : 0);
-    int (&blocks_per_sm)[2][8] = ctx->fused_bps;  // per ctx = per device: carve-out and occupancy are set on this device
+    const int variant = unk_per_query ? (desc ? 9 : 8) : (desc ? 4 : 0) | (filt ? 2 : 0) | (offs ? 1 : 0);
+    int (&blocks_per_sm)[2][10] = ctx->fused_bps;  // per ctx = per device: carve-out and occupancy are set on this device
     int grid = 0;
     cudaError_t err = cudaSuccess;
-#define GT_LAUNCH(D, F, O, LEAN, WS, RUN_IF)                                                                             \
+#define GT_LAUNCH(D, F, O, LEAN, WS, RUN_IF, U)                                                                           \
     do {                                                                                                                \
         int& bps = blocks_per_sm[LEAN ? 1 : 0][variant];                                                                \
         if (!bps) {                                                                                                     \
-            err = launch_variant<D, F, O, LEAN>(0, st, ix->view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end, \
+            err = launch_variant<D, F, O, LEAN, U>(0, st, ix->view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end, \
                                                 min_overlap, d_out_ids, ids_capacity, d_out_offsets, d_out_file_tok, WS,  \
-                                                d_base, d_total_out, d_errflag, RUN_IF, &bps);                          \
+                                                d_base, d_total_out, d_errflag, RUN_IF, &bps, unk_id);                  \
             if (err != cudaSuccess) break;                                                                              \
             if (bps < 1) bps = 1;                                                                                       \
         }                                                                                                               \
         grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * bps);                                         \
-        err = launch_variant<D, F, O, LEAN>(grid, st, ix->view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end,  \
+        err = launch_variant<D, F, O, LEAN, U>(grid, st, ix->view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end,  \
                                             min_overlap, d_out_ids, ids_capacity, d_out_offsets, d_out_file_tok, WS, d_base, \
-                                            d_total_out, d_errflag, RUN_IF, nullptr);                                    \
+                                            d_total_out, d_errflag, RUN_IF, nullptr, unk_id);                            \
         ctx->launches++;                                                                                                \
     } while (0)
-#define GT_VARIANT(D, F, O)                                                                                              \
-    case ((D ? 4 : 0) | (F ? 2 : 0) | (O ? 1 : 0)):                                                                      \
+#define GT_VARIANT_AT(V, D, F, O, U)                                                                                     \
+    case V:                                                                                                             \
         ctx->time_begin();                                                                                              \
         if (use_lean) {                                                                                                 \
-            GT_LAUNCH(D, F, O, true, ws, nullptr);                                                                      \
-            if (err == cudaSuccess) GT_LAUNCH(D, F, O, false, ws_fallback, ws.lean_flag);                               \
+            GT_LAUNCH(D, F, O, true, ws, nullptr, U);                                                                   \
+            if (err == cudaSuccess) GT_LAUNCH(D, F, O, false, ws_fallback, ws.lean_flag, U);                            \
         } else {                                                                                                        \
-            GT_LAUNCH(D, F, O, false, ws, nullptr);                                                                     \
+            GT_LAUNCH(D, F, O, false, ws, nullptr, U);                                                                  \
         }                                                                                                               \
         ctx->time_end();                                                                                                \
         break;
+#define GT_VARIANT(D, F, O) GT_VARIANT_AT(((D ? 4 : 0) | (F ? 2 : 0) | (O ? 1 : 0)), D, F, O, false)
     switch (variant) {
         GT_VARIANT(false, false, false)
         GT_VARIANT(false, false, true)
@@ -1529,8 +1558,11 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
         GT_VARIANT(true, false, true)
         GT_VARIANT(true, true, false)
         GT_VARIANT(true, true, true)
+        GT_VARIANT_AT(8, false, false, true, true)  // per-query [unk] rule (fragments): offsets on, no filter
+        GT_VARIANT_AT(9, true, false, true, true)
     }
 #undef GT_VARIANT
+#undef GT_VARIANT_AT
 #undef GT_LAUNCH
     if (err != cudaSuccess) return fail(GTGPU_ERR_CUDA, std::string("fused_find launch: ") + cudaGetErrorString(err));
     if (use_lean && ix->h_lean_probe) cudaMemcpyAsync(ix->h_lean_probe, ws.lean_flag, 4, cudaMemcpyDeviceToHost, st);

@@ -4,7 +4,7 @@
 // single-pass tricks): they run once per call over arrays that are small next to the fused find kernel's traffic.
 //
 //   exclusive_scan<T>:  reduce per 2 048-element tile -> scan of the tile sums by one block -> per-tile rescan + offset.
-//   radix_sort_pairs:   8 bits per pass; per pass  (1) per-tile digit histograms, stored digit-major,
+//   radix_sort_pairs:   8 (or 9, when that saves a pass) bits per pass; per pass  (1) per-tile digit histograms, stored digit-major,
 //                       (2) exclusive scan of that table = global start of every (digit, tile) bucket,
 //                       (3) scatter: each warp owns 512 consecutive elements, ranks them round by round with
 //                           __match_any_sync, so equal digits keep their input order (stable).
@@ -213,29 +213,39 @@ constexpr int RS_ROUNDS = 16;                          // elements per lane
 constexpr int RS_WARP_TILE = 32 * RS_ROUNDS;           // 512 consecutive elements per warp
 constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;        // 4 096 per block
 
-__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, int shift,
+// DB = digit width of the pass: 8 bits, or 9 when that saves a whole pass (17-18 and 25-27 significant bits)
+template <int DB>
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n_cap,
+                                                                const uint64_t* __restrict__ d_n, int shift,
                                                                 uint32_t n_tiles, uint32_t* __restrict__ hist) {
-    __shared__ uint32_t s_hist[256];
-    s_hist[threadIdx.x] = 0;
+    constexpr uint32_t ND = 1u << DB;
+    const uint64_t n = d_n ? min((uint64_t)*d_n, n_cap) : n_cap;  // element count known on the device only (no host sync)
+    __shared__ uint32_t s_hist[ND];
+    for (uint32_t d = threadIdx.x; d < ND; d += RS_THREADS) s_hist[d] = 0;
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
 #pragma unroll 4
     for (int k = 0; k < RS_ROUNDS; ++k) {
         const uint64_t i = base + (uint64_t)k * RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&s_hist[(keys[i] >> shift) & 0xFF], 1u);
+        if (i < n) atomicAdd(&s_hist[(keys[i] >> shift) & (ND - 1)], 1u);
     }
     __syncthreads();
-    hist[(uint64_t)threadIdx.x * n_tiles + blockIdx.x] = s_hist[threadIdx.x];  // digit-major: one scan orders everything
+    for (uint32_t d = threadIdx.x; d < ND; d += RS_THREADS)
+        hist[(uint64_t)d * n_tiles + blockIdx.x] = s_hist[d];  // digit-major: one scan orders everything
 }
 
+template <int DB>
 __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
-                                                                   const uint32_t* __restrict__ vals_in, uint64_t n, int shift,
+                                                                   const uint32_t* __restrict__ vals_in, uint64_t n_cap,
+                                                                   const uint64_t* __restrict__ d_n, int shift,
                                                                    uint32_t n_tiles, const uint32_t* __restrict__ bucket_start,
                                                                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
     constexpr int WARPS = RS_THREADS / 32;
-    __shared__ uint32_t s_count[WARPS][256];  // first per-warp digit counts, then the running output cursor per (warp, digit)
+    constexpr uint32_t ND = 1u << DB;
+    const uint64_t n = d_n ? min((uint64_t)*d_n, n_cap) : n_cap;
+    __shared__ uint32_t s_count[WARPS][ND];  // first per-warp digit counts, then the running output cursor per (warp, digit)
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < WARPS * 256; i += RS_THREADS) (&s_count[0][0])[i] = 0;
+    for (uint32_t i = threadIdx.x; i < WARPS * ND; i += RS_THREADS) (&s_count[0][0])[i] = 0;
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x * RS_TILE + (uint64_t)warp * RS_WARP_TILE + lane;
     uint32_t key[RS_ROUNDS], val[RS_ROUNDS];
@@ -245,11 +255,11 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
         const bool ok = i < n;
         key[r] = ok ? keys_in[i] : 0;
         val[r] = ok ? vals_in[i] : 0;
-        if (ok) atomicAdd(&s_count[warp][(key[r] >> shift) & 0xFF], 1u);
+        if (ok) atomicAdd(&s_count[warp][(key[r] >> shift) & (ND - 1)], 1u);
     }
     __syncthreads();
-    {   // thread d turns the per-warp counts of digit d into output cursors (warp order = input order)
-        const uint32_t d = threadIdx.x;
+    // thread d turns the per-warp counts of digit d into output cursors (warp order = input order)
+    for (uint32_t d = threadIdx.x; d < ND; d += RS_THREADS) {
         uint32_t run = bucket_start[(uint64_t)d * n_tiles + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) {
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
 #pragma unroll
     for (int r = 0; r < RS_ROUNDS; ++r) {
         const bool ok = base + 32 * r < n;
-        const uint32_t d = ok ? (key[r] >> shift) & 0xFF : 0x100u + lane;  // invalid lanes never match anyone
+        const uint32_t d = ok ? (key[r] >> shift) & (ND - 1) : ND + lane;  // invalid lanes never match anyone
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
         const uint32_t rank = __popc(peers & ((1u << lane) - 1));
         uint32_t pos = 0;
@@ -277,30 +287,41 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
     }
 }
 
+// passes and digit width for `bits` significant key bits: as few passes as 9-bit digits allow, 8-bit digits otherwise
+void radix_plan(int bits, int* passes, int* width) {
+    *passes = (bits + 8) / 9;
+    *width = ((bits + *passes - 1) / *passes) <= 8 ? 8 : 9;
+}
+
 size_t radix_sort_temp_bytes(uint64_t n) {
     const uint64_t tiles = (n + RS_TILE - 1) / RS_TILE;
-    const uint64_t table = 256 * tiles;
+    const uint64_t table = 512 * tiles;
     return (size_t)(table * 4 * 2 + exclusive_scan_temp_bytes(table, 4) + 256);
 }
 
 // Sorts by bits [0, bits) of the key.  keys/vals ping-pong between the a and b buffers; *result_in_b tells where the
 // sorted data ended up.  n < 2^32.
+// d_n (optional, device): the real element count when only the device knows it; n is then the capacity the grid is sized for.
 int32_t radix_sort_pairs(gtgpu_ctx* ctx, uint64_t n, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
-                         int bits, void* d_temp, int* result_in_b) {
+                         int bits, void* d_temp, int* result_in_b, const uint64_t* d_n) {
     *result_in_b = 0;
     if (n == 0 || bits <= 0) return GTGPU_OK;
     if (n >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "radix_sort_pairs: too many elements");
+    int passes, width;
+    radix_plan(std::min(bits, 32), &passes, &width);
     const uint32_t tiles = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
-    const uint64_t table = 256ull * tiles;
+    const uint64_t table = ((uint64_t)1 << width) * tiles;
     uint32_t* hist = reinterpret_cast<uint32_t*>(d_temp);
-    uint32_t* starts = hist + table;
-    void* scan_tmp = starts + table;
+    uint32_t* starts = hist + 512ull * tiles;
+    void* scan_tmp = starts + 512ull * tiles;
     uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
-    for (int shift = 0; shift < bits; shift += 8) {
-        radix_hist_kernel<<<tiles, RS_THREADS, 0, ctx->stream>>>(ki, n, shift, tiles, hist);
+    for (int p = 0, shift = 0; p < passes; ++p, shift += width) {
+        if (width == 8) radix_hist_kernel<8><<<tiles, RS_THREADS, 0, ctx->stream>>>(ki, n, d_n, shift, tiles, hist);
+        else radix_hist_kernel<9><<<tiles, RS_THREADS, 0, ctx->stream>>>(ki, n, d_n, shift, tiles, hist);
         ctx->launches++;
         GT_TRY(exclusive_scan<uint32_t>(ctx, hist, starts, table, scan_tmp));
-        radix_scatter_kernel<<<tiles, RS_THREADS, 0, ctx->stream>>>(ki, vi, n, shift, tiles, starts, ko, vo);
+        if (width == 8) radix_scatter_kernel<8><<<tiles, RS_THREADS, 0, ctx->stream>>>(ki, vi, n, d_n, shift, tiles, starts, ko, vo);
+        else radix_scatter_kernel<9><<<tiles, RS_THREADS, 0, ctx->stream>>>(ki, vi, n, d_n, shift, tiles, starts, ko, vo);
         ctx->launches++;
         std::swap(ki, ko);
         std::swap(vi, vo);

@@ -173,9 +173,9 @@ int32_t gtgpu_tokenize_fragments(gtgpu_index* index, uint64_t n, const uint32_t*
                                  uint64_t* out_barcode_offsets, gtgpu_buf** out_ids);
 
 /* gtgpu_tokenize_fragments with everything device-resident and asynchronous on the ctx stream: d_out_barcode_offsets has
- * n_barcodes + 1 entries, d_out_ids room for ids_capacity ids (ids beyond it are not written), *d_out_total (device u64)
- * receives the number of ids — one per hit, one unk_id per fragment without a hit — or UINT64_MAX when the fragments
- * produced more than n + n/4 + 1024 hits (use the host entry point, which re-runs with an exact buffer). */
+ * n_barcodes + 1 entries, d_out_ids room for ids_capacity >= n ids, *d_out_total (device u64) receives the number of ids
+ * — one per hit, one unk_id per fragment without a hit — or UINT64_MAX when they did not fit ids_capacity (the output is
+ * then incomplete; the host entry point re-runs with an exact buffer by itself). */
 int32_t gtgpu_tokenize_fragments_dev(gtgpu_index* index, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
                                      const uint32_t* d_end, const uint32_t* d_barcode_id, uint32_t n_barcodes,
                                      uint32_t unk_id, uint64_t* d_out_barcode_offsets, uint32_t* d_out_ids,

@@ -394,6 +394,47 @@ def test_fragments_random_differential(ctx, kind):
 
 
 @pytest.mark.parametrize("kind", ["bits", "ailist"])
+@pytest.mark.parametrize("style,n_bc", [("peaks", 70_000), ("nested", 513), ("overlap", 40)])
+def test_fragments_device_resident_entry_point(ctx, kind, style, n_bc):
+    """gtgpu_tokenize_fragments_dev (no host copies, no synchronisation) and the host entry point against the oracle:
+    lean universes, multi-hit universes (pool lists / generic walk under the per-query [unk] rule), barcode counts that
+    need one, two (9-bit digits) and three radix passes, degenerate and unknown-chromosome fragments, a partial last tile."""
+    import torch
+    rng = np.random.default_rng(zlib.crc32(f"fragdev/{kind}/{style}".encode()))
+    n_chroms = 4
+    offs, s, e, v = _random_index(rng, n_chroms, 5000, style)
+    g, o = _both(ctx, kind, offs, s, e, v)
+    n = 150_001
+    qc, qs, qe = _random_queries(rng, n_chroms, n, degenerate=True)
+    bc = (rng.integers(0, n_bc, n) ** 2 // n_bc).astype(np.uint32)
+    unk = 5000
+    o_off, o_ids = o.tokenize_fragments(qc, qs, qe, bc, n_bc, unk)
+    h_off, h_ids = g.tokenize_fragments(qc, qs, qe, bc, n_bc, unk)
+    assert np.array_equal(h_off, o_off) and np.array_equal(h_ids, o_ids)
+    dev = torch.device("cuda", 0)
+    t = [torch.from_numpy(a.view(np.int32)).to(dev) for a in (qc, qs, qe, bc)]
+    cap = int(o_off[-1]) + 17
+    d_ids = torch.zeros(cap, dtype=torch.int32, device=dev)
+    d_bco = torch.zeros(n_bc + 1, dtype=torch.int64, device=dev)
+    d_total = torch.zeros(1, dtype=torch.int64, device=dev)
+    g.tokenize_fragments_dev(n, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), n_bc, unk, d_bco.data_ptr(),
+                             d_ids.data_ptr(), cap, d_total.data_ptr())
+    ctx.synchronize()
+    assert int(d_total.item()) == int(o_off[-1])
+    assert np.array_equal(d_bco.cpu().numpy().astype(np.uint64), o_off)
+    assert np.array_equal(d_ids[:int(o_off[-1])].cpu().numpy().view(np.uint32), o_ids)
+    assert np.array_equal(t[3].cpu().numpy().view(np.uint32), bc)      # the caller's barcode array is not modified
+    # a buffer that cannot hold the tokens is reported, not overrun
+    small = n + 3
+    if int(o_off[-1]) > small:
+        d_small = torch.zeros(small + 8, dtype=torch.int32, device=dev)
+        g.tokenize_fragments_dev(n, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), n_bc, unk, d_bco.data_ptr(),
+                                 d_small.data_ptr(), small, d_total.data_ptr())
+        ctx.synchronize()
+        assert int(d_total.item()) == -1 and int(d_small[small:].abs().sum().item()) == 0
+
+
+@pytest.mark.parametrize("kind", ["bits", "ailist"])
 def test_tokenize_files_pipelined_chunks(ctx, kind, monkeypatch):
     """The chunked H2D / kernel / D2H pipeline of gtgpu_tokenize_files (forced here with 4 096-query chunks) is
     bit-identical to the single-launch path, with file boundaries on, before and after chunk boundaries."""
