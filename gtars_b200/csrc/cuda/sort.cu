@@ -208,10 +208,11 @@ int32_t inclusive_max_scan_u64(gtgpu_ctx* ctx, const unsigned long long* d_in, u
 }
 
 // ---- radix sort -----------------------------------------------------------------------------------------------------------
-constexpr int RS_THREADS = 256;
+constexpr int RS_THREADS = 512;
 constexpr int RS_ROUNDS = 16;                          // elements per lane
 constexpr int RS_WARP_TILE = 32 * RS_ROUNDS;           // 512 consecutive elements per warp
-constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;        // 4 096 per block
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;        // 8 192 per block
+constexpr int RS_WARPS = RS_THREADS / 32;
 
 // DB = digit width of the pass: 8 bits, or 9 when that saves a whole pass (17-18 and 25-27 significant bits)
 template <int DB>
@@ -220,72 +221,126 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* 
                                                                 uint32_t n_tiles, uint32_t* __restrict__ hist) {
     constexpr uint32_t ND = 1u << DB;
     const uint64_t n = d_n ? min((uint64_t)*d_n, n_cap) : n_cap;  // element count known on the device only (no host sync)
-    __shared__ uint32_t s_hist[ND];
-    for (uint32_t d = threadIdx.x; d < ND; d += RS_THREADS) s_hist[d] = 0;
+    // one histogram per warp (no contention between warps; a warp's 32 lanes rarely share a digit), summed at the end
+    __shared__ uint32_t s_hist[RS_WARPS / 2][ND];
+    for (uint32_t i = threadIdx.x; i < (RS_WARPS / 2) * ND; i += RS_THREADS) (&s_hist[0][0])[i] = 0;
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
+    uint32_t* mine = s_hist[(threadIdx.x >> 5) >> 1];
 #pragma unroll 4
     for (int k = 0; k < RS_ROUNDS; ++k) {
         const uint64_t i = base + (uint64_t)k * RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&s_hist[(keys[i] >> shift) & (ND - 1)], 1u);
+        if (i < n) atomicAdd(&mine[(__ldcs(keys + i) >> shift) & (ND - 1)], 1u);
     }
     __syncthreads();
-    for (uint32_t d = threadIdx.x; d < ND; d += RS_THREADS)
-        hist[(uint64_t)d * n_tiles + blockIdx.x] = s_hist[d];  // digit-major: one scan orders everything
+    for (uint32_t d = threadIdx.x; d < ND; d += RS_THREADS) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS / 2; ++w) t += s_hist[w][d];
+        hist[(uint64_t)d * n_tiles + blockIdx.x] = t;  // digit-major: one scan orders everything
+    }
 }
 
+// Scatter of one pass.  A block sorts its 8 192-element tile by digit in SHARED memory first (stable: per-warp ranks from
+// __match_any_sync round by round, warps in order), then writes the tile out digit by digit — a digit's elements of one
+// tile go to consecutive addresses, so the global stores are coalesced runs (32-64 B per digit and tile on average)
+// instead of 8 192 single words.  The first version stored every element straight from its ranking round: 16 scattered
+// 4-byte stores per lane and array, 9.8 ms per 2.5e8 pairs; this one: see profiles/r02.
 template <int DB>
-__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
+__global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
                                                                    const uint32_t* __restrict__ vals_in, uint64_t n_cap,
                                                                    const uint64_t* __restrict__ d_n, int shift,
                                                                    uint32_t n_tiles, const uint32_t* __restrict__ bucket_start,
                                                                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
-    constexpr int WARPS = RS_THREADS / 32;
     constexpr uint32_t ND = 1u << DB;
     const uint64_t n = d_n ? min((uint64_t)*d_n, n_cap) : n_cap;
-    __shared__ uint32_t s_count[WARPS][ND];  // first per-warp digit counts, then the running output cursor per (warp, digit)
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t i = threadIdx.x; i < WARPS * ND; i += RS_THREADS) (&s_count[0][0])[i] = 0;
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    uint32_t* s_key = s_mem;                        // [RS_TILE] the tile, sorted by digit
+    uint32_t* s_val = s_mem + RS_TILE;              // [RS_TILE]
+    uint32_t* s_cnt = s_mem + 2 * RS_TILE;          // [RS_WARPS][ND] per-warp digit counts, then each warp's first slot per digit
+    uint32_t* s_dbase = s_cnt + RS_WARPS * ND;      // [ND] first slot of each digit in the sorted tile
+    uint32_t* s_gbase = s_dbase + ND;               // [ND] global position of the digit's first element minus s_dbase
+    __shared__ uint32_t s_wsum[RS_WARPS];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t tile0 = (uint64_t)blockIdx.x * RS_TILE;
+    if (tile0 >= n) return;
+    const uint32_t tile_n = (uint32_t)min((uint64_t)RS_TILE, n - tile0);
+    for (uint32_t i = tid; i < RS_WARPS * ND; i += RS_THREADS) s_cnt[i] = 0;
     __syncthreads();
-    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE + (uint64_t)warp * RS_WARP_TILE + lane;
-    uint32_t key[RS_ROUNDS], val[RS_ROUNDS];
+    // ---- 1. rank inside the warp, round by round (stable) ----------------------------------------------------------------
+    const uint32_t wbase = warp * RS_WARP_TILE + lane;
+    uint32_t key[RS_ROUNDS];
+    uint16_t rank[RS_ROUNDS];
+    uint32_t* my_cnt = s_cnt + warp * ND;
 #pragma unroll
     for (int r = 0; r < RS_ROUNDS; ++r) {
-        const uint64_t i = base + 32 * r;
-        const bool ok = i < n;
-        key[r] = ok ? keys_in[i] : 0;
-        val[r] = ok ? vals_in[i] : 0;
-        if (ok) atomicAdd(&s_count[warp][(key[r] >> shift) & (ND - 1)], 1u);
+        const uint32_t j = wbase + 32 * r;
+        key[r] = j < tile_n ? __ldcs(keys_in + tile0 + j) : 0;
     }
-    __syncthreads();
-    // thread d turns the per-warp counts of digit d into output cursors (warp order = input order)
-    for (uint32_t d = threadIdx.x; d < ND; d += RS_THREADS) {
-        uint32_t run = bucket_start[(uint64_t)d * n_tiles + blockIdx.x];
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            const uint32_t c = s_count[w][d];
-            s_count[w][d] = run;
-            run += c;
-        }
-    }
-    __syncthreads();
 #pragma unroll
     for (int r = 0; r < RS_ROUNDS; ++r) {
-        const bool ok = base + 32 * r < n;
+        const bool ok = wbase + 32 * r < tile_n;
         const uint32_t d = ok ? (key[r] >> shift) & (ND - 1) : ND + lane;  // invalid lanes never match anyone
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-        const uint32_t rank = __popc(peers & ((1u << lane) - 1));
-        uint32_t pos = 0;
-        if (ok) pos = s_count[warp][d] + rank;
+        const uint32_t before = __popc(peers & ((1u << lane) - 1));
+        uint32_t prev = 0;
+        if (ok) prev = my_cnt[d];
         __syncwarp();
-        if (ok && rank == 0) s_count[warp][d] += __popc(peers);
+        if (ok && before == 0) my_cnt[d] = prev + __popc(peers);
         __syncwarp();
-        if (ok) {
-            keys_out[pos] = key[r];
-            vals_out[pos] = val[r];
+        rank[r] = (uint16_t)(prev + before);
+    }
+    __syncthreads();
+    // ---- 2. digit totals -> first slot of every digit, and of every (warp, digit) ------------------------------------------
+    uint32_t tot = 0;  // thread d: tile total of digit d (ND <= RS_THREADS)
+    if (tid < ND) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            const uint32_t c = s_cnt[w * ND + tid];
+            s_cnt[w * ND + tid] = run;  // elements of this digit in earlier warps
+            run += c;
+        }
+        tot = run;
+    }
+    uint32_t incl = tot;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, k);
+        if (lane >= (uint32_t)k) incl += t;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    if (tid < ND) {
+        uint32_t before = 0;
+        for (uint32_t w = 0; w < warp; ++w) before += s_wsum[w];
+        const uint32_t first = before + incl - tot;
+        s_dbase[tid] = first;
+        s_gbase[tid] = bucket_start[(uint64_t)tid * n_tiles + blockIdx.x] - first;  // wrapping on purpose
+    }
+    __syncthreads();
+    // ---- 3. the tile, sorted by digit, in shared memory ------------------------------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        if (wbase + 32 * r < tile_n) {
+            const uint32_t d = (key[r] >> shift) & (ND - 1);
+            const uint32_t p = s_dbase[d] + my_cnt[d] + rank[r];
+            s_key[p] = key[r];
+            s_val[p] = __ldcs(vals_in + tile0 + wbase + 32 * r);  // values are only touched here: 16 fewer live registers while ranking
         }
     }
+    __syncthreads();
+    // ---- 4. write out: consecutive threads = consecutive slots = (inside a digit) consecutive global addresses ------------------
+    for (uint32_t p = tid; p < tile_n; p += RS_THREADS) {
+        const uint32_t k = s_key[p];
+        const uint32_t dst = s_gbase[(k >> shift) & (ND - 1)] + p;
+        keys_out[dst] = k;
+        vals_out[dst] = s_val[p];
+    }
 }
+
+template <int DB>
+static constexpr size_t radix_scatter_smem() { return (size_t)(2 * RS_TILE + RS_WARPS * (1 << DB) + 2 * (1 << DB)) * 4; }
 
 // passes and digit width for `bits` significant key bits: as few passes as 9-bit digits allow, 8-bit digits otherwise
 void radix_plan(int bits, int* passes, int* width) {
@@ -309,6 +364,9 @@ int32_t radix_sort_pairs(gtgpu_ctx* ctx, uint64_t n, uint32_t* keys_a, uint32_t*
     if (n >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "radix_sort_pairs: too many elements");
     int passes, width;
     radix_plan(std::min(bits, 32), &passes, &width);
+    // > 48 KB of dynamic shared memory is an opt-in per kernel and per device: set it on every call (cheap)
+    GT_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)radix_scatter_smem<8>()));
+    GT_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)radix_scatter_smem<9>()));
     const uint32_t tiles = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
     const uint64_t table = ((uint64_t)1 << width) * tiles;
     uint32_t* hist = reinterpret_cast<uint32_t*>(d_temp);
@@ -320,8 +378,10 @@ int32_t radix_sort_pairs(gtgpu_ctx* ctx, uint64_t n, uint32_t* keys_a, uint32_t*
         else radix_hist_kernel<9><<<tiles, RS_THREADS, 0, ctx->stream>>>(ki, n, d_n, shift, tiles, hist);
         ctx->launches++;
         GT_TRY(exclusive_scan<uint32_t>(ctx, hist, starts, table, scan_tmp));
-        if (width == 8) radix_scatter_kernel<8><<<tiles, RS_THREADS, 0, ctx->stream>>>(ki, vi, n, d_n, shift, tiles, starts, ko, vo);
-        else radix_scatter_kernel<9><<<tiles, RS_THREADS, 0, ctx->stream>>>(ki, vi, n, d_n, shift, tiles, starts, ko, vo);
+        if (width == 8)
+            radix_scatter_kernel<8><<<tiles, RS_THREADS, radix_scatter_smem<8>(), ctx->stream>>>(ki, vi, n, d_n, shift, tiles, starts, ko, vo);
+        else
+            radix_scatter_kernel<9><<<tiles, RS_THREADS, radix_scatter_smem<9>(), ctx->stream>>>(ki, vi, n, d_n, shift, tiles, starts, ko, vo);
         ctx->launches++;
         std::swap(ki, ko);
         std::swap(vi, vo);
