@@ -221,10 +221,16 @@ class Dist:
             import torch.distributed as dist
             self.dist = dist
             dist.init_process_group("nccl", device_id=dev)
+            self.cpu_group = dist.new_group(backend="gloo")  # host-side waits that keep the waiting ranks off their GPUs
 
     def barrier(self):
         if self.world > 1:
             self.dist.barrier()
+
+    def host_barrier(self):
+        """Barrier on the CPU (gloo): ranks waiting here launch nothing on their GPU (an NCCL barrier spins a kernel)."""
+        if self.world > 1:
+            self.dist.barrier(group=self.cpu_group)
 
     def _reduce(self, x, op):
         if self.world == 1:
@@ -795,6 +801,42 @@ def main():
                                    "NOT inside ms_per_step",
                            "value_with_marshal": total_queries / (e2e_s + marshal_s), "unit": UNIT}}
         assert e2e_total == hits + n_empty_files
+        if world > 1:
+            # The drop-in form of multi-GPU use: ONE process (rank 0) drives all N GPUs through a multi-device context
+            # (gtgpu_init_multi) and the same entry point; its 1e9 queries are dealt to the devices chunk by chunk (strong
+            # scaling of one caller's batch).  The other ranks wait on the host meanwhile, their GPUs idle.
+            torch.cuda.synchronize()
+            D.barrier()
+            try:
+                if rank == 0:
+                    mctx = ffi.Context(devices=list(range(world)))
+                    mindex = ffi.Index(mctx, kind, offs, s, e, v)
+
+                    def m_call():
+                        return mindex.tokenize_files_compact(h_fo, h_run_off, h_run_chr, h_start, h_w16, h_wide_idx, h_wide_end, u["unk_id"],
+                                                             keep_buf=True)
+                    off_m, buf_m = m_call()
+                    ids_m = np.ctypeslib.as_array(C.cast(L.gtgpu_buf_data(buf_m), C.POINTER(C.c_uint32)), shape=(int(off_m[-1]),))
+                    same = bool(int(off_m[-1]) == e2e_total and (n_empty_files > 0 or (
+                        np.array_equal(ids_m[:k_chk], d_ids[:k_chk].cpu().numpy().view(np.uint32))
+                        and np.array_equal(ids_m[-k_chk:], d_ids[hits - k_chk:hits].cpu().numpy().view(np.uint32)))))
+                    del ids_m
+                    L.gtgpu_buf_free(buf_m)
+                    t0 = time.perf_counter()
+                    for _ in range(args.steps):
+                        off_m, buf_m = m_call()
+                        L.gtgpu_buf_free(buf_m)
+                    m_s = (time.perf_counter() - t0) / args.steps
+                    e2e["single_process_multi_device"] = {
+                        "devices": world, "queries": n, "ms_per_call": m_s * 1e3, "value": n / m_s, "unit": UNIT,
+                        "ids_match_device_resident_path": same, "scaling": "strong (one caller's batch over all devices)",
+                        "api": "gtgpu_init_multi + gtgpu_tokenize_files_compact: chunks dealt round-robin to the devices, ids land "
+                               "at their final offsets in one pinned buffer"}
+                    mindex.close()
+                    mctx.close()
+            except Exception as ex:
+                e2e["single_process_multi_device"] = {"error": repr(ex)}
+            D.host_barrier()
         ffi.pinned_free(h_start)
         ffi.pinned_free(h_w16)
         if not compact:

@@ -103,7 +103,9 @@ __global__ void ingest_parse_lines_kernel(uint32_t n_lines, uint32_t n_newlines,
     for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < n_lines; li += stride) {
         uint32_t a = li ? nl_pos[li - 1] + 1 : 0;
         uint32_t b = li < n_newlines ? nl_pos[li] : (uint32_t)n_bytes;
-        if (b > a && text[b - 1] == '\r') --b;  // BufRead::lines strips "\r\n"
+        // BufRead::lines strips "\n" and a "\r" right before it; a final line WITHOUT a newline keeps its '\r' (the reference then
+        // fails to parse the field, and so do we)
+        if (li < n_newlines && b > a && text[b - 1] == '\r') --b;
         uint32_t k = 0, c = GTGPU_UNKNOWN_CHROM, s = 0, e = 0;
         if (has_prefix(text, a, b, "browser", 7) || has_prefix(text, a, b, "track", 5) || has_prefix(text, a, b, "#", 1)) {
             k = 0;
@@ -211,7 +213,7 @@ __global__ void ingest_parse_fragments_kernel(uint32_t n_lines, uint32_t n_newli
     for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < n_lines; li += stride) {
         uint32_t a = li ? nl_pos[li - 1] + 1 : 0;
         uint32_t b = li < n_newlines ? nl_pos[li] : (uint32_t)n_bytes;
-        if (b > a && text[b - 1] == '\r') --b;
+        if (li < n_newlines && b > a && text[b - 1] == '\r') --b;  // only a '\r' in front of a '\n' is part of the line ending
         uint32_t k = 0, c = GTGPU_UNKNOWN_CHROM, s = 0, e = 0, bo = 0, bl = 0;
         unsigned long long h = 1469598103934665603ull;
         if (!(b > a && text[a] == '#')) {

@@ -29,7 +29,8 @@ std::vector<std::string> read_lines(const std::string& path) {
         size_t nl = data.find('\n', pos);
         size_t end = nl == std::string::npos ? data.size() : nl;
         lines.emplace_back(data, pos, end - pos);
-        if (!lines.back().empty() && lines.back().back() == '\r') lines.back().pop_back();
+        // BufRead::lines: only a '\r' in front of the stripped '\n' goes; a last line without a newline keeps it
+        if (nl != std::string::npos && !lines.back().empty() && lines.back().back() == '\r') lines.back().pop_back();
         pos = nl == std::string::npos ? data.size() : nl + 1;
     }
     return lines;
@@ -102,7 +103,12 @@ std::string read_file_bytes(const std::string& path) {
         char buf[1 << 16];
         int n;
         while ((n = gzread(f, buf, sizeof buf)) > 0) data.append(buf, n);
-        gzclose(f);
+        int zerr = Z_OK;
+        const char* zmsg = n < 0 ? gzerror(f, &zerr) : nullptr;  // a truncated / corrupt stream is an error, not an early EOF
+        const std::string why = zmsg ? zmsg : "";
+        const int closed = gzclose(f);
+        if (n < 0 || closed != Z_OK)  // Z_BUF_ERROR from gzclose = the stream ended in the middle of a gzip member (truncated)
+            throw Error("Failed to read gzip file: \"" + path + "\"" + (why.empty() ? "" : ": " + why));
     } else {
         std::ifstream f(path, std::ios::binary | std::ios::ate);
         if (!f) throw Error("Failed to open file: \"" + path + "\"");
@@ -822,9 +828,16 @@ std::vector<std::pair<std::string, std::map<uint32_t, uint32_t>>> barcode_scorin
     check(gtgpu_score_barcodes(consensus.index(), bc.size(), pf.q.chr.data(), pf.q.start.data(), pf.q.end.data(), bc.data(),
                                (uint32_t)barcodes.size(), offsets.data(), &peaks.buf, &counts.buf),
           "gtgpu_score_barcodes");
+    // Key set of the reference: `barcode_counts.entry(barcode).or_default()` runs whenever ConsensusSet::find_overlaps returns
+    // Some(..), i.e. whenever the fragment's chromosome has a tree in the consensus — also when nothing overlaps
+    // (gtars-scoring/src/files.rs:106-129, fragment_scoring.rs:146-153).  So a barcode seen on a consensus chromosome gets an
+    // entry even if its inner map stays empty; only barcodes seen solely on unknown chromosomes are absent.
+    std::vector<uint8_t> seen_on_known(barcodes.size(), 0);
+    for (size_t i = 0; i < bc.size(); ++i)
+        if (pf.q.chr[i] != GTGPU_UNKNOWN_CHROM) seen_on_known[bc[i]] = 1;
     std::vector<std::pair<std::string, std::map<uint32_t, uint32_t>>> out;
     for (size_t b = 0; b < barcodes.size(); ++b) {
-        if (offsets[b] == offsets[b + 1]) continue;  // the reference only creates an entry on the first overlap
+        if (!seen_on_known[b]) continue;
         std::map<uint32_t, uint32_t> m;
         for (uint64_t k = offsets[b]; k < offsets[b + 1]; ++k) m[peaks.data()[k]] = counts.data()[k];
         out.emplace_back(barcodes[b], std::move(m));

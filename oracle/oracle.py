@@ -61,6 +61,8 @@ def lib():
         "orc_tokenize_fragments": (vp, [vp, u64, vp, vp, vp, vp, u32, u32, vp, vp]),
         "orc_score_matrix": (None, [vp, u64, vp, vp, vp, vp, cint, u64, vp, cint]),
         "orc_score_barcodes": (vp, [vp, u64, vp, vp, vp, vp, u32, vp]),
+        "orc_barcode_scoring_file": (vp, [vp, C.c_char_p]), "orc_bscores_free": (None, [vp]), "orc_bscores_n": (u64, [vp]),
+        "orc_bscores_barcode": (C.c_char_p, [vp, u64]), "orc_bscores_len": (u64, [vp, u64]), "orc_bscores_pairs": (vp, [vp, u64]),
         "orc_consensus_from_bed": (vp, [C.c_char_p]),
         "orc_consensus_free": (None, [vp]),
         "orc_consensus_len": (u64, [vp]),
@@ -265,6 +267,28 @@ def region_scoring_files(consensus_path, fragment_paths, mode=SCORE_ATAC):
         arr = (C.c_char_p * len(fragment_paths))(*[os.fsencode(p) for p in fragment_paths])
         if L.orc_region_scoring_files(h, len(fragment_paths), arr, mode, _ptr(out)) != 0:
             raise ValueError(_err())
+        return out
+    finally:
+        L.orc_consensus_free(h)
+
+
+def barcode_scoring_file(consensus_path, fragment_path):
+    """barcode_scoring_from_fragments (fragment_scoring.rs:126-155) with the reference's key set: {barcode: {peak: count}};
+    a barcode whose fragments lie on consensus chromosomes but overlap nothing maps to {} (see gtars_oracle.cpp)."""
+    L = lib()
+    h = L.orc_consensus_from_bed(os.fsencode(consensus_path))
+    if not h:
+        raise ValueError(_err())
+    try:
+        r = L.orc_barcode_scoring_file(h, os.fsencode(fragment_path))
+        if not r:
+            raise ValueError(_err())
+        out = {}
+        for i in range(L.orc_bscores_n(r)):
+            k = L.orc_bscores_len(r, i)
+            pairs = np.ctypeslib.as_array(C.cast(L.orc_bscores_pairs(r, i), C.POINTER(C.c_uint32)), shape=(k,)).copy() if k else np.zeros(0, np.uint32)
+            out[L.orc_bscores_barcode(r, i).decode()] = {int(p): int(c) for p, c in pairs.reshape(-1, 2)}
+        L.orc_bscores_free(r)
         return out
     finally:
         L.orc_consensus_free(h)

@@ -200,14 +200,37 @@ def test_scoring_kat_through_api(api, golden, fixture_dir):
     from oracle import oracle as orc
     chip = api.region_scoring_from_fragments(files, cons, api.SCORING_CHIP)
     assert np.array_equal(chip, orc.region_scoring_files(os.path.join(fixture_dir, k["consensus"]), files, orc.SCORE_CHIP))
-    # sparse per-barcode counts of the first file: sums must equal the Chip row; every barcode listed has a hit
+    # sparse per-barcode counts of the first file: the oracle's dict (incl. its key set), and sums equal to the Chip row
     sparse = api.barcode_scoring_from_fragments(files[0], cons)
+    assert sparse == orc.barcode_scoring_file(os.path.join(fixture_dir, k["consensus"]), files[0])
     tot = np.zeros(k["cols"], dtype=np.int64)
     for bc, counts in sparse.items():
-        assert counts
         for peak, c in counts.items():
             tot[peak] += c
     assert tot.tolist() == chip[0].tolist()
+
+
+def test_barcode_scoring_key_set_matches_reference(api, tmp_path):
+    """fragment_scoring.rs:146-153 + files.rs:106-129: a barcode gets an entry as soon as one of its fragments lies on a
+    chromosome the consensus knows — even when nothing overlaps (empty inner map) — and none when it was only ever seen on
+    unknown chromosomes."""
+    from oracle import oracle as orc
+    cons_path, frag_path = str(tmp_path / "consensus.bed"), str(tmp_path / "frags.tsv")
+    with open(cons_path, "w") as f:
+        f.write("chr1\t100\t200\nchr1\t300\t400\nchr2\t50\t80\n")
+    with open(frag_path, "w") as f:
+        f.write("# a comment line\n"
+                "chr1\t120\t130\tHIT\t1\n"          # overlaps peak 0
+                "chr1\t1000\t1100\tMISS\t1\n"       # known chromosome, no overlap  -> {}
+                "chr9\t120\t130\tGHOST\t1\n"        # unknown chromosome only      -> absent
+                "chr9\t1\t2\tHIT\t1\n"
+                "chr2\t60\t70\tHIT\t2\n"
+                "chr1\t150\t350\tBOTH\t1\n"         # peaks 0 and 1
+                "chr1\t150\t160\tBOTH\t1\n")
+    want = orc.barcode_scoring_file(cons_path, frag_path)
+    assert want == {"HIT": {0: 1, 2: 1}, "MISS": {}, "BOTH": {0: 2, 1: 1}}
+    got = api.barcode_scoring_from_fragments(frag_path, api.ConsensusSet(cons_path))
+    assert got == want and "GHOST" not in got
 
 
 def test_indexed_region_set_kats(api, golden):
@@ -339,12 +362,23 @@ def test_parse_bed_errors_and_tokenize_bed_file(api, fixture_dir, tmp_path):
     for name, text in [("bad_start.bed", "chr1\t1\t2\nchr1\tx\t5\n"), ("neg.bed", "chr1\t-1\t2\n"),
                        ("two_cols.bed", "chr1\t1\t2\nchr1\t7\n"), ("blank.bed", "chr1\t1\t2\n\nchr1\t3\t4\n"),
                        ("overflow.bed", "chr1\t1\t4294967296\n"), ("only_comments.bed", "# nothing\ntrack x\n"),
-                       ("space.bed", "chr1\t 1\t2\n")]:
+                       ("space.bed", "chr1\t 1\t2\n"),
+                       # BufRead::lines only drops a '\r' that precedes a '\n': a last line without newline keeps it -> "2\r"
+                       ("cr_no_newline.bed", "chr1\t1\t2\r\nchr1\t1\t2\r")]:
         p = write(name, text)
         with pytest.raises(api.GtarsError):
             api.parse_bed_file(p, ["chr1"])
         with pytest.raises(ValueError):
             orc.regionset_from_file(p)                               # the reference rejects the same files
+    c, s, e = api.parse_bed_file(write("crlf_last.bed", "chr1\t5\t6\r\nchr1\t1\t2\r\n"), ["chr1"])
+    assert (c.tolist(), s.tolist(), e.tolist()) == ([0, 0], [1, 5], [2, 6])
+    # a truncated gzip stream is an error, not a shorter file
+    import gzip
+    full = gzip.compress(("chr1\t1\t2\n" * 20000).encode())
+    trunc = str(tmp_path / "trunc.bed.gz")
+    open(trunc, "wb").write(full[: len(full) // 2])
+    with pytest.raises(api.GtarsError):
+        api.RegionSet(trunc)
     c, s, e = api.parse_bed_file(write("edge.bed", "chr1\t4294967295\t+0\nchr1\t0\t1"), ["chr1"])
     assert (c.tolist(), s.tolist(), e.tolist()) == ([0, 0], [0, 4294967295], [1, 0])
     # text -> token ids entirely on the device == encode(RegionSet(path))

@@ -355,3 +355,16 @@ def test_igd_file_format_roundtrip(tmp_path):
             a = g.count_overlaps(c_old, q[0], q[1])
             bb = h.count_overlaps(c_new, q[0], q[1])
             assert a[0] == bb[0] and list(a[1]) == list(bb[1])
+
+
+def test_barcode_scoring_file_key_set(tmp_path):
+    """fragment_scoring.rs:146-153 + files.rs:106-129 restated: an entry per barcode seen on a consensus chromosome (possibly
+    empty), none for barcodes seen on unknown chromosomes only; '#' lines skipped."""
+    from oracle import oracle as orc
+    cons, frags = str(tmp_path / "c.bed"), str(tmp_path / "f.tsv")
+    with open(cons, "w") as f:
+        f.write("chr1\t100\t200\nchr1\t300\t400\nchr2\t50\t80\n")
+    with open(frags, "w") as f:
+        f.write("#header\nchr1\t120\t130\tHIT\t1\nchr1\t1000\t1100\tMISS\t1\nchr9\t120\t130\tGHOST\t1\n"
+                "chr2\t60\t70\tHIT\t2\nchr1\t150\t350\tBOTH\t1\nchr1\t150\t160\tBOTH\t1\n")
+    assert orc.barcode_scoring_file(cons, frags) == {"HIT": {0: 1, 2: 1}, "MISS": {}, "BOTH": {0: 2, 1: 1}}
