@@ -430,10 +430,13 @@ class Igd:
     def count_region_hits(self, set_offsets, chr, start, end, min_overlap=1):
         return self._count(lib().gtgpu_igd_count_region_hits, set_offsets, chr, start, end, min_overlap)
 
-    def count_sharded(self, binary, n_files_global, set_offsets, chr, start, end, min_overlap=1):
+    def count_sharded(self, binary, n_files_global, set_offsets, chr, start, end, min_overlap=1, out=None):
+        """`out` (optional): a caller-owned uint64 [n_sets, n_files_global] array, e.g. pinned memory from pinned_empty."""
         so = _arr(set_offsets, np.uint64)
         chr, start, end = _arr(chr, np.uint32), _arr(start, np.uint32), _arr(end, np.uint32)
-        out = np.zeros((len(so) - 1, n_files_global), dtype=np.uint64)
+        if out is None:
+            out = np.zeros((len(so) - 1, n_files_global), dtype=np.uint64)
+        assert out.dtype == np.uint64 and out.shape == (len(so) - 1, n_files_global) and out.flags.c_contiguous
         check(lib().gtgpu_igd_count_sharded(self.ctx._h, self._h, 1 if binary else 0, n_files_global, len(so) - 1, _p(so),
                                             _p(chr), _p(start), _p(end), min_overlap, _p(out)))
         return out
