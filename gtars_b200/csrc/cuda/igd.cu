@@ -15,6 +15,7 @@
 // min_overlap <= 0 is tile-dependent in the reference (touching records count only when co-tiled) and is rejected.
 #include <algorithm>
 #include <condition_variable>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <numeric>
@@ -210,11 +211,30 @@ __global__ void __launch_bounds__(256) igd_count_kernel(IgdView v, uint64_t n, c
         const uint32_t ub = lb_i32(v.start + o, v.lut + __ldg(v.lut_s_off + c), __ldg(v.nb_s + c), len, v.shift, e);
         const uint32_t lo = lb_i32(v.pmax + o, v.lut + __ldg(v.lut_p_off + c), __ldg(v.nb_p + c), len, v.shift, s + 1);
         unsigned long long* row = out + (uint64_t)__ldg(set_of + q) * v.n_files;
-        for (uint32_t i = o + lo + lane; i < o + ub; i += 32) {
-            const int32_t rs = __ldg(v.start + i), re = __ldg(v.end + i);
-            if (min(re, e) - max(rs, s) < m) continue;
-            if (BINARY && (int64_t)__ldg(v.psame + i) - s >= m) continue;  // an earlier record of this file already hit
-            atomicAdd(row + __ldg(v.file + i), 1ull);
+        // 128 candidates per round: every lane requests its four records (start, end, file, psame — sixteen independent loads)
+        // before it tests any of them: 24.7 -> 18.9 ms on the LOLA configuration (1 k x 10 k sets).  What remains is the L2's
+        // atomic rate (1.7e9 hits in 18.9 ms = 9e10 64-bit atomics / s): walking the queries in genome order (radix-sorted,
+        // L2-resident record segments) did not change the kernel time (18.4 ms), and a variant that kept the current set's
+        // matrix row in shared memory (32-bit shared atomics, one flush per 4 096 queries) was slower (41 ms) — both measured
+        // in round 2 and dropped.
+        for (uint32_t base = o + lo; base < o + ub; base += 128) {
+            int32_t rs[4], re[4], ps[4];
+            uint32_t fl[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t i = base + 32 * k + lane;
+                const bool ok = i < o + ub;
+                rs[k] = ok ? __ldg(v.start + i) : 0;
+                re[k] = ok ? __ldg(v.end + i) : 0;  // an absent record [0, 0) never reaches m >= 1 bp of overlap
+                fl[k] = ok ? __ldg(v.file + i) : 0;
+                ps[k] = (BINARY && ok) ? __ldg(v.psame + i) : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (min(re[k], e) - max(rs[k], s) < m) continue;
+                if (BINARY && (int64_t)ps[k] - s >= m) continue;  // an earlier record of this file already hit
+                atomicAdd(row + fl[k], 1ull);
+            }
         }
     }
 }
@@ -472,8 +492,7 @@ int32_t igd_count_dev_locked(gtgpu_igd* g, bool binary, uint64_t n, const uint32
     if (n == 0) return GTGPU_OK;
     IgdView v{g->d_off, g->d_lut_s_off, g->d_nb_s, g->d_lut_p_off, g->d_nb_p, g->d_file, g->d_lut,
               g->d_start, g->d_end, g->d_pmax, d_psame, g->n_chroms, g->shift, g->n_files};
-    uint64_t warps_needed = n;
-    int grid = (int)std::min<uint64_t>((warps_needed + 7) / 8, (uint64_t)ctx->sm_count * 8);
+    const int grid = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 8);
     ctx->time_begin();
     if (binary)
         igd_count_kernel<true><<<grid, 256, 0, ctx->stream>>>(v, n, d_set_of, d_chr, d_start, d_end, m, (unsigned long long*)d_out);

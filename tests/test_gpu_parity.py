@@ -341,6 +341,43 @@ def test_igd_random_differential(ctx, min_overlap):
     g.close()
 
 
+@pytest.mark.parametrize("binary", [True, False])
+def test_igd_count_dev_any_set_order(ctx, binary):
+    """gtgpu_igd_count_dev takes the set of every query as an array: any order is fine (the host entry points pass runs)."""
+    import torch
+    from gtars_b200 import ffi
+    from oracle import oracle as orc
+    rng = np.random.default_rng(909 + int(binary))
+    n_chroms, n_files, n_sets = 3, 61, 7
+    sizes = rng.integers(100, 500, n_files)
+    n = int(sizes.sum())
+    fo = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    dc = rng.integers(0, n_chroms, n).astype(np.uint32)
+    ds = rng.integers(0, 1_000_000, n).astype(np.uint32)
+    de = (ds + rng.integers(1, 40_000, n)).astype(np.uint32)
+    g = ffi.Igd(ctx, fo, n_chroms, dc, ds, de)
+    o = orc.Igd(fo, dc, ds, de)
+    nq = 23_000
+    qc = rng.integers(0, n_chroms + 1, nq).astype(np.uint32)
+    qs = rng.integers(0, 1_010_000, nq).astype(np.uint32)
+    qe = (qs + rng.integers(1, 30_000, nq)).astype(np.uint32)
+    set_of = rng.integers(0, n_sets, nq).astype(np.uint32)            # arbitrary order
+    set_of[5000:14000] = 3                                            # ... with one long run across chunk boundaries
+    # oracle: group the queries by set (stable), count per set
+    order = np.argsort(set_of, kind="stable")
+    so = np.concatenate([[0], np.cumsum(np.bincount(set_of, minlength=n_sets))]).astype(np.uint64)
+    fn = o.count_region_hits if binary else o.count_set_overlaps
+    want = fn(so, qc[order], qs[order], qe[order], 2, threads=orc.max_threads())
+    dev = torch.device("cuda", 0)
+    t = [torch.from_numpy(a.view(np.int32)).to(dev) for a in (set_of, qc, qs, qe)]
+    d_out = torch.zeros(n_sets * n_files, dtype=torch.int64, device=dev)
+    ffi.check(ffi.lib().gtgpu_igd_count_dev(g._h, 1 if binary else 0, nq, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(),
+                                            t[3].data_ptr(), 2, d_out.data_ptr()))
+    ctx.synchronize()
+    assert np.array_equal(d_out.cpu().numpy().astype(np.uint64).reshape(n_sets, n_files), want)
+    g.close()
+
+
 @pytest.mark.parametrize("min_overlap", [1, 25])
 def test_igd_large_batch_many_sets(ctx, min_overlap):
     """A larger IGD batch (40 k queries, 90 files, 11 query sets incl. empty and one-query sets): both count semantics
