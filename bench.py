@@ -18,6 +18,7 @@ over BASELINE.json configs[1] (C2): 10 000 files x 100 000 regions = 1e9 query i
               c3  Bits count, 100 M queries vs a 50 M-interval database, query-sharded (strong scaling)
               c4  LOLA region-hit matrix, 1 k user sets x 10 k database sets, database sharded by set + ncclAllGather
               c5  fragment tokenization, 1 B unsorted fragments vs the 1 M-peak universe, fragment-sharded
+              backend  the headline workload (a tenth of the files) on the other overlapper backend (AIList when C2 runs Bits)
 
 `--scaling weak` (default): every rank owns `--files` files (1e9 queries per GPU); `--scaling strong`: `--files` files in
 total.  `--impl reference` times the oracle with all host threads instead (rank 0 only).  Multi-GPU (torchrun): files
@@ -63,7 +64,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-api", default="compact", choices=["compact", "runs"], help="host entry point of the e2e leg")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--configs", default="c3,c4,c5", help="sub-records to add (comma separated; empty = none)")
+    ap.add_argument("--configs", default="backend,c3,c4,c5", help="sub-records to add (comma separated; empty = none)")
     ap.add_argument("--sub-scale", type=float, default=1.0, help="scale factor on the sizes of the c3/c4/c5 sub-records")
     ap.add_argument("--parity-files", type=int, default=1000, help="files of the full-size C2 result checked against the oracle")
     ap.add_argument("--no-pcie-probe", action="store_true")
@@ -563,6 +564,67 @@ def sub_c5(args, torch, dev, ctx, stream, D, rank, world, peak, universe, index)
             "parity_digest": digest64(*got_parts)}
 
 
+def sub_backend(args, torch, dev, ctx, stream, D, rank, world, peak, universe, offs, s, e, v, other_kind):
+    """The headline workload on the OTHER overlapper backend (`tokenizer_type` bits / ailist are both first-class configs,
+    gtars-tokenizers/src/config.rs:29-34): same files, device-resident, K steps, parity on a sample of files."""
+    from gtars_b200 import ffi, synth
+    n_files = max(1, (args.files if args.scaling == "weak" else args.files // world) // 10)   # a tenth of the files
+    per_file = args.per_file
+    n = n_files * per_file
+    t0 = time.perf_counter()
+    ix = ffi.Index(ctx, ffi.KIND_AILIST if other_kind == "ailist" else ffi.KIND_BITS, offs, s, e, v)
+    build_s = time.perf_counter() - t0
+    d_chr = torch.empty(n, dtype=torch.int32, device=dev)
+    d_start = torch.empty(n, dtype=torch.int32, device=dev)
+    d_end = torch.empty(n, dtype=torch.int32, device=dev)
+    chunk = max(1, min(n_files, (32 << 20) // per_file))
+    first_file = rank * n_files
+    for f0 in range(0, n_files, chunk):
+        k = min(chunk, n_files - f0)
+        q = synth.make_query_files(universe, k, per_file, device=dev, first_file=first_file + f0, width_scale=args.width_scale)
+        sl = slice(f0 * per_file, (f0 + k) * per_file)
+        d_chr[sl], d_start[sl], d_end[sl] = q["chr"], q["start"], q["end"]
+        del q
+    d_fo = torch.arange(n_files + 1, dtype=torch.int64, device=dev) * per_file
+    cap = 2 * n + 1024
+    d_ids = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_tok = torch.empty(n_files + 1, dtype=torch.int64, device=dev)
+    d_total = torch.zeros(1, dtype=torch.int64, device=dev)
+    step = lambda: ix.find_dev(n, d_chr.data_ptr(), d_start.data_ptr(), d_end.data_ptr(), 0, n_files, d_fo.data_ptr(), d_ids.data_ptr(),
+                               cap, None, d_tok.data_ptr(), d_total.data_ptr())
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            step()
+        stream.synchronize()
+        hits = int(d_total.item())
+        assert hits <= cap
+        D.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        stream.synchronize()
+    ms = D.max(ev0.elapsed_time(ev1) / args.steps)
+    # parity: every 10th file, all ids in order
+    from oracle import oracle as orc
+    files = np.arange(0, n_files, 10)
+    g_tok = d_tok.cpu().numpy().astype(np.int64)
+    qsel = (torch.from_numpy(files).to(dev).view(-1, 1) * per_file + torch.arange(per_file, device=dev).view(1, -1)).flatten()
+    qc, qs, qe = (t[qsel].cpu().numpy().view(np.uint32) for t in (d_chr, d_start, d_end))
+    o = orc.Index(orc.AILIST if other_kind == "ailist" else orc.BITS, offs, s, e, v)
+    o_off, o_ids = o.tokenize_files((np.arange(len(files) + 1) * per_file).astype(np.uint64), qc, qs, qe, universe["unk_id"], threads=host_threads())
+    seg = torch.cat([torch.arange(int(g_tok[f]), int(g_tok[f + 1]), device=dev) for f in files])
+    ok = bool(np.array_equal(d_ids[seg].cpu().numpy().view(np.uint32), o_ids))
+    info = ix.info()
+    algo = 12 * n + 4 * hits + 8 * (n_files + 1) + 12 * info["n_intervals"]
+    ix.close()
+    return {"workload": f"C2 on the {other_kind} backend: tokenize {n_files} files x {per_file} regions per GPU (a tenth of the headline batch)",
+            "backend": other_kind, "queries_per_gpu": n, "ms": ms, "value": D.sum(float(n)) / (ms * 1e-3), "unit": UNIT,
+            "algorithmic_bytes": algo, "frac": algo / (ms * 1e-3) / 1e9 / peak, "index_build_s": build_s, "index": info,
+            "parity_vs_oracle": all(D.gather_objects(ok)), "parity_files_checked": int(len(files))}
+
+
 def _fragments(synth, universe, first, k, dev):
     """Fragments [first, first + k) of the C5 stream: nucleosomal width mixture (modes ~50 / 200 / 400 bp), 60 % inside
     peaks, Zipf-ish barcode sizes; unsorted."""
@@ -886,6 +948,9 @@ def main():
                 rec = sub_c4(args, torch, dev, ctx, stream, D, rank, world, peak)
             elif name == "c5":
                 rec = sub_c5(args, torch, dev, ctx, stream, D, rank, world, peak, u, index)
+            elif name == "backend":
+                rec = sub_backend(args, torch, dev, ctx, stream, D, rank, world, peak, u, offs, s, e, v,
+                                  "ailist" if args.kind == "bits" else "bits")
             else:
                 continue
         except Exception as ex:
