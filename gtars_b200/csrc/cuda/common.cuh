@@ -236,6 +236,7 @@ constexpr int CHROM_CACHE = 256;             // per-chromosome table entries sta
 
 enum CountMode { COUNT_U32 = 0, COUNT_ANY_U8 = 1, COUNT_BITS_RAW_U64 = 2 };
 
+void release_l2_window(gtgpu_ctx* ctx);
 int32_t launch_count(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
                      const uint32_t* d_end, int32_t min_overlap, int mode, void* d_out);
 

@@ -634,13 +634,7 @@ int32_t host_index_upload(gtgpu_ctx* ctx, const HostIndex& H, gtgpu_index** out_
 int32_t index_free_impl(gtgpu_index* ix) {
     if (!ix) return GTGPU_OK;
     cudaSetDevice(ix->ctx->device);
-    if (ix->ctx->l2_window_owner == ix) {  // the stream's access-policy window points into this index: drop it
-        cudaStreamAttrValue attr;
-        memset(&attr, 0, sizeof attr);
-        cudaStreamSetAttribute(ix->ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-        cudaGetLastError();
-        ix->ctx->l2_window_owner = nullptr;
-    }
+    if (ix->ctx->l2_window_owner == ix) release_l2_window(ix->ctx);  // the stream's access-policy window points into this index
     for (void* p : ix->allocs) cudaFree(p);
     if (ix->h_lean_probe) {
         cudaStreamSynchronize(ix->ctx->stream);  // a probe copy may still be in flight

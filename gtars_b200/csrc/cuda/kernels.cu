@@ -585,6 +585,19 @@ static int32_t launch_count_partitioned(gtgpu_index* ix, uint64_t n, const uint3
     return GTGPU_OK;
 }
 
+// Gives back what a find on this ctx set aside in the L2 for its window table: the stream's access-policy window, the
+// persisting lines and the set-aside itself (the next find re-establishes all three).
+void release_l2_window(gtgpu_ctx* ctx) {
+    if (!ctx->l2_window_owner) return;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaCtxResetPersistingL2Cache();
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    cudaGetLastError();
+    ctx->l2_window_owner = nullptr;
+}
+
 int32_t launch_count(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
                      const uint32_t* d_end, int32_t min_overlap, int mode, void* d_out) {
     if (n == 0) return GTGPU_OK;
@@ -593,15 +606,7 @@ int32_t launch_count(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const u
     if (count_wants_partition(ix, n, d_chr, d_end, min_overlap)) {
         // The bucketed pass lives on its LUT slices staying in the L2: give back what an earlier find on this ctx set aside
         // for its window table (persisting lines + the stream's access-policy window; the next find re-establishes both).
-        if (ctx->l2_window_owner) {
-            cudaStreamAttrValue attr;
-            memset(&attr, 0, sizeof attr);
-            cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-            cudaCtxResetPersistingL2Cache();
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
-            cudaGetLastError();
-            ctx->l2_window_owner = nullptr;
-        }
+        release_l2_window(ctx);
         return launch_count_partitioned(ix, n, d_chr, d_start, d_end, min_overlap, mode, d_out);
     }
     ctx->time_begin();
