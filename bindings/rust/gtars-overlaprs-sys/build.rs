@@ -9,7 +9,7 @@ fn main() {
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     let mut objs = vec![];
     // every source of gtars_b200/csrc/Makefile's SRCS (tests/test_abi.py keeps the two lists identical)
-    for f in ["api", "index", "kernels", "igd", "fragments", "scoring", "ingest", "comm", "sort", "build", "marshal"] {
+    for f in ["api", "index", "kernels", "igd", "fragments", "scoring", "ingest", "comm", "sort", "build", "marshal", "inflate"] {
         let src = root.join(format!("gtars_b200/csrc/cuda/{f}.cu"));
         let obj = out.join(format!("{f}.o"));
         let ok = Command::new(&nvcc)

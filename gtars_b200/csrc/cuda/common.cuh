@@ -159,6 +159,7 @@ struct gtgpu_ctx {
     std::mutex group_mu;                          // serialises group-wide calls
     bool group_comm_tried = false;                // in-process NCCL communicators (ncclCommInitAll) were set up / attempted
     int fused_bps[2][10] = {{0}, {0}};  // resident CTAs per SM of the fused find variants
+    const void* ingest_d_text = nullptr;          // set (under mu) while a *_gz entry point feeds device-resident text to the ingest
     const void* l2_window_owner = nullptr;        // the index whose window table the stream's access-policy window covers
     bool timing = false;                          // bracket dominant kernels with events
     std::vector<cudaEvent_t> ev_begin, ev_end;
@@ -216,7 +217,7 @@ enum ScratchRole {
     SC_CHR = 0, SC_START, SC_END, SC_BARCODE, SC_OUT_IDS, SC_OUT_IDS2, SC_OUT_OFFS, SC_FILE_OFFS, SC_FILE_TOK,
     SC_FILE_TOK2, SC_TILE_STATUS, SC_TILE_FILE, SC_MISC, SC_COUNTS, SC_IN2_CHR, SC_IN2_START, SC_IN2_END,
     SC_IN3_CHR, SC_IN3_START, SC_IN3_END, SC_SET_ID, SC_MATRIX, SC_ING_0, SC_ING_1, SC_ING_2, SC_ING_3, SC_ING_4, SC_ING_5,
-    SC_ING_6, SC_ING_7, SC_CNT_CHR, SC_CNT_START, SC_CNT_END, SC_CNT_SLOT, SC_CNT_TMP, SC_CNT_CURSORS, SC_N_ROLES
+    SC_ING_6, SC_ING_7, SC_GZ_IN, SC_GZ_OUT, SC_GZ_MOFF, SC_GZ_OOFF, SC_GZ_STATUS, SC_CNT_CHR, SC_CNT_START, SC_CNT_END, SC_CNT_SLOT, SC_CNT_TMP, SC_CNT_CURSORS, SC_N_ROLES
 };
 
 // kernels.cu
@@ -282,6 +283,13 @@ size_t radix_sort_temp_bytes(uint64_t n);
 int32_t radix_sort_pairs(gtgpu_ctx* ctx, uint64_t n, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
                          int bits, void* d_temp, int* result_in_b, const uint64_t* d_n = nullptr);
 void radix_plan(int bits, int* passes, int* width);
+
+// ingest.cu / inflate.cu (the caller holds ctx->mu)
+int32_t tokenize_bed_locked(gtgpu_index* ix, const char* text, uint64_t n_bytes, uint32_t n_names, const char* names,
+                            const uint32_t* name_offsets, uint32_t unk_id, gtgpu_buf** out_ids);
+int32_t tokenize_fragments_text_locked(gtgpu_index* ix, const char* text, uint64_t n_bytes, uint32_t n_names, const char* names,
+                                       const uint32_t* name_offsets, uint32_t unk_id, uint32_t* out_n_barcodes,
+                                       gtgpu_buf** out_barcode_spans, gtgpu_buf** out_barcode_offsets, gtgpu_buf** out_ids);
 
 // groups (api.cu, comm.cu, igd.cu)
 int32_t for_each_device(size_t n_devices, const std::function<int32_t(size_t)>& fn);

@@ -368,12 +368,14 @@ static int32_t parse_bed_locked(gtgpu_ctx* ctx, const char* text, uint64_t n_byt
     void* d_tmp;
     char* d_names;
     const uint64_t n_chunks = (n_bytes + INGEST_CHUNK - 1) / INGEST_CHUNK;
-    GT_TRY(ctx->scratch_get(SC_OUT_IDS2, n_bytes + 64, (void**)&d_text));
+    // the text is either the caller's host buffer or already on the device (gtgpu_*_gz: inflated there, ctx->ingest_d_text)
+    if (ctx->ingest_d_text) d_text = (char*)ctx->ingest_d_text;
+    else GT_TRY(ctx->scratch_get(SC_OUT_IDS2, n_bytes + 64, (void**)&d_text));
     GT_TRY(ctx->scratch_get(SC_COUNTS, n_chunks * 4 + 4, (void**)&d_counts));
     GT_TRY(ctx->scratch_get(SC_IN3_CHR, n_chunks * 4 + 4, (void**)&d_crank));
     const size_t names_bytes = ((size_t)blob_bytes + 15) / 16 * 16 + ((size_t)n_names + 1) * 4 + (size_t)n_names * 8 + (size_t)n_names * 4 * 2 + 64;
     GT_TRY(ctx->scratch_get(SC_SET_ID, names_bytes, (void**)&d_names));
-    GT_CUDA(cudaMemcpyAsync(d_text, text, n_bytes, cudaMemcpyHostToDevice, st));
+    if (!ctx->ingest_d_text) GT_CUDA(cudaMemcpyAsync(d_text, text, n_bytes, cudaMemcpyHostToDevice, st));
     // layout of the name scratch: hashes (8-byte aligned first), offsets, hash ids, ranks, blob
     unsigned long long* d_hash = reinterpret_cast<unsigned long long*>(d_names);
     uint32_t* d_noff = reinterpret_cast<uint32_t*>(d_hash + n_names);
@@ -397,9 +399,11 @@ static int32_t parse_bed_locked(gtgpu_ctx* ctx, const char* text, uint64_t n_byt
     uint32_t last[2];
     GT_CUDA(cudaMemcpyAsync(&last[0], d_crank + n_chunks - 1, 4, cudaMemcpyDeviceToHost, st));
     GT_CUDA(cudaMemcpyAsync(&last[1], d_counts + n_chunks - 1, 4, cudaMemcpyDeviceToHost, st));
+    char last_byte = 0;  // read back from the device: with device-resident text there is no host copy
+    GT_CUDA(cudaMemcpyAsync(&last_byte, d_text + n_bytes - 1, 1, cudaMemcpyDeviceToHost, st));
     GT_CUDA(cudaStreamSynchronize(st));  // the host's text buffer may be reused after this point
     const uint32_t n_newlines = last[0] + last[1];
-    const uint32_t n_lines = n_newlines + (text[n_bytes - 1] != '\n' ? 1u : 0u);
+    const uint32_t n_lines = n_newlines + (last_byte != '\n' ? 1u : 0u);
     GT_TRY(ctx->scratch_get(SC_IN3_END, (size_t)n_newlines * 4 + 4, (void**)&d_nl));
     ingest_newline_positions_kernel<<<igrid(ctx, n_chunks), 256, 0, st>>>(n_bytes, d_text, d_crank, d_nl);
     ctx->launches++;
@@ -528,6 +532,13 @@ extern "C" int32_t gtgpu_tokenize_bed(gtgpu_index* ix, const char* text, uint64_
     gtgpu_ctx* ctx = ix->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
     GT_CUDA(cudaSetDevice(ctx->device));
+    return tokenize_bed_locked(ix, text, n_bytes, n_names, names, name_offsets, unk_id, out_ids);
+} GT_CATCH
+
+// the caller holds ctx->mu; `text` is ignored when ctx->ingest_d_text points at the text on the device
+int32_t gtgpu::tokenize_bed_locked(gtgpu_index* ix, const char* text, uint64_t n_bytes, uint32_t n_names, const char* names,
+                                   const uint32_t* name_offsets, uint32_t unk_id, gtgpu_buf** out_ids) {
+    gtgpu_ctx* ctx = ix->ctx;
     uint32_t *d_chr, *d_start, *d_end, *d_ids = nullptr;
     uint64_t n = 0, total = 0;
     GT_TRY(parse_bed_locked(ctx, text, n_bytes, n_names, names, name_offsets, &n, &d_chr, &d_start, &d_end));
@@ -546,7 +557,7 @@ extern "C" int32_t gtgpu_tokenize_bed(gtgpu_index* ix, const char* text, uint64_
         return GTGPU_OK;
     }
     return to_host_buf(ctx, d_ids, total, out_ids);
-} GT_CATCH
+}
 
 // tokenize_fragment_file (fragments.rs:61-82) from the file's text: parse on the device, barcodes -> dense ids in
 // first-appearance order through a device hash table, then the fragment tokenizer core.
@@ -557,10 +568,19 @@ extern "C" int32_t gtgpu_tokenize_fragments_text(gtgpu_index* ix, const char* te
     if (!ix || !out_n_barcodes || !out_barcode_spans || !out_barcode_offsets || !out_ids || (n_bytes && !text) ||
         (n_names && (!names || !name_offsets)))
         return fail(GTGPU_ERR_INVALID, "tokenize_fragments_text: null argument");
-    if (n_bytes >= 0xFFFFFFF0ull) return fail(GTGPU_ERR_UNSUPPORTED, "tokenize_fragments_text: at most 4 GiB of text per call");
     gtgpu_ctx* ctx = ix->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
     GT_CUDA(cudaSetDevice(ctx->device));
+    return tokenize_fragments_text_locked(ix, text, n_bytes, n_names, names, name_offsets, unk_id, out_n_barcodes, out_barcode_spans,
+                                          out_barcode_offsets, out_ids);
+} GT_CATCH
+
+// the caller holds ctx->mu; `text` is ignored when ctx->ingest_d_text points at the text on the device
+int32_t gtgpu::tokenize_fragments_text_locked(gtgpu_index* ix, const char* text, uint64_t n_bytes, uint32_t n_names, const char* names,
+                                              const uint32_t* name_offsets, uint32_t unk_id, uint32_t* out_n_barcodes,
+                                              gtgpu_buf** out_barcode_spans, gtgpu_buf** out_barcode_offsets, gtgpu_buf** out_ids) {
+    if (n_bytes >= 0xFFFFFFF0ull) return fail(GTGPU_ERR_UNSUPPORTED, "tokenize_fragments_text: at most 4 GiB of text per call");
+    gtgpu_ctx* ctx = ix->ctx;
     cudaStream_t st = ctx->stream;
 
     uint32_t n = 0, n_barcodes = 0;
@@ -582,11 +602,12 @@ extern "C" int32_t gtgpu_tokenize_fragments_text(gtgpu_index* ix, const char* te
         uint32_t *d_counts, *d_crank, *d_nl;
         void* d_tmp;
         const uint64_t n_chunks = (n_bytes + INGEST_CHUNK - 1) / INGEST_CHUNK;
-        GT_TRY(ctx->scratch_get(SC_OUT_IDS2, n_bytes + 64, (void**)&d_text));
+        if (ctx->ingest_d_text) d_text = (char*)ctx->ingest_d_text;
+        else GT_TRY(ctx->scratch_get(SC_OUT_IDS2, n_bytes + 64, (void**)&d_text));
         GT_TRY(ctx->scratch_get(SC_COUNTS, n_chunks * 4 + 4, (void**)&d_counts));
         GT_TRY(ctx->scratch_get(SC_IN3_CHR, n_chunks * 4 + 4, (void**)&d_crank));
         GT_TRY(ctx->scratch_get(SC_SET_ID, (size_t)n_names * 16 + ((size_t)n_names + 1) * 4 + blob_bytes + 64, (void**)&d_names));
-        GT_CUDA(cudaMemcpyAsync(d_text, text, n_bytes, cudaMemcpyHostToDevice, st));
+        if (!ctx->ingest_d_text) GT_CUDA(cudaMemcpyAsync(d_text, text, n_bytes, cudaMemcpyHostToDevice, st));
         unsigned long long* d_hash = reinterpret_cast<unsigned long long*>(d_names);
         uint32_t* d_noff = reinterpret_cast<uint32_t*>(d_hash + n_names);
         uint32_t* d_hid = d_noff + n_names + 1;
@@ -606,9 +627,11 @@ extern "C" int32_t gtgpu_tokenize_fragments_text(gtgpu_index* ix, const char* te
         uint32_t last[2];
         GT_CUDA(cudaMemcpyAsync(&last[0], d_crank + n_chunks - 1, 4, cudaMemcpyDeviceToHost, st));
         GT_CUDA(cudaMemcpyAsync(&last[1], d_counts + n_chunks - 1, 4, cudaMemcpyDeviceToHost, st));
+        char last_byte = 0;  // read back from the device: with device-resident text there is no host copy
+        GT_CUDA(cudaMemcpyAsync(&last_byte, d_text + n_bytes - 1, 1, cudaMemcpyDeviceToHost, st));
         GT_CUDA(cudaStreamSynchronize(st));
         const uint32_t n_newlines = last[0] + last[1];
-        const uint32_t n_lines = n_newlines + (text[n_bytes - 1] != '\n' ? 1u : 0u);
+        const uint32_t n_lines = n_newlines + (last_byte != '\n' ? 1u : 0u);
         GT_TRY(ctx->scratch_get(SC_IN3_END, (size_t)n_newlines * 4 + 4, (void**)&d_nl));
         ingest_newline_positions_kernel<<<igrid(ctx, n_chunks), 256, 0, st>>>(n_bytes, d_text, d_crank, d_nl);
         ctx->launches++;
@@ -708,4 +731,4 @@ extern "C" int32_t gtgpu_tokenize_fragments_text(gtgpu_index* ix, const char* te
     *out_barcode_offsets = offs;
     *out_ids = ids;
     return GTGPU_OK;
-} GT_CATCH
+}

@@ -616,10 +616,37 @@ std::vector<std::vector<uint32_t>> Tokenizer::encode_batch(const std::vector<con
 
 std::vector<uint32_t> Tokenizer::encode(const std::vector<Region>& regions) const { return encode_batch({&regions})[0]; }
 
+// A `.gz` input made of many gzip members (bgzip / BGZF, or concatenated gzips) is inflated on the device, one warp per
+// member, and parsed there; a single-member stream is sequential, so it stays with zlib on the host (get_dynamic_reader's
+// MultiGzDecoder semantics either way: the text is the concatenation of the members).
+static bool gz_members_for_device(const std::string& path, std::string& raw, std::vector<uint64_t>& members) {
+    if (!(path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0)) return false;
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) throw Error("Failed to open file: \"" + path + "\"");
+    const std::streamsize size = f.tellg();
+    f.seekg(0);
+    raw.resize((size_t)std::max<std::streamsize>(size, 0));
+    if (size > 0 && !f.read(&raw[0], size)) throw Error("Failed to read file: \"" + path + "\"");
+    uint64_t n = 0;
+    gtgpu_gzip_members((const uint8_t*)raw.data(), raw.size(), 0, nullptr, &n);  // count only
+    if (n < 16) return false;
+    members.resize(n + 1);
+    check(gtgpu_gzip_members((const uint8_t*)raw.data(), raw.size(), members.size(), members.data(), &n), "gtgpu_gzip_members");
+    return true;
+}
+
 std::vector<uint32_t> Tokenizer::encode_bed_file(const std::string& path) const {
-    const std::string text = read_file_bytes(path);
     NameBlob nb(cmap_);
     PinnedResult ids;
+    std::string raw;
+    std::vector<uint64_t> members;
+    if (gz_members_for_device(path, raw, members)) {
+        check(gtgpu_tokenize_bed_gz(index_, members.size() - 1, (const uint8_t*)raw.data(), members.data(), (uint32_t)cmap_.size(),
+                                    nb.blob.data(), nb.offsets.data(), unk_id_, &ids.buf),
+              "gtgpu_tokenize_bed_gz");
+        return std::vector<uint32_t>(ids.data(), ids.data() + ids.len());
+    }
+    const std::string text = read_file_bytes(path);
     check(gtgpu_tokenize_bed(index_, text.data(), text.size(), (uint32_t)cmap_.size(), nb.blob.data(), nb.offsets.data(), unk_id_,
                              &ids.buf),
           "gtgpu_tokenize_bed");
@@ -686,18 +713,30 @@ std::vector<std::pair<std::string, std::vector<uint32_t>>> Tokenizer::tokenize_f
 }
 
 std::vector<std::pair<std::string, std::vector<uint32_t>>> Tokenizer::tokenize_fragment_file_device(const std::string& path) const {
-    const std::string text = read_file_bytes(path);
     NameBlob nb(cmap_);
     uint32_t n_barcodes = 0;
-    PinnedResult spans, offs, ids;
-    check(gtgpu_tokenize_fragments_text(index_, text.data(), text.size(), (uint32_t)cmap_.size(), nb.blob.data(), nb.offsets.data(),
-                                        unk_id_, &n_barcodes, &spans.buf, &offs.buf, &ids.buf),
-          "gtgpu_tokenize_fragments_text");
+    PinnedResult spans, offs, ids, dev_text;
+    std::string raw, host_text;
+    std::vector<uint64_t> members;
+    const char* text = nullptr;
+    if (gz_members_for_device(path, raw, members)) {  // bgzip'ed fragment file: inflated on the device, the text comes back once
+        check(gtgpu_tokenize_fragments_gz(index_, members.size() - 1, (const uint8_t*)raw.data(), members.data(), (uint32_t)cmap_.size(),
+                                          nb.blob.data(), nb.offsets.data(), unk_id_, &n_barcodes, &spans.buf, &offs.buf, &ids.buf,
+                                          &dev_text.buf),
+              "gtgpu_tokenize_fragments_gz");
+        text = (const char*)gtgpu_buf_data(dev_text.buf);
+    } else {
+        host_text = read_file_bytes(path);
+        check(gtgpu_tokenize_fragments_text(index_, host_text.data(), host_text.size(), (uint32_t)cmap_.size(), nb.blob.data(),
+                                            nb.offsets.data(), unk_id_, &n_barcodes, &spans.buf, &offs.buf, &ids.buf),
+              "gtgpu_tokenize_fragments_text");
+        text = host_text.data();
+    }
     const uint64_t* off = (const uint64_t*)gtgpu_buf_data(offs.buf);
     std::vector<std::pair<std::string, std::vector<uint32_t>>> out;
     out.reserve(n_barcodes);
     for (uint32_t b = 0; b < n_barcodes; ++b)
-        out.emplace_back(text.substr(spans.data()[2 * b], spans.data()[2 * b + 1]),
+        out.emplace_back(std::string(text + spans.data()[2 * b], spans.data()[2 * b + 1]),
                          std::vector<uint32_t>(ids.data() + off[b], ids.data() + off[b + 1]));
     return out;
 }

@@ -53,6 +53,10 @@ SIGNATURES = {
     "gtgpu_parse_bed": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gtgpu_tokenize_bed": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp, _u32, _vp]),
     "gtgpu_tokenize_fragments_text": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "gtgpu_gzip_members": (_i32, [_vp, _u64, _u64, _vp, _vp]),
+    "gtgpu_gunzip": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp]),
+    "gtgpu_tokenize_bed_gz": (_i32, [_vp, _u64, _vp, _vp, _u32, _vp, _vp, _u32, _vp]),
+    "gtgpu_tokenize_fragments_gz": (_i32, [_vp, _u64, _vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
     "gtgpu_score_matrix": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _i32, _u64, _vp]),
     "gtgpu_score_matrix_dev": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _i32, _u64, _vp]),
     "gtgpu_score_barcodes": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp]),
@@ -323,6 +327,33 @@ class Index:
         check(lib().gtgpu_tokenize_bed(self._h, text, len(text), len(chrom_names), blob, _p(offs), unk_id, C.byref(h)))
         return _take(h)
 
+    def tokenize_bed_gz(self, gz: bytes, chrom_names, unk_id, member_offsets=None):
+        """gtgpu_tokenize_bed_gz: gzip members in, token ids out (inflate + parse + sort + encode on the device)."""
+        mo = _arr(member_offsets if member_offsets is not None else gzip_members(gz), np.uint64)
+        blob, offs = _names_blob(chrom_names)
+        h = C.c_void_p()
+        check(lib().gtgpu_tokenize_bed_gz(self._h, len(mo) - 1, gz, _p(mo), len(chrom_names), blob, _p(offs), unk_id, C.byref(h)))
+        return _take(h)
+
+    def tokenize_fragments_text(self, text: bytes, chrom_names, unk_id, gz_member_offsets=None):
+        """gtgpu_tokenize_fragments_text (or _gz when gz_member_offsets is given: `text` is then the gzip data):
+        ([barcode strings], offsets, ids)."""
+        blob, offs = _names_blob(chrom_names)
+        nb = C.c_uint32(0)
+        hs, ho, hi, ht = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        if gz_member_offsets is not None:
+            mo = _arr(gz_member_offsets, np.uint64)
+            check(lib().gtgpu_tokenize_fragments_gz(self._h, len(mo) - 1, text, _p(mo), len(chrom_names), blob, _p(offs), unk_id,
+                                                    C.byref(nb), C.byref(hs), C.byref(ho), C.byref(hi), C.byref(ht)))
+            text = _take(ht, dtype=np.uint8).tobytes()
+        else:
+            check(lib().gtgpu_tokenize_fragments_text(self._h, text, len(text), len(chrom_names), blob, _p(offs), unk_id,
+                                                      C.byref(nb), C.byref(hs), C.byref(ho), C.byref(hi)))
+        spans = _take(hs).reshape(-1, 2)
+        off = _take(ho, dtype=np.uint64)
+        ids = _take(hi)
+        return [text[int(a):int(a) + int(n)].decode() for a, n in spans[:nb.value]], off, ids
+
     def score_matrix(self, file_offsets, chr, start, end, mode, n_cols):
         """region_scoring_from_fragments: uint32 [n_files, n_cols]."""
         fo = _arr(file_offsets, np.uint64)
@@ -377,6 +408,33 @@ def marshal_compact(chr, start, end, file_offsets, width16_out=None, threads=0):
         check(st)
         return ro[:n_runs.value + 1], rc[:n_runs.value], w16, wi[:n_wide.value], we[:n_wide.value]
     raise GtarsGpuError(4, "marshal_compact: capacity retry failed")
+
+
+def gzip_members(gz: bytes) -> np.ndarray:
+    """gtgpu_gzip_members: offsets (n_members + 1) of the gzip members of `gz` (BGZF blocks split, else one member)."""
+    n = C.c_uint64(0)
+    st = lib().gtgpu_gzip_members(gz, len(gz), 0, None, C.byref(n))
+    if st not in (0, 4):
+        check(st)
+    offs = np.zeros(n.value + 1, dtype=np.uint64)
+    check(lib().gtgpu_gzip_members(gz, len(gz), len(offs), _p(offs), C.byref(n)))
+    return offs
+
+
+def gunzip(ctx: "Context", gz: bytes, member_offsets=None):
+    """gtgpu_gunzip: (text bytes, member text offsets); member_offsets default = gzip_members(gz)."""
+    mo = _arr(member_offsets if member_offsets is not None else gzip_members(gz), np.uint64)
+    out_off = np.zeros(len(mo), dtype=np.uint64)
+    h = C.c_void_p()
+    check(lib().gtgpu_gunzip(ctx._h, len(mo) - 1, gz, _p(mo), C.byref(h), _p(out_off)))
+    return _take(h, dtype=np.uint8).tobytes(), out_off
+
+
+def _names_blob(chrom_names):
+    blob = b"".join(n.encode() for n in chrom_names)
+    offs = np.zeros(len(chrom_names) + 1, dtype=np.uint32)
+    offs[1:] = np.cumsum([len(n.encode()) for n in chrom_names])
+    return blob, offs
 
 
 def comm_unique_id() -> bytes:

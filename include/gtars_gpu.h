@@ -83,7 +83,7 @@ int32_t gtgpu_host_free(void* ptr);
 
 /* result buffers */
 const void* gtgpu_buf_data(const gtgpu_buf* buf);
-uint64_t gtgpu_buf_len(const gtgpu_buf* buf); /* elements, not bytes */
+uint64_t gtgpu_buf_len(const gtgpu_buf* buf); /* elements (4-byte ids unless the entry point says otherwise), not bytes */
 int32_t gtgpu_buf_free(gtgpu_buf* buf);       /* returns the pinned block to the ctx cache */
 
 /* ---- index: Overlapper::build per chromosome -------------------------------------------------------------
@@ -209,6 +209,34 @@ int32_t gtgpu_tokenize_fragments_text(gtgpu_index* index, const char* text, uint
                                       const char* names, const uint32_t* name_offsets, uint32_t unk_id,
                                       uint32_t* out_n_barcodes, gtgpu_buf** out_barcode_spans,
                                       gtgpu_buf** out_barcode_offsets, gtgpu_buf** out_ids);
+
+/* ---- gzip on the device ------------------------------------------------------------------------------------------------
+ * The reference reads `.gz` inputs through flate2's MultiGzDecoder (gtars-core/src/utils.rs:115-126): the text is the
+ * concatenation of the file's gzip members.  A DEFLATE stream is sequential, so the device inflates MEMBERS in parallel, one
+ * warp each: a bgzip'ed fragment file is thousands of independent <= 64 KiB BGZF members, a tokenization batch thousands of
+ * one-member `.bed.gz` files back to back.  (One multi-gigabyte single-member stream is a job for the host's zlib.)
+ *
+ * gtgpu_gzip_members (host only): member boundaries of a gzip buffer — BGZF blocks are split by their BSIZE field, anything
+ * else is one member to the end of the buffer.  out_member_offsets needs n_members + 1 entries (`capacity` of them are
+ * available; *out_n_members always receives the count, GTGPU_ERR_CAPACITY when it did not fit).
+ * gtgpu_gunzip: member k = gz[member_offsets[k], member_offsets[k+1]) (whole members; several files may simply be laid
+ * back to back).  *out_text (byte elements) = the members' texts concatenated, out_member_offsets[n_members + 1] where each
+ * starts.  Every member's ISIZE and CRC-32 are verified; corrupt data, a unit that holds more than one member, or a member
+ * with >= 4 GiB of text give GTGPU_ERR_INVALID naming the member.
+ * gtgpu_tokenize_bed_gz / gtgpu_tokenize_fragments_gz = inflate + gtgpu_tokenize_bed / gtgpu_tokenize_fragments_text with
+ * the text never leaving the device on its way to the parser (the fragment form also returns the text: the barcode spans
+ * index into it). */
+int32_t gtgpu_gzip_members(const uint8_t* gz, uint64_t n_bytes, uint64_t capacity, uint64_t* out_member_offsets,
+                           uint64_t* out_n_members);
+int32_t gtgpu_gunzip(gtgpu_ctx* ctx, uint64_t n_members, const uint8_t* gz, const uint64_t* member_offsets,
+                     gtgpu_buf** out_text, uint64_t* out_member_offsets);
+int32_t gtgpu_tokenize_bed_gz(gtgpu_index* index, uint64_t n_members, const uint8_t* gz, const uint64_t* member_offsets,
+                              uint32_t n_names, const char* names, const uint32_t* name_offsets, uint32_t unk_id,
+                              gtgpu_buf** out_ids);
+int32_t gtgpu_tokenize_fragments_gz(gtgpu_index* index, uint64_t n_members, const uint8_t* gz, const uint64_t* member_offsets,
+                                    uint32_t n_names, const char* names, const uint32_t* name_offsets, uint32_t unk_id,
+                                    uint32_t* out_n_barcodes, gtgpu_buf** out_barcode_spans, gtgpu_buf** out_barcode_offsets,
+                                    gtgpu_buf** out_ids, gtgpu_buf** out_text);
 
 /* ---- gtars-scoring: fragments x consensus peaks ------------------------------------------------------------------------
  * gtgpu_score_matrix replaces region_scoring_from_fragments (gtars-scoring/src/fragment_scoring.rs:19-121) over
