@@ -5,9 +5,9 @@ A "step" is one pass of the hot path (Tokenizer::encode for every file, gtars-to
 over BASELINE.json configs[1] (C2): 10 000 files x 100 000 regions = 1e9 query intervals vs a 1 M-region universe.
 
   value     query intervals / s, device-resident inputs, CUDA events around K back-to-back steps (max over ranks)
-  e2e       the same metric through the C-ABI host entry point gtgpu_tokenize_files_compact with PINNED HOST buffers,
-            H2D of the queries and D2H of the ids inside the timed region; `marshal` = the host-side packing of the
-            caller's flat (chr, start, end) arrays into that wire format (gtgpu_marshal_compact), timed separately;
+  e2e       the same metric through the C-ABI host entry point gtgpu_tokenize_files_packed (--e2e-api: packed / compact /
+            runs) with PINNED HOST buffers, H2D of the queries and D2H of the ids inside the timed region; `marshal` = the
+            host-side packing of the caller's flat (chr, start, end) arrays into that wire format, timed separately;
             `pcie` = what concurrent pinned H2D + D2H copies reach on this box (the ceiling of any e2e number)
   roofline  algorithmic HBM bytes of the fused kernel / its own CUDA-event time, vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the CPU oracle (C++ restatement of the reference's algorithm; the reference is Rust and cannot be
@@ -19,6 +19,7 @@ over BASELINE.json configs[1] (C2): 10 000 files x 100 000 regions = 1e9 query i
               c4  LOLA region-hit matrix, 1 k user sets x 10 k database sets, database sharded by set + ncclAllGather
               c5  fragment tokenization, 1 B unsorted fragments vs the 1 M-peak universe, fragment-sharded
               backend  the headline workload (a tenth of the files) on the other overlapper backend (AIList when C2 runs Bits)
+              gz  a bgzip'ed BED file inflated on the device (one warp per member) and tokenized, vs zlib on one host thread
 
 `--scaling weak` (default): every rank owns `--files` files (1e9 queries per GPU); `--scaling strong`: `--files` files in
 total.  `--impl reference` times the oracle with all host threads instead (rank 0 only).  Multi-GPU (torchrun): files
@@ -62,9 +63,9 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-api", default="compact", choices=["compact", "runs"], help="host entry point of the e2e leg")
+    ap.add_argument("--e2e-api", default="packed", choices=["packed", "compact", "runs"], help="host entry point of the e2e leg")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--configs", default="backend,c3,c4,c5", help="sub-records to add (comma separated; empty = none)")
+    ap.add_argument("--configs", default="backend,gz,c3,c4,c5", help="sub-records to add (comma separated; empty = none)")
     ap.add_argument("--sub-scale", type=float, default=1.0, help="scale factor on the sizes of the c3/c4/c5 sub-records")
     ap.add_argument("--parity-files", type=int, default=1000, help="files of the full-size C2 result checked against the oracle")
     ap.add_argument("--no-pcie-probe", action="store_true")
@@ -564,6 +565,72 @@ def sub_c5(args, torch, dev, ctx, stream, D, rank, world, peak, universe, index)
             "parity_digest": digest64(*got_parts)}
 
 
+def bgzf_compress(data: bytes, block=60_000, level=6) -> bytes:
+    """A BGZF file as bgzip writes it: independent gzip members with the 'BC' extra field (BSIZE) + the empty EOF block."""
+    import struct
+    import zlib
+    out = []
+    for a in list(range(0, len(data), block)) + [None]:
+        ch = data[a:a + block] if a is not None else b""
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        body = co.compress(ch) + co.flush()
+        out.append(b"\x1f\x8b\x08\x04" + b"\0" * 4 + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, 12 + 6 + len(body) + 8 - 1)
+                   + body + struct.pack("<II", zlib.crc32(ch), len(ch)))
+    return b"".join(out)
+
+
+def sub_gz(args, torch, dev, ctx, stream, D, rank, world, peak, universe, index):
+    """a bgzip'ed BED file (the reference reads `.gz` through flate2's MultiGzDecoder, gtars-core/src/utils.rs:115-126)
+    inflated on the device, one warp per BGZF member, and tokenized without the text ever crossing PCIe.  Rank-local, same file
+    on every rank; compared with zlib on one host thread (what the reference's reader does)."""
+    import zlib
+    import pandas as pd
+    from gtars_b200 import ffi, synth
+    n_lines = 2_000_000
+    q = synth.make_query_files(universe, 20, n_lines // 20, first_file=0)
+    names = np.array(list(synth.CHROM_NAMES))
+    qc, qs, qe = (q[k].numpy() for k in ("chr", "start", "end"))
+    t0 = time.perf_counter()
+    text = pd.DataFrame({"c": names[qc], "s": qs, "e": qe}).to_csv(sep="\t", header=False, index=False).encode()
+    gz = bgzf_compress(text)
+    prep_s = time.perf_counter() - t0
+    members = ffi.gzip_members(gz)
+    t0 = time.perf_counter()
+    z_text = b"".join(zlib.decompress(gz[int(a):int(b)], 31) for a, b in zip(members[:-1], members[1:]))
+    zlib_s = time.perf_counter() - t0
+    got, _ = ffi.gunzip(ctx, gz, members)   # warm-up + parity
+    same_text = got == text and z_text == text
+    del got, z_text
+    ctx.timing_enable(True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ffi.gunzip(ctx, gz, members)
+    wall_s = (time.perf_counter() - t0) / args.steps
+    k_ms = ctx.timing_read()
+    ctx.timing_enable(False)
+    kernel_ms = statistics.median(k_ms) if k_ms else None
+    unk = int(universe["unk_id"])
+    want = index.tokenize_bed(text, list(names), unk)
+    ids = index.tokenize_bed_gz(gz, list(names), unk, member_offsets=members)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        index.tokenize_bed_gz(gz, list(names), unk, member_offsets=members)
+    tok_s = (time.perf_counter() - t0) / args.steps
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        index.tokenize_bed(text, list(names), unk)
+    tok_text_s = (time.perf_counter() - t0) / args.steps
+    ok = bool(same_text and np.array_equal(ids, want))
+    return {"workload": f"bgzip'ed BED file, {n_lines} lines: inflate on the device (one warp per BGZF member) + parse + sort + tokenize",
+            "gz_bytes": len(gz), "text_bytes": len(text), "members": int(len(members) - 1),
+            "gunzip_kernel_ms": kernel_ms, "gunzip_kernel_text_gbs": (len(text) / (kernel_ms * 1e-3) / 1e9) if kernel_ms else None,
+            "gunzip_host_to_host_ms": wall_s * 1e3, "zlib_one_thread_ms": zlib_s * 1e3,
+            "tokenize_bed_gz_ms": tok_s * 1e3, "tokenize_bed_text_ms": tok_text_s * 1e3, "ids": int(len(ids)),
+            "lines_per_s": n_lines / tok_s, "parity_vs_zlib_and_text_path": all(D.gather_objects(ok)), "data_gen_s": prep_s,
+            "note": "gunzip_host_to_host = gtgpu_gunzip from / to host memory (H2D of the members, kernel, D2H of the text); "
+                    "tokenize_bed_gz = gz bytes in, token ids out"}
+
+
 def sub_backend(args, torch, dev, ctx, stream, D, rank, world, peak, universe, offs, s, e, v, other_kind):
     """The headline workload on the OTHER overlapper backend (`tokenizer_type` bits / ailist are both first-class configs,
     gtars-tokenizers/src/config.rs:29-34): same files, device-resident, K steps, parity on a sample of files."""
@@ -809,34 +876,52 @@ def main():
     pcie = None
     if not args.no_e2e:
         # What a Rust caller holds after RegionSet::try_from + a chromosome-name lookup: flat (chr id, start, end) arrays.
-        # gtgpu_marshal_compact (host, multithreaded) turns them into the wire format of gtgpu_tokenize_files_compact:
-        # chromosome runs, u32 starts, u16 widths, an exception list — 6 B of PCIe per region instead of 12.
-        compact = args.e2e_api == "compact"
+        # A host-side packer (multithreaded C++) turns them into a wire format of the host entry point:
+        #   packed  (default) gtgpu_marshal_packed -> gtgpu_tokenize_files_packed: chromosome runs, ONE u32 per region (offset from
+        #           the anchor of its 32-region block | width) + the anchors + an exception list: 4.125 B of PCIe per region;
+        #   compact gtgpu_marshal_compact -> gtgpu_tokenize_files_compact: runs, u32 starts, u16 widths: 6 B per region;
+        #   runs    runs + u32 starts + u32 ends: 8 B per region (instead of the 12 B of the flat arrays).
+        api = args.e2e_api
+        packed, compact = api == "packed", api == "compact"
         h_chr = np.empty(n, dtype=np.uint32)
-        h_start = ffi.pinned_empty(n, np.uint32)
-        h_end = ffi.pinned_empty(n, np.uint32) if not compact else np.empty(n, dtype=np.uint32)
+        h_start = ffi.pinned_empty(n, np.uint32) if not packed else np.empty(n, dtype=np.uint32)
+        h_end = ffi.pinned_empty(n, np.uint32) if api == "runs" else np.empty(n, dtype=np.uint32)
         torch.from_numpy(h_chr.view(np.int32)).copy_(d_chr)
         torch.from_numpy(h_start.view(np.int32)).copy_(d_start)
         torch.from_numpy(h_end.view(np.int32)).copy_(d_end)
         h_fo = d_file_offsets.cpu().numpy().astype(np.uint64)
-        h_w16 = ffi.pinned_empty(n, np.uint16)
+        h_w16 = ffi.pinned_empty(n, np.uint16) if not packed else None
+        h_pk = ffi.pinned_empty(n, np.uint32) if packed else None
+        h_an = ffi.pinned_empty((n + 31) // 32, np.uint32) if packed else None
         marshal_s = []
         for _ in range(2):
             t0 = time.perf_counter()
-            h_run_off, h_run_chr, _, h_wide_idx, h_wide_end = ffi.marshal_compact(h_chr, h_start, h_end, h_fo, width16_out=h_w16)
+            if packed:
+                h_run_off, h_run_chr, pk_bits, _, _, h_exc_idx, h_exc_start, h_exc_end = ffi.marshal_packed(
+                    h_chr, h_start, h_end, h_fo, packed_out=h_pk, anchors_out=h_an)
+            else:
+                h_run_off, h_run_chr, _, h_wide_idx, h_wide_end = ffi.marshal_compact(h_chr, h_start, h_end, h_fo, width16_out=h_w16)
             marshal_s.append(time.perf_counter() - t0)
         marshal_s = D.max(min(marshal_s))
         del h_chr
-        if compact:
+        if api != "runs":
             del h_end
+        if packed:
+            del h_start
         torch.cuda.synchronize()
         L = ffi.lib()
 
-        def e2e_call():
+        def e2e_on(ix):
+            if packed:
+                return ix.tokenize_files_packed(h_fo, h_run_off, h_run_chr, pk_bits, h_pk, h_an, h_exc_idx, h_exc_start, h_exc_end,
+                                                u["unk_id"], keep_buf=True)
             if compact:
-                return index.tokenize_files_compact(h_fo, h_run_off, h_run_chr, h_start, h_w16, h_wide_idx, h_wide_end, u["unk_id"],
-                                                    keep_buf=True)
-            return index.tokenize_files_runs(h_fo, h_run_off, h_run_chr, h_start, h_end, u["unk_id"], keep_buf=True)
+                return ix.tokenize_files_compact(h_fo, h_run_off, h_run_chr, h_start, h_w16, h_wide_idx, h_wide_end, u["unk_id"],
+                                                 keep_buf=True)
+            return ix.tokenize_files_runs(h_fo, h_run_off, h_run_chr, h_start, h_end, u["unk_id"], keep_buf=True)
+
+        def e2e_call():
+            return e2e_on(index)
 
         def e2e_step():
             off, buf = e2e_call()
@@ -863,17 +948,28 @@ def main():
         torch.cuda.synchronize()
         D.barrier()
         e2e_s = D.max((time.perf_counter() - t0) / args.steps)
-        h2d = (6 * n + 12 * len(h_wide_idx) if compact else 8 * n) + 8 * (n_files + 1) + 12 * len(h_run_chr) + 8
+        if packed:
+            h2d_q = 4 * n + 4 * ((n + 31) // 32) + 16 * len(h_exc_idx)
+        elif compact:
+            h2d_q = 6 * n + 12 * len(h_wide_idx)
+        else:
+            h2d_q = 8 * n
+        h2d = h2d_q + 8 * (n_files + 1) + 12 * len(h_run_chr) + 8
         d2h = 4 * e2e_total + 8 * (n_files + 1)
+        api_text = {
+            "packed": "gtgpu_tokenize_files_packed (pinned host: one u32 per region = offset from its 32-region block anchor | width, "
+                      "+ anchors + exceptions + chromosome runs in, pinned result buffer out)",
+            "compact": "gtgpu_tokenize_files_compact (pinned host start u32 + width u16 + chromosome runs in, pinned result buffer out)",
+            "runs": "gtgpu_tokenize_files_runs (pinned host start/end + chromosome runs in, pinned result buffer out)"}[api]
         e2e = {"value": total_queries / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": e2e_s * 1e3,
-               "api": ("gtgpu_tokenize_files_compact (pinned host start u32 + width u16 + chromosome runs in, pinned result buffer out)"
-                       if compact else "gtgpu_tokenize_files_runs (pinned host start/end + chromosome runs in, pinned result buffer out)"),
+               "ms_per_step": e2e_s * 1e3, "api": api_text,
                "ids_match_device_resident_path": e2e_matches_device, "chromosome_runs": int(len(h_run_chr)),
                "marshal": {"seconds": marshal_s, "threads": host_threads(),
-                           "what": "gtgpu_marshal_compact: flat (chr id, start, end) u32 arrays -> runs + u16 widths + exceptions, host side, "
-                                   "NOT inside ms_per_step",
+                           "what": ("gtgpu_marshal_packed" if packed else "gtgpu_marshal_compact") + ": flat (chr id, start, end) u32 "
+                                   "arrays -> the wire format above, host side, NOT inside ms_per_step",
                            "value_with_marshal": total_queries / (e2e_s + marshal_s), "unit": UNIT}}
+        if packed:
+            e2e["packed"] = {"width_bits": int(pk_bits), "exceptions": int(len(h_exc_idx)), "bytes_per_region": h2d_q / max(n, 1)}
         assert e2e_total == hits + n_empty_files
         if world > 1:
             # The drop-in form of multi-GPU use: ONE process (rank 0) drives all N GPUs through a multi-device context
@@ -887,8 +983,7 @@ def main():
                     mindex = ffi.Index(mctx, kind, offs, s, e, v)
 
                     def m_call():
-                        return mindex.tokenize_files_compact(h_fo, h_run_off, h_run_chr, h_start, h_w16, h_wide_idx, h_wide_end, u["unk_id"],
-                                                             keep_buf=True)
+                        return e2e_on(mindex)
                     off_m, buf_m = m_call()
                     ids_m = np.ctypeslib.as_array(C.cast(L.gtgpu_buf_data(buf_m), C.POINTER(C.c_uint32)), shape=(int(off_m[-1]),))
                     same = bool(int(off_m[-1]) == e2e_total and (n_empty_files > 0 or (
@@ -904,17 +999,15 @@ def main():
                     e2e["single_process_multi_device"] = {
                         "devices": world, "queries": n, "ms_per_call": m_s * 1e3, "value": n / m_s, "unit": UNIT,
                         "ids_match_device_resident_path": same, "scaling": "strong (one caller's batch over all devices)",
-                        "api": "gtgpu_init_multi + gtgpu_tokenize_files_compact: chunks dealt round-robin to the devices, ids land "
+                        "api": f"gtgpu_init_multi + gtgpu_tokenize_files_{api}: chunks dealt round-robin to the devices, ids land "
                                "at their final offsets in one pinned buffer"}
                     mindex.close()
                     mctx.close()
             except Exception as ex:
                 e2e["single_process_multi_device"] = {"error": repr(ex)}
             D.host_barrier()
-        ffi.pinned_free(h_start)
-        ffi.pinned_free(h_w16)
-        if not compact:
-            ffi.pinned_free(h_end)
+        for h_buf in ([h_pk, h_an] if packed else [h_start, h_w16] + ([h_end] if api == "runs" else [])):
+            ffi.pinned_free(h_buf)
         if not args.no_pcie_probe:
             try:
                 pcie = pcie_probe(torch, dev, D, h2d, d2h)
@@ -948,6 +1041,8 @@ def main():
                 rec = sub_c4(args, torch, dev, ctx, stream, D, rank, world, peak)
             elif name == "c5":
                 rec = sub_c5(args, torch, dev, ctx, stream, D, rank, world, peak, u, index)
+            elif name == "gz":
+                rec = sub_gz(args, torch, dev, ctx, stream, D, rank, world, peak, u, index)
             elif name == "backend":
                 rec = sub_backend(args, torch, dev, ctx, stream, D, rank, world, peak, u, offs, s, e, v,
                                   "ailist" if args.kind == "bits" else "bits")

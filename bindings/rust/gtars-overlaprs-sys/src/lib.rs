@@ -72,6 +72,16 @@ extern "C" {
                                  threads: i32, out_width16: *mut u16, run_capacity: u64, out_run_offsets: *mut u64,
                                  out_run_chr: *mut u32, out_n_runs: *mut u64, wide_capacity: u64, out_wide_index: *mut u64,
                                  out_wide_end: *mut u32, out_n_wide: *mut u64) -> i32;
+    pub fn gtgpu_tokenize_files_packed(index: *mut gtgpu_index, n_files: u64, file_offsets: *const u64, n_runs: u64,
+                                       run_offsets: *const u64, run_chr: *const u32, width_bits: u32, packed: *const u32,
+                                       anchors: *const u32, n_exc: u64, exc_index: *const u64, exc_start: *const u32,
+                                       exc_end: *const u32, unk_id: u32, out_file_token_offsets: *mut u64,
+                                       out_ids: *mut *mut gtgpu_buf) -> i32;
+    pub fn gtgpu_marshal_packed(n: u64, chr: *const u32, start: *const u32, end: *const u32, n_files: u64, file_offsets: *const u64,
+                                threads: i32, width_bits: u32, out_packed: *mut u32, out_anchors: *mut u32, run_capacity: u64,
+                                out_run_offsets: *mut u64, out_run_chr: *mut u32, out_n_runs: *mut u64, exc_capacity: u64,
+                                out_exc_index: *mut u64, out_exc_start: *mut u32, out_exc_end: *mut u32, out_n_exc: *mut u64,
+                                out_width_bits: *mut u32) -> i32;
     pub fn gtgpu_gzip_members(gz: *const u8, n_bytes: u64, capacity: u64, out_member_offsets: *mut u64, out_n_members: *mut u64) -> i32;
     pub fn gtgpu_gunzip(ctx: *mut gtgpu_ctx, n_members: u64, gz: *const u8, member_offsets: *const u64,
                         out_text: *mut *mut gtgpu_buf, out_member_offsets: *mut u64) -> i32;

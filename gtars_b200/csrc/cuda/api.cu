@@ -584,7 +584,8 @@ struct PipeDev {
     gtgpu_ctx* ctx = nullptr;
     uint32_t* in[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     uint16_t* d_w16[2] = {nullptr, nullptr};
-    uint32_t *d_ids = nullptr, *d_run_chr = nullptr, *d_wide_end = nullptr;
+    uint32_t* d_anc[2] = {nullptr, nullptr};
+    uint32_t *d_ids = nullptr, *d_run_chr = nullptr, *d_wide_end = nullptr, *d_exc_start = nullptr;
     uint64_t *d_fo = nullptr, *d_raw_tok = nullptr, *d_chain = nullptr, *d_misc = nullptr, *d_run_off = nullptr, *d_wide_idx = nullptr;
     void* d_ws = nullptr;
     uint64_t cap = 0, n_local = 0;
@@ -597,7 +598,10 @@ int32_t tokenize_files_pipelined(gtgpu_index* gix, uint64_t n, uint64_t n_files,
                                  uint64_t* out_file_tok, gtgpu_buf** out_ids, int* fallback, uint64_t n_runs = 0,
                                  const uint64_t* run_offsets = nullptr, const uint32_t* run_chr = nullptr,
                                  const uint16_t* width16 = nullptr, uint64_t n_wide = 0, const uint64_t* wide_index = nullptr,
-                                 const uint32_t* wide_end = nullptr) {
+                                 const uint32_t* wide_end = nullptr, const uint32_t* packed = nullptr,
+                                 const uint32_t* anchors = nullptr, uint32_t width_bits = 0, const uint32_t* exc_start = nullptr) {
+    // packed != nullptr: the packed wire format (start / end rebuilt on the device from packed words + block anchors; the
+    // exception list is (wide_index, exc_start, wide_end)); `start`, `end` and `width16` are then unused
     *fallback = 0;
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
     const size_t D = std::max<size_t>(gix->replicas.size(), 1);
@@ -673,7 +677,18 @@ int32_t tokenize_files_pipelined(gtgpu_index* gix, uint64_t n, uint64_t n_files,
                 GT_CUDA(cudaMemcpyAsync(d.d_run_chr, run_chr, n_runs * 4, cudaMemcpyHostToDevice, st));
             }
             // ends given as 16-bit widths (+ an exception list): 2 bytes per query cross PCIe instead of 4
-            if (width16) {
+            if (packed) {
+                GT_TRY(ctx->scratch_get(SC_BARCODE, chunk / 32 * 4 + 64, (void**)&d.d_anc[0]));
+                GT_TRY(ctx->scratch_get(SC_SET_ID, chunk / 32 * 4 + 64, (void**)&d.d_anc[1]));
+                if (n_wide) {
+                    GT_TRY(ctx->scratch_get(SC_IN3_END, n_wide * 8, (void**)&d.d_wide_idx));
+                    GT_TRY(ctx->scratch_get(SC_MATRIX, n_wide * 4, (void**)&d.d_wide_end));
+                    GT_TRY(ctx->scratch_get(SC_OUT_OFFS, n_wide * 4, (void**)&d.d_exc_start));
+                    GT_CUDA(cudaMemcpyAsync(d.d_wide_idx, wide_index, n_wide * 8, cudaMemcpyHostToDevice, st));
+                    GT_CUDA(cudaMemcpyAsync(d.d_wide_end, wide_end, n_wide * 4, cudaMemcpyHostToDevice, st));
+                    GT_CUDA(cudaMemcpyAsync(d.d_exc_start, exc_start, n_wide * 4, cudaMemcpyHostToDevice, st));
+                }
+            } else if (width16) {
                 GT_TRY(ctx->scratch_get(SC_BARCODE, chunk * 2, (void**)&d.d_w16[0]));
                 GT_TRY(ctx->scratch_get(SC_SET_ID, chunk * 2, (void**)&d.d_w16[1]));
                 if (n_wide) {
@@ -746,13 +761,23 @@ int32_t tokenize_files_pipelined(gtgpu_index* gix, uint64_t n, uint64_t n_files,
         fold(cudaSetDevice(ctx->device));
         if (i >= 2) fold(cudaStreamWaitEvent(ctx->copy_in, d.ev_free[b], 0));
         if (!run_offsets) fold(cudaMemcpyAsync(d.in[b][0], chr + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in));
-        fold(cudaMemcpyAsync(d.in[b][1], start + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in));
-        if (width16) fold(cudaMemcpyAsync(d.d_w16[b], width16 + q0, cn * 2, cudaMemcpyHostToDevice, ctx->copy_in));
-        else fold(cudaMemcpyAsync(d.in[b][2], end + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+        if (packed) {  // q0 is a multiple of the tile size, so the chunk starts on an anchor block
+            fold(cudaMemcpyAsync(d.in[b][1], packed + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+            fold(cudaMemcpyAsync(d.d_anc[b], anchors + q0 / 32, (cn + 31) / 32 * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+        } else {
+            fold(cudaMemcpyAsync(d.in[b][1], start + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+            if (width16) fold(cudaMemcpyAsync(d.d_w16[b], width16 + q0, cn * 2, cudaMemcpyHostToDevice, ctx->copy_in));
+            else fold(cudaMemcpyAsync(d.in[b][2], end + q0, cn * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+        }
         fold(cudaEventRecord(d.ev_in[b], ctx->copy_in));
         fold(cudaStreamWaitEvent(st, d.ev_in[b], 0));
         if (cerr != cudaSuccess) break;
-        if (width16) {
+        if (packed) {
+            const uint64_t lo = std::lower_bound(wide_index, wide_index + n_wide, q0) - wide_index;
+            const uint64_t hi = std::lower_bound(wide_index, wide_index + n_wide, q0 + cn) - wide_index;
+            status = launch_expand_packed(ctx, cn, d.in[b][1], d.d_anc[b], width_bits, d.in[b][1], d.in[b][2], hi - lo, d.d_wide_idx + lo,
+                                          d.d_exc_start + lo, d.d_wide_end + lo, q0);
+        } else if (width16) {
             const uint64_t lo = std::lower_bound(wide_index, wide_index + n_wide, q0) - wide_index;
             const uint64_t hi = std::lower_bound(wide_index, wide_index + n_wide, q0 + cn) - wide_index;
             status = launch_expand_widths(ctx, cn, d.in[b][1], d.d_w16[b], d.in[b][2], hi - lo, d.d_wide_idx + lo, d.d_wide_end + lo, q0);
@@ -927,6 +952,53 @@ int32_t gtgpu_tokenize_files_compact(gtgpu_index* ix, uint64_t n_files, const ui
     for (uint64_t i = 0; i < n; ++i) end[i] = start[i] + width16[i];
     for (uint64_t i = 0; i < n_wide; ++i) end[wide_index[i]] = wide_end[i];
     return tokenize_files_plain(ix, n, n_files, file_offsets, chr.data(), start, end.data(), unk_id, out_file_token_offsets, out_ids);
+} GT_CATCH
+
+int32_t gtgpu_tokenize_files_packed(gtgpu_index* ix, uint64_t n_files, const uint64_t* file_offsets, uint64_t n_runs,
+                                    const uint64_t* run_offsets, const uint32_t* run_chr, uint32_t width_bits, const uint32_t* packed,
+                                    const uint32_t* anchors, uint64_t n_exc, const uint64_t* exc_index, const uint32_t* exc_start,
+                                    const uint32_t* exc_end, uint32_t unk_id, uint64_t* out_file_token_offsets,
+                                    gtgpu_buf** out_ids) try {
+    if (!ix || !file_offsets || !run_offsets || !out_file_token_offsets || !out_ids || (n_runs && !run_chr) ||
+        (n_exc && (!exc_index || !exc_start || !exc_end)))
+        return fail(GTGPU_ERR_INVALID, "tokenize_files_packed: null argument");
+    if (width_bits < 1 || width_bits > 24) return fail(GTGPU_ERR_INVALID, "tokenize_files_packed: width_bits must be 1..24");
+    if (file_offsets[0] != 0 || run_offsets[0] != 0)
+        return fail(GTGPU_ERR_INVALID, "tokenize_files_packed: offsets must start at 0");
+    for (uint64_t f = 0; f < n_files; ++f)
+        if (file_offsets[f] > file_offsets[f + 1]) return fail(GTGPU_ERR_INVALID, "tokenize_files_packed: file_offsets not monotone");
+    for (uint64_t r = 0; r < n_runs; ++r)
+        if (run_offsets[r] > run_offsets[r + 1]) return fail(GTGPU_ERR_INVALID, "tokenize_files_packed: run_offsets not monotone");
+    const uint64_t n = file_offsets[n_files];
+    if (run_offsets[n_runs] != n) return fail(GTGPU_ERR_INVALID, "tokenize_files_packed: runs do not cover the queries");
+    if (n && (!packed || !anchors)) return fail(GTGPU_ERR_INVALID, "tokenize_files_packed: null query arrays");
+    for (uint64_t i = 0; i < n_exc; ++i)
+        if (exc_index[i] >= n || (i && exc_index[i] <= exc_index[i - 1]))
+            return fail(GTGPU_ERR_INVALID, "tokenize_files_packed: exc_index must be strictly increasing and < n");
+    std::unique_lock<std::mutex> glk;
+    if (is_group(ix)) glk = std::unique_lock<std::mutex>(ix->ctx->group_mu);
+    const uint64_t chunk = pipe_chunk(ix, n);
+    if (pipe_wanted(n, chunk)) {
+        int fallback = 0;
+        GT_TRY(tokenize_files_pipelined(ix, n, n_files, file_offsets, nullptr, nullptr, nullptr, chunk, out_file_token_offsets, out_ids,
+                                        &fallback, n_runs, run_offsets, run_chr, nullptr, n_exc, exc_index, exc_end, packed, anchors,
+                                        width_bits, exc_start));
+        if (!fallback) return GTGPU_OK;
+    }
+    // small batches and the rare fallbacks: expand on the host and take the plain path
+    std::vector<uint32_t> chr(n), start(n), end(n);
+    for (uint64_t r = 0; r < n_runs; ++r) std::fill(chr.begin() + run_offsets[r], chr.begin() + run_offsets[r + 1], run_chr[r]);
+    const uint32_t off_bits = 32 - width_bits, off_mask = (1u << off_bits) - 1u;
+    for (uint64_t i = 0; i < n; ++i) {
+        start[i] = anchors[i >> 5] + (packed[i] & off_mask);
+        end[i] = start[i] + (packed[i] >> off_bits);
+    }
+    for (uint64_t i = 0; i < n_exc; ++i) {
+        start[exc_index[i]] = exc_start[i];
+        end[exc_index[i]] = exc_end[i];
+    }
+    return tokenize_files_plain(ix, n, n_files, file_offsets, chr.data(), start.data(), end.data(), unk_id, out_file_token_offsets,
+                                out_ids);
 } GT_CATCH
 
 int32_t gtgpu_count_dev(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,

@@ -258,6 +258,9 @@ int32_t launch_expand_runs(gtgpu_ctx* ctx, uint64_t n_runs, const uint64_t* d_ru
                            uint64_t cn, uint32_t* d_out);
 int32_t launch_expand_widths(gtgpu_ctx* ctx, uint64_t n, const uint32_t* d_start, const uint16_t* d_w16, uint32_t* d_end,
                              uint64_t n_wide, const uint64_t* d_wide_index, const uint32_t* d_wide_end, uint64_t q0);
+int32_t launch_expand_packed(gtgpu_ctx* ctx, uint64_t n, const uint32_t* d_packed, const uint32_t* d_anchors, uint32_t width_bits,
+                             uint32_t* d_start, uint32_t* d_end, uint64_t n_exc, const uint64_t* d_exc_index,
+                             const uint32_t* d_exc_start, const uint32_t* d_exc_end, uint64_t q0);
 int32_t launch_fill_set_ids(gtgpu_ctx* ctx, uint64_t n_sets, const uint64_t* d_set_offsets, uint32_t* d_set_of);
 int32_t launch_unk_expand(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* d_raw_file_tok,
                           const uint64_t* d_out_file_tok, const uint32_t* d_raw_ids, uint32_t unk_id,

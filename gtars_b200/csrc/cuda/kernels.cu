@@ -1638,6 +1638,46 @@ int32_t launch_expand_widths(gtgpu_ctx* ctx, uint64_t n, const uint32_t* d_start
     return GTGPU_OK;
 }
 
+// Packed wire format (gtgpu_tokenize_files_packed): one 32-bit word per query = offset from the anchor of its 32-query block
+// | width << off_bits.  `packed` may alias `start` (every thread reads its word before it writes).  Exceptions carry their
+// absolute (start, end).  4 bytes per query (+ 1/8 for the anchors) cross PCIe instead of 6.
+__global__ void expand_packed_kernel(uint64_t n, const uint32_t* packed, const uint32_t* __restrict__ anchors, uint32_t off_bits,
+                                     uint32_t* start, uint32_t* __restrict__ end) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t off_mask = (1u << off_bits) - 1u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t w = packed[i];
+        const uint32_t s = anchors[i >> 5] + (w & off_mask);
+        start[i] = s;
+        end[i] = s + (w >> off_bits);
+    }
+}
+__global__ void patch_exceptions_kernel(uint64_t n_exc, const uint64_t* __restrict__ exc_index, const uint32_t* __restrict__ exc_start,
+                                        const uint32_t* __restrict__ exc_end, uint64_t q0, uint32_t* __restrict__ start,
+                                        uint32_t* __restrict__ end) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_exc) {
+        start[exc_index[i] - q0] = exc_start[i];
+        end[exc_index[i] - q0] = exc_end[i];
+    }
+}
+int32_t launch_expand_packed(gtgpu_ctx* ctx, uint64_t n, const uint32_t* d_packed, const uint32_t* d_anchors, uint32_t width_bits,
+                             uint32_t* d_start, uint32_t* d_end, uint64_t n_exc, const uint64_t* d_exc_index,
+                             const uint32_t* d_exc_start, const uint32_t* d_exc_end, uint64_t q0) {
+    if (n) {
+        const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 16);
+        expand_packed_kernel<<<grid, 256, 0, ctx->stream>>>(n, d_packed, d_anchors, 32u - width_bits, d_start, d_end);
+        ctx->launches++;
+    }
+    if (n_exc) {
+        patch_exceptions_kernel<<<(unsigned)((n_exc + 255) / 256), 256, 0, ctx->stream>>>(n_exc, d_exc_index, d_exc_start, d_exc_end, q0,
+                                                                                           d_start, d_end);
+        ctx->launches++;
+    }
+    GT_CUDA(cudaGetLastError());
+    return GTGPU_OK;
+}
+
 // ================================================================================================================
 // per-call [unk] rule (tokenizer.rs:158-160): a file whose raw id run is empty becomes the single id unk
 // ================================================================================================================

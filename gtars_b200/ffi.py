@@ -48,6 +48,9 @@ SIGNATURES = {
     "gtgpu_tokenize_files_runs": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
     "gtgpu_tokenize_files_compact": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _u32, _vp, _vp]),
     "gtgpu_marshal_compact": (_i32, [_u64, _vp, _vp, _vp, _u64, _vp, _i32, _vp, _u64, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "gtgpu_tokenize_files_packed": (_i32, [_vp, _u64, _vp, _u64, _vp, _vp, _u32, _vp, _vp, _u64, _vp, _vp, _vp, _u32, _vp, _vp]),
+    "gtgpu_marshal_packed": (_i32, [_u64, _vp, _vp, _vp, _u64, _vp, _i32, _u32, _vp, _vp, _u64, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp,
+                                    _vp]),
     "gtgpu_tokenize_fragments": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "gtgpu_tokenize_fragments_dev": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _u64, _vp]),
     "gtgpu_parse_bed": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -308,6 +311,19 @@ class Index:
             return out_off, h
         return out_off, _take(h)
 
+    def tokenize_files_packed(self, file_offsets, run_offsets, run_chr, width_bits, packed, anchors, exc_index, exc_start, exc_end,
+                              unk_id, keep_buf=False):
+        fo, ro = _arr(file_offsets, np.uint64), _arr(run_offsets, np.uint64)
+        rc, pk, an = _arr(run_chr, np.uint32), _arr(packed, np.uint32), _arr(anchors, np.uint32)
+        xi, xs, xe = _arr(exc_index, np.uint64), _arr(exc_start, np.uint32), _arr(exc_end, np.uint32)
+        out_off = np.empty(len(fo), dtype=np.uint64)
+        h = C.c_void_p()
+        check(lib().gtgpu_tokenize_files_packed(self._h, len(fo) - 1, _p(fo), len(rc), _p(ro), _p(rc), width_bits, _p(pk), _p(an),
+                                                len(xi), _p(xi), _p(xs), _p(xe), unk_id, _p(out_off), C.byref(h)))
+        if keep_buf:
+            return out_off, h
+        return out_off, _take(h)
+
     def tokenize_fragments(self, chr, start, end, barcode, n_barcodes, unk_id, keep_buf=False):
         chr, start, end, barcode = (_arr(a, np.uint32) for a in (chr, start, end, barcode))
         out_off = np.empty(n_barcodes + 1, dtype=np.uint64)
@@ -408,6 +424,30 @@ def marshal_compact(chr, start, end, file_offsets, width16_out=None, threads=0):
         check(st)
         return ro[:n_runs.value + 1], rc[:n_runs.value], w16, wi[:n_wide.value], we[:n_wide.value]
     raise GtarsGpuError(4, "marshal_compact: capacity retry failed")
+
+
+def marshal_packed(chr, start, end, file_offsets, width_bits=0, packed_out=None, anchors_out=None, threads=0):
+    """gtgpu_marshal_packed: (run_offsets, run_chr, width_bits, packed, anchors, exc_index, exc_start, exc_end) for
+    gtgpu_tokenize_files_packed."""
+    chr, start, end = _arr(chr, np.uint32), _arr(start, np.uint32), _arr(end, np.uint32)
+    fo = _arr(file_offsets, np.uint64)
+    n = len(chr)
+    pk = packed_out if packed_out is not None else np.empty(n, dtype=np.uint32)
+    an = anchors_out if anchors_out is not None else np.empty((n + 31) // 32, dtype=np.uint32)
+    run_cap, exc_cap = 64 * (len(fo) - 1) + 1024, 32 * (64 * (len(fo) - 1) + 1024)
+    for _ in range(2):
+        ro, rc = np.empty(run_cap + 1, dtype=np.uint64), np.empty(run_cap, dtype=np.uint32)
+        xi, xs, xe = np.empty(exc_cap, dtype=np.uint64), np.empty(exc_cap, dtype=np.uint32), np.empty(exc_cap, dtype=np.uint32)
+        n_runs, n_exc, wb = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+        st = lib().gtgpu_marshal_packed(n, _p(chr), _p(start), _p(end), len(fo) - 1, _p(fo), threads, width_bits, _p(pk), _p(an),
+                                        run_cap, _p(ro), _p(rc), C.byref(n_runs), exc_cap, _p(xi), _p(xs), _p(xe), C.byref(n_exc),
+                                        C.byref(wb))
+        if st == 4:  # GTGPU_ERR_CAPACITY: the needed counts came back
+            run_cap, exc_cap = max(n_runs.value, 1), max(n_exc.value, 1)
+            continue
+        check(st)
+        return (ro[:n_runs.value + 1], rc[:n_runs.value], wb.value, pk, an, xi[:n_exc.value], xs[:n_exc.value], xe[:n_exc.value])
+    raise GtarsGpuError(4, "marshal_packed: capacity retry failed")
 
 
 def gzip_members(gz: bytes) -> np.ndarray:

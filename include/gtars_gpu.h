@@ -164,6 +164,34 @@ int32_t gtgpu_marshal_compact(uint64_t n, const uint32_t* chr, const uint32_t* s
                               uint64_t* out_run_offsets, uint32_t* out_run_chr, uint64_t* out_n_runs, uint64_t wide_capacity,
                               uint64_t* out_wide_index, uint32_t* out_wide_end, uint64_t* out_n_wide);
 
+/* gtgpu_tokenize_files_runs with start AND width in ONE 32-bit word per query ("packed" wire format, 4.125 bytes of PCIe
+ * traffic per region instead of 6): queries are taken in blocks of 32 (block b = queries [32 b, 32 b + 32)), every block
+ * has an anchor, and
+ *     start[i] = anchors[i / 32] + (packed[i] & ((1 << (32 - width_bits)) - 1)),   end[i] = start[i] + (packed[i] >> (32 - width_bits))
+ * except for the queries listed in exc_index (strictly increasing), which are (exc_start[k], exc_end[k]).  A file read by
+ * RegionSet::try_from is sorted by (chromosome, start) (gtars-core/src/models/region_set.rs:502-505), so inside a block the
+ * offsets are small; what does not fit (the far side of a chromosome / file boundary inside a block, wide or reversed
+ * regions) is an exception.  anchors has ceil(n / 32) entries; width_bits is 1..24.  Results are identical to
+ * gtgpu_tokenize_files on the expanded arrays. */
+int32_t gtgpu_tokenize_files_packed(gtgpu_index* index, uint64_t n_files, const uint64_t* file_offsets, uint64_t n_runs,
+                                    const uint64_t* run_offsets, const uint32_t* run_chr, uint32_t width_bits,
+                                    const uint32_t* packed, const uint32_t* anchors, uint64_t n_exc, const uint64_t* exc_index,
+                                    const uint32_t* exc_start, const uint32_t* exc_end, uint32_t unk_id,
+                                    uint64_t* out_file_token_offsets, gtgpu_buf** out_ids);
+
+/* Host-side marshalling for gtgpu_tokenize_files_packed (no device work; `threads` host threads, 0 = all cores): chromosome
+ * runs as in gtgpu_marshal_compact, packed words (out_packed[n]), block anchors (out_anchors[ceil(n / 32)]; the start of the
+ * block's first query, or of the first query after a descent when that leaves fewer exceptions) and the exception list.
+ * width_bits = 0 lets the packer choose the split (6..16 bits of width, fewest exceptions on a sample of blocks);
+ * *out_width_bits receives the split used.  Unsorted inputs still round-trip exactly — as exceptions, 16 bytes each — so a
+ * caller compares *out_n_exc with n before preferring this format.  GTGPU_ERR_CAPACITY when a capacity was too small (the
+ * needed counts are returned). */
+int32_t gtgpu_marshal_packed(uint64_t n, const uint32_t* chr, const uint32_t* start, const uint32_t* end, uint64_t n_files,
+                             const uint64_t* file_offsets, int32_t threads, uint32_t width_bits, uint32_t* out_packed,
+                             uint32_t* out_anchors, uint64_t run_capacity, uint64_t* out_run_offsets, uint32_t* out_run_chr,
+                             uint64_t* out_n_runs, uint64_t exc_capacity, uint64_t* out_exc_index, uint32_t* out_exc_start,
+                             uint32_t* out_exc_end, uint64_t* out_n_exc, uint32_t* out_width_bits);
+
 /* tokenize_fragment_file (gtars-tokenizers/src/utils/fragments.rs:12-82) over pre-parsed fragments: every fragment
  * is one Tokenizer::tokenize call (a fragment with no hit, or on an unknown chromosome, yields unk_id), ids are
  * appended to the fragment's barcode list in input order.  barcode_id[i] < n_barcodes (dense ids, mapped by the

@@ -88,3 +88,50 @@ def test_marshal_compact_matches_numpy():
         assert np.array_equal(w16[~wide], (end - start)[~wide].astype(np.uint16)) and (w16[wide] == 0xFFFF).all()
     ro, rc, w16, wi, we = ffi.marshal_compact(chr_[:0], start[:0], end[:0], np.zeros(1, np.uint64))
     assert len(rc) == 0 and len(wi) == 0 and ro[0] == 0
+
+
+def _unpack(n, wb, pk, an, xi, xs, xe):
+    off_bits = 32 - wb
+    start = (an[np.arange(n) >> 5] + (pk & np.uint32((1 << off_bits) - 1))).astype(np.uint32)
+    end = (start + (pk >> np.uint32(off_bits))).astype(np.uint32)
+    start[xi.astype(np.int64)] = xs
+    end[xi.astype(np.int64)] = xe
+    return start, end
+
+
+def test_marshal_packed_round_trips():
+    """gtgpu_marshal_packed is host code: whatever the input, (packed, anchors, exceptions) decode to the caller's arrays; sorted
+    files cost few exceptions (only around run boundaries), unsorted input degrades to exceptions but stays exact."""
+    from gtars_b200 import ffi
+    rng = np.random.default_rng(11)
+    n_files, per = 7, 150_001                       # odd sizes: file and run boundaries fall inside 32-query blocks
+    n = n_files * per
+    fo = (np.arange(n_files + 1) * per).astype(np.uint64)
+    chr_ = np.concatenate([np.sort(rng.integers(0, 25, per)) for _ in range(n_files)]).astype(np.uint32)
+    start = rng.integers(0, 200_000_000, n).astype(np.uint32)
+    # RegionSet::sort order inside every file: by chromosome, then start
+    for f in range(n_files):
+        a, b = f * per, (f + 1) * per
+        o = np.lexsort((start[a:b], chr_[a:b]))
+        start[a:b] = start[a:b][o]
+    end = (start + rng.integers(150, 1000, n)).astype(np.uint32)
+    end[5] = start[5] - 3                            # reversed
+    end[77_777] = start[77_777] + 5_000_000          # wide
+    for threads in (1, 3, 0):
+        ro, rc, wb, pk, an, xi, xs, xe = ffi.marshal_packed(chr_, start, end, fo, threads=threads)
+        ro2, rc2, _, _, _ = ffi.marshal_compact(chr_, start, end, fo, threads=threads)
+        assert np.array_equal(ro, ro2) and np.array_equal(rc, rc2)
+        assert 6 <= wb <= 16 and len(an) == (n + 31) // 32
+        assert np.all(np.diff(xi.astype(np.int64)) > 0) and {5, 77_777} <= set(xi.tolist())
+        assert len(xi) < 32 * len(rc)                # only blocks that hold a run boundary have exceptions (+ the two above)
+        s2, e2 = _unpack(n, wb, pk, an, xi, xs, xe)
+        assert np.array_equal(s2, start) and np.array_equal(e2, end)
+    # a fixed split, unsorted starts, a ragged tail block
+    m = 100_003
+    us, ue = rng.integers(0, 1 << 32, m, dtype=np.uint64).astype(np.uint32), rng.integers(0, 1 << 32, m, dtype=np.uint64).astype(np.uint32)
+    ro, rc, wb, pk, an, xi, xs, xe = ffi.marshal_packed(chr_[:m], us, ue, np.array([0, m], np.uint64), width_bits=12)
+    assert wb == 12
+    s2, e2 = _unpack(m, wb, pk, an, xi, xs, xe)
+    assert np.array_equal(s2, us) and np.array_equal(e2, ue)
+    ro, rc, wb, pk, an, xi, xs, xe = ffi.marshal_packed(chr_[:0], start[:0], end[:0], np.zeros(1, np.uint64))
+    assert len(rc) == 0 and len(xi) == 0 and ro[0] == 0

@@ -81,6 +81,9 @@ def test_tokenize_files_all_entry_points(ctxs, kind, chunk, monkeypatch):
     assert np.array_equal(want[0], got[0]) and np.array_equal(want[1], got[1])
     got = gm.tokenize_files_compact(fo, ro, rc, qs, w16, wi, we, u["unk_id"])
     assert np.array_equal(want[0], got[0]) and np.array_equal(want[1], got[1])
+    ro, rc, wb, pk, an, xi, xs, xe = ffi.marshal_packed(qc, qs, qe, fo)
+    got = gm.tokenize_files_packed(fo, ro, rc, wb, pk, an, xi, xs, xe, u["unk_id"])
+    assert np.array_equal(want[0], got[0]) and np.array_equal(want[1], got[1])
     # ragged files, two of them without any token (all queries on an unknown chromosome): the [unk] rule
     fo2 = np.array([0, 10, 10, 400_000, 400_003, 900_000, len(qc)], dtype=np.uint64)
     qc2 = qc.copy()

@@ -548,6 +548,19 @@ def test_tokenize_files_runs_variant(ctx, monkeypatch):
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
     with pytest.raises(GtarsGpuError):
         g.tokenize_files_compact(fo, run_offsets, run_chr, qs, w16, [5, 5], [1, 2], u["unk_id"])  # not strictly increasing
+    # packed wire format: one word per query (offset from the block anchor | width), exceptions with absolute coordinates
+    from gtars_b200 import ffi
+    for wb in (0, 8, 16):
+        ro, rc, wbits, pk, an, xi, xs, xe = ffi.marshal_packed(qc, qs, qe2, fo, width_bits=wb)
+        assert len(xi) >= 300 and (wb == 0 or wbits == wb)
+        for chunk in ("1000000000", "4096"):
+            monkeypatch.setenv("GTGPU_PIPE_CHUNK", chunk)
+            got = g.tokenize_files_packed(fo, ro, rc, wbits, pk, an, xi, xs, xe, u["unk_id"])
+            assert np.array_equal(got[0], want2[0]) and np.array_equal(got[1], want2[1])
+    with pytest.raises(GtarsGpuError):
+        g.tokenize_files_packed(fo, ro, rc, 0, pk, an, xi, xs, xe, u["unk_id"])  # width_bits out of range
+    with pytest.raises(GtarsGpuError):
+        g.tokenize_files_packed(fo, ro, rc, wbits, pk, an, [5, 5], [1, 2], [3, 4], u["unk_id"])  # not strictly increasing
 
 
 @pytest.mark.parametrize("kind", ["bits", "ailist"])
