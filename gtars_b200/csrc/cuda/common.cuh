@@ -86,13 +86,22 @@ struct ChromMeta {    // 32 bytes
 // (measured: 10.9 -> 9.8 ms per 1e9 queries; an 8-byte record that left two-candidate windows to bt_ent was slower).
 // Coordinates are relative to the window base (b << bt_shift) and clamped to [0, 2^(bt_shift+1)]: a fast-path query
 // starts in bin b and ends inside the window, so the clamped values compare (and overlap-measure) exactly like the
-// absolute ones.  rel = s_rel | e_rel << (bt_shift + 2); needs 2 + 2 (bt_shift + 2) <= 32 bits: bt_shift <= 13.
-//   word 0 = kind | rel0 << 2,  kind 0 = empty, 1 = one candidate inline, 2 = two candidates, 3 = pool list / overflow
-//   word 1 = val0,  word 2 = rel1 << 2,  word 3 = val1 (second candidate, kind 2)
-//   kind 3: word 1 = the window's bt_lut word (pool list offset and length, or BT_OVERFLOW)
+// absolute ones; bt_shift <= 13 keeps them below 2^15.  A candidate is ONE precomputed word:
+//   word 0 / 2 = ((e_rel + 0x7FFF) << 16) - s_rel      (absent candidate: e_rel = s_rel = 0, i.e. BT_REC_EMPTY)
+//   word 1 / 3 = val of that candidate
+// A window query (s_rel = start - base < 2^shift, d = end - 1 - base < 2^(shift+1)) hits the candidate iff
+// s_rel_c <= d and s_rel <= e_rel_c - 1, i.e. iff bits 15 and 31 of
+//   T = word + ((d + 0x8000) - (s_rel << 16))  =  [ (e_rel_c - 1 + 0x8000) - s_rel ] << 16  |  [ (d + 0x8000) - s_rel_c ]
+// are both set (neither half can borrow or carry: every operand is below 2^15) — one add and one logic op per candidate
+// (round 2: bit fields that had to be shifted and masked apart cost 7 instructions per candidate; 5.88 -> 5.75 ms).
+// The bp filter (min_overlap > 1) recovers the coordinates: s_rel_c = -word mod 2^16, e_rel_c from the upper half.
+//   pool list / overflow window: word 0 = BT_REC_SLOW, word 1 = the window's bt_lut word (list offset and length, or
+//   BT_OVERFLOW), word 2 = BT_REC_EMPTY.
 // bt_lut / bt_ent / bt_pool stay the slow path's view of the same windows (pool lists, multi-window queries).
 #define BT_REC_WORDS 4
 #define BT_REC_MAX_SHIFT 13u
+#define BT_REC_EMPTY 0x7FFF0000u
+#define BT_REC_SLOW 0xFFFFFFFFu
 
 struct ChromBT {         // 8 bytes
     uint32_t off;        // first bin record of this chromosome

@@ -410,14 +410,16 @@ int32_t host_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_chroms, const 
             chrom_bt[c].off = (uint32_t)pos;
             if (chroms[c].seg_end == chroms[c].seg_begin) {
                 chrom_bt[c].n_bins = 0;  // absent chromosome: nothing can hit
-            } else if (!cover_end[c] || !enabled) {
+                chrom_bt[c].off = 0;     // (its one readable record is the global empty sentinel)
+            } else if (!cover_end[c] || !enabled || (uint64_t)cover_end[c] > 0xFFFFFFFFull - (8ull << bt_shift)) {
+                // (a table never reaches the top of the u32 range: the lean kernel's window test relies on it for e == 0)
                 chrom_bt[c].n_bins = BT_GENERIC_CHROM;
                 chrom_bt[c].off = 0;
             } else {
                 uint64_t nb = ((cover_end[c] - 1) >> bt_shift) + 1;
                 if (nb >= BT_NBINS_MASK) return fail(GTGPU_ERR_UNSUPPORTED, "index_build: too many bins on one chromosome");
                 chrom_bt[c].n_bins = (uint32_t)nb;
-                pos += nb;
+                pos += nb + 1;  // + one always-empty record: where the fused kernel sends bins past the chromosome's last one
             }
         }
         auto has_table = [&](uint32_t c) { return chrom_bt[c].n_bins != 0 && !(chrom_bt[c].n_bins & BT_GENERIC_CHROM); };
@@ -524,12 +526,12 @@ int32_t host_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_chroms, const 
         bt_ent[total] = bt_ent[total + 1] = make_uint4(0xFFFFFFFFu, 0, 0, 0);
         // Window records: the direct runs again, inline and window-relative (record 0 stays the empty sentinel).
         bt_rec.assign(pos * BT_REC_WORDS, 0);
-        const uint32_t rel_bits = bt_shift + 2;
         const uint64_t rel_max = 2ull << bt_shift;
+        for (uint64_t k = 0; k < pos; ++k) bt_rec[k * BT_REC_WORDS] = bt_rec[k * BT_REC_WORDS + 2] = BT_REC_EMPTY;
         auto rel = [&](uint32_t i, uint64_t base) {
             const uint64_t s = h_starts[i] <= base ? 0 : std::min<uint64_t>(h_starts[i] - base, rel_max);
             const uint64_t e = h_ends[i] <= base ? 0 : std::min<uint64_t>(h_ends[i] - base, rel_max);
-            return (uint32_t)(s | (e << rel_bits));
+            return (uint32_t)(((e + 0x7FFFu) << 16) - s);
         };
         parallel_for(n_chroms, [&](uint64_t cc) {
             const uint32_t c = (uint32_t)cc;
@@ -541,15 +543,15 @@ int32_t host_index_build(gtgpu_ctx* ctx, int32_t kind, uint32_t n_chroms, const 
                 uint32_t* r = &bt_rec[k * BT_REC_WORDS];
                 if (w == 0) continue;
                 if (w & BT_POOL_FLAG) {  // pool list or overflow (BT_OVERFLOW has the flag bit too)
-                    r[0] = 3;
+                    r[0] = BT_REC_SLOW;
                     r[1] = w;  // the full kernel walks the pool list straight from the record
                     continue;
                 }
                 const uint32_t first = w >> 2, cnt = w & 3;
-                r[0] = cnt | (rel(first, base) << 2);
+                r[0] = rel(first, base);
                 r[1] = h_vals[first];
                 if (cnt == 2) {
-                    r[2] = rel(first + 1, base) << 2;
+                    r[2] = rel(first + 1, base);
                     r[3] = h_vals[first + 1];
                 }
             }
@@ -603,6 +605,7 @@ int32_t host_index_upload(gtgpu_ctx* ctx, const HostIndex& H, gtgpu_index** out_
     ix->bt_clean = H.bt_overflow == 0 && H.bt_pool_windows == 0 && H.total > 0;
     for (uint32_t c = 0; c < H.n_chroms; ++c)
         if (H.chrom_bt[c].n_bins & BT_GENERIC_CHROM) ix->bt_clean = false;
+    if (H.n_chroms >= (uint32_t)CHROM_CACHE) ix->bt_clean = false;  // the lean kernel reads chromosome entries from its shared-memory cache only
     if (ix->bt_clean && cudaHostAlloc((void**)&ix->h_lean_probe, 4, cudaHostAllocDefault) == cudaSuccess) *ix->h_lean_probe = 0;
     else { ix->h_lean_probe = nullptr; cudaGetLastError(); }
     up(H.chroms, &v.chroms);

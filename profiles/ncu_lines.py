@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-source-line digest of an ncu report: executed warp instructions and stall samples per CUDA source line.
 
-usage: ncu_lines.py <report.ncu-rep> <lib.so> <mangled-kernel-substring> <warp_tiles> [min_inst_per_tile]
+usage: ncu_lines.py <report.ncu-rep> <lib.so> <mangled-kernel-substring> <warp_tiles> [min_inst_per_tile] [demangled-name-hint]
 Joins `ncu --page source --print-source sass` (per-SASS counters) with `nvdisasm -g` line info of the same cubin.
 """
 import csv, io, os, re, subprocess, sys, tempfile
@@ -12,8 +12,13 @@ thr = float(sys.argv[5]) if len(sys.argv) > 5 else 1.5
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sass_csv = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(sass_csv)))
+# a report may hold several kernels: take the first one whose name contains the demangled hint in argv[6] (default: the first)
+kidx = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+hint = sys.argv[6] if len(sys.argv) > 6 else ""
+k = next(j for j in range(len(kidx) - 1) if hint in rows[kidx[j]][1])
+rows = rows[kidx[k]:kidx[k + 1]]
 hi = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
-hdr, data = rows[hi], rows[hi + 1:]
+hdr, data = rows[hi], [r for r in rows[hi + 1:] if len(r) == len(rows[hi])]
 ia, isamp = hdr.index("Instructions Executed"), hdr.index("# Samples")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 with tempfile.TemporaryDirectory() as td:

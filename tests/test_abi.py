@@ -189,12 +189,14 @@ def test_device_code_is_sm100a_and_keeps_its_resource_budgets():
                  "count_gather_kernel", "igd_count_kernel", "radix_scatter_kernel", "scan_down_kernel", "score_hist_kernel",
                  "ingest_parse_lines_kernel", "untranspose_blocks_kernel"):
         assert any(name in k for k in res), f"{name} missing from the device code"
-    # lean fused find kernel: template flags <ROWS=4, DESC, FILTER, OFFS, LEAN=1>; 48 registers, no stack = 5 CTAs per SM
-    lean = [v for k, v in res.items() if "fused_find_kernelILi4E" in k and k.split("fused_find_kernelILi4E")[1].startswith("Lb") and
-            re.match(r"(Lb[01]E){3}Lb1E", k.split("fused_find_kernelILi4E")[1])]
-    assert lean, "no lean instantiation of the fused kernel"
-    for reg, stack, shared in lean:
-        assert reg <= 48 and stack == 0 and shared <= 24 * 1024, (reg, stack, shared)
+    # lean fused find kernel: template flags <ROWS=4, DESC, FILTER, OFFS, LEAN=1>; no stack; 40 registers = 6 CTAs per SM
+    # (tokenize), 48 registers = 5 CTAs per SM when it also writes per-query offsets (find, fragments)
+    lean = [(re.match(r"(?:Lb[01]E){2}Lb([01])ELb1E", k.split("fused_find_kernelILi4E")[1]), v) for k, v in res.items()
+            if "fused_find_kernelILi4E" in k]
+    lean = [(m.group(1) == "1", v) for m, v in lean if m]
+    assert lean and any(o for o, _ in lean) and any(not o for o, _ in lean), "lean instantiations of the fused kernel missing"
+    for offs, (reg, stack, shared) in lean:
+        assert reg <= (48 if offs else 40) and stack == 0 and shared <= 24 * 1024, (offs, reg, stack, shared)
     part = [v for k, v in res.items() if "count_partition_kernel" in k]
     assert all(reg <= 64 and stack == 0 for reg, stack, _ in part), part   # two 512-thread CTAs per SM
 
