@@ -130,6 +130,13 @@ struct IndexView {
     // one DRAM sector per search instead of a LUT read plus a bisection over 32-byte sectors of the sorted array.
     const unsigned long long* rank_lut;
     uint32_t rank_shift, rank_inline;
+    // The rank LUT holds the starts LUTs of all chromosomes back to back, then (from word rank_ends_off) their ends LUTs.
+    // rank_lin[c] = {first starts word << rank_shift, starts bins << rank_shift, first ends word (inside the ends block) <<
+    // rank_shift, ends bins << rank_shift}: lin = .x + min(key, .y) names the LUT word (lin >> rank_shift) AND the in-bin
+    // offset (low bits) of a starts search without the chromosome — 4 bytes per search for the bucketed counting pass.
+    // nullptr when a block's linearised span does not fit 32 bits (that pass is then not used).
+    const uint4* rank_lin;
+    uint32_t rank_ends_off;
     uint32_t n_chroms;
     uint32_t shift;
     uint32_t descending;  // 1 = AIList emission order (descending position inside a segment)
@@ -226,7 +233,7 @@ enum ScratchRole {
     SC_CHR = 0, SC_START, SC_END, SC_BARCODE, SC_OUT_IDS, SC_OUT_IDS2, SC_OUT_OFFS, SC_FILE_OFFS, SC_FILE_TOK,
     SC_FILE_TOK2, SC_TILE_STATUS, SC_TILE_FILE, SC_MISC, SC_COUNTS, SC_IN2_CHR, SC_IN2_START, SC_IN2_END,
     SC_IN3_CHR, SC_IN3_START, SC_IN3_END, SC_SET_ID, SC_MATRIX, SC_ING_0, SC_ING_1, SC_ING_2, SC_ING_3, SC_ING_4, SC_ING_5,
-    SC_ING_6, SC_ING_7, SC_GZ_IN, SC_GZ_OUT, SC_GZ_MOFF, SC_GZ_OOFF, SC_GZ_STATUS, SC_CNT_CHR, SC_CNT_START, SC_CNT_END, SC_CNT_SLOT, SC_CNT_TMP, SC_CNT_CURSORS, SC_N_ROLES
+    SC_ING_6, SC_ING_7, SC_GZ_IN, SC_GZ_OUT, SC_GZ_MOFF, SC_GZ_OOFF, SC_GZ_STATUS, SC_CNT_KEYS, SC_CNT_RES, SC_CNT_POS, SC_CNT_RUNS, SC_N_ROLES
 };
 
 // kernels.cu

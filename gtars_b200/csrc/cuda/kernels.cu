@@ -286,133 +286,162 @@ __global__ void __launch_bounds__(256) count_kernel_x4(IndexView ix, uint64_t n,
     }
 }
 
-// ---- partitioned counting: databases whose rank LUTs exceed the L2 ------------------------------------------
-// A search through the rank LUT is one 8-byte load, but with unsorted queries over a 50 M-interval database (C3:
-// 1.5 GB of LUT words) every one of them is a random DRAM sector.  One coarse radix pass over the queries (the
-// bucket = the position of the query's LUT word >> bucket_shift, 32 to CP_MAX_BUCKETS of them) makes the counting pass
-// sweep the LUT once, slice by slice, each slice small enough to stay in the L2 while its bucket is being resolved.
-//   1. count_bucket_hist_kernel + one exclusive scan: where each tile's run of each bucket starts;
-//   2. count_partition_kernel: a tile of CP_TILE queries is grouped by bucket in shared memory and written as
-//      coalesced runs of (chr, start, end), plus, per query in input order, the slot it went to (tiles keep their order inside a bucket);
-//   3. the counting kernel over the bucketed queries (slot order), on a grid that is resident all at once;
-//   4. count_gather_kernel out[i] = tmp[slot[i]] reads one slowly advancing front per bucket: every sector once.
-// Results do not depend on the slots: out[] is identical to the direct pass.
-constexpr int CP_MAX_BUCKETS = 256;  // bucket ids fit a byte; the actual number (a power of two >= 32) is chosen per launch
-#ifndef GT_CP_THREADS
-#define GT_CP_THREADS 512
-#endif
-#ifndef GT_CP_ITEMS
-#define GT_CP_ITEMS 8
-#endif
-#ifndef GT_CP_MINBLOCKS
-#define GT_CP_MINBLOCKS 2
-#endif
-constexpr int CP_THREADS = GT_CP_THREADS;  // >= CP_MAX_BUCKETS
-constexpr int CP_ITEMS = GT_CP_ITEMS;
-constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
-constexpr int CP_STAGE_BYTES = CP_TILE * 13;        // (chr, start, end) + bucket byte per staged query
-
-__device__ __forceinline__ uint32_t count_bucket_of(const IndexView& ix, uint32_t bucket_shift, uint32_t nb, uint32_t c, uint32_t e) {
-    if (c >= ix.n_chroms) return 0;
-    const uint2 w = __ldg(reinterpret_cast<const uint2*>(ix.chroms + c) + 2);  // lut_cs, nb_cs
-    const uint32_t bin = min(e >> ix.rank_shift, w.y);
-    // the chromosome's starts LUT and ends LUT lie back to back: 2 x bin is about where both words of this query are
-    const uint64_t pos = (uint64_t)w.x + 2ull * bin;
-    return (uint32_t)min(pos >> bucket_shift, (uint64_t)(nb - 1));
+// ---- TMA (bulk async copy) staging of a tile's query rows into shared memory ------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
+}
+// L2 residency: the bin table is re-read by every tile (evict_last), queries and ids are touched once (evict_first).
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 
-// Per-tile bucket histogram, bucket-major ([bucket][tile]) so that ONE exclusive scan over the whole array yields the
-// slot where each tile's run of each bucket starts: no atomics on shared cursors (48 k tiles x 128 buckets adding to
-// the same 128 words serialised in the L2 and made the partition 6x slower at 1e8 queries), and a stable partition.
-__global__ void __launch_bounds__(CP_THREADS) count_bucket_hist_kernel(IndexView ix, uint64_t n, uint32_t bucket_shift, uint32_t nb,
-                                                                        const uint32_t* __restrict__ chr,
-                                                                        const uint32_t* __restrict__ end,
-                                                                        uint32_t* __restrict__ tile_hist) {
-    __shared__ uint32_t s_cnt[CP_MAX_BUCKETS];
-    const uint32_t tid = threadIdx.x;
-    const uint64_t n_tiles = (n + CP_TILE - 1) / CP_TILE;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t t0 = tile * CP_TILE;
-        const uint32_t tn = (uint32_t)min((uint64_t)CP_TILE, n - t0);
+// ---- bucketed counting: databases whose rank LUTs exceed the L2 ----------------------------------------------
+// A search through the rank LUT is one 8-byte load, but with unsorted queries over a 50 M-interval database (C3:
+// 0.8-1.5 GB of LUT words) every one of them is a random DRAM sector.  The bucketed pass makes the counting kernel sweep
+// the LUT once, slice by slice, each slice small enough to stay in the L2 while its bucket is being resolved — WITHOUT
+// a global partition of the queries (round 1: histogram + scan + partition + count + gather, 8.0 GB of traffic for
+// 2.0 GB of algorithmic bytes):
+//   1. count_stage_kernel: a tile of CP_TILE queries is reduced to the two linearised search keys of each query
+//      (IndexView::rank_lin: 8 bytes instead of 12, no chromosome look-up later), grouped by bucket in shared memory
+//      (bucket = position of the starts-LUT word >> bucket_shift) and written to the TILE'S OWN region of the staging
+//      array, runs padded to whole 64-byte lines.  Per tile and bucket one word (run start | run length) goes into a
+//      bucket-major table; per query a 16-bit staged position.  No histogram pass, no scan, no slots.
+//   2. count_runs_kernel: one warp per (bucket, tile) run, runs taken bucket-major by a grid that is resident all at
+//      once: the two LUT words of a query are its only gathers.  Results are written over the same staged positions.
+//   3. count_unstage_kernel: a tile's results come back as ONE contiguous read and are put back into query order through
+//      shared memory (position 0xFFFF = a query the identity does not cover: walked here, from the original arrays).
+// Results do not depend on the staging: out[] is identical to the direct pass.
+constexpr int CP_MAX_BUCKETS = 256;
+constexpr int CP_THREADS = 1024;
+constexpr int CP_ITEMS = 4;  // consecutive queries per thread: 128-bit query loads
+constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
+constexpr int CP_PAD = 8;               // runs start on multiples of 8 staged entries (64 B of keys, 32 B of u32 results)
+constexpr uint32_t CP_WALK = 0xFFFFu;   // staged position of a query that bypasses the identity
+constexpr int CP_CHROM_CACHE = 256;     // rank_lin entries kept in shared memory
+static_assert(CP_TILE + CP_PAD * CP_MAX_BUCKETS < (int)CP_WALK, "staged positions are 16 bits");
+static_assert(CP_TILE <= 0xFFFF, "run lengths are 16 bits");
+
+// RAW: Bits::count's wrapping identity (every query with a known chromosome takes it); else count / any (start < end).
+// The three query rows of the block's NEXT tile are fetched by bulk copies (TMA, evict-first) into shared memory while
+// the current tile is grouped and written out (the phases of a tile are separated by block barriers, and the two
+// 1024-thread blocks of an SM need no registers for rows that are still on their way).
+template <bool RAW>
+__global__ void __launch_bounds__(CP_THREADS, 2)
+count_stage_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint32_t bucket_shift, uint32_t nb, uint32_t cap,
+                   const uint32_t* __restrict__ chr, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
+                   uint2* __restrict__ keys, uint16_t* __restrict__ pos, uint32_t* __restrict__ runs, uint32_t* __restrict__ tile_used,
+                   uint32_t* __restrict__ run_counter) {
+    __shared__ uint32_t s_cnt[CP_MAX_BUCKETS];   // tile histogram = rank dispenser
+    __shared__ uint32_t s_base[CP_MAX_BUCKETS];  // first staged position of each bucket's run
+    __shared__ uint32_t s_used;
+    __shared__ uint4 s_lin[CP_CHROM_CACHE];
+    __shared__ __align__(8) uint64_t s_bar;
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    uint32_t* s_in = reinterpret_cast<uint32_t*>(s_dyn);                  // 3 x CP_TILE: chr, start, end of a whole tile
+    uint2* s_keys = reinterpret_cast<uint2*>(s_dyn + 3 * CP_TILE * 4);    // cap entries: the tile grouped by bucket
+    const uint32_t tid = threadIdx.x, rs = ix.rank_shift;
+    // a whole tile comes through the bulk copies (the launcher checked the 16-byte alignment of the three arrays)
+    auto whole = [&](uint32_t tile) { return tile < n_tiles && ((uint64_t)tile + 1) * CP_TILE <= n; };
+    auto fetch = [&](uint32_t tile) {  // one thread
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the buffer are done
+        mbar_expect_tx(&s_bar, 3 * CP_TILE * 4);
+        const uint64_t q0 = (uint64_t)tile * CP_TILE, pol = policy_evict_first();
+        bulk_g2s(s_in, chr + q0, CP_TILE * 4, &s_bar, pol);
+        bulk_g2s(s_in + CP_TILE, start + q0, CP_TILE * 4, &s_bar, pol);
+        bulk_g2s(s_in + 2 * CP_TILE, end + q0, CP_TILE * 4, &s_bar, pol);
+    };
+    for (uint32_t i = tid; i < (uint32_t)CP_CHROM_CACHE && i < ix.n_chroms; i += CP_THREADS) s_lin[i] = __ldg(ix.rank_lin + i);
+    if (tid == 0) {
+        if (blockIdx.x == 0) *run_counter = 0;  // the chunk dispenser of count_runs_kernel
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (whole(blockIdx.x)) fetch(blockIdx.x);
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t t0 = (uint64_t)tile * CP_TILE;
+        const uint32_t tn = (uint32_t)min((uint64_t)CP_TILE, n - t0), j0 = tid * CP_ITEMS;
         if (tid < CP_MAX_BUCKETS) s_cnt[tid] = 0;
-        __syncthreads();
-        uint32_t qc[CP_ITEMS], qe[CP_ITEMS];
+        uint32_t qc[CP_ITEMS], qs[CP_ITEMS], qe[CP_ITEMS];
+        if (tn == (uint32_t)CP_TILE) {
+            mbar_wait(&s_bar, phase);
+            phase ^= 1u;
+            const uint4 c4 = reinterpret_cast<const uint4*>(s_in)[tid];
+            const uint4 s4 = reinterpret_cast<const uint4*>(s_in + CP_TILE)[tid];
+            const uint4 e4 = reinterpret_cast<const uint4*>(s_in + 2 * CP_TILE)[tid];
+            qc[0] = c4.x, qc[1] = c4.y, qc[2] = c4.z, qc[3] = c4.w;
+            qs[0] = s4.x, qs[1] = s4.y, qs[2] = s4.z, qs[3] = s4.w;
+            qe[0] = e4.x, qe[1] = e4.y, qe[2] = e4.z, qe[3] = e4.w;
+        } else {
 #pragma unroll
-        for (int k = 0; k < CP_ITEMS; ++k) {
-            const uint32_t j = k * CP_THREADS + tid;
-            if (j < tn) {
-                qc[k] = __ldg(chr + t0 + j);
-                qe[k] = __ldg(end + t0 + j);
+            for (int k = 0; k < CP_ITEMS; ++k) {
+                const bool ok = j0 + k < tn;
+                qc[k] = ok ? __ldcs(chr + t0 + j0 + k) : 0xFFFFFFFFu;  // past the end: an unknown chromosome (never stored)
+                qs[k] = ok ? __ldcs(start + t0 + j0 + k) : 0;
+                qe[k] = ok ? __ldcs(end + t0 + j0 + k) : 0;
             }
         }
+        __syncthreads();  // s_cnt zeroed, the staged rows are in registers
+        if (tid == 0 && whole(tile + gridDim.x)) fetch(tile + gridDim.x);
+        uint32_t br[CP_ITEMS];  // bucket << 16 | rank inside the tile's bucket; all ones = not staged
+#pragma unroll
+        for (int k = 0; k < CP_ITEMS; ++k) {
+            br[k] = 0xFFFFFFFFu;
+            if (qc[k] < ix.n_chroms && (RAW || qs[k] < qe[k])) {
+                const uint4 L = qc[k] < (uint32_t)CP_CHROM_CACHE ? s_lin[qc[k]] : __ldg(ix.rank_lin + qc[k]);
+                qe[k] = L.x + min(qe[k], L.y);        // key of the search over the starts: #starts < end
+                qs[k] = L.z + min(qs[k] + 1u, L.w);   // key of the search over the ends: #ends < start + 1 (wrapping, bits.rs:337-344)
+                br[k] = min((qe[k] >> rs) >> bucket_shift, nb - 1);
+            }
+        }
+        // ranks from one shared-memory atomic per query.  Letting the lanes that drew the same bucket share an atomic was
+        // slower both ways it was tried (0.46 ms per 1e8 queries as is; __match_any_sync 1.43 ms, one ballot per bucket
+        // bit 0.71 ms).
 #pragma unroll
         for (int k = 0; k < CP_ITEMS; ++k)
-            if (k * CP_THREADS + tid < tn) atomicAdd(&s_cnt[count_bucket_of(ix, bucket_shift, nb, qc[k], qe[k])], 1u);
+            if (br[k] != 0xFFFFFFFFu) br[k] = br[k] << 16 | atomicAdd(&s_cnt[br[k]], 1u);
         __syncthreads();
-        if (tid < nb) tile_hist[(uint64_t)tid * n_tiles + tile] = s_cnt[tid];
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(CP_THREADS, GT_CP_MINBLOCKS) count_partition_kernel(IndexView ix, uint64_t n, uint32_t bucket_shift, uint32_t nb,
-                                                                         const uint32_t* __restrict__ chr,
-                                                                         const uint32_t* __restrict__ start,
-                                                                         const uint32_t* __restrict__ end,
-                                                                         const uint32_t* __restrict__ tile_base,
-                                                                         uint32_t* __restrict__ o_chr, uint32_t* __restrict__ o_start,
-                                                                         uint32_t* __restrict__ o_end, uint32_t* __restrict__ o_slot) {
-    __shared__ uint32_t s_cnt[CP_MAX_BUCKETS];    // tile histogram = rank dispenser
-    __shared__ uint32_t s_base[CP_MAX_BUCKETS];   // first staged position of each bucket
-    __shared__ uint32_t s_gbase[CP_MAX_BUCKETS];  // global slot of staged position 0 of each bucket (wrapping)
-    extern __shared__ __align__(16) uint32_t s_stage[];  // CP_STAGE_BYTES: the tile grouped by bucket
-    uint32_t *s_c = s_stage, *s_s = s_stage + CP_TILE, *s_e = s_stage + 2 * CP_TILE;
-    uint8_t* s_bk = reinterpret_cast<uint8_t*>(s_stage + 3 * CP_TILE);
-    const uint32_t tid = threadIdx.x;
-    const uint64_t n_tiles = (n + CP_TILE - 1) / CP_TILE;
-    // The queries (and run starts) of the block's NEXT tile are requested while this tile is written out: the phases
-    // of a tile are separated by block barriers, so without this only the co-resident blocks hide the load latency.
-    uint32_t qc[CP_ITEMS], qs[CP_ITEMS], qe[CP_ITEMS], br[CP_ITEMS];  // br = bucket << 16 | rank inside the tile's bucket
-    uint32_t my_base = 0;
-    auto request = [&](uint64_t tile) {
-        const uint64_t t0 = tile * CP_TILE;
-        const uint32_t tn = (uint32_t)min((uint64_t)CP_TILE, n - t0);
-        if (tid < nb) my_base = __ldg(tile_base + (uint64_t)tid * n_tiles + tile);
-#pragma unroll
-        for (int k = 0; k < CP_ITEMS; ++k) {
-            const uint32_t j = k * CP_THREADS + tid;
-            if (j < tn) {
-                qc[k] = __ldcs(chr + t0 + j);
-                qs[k] = __ldcs(start + t0 + j);
-                qe[k] = __ldcs(end + t0 + j);
-            }
-        }
-    };
-    if (blockIdx.x < n_tiles) request(blockIdx.x);
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t t0 = tile * CP_TILE;
-        const uint32_t tn = (uint32_t)min((uint64_t)CP_TILE, n - t0);
-        if (tid < CP_MAX_BUCKETS) s_cnt[tid] = 0;
-        const uint32_t this_base = my_base;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < CP_ITEMS; ++k) {
-            const uint32_t j = k * CP_THREADS + tid;
-            if (j < tn) {
-                const uint32_t b = count_bucket_of(ix, bucket_shift, nb, qc[k], qe[k]);
-                br[k] = b << 16 | atomicAdd(&s_cnt[b], 1u);
-            }
-        }
-        __syncthreads();
-        if (tid < 32) {  // exclusive scan of the bucket sizes (eight per lane)
+        if (tid < 32) {  // exclusive scan of the padded bucket sizes (eight per lane)
             uint32_t v[8], s = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                v[k] = s_cnt[8 * tid + k];
+                v[k] = (s_cnt[8 * tid + k] + (CP_PAD - 1)) & ~(uint32_t)(CP_PAD - 1);
                 s += v[k];
             }
             uint32_t incl = s;
+#pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
                 if (tid >= (uint32_t)d) incl += t;
             }
             uint32_t run = incl - s;
@@ -421,72 +450,222 @@ __global__ void __launch_bounds__(CP_THREADS, GT_CP_MINBLOCKS) count_partition_k
                 s_base[8 * tid + k] = run;
                 run += v[k];
             }
-        }
-        __syncthreads();
-        if (tid < CP_MAX_BUCKETS) s_gbase[tid] = this_base - s_base[tid];
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < CP_ITEMS; ++k) {
-            const uint32_t j = k * CP_THREADS + tid;
-            if (j < tn) {
-                const uint32_t b = br[k] >> 16, p = s_base[b] + (br[k] & 0xFFFFu);
-                s_c[p] = qc[k];
-                s_s[p] = qs[k];
-                s_e[p] = qe[k];
-                s_bk[p] = (uint8_t)b;
-                __stcs(o_slot + t0 + j, s_gbase[b] + p);
+            if (tid == 31) {
+                s_used = incl;
+                tile_used[tile] = incl;
             }
         }
-        if (tile + gridDim.x < n_tiles) request(tile + gridDim.x);
         __syncthreads();
-        for (uint32_t p = tid; p < tn; p += CP_THREADS) {
-            const uint32_t dst = s_gbase[s_bk[p]] + p;
-            o_chr[dst] = s_c[p];
-            o_start[dst] = s_s[p];
-            o_end[dst] = s_e[p];
+        if (tid < nb) runs[(uint64_t)tid * n_tiles + tile] = s_base[tid] << 16 | s_cnt[tid];
+        uint32_t p[CP_ITEMS];
+#pragma unroll
+        for (int k = 0; k < CP_ITEMS; ++k) {
+            p[k] = CP_WALK;
+            if (br[k] != 0xFFFFFFFFu) {
+                p[k] = s_base[br[k] >> 16] + (br[k] & 0xFFFFu);
+                s_keys[p[k]] = make_uint2(qe[k], qs[k]);
+            }
         }
+        if (tn == (uint32_t)CP_TILE) {
+            __stcs(reinterpret_cast<uint2*>(pos + t0) + tid, make_uint2(p[0] | p[1] << 16, p[2] | p[3] << 16));
+        } else {
+#pragma unroll
+            for (int k = 0; k < CP_ITEMS; ++k)
+                if (j0 + k < tn) pos[t0 + j0 + k] = (uint16_t)p[k];
+        }
+        __syncthreads();
+        // the padding between the runs travels along (whole lines; nobody reads it)
+        const uint32_t used2 = s_used / 2;
+        uint4* dst = reinterpret_cast<uint4*>(keys + (uint64_t)tile * cap);
+        for (uint32_t i = tid; i < used2; i += CP_THREADS) __stcs(dst + i, reinterpret_cast<const uint4*>(s_keys)[i]);
         __syncthreads();
     }
 }
 
-// Sixteen results per thread: four 128-bit slot loads, then sixteen independent gathers in flight (a thread that
-// chains one slot load and four gathers at DRAM latency moved 2e11 elements/s, a third of what the traffic allows).
-template <typename T>
-__global__ void __launch_bounds__(256) count_gather_kernel(uint64_t n, const uint32_t* __restrict__ slot,
-                                                           const T* __restrict__ tmp, T* __restrict__ out) {
-    const uint64_t n16 = n / 16, groups_per_block = blockDim.x;  // a block covers 256 x 16 consecutive results per step
-    for (uint64_t blk = blockIdx.x; blk * groups_per_block < n16; blk += gridDim.x) {
-        const uint64_t g0 = blk * groups_per_block * 4;  // first uint4 of this block's span
-        uint4 p[4];
-        bool ok[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {  // lane-contiguous 128-bit loads: k-th quarter of the span
-            const uint64_t q = g0 + (uint64_t)k * blockDim.x + threadIdx.x;
-            ok[k] = q < n16 * 4;
-            if (ok[k]) p[k] = __ldcs(reinterpret_cast<const uint4*>(slot) + q);
-        }
-        T v[16];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (ok[k]) {
-                v[4 * k] = __ldg(tmp + p[k].x);
-                v[4 * k + 1] = __ldg(tmp + p[k].y);
-                v[4 * k + 2] = __ldg(tmp + p[k].z);
-                v[4 * k + 3] = __ldg(tmp + p[k].w);
-            }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (ok[k]) {
-                const uint64_t i = (g0 + (uint64_t)k * blockDim.x + threadIdx.x) * 4;
-                __stcs(out + i, v[4 * k]);
-                __stcs(out + i + 1, v[4 * k + 1]);
-                __stcs(out + i + 2, v[4 * k + 2]);
-                __stcs(out + i + 3, v[4 * k + 3]);
-            }
+// The chromosome a LUT word belongs to, for the rare bin with more entries than a word holds inline (the bisection
+// needs the chromosome's slice of the sorted array): the last chromosome whose LUT starts at or before the word.
+__device__ __noinline__ uint32_t rank_lin_bisect(const ChromMeta* __restrict__ chroms, uint32_t n_chroms, const uint32_t* __restrict__ sorted,
+                                                 uint32_t lut_word /* 2 = lut_cs, 3 = lut_ce */, uint32_t mask, uint32_t word, uint32_t lo,
+                                                 uint32_t hi, uint32_t r) {
+    uint32_t a = 0, b = n_chroms;  // invariant: lut(a) <= word
+    while (b - a > 1) {
+        const uint32_t m = (a + b) >> 1;
+        if (__ldg(reinterpret_cast<const uint2*>(chroms + m) + lut_word).x <= word) a = m;
+        else b = m;
     }
-    if (blockIdx.x == 0 && threadIdx.x < (uint32_t)(n - n16 * 16)) {
-        const uint64_t i = n16 * 16 + threadIdx.x;
-        out[i] = tmp[__ldg(slot + i)];
+    const uint32_t* arr = sorted + __ldg(reinterpret_cast<const uint4*>(chroms + a)).z;  // ChromMeta::off
+    while (lo < hi) {  // every entry in [lo, hi) lies in the key's bin: the in-bin offsets decide
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((__ldg(arr + mid) & mask) < r) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ uint32_t rank_lin_resolve(const IndexView& ix, bool ends, unsigned long long w, uint32_t lin) {
+    const uint32_t shift = ix.rank_shift, mask = (1u << shift) - 1, base = (uint32_t)w, cnt = (uint32_t)(w >> 32) & 7u, r = lin & mask;
+    if (cnt == 7u) {
+        const uint32_t word = (lin >> shift) + (ends ? ix.rank_ends_off : 0u);
+        return rank_lin_bisect(ix.chroms, ix.n_chroms, ends ? ix.cs_ends : ix.cs_starts, ends ? 3 : 2, mask, word, base,
+                               (uint32_t)__ldg(ix.rank_lut + word + 1), r);
+    }
+    uint32_t below = 0;
+    unsigned long long offs = w >> 35;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {  // at most four inline entries (index.cu); branch-free
+        below += (j < cnt) & ((uint32_t)(offs & mask) < r);
+        offs >>= shift;
+    }
+    return base + below;
+}
+
+// Warps draw chunks of CR_RUNS consecutive (bucket, tile) runs from one counter, in order: the whole grid works at one
+// front that moves through the buckets, so the LUT slices in use stay in the L2 (a static round-robin let the warps drift
+// several buckets apart: 5.5 GB of DRAM reads instead of 1.7).  A chunk's runs are walked as one flat sequence, two
+// staged queries per lane and round; their four LUT words are in flight together, and the next round's keys, the next
+// chunk's run words and the chunk after that's number are requested before the current ones are consumed.
+constexpr uint32_t CR_RUNS = 4;
+#ifndef GT_CR_MINBLOCKS
+#define GT_CR_MINBLOCKS 4
+#endif
+template <typename R>
+__global__ void __launch_bounds__(256, GT_CR_MINBLOCKS) count_runs_kernel(IndexView ix, uint32_t n_runs, uint32_t n_tiles, uint32_t cap,
+                                                         const uint32_t* __restrict__ runs, const uint2* __restrict__ keys,
+                                                         R* __restrict__ res, uint32_t* __restrict__ counter) {
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t lane = threadIdx.x & 31, rs = ix.rank_shift;
+    const unsigned long long* lut_s = ix.rank_lut;
+    const unsigned long long* lut_e = ix.rank_lut + ix.rank_ends_off;
+    const uint32_t n_chunks = (n_runs + CR_RUNS - 1) / CR_RUNS;
+    auto run_word = [&](uint32_t chunk) {
+        const uint32_t r = chunk * CR_RUNS + lane;
+        return lane < CR_RUNS && chunk < n_chunks && r < n_runs ? __ldg(runs + r) : 0u;
+    };
+    uint32_t cur = 0;
+    if (lane == 0) cur = atomicAdd(counter, 2u);
+    cur = __shfl_sync(FULL, cur, 0);
+    uint32_t nxt = cur + 1, w_cur = run_word(cur);
+    while (cur < n_chunks) {
+        const uint32_t w_nxt = run_word(nxt);
+        uint32_t after = 0;
+        if (lane == 0) after = atomicAdd(counter, 1u);
+        // lanes 0 .. CR_RUNS-1 hold one run each: length, and where staged entry f of the flat sequence lives (adj + f)
+        const uint32_t cnt = w_cur & 0xFFFFu;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (uint32_t d = 1; d < CR_RUNS; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t adj = ((cur * CR_RUNS + lane) % n_tiles) * cap + (w_cur >> 16) - (incl - cnt);
+        const uint32_t p0 = __shfl_sync(FULL, incl, 0), p1 = __shfl_sync(FULL, incl, 1), p2 = __shfl_sync(FULL, incl, 2);
+        const uint32_t total = __shfl_sync(FULL, incl, 3);
+        static_assert(CR_RUNS == 4, "the run of a flat position is found with three comparisons");
+        auto where = [&](uint32_t f) { return __shfl_sync(FULL, adj, (f >= p0) + (f >= p1) + (f >= p2)) + f; };
+        uint32_t f = lane, ia = where(f), ib = where(f + 32);
+        uint2 ka = f < total ? __ldcs(keys + ia) : make_uint2(0, 0);  // (0, 0): the first word of either block
+        uint2 kb = f + 32 < total ? __ldcs(keys + ib) : make_uint2(0, 0);
+        for (uint32_t f0 = 0; f0 < total; f0 += 64) {
+            const unsigned long long wa_s = __ldg(lut_s + (ka.x >> rs)), wa_e = __ldg(lut_e + (ka.y >> rs));
+            const unsigned long long wb_s = __ldg(lut_s + (kb.x >> rs)), wb_e = __ldg(lut_e + (kb.y >> rs));
+            const uint32_t f2 = f + 64, ia2 = where(f2), ib2 = where(f2 + 32);
+            const uint2 ka2 = f2 < total ? __ldcs(keys + ia2) : make_uint2(0, 0);
+            const uint2 kb2 = f2 + 32 < total ? __ldcs(keys + ib2) : make_uint2(0, 0);
+            if (f < total) {
+                const uint32_t last = rank_lin_resolve(ix, false, wa_s, ka.x), first = rank_lin_resolve(ix, true, wa_e, ka.y);
+                __stcs(res + ia, sizeof(R) == 8 ? (R)((uint64_t)last - (uint64_t)first) : (R)(last - first));
+            }
+            if (f + 32 < total) {
+                const uint32_t last = rank_lin_resolve(ix, false, wb_s, kb.x), first = rank_lin_resolve(ix, true, wb_e, kb.y);
+                __stcs(res + ib, sizeof(R) == 8 ? (R)((uint64_t)last - (uint64_t)first) : (R)(last - first));
+            }
+            f = f2, ia = ia2, ib = ib2, ka = ka2, kb = kb2;
+        }
+        cur = nxt;
+        w_cur = w_nxt;
+        nxt = __shfl_sync(FULL, after, 0);
+    }
+}
+
+// A tile's results (one contiguous block) and its staged positions arrive by bulk copies, double-buffered: the next
+// tile's are in flight while this one is put back into query order.
+template <int MODE, typename R>
+__global__ void __launch_bounds__(CP_THREADS, 2)
+count_unstage_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint32_t cap, const uint32_t* __restrict__ chr,
+                     const uint32_t* __restrict__ start, const uint32_t* __restrict__ end, int32_t min_bp,
+                     const uint16_t* __restrict__ pos, const R* __restrict__ res, const uint32_t* __restrict__ tile_used,
+                     void* __restrict__ out, bool out_aligned) {
+    __shared__ __align__(8) uint64_t s_bar[2];
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    const uint32_t buf_bytes = cap * (uint32_t)sizeof(R) + CP_TILE * 2;  // cap results, then CP_TILE positions
+    const uint32_t tid = threadIdx.x;
+    auto fetch = [&](uint32_t tile, uint32_t b) {  // one thread
+        const uint32_t res_bytes = __ldg(tile_used + tile) * (uint32_t)sizeof(R);  // a multiple of 32
+        const bool whole = ((uint64_t)tile + 1) * CP_TILE <= n;
+        unsigned char* buf = s_dyn + b * buf_bytes;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the buffer are done
+        if (res_bytes + (whole ? CP_TILE * 2 : 0) == 0) {
+            mbar_arrive(&s_bar[b]);
+            return;
+        }
+        mbar_expect_tx(&s_bar[b], res_bytes + (whole ? CP_TILE * 2 : 0));
+        const uint64_t pol = policy_evict_first();
+        if (res_bytes) bulk_g2s(buf, res + (uint64_t)tile * cap, res_bytes, &s_bar[b], pol);
+        if (whole) bulk_g2s(buf + cap * sizeof(R), pos + (uint64_t)tile * CP_TILE, CP_TILE * 2, &s_bar[b], pol);
+    };
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (blockIdx.x < n_tiles) fetch(blockIdx.x, 0);
+    }
+    __syncthreads();
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t b = it & 1u;
+        if (tid == 0 && tile + gridDim.x < n_tiles) fetch(tile + gridDim.x, b ^ 1u);  // that buffer was consumed a round ago
+        const uint64_t t0 = (uint64_t)tile * CP_TILE;
+        const uint32_t tn = (uint32_t)min((uint64_t)CP_TILE, n - t0), j0 = tid * CP_ITEMS;
+        const R* s_res = reinterpret_cast<const R*>(s_dyn + b * buf_bytes);
+        mbar_wait(&s_bar[b], (it >> 1) & 1u);
+        uint32_t p[CP_ITEMS];
+        const bool whole = tn == (uint32_t)CP_TILE;
+        if (whole) {
+            const uint2 pp = reinterpret_cast<const uint2*>(s_dyn + b * buf_bytes + cap * sizeof(R))[tid];
+            p[0] = pp.x & 0xFFFFu, p[1] = pp.x >> 16, p[2] = pp.y & 0xFFFFu, p[3] = pp.y >> 16;
+        } else {
+#pragma unroll
+            for (int k = 0; k < CP_ITEMS; ++k) p[k] = j0 + k < tn ? pos[t0 + j0 + k] : CP_WALK;
+        }
+        uint64_t v[CP_ITEMS];
+#pragma unroll
+        for (int k = 0; k < CP_ITEMS; ++k) {
+            if (p[k] != CP_WALK) {
+                v[k] = s_res[p[k]];
+            } else {
+                v[k] = 0;
+                if (MODE != COUNT_BITS_RAW_U64 && j0 + k < tn) {
+                    const uint32_t c = __ldg(chr + t0 + j0 + k);
+                    if (c < ix.n_chroms) v[k] = count_query_walk(ix, c, __ldg(start + t0 + j0 + k), __ldg(end + t0 + j0 + k), min_bp);
+                }
+            }
+        }
+        if (whole && out_aligned) {
+            const uint64_t g = t0 / CP_ITEMS + tid;
+            if (MODE == COUNT_U32) {
+                __stcs(reinterpret_cast<uint4*>(out) + g, make_uint4((uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2], (uint32_t)v[3]));
+            } else if (MODE == COUNT_ANY_U8) {
+                __stcs(reinterpret_cast<uchar4*>(out) + g, make_uchar4(v[0] != 0, v[1] != 0, v[2] != 0, v[3] != 0));
+            } else {
+                __stcs(reinterpret_cast<ulonglong2*>(out) + 2 * g, make_ulonglong2(v[0], v[1]));
+                __stcs(reinterpret_cast<ulonglong2*>(out) + 2 * g + 1, make_ulonglong2(v[2], v[3]));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < CP_ITEMS; ++k)
+                if (j0 + k < tn) count_store<MODE>(out, t0 + j0 + k, v[k]);
+        }
+        __syncthreads();  // buffer b may be refilled
     }
 }
 
@@ -519,70 +698,73 @@ static void launch_count_mode(const gtgpu_ctx* ctx, const IndexView& v, uint64_t
     }
 }
 
-// Whether this launch goes through the partition: the identity path only, LUTs well beyond what stays in the L2,
-// enough queries to pay for the extra passes.  GTGPU_COUNT_PARTITION=0 / 1 forces it off / on (tests, measurements).
-static bool count_wants_partition(const gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_end,
-                                  int32_t min_overlap) {
-    if (min_overlap > 1 || !ix->view.proper || n >= 0xFFFFFFFFull || ix->rank_lut_len == 0) return false;
-    if (!aligned16(d_chr) || !aligned16(d_end)) return false;
+// Whether this launch goes through the bucketed pass: the identity path only, an index whose linearised search keys fit
+// 32 bits, LUTs well beyond what stays in the L2, enough queries to pay for the extra passes.  GTGPU_COUNT_PARTITION=0 / 1
+// forces it off / on (tests, measurements).
+static bool count_wants_partition(const gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
+                                  const uint32_t* d_end, int32_t min_overlap) {
+    if (min_overlap > 1 || !ix->view.proper || n >= (1ull << 31) || ix->rank_lut_len == 0 || !ix->view.rank_lin) return false;  // (staged positions are 32-bit)
+    if (!aligned16(d_chr) || !aligned16(d_start) || !aligned16(d_end)) return false;
     if (const char* env = getenv("GTGPU_COUNT_PARTITION")) return env[0] == '1';
     return ix->rank_lut_len * 8 > (64ull << 20) && n >= (4ull << 20);
 }
 
-static int32_t launch_count_partitioned(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
-                                        const uint32_t* d_end, int32_t min_overlap, int mode, void* d_out) {
+template <int MODE, typename R>
+static int32_t launch_count_bucketed_mode(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
+                                          const uint32_t* d_end, int32_t min_overlap, void* d_out) {
     gtgpu_ctx* ctx = ix->ctx;
     cudaStream_t st = ctx->stream;
-    const size_t elem = mode == COUNT_BITS_RAW_U64 ? 8 : mode == COUNT_ANY_U8 ? 1 : 4;
-    uint32_t *b_chr, *b_start, *b_end, *slot;
-    void* tmp;
-    // Slices of about 16 MB of LUT words per bucket (an eighth of the L2), between 32 and 256 buckets.
+    // Buckets: (a) a slice of at most 16 MB of LUT words (an eighth of the L2; half of it starts, half ends); (b) the
+    // chunks the resident warps of count_runs_kernel hold at any time (two each) should span at most about 64 MB of LUT —
+    // with few queries per call (a rank's block of a query-sharded batch) that span, not the slice, is what has to fit the
+    // L2.  Runs shorter than 32 queries cost more than they save: at most 128 buckets (measured at 1.25e7, 5e7 and 1e8
+    // queries against 0.78 GB of LUT: 128 / 64 / 64 buckets are the fastest).
+    const uint64_t lut_bytes = ix->rank_lut_len * 8;
+    const uint64_t held = (uint64_t)ctx->sm_count * GT_CR_MINBLOCKS * 8 * 2 * CR_RUNS * CP_TILE;  // queries held x buckets
     uint32_t nb = 32;
-    while (nb < (uint32_t)CP_MAX_BUCKETS && ix->rank_lut_len * 8 / nb > (16ull << 20)) nb *= 2;
+    while (nb < 128 && (lut_bytes / nb > (16ull << 20) || (held / nb) * (double)lut_bytes / (double)n > (double)(64ull << 20))) nb *= 2;
     if (const char* env = getenv("GTGPU_COUNT_BUCKETS")) nb = (uint32_t)std::min(CP_MAX_BUCKETS, std::max(2, atoi(env)));
     uint32_t bucket_shift = 0;
-    while (((ix->rank_lut_len + 2) >> bucket_shift) >= (uint64_t)nb) ++bucket_shift;
-    const uint64_t n_tiles = (n + CP_TILE - 1) / CP_TILE, n_hist = n_tiles * nb;
-    const size_t hist_bytes = (size_t)((n_hist * 4 + 255) / 256 * 256);
-    char* hist_ws;
-    GT_TRY(ctx->scratch_get(SC_CNT_CHR, n * 4, (void**)&b_chr));
-    GT_TRY(ctx->scratch_get(SC_CNT_START, n * 4, (void**)&b_start));
-    GT_TRY(ctx->scratch_get(SC_CNT_END, n * 4, (void**)&b_end));
-    GT_TRY(ctx->scratch_get(SC_CNT_SLOT, n * 4, (void**)&slot));
-    GT_TRY(ctx->scratch_get(SC_CNT_TMP, n * elem, &tmp));
-    GT_TRY(ctx->scratch_get(SC_CNT_CURSORS, 2 * hist_bytes + exclusive_scan_temp_bytes(n_hist, 4), (void**)&hist_ws));
-    uint32_t* tile_hist = reinterpret_cast<uint32_t*>(hist_ws);
-    uint32_t* tile_base = reinterpret_cast<uint32_t*>(hist_ws + hist_bytes);
-    const int hist_grid = resident_grid(ctx, count_bucket_hist_kernel, CP_THREADS, n_tiles);
-    GT_CUDA(cudaFuncSetAttribute(count_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_STAGE_BYTES));
-    const int part_grid = resident_grid(ctx, count_partition_kernel, CP_THREADS, n_tiles, CP_STAGE_BYTES);
+    while ((ix->view.rank_ends_off >> bucket_shift) >= nb) ++bucket_shift;
+    const uint32_t n_tiles = (uint32_t)((n + CP_TILE - 1) / CP_TILE), n_runs = n_tiles * nb;
+    const uint32_t cap = CP_TILE + CP_PAD * nb;  // staged entries per tile: every run padded to a multiple of CP_PAD
+    uint2* keys;
+    R* res;
+    uint16_t* pos;
+    uint32_t* runs;
+    GT_TRY(ctx->scratch_get(SC_CNT_KEYS, (size_t)n_tiles * cap * 8, (void**)&keys));
+    GT_TRY(ctx->scratch_get(SC_CNT_RES, (size_t)n_tiles * cap * sizeof(R), (void**)&res));
+    GT_TRY(ctx->scratch_get(SC_CNT_POS, (size_t)n_tiles * CP_TILE * 2, (void**)&pos));
+    GT_TRY(ctx->scratch_get(SC_CNT_RUNS, ((size_t)n_runs + n_tiles + 1) * 4, (void**)&runs));
+    uint32_t* tile_used = runs + n_runs;
+    uint32_t* run_counter = tile_used + n_tiles;  // zeroed by the staging kernel
+    constexpr bool RAW = MODE == COUNT_BITS_RAW_U64;
+    const size_t stage_smem = (size_t)cap * 8 + 3 * CP_TILE * 4, unstage_smem = 2 * ((size_t)cap * sizeof(R) + CP_TILE * 2);
+    GT_CUDA(cudaFuncSetAttribute(count_stage_kernel<RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem));
+    GT_CUDA(cudaFuncSetAttribute(count_unstage_kernel<MODE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unstage_smem));
+    const int stage_grid = resident_grid(ctx, count_stage_kernel<RAW>, CP_THREADS, n_tiles, stage_smem);
+    const int runs_grid = resident_grid(ctx, count_runs_kernel<R>, 256, ((uint64_t)n_runs + 7) / 8);
+    const int unstage_grid = resident_grid(ctx, count_unstage_kernel<MODE, R>, CP_THREADS, n_tiles, unstage_smem);
     ctx->time_begin();
-    count_bucket_hist_kernel<<<hist_grid, CP_THREADS, 0, st>>>(ix->view, n, bucket_shift, nb, d_chr, d_end, tile_hist);
-    GT_TRY(exclusive_scan<uint32_t>(ctx, tile_hist, tile_base, n_hist, hist_ws + 2 * hist_bytes));
-    count_partition_kernel<<<part_grid, CP_THREADS, CP_STAGE_BYTES, st>>>(ix->view, n, bucket_shift, nb, d_chr, d_start, d_end, tile_base,
-                                                            b_chr, b_start, b_end, slot);
-    const uint64_t gblocks = (n / 16 + 255) / 256;
-    switch (mode) {
-        case COUNT_U32:
-            launch_count_mode<COUNT_U32>(ctx, ix->view, n, b_chr, b_start, b_end, min_overlap, tmp, true);
-            count_gather_kernel<uint32_t><<<resident_grid(ctx, count_gather_kernel<uint32_t>, 256, gblocks), 256, 0, st>>>(
-                n, slot, (const uint32_t*)tmp, (uint32_t*)d_out);
-            break;
-        case COUNT_ANY_U8:
-            launch_count_mode<COUNT_ANY_U8>(ctx, ix->view, n, b_chr, b_start, b_end, min_overlap, tmp, true);
-            count_gather_kernel<uint8_t><<<resident_grid(ctx, count_gather_kernel<uint8_t>, 256, gblocks), 256, 0, st>>>(
-                n, slot, (const uint8_t*)tmp, (uint8_t*)d_out);
-            break;
-        default:
-            launch_count_mode<COUNT_BITS_RAW_U64>(ctx, ix->view, n, b_chr, b_start, b_end, min_overlap, tmp, true);
-            count_gather_kernel<uint64_t><<<resident_grid(ctx, count_gather_kernel<uint64_t>, 256, gblocks), 256, 0, st>>>(
-                n, slot, (const uint64_t*)tmp, (uint64_t*)d_out);
-            break;
-    }
+    count_stage_kernel<RAW><<<stage_grid, CP_THREADS, stage_smem, st>>>(ix->view, n, n_tiles, bucket_shift, nb, cap, d_chr, d_start,
+                                                                         d_end, keys, pos, runs, tile_used, run_counter);
+    count_runs_kernel<R><<<runs_grid, 256, 0, st>>>(ix->view, n_runs, n_tiles, cap, runs, keys, res, run_counter);
+    count_unstage_kernel<MODE, R><<<unstage_grid, CP_THREADS, unstage_smem, st>>>(ix->view, n, n_tiles, cap, d_chr, d_start, d_end,
+                                                                                  min_overlap, pos, res, tile_used, d_out,
+                                                                                  aligned16(d_out));
     ctx->time_end();
-    ctx->launches += 4;  // + 3 counted by the scan
+    ctx->launches += 3;
     GT_CUDA(cudaGetLastError());
     return GTGPU_OK;
+}
+
+static int32_t launch_count_partitioned(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start,
+                                        const uint32_t* d_end, int32_t min_overlap, int mode, void* d_out) {
+    switch (mode) {
+        case COUNT_U32: return launch_count_bucketed_mode<COUNT_U32, uint32_t>(ix, n, d_chr, d_start, d_end, min_overlap, d_out);
+        case COUNT_ANY_U8: return launch_count_bucketed_mode<COUNT_ANY_U8, uint32_t>(ix, n, d_chr, d_start, d_end, min_overlap, d_out);
+        default: return launch_count_bucketed_mode<COUNT_BITS_RAW_U64, unsigned long long>(ix, n, d_chr, d_start, d_end, min_overlap, d_out);
+    }
 }
 
 // Gives back what a find on this ctx set aside in the L2 for its window table: the stream's access-policy window, the
@@ -603,7 +785,7 @@ int32_t launch_count(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const u
     if (n == 0) return GTGPU_OK;
     gtgpu_ctx* ctx = ix->ctx;
     if (const char* env = getenv("GTGPU_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(env));  // tuning knob
-    if (count_wants_partition(ix, n, d_chr, d_end, min_overlap)) {
+    if (count_wants_partition(ix, n, d_chr, d_start, d_end, min_overlap)) {
         // The bucketed pass lives on its LUT slices staying in the L2: give back what an earlier find on this ctx set aside
         // for its window table (persisting lines + the stream's access-policy window; the next find re-establishes both).
         release_l2_window(ctx);
@@ -803,43 +985,6 @@ __device__ __forceinline__ void red_status(uint64_t* p, uint64_t v) {
     asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// ---- TMA (bulk async copy) staging of a tile's query rows into shared memory ------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra.uni WAIT_DONE;\n"
-        "bra.uni WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_addr(bar)), "r"(phase) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                     smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
-}
-// L2 residency: the bin table is re-read by every tile (evict_last), queries and ids are touched once (evict_first).
-__device__ __forceinline__ uint64_t policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
 __device__ __forceinline__ uint32_t ldg32_keep(const void* p, uint64_t policy) {
     uint32_t v;
     asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));

@@ -19,7 +19,8 @@ dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(device=dev)
 ctx = ffi.Context(0, stream=stream.cuda_stream)
 u32 = lambda t: t.cpu().numpy().view(np.uint32)
-n_db, n_q = int(50_000_000 * scale), int(100_000_000 * scale)
+qscale = float(sys.argv[4]) if len(sys.argv) > 4 else scale  # queries alone (one rank's block of a query-sharded run)
+n_db, n_q = int(50_000_000 * scale), int(100_000_000 * qscale)
 db = synth.make_uniform_intervals(n_db, synth.SEED_LOLA_DB, device=dev, min_w=100, max_w=10_000)
 g = synth.group_by_chrom(db["chr"], db["start"], db["end"])
 offs, s, e = g["chrom_offsets"].cpu().numpy().astype(np.uint64), u32(g["g_start"]), u32(g["g_end"])

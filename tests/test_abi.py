@@ -185,8 +185,8 @@ def test_device_code_is_sm100a_and_keeps_its_resource_budgets():
     res = {}
     for m in re.finditer(r"Function (\S+):\n\s+REG:(\d+) STACK:(\d+) SHARED:(\d+)", usage):
         res[m.group(1)] = tuple(int(x) for x in m.groups()[1:])
-    for name in ("fused_find_kernel", "count_kernel_x4", "count_partition_kernel", "count_bucket_hist_kernel",
-                 "count_gather_kernel", "igd_count_kernel", "radix_scatter_kernel", "scan_down_kernel", "score_hist_kernel",
+    for name in ("fused_find_kernel", "count_kernel_x4", "count_stage_kernel", "count_runs_kernel",
+                 "count_unstage_kernel", "igd_count_kernel", "radix_scatter_kernel", "scan_down_kernel", "score_hist_kernel",
                  "ingest_parse_lines_kernel", "untranspose_blocks_kernel"):
         assert any(name in k for k in res), f"{name} missing from the device code"
     # lean fused find kernel: template flags <ROWS=4, DESC, FILTER, OFFS, LEAN=1>; no stack; 40 registers = 6 CTAs per SM
@@ -197,8 +197,8 @@ def test_device_code_is_sm100a_and_keeps_its_resource_budgets():
     assert lean and any(o for o, _ in lean) and any(not o for o, _ in lean), "lean instantiations of the fused kernel missing"
     for offs, (reg, stack, shared) in lean:
         assert reg <= (48 if offs else 40) and stack == 0 and shared <= 24 * 1024, (offs, reg, stack, shared)
-    part = [v for k, v in res.items() if "count_partition_kernel" in k]
-    assert all(reg <= 64 and stack == 0 for reg, stack, _ in part), part   # two 512-thread CTAs per SM
+    part = [v for k, v in res.items() if "count_stage_kernel" in k or "count_unstage_kernel" in k]
+    assert part and all(reg <= 32 and stack <= 32 for reg, stack, _ in part), part   # two 1024-thread CTAs per SM
 
 
 def test_rust_sys_stub_declares_every_entry_point():

@@ -228,13 +228,41 @@ def test_partitioned_count_matches_direct_and_oracle(ctx, kind, style, monkeypat
         monkeypatch.setenv("GTGPU_COUNT_PARTITION", "1")
         n0 = ctx.launch_count()
         part = g.count(qc, qs, qe), g.any(qc, qs, qe), (g.bits_count(qc, qs, qe) if kind == "bits" else None)
-        per_call = 7 if g.info()["proper"] else 1                        # hist, scan x 3, partition, count, gather
+        per_call = 3 if g.info()["proper"] else 1                        # stage, count the runs, unstage
         assert ctx.launch_count() - n0 == per_call * (3 if kind == "bits" else 2)
         assert np.array_equal(part[0], o.count(qc, qs, qe))
         assert np.array_equal(part[0], direct[0]) and np.array_equal(part[1], direct[1])
         if kind == "bits":
             assert np.array_equal(part[2], o.bits_count(qc, qs, qe)) and np.array_equal(part[2], direct[2])
         assert np.array_equal(g.count(qc, qs, qe, 2), o.count(qc, qs, qe, 2))  # min_overlap > 1 never partitions
+
+
+def test_bucketed_count_wide_coordinates(ctx, monkeypatch):
+    """Chromosomes that reach up to 2^32 - 1: where the linearised search keys of the bucketed pass do not fit 32 bits the
+    launcher stays on the direct pass; where they fit (one such chromosome) clamped and wrapping keys resolve like the
+    oracle's (bits.rs:337-344)."""
+    rng = np.random.default_rng(77)
+    for n_chroms, expect_bucketed in ((3, False), (1, True)):
+        n = 4000
+        chr_ = np.sort(rng.integers(0, n_chroms, n))
+        offs = np.searchsorted(chr_, np.arange(n_chroms + 1)).astype(np.uint64)
+        top = 0xFFFFFFFF if n_chroms > 1 else 0xFF000000  # one chromosome: its LUT bins (+ sentinel) still fit below 2^32
+        s = rng.integers(0, top - 0xFFFFF, n)
+        e = np.minimum(s + rng.integers(1, 1 << 24, n), top)
+        g, o = _both(ctx, "bits", offs, s.astype(np.uint32), e.astype(np.uint32))
+        nq = 9001
+        qc = rng.integers(0, n_chroms + 1, nq).astype(np.uint32)
+        qs = rng.integers(0, 0xFFFFFFFF, nq, dtype=np.uint64)
+        qe = np.minimum(qs + rng.integers(1, 1 << 26, nq).astype(np.uint64), 0xFFFFFFFF)
+        qs[:50] = 0xFFFFFFFF  # start + 1 wraps
+        qe[50:100] = 0xFFFFFFFF
+        qs, qe = qs.astype(np.uint32), qe.astype(np.uint32)
+        monkeypatch.setenv("GTGPU_COUNT_PARTITION", "1")
+        n0 = ctx.launch_count()
+        cnt, raw = g.count(qc, qs, qe), g.bits_count(qc, qs, qe)
+        assert ctx.launch_count() - n0 == (6 if expect_bucketed else 2)
+        monkeypatch.delenv("GTGPU_COUNT_PARTITION")
+        assert np.array_equal(cnt, o.count(qc, qs, qe)) and np.array_equal(raw, o.bits_count(qc, qs, qe))
 
 
 @pytest.mark.parametrize("kind", ["bits", "ailist"])
