@@ -174,7 +174,7 @@ struct gtgpu_ctx {
     std::vector<gtgpu_ctx*> peers;
     std::mutex group_mu;                          // serialises group-wide calls
     bool group_comm_tried = false;                // in-process NCCL communicators (ncclCommInitAll) were set up / attempted
-    int fused_bps[2][10] = {{0}, {0}};  // resident CTAs per SM of the fused find variants
+    int fused_bps[2][12] = {{0}, {0}};  // resident CTAs per SM of the fused find variants
     const void* ingest_d_text = nullptr;          // set (under mu) while a *_gz entry point feeds device-resident text to the ingest
     const void* l2_window_owner = nullptr;        // the index whose window table the stream's access-policy window covers
     bool timing = false;                          // bracket dominant kernels with events
@@ -266,7 +266,11 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
                           int32_t min_overlap, uint32_t* d_out_ids, uint64_t ids_capacity,
                           uint64_t* d_out_offsets, uint64_t* d_out_file_tok, void* d_workspace,
                           const uint64_t* d_base, uint64_t* d_total_out, uint32_t* d_errflag, int unk_per_query = 0,
-                          uint32_t unk_id = 0);
+                          uint32_t unk_id = 0, const uint32_t* d_tag_in = nullptr, uint32_t* d_out_tags = nullptr,
+                          const uint32_t** tags_pending_if = nullptr);
+// d_out_tags (with unk_per_query): out_tags[j] = d_tag_in[query of id j], written by the find itself when the lean kernel
+// serves the launch.  *tags_pending_if then points at a device flag that is non-zero iff the launch fell back to the full
+// kernel (which writes per-query offsets instead: tag from those); nullptr = the tags were not written at all.
 // Per-call [unk] rule: expands raw per-file id runs into d_out, inserting unk_id for files with no ids.
 int32_t launch_unk_offsets(gtgpu_ctx* ctx, uint64_t n_files, const uint64_t* d_raw_file_tok,
                            uint64_t* d_out_file_tok, uint64_t* d_n_empty);

@@ -19,8 +19,10 @@
 namespace gtgpu {
 
 // tag[j] = barcode of the fragment that token j belongs to; four fragments per thread keep the offset loads wide
+// run_if (optional): the find wrote the tags itself unless this device flag is non-zero (its lean kernel fell back)
 __global__ void frag_tag_tokens_kernel(uint64_t n, const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ barcode,
-                                       uint64_t capacity, uint32_t* __restrict__ tags) {
+                                       uint64_t capacity, uint32_t* __restrict__ tags, const uint32_t* __restrict__ run_if) {
+    if (run_if && *run_if == 0) return;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t a = offsets[i], b = min(offsets[i + 1], capacity);
@@ -53,7 +55,7 @@ __global__ void frag_barcode_offsets_kernel(uint32_t n_barcodes, const uint64_t*
 static int32_t fragments_group_by(gtgpu_index* ix, uint64_t n, const uint32_t* d_chr, const uint32_t* d_start, const uint32_t* d_end,
                                   const uint32_t* d_bc, uint32_t n_barcodes, uint32_t unk_id, uint64_t cap, uint32_t* d_out,
                                   uint32_t* d_alt, uint32_t* d_tag_a, uint32_t* d_tag_b, uint64_t* d_off, void* d_ws, void* d_sort_tmp,
-                                  uint64_t* d_misc, uint64_t* d_bco, uint64_t* d_total_or_null, int stage) {
+                                  uint64_t* d_misc, uint64_t* d_bco, uint64_t* d_total_or_null, int stage, const uint32_t** tag_if) {
     gtgpu_ctx* ctx = ix->ctx;
     cudaStream_t st = ctx->stream;
     int bits = 1;
@@ -65,12 +67,14 @@ static int32_t fragments_group_by(gtgpu_index* ix, uint64_t n, const uint32_t* d
     uint32_t* second = (passes & 1) ? d_out : d_alt;
     if (stage == 0 || stage == 1) {
         GT_CUDA(cudaMemsetAsync(d_misc, 0, 64, st));
+        // the find writes (token, barcode) pairs itself when its lean kernel serves the index; *tag_if then is the device
+        // flag of the exception (fallback to the full kernel: offsets were written, step 2 tags from them)
         GT_TRY(launch_fused_find(ix, n, 0, nullptr, d_chr, d_start, d_end, 0, first, cap, d_off, nullptr, d_ws, nullptr, d_misc,
-                                 (uint32_t*)(d_misc + 2), 1, unk_id));
+                                 (uint32_t*)(d_misc + 2), 1, unk_id, d_bc, d_tag_a, tag_if));
     }
     if (stage == 0 || stage == 2) {
         const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 16);
-        frag_tag_tokens_kernel<<<grid, 256, 0, st>>>(n, d_off, d_bc, cap, d_tag_a);
+        frag_tag_tokens_kernel<<<grid, 256, 0, st>>>(n, d_off, d_bc, cap, d_tag_a, *tag_if);
         ctx->launches++;
         int in_b = 0;
         GT_TRY(radix_sort_pairs(ctx, cap, d_tag_a, first, d_tag_b, second, bits, d_sort_tmp, &in_b, d_misc));
@@ -115,6 +119,7 @@ int32_t tokenize_fragments_core(gtgpu_index* ix, uint64_t n, const uint32_t* d_c
     GT_TRY(ctx->scratch_get(SC_TILE_STATUS, fused_workspace_bytes(n), &d_ws));
     GT_TRY(ctx->scratch_get(SC_MISC, 64, (void**)&d_misc));
     uint64_t cap = n + n / 4 + 1024, total = 0;
+    const uint32_t* tag_if = nullptr;  // set by step 1, read by step 2
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (cap >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "tokenize_fragments: more than 2^32-2 tokens per call");
         GT_TRY(ctx->scratch_get(SC_OUT_IDS, cap * 4, (void**)&d_out));
@@ -124,7 +129,7 @@ int32_t tokenize_fragments_core(gtgpu_index* ix, uint64_t n, const uint32_t* d_c
         GT_TRY(ctx->scratch_get(SC_IN3_START, radix_sort_temp_bytes(cap), &d_tmp));
         // 1. tokens of every fragment in fragment order (hits, or unk), with per-fragment offsets
         GT_TRY(fragments_group_by(ix, n, d_chr, d_start, d_end, d_bc, n_barcodes, unk_id, cap, d_out, d_alt, d_tag_a, d_tag_b, d_off,
-                                  d_ws, d_tmp, d_misc, d_bco, nullptr, 1));
+                                  d_ws, d_tmp, d_misc, d_bco, nullptr, 1, &tag_if));
         GT_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_misc, 24, cudaMemcpyDeviceToHost, st));
         GT_CUDA(cudaStreamSynchronize(st));
         total = ctx->h_scalars[0];
@@ -135,7 +140,7 @@ int32_t tokenize_fragments_core(gtgpu_index* ix, uint64_t n, const uint32_t* d_c
     }
     // 2.-4. tag, sort by barcode, offsets
     GT_TRY(fragments_group_by(ix, n, d_chr, d_start, d_end, d_bc, n_barcodes, unk_id, cap, d_out, d_alt, d_tag_a, d_tag_b, d_off, d_ws,
-                              d_tmp, d_misc, d_bco, nullptr, 2));
+                              d_tmp, d_misc, d_bco, nullptr, 2, &tag_if));
     GT_CUDA(cudaMemcpyAsync(out_barcode_offsets, d_bco, ((uint64_t)n_barcodes + 1) * 8, cudaMemcpyDeviceToHost, st));
 
     gtgpu_buf* buf = new gtgpu_buf();
@@ -285,6 +290,7 @@ extern "C" int32_t gtgpu_tokenize_fragments_dev(gtgpu_index* ix, uint64_t n, con
     GT_TRY(ctx->scratch_get(SC_TILE_STATUS, fused_workspace_bytes(n), &d_ws));
     GT_TRY(ctx->scratch_get(SC_MISC, 64, (void**)&d_misc));
     GT_TRY(ctx->scratch_get(SC_IN3_START, radix_sort_temp_bytes(cap), &d_tmp));
+    const uint32_t* tag_if = nullptr;
     return fragments_group_by(ix, n, d_chr, d_start, d_end, d_barcode_id, n_barcodes, unk_id, cap, d_out_ids, d_alt, d_tag_a, d_tag_b,
-                              d_off, d_ws, d_tmp, d_misc, d_out_barcode_offsets, d_out_total, 0);
+                              d_off, d_ws, d_tmp, d_misc, d_out_barcode_offsets, d_out_total, 0, &tag_if);
 } GT_CATCH

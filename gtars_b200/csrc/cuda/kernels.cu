@@ -1069,14 +1069,18 @@ __device__ __forceinline__ bool cand_hit(uint32_t cs, uint32_t ce, uint32_t s, u
 #endif
 // UNK1: the per-query [unk] rule of fragment tokenization (fragments.rs:42-47: every fragment is its own tokenize() call) —
 // a query without a hit emits the single id unk_id, so the id stream IS the token stream and the per-query offsets index it.
-template <int ROWS, bool DESC, bool FILTER, bool OFFS, bool LEAN, bool UNK1 = false>
-__global__ void __launch_bounds__(FUSED_BLOCK, LEAN ? (OFFS ? 5 : GT_LEAN_MINBLOCKS) : GT_FUSED_MINBLOCKS)  // with per-query offsets (find, fragments) 40 registers spill
+// TAG (lean kernel only): every emitted id is accompanied by its query's tag (out_tags[pos] = tag_in[query]) — fragment
+// tokenization gets its (barcode, token) pairs straight from the find, without per-query offsets going to HBM and back.
+template <int ROWS, bool DESC, bool FILTER, bool OFFS, bool LEAN, bool UNK1 = false, bool TAG = false>
+__global__ void __launch_bounds__(FUSED_BLOCK, LEAN ? ((OFFS || TAG) ? 5 : GT_LEAN_MINBLOCKS) : GT_FUSED_MINBLOCKS)  // with per-query offsets or tags 40 registers spill
 fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, const uint64_t* __restrict__ file_offsets,
                   const uint32_t* __restrict__ chr, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
                   int32_t min_bp, int tma_ok, uint32_t* __restrict__ out_ids, uint64_t capacity,
                   uint64_t* __restrict__ out_offsets, uint64_t* __restrict__ out_file_tok, FusedWorkspace ws,
                   const uint64_t* __restrict__ d_base, uint64_t* __restrict__ d_total, uint32_t* __restrict__ d_err,
-                  uint32_t* __restrict__ lean_flag, const uint32_t* __restrict__ run_if, uint32_t unk_id) {
+                  uint32_t* __restrict__ lean_flag, const uint32_t* __restrict__ run_if, uint32_t unk_id,
+                  const uint32_t* __restrict__ tag_in, uint32_t* __restrict__ out_tags) {
+    static_assert(!TAG || LEAN, "tags are written by the lean kernel only (its fallback writes offsets; fragments.cu tags from those)");
     static_assert(ROWS == 4, "state packing (2-bit counts, 8-bit offsets) is written for four rows per thread");
     if (!LEAN && run_if && *run_if == 0) return;  // fallback launch, and the lean kernel resolved everything
     constexpr int WARPS = FUSED_BLOCK / 32;
@@ -1540,6 +1544,13 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     if (DESC && c == 2) { const uint32_t t = a; a = b; b = t; }
                     if (c != 0) __stcs(outp + o, a);
                     if (c == 2) __stcs(outp + o + 1, b);
+                    if constexpr (TAG) {
+                        if (c != 0) {  // (a query past the end has no id)
+                            const uint32_t t = __ldcs(tag_in + tile_start + wl + 32 * k);
+                            __stcs(out_tags + warp_base + o, t);
+                            if (c == 2) __stcs(out_tags + warp_base + o + 1, t);
+                        }
+                    }
                 }
             } else if (LEAN || !(prev.slow & WARP_SLOW)) {
 #pragma unroll
@@ -1558,6 +1569,11 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
                     } else {
                         if (warp_base + o < capacity) out_ids[warp_base + o] = a;
                         if (c == 2 && warp_base + o + 1 < capacity) out_ids[warp_base + o + 1] = b;
+                    }
+                    if constexpr (TAG) {
+                        const uint32_t t = __ldcs(tag_in + tile_start + wl + 32 * k);
+                        if (warp_base + o < capacity) out_tags[warp_base + o] = t;
+                        if (c == 2 && warp_base + o + 1 < capacity) out_tags[warp_base + o + 1] = t;
                     }
                 }
             } else {
@@ -1622,18 +1638,19 @@ fused_find_kernel(IndexView ix, uint64_t n, uint32_t n_tiles, uint64_t n_files, 
 #endif
 }
 
-template <bool DESC, bool FILTER, bool OFFS, bool LEAN, bool UNK1 = false>
+template <bool DESC, bool FILTER, bool OFFS, bool LEAN, bool UNK1 = false, bool TAG = false>
 static cudaError_t launch_variant(int grid, cudaStream_t st, const IndexView& view, uint64_t n, uint32_t n_tiles,
                                   uint64_t n_files, const uint64_t* d_file_offsets, const uint32_t* d_chr,
                                   const uint32_t* d_start, const uint32_t* d_end, int32_t min_overlap, uint32_t* d_out_ids,
                                   uint64_t cap, uint64_t* d_out_offsets, uint64_t* d_out_file_tok, FusedWorkspace ws,
                                   const uint64_t* d_base, uint64_t* d_total_out, uint32_t* d_errflag, const uint32_t* run_if,
-                                  int* blocks_per_sm, uint32_t unk_id = 0) {
-    auto kern = fused_find_kernel<FUSED_ROWS, DESC, FILTER, OFFS, LEAN, UNK1>;
+                                  int* blocks_per_sm, uint32_t unk_id = 0, const uint32_t* d_tag_in = nullptr,
+                                  uint32_t* d_out_tags = nullptr) {
+    auto kern = fused_find_kernel<FUSED_ROWS, DESC, FILTER, OFFS, LEAN, UNK1, TAG>;
     if (blocks_per_sm) {
         // 4 CTAs x 24 KB fit the 100 KB shared-memory configuration (6 CTAs of the lean kernel: 164 KB; 60-70 % measured
         // alike, 75 % costs 6 %); the rest of the unified L1 serves the gathers
-        int carve = LEAN ? (GT_LEAN_MINBLOCKS >= 6 && !OFFS ? 65 : 50) : 40;
+        int carve = LEAN ? (GT_LEAN_MINBLOCKS >= 6 && !OFFS && !TAG ? 65 : 50) : 40;
         if (const char* env = getenv("GTGPU_CARVEOUT")) carve = atoi(env);  // tuning knob, percent
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, FUSED_BLOCK, 0);
@@ -1644,7 +1661,7 @@ static cudaError_t launch_variant(int grid, cudaStream_t st, const IndexView& vi
                                     reinterpret_cast<uintptr_t>(d_end)) & 15) == 0;
     kern<<<grid, FUSED_BLOCK, 0, st>>>(view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, d_end, min_overlap, tma_ok,
                                        d_out_ids, cap, d_out_offsets, d_out_file_tok, ws, d_base, d_total_out, d_errflag,
-                                       ws.lean_flag, run_if, unk_id);
+                                       ws.lean_flag, run_if, unk_id, d_tag_in, d_out_tags);
     return cudaGetLastError();
 }
 
@@ -1663,8 +1680,12 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
                           const uint32_t* d_chr, const uint32_t* d_start, const uint32_t* d_end,
                           int32_t min_overlap, uint32_t* d_out_ids, uint64_t ids_capacity,
                           uint64_t* d_out_offsets, uint64_t* d_out_file_tok, void* d_workspace,
-                          const uint64_t* d_base, uint64_t* d_total_out, uint32_t* d_errflag, int unk_per_query, uint32_t unk_id) {
+                          const uint64_t* d_base, uint64_t* d_total_out, uint32_t* d_errflag, int unk_per_query, uint32_t unk_id,
+                          const uint32_t* d_tag_in, uint32_t* d_out_tags, const uint32_t** tags_pending_if) {
     gtgpu_ctx* ctx = ix->ctx;
+    if (d_out_tags && (!unk_per_query || !d_tag_in || !tags_pending_if))
+        return fail(GTGPU_ERR_INVALID, "fused_find: tags go with the per-query [unk] rule");
+    if (tags_pending_if) *tags_pending_if = nullptr;
     if (unk_per_query && (!d_out_offsets || min_overlap > 1 || d_out_file_tok || n == 0))
         return fail(GTGPU_ERR_INVALID, "fused_find: the per-query [unk] rule needs per-query offsets, no bp filter, no files, n > 0");
     cudaStream_t st = ctx->stream;
@@ -1728,7 +1749,7 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
     }
     const bool desc = ix->view.descending != 0, filt = min_overlap > 1, offs = d_out_offsets != nullptr;
     const int variant = unk_per_query ? (desc ? 9 : 8) : (desc ? 4 : 0) | (filt ? 2 : 0) | (offs ? 1 : 0);
-    int (&blocks_per_sm)[2][10] = ctx->fused_bps;  // per ctx = per device: carve-out and occupancy are set on this device
+    int (&blocks_per_sm)[2][12] = ctx->fused_bps;  // per ctx = per device: carve-out and occupancy are set on this device
     int grid = 0;
     cudaError_t err = cudaSuccess;
 #define GT_LAUNCH(D, F, O, LEAN, WS, RUN_IF, U)                                                                           \
@@ -1759,6 +1780,34 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
         ctx->time_end();                                                                                                \
         break;
 #define GT_VARIANT(D, F, O) GT_VARIANT_AT(((D ? 4 : 0) | (F ? 2 : 0) | (O ? 1 : 0)), D, F, O, false)
+    // Fragment tokenization with tags: the lean kernel writes (id, tag) pairs and no offsets; its fallback is the full
+    // kernel WITH offsets (the caller then tags from those: *tags_pending_if = the flag that says so, on the device).
+#define GT_TAGGED(D)                                                                                                    \
+    do {                                                                                                                \
+        int& bps = blocks_per_sm[1][10 + (D ? 1 : 0)];                                                                  \
+        ctx->time_begin();                                                                                              \
+        if (!bps) {                                                                                                     \
+            err = launch_variant<D, false, false, true, true, true>(0, st, ix->view, n, n_tiles, n_files, d_file_offsets, d_chr, d_start, \
+                                                                    d_end, min_overlap, d_out_ids, ids_capacity, nullptr, nullptr, ws,    \
+                                                                    d_base, d_total_out, d_errflag, nullptr, &bps, unk_id, d_tag_in,      \
+                                                                    d_out_tags);                                        \
+            if (bps < 1) bps = 1;                                                                                       \
+        }                                                                                                               \
+        grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * bps);                                         \
+        if (err == cudaSuccess)                                                                                         \
+            err = launch_variant<D, false, false, true, true, true>(grid, st, ix->view, n, n_tiles, n_files, d_file_offsets, d_chr,       \
+                                                                    d_start, d_end, min_overlap, d_out_ids, ids_capacity, nullptr,        \
+                                                                    nullptr, ws, d_base, d_total_out, d_errflag, nullptr, nullptr, unk_id, \
+                                                                    d_tag_in, d_out_tags);                              \
+        ctx->launches++;                                                                                                \
+        if (err == cudaSuccess) GT_LAUNCH(D, false, true, false, ws_fallback, ws.lean_flag, true);                      \
+        ctx->time_end();                                                                                                \
+        *tags_pending_if = ws.lean_flag;                                                                                \
+    } while (0)
+    if (d_out_tags && use_lean) {
+        if (desc) GT_TAGGED(true);
+        else GT_TAGGED(false);
+    } else
     switch (variant) {
         GT_VARIANT(false, false, false)
         GT_VARIANT(false, false, true)
@@ -1771,6 +1820,7 @@ int32_t launch_fused_find(gtgpu_index* ix, uint64_t n, uint64_t n_files, const u
         GT_VARIANT_AT(8, false, false, true, true)  // per-query [unk] rule (fragments): offsets on, no filter
         GT_VARIANT_AT(9, true, false, true, true)
     }
+#undef GT_TAGGED
 #undef GT_VARIANT
 #undef GT_VARIANT_AT
 #undef GT_LAUNCH

@@ -191,9 +191,10 @@ def test_device_code_is_sm100a_and_keeps_its_resource_budgets():
         assert any(name in k for k in res), f"{name} missing from the device code"
     # lean fused find kernel: template flags <ROWS=4, DESC, FILTER, OFFS, LEAN=1>; no stack; 40 registers = 6 CTAs per SM
     # (tokenize), 48 registers = 5 CTAs per SM when it also writes per-query offsets (find, fragments)
-    lean = [(re.match(r"(?:Lb[01]E){2}Lb([01])ELb1E", k.split("fused_find_kernelILi4E")[1]), v) for k, v in res.items()
+    # (flags after LEAN: UNK1, TAG — the tagged variant of fragment tokenization has the 48-register budget too)
+    lean = [(re.match(r"(?:Lb[01]E){2}Lb([01])ELb1ELb[01]ELb([01])E", k.split("fused_find_kernelILi4E")[1]), v) for k, v in res.items()
             if "fused_find_kernelILi4E" in k]
-    lean = [(m.group(1) == "1", v) for m, v in lean if m]
+    lean = [(m.group(1) == "1" or m.group(2) == "1", v) for m, v in lean if m]
     assert lean and any(o for o, _ in lean) and any(not o for o, _ in lean), "lean instantiations of the fused kernel missing"
     for offs, (reg, stack, shared) in lean:
         assert reg <= (48 if offs else 40) and stack == 0 and shared <= 24 * 1024, (offs, reg, stack, shared)
