@@ -227,11 +227,16 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* 
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
     uint32_t* mine = s_hist[(threadIdx.x >> 5) >> 1];
-#pragma unroll 4
+    // all sixteen loads of a thread in flight before the first atomic (four at a time left the DRAM at a quarter of its rate)
+    uint32_t key[RS_ROUNDS];
+#pragma unroll
     for (int k = 0; k < RS_ROUNDS; ++k) {
         const uint64_t i = base + (uint64_t)k * RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&mine[(__ldcs(keys + i) >> shift) & (ND - 1)], 1u);
+        key[k] = i < n ? __ldcs(keys + i) : 0;
     }
+#pragma unroll
+    for (int k = 0; k < RS_ROUNDS; ++k)
+        if (base + (uint64_t)k * RS_THREADS + threadIdx.x < n) atomicAdd(&mine[(key[k] >> shift) & (ND - 1)], 1u);
     __syncthreads();
     for (uint32_t d = threadIdx.x; d < ND; d += RS_THREADS) {
         uint32_t t = 0;
@@ -277,16 +282,24 @@ __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const uint
         const uint32_t j = wbase + 32 * r;
         key[r] = j < tile_n ? __ldcs(keys_in + tile0 + j) : 0;
     }
+    // the sixteen matches do not depend on each other: issue them together (a match per round in front of that round's
+    // counter update left every warp waiting on its result: a third of the kernel's stall samples) ...
 #pragma unroll
     for (int r = 0; r < RS_ROUNDS; ++r) {
         const bool ok = wbase + 32 * r < tile_n;
         const uint32_t d = ok ? (key[r] >> shift) & (ND - 1) : ND + lane;  // invalid lanes never match anyone
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-        const uint32_t before = __popc(peers & ((1u << lane) - 1));
+        rank[r] = (uint16_t)(__popc(peers & ((1u << lane) - 1)) | __popc(peers) << 8);  // lanes before me | group size
+    }
+    // ... then the per-warp digit counters advance round by round (stable)
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const bool ok = wbase + 32 * r < tile_n;
+        const uint32_t d = (key[r] >> shift) & (ND - 1), before = rank[r] & 0xFFu, group = rank[r] >> 8;
         uint32_t prev = 0;
         if (ok) prev = my_cnt[d];
         __syncwarp();
-        if (ok && before == 0) my_cnt[d] = prev + __popc(peers);
+        if (ok && before == 0) my_cnt[d] = prev + group;
         __syncwarp();
         rank[r] = (uint16_t)(prev + before);
     }

@@ -23,7 +23,8 @@ ia, isamp = hdr.index("Instructions Executed"), hdr.index("# Samples")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 with tempfile.TemporaryDirectory() as td:
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=td, capture_output=True)
-    cub = next(os.path.join(td, f) for f in os.listdir(td) if f.startswith("kernels"))
+    stem = os.environ.get("NCU_LINES_CUBIN", "kernels")  # which translation unit holds the kernel
+    cub = next(os.path.join(td, f) for f in os.listdir(td) if f.startswith(stem))
     dis = subprocess.run(["nvdisasm", "-g", cub], capture_output=True, text=True).stdout.split("\n")
 start = next(i for i, l in enumerate(dis) if l.startswith(".text.") and kname in l)
 cur, seq = None, []
