@@ -171,18 +171,22 @@ int32_t device_psame(gtgpu_igd* g, int32_t m, int32_t* d_psame) {
 
 }  // namespace
 
-__device__ __forceinline__ uint32_t lb_i32(const int32_t* __restrict__ arr, const uint32_t* __restrict__ lut, uint32_t nb,
-                                           uint32_t n, uint32_t shift, int32_t key) {
-    if (key <= 0) return 0;
-    uint32_t b = (uint32_t)key >> shift;
-    if (b >= nb) return n;
-    uint32_t lo = __ldg(lut + b), hi = __ldg(lut + b + 1);
-    while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(arr + mid) < key) lo = mid + 1;
-        else hi = mid;
+// Warp-cooperative lower bound (first index whose value is >= key) inside [lo, hi): 32 probes per step instead of one.
+// A bisection costs log2(range) DEPENDENT loads, and with one query per warp that chain — two searches of five to eight
+// round trips each — was most of a query's time: nothing in the memory system was more than 60 % busy (ncu, C4).
+__device__ __forceinline__ uint32_t lb_warp(const int32_t* __restrict__ arr, uint32_t lo, uint32_t hi, int32_t key, uint32_t lane) {
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    while (hi - lo > 32u) {  // 32 evenly spaced samples: the answer lies between two neighbours
+        const uint32_t step = (hi - lo + 31u) / 32u, idx = lo + lane * step;
+        const bool below = idx < hi && __ldg(arr + idx) < key;
+        const uint32_t k = __popc(__ballot_sync(FULL, below));  // the samples are sorted: the first k are below the key
+        if (k == 0) return lo;
+        const uint32_t first = lo + (k - 1) * step + 1;
+        hi = min(lo + k * step, hi);
+        lo = first;
     }
-    return lo;
+    const bool below = lo + lane < hi && __ldg(arr + lo + lane) < key;
+    return lo + __popc(__ballot_sync(FULL, below));
 }
 
 struct IgdView {
@@ -193,28 +197,62 @@ struct IgdView {
 };
 
 // One warp per query.  BINARY selects count_region_hits semantics.
+#ifndef GT_IGD_MINBLOCKS
+#define GT_IGD_MINBLOCKS 5
+#endif
 template <bool BINARY>
-__global__ void __launch_bounds__(256) igd_count_kernel(IgdView v, uint64_t n, const uint32_t* __restrict__ set_of,
+__global__ void __launch_bounds__(256, GT_IGD_MINBLOCKS) igd_count_kernel(IgdView v, uint64_t n, const uint32_t* __restrict__ set_of,
                                                          const uint32_t* __restrict__ chr, const uint32_t* __restrict__ qstart,
                                                          const uint32_t* __restrict__ qend, int32_t m,
                                                          unsigned long long* __restrict__ out) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n; q += warps) {
-        const uint32_t c = __ldg(chr + q);
-        int32_t s = (int32_t)__ldg(qstart + q), e = (int32_t)__ldg(qend + q);
+    uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // the next query (and its set) is requested while this one is resolved
+    uint32_t nc = 0, nset = 0;
+    int32_t ns = 0, ne = 0;
+    if (q < n) {
+        nc = __ldg(chr + q);
+        ns = (int32_t)__ldg(qstart + q);
+        ne = (int32_t)__ldg(qend + q);
+        nset = __ldg(set_of + q);
+    }
+    for (; q < n; q += warps) {
+        const uint32_t c = nc, set = nset;
+        int32_t s = ns, e = ne;
+        if (q + warps < n) {
+            nc = __ldg(chr + q + warps);
+            ns = (int32_t)__ldg(qstart + q + warps);
+            ne = (int32_t)__ldg(qend + q + warps);
+            nset = __ldg(set_of + q + warps);
+        }
         if (c >= v.n_chroms || s >= e || e <= 0) continue;  // igd.rs:514-522
         s = max(s, 0);
         const uint32_t o = __ldg(v.off + c), len = __ldg(v.off + c + 1) - o;
         if (len == 0) continue;
-        // records that can reach the query: start < e, and some record at or before them ends after s
-        const uint32_t ub = lb_i32(v.start + o, v.lut + __ldg(v.lut_s_off + c), __ldg(v.nb_s + c), len, v.shift, e);
-        const uint32_t lo = lb_i32(v.pmax + o, v.lut + __ldg(v.lut_p_off + c), __ldg(v.nb_p + c), len, v.shift, s + 1);
-        unsigned long long* row = out + (uint64_t)__ldg(set_of + q) * v.n_files;
+        // records that can reach the query: start < e, and some record at or before them ends after s.  Both searches start
+        // from their LUT bins (four independent loads), then narrow 32 probes at a time.
+        const uint32_t* lut_s = v.lut + __ldg(v.lut_s_off + c);
+        const uint32_t* lut_p = v.lut + __ldg(v.lut_p_off + c);
+        const uint32_t nb_s = __ldg(v.nb_s + c), nb_p = __ldg(v.nb_p + c);
+        const uint32_t bs = (uint32_t)e >> v.shift, bp = (uint32_t)(s + 1) >> v.shift;  // e >= 1, s + 1 >= 1
+        uint32_t s_lo = len, s_hi = len, p_lo = len, p_hi = len;
+        if (bs < nb_s) {
+            s_lo = __ldg(lut_s + bs);
+            s_hi = __ldg(lut_s + bs + 1);
+        }
+        if (bp < nb_p) {
+            p_lo = __ldg(lut_p + bp);
+            p_hi = __ldg(lut_p + bp + 1);
+        }
+        const uint32_t ub = lb_warp(v.start + o, s_lo, s_hi, e, lane);
+        const uint32_t lo = lb_warp(v.pmax + o, p_lo, p_hi, s + 1, lane);
+        unsigned long long* row = out + (uint64_t)set * v.n_files;
         // 128 candidates per round: every lane requests its four records (start, end, file, psame — sixteen independent loads)
-        // before it tests any of them: 24.7 -> 18.9 ms on the LOLA configuration (1 k x 10 k sets).  What remains is the L2's
-        // atomic rate (1.7e9 hits in 18.9 ms = 9e10 64-bit atomics / s): walking the queries in genome order (radix-sorted,
-        // L2-resident record segments) did not change the kernel time (18.4 ms), and a variant that kept the current set's
+        // before it tests any of them: 24.7 -> 18.9 ms on the LOLA configuration (1 k x 10 k sets).  ncu (profiles/r02/
+        // c4_igd_count_ncu_full.txt): the reductions run at a quarter of the L2's rate; the kernel waits on its own chain of
+        // loads per query with the memory system at half load (72 GB of record reads from DRAM).  Walking the queries in
+        // genome order (radix-sorted) did not change the kernel time (18.4 ms), and a variant that kept the current set's
         // matrix row in shared memory (32-bit shared atomics, one flush per 4 096 queries) was slower (41 ms) — both measured
         // in round 2 and dropped.
         for (uint32_t base = o + lo; base < o + ub; base += 128) {
@@ -492,7 +530,15 @@ int32_t igd_count_dev_locked(gtgpu_igd* g, bool binary, uint64_t n, const uint32
     if (n == 0) return GTGPU_OK;
     IgdView v{g->d_off, g->d_lut_s_off, g->d_nb_s, g->d_lut_p_off, g->d_nb_p, g->d_file, g->d_lut,
               g->d_start, g->d_end, g->d_pmax, d_psame, g->n_chroms, g->shift, g->n_files};
-    const int grid = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 8);
+    // exactly the blocks that are resident at once (the queries are strided over the warps): a grid of 8 blocks per SM
+    // ran a second, partial wave (17.3 vs 16.6 ms on C4); fewer resident warps are slower (4 per SM 17.8, 3: 21.3, 2: 28.9 ms),
+    // and a sixth block per SM only fits with spills (21.9 ms)
+    int ctas_per_sm = 0;
+    if (binary) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, igd_count_kernel<true>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, igd_count_kernel<false>, 256, 0);
+    if (ctas_per_sm < 1) ctas_per_sm = 4;
+    if (const char* env = getenv("GTGPU_IGD_CTAS")) ctas_per_sm = std::max(1, atoi(env));  // tuning knob: blocks per SM of the grid
+    const int grid = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * ctas_per_sm);
     ctx->time_begin();
     if (binary)
         igd_count_kernel<true><<<grid, 256, 0, ctx->stream>>>(v, n, d_set_of, d_chr, d_start, d_end, m, (unsigned long long*)d_out);
