@@ -212,86 +212,165 @@ int32_t inclusive_max_scan_u64(gtgpu_ctx* ctx, const unsigned long long* d_in, u
 #ifndef GT_RS_BALLOT
 #define GT_RS_BALLOT 1
 #endif
-constexpr int RS_THREADS = 512;
-constexpr int RS_ROUNDS = 16;                          // elements per lane
-constexpr int RS_WARP_TILE = 32 * RS_ROUNDS;           // 512 consecutive elements per warp
-constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;        // 8 192 per block
-constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_HIST_THREADS = 512;
+
+// Shape of the scatter kernel: threads per block, elements per lane ("rounds": the length of a warp's ranking chain), blocks
+// per SM.  The tile (threads x rounds) is also the histogram kernel's tile.  Shared memory per block = 8 B per tile element +
+// 2 B per (warp, digit) counter + 8 B per digit, so a shorter tile buys resident warps: the kernel is bound by the latency of
+// its phases (load, rank, stage, write), not by a pipe, and what hides that latency is other blocks in other phases.
+struct RsShape {
+    int threads, rounds, min_blocks;
+};
+constexpr RsShape RS_SHAPES[] = {
+    {512, 16, 2},  // 0: 8 192-element tile, 32 warps per SM (round 2's first shape)
+    {512, 12, 3},  // 1: 6 144, 48 warps
+    {512, 8, 4},   // 2: 4 096, 64 warps (32 registers)
+    {256, 16, 4},  // 3: 4 096, 32 warps in four blocks
+    {256, 16, 5},  // 4: 4 096, 40 warps
+    {256, 12, 6},  // 5: 3 072, 48 warps
+    {1024, 8, 2},  // 6: 8 192, 64 warps (32 registers)
+    {1024, 16, 1}, // 7: 16 384, 32 warps in one block
+    {1024, 20, 1}, // 8: 20 480, 32 warps in one block
+};
+constexpr int RS_N_SHAPES = (int)(sizeof(RS_SHAPES) / sizeof(RS_SHAPES[0]));
+#ifndef GT_RS_DEFAULT_SHAPE
+#define GT_RS_DEFAULT_SHAPE 0
+#endif
+
+// run-time choice (GTGPU_RS_SHAPE, for sweeps; read at every call so that one process can compare shapes)
+static int rs_shape_index() {
+    const char* e = getenv("GTGPU_RS_SHAPE");
+    if (e && *e) {
+        const int v = atoi(e);
+        if (v >= 0 && v < RS_N_SHAPES) return v;
+    }
+    return GT_RS_DEFAULT_SHAPE;
+}
+static bool rs_prefetch() {
+    const char* e = getenv("GTGPU_RS_PREFETCH");
+    return !(e && *e == '0');
+}
 
 // DB = digit width of the pass: 8 bits, or 9 when that saves a whole pass (17-18 and 25-27 significant bits)
-template <int DB>
-__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n_cap,
-                                                                const uint64_t* __restrict__ d_n, int shift,
-                                                                uint32_t n_tiles, uint32_t* __restrict__ hist) {
+template <int DB, int TILE>
+__global__ void __launch_bounds__(RS_HIST_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n_cap,
+                                                                     const uint64_t* __restrict__ d_n, int shift,
+                                                                     uint32_t n_tiles, uint32_t* __restrict__ hist) {
     constexpr uint32_t ND = 1u << DB;
+    constexpr int WARPS = RS_HIST_THREADS / 32;
+    constexpr int ROUNDS = (TILE + RS_HIST_THREADS - 1) / RS_HIST_THREADS;
     const uint64_t n = d_n ? min((uint64_t)*d_n, n_cap) : n_cap;  // element count known on the device only (no host sync)
-    // one histogram per warp (no contention between warps; a warp's 32 lanes rarely share a digit), summed at the end
-    __shared__ uint32_t s_hist[RS_WARPS / 2][ND];
-    for (uint32_t i = threadIdx.x; i < (RS_WARPS / 2) * ND; i += RS_THREADS) (&s_hist[0][0])[i] = 0;
+    // one histogram per warp pair (little contention; a warp's 32 lanes rarely share a digit), summed at the end
+    __shared__ uint32_t s_hist[WARPS / 2][ND];
+    for (uint32_t i = threadIdx.x; i < (WARPS / 2) * ND; i += RS_HIST_THREADS) (&s_hist[0][0])[i] = 0;
     __syncthreads();
-    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
+    const uint64_t base = (uint64_t)blockIdx.x * TILE;
+    const uint64_t lim = min(n, base + TILE);
     uint32_t* mine = s_hist[(threadIdx.x >> 5) >> 1];
-    // all sixteen loads of a thread in flight before the first atomic (four at a time left the DRAM at a quarter of its rate)
-    uint32_t key[RS_ROUNDS];
+    // all loads of a thread in flight before the first atomic (four at a time left the DRAM at a quarter of its rate)
+    uint32_t key[ROUNDS];
 #pragma unroll
-    for (int k = 0; k < RS_ROUNDS; ++k) {
-        const uint64_t i = base + (uint64_t)k * RS_THREADS + threadIdx.x;
-        key[k] = i < n ? __ldcs(keys + i) : 0;
+    for (int k = 0; k < ROUNDS; ++k) {
+        const uint64_t i = base + (uint64_t)k * RS_HIST_THREADS + threadIdx.x;
+        key[k] = i < lim ? __ldcs(keys + i) : 0;
     }
 #pragma unroll
-    for (int k = 0; k < RS_ROUNDS; ++k)
-        if (base + (uint64_t)k * RS_THREADS + threadIdx.x < n) atomicAdd(&mine[(key[k] >> shift) & (ND - 1)], 1u);
+    for (int k = 0; k < ROUNDS; ++k)
+        if (base + (uint64_t)k * RS_HIST_THREADS + threadIdx.x < lim) atomicAdd(&mine[(key[k] >> shift) & (ND - 1)], 1u);
     __syncthreads();
-    for (uint32_t d = threadIdx.x; d < ND; d += RS_THREADS) {
+    for (uint32_t d = threadIdx.x; d < ND; d += RS_HIST_THREADS) {
         uint32_t t = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS / 2; ++w) t += s_hist[w][d];
+        for (int w = 0; w < WARPS / 2; ++w) t += s_hist[w][d];
         hist[(uint64_t)d * n_tiles + blockIdx.x] = t;  // digit-major: one scan orders everything
     }
 }
 
-// Scatter of one pass.  A block sorts its 8 192-element tile by digit in SHARED memory first (stable: per-warp ranks from
-// __match_any_sync round by round, warps in order), then writes the tile out digit by digit — a digit's elements of one
-// tile go to consecutive addresses, so the global stores are coalesced runs (32-64 B per digit and tile on average)
-// instead of 8 192 single words.  The first version stored every element straight from its ranking round: 16 scattered
-// 4-byte stores per lane and array, 9.8 ms per 2.5e8 pairs; this one: see profiles/r02.
-template <int DB>
-__global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
-                                                                   const uint32_t* __restrict__ vals_in, uint64_t n_cap,
-                                                                   const uint64_t* __restrict__ d_n, int shift,
-                                                                   uint32_t n_tiles, const uint32_t* __restrict__ bucket_start,
-                                                                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+// Scatter of one pass.  A block sorts its tile by digit in SHARED memory first (stable: per-warp ranks from the set of lanes
+// with the same digit, round by round, warps in order), then writes the tile out digit by digit — a digit's elements of one
+// tile go to consecutive addresses, so the global stores are coalesced runs instead of single words.  (The first version
+// stored every element straight from its ranking round: 16 scattered 4-byte stores per lane and array, 9.8 ms per 2.5e8
+// pairs; the second held the keys in registers and fetched the values in the middle of the kernel: 64 registers, two blocks
+// per SM, two exposed load latencies per tile; see profiles/r02.)
+//
+// The tile arrives by cp.async at the very top — keys into the buffer that will hold the sorted VALUES, values into the buffer
+// that will hold the sorted KEYS — and the kernel only waits for the keys before it ranks; the values land while it does.
+// Ranking reads the keys back from shared memory round by round (conflict-free: a warp's round is 32 consecutive words), so
+// the only per-element state in registers is the 16-bit rank (two per register).  The swap into sorted order lifts the
+// values into registers, moves the keys buffer to buffer, then drops the values: ROUNDS registers at the peak instead of
+// 3 x ROUNDS, which is what lets the shorter shapes keep three or four blocks on an SM without spilling.
+__device__ __forceinline__ uint32_t rs_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rs_cp_async16(void* s, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rs_smem_addr(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void rs_cp_async4(void* s, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rs_smem_addr(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void rs_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void rs_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// tile_n words from g to s: 16-byte copies when the source is aligned and the tile is full, single words otherwise
+template <int THREADS, int TILE>
+__device__ __forceinline__ void rs_stage_tile(uint32_t* s, const uint32_t* g, uint32_t tile_n, uint32_t tid) {
+    if (tile_n == TILE && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+#pragma unroll
+        for (uint32_t c = tid; c < TILE / 4; c += THREADS) rs_cp_async16(s + 4 * c, g + 4 * c);
+    } else {
+        for (uint32_t j = tid; j < tile_n; j += THREADS) rs_cp_async4(s + j, g + j);
+    }
+}
+
+template <int DB, int THREADS, int ROUNDS, int MINB, bool PF>
+__global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
+                                                                      const uint32_t* __restrict__ vals_in, uint64_t n_cap,
+                                                                      const uint64_t* __restrict__ d_n, int shift,
+                                                                      uint32_t n_tiles, const uint32_t* __restrict__ bucket_start,
+                                                                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
     constexpr uint32_t ND = 1u << DB;
+    constexpr int WARPS = THREADS / 32, TILE = THREADS * ROUNDS, WARP_TILE = 32 * ROUNDS;
+    constexpr int DPT = (int)ND > THREADS ? (int)ND / THREADS : 1;  // digits per thread in phase 2
+    static_assert((int)ND % THREADS == 0 || (int)ND < THREADS, "digits must divide over the threads");
+    static_assert(ROUNDS % 4 == 0, "ranks are packed in pairs, the tile is staged in 16-byte pieces");
     const uint64_t n = d_n ? min((uint64_t)*d_n, n_cap) : n_cap;
     extern __shared__ __align__(16) uint32_t s_mem[];
-    uint32_t* s_key = s_mem;                        // [RS_TILE] the tile, sorted by digit
-    uint32_t* s_val = s_mem + RS_TILE;              // [RS_TILE]
-    uint32_t* s_cnt = s_mem + 2 * RS_TILE;          // [RS_WARPS][ND] per-warp digit counts, then each warp's first slot per digit
-    uint32_t* s_dbase = s_cnt + RS_WARPS * ND;      // [ND] first slot of each digit in the sorted tile
-    uint32_t* s_gbase = s_dbase + ND;               // [ND] global position of the digit's first element minus s_dbase
-    __shared__ uint32_t s_wsum[RS_WARPS];
+    uint32_t* s_key = s_mem;                                       // [TILE] the values as they arrive, then the keys sorted by digit
+    uint32_t* s_val = s_mem + TILE;                                // [TILE] the keys as they arrive, then the values sorted by digit
+    uint32_t* s_dbase = s_mem + 2 * TILE;                          // [ND] first slot of each digit in the sorted tile
+    uint32_t* s_gbase = s_dbase + ND;                              // [ND] global position of the digit's first element minus s_dbase
+    uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_gbase + ND);   // [WARPS][ND] per-warp digit counts (<= 32 x ROUNDS), then
+                                                                   // the digit's elements in earlier warps (<= TILE < 65 536)
+    __shared__ uint32_t s_wsum[WARPS];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t tile0 = (uint64_t)blockIdx.x * RS_TILE;
+    const uint64_t tile0 = (uint64_t)blockIdx.x * TILE;
     if (tile0 >= n) return;
-    const uint32_t tile_n = (uint32_t)min((uint64_t)RS_TILE, n - tile0);
-    for (uint32_t i = tid; i < RS_WARPS * ND; i += RS_THREADS) s_cnt[i] = 0;
-    __syncthreads();
-    // ---- 1. rank inside the warp, round by round (stable) ----------------------------------------------------------------
-    const uint32_t wbase = warp * RS_WARP_TILE + lane;
-    uint32_t key[RS_ROUNDS];
-    uint16_t rank[RS_ROUNDS];
-    uint32_t* my_cnt = s_cnt + warp * ND;
+    const uint32_t tile_n = (uint32_t)min((uint64_t)TILE, n - tile0);
+    uint32_t* in_key = s_val;  // arrival buffers
+    uint32_t* in_val = s_key;
+    rs_stage_tile<THREADS, TILE>(in_key, keys_in + tile0, tile_n, tid);
+    rs_cp_async_commit();
+    rs_stage_tile<THREADS, TILE>(in_val, vals_in + tile0, tile_n, tid);
+    rs_cp_async_commit();
+    // this tile's row of the bucket table (a gather: the table is digit-major), requested now, used after phase 2
+    const bool has_digits = tid * DPT < ND;
+    uint32_t gstart[DPT];
+    if (PF && has_digits) {
 #pragma unroll
-    for (int r = 0; r < RS_ROUNDS; ++r) {
-        const uint32_t j = wbase + 32 * r;
-        key[r] = j < tile_n ? __ldcs(keys_in + tile0 + j) : 0;
+        for (int k = 0; k < DPT; ++k) gstart[k] = __ldg(bucket_start + (uint64_t)(tid * DPT + k) * n_tiles + blockIdx.x);
     }
-    // the sixteen matches do not depend on each other: issue them together (a match per round in front of that round's
-    // counter update left every warp waiting on its result: a third of the kernel's stall samples) ...
+    for (uint32_t i = tid; i < WARPS * ND / 2; i += THREADS) reinterpret_cast<uint32_t*>(s_cnt)[i] = 0;
+    rs_cp_async_wait<1>();  // my pieces of the keys have landed ...
+    __syncthreads();        // ... everyone's have, and the counters are zero
+    // ---- 1. rank inside the warp, round by round (stable) ----------------------------------------------------------------
+    const uint32_t wbase = warp * WARP_TILE + lane;
+    uint32_t rank2[ROUNDS / 2];  // two 16-bit ranks per register
+    uint16_t* my_cnt = s_cnt + warp * ND;
+    // the matches do not depend on each other: issue them ahead of the counter rounds (a match per round in front of that
+    // round's counter update left every warp waiting on its result: a third of the kernel's stall samples) ...
 #pragma unroll
-    for (int r = 0; r < RS_ROUNDS; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         const bool ok = wbase + 32 * r < tile_n;
-        const uint32_t d = ok ? (key[r] >> shift) & (ND - 1) : ND + lane;  // invalid lanes never match anyone
+        const uint32_t d = ok ? (in_key[wbase + 32 * r] >> shift) & (ND - 1) : ND + lane;  // invalid lanes never match anyone
 #if GT_RS_BALLOT
         uint32_t peers = __ballot_sync(0xFFFFFFFFu, ok);
 #pragma unroll
@@ -303,32 +382,41 @@ __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const uint
 #else
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
 #endif
-        rank[r] = (uint16_t)(__popc(peers & ((1u << lane) - 1)) | __popc(peers) << 8);  // lanes before me | group size
+        const uint32_t packed = __popc(peers & ((1u << lane) - 1)) | __popc(peers) << 8;  // lanes before me | group size
+        if (r & 1) rank2[r >> 1] |= packed << 16;
+        else rank2[r >> 1] = packed;
     }
     // ... then the per-warp digit counters advance round by round (stable)
 #pragma unroll
-    for (int r = 0; r < RS_ROUNDS; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         const bool ok = wbase + 32 * r < tile_n;
-        const uint32_t d = (key[r] >> shift) & (ND - 1), before = rank[r] & 0xFFu, group = rank[r] >> 8;
+        const uint32_t mine = (r & 1) ? rank2[r >> 1] >> 16 : rank2[r >> 1] & 0xFFFFu;
+        const uint32_t d = ok ? (in_key[wbase + 32 * r] >> shift) & (ND - 1) : 0, before = mine & 0xFFu, group = mine >> 8;
         uint32_t prev = 0;
         if (ok) prev = my_cnt[d];
         __syncwarp();
-        if (ok && before == 0) my_cnt[d] = prev + group;
+        if (ok && before == 0) my_cnt[d] = (uint16_t)(prev + group);
         __syncwarp();
-        rank[r] = (uint16_t)(prev + before);
+        if (r & 1) rank2[r >> 1] = (rank2[r >> 1] & 0xFFFFu) | (prev + before) << 16;
+        else rank2[r >> 1] = (rank2[r >> 1] & 0xFFFF0000u) | (prev + before);
     }
     __syncthreads();
     // ---- 2. digit totals -> first slot of every digit, and of every (warp, digit) ------------------------------------------
-    uint32_t tot = 0;  // thread d: tile total of digit d (ND <= RS_THREADS)
-    if (tid < ND) {
-        uint32_t run = 0;
+    uint32_t tot = 0, sub[DPT];  // thread t: digits [t * DPT, (t + 1) * DPT)
+    if (has_digits) {
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
-            const uint32_t c = s_cnt[w * ND + tid];
-            s_cnt[w * ND + tid] = run;  // elements of this digit in earlier warps
-            run += c;
+        for (int k = 0; k < DPT; ++k) {
+            const uint32_t d = tid * DPT + k;
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t c = s_cnt[w * ND + d];
+                s_cnt[w * ND + d] = (uint16_t)run;  // elements of this digit in earlier warps
+                run += c;
+            }
+            sub[k] = run;
+            tot += run;
         }
-        tot = run;
     }
     uint32_t incl = tot;
 #pragma unroll
@@ -338,27 +426,44 @@ __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const uint
     }
     if (lane == 31) s_wsum[warp] = incl;
     __syncthreads();
-    if (tid < ND) {
-        uint32_t before = 0;
-        for (uint32_t w = 0; w < warp; ++w) before += s_wsum[w];
-        const uint32_t first = before + incl - tot;
-        s_dbase[tid] = first;
-        s_gbase[tid] = bucket_start[(uint64_t)tid * n_tiles + blockIdx.x] - first;  // wrapping on purpose
+    if (has_digits) {
+        uint32_t first = incl - tot;
+        for (uint32_t w = 0; w < warp; ++w) first += s_wsum[w];
+#pragma unroll
+        for (int k = 0; k < DPT; ++k) {
+            const uint32_t d = tid * DPT + k;
+            const uint32_t g = PF ? gstart[k] : bucket_start[(uint64_t)d * n_tiles + blockIdx.x];
+            s_dbase[d] = first;
+            s_gbase[d] = g - first;  // wrapping on purpose
+            first += sub[k];
+        }
     }
+    rs_cp_async_wait<0>();  // my pieces of the values have landed
     __syncthreads();
     // ---- 3. the tile, sorted by digit, in shared memory ------------------------------------------------------------------------
+    // values up into registers (their buffer becomes the sorted keys), keys across, values down
+    uint32_t val[ROUNDS];
 #pragma unroll
-    for (int r = 0; r < RS_ROUNDS; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) val[r] = wbase + 32 * r < tile_n ? in_val[wbase + 32 * r] : 0;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
         if (wbase + 32 * r < tile_n) {
-            const uint32_t d = (key[r] >> shift) & (ND - 1);
-            const uint32_t p = s_dbase[d] + my_cnt[d] + rank[r];
-            s_key[p] = key[r];
-            s_val[p] = __ldcs(vals_in + tile0 + wbase + 32 * r);  // values are only touched here: 16 fewer live registers while ranking
+            const uint32_t k = in_key[wbase + 32 * r];
+            const uint32_t d = (k >> shift) & (ND - 1);
+            const uint32_t p = s_dbase[d] + my_cnt[d] + ((r & 1) ? rank2[r >> 1] >> 16 : rank2[r >> 1] & 0xFFFFu);
+            s_key[p] = k;
+            if (r & 1) rank2[r >> 1] = (rank2[r >> 1] & 0xFFFFu) | p << 16;  // the slot replaces the rank (TILE <= 65 536)
+            else rank2[r >> 1] = (rank2[r >> 1] & 0xFFFF0000u) | p;
         }
     }
     __syncthreads();
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r)
+        if (wbase + 32 * r < tile_n) s_val[(r & 1) ? rank2[r >> 1] >> 16 : rank2[r >> 1] & 0xFFFFu] = val[r];
+    __syncthreads();
     // ---- 4. write out: consecutive threads = consecutive slots = (inside a digit) consecutive global addresses ------------------
-    for (uint32_t p = tid; p < tile_n; p += RS_THREADS) {
+    for (uint32_t p = tid; p < tile_n; p += THREADS) {
         const uint32_t k = s_key[p];
         const uint32_t dst = s_gbase[(k >> shift) & (ND - 1)] + p;
         keys_out[dst] = k;
@@ -366,8 +471,42 @@ __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const uint
     }
 }
 
-template <int DB>
-static constexpr size_t radix_scatter_smem() { return (size_t)(2 * RS_TILE + RS_WARPS * (1 << DB) + 2 * (1 << DB)) * 4; }
+static size_t radix_scatter_smem(int width, const RsShape& sh) {
+    const size_t nd = (size_t)1 << width, tile = (size_t)sh.threads * sh.rounds;
+    return 8 * tile + 8 * nd + 2 * nd * (size_t)(sh.threads / 32);
+}
+
+template <int DB, int S, bool PF>
+static cudaError_t launch_radix_pass(gtgpu_ctx* ctx, const uint32_t* ki, const uint32_t* vi, uint64_t n, const uint64_t* d_n, int shift,
+                                     uint32_t tiles, uint32_t* hist, uint32_t* starts, void* scan_tmp, uint32_t* ko, uint32_t* vo,
+                                     int32_t* status) {
+    constexpr RsShape sh = RS_SHAPES[S];
+    constexpr int TILE = sh.threads * sh.rounds;
+    auto kern = radix_scatter_kernel<DB, sh.threads, sh.rounds, sh.min_blocks, PF>;
+    const size_t smem = radix_scatter_smem(DB, sh);
+    // > 48 KB of dynamic shared memory is an opt-in per kernel and per device: set it on every call (cheap)
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    radix_hist_kernel<DB, TILE><<<tiles, RS_HIST_THREADS, 0, ctx->stream>>>(ki, n, d_n, shift, tiles, hist);
+    ctx->launches++;
+    *status = exclusive_scan<uint32_t>(ctx, hist, starts, ((uint64_t)1 << DB) * tiles, scan_tmp);
+    if (*status != GTGPU_OK) return cudaSuccess;
+    kern<<<tiles, sh.threads, smem, ctx->stream>>>(ki, vi, n, d_n, shift, tiles, starts, ko, vo);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+template <int S>
+static cudaError_t launch_radix_pass_s(int width, bool pf, gtgpu_ctx* ctx, const uint32_t* ki, const uint32_t* vi, uint64_t n,
+                                       const uint64_t* d_n, int shift, uint32_t tiles, uint32_t* hist, uint32_t* starts, void* scan_tmp,
+                                       uint32_t* ko, uint32_t* vo, int32_t* status) {
+    if (width == 8) {
+        return pf ? launch_radix_pass<8, S, true>(ctx, ki, vi, n, d_n, shift, tiles, hist, starts, scan_tmp, ko, vo, status)
+                  : launch_radix_pass<8, S, false>(ctx, ki, vi, n, d_n, shift, tiles, hist, starts, scan_tmp, ko, vo, status);
+    }
+    return pf ? launch_radix_pass<9, S, true>(ctx, ki, vi, n, d_n, shift, tiles, hist, starts, scan_tmp, ko, vo, status)
+              : launch_radix_pass<9, S, false>(ctx, ki, vi, n, d_n, shift, tiles, hist, starts, scan_tmp, ko, vo, status);
+}
 
 // passes and digit width for `bits` significant key bits: as few passes as 9-bit digits allow, 8-bit digits otherwise
 void radix_plan(int bits, int* passes, int* width) {
@@ -375,8 +514,15 @@ void radix_plan(int bits, int* passes, int* width) {
     *width = ((bits + *passes - 1) / *passes) <= 8 ? 8 : 9;
 }
 
+static uint64_t rs_min_tile() {
+    uint64_t t = ~0ull;
+    for (const RsShape& s : RS_SHAPES) t = std::min<uint64_t>(t, (uint64_t)s.threads * s.rounds);
+    return t;
+}
+
+// sized for the smallest tile any shape uses (the shape is a run-time choice)
 size_t radix_sort_temp_bytes(uint64_t n) {
-    const uint64_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    const uint64_t tiles = (n + rs_min_tile() - 1) / rs_min_tile();
     const uint64_t table = 512 * tiles;
     return (size_t)(table * 4 * 2 + exclusive_scan_temp_bytes(table, 4) + 256);
 }
@@ -391,30 +537,34 @@ int32_t radix_sort_pairs(gtgpu_ctx* ctx, uint64_t n, uint32_t* keys_a, uint32_t*
     if (n >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "radix_sort_pairs: too many elements");
     int passes, width;
     radix_plan(std::min(bits, 32), &passes, &width);
-    // > 48 KB of dynamic shared memory is an opt-in per kernel and per device: set it on every call (cheap)
-    GT_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)radix_scatter_smem<8>()));
-    GT_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)radix_scatter_smem<9>()));
-    const uint32_t tiles = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
-    const uint64_t table = ((uint64_t)1 << width) * tiles;
+    const int shape = rs_shape_index();
+    const bool pf = rs_prefetch();
+    const uint64_t tile = (uint64_t)RS_SHAPES[shape].threads * RS_SHAPES[shape].rounds;
+    const uint32_t tiles = (uint32_t)((n + tile - 1) / tile);
+    // the table layout of radix_sort_temp_bytes: two tables of 512 words per (smallest) tile, then the scan's own scratch
+    const uint64_t cap_tiles = (n + rs_min_tile() - 1) / rs_min_tile();
     uint32_t* hist = reinterpret_cast<uint32_t*>(d_temp);
-    uint32_t* starts = hist + 512ull * tiles;
-    void* scan_tmp = starts + 512ull * tiles;
+    uint32_t* starts = hist + 512ull * cap_tiles;
+    void* scan_tmp = starts + 512ull * cap_tiles;
     uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
     for (int p = 0, shift = 0; p < passes; ++p, shift += width) {
-        if (width == 8) radix_hist_kernel<8><<<tiles, RS_THREADS, 0, ctx->stream>>>(ki, n, d_n, shift, tiles, hist);
-        else radix_hist_kernel<9><<<tiles, RS_THREADS, 0, ctx->stream>>>(ki, n, d_n, shift, tiles, hist);
-        ctx->launches++;
-        GT_TRY(exclusive_scan<uint32_t>(ctx, hist, starts, table, scan_tmp));
-        if (width == 8)
-            radix_scatter_kernel<8><<<tiles, RS_THREADS, radix_scatter_smem<8>(), ctx->stream>>>(ki, vi, n, d_n, shift, tiles, starts, ko, vo);
-        else
-            radix_scatter_kernel<9><<<tiles, RS_THREADS, radix_scatter_smem<9>(), ctx->stream>>>(ki, vi, n, d_n, shift, tiles, starts, ko, vo);
-        ctx->launches++;
+        int32_t status = GTGPU_OK;
+        cudaError_t e = cudaErrorInvalidValue;
+        switch (shape) {
+#define GT_RS_CASE(S)                                                                                                              \
+    case S:                                                                                                                        \
+        e = launch_radix_pass_s<S>(width, pf, ctx, ki, vi, n, d_n, shift, tiles, hist, starts, scan_tmp, ko, vo, &status);        \
+        break;
+            GT_RS_CASE(0) GT_RS_CASE(1) GT_RS_CASE(2) GT_RS_CASE(3) GT_RS_CASE(4) GT_RS_CASE(5) GT_RS_CASE(6) GT_RS_CASE(7) GT_RS_CASE(8)
+#undef GT_RS_CASE
+        }
+        static_assert(RS_N_SHAPES == 9, "one case per shape");
+        GT_TRY(status);
+        GT_CUDA(e);
         std::swap(ki, ko);
         std::swap(vi, vo);
         *result_in_b ^= 1;
     }
-    GT_CUDA(cudaGetLastError());
     return GTGPU_OK;
 }
 
