@@ -306,6 +306,12 @@ size_t radix_sort_temp_bytes(uint64_t n);
 int32_t radix_sort_pairs(gtgpu_ctx* ctx, uint64_t n, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
                          int bits, void* d_temp, int* result_in_b, const uint64_t* d_n = nullptr);
 void radix_plan(int bits, int* passes, int* width);
+// stable group-by of values by key in two passes, the second over packed words (sort.cu)
+bool radix_group_fits(uint32_t n_keys, uint32_t max_val);
+size_t radix_group_temp_bytes(uint64_t n, uint32_t n_keys);
+int32_t radix_group_values(gtgpu_ctx* ctx, uint64_t n_cap, const uint32_t* keys, const uint32_t* vals, uint32_t* packed_tmp,
+                           uint32_t* vals_out, uint32_t n_keys, uint32_t max_val, void* d_temp, const uint64_t* d_n,
+                           uint64_t* out_offsets, uint64_t* d_total);
 
 // ingest.cu / inflate.cu (the caller holds ctx->mu)
 int32_t tokenize_bed_locked(gtgpu_index* ix, const char* text, uint64_t n_bytes, uint32_t n_names, const char* names,

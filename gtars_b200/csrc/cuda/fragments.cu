@@ -76,11 +76,19 @@ static int32_t fragments_group_by(gtgpu_index* ix, uint64_t n, const uint32_t* d
         const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 16);
         frag_tag_tokens_kernel<<<grid, 256, 0, st>>>(n, d_off, d_bc, cap, d_tag_a, *tag_if);
         ctx->launches++;
-        int in_b = 0;
-        GT_TRY(radix_sort_pairs(ctx, cap, d_tag_a, first, d_tag_b, second, bits, d_sort_tmp, &in_b, d_misc));
-        const uint32_t* sorted_tags = in_b ? d_tag_b : d_tag_a;
-        frag_barcode_offsets_kernel<<<(n_barcodes + 1 + 255) / 256, 256, 0, st>>>(n_barcodes, d_misc, cap, sorted_tags, d_bco, d_total_or_null);
-        ctx->launches++;
+        const uint32_t max_token = std::max(ix->max_val, unk_id);
+        if (radix_group_fits(n_barcodes, max_token)) {
+            // two digit passes and the barcode's upper digit fits next to a token: the second pass sorts packed words and the
+            // barcode offsets come from counts (sort.cu, radix_group_values) — no sorted tags, 20 instead of 32 B per token
+            GT_TRY(radix_group_values(ctx, cap, d_tag_a, first, d_tag_b, d_out, n_barcodes, max_token, d_sort_tmp, d_misc, d_bco,
+                                      d_total_or_null));
+        } else {
+            int in_b = 0;
+            GT_TRY(radix_sort_pairs(ctx, cap, d_tag_a, first, d_tag_b, second, bits, d_sort_tmp, &in_b, d_misc));
+            const uint32_t* sorted_tags = in_b ? d_tag_b : d_tag_a;
+            frag_barcode_offsets_kernel<<<(n_barcodes + 1 + 255) / 256, 256, 0, st>>>(n_barcodes, d_misc, cap, sorted_tags, d_bco, d_total_or_null);
+            ctx->launches++;
+        }
         GT_CUDA(cudaGetLastError());
     }
     return GTGPU_OK;
@@ -126,7 +134,7 @@ int32_t tokenize_fragments_core(gtgpu_index* ix, uint64_t n, const uint32_t* d_c
         GT_TRY(ctx->scratch_get(SC_OUT_IDS2, cap * 4, (void**)&d_alt));
         GT_TRY(ctx->scratch_get(SC_IN2_CHR, cap * 4, (void**)&d_tag_a));
         GT_TRY(ctx->scratch_get(SC_IN2_START, cap * 4, (void**)&d_tag_b));
-        GT_TRY(ctx->scratch_get(SC_IN3_START, radix_sort_temp_bytes(cap), &d_tmp));
+        GT_TRY(ctx->scratch_get(SC_IN3_START, radix_group_temp_bytes(cap, n_barcodes), &d_tmp));
         // 1. tokens of every fragment in fragment order (hits, or unk), with per-fragment offsets
         GT_TRY(fragments_group_by(ix, n, d_chr, d_start, d_end, d_bc, n_barcodes, unk_id, cap, d_out, d_alt, d_tag_a, d_tag_b, d_off,
                                   d_ws, d_tmp, d_misc, d_bco, nullptr, 1, &tag_if));
@@ -289,7 +297,7 @@ extern "C" int32_t gtgpu_tokenize_fragments_dev(gtgpu_index* ix, uint64_t n, con
     GT_TRY(ctx->scratch_get(SC_OUT_OFFS, (n + 1) * 8, (void**)&d_off));
     GT_TRY(ctx->scratch_get(SC_TILE_STATUS, fused_workspace_bytes(n), &d_ws));
     GT_TRY(ctx->scratch_get(SC_MISC, 64, (void**)&d_misc));
-    GT_TRY(ctx->scratch_get(SC_IN3_START, radix_sort_temp_bytes(cap), &d_tmp));
+    GT_TRY(ctx->scratch_get(SC_IN3_START, radix_group_temp_bytes(cap, n_barcodes), &d_tmp));
     const uint32_t* tag_if = nullptr;
     return fragments_group_by(ix, n, d_chr, d_start, d_end, d_barcode_id, n_barcodes, unk_id, cap, d_out_ids, d_alt, d_tag_a, d_tag_b,
                               d_off, d_ws, d_tmp, d_misc, d_out_barcode_offsets, d_out_total, 0, &tag_if);

@@ -222,16 +222,15 @@ struct RsShape {
     int threads, rounds, min_blocks;
 };
 constexpr RsShape RS_SHAPES[] = {
-    {512, 16, 2},  // 0: 8 192-element tile, 32 warps per SM (round 2's first shape)
-    {512, 12, 3},  // 1: 6 144, 48 warps
-    {512, 8, 4},   // 2: 4 096, 64 warps (32 registers)
-    {256, 16, 4},  // 3: 4 096, 32 warps in four blocks
-    {256, 16, 5},  // 4: 4 096, 40 warps
-    {256, 12, 6},  // 5: 3 072, 48 warps
-    {1024, 8, 2},  // 6: 8 192, 64 warps (32 registers)
-    {1024, 16, 1}, // 7: 16 384, 32 warps in one block
-    {1024, 20, 1}, // 8: 20 480, 32 warps in one block
+    {512, 16, 2},   // 0: 8 192-element tile, 32 warps per SM — the default: 24.9 ms per 1e9 fragments on C5
+    {512, 12, 3},   // 1: 6 144, 48 warps: 27.4 ms (shorter runs, a larger bucket table)
+    {1024, 16, 1},  // 2: 16 384, 32 warps in one block: 27.9 ms (nothing overlaps the block's own phases)
 };
+// also measured (profiles/r02/c5_scatter_shape_sweep_*.jsonl): 512 x 8 x 4 blocks, 256 x 16 x 4 / 5, 256 x 12 x 6, 1 024 x 8 x 2,
+// 1 024 x 20 x 1 — all slower than shape 0 — and a shared-memory table instead of the ballots (every lane writes its lane number
+// at its digit and reads the slot back, only shared digits are then resolved by votes): 35 % fewer instructions, but the kernel is
+// as busy in the shared-memory pipe as in the issue slots, and two more conflicted accesses per round made it 4 % slower
+// (profiles/r02/c5_scatter_table_match_sweep.jsonl).
 constexpr int RS_N_SHAPES = (int)(sizeof(RS_SHAPES) / sizeof(RS_SHAPES[0]));
 #ifndef GT_RS_DEFAULT_SHAPE
 #define GT_RS_DEFAULT_SHAPE 0
@@ -245,10 +244,6 @@ static int rs_shape_index() {
         if (v >= 0 && v < RS_N_SHAPES) return v;
     }
     return GT_RS_DEFAULT_SHAPE;
-}
-static bool rs_prefetch() {
-    const char* e = getenv("GTGPU_RS_PREFETCH");
-    return !(e && *e == '0');
 }
 
 // DB = digit width of the pass: 8 bits, or 9 when that saves a whole pass (17-18 and 25-27 significant bits)
@@ -321,12 +316,20 @@ __device__ __forceinline__ void rs_stage_tile(uint32_t* s, const uint32_t* g, ui
     }
 }
 
-template <int DB, int THREADS, int ROUNDS, int MINB, bool PF>
+//
+// MODE: what moves.  RS_PAIRS: (key, value) in, (key, value) out.  RS_PACK: (key, value) in, ONE word out —
+// (key >> (shift + DB)) << aux | value: the key bits no later pass has sorted yet, next to the value.  RS_KEYS: one word in,
+// word & aux out (to vals_out) — the last pass over such packed words sheds the key.  radix_group_values runs PACK then KEYS:
+// 20 instead of 32 bytes of scatter traffic per element, and the second pass moves one array through shared memory, not two.
+enum { RS_PAIRS = 0, RS_PACK = 1, RS_KEYS = 2 };
+
+template <int DB, int THREADS, int ROUNDS, int MINB, int MODE>
 __global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
                                                                       const uint32_t* __restrict__ vals_in, uint64_t n_cap,
                                                                       const uint64_t* __restrict__ d_n, int shift,
                                                                       uint32_t n_tiles, const uint32_t* __restrict__ bucket_start,
-                                                                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+                                                                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                                      uint32_t aux) {
     constexpr uint32_t ND = 1u << DB;
     constexpr int WARPS = THREADS / 32, TILE = THREADS * ROUNDS, WARP_TILE = 32 * ROUNDS;
     constexpr int DPT = (int)ND > THREADS ? (int)ND / THREADS : 1;  // digits per thread in phase 2
@@ -349,12 +352,12 @@ __global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(const uint
     uint32_t* in_val = s_key;
     rs_stage_tile<THREADS, TILE>(in_key, keys_in + tile0, tile_n, tid);
     rs_cp_async_commit();
-    rs_stage_tile<THREADS, TILE>(in_val, vals_in + tile0, tile_n, tid);
-    rs_cp_async_commit();
+    if (MODE != RS_KEYS) rs_stage_tile<THREADS, TILE>(in_val, vals_in + tile0, tile_n, tid);
+    rs_cp_async_commit();  // (an empty group when there are no values)
     // this tile's row of the bucket table (a gather: the table is digit-major), requested now, used after phase 2
     const bool has_digits = tid * DPT < ND;
     uint32_t gstart[DPT];
-    if (PF && has_digits) {
+    if (has_digits) {
 #pragma unroll
         for (int k = 0; k < DPT; ++k) gstart[k] = __ldg(bucket_start + (uint64_t)(tid * DPT + k) * n_tiles + blockIdx.x);
     }
@@ -432,9 +435,8 @@ __global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(const uint
 #pragma unroll
         for (int k = 0; k < DPT; ++k) {
             const uint32_t d = tid * DPT + k;
-            const uint32_t g = PF ? gstart[k] : bucket_start[(uint64_t)d * n_tiles + blockIdx.x];
             s_dbase[d] = first;
-            s_gbase[d] = g - first;  // wrapping on purpose
+            s_gbase[d] = gstart[k] - first;  // wrapping on purpose
             first += sub[k];
         }
     }
@@ -442,10 +444,12 @@ __global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(const uint
     __syncthreads();
     // ---- 3. the tile, sorted by digit, in shared memory ------------------------------------------------------------------------
     // values up into registers (their buffer becomes the sorted keys), keys across, values down
-    uint32_t val[ROUNDS];
+    uint32_t val[MODE == RS_KEYS ? 1 : ROUNDS];
+    if (MODE != RS_KEYS) {
 #pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) val[r] = wbase + 32 * r < tile_n ? in_val[wbase + 32 * r] : 0;
-    __syncthreads();
+        for (int r = 0; r < ROUNDS; ++r) val[r] = wbase + 32 * r < tile_n ? in_val[wbase + 32 * r] : 0;
+        __syncthreads();
+    }
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
         if (wbase + 32 * r < tile_n) {
@@ -458,16 +462,24 @@ __global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(const uint
         }
     }
     __syncthreads();
+    if (MODE != RS_KEYS) {
 #pragma unroll
-    for (int r = 0; r < ROUNDS; ++r)
-        if (wbase + 32 * r < tile_n) s_val[(r & 1) ? rank2[r >> 1] >> 16 : rank2[r >> 1] & 0xFFFFu] = val[r];
-    __syncthreads();
+        for (int r = 0; r < ROUNDS; ++r)
+            if (wbase + 32 * r < tile_n) s_val[(r & 1) ? rank2[r >> 1] >> 16 : rank2[r >> 1] & 0xFFFFu] = val[r];
+        __syncthreads();
+    }
     // ---- 4. write out: consecutive threads = consecutive slots = (inside a digit) consecutive global addresses ------------------
     for (uint32_t p = tid; p < tile_n; p += THREADS) {
         const uint32_t k = s_key[p];
         const uint32_t dst = s_gbase[(k >> shift) & (ND - 1)] + p;
-        keys_out[dst] = k;
-        vals_out[dst] = s_val[p];
+        if (MODE == RS_PAIRS) {
+            keys_out[dst] = k;
+            vals_out[dst] = s_val[p];
+        } else if (MODE == RS_PACK) {
+            keys_out[dst] = (k >> (shift + DB)) << aux | s_val[p];
+        } else {
+            vals_out[dst] = k & aux;
+        }
     }
 }
 
@@ -476,36 +488,35 @@ static size_t radix_scatter_smem(int width, const RsShape& sh) {
     return 8 * tile + 8 * nd + 2 * nd * (size_t)(sh.threads / 32);
 }
 
-template <int DB, int S, bool PF>
+// one pass = histogram (or the caller's own, when it has more to count), scan, scatter
+template <int DB, int S, int MODE>
 static cudaError_t launch_radix_pass(gtgpu_ctx* ctx, const uint32_t* ki, const uint32_t* vi, uint64_t n, const uint64_t* d_n, int shift,
                                      uint32_t tiles, uint32_t* hist, uint32_t* starts, void* scan_tmp, uint32_t* ko, uint32_t* vo,
-                                     int32_t* status) {
+                                     uint32_t aux, bool hist_done, int32_t* status) {
     constexpr RsShape sh = RS_SHAPES[S];
     constexpr int TILE = sh.threads * sh.rounds;
-    auto kern = radix_scatter_kernel<DB, sh.threads, sh.rounds, sh.min_blocks, PF>;
+    auto kern = radix_scatter_kernel<DB, sh.threads, sh.rounds, sh.min_blocks, MODE>;
     const size_t smem = radix_scatter_smem(DB, sh);
     // > 48 KB of dynamic shared memory is an opt-in per kernel and per device: set it on every call (cheap)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    radix_hist_kernel<DB, TILE><<<tiles, RS_HIST_THREADS, 0, ctx->stream>>>(ki, n, d_n, shift, tiles, hist);
-    ctx->launches++;
+    if (!hist_done) {
+        radix_hist_kernel<DB, TILE><<<tiles, RS_HIST_THREADS, 0, ctx->stream>>>(ki, n, d_n, shift, tiles, hist);
+        ctx->launches++;
+    }
     *status = exclusive_scan<uint32_t>(ctx, hist, starts, ((uint64_t)1 << DB) * tiles, scan_tmp);
     if (*status != GTGPU_OK) return cudaSuccess;
-    kern<<<tiles, sh.threads, smem, ctx->stream>>>(ki, vi, n, d_n, shift, tiles, starts, ko, vo);
+    kern<<<tiles, sh.threads, smem, ctx->stream>>>(ki, vi, n, d_n, shift, tiles, starts, ko, vo, aux);
     ctx->launches++;
     return cudaGetLastError();
 }
 
 template <int S>
-static cudaError_t launch_radix_pass_s(int width, bool pf, gtgpu_ctx* ctx, const uint32_t* ki, const uint32_t* vi, uint64_t n,
+static cudaError_t launch_radix_pass_s(int width, gtgpu_ctx* ctx, const uint32_t* ki, const uint32_t* vi, uint64_t n,
                                        const uint64_t* d_n, int shift, uint32_t tiles, uint32_t* hist, uint32_t* starts, void* scan_tmp,
                                        uint32_t* ko, uint32_t* vo, int32_t* status) {
-    if (width == 8) {
-        return pf ? launch_radix_pass<8, S, true>(ctx, ki, vi, n, d_n, shift, tiles, hist, starts, scan_tmp, ko, vo, status)
-                  : launch_radix_pass<8, S, false>(ctx, ki, vi, n, d_n, shift, tiles, hist, starts, scan_tmp, ko, vo, status);
-    }
-    return pf ? launch_radix_pass<9, S, true>(ctx, ki, vi, n, d_n, shift, tiles, hist, starts, scan_tmp, ko, vo, status)
-              : launch_radix_pass<9, S, false>(ctx, ki, vi, n, d_n, shift, tiles, hist, starts, scan_tmp, ko, vo, status);
+    if (width == 8) return launch_radix_pass<8, S, RS_PAIRS>(ctx, ki, vi, n, d_n, shift, tiles, hist, starts, scan_tmp, ko, vo, 0, false, status);
+    return launch_radix_pass<9, S, RS_PAIRS>(ctx, ki, vi, n, d_n, shift, tiles, hist, starts, scan_tmp, ko, vo, 0, false, status);
 }
 
 // passes and digit width for `bits` significant key bits: as few passes as 9-bit digits allow, 8-bit digits otherwise
@@ -538,7 +549,6 @@ int32_t radix_sort_pairs(gtgpu_ctx* ctx, uint64_t n, uint32_t* keys_a, uint32_t*
     int passes, width;
     radix_plan(std::min(bits, 32), &passes, &width);
     const int shape = rs_shape_index();
-    const bool pf = rs_prefetch();
     const uint64_t tile = (uint64_t)RS_SHAPES[shape].threads * RS_SHAPES[shape].rounds;
     const uint32_t tiles = (uint32_t)((n + tile - 1) / tile);
     // the table layout of radix_sort_temp_bytes: two tables of 512 words per (smallest) tile, then the scan's own scratch
@@ -553,18 +563,181 @@ int32_t radix_sort_pairs(gtgpu_ctx* ctx, uint64_t n, uint32_t* keys_a, uint32_t*
         switch (shape) {
 #define GT_RS_CASE(S)                                                                                                              \
     case S:                                                                                                                        \
-        e = launch_radix_pass_s<S>(width, pf, ctx, ki, vi, n, d_n, shift, tiles, hist, starts, scan_tmp, ko, vo, &status);        \
+        e = launch_radix_pass_s<S>(width, ctx, ki, vi, n, d_n, shift, tiles, hist, starts, scan_tmp, ko, vo, &status);        \
         break;
-            GT_RS_CASE(0) GT_RS_CASE(1) GT_RS_CASE(2) GT_RS_CASE(3) GT_RS_CASE(4) GT_RS_CASE(5) GT_RS_CASE(6) GT_RS_CASE(7) GT_RS_CASE(8)
+            GT_RS_CASE(0) GT_RS_CASE(1) GT_RS_CASE(2)
 #undef GT_RS_CASE
         }
-        static_assert(RS_N_SHAPES == 9, "one case per shape");
+        static_assert(RS_N_SHAPES == 3, "one case per shape");
         GT_TRY(status);
         GT_CUDA(e);
         std::swap(ki, ko);
         std::swap(vi, vo);
         *result_in_b ^= 1;
     }
+    return GTGPU_OK;
+}
+
+// ---- stable group-by of values by key: two passes, the second one over packed words ------------------------------------------
+// For keys of 10-18 bits whose upper digit fits next to the value in 32 bits (C5: 17-bit barcodes, 20-bit tokens).  Pass 1
+// sorts the pairs by the low digit and writes (upper digit << value bits | value); pass 2 sorts those words by the upper digit
+// and writes the bare values.  The sorted keys never exist, so the group offsets come from counts: pass 1's output is ordered
+// by low digit, G[lo] = where digit lo starts in it; a tile of pass 2 that lies inside one low digit (all but <= 2^w of them)
+// knows the full key of every element from its upper digit alone, and its histogram — which pass 2 needs anyway — is added
+// to the per-key counts with one atomic per (tile, upper digit); tiles across a boundary look every element's position up.
+__global__ void rs_group_prepare_kernel(const uint32_t* __restrict__ starts, uint32_t n_tiles, uint32_t n_lo, uint64_t n_cap,
+                                        const uint64_t* __restrict__ d_n, uint32_t tile, uint32_t* __restrict__ G,
+                                        uint32_t* __restrict__ tile_lo, uint64_t* __restrict__ d_total) {
+    // G[lo] = first position of low digit lo in pass 1's output (= its bucket of tile 0), G[n_lo] = n; every block keeps a copy
+    __shared__ uint32_t s_G[513];
+    const uint64_t n = d_n ? min((uint64_t)*d_n, n_cap) : n_cap;
+    for (uint32_t lo = threadIdx.x; lo <= n_lo; lo += blockDim.x) {
+        const uint32_t g = lo < n_lo ? starts[(uint64_t)lo * n_tiles] : (uint32_t)n;
+        s_G[lo] = g;
+        if (blockIdx.x == 0) G[lo] = g;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && d_total) *d_total = (d_n && *d_n > n_cap) ? ~0ull : n;
+    __syncthreads();
+    // tile_lo[t] = low digit of the tile's first element | 1 << 31 when its last element belongs to another one
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const uint64_t first = (uint64_t)t * tile, last = min(first + tile, n);
+    if (first >= n) {
+        tile_lo[t] = 0;
+        return;
+    }
+    uint32_t a = 0, b = n_lo;  // largest lo with G[lo] <= first
+    while (b - a > 1) {
+        const uint32_t m = (a + b) >> 1;
+        if (s_G[m] <= first) a = m;
+        else b = m;
+    }
+    tile_lo[t] = a | (last > s_G[a + 1] ? 0x80000000u : 0u);
+}
+
+template <int DB, int TILE>
+__global__ void __launch_bounds__(RS_HIST_THREADS) radix_hist_group_kernel(const uint32_t* __restrict__ keys, uint64_t n_cap,
+                                                                           const uint64_t* __restrict__ d_n, int shift,
+                                                                           uint32_t n_tiles, uint32_t* __restrict__ hist,
+                                                                           const uint32_t* __restrict__ tile_lo,
+                                                                           const uint32_t* __restrict__ G, uint32_t n_lo, int w,
+                                                                           unsigned long long* __restrict__ key_count, uint32_t n_keys) {
+    constexpr uint32_t ND = 1u << DB;
+    constexpr int WARPS = RS_HIST_THREADS / 32;
+    constexpr int ROUNDS = (TILE + RS_HIST_THREADS - 1) / RS_HIST_THREADS;
+    const uint64_t n = d_n ? min((uint64_t)*d_n, n_cap) : n_cap;
+    __shared__ uint32_t s_hist[WARPS / 2][ND];
+    for (uint32_t i = threadIdx.x; i < (WARPS / 2) * ND; i += RS_HIST_THREADS) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * TILE;
+    const uint64_t lim = min(n, base + TILE);
+    const uint32_t tl = tile_lo[blockIdx.x];
+    uint32_t* mine = s_hist[(threadIdx.x >> 5) >> 1];
+    uint32_t key[ROUNDS];
+#pragma unroll
+    for (int k = 0; k < ROUNDS; ++k) {
+        const uint64_t i = base + (uint64_t)k * RS_HIST_THREADS + threadIdx.x;
+        key[k] = i < lim ? __ldcs(keys + i) : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < ROUNDS; ++k) {
+        const uint64_t i = base + (uint64_t)k * RS_HIST_THREADS + threadIdx.x;
+        if (i < lim) {
+            const uint32_t d = (key[k] >> shift) & (ND - 1);
+            atomicAdd(&mine[d], 1u);
+            if (tl >> 31) {  // a tile across a low-digit boundary: this element's own low digit, from its position
+                uint32_t a = tl & 0x7FFFFFFFu, b = n_lo;
+                while (b - a > 1) {
+                    const uint32_t m = (a + b) >> 1;
+                    if (__ldg(G + m) <= i) a = m;
+                    else b = m;
+                }
+                if ((((uint64_t)d << w) | a) < n_keys) atomicAdd(key_count + (((uint64_t)d << w) | a), 1ull);  // (keys >= n_keys: caller's bug, not counted)
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t d = threadIdx.x; d < ND; d += RS_HIST_THREADS) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int k = 0; k < WARPS / 2; ++k) t += s_hist[k][d];
+        hist[(uint64_t)d * n_tiles + blockIdx.x] = t;
+        if (t && !(tl >> 31) && (((uint64_t)d << w) | tl) < n_keys) atomicAdd(key_count + (((uint64_t)d << w) | tl), (unsigned long long)t);
+    }
+}
+
+static int rs_bits_for(uint64_t n_values) {
+    int b = 1;
+    while (b < 63 && (1ull << b) < n_values) ++b;
+    return b;
+}
+
+bool radix_group_fits(uint32_t n_keys, uint32_t max_val) {
+    const char* e = getenv("GTGPU_NO_GROUP_SORT");
+    if (e && *e == '1') return false;
+    int passes, width;
+    const int bits = rs_bits_for(n_keys);
+    radix_plan(bits, &passes, &width);
+    return passes == 2 && (bits - width) + rs_bits_for((uint64_t)max_val + 1) <= 32;
+}
+
+static uint64_t rs_group_tiles(uint64_t n) {
+    constexpr uint64_t tile = (uint64_t)RS_SHAPES[0].threads * RS_SHAPES[0].rounds;
+    return (n + tile - 1) / tile;
+}
+
+// scratch of radix_group_values for n elements and n_keys keys (includes radix_sort_temp_bytes(n))
+size_t radix_group_temp_bytes(uint64_t n, uint32_t n_keys) {
+    return radix_sort_temp_bytes(n) + (size_t)(520 + rs_group_tiles(n) + 8) * 4 + ((size_t)n_keys + 2) * 8 +
+           exclusive_scan_temp_bytes((uint64_t)n_keys + 1, 8) + 64;
+}
+
+// vals_out = the values ordered by key (stable), out_offsets[k] = number of elements with a key < k for k in [0, n_keys],
+// *d_total (optional) = the element count, ~0 when *d_n exceeded n_cap.  keys < n_keys, vals <= max_val, radix_group_fits.
+// packed_tmp: n_cap words; keys / vals are only read.  All on the ctx stream, no host synchronisation.
+int32_t radix_group_values(gtgpu_ctx* ctx, uint64_t n_cap, const uint32_t* keys, const uint32_t* vals, uint32_t* packed_tmp,
+                           uint32_t* vals_out, uint32_t n_keys, uint32_t max_val, void* d_temp, const uint64_t* d_n,
+                           uint64_t* out_offsets, uint64_t* d_total) {
+    if (n_cap == 0 || n_cap >= 0xFFFFFFFFull) return fail(GTGPU_ERR_UNSUPPORTED, "radix_group_values: element count");
+    if (!radix_group_fits(n_keys, max_val)) return fail(GTGPU_ERR_INVALID, "radix_group_values: keys and values do not pack");
+    constexpr int S = 0;  // the default shape; the histogram tile below must be the scatter's
+    constexpr int TILE = RS_SHAPES[S].threads * RS_SHAPES[S].rounds;
+    int passes, w;
+    const int bits = rs_bits_for(n_keys);
+    radix_plan(bits, &passes, &w);
+    const int hw = bits - w, tb = rs_bits_for((uint64_t)max_val + 1);
+    const uint32_t tiles = (uint32_t)rs_group_tiles(n_cap);
+    const uint64_t cap_tiles = (n_cap + rs_min_tile() - 1) / rs_min_tile();
+    uint32_t* hist = reinterpret_cast<uint32_t*>(d_temp);
+    uint32_t* starts = hist + 512ull * cap_tiles;
+    void* scan_tmp = starts + 512ull * cap_tiles;
+    char* aux = reinterpret_cast<char*>(d_temp) + ((radix_sort_temp_bytes(n_cap) + 15) & ~(size_t)15);
+    uint32_t* G = reinterpret_cast<uint32_t*>(aux);
+    uint32_t* tile_lo = G + 520;
+    unsigned long long* key_count = reinterpret_cast<unsigned long long*>(aux + (((size_t)(520 + tiles) * 4 + 15) & ~(size_t)15));
+    void* scan_tmp2 = key_count + n_keys + 2;
+    cudaStream_t st = ctx->stream;
+    GT_CUDA(cudaMemsetAsync(key_count, 0, ((size_t)n_keys + 1) * 8, st));
+    int32_t status = GTGPU_OK;
+    // pass 1: pairs by the low digit -> packed words
+    cudaError_t e = w == 8 ? launch_radix_pass<8, S, RS_PACK>(ctx, keys, vals, n_cap, d_n, 0, tiles, hist, starts, scan_tmp, packed_tmp, nullptr, (uint32_t)tb, false, &status)
+                           : launch_radix_pass<9, S, RS_PACK>(ctx, keys, vals, n_cap, d_n, 0, tiles, hist, starts, scan_tmp, packed_tmp, nullptr, (uint32_t)tb, false, &status);
+    GT_TRY(status);
+    GT_CUDA(e);
+    rs_group_prepare_kernel<<<(tiles + 255) / 256, 256, 0, st>>>(starts, tiles, 1u << w, n_cap, d_n, TILE, G, tile_lo, d_total);
+    // pass 2: packed words by the upper digit -> values; its histogram also counts the keys
+    const uint32_t mask = tb >= 32 ? 0xFFFFFFFFu : (1u << tb) - 1;
+    if (hw <= 8) {
+        radix_hist_group_kernel<8, TILE><<<tiles, RS_HIST_THREADS, 0, st>>>(packed_tmp, n_cap, d_n, tb, tiles, hist, tile_lo, G, 1u << w, w, key_count, n_keys);
+        e = launch_radix_pass<8, S, RS_KEYS>(ctx, packed_tmp, nullptr, n_cap, d_n, tb, tiles, hist, starts, scan_tmp, nullptr, vals_out, mask, true, &status);
+    } else {
+        radix_hist_group_kernel<9, TILE><<<tiles, RS_HIST_THREADS, 0, st>>>(packed_tmp, n_cap, d_n, tb, tiles, hist, tile_lo, G, 1u << w, w, key_count, n_keys);
+        e = launch_radix_pass<9, S, RS_KEYS>(ctx, packed_tmp, nullptr, n_cap, d_n, tb, tiles, hist, starts, scan_tmp, nullptr, vals_out, mask, true, &status);
+    }
+    ctx->launches += 2;
+    GT_TRY(status);
+    GT_CUDA(e);
+    GT_TRY(exclusive_scan<unsigned long long>(ctx, key_count, reinterpret_cast<unsigned long long*>(out_offsets), (uint64_t)n_keys + 1, scan_tmp2));
     return GTGPU_OK;
 }
 

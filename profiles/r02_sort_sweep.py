@@ -46,7 +46,7 @@ def main():
                                               d_bco.data_ptr(), d_ids.data_ptr(), cap, d_total.data_ptr())
     ref_ids = ref_bco = None
     for shape in shapes:
-        for pf in (1, 0):
+        for pf in (1,):
             os.environ["GTGPU_RS_SHAPE"] = str(shape)
             os.environ["GTGPU_RS_PREFETCH"] = str(pf)
             d_ids.zero_()

@@ -161,6 +161,31 @@ def test_c5_fragments_unsorted(ctx):
     assert len(ids) == int(np.maximum(counts, 1).sum(dtype=np.uint64))  # per-fragment [unk]
 
 
+def test_c5_packed_group_by_equals_pair_sort(ctx, monkeypatch):
+    """The two-pass group-by over packed words (sort.cu radix_group_values: barcode offsets from counts, tiles inside one
+    low digit and tiles across a boundary) against the plain (barcode, token) pair sort + search, 17-bit barcodes with
+    9-bit digits, and both against the oracle on the barcodes of a slice."""
+    from gtars_b200 import ffi, synth
+    from oracle import oracle as orc
+    u, ix, arrays = _universe(ctx, ffi.KIND_BITS)
+    n, n_bc = 6_000_000, 100_000
+    q = synth.make_query_files(u, 1, n, seed=synth.SEED_FRAGMENTS + 1, sort_files=False)
+    qc, qs, qe = (_np(q[k]) for k in ("chr", "start", "end"))
+    rng = np.random.default_rng(5)
+    bc = (rng.integers(0, n_bc, n) ** 2 // n_bc).astype(np.uint32)
+    bc[bc == n_bc - 1] = n_bc - 2  # the last barcode stays empty
+    off, ids = ix.tokenize_fragments(qc, qs, qe, bc, n_bc, u["unk_id"])
+    monkeypatch.setenv("GTGPU_NO_GROUP_SORT", "1")
+    off2, ids2 = ix.tokenize_fragments(qc, qs, qe, bc, n_bc, u["unk_id"])
+    monkeypatch.delenv("GTGPU_NO_GROUP_SORT")
+    assert np.array_equal(off, off2) and np.array_equal(ids, ids2)
+    assert off[n_bc - 1] == off[n_bc] == len(ids)
+    m = 400_000
+    oo, oi = orc.Index(orc.BITS, *arrays).tokenize_fragments(qc[:m], qs[:m], qe[:m], bc[:m], n_bc, u["unk_id"])
+    go, gi = ix.tokenize_fragments(qc[:m], qs[:m], qe[:m], bc[:m], n_bc, u["unk_id"])
+    assert np.array_equal(go, oo) and np.array_equal(gi, oi)
+
+
 def test_scoring_matrix_properties_20m_fragments(ctx):
     """gtars-scoring at scale (4 files x 5 M unsorted fragments vs the 1 M-peak universe): the count matrix must agree
     with the independent counting kernel on the same lookups (ATAC: shifted start + reversed end interval; ChIP: the
