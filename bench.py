@@ -556,7 +556,7 @@ def sub_c5(args, torch, dev, ctx, stream, D, rank, world, peak, universe, index)
             "value": n_total / (ms * 1e-3), "unit": "fragments/s", "algorithmic_bytes_per_gpu": algo,
             "frac": algo / (ms * 1e-3) / 1e9 / peak,
             "frac_note": "per GPU: (16 B x fragments + 4 B x tokens + barcode offsets + universe) / time of the whole device-resident "
-                         "pipeline (find + 3 radix passes + scan + scatter) / measured HBM peak",
+                         "pipeline (find with barcode tags, two radix passes: pairs -> packed words -> tokens, scans) / measured HBM peak",
             "kernels_per_step": launches, "data_gen_s": gen_s,
             "e2e": {"fragments_per_gpu": m, "seconds": e2e_s, "value": m * world / e2e_s, "unit": "fragments/s",
                     "note": "gtgpu_tokenize_fragments, pinned host arrays in (16 B/fragment), pinned result out; bounded slice of the block",
