@@ -323,6 +323,23 @@ __device__ __forceinline__ void rs_stage_tile(uint32_t* s, const uint32_t* g, ui
 // 20 instead of 32 bytes of scatter traffic per element, and the second pass moves one array through shared memory, not two.
 enum { RS_PAIRS = 0, RS_PACK = 1, RS_KEYS = 2 };
 
+// peers &= the lanes whose digit agrees with mine in bit `bit`, in PTX — the plain C++
+// (`peers &= (d & bit) ? bal : ~bal`) compiled to seven instructions per bit (shift, mask, compare, vote, test, select, combine;
+// this form: one R2P for seven bits, then vote, select, combine),
+// and the ten votes of a round with their arithmetic were 45 % of the kernel's instructions
+__device__ __forceinline__ void rs_match_bit(uint32_t& peers, uint32_t d, uint32_t bit) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t, bal;\n"
+        "and.b32 t, %1, %2;\n"
+        "setp.ne.u32 p, t, 0;\n"
+        "vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
+        "selp.b32 t, 0, 0xffffffff, p;\n"
+        "lop3.b32 %0, %0, bal, t, 0x60;\n"  // peers & (bal ^ t): bal where my bit is set, ~bal where it is not
+        "}\n" : "+r"(peers) : "r"(d), "r"(bit));
+}
+
 template <int DB, int THREADS, int ROUNDS, int MINB, int MODE>
 __global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
                                                                       const uint32_t* __restrict__ vals_in, uint64_t n_cap,
@@ -377,10 +394,7 @@ __global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(const uint
 #if GT_RS_BALLOT
         uint32_t peers = __ballot_sync(0xFFFFFFFFu, ok);
 #pragma unroll
-        for (int b = 0; b < DB; ++b) {
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, (d >> b) & 1u);
-            peers &= ((d >> b) & 1u) ? bal : ~bal;
-        }
+        for (int b = 0; b < DB; ++b) rs_match_bit(peers, d, 1u << b);
         if (!ok) peers = 1u << lane;
 #else
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
