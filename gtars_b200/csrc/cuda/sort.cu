@@ -340,36 +340,28 @@ __device__ __forceinline__ void rs_match_bit(uint32_t& peers, uint32_t d, uint32
         "}\n" : "+r"(peers) : "r"(d), "r"(bit));
 }
 
-template <int DB, int THREADS, int ROUNDS, int MINB, int MODE>
-__global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
-                                                                      const uint32_t* __restrict__ vals_in, uint64_t n_cap,
-                                                                      const uint64_t* __restrict__ d_n, int shift,
-                                                                      uint32_t n_tiles, const uint32_t* __restrict__ bucket_start,
-                                                                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                                                                      uint32_t aux) {
+// FULL: every element of the tile exists (all tiles but the last): no bounds tests, no predicates on the element accesses
+template <int DB, int THREADS, int ROUNDS, int MODE, bool FULL>
+__device__ __forceinline__ void rs_scatter_tile(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                uint64_t tile0, uint32_t tile_n, int shift, uint32_t n_tiles,
+                                                const uint32_t* __restrict__ bucket_start, uint32_t* __restrict__ keys_out,
+                                                uint32_t* __restrict__ vals_out, uint32_t aux, uint32_t* s_mem, uint32_t* s_wsum) {
     constexpr uint32_t ND = 1u << DB;
     constexpr int WARPS = THREADS / 32, TILE = THREADS * ROUNDS, WARP_TILE = 32 * ROUNDS;
     constexpr int DPT = (int)ND > THREADS ? (int)ND / THREADS : 1;  // digits per thread in phase 2
-    static_assert((int)ND % THREADS == 0 || (int)ND < THREADS, "digits must divide over the threads");
-    static_assert(ROUNDS % 4 == 0, "ranks are packed in pairs, the tile is staged in 16-byte pieces");
-    const uint64_t n = d_n ? min((uint64_t)*d_n, n_cap) : n_cap;
-    extern __shared__ __align__(16) uint32_t s_mem[];
     uint32_t* s_key = s_mem;                                       // [TILE] the values as they arrive, then the keys sorted by digit
     uint32_t* s_val = s_mem + TILE;                                // [TILE] the keys as they arrive, then the values sorted by digit
     uint32_t* s_dbase = s_mem + 2 * TILE;                          // [ND] first slot of each digit in the sorted tile
     uint32_t* s_gbase = s_dbase + ND;                              // [ND] global position of the digit's first element minus s_dbase
     uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_gbase + ND);   // [WARPS][ND] per-warp digit counts (<= 32 x ROUNDS), then
                                                                    // the digit's elements in earlier warps (<= TILE < 65 536)
-    __shared__ uint32_t s_wsum[WARPS];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t tile0 = (uint64_t)blockIdx.x * TILE;
-    if (tile0 >= n) return;
-    const uint32_t tile_n = (uint32_t)min((uint64_t)TILE, n - tile0);
+#define RS_OK(r) (FULL || wbase + 32 * (r) < tile_n)
     uint32_t* in_key = s_val;  // arrival buffers
     uint32_t* in_val = s_key;
-    rs_stage_tile<THREADS, TILE>(in_key, keys_in + tile0, tile_n, tid);
+    rs_stage_tile<THREADS, TILE>(in_key, keys_in + tile0, FULL ? TILE : tile_n, tid);
     rs_cp_async_commit();
-    if (MODE != RS_KEYS) rs_stage_tile<THREADS, TILE>(in_val, vals_in + tile0, tile_n, tid);
+    if (MODE != RS_KEYS) rs_stage_tile<THREADS, TILE>(in_val, vals_in + tile0, FULL ? TILE : tile_n, tid);
     rs_cp_async_commit();  // (an empty group when there are no values)
     // this tile's row of the bucket table (a gather: the table is digit-major), requested now, used after phase 2
     const bool has_digits = tid * DPT < ND;
@@ -389,10 +381,10 @@ __global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(const uint
     // round's counter update left every warp waiting on its result: a third of the kernel's stall samples) ...
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
-        const bool ok = wbase + 32 * r < tile_n;
+        const bool ok = RS_OK(r);
         const uint32_t d = ok ? (in_key[wbase + 32 * r] >> shift) & (ND - 1) : ND + lane;  // invalid lanes never match anyone
 #if GT_RS_BALLOT
-        uint32_t peers = __ballot_sync(0xFFFFFFFFu, ok);
+        uint32_t peers = FULL ? 0xFFFFFFFFu : __ballot_sync(0xFFFFFFFFu, ok);
 #pragma unroll
         for (int b = 0; b < DB; ++b) rs_match_bit(peers, d, 1u << b);
         if (!ok) peers = 1u << lane;
@@ -406,7 +398,7 @@ __global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(const uint
     // ... then the per-warp digit counters advance round by round (stable)
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
-        const bool ok = wbase + 32 * r < tile_n;
+        const bool ok = RS_OK(r);
         const uint32_t mine = (r & 1) ? rank2[r >> 1] >> 16 : rank2[r >> 1] & 0xFFFFu;
         const uint32_t d = ok ? (in_key[wbase + 32 * r] >> shift) & (ND - 1) : 0, before = mine & 0xFFu, group = mine >> 8;
         uint32_t prev = 0;
@@ -461,12 +453,12 @@ __global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(const uint
     uint32_t val[MODE == RS_KEYS ? 1 : ROUNDS];
     if (MODE != RS_KEYS) {
 #pragma unroll
-        for (int r = 0; r < ROUNDS; ++r) val[r] = wbase + 32 * r < tile_n ? in_val[wbase + 32 * r] : 0;
+        for (int r = 0; r < ROUNDS; ++r) val[r] = RS_OK(r) ? in_val[wbase + 32 * r] : 0;
         __syncthreads();
     }
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
-        if (wbase + 32 * r < tile_n) {
+        if (RS_OK(r)) {
             const uint32_t k = in_key[wbase + 32 * r];
             const uint32_t d = (k >> shift) & (ND - 1);
             const uint32_t p = s_dbase[d] + my_cnt[d] + ((r & 1) ? rank2[r >> 1] >> 16 : rank2[r >> 1] & 0xFFFFu);
@@ -479,11 +471,12 @@ __global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(const uint
     if (MODE != RS_KEYS) {
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r)
-            if (wbase + 32 * r < tile_n) s_val[(r & 1) ? rank2[r >> 1] >> 16 : rank2[r >> 1] & 0xFFFFu] = val[r];
+            if (RS_OK(r)) s_val[(r & 1) ? rank2[r >> 1] >> 16 : rank2[r >> 1] & 0xFFFFu] = val[r];
         __syncthreads();
     }
     // ---- 4. write out: consecutive threads = consecutive slots = (inside a digit) consecutive global addresses ------------------
-    for (uint32_t p = tid; p < tile_n; p += THREADS) {
+#pragma unroll
+    for (uint32_t p = tid; p < (FULL ? (uint32_t)TILE : tile_n); p += THREADS) {
         const uint32_t k = s_key[p];
         const uint32_t dst = s_gbase[(k >> shift) & (ND - 1)] + p;
         if (MODE == RS_PAIRS) {
@@ -495,6 +488,29 @@ __global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(const uint
             vals_out[dst] = k & aux;
         }
     }
+#undef RS_OK
+}
+
+template <int DB, int THREADS, int ROUNDS, int MINB, int MODE>
+__global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
+                                                                      const uint32_t* __restrict__ vals_in, uint64_t n_cap,
+                                                                      const uint64_t* __restrict__ d_n, int shift,
+                                                                      uint32_t n_tiles, const uint32_t* __restrict__ bucket_start,
+                                                                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                                      uint32_t aux) {
+    constexpr int TILE = THREADS * ROUNDS;
+    static_assert((1 << DB) % THREADS == 0 || (1 << DB) < THREADS, "digits must divide over the threads");
+    static_assert(ROUNDS % 4 == 0, "ranks are packed in pairs, the tile is staged in 16-byte pieces");
+    const uint64_t n = d_n ? min((uint64_t)*d_n, n_cap) : n_cap;
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    __shared__ uint32_t s_wsum[THREADS / 32];
+    const uint64_t tile0 = (uint64_t)blockIdx.x * TILE;
+    if (tile0 >= n) return;
+    const uint32_t tile_n = (uint32_t)min((uint64_t)TILE, n - tile0);
+    if (tile_n == TILE)
+        rs_scatter_tile<DB, THREADS, ROUNDS, MODE, true>(keys_in, vals_in, tile0, tile_n, shift, n_tiles, bucket_start, keys_out, vals_out, aux, s_mem, s_wsum);
+    else
+        rs_scatter_tile<DB, THREADS, ROUNDS, MODE, false>(keys_in, vals_in, tile0, tile_n, shift, n_tiles, bucket_start, keys_out, vals_out, aux, s_mem, s_wsum);
 }
 
 static size_t radix_scatter_smem(int width, const RsShape& sh) {
