@@ -187,8 +187,11 @@ def test_device_code_is_sm100a_and_keeps_its_resource_budgets():
         res[m.group(1)] = tuple(int(x) for x in m.groups()[1:])
     for name in ("fused_find_kernel", "count_kernel_x4", "count_stage_kernel", "count_runs_kernel",
                  "count_unstage_kernel", "igd_count_kernel", "radix_scatter_kernel", "scan_down_kernel", "score_hist_kernel",
-                 "ingest_parse_lines_kernel", "untranspose_blocks_kernel"):
+                 "ingest_parse_lines_kernel", "untranspose_blocks_kernel", "radix_hist_group_kernel", "gunzip_kernel"):
         assert any(name in k for k in res), f"{name} missing from the device code"
+    # radix scatter, default shape (512 threads x 16 rounds, two blocks per SM = 64 registers), all three modes: no stack
+    scat = [v for k, v in res.items() if "radix_scatter_kernelILi" in k and "ELi512ELi16ELi2E" in k]
+    assert len(scat) >= 4 and all(reg <= 64 and stack == 0 for reg, stack, _ in scat), scat
     # lean fused find kernel: template flags <ROWS=4, DESC, FILTER, OFFS, LEAN=1>; no stack; 40 registers = 6 CTAs per SM
     # (tokenize), 48 registers = 5 CTAs per SM when it also writes per-query offsets (find, fragments)
     # (flags after LEAN: UNK1, TAG — the tagged variant of fragment tokenization has the 48-register budget too)
