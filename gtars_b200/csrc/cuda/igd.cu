@@ -200,8 +200,14 @@ struct IgdView {
 #ifndef GT_IGD_MINBLOCKS
 #define GT_IGD_MINBLOCKS 5
 #endif
-template <bool BINARY>
-__global__ void __launch_bounds__(256, GT_IGD_MINBLOCKS) igd_count_kernel(IgdView v, uint64_t n, const uint32_t* __restrict__ set_of,
+#ifndef GT_IGD_MINBLOCKS_M1
+#define GT_IGD_MINBLOCKS_M1 6
+#endif
+// M1: min_overlap == 1 (LOLA's and every reference caller's setting).  Every candidate already starts before the query's end,
+// and a stored record has start < end, so it overlaps by at least one base iff it ends after the query's start: the start
+// array is not read at all — 12 instead of 16 bytes per candidate of a kernel that pulls 72 GB of records from DRAM on C4.
+template <bool BINARY, bool M1>
+__global__ void __launch_bounds__(256, M1 ? GT_IGD_MINBLOCKS_M1 : GT_IGD_MINBLOCKS) igd_count_kernel(IgdView v, uint64_t n, const uint32_t* __restrict__ set_of,
                                                          const uint32_t* __restrict__ chr, const uint32_t* __restrict__ qstart,
                                                          const uint32_t* __restrict__ qend, int32_t m,
                                                          unsigned long long* __restrict__ out) {
@@ -262,14 +268,14 @@ __global__ void __launch_bounds__(256, GT_IGD_MINBLOCKS) igd_count_kernel(IgdVie
             for (int k = 0; k < 4; ++k) {
                 const uint32_t i = base + 32 * k + lane;
                 const bool ok = i < o + ub;
-                rs[k] = ok ? __ldg(v.start + i) : 0;
-                re[k] = ok ? __ldg(v.end + i) : 0;  // an absent record [0, 0) never reaches m >= 1 bp of overlap
+                rs[k] = (!M1 && ok) ? __ldg(v.start + i) : 0;
+                re[k] = ok ? __ldg(v.end + i) : 0;  // an absent record [0, 0) never reaches m >= 1 bp of overlap (s >= 0)
                 fl[k] = ok ? __ldg(v.file + i) : 0;
                 ps[k] = (BINARY && ok) ? __ldg(v.psame + i) : 0;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (min(re[k], e) - max(rs[k], s) < m) continue;
+                if (M1 ? re[k] <= s : min(re[k], e) - max(rs[k], s) < m) continue;
                 if (BINARY && (int64_t)ps[k] - s >= m) continue;  // an earlier record of this file already hit
                 atomicAdd(row + fl[k], 1ull);
             }
@@ -534,16 +540,15 @@ int32_t igd_count_dev_locked(gtgpu_igd* g, bool binary, uint64_t n, const uint32
     // ran a second, partial wave (17.3 vs 16.6 ms on C4); fewer resident warps are slower (4 per SM 17.8, 3: 21.3, 2: 28.9 ms),
     // and a sixth block per SM only fits with spills (21.9 ms)
     int ctas_per_sm = 0;
-    if (binary) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, igd_count_kernel<true>, 256, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, igd_count_kernel<false>, 256, 0);
+    const bool m1 = m == 1 && !(getenv("GTGPU_IGD_NO_M1") && *getenv("GTGPU_IGD_NO_M1") == '1');
+    auto kern = binary ? (m1 ? igd_count_kernel<true, true> : igd_count_kernel<true, false>)
+                       : (m1 ? igd_count_kernel<false, true> : igd_count_kernel<false, false>);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 256, 0);
     if (ctas_per_sm < 1) ctas_per_sm = 4;
     if (const char* env = getenv("GTGPU_IGD_CTAS")) ctas_per_sm = std::max(1, atoi(env));  // tuning knob: blocks per SM of the grid
     const int grid = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * ctas_per_sm);
     ctx->time_begin();
-    if (binary)
-        igd_count_kernel<true><<<grid, 256, 0, ctx->stream>>>(v, n, d_set_of, d_chr, d_start, d_end, m, (unsigned long long*)d_out);
-    else
-        igd_count_kernel<false><<<grid, 256, 0, ctx->stream>>>(v, n, d_set_of, d_chr, d_start, d_end, m, (unsigned long long*)d_out);
+    kern<<<grid, 256, 0, ctx->stream>>>(v, n, d_set_of, d_chr, d_start, d_end, m, (unsigned long long*)d_out);
     ctx->time_end();
     ctx->launches++;
     GT_CUDA(cudaGetLastError());
