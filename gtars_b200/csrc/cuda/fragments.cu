@@ -8,6 +8,8 @@
 //   3. stable LSD radix sort of (barcode, token) pairs by barcode (sort.cu, hand-written; 2 passes of 9 bits for 100 k
 //      barcodes): the sorted tokens are the output, barcode-major, input order kept inside a barcode
 //   4. barcode offsets by binary search over the sorted tags
+//   3+4 for barcodes of 10-18 bits whose upper digit fits next to a token in 32 bits (the usual case): radix_group_values —
+//      pass 1 writes packed (upper digit | token) words, pass 2 sorts those and writes bare tokens, offsets from counts
 // Nothing is gathered at random: every pass streams (the first version sorted fragment indices and then chased offsets
 // and ids per fragment — 190 ms per 1e9 fragments, against ~45 ms for this one).
 // Output is barcode-major: out_barcode_offsets[n_barcodes + 1] + ids.
