@@ -20,7 +20,7 @@ def main():
 
     n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 250_000_000
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-    shapes = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else list(range(7))
+    shapes = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else list(range(3))
     n_bc = 100_000
     dev = torch.device("cuda", 0)
     stream = torch.cuda.Stream(device=dev)
@@ -45,7 +45,7 @@ def main():
     fn = lambda: index.tokenize_fragments_dev(n, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n_bc, unk,
                                               d_bco.data_ptr(), d_ids.data_ptr(), cap, d_total.data_ptr())
     ref_ids = ref_bco = None
-    for shape in shapes:
+    for shape in [x for x in shapes if 0 <= x < 3]:
         for pf in (1,):
             os.environ["GTGPU_RS_SHAPE"] = str(shape)
             os.environ["GTGPU_RS_PREFETCH"] = str(pf)
